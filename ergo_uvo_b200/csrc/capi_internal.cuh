@@ -1,0 +1,24 @@
+// capi_internal.cuh -- definition of the opaque uvo_ctx and of the grow-only scratch the stage-level (host buffer)
+// entry points use.  Whole-frame pipelines own their buffers separately (frame.cu).
+#pragma once
+#include "common.cuh"
+#include "frontend.cuh"
+#include "imgprep.cuh"
+
+namespace uvo {
+
+struct StageScratch {
+  DevBuf<uint8_t> src3, gray, lut;
+  DevBuf<unsigned int> hist;
+  DevBuf<int32_t> integral;
+  DevBuf<uint8_t> bytes_a, bytes_b, bytes_c, bytes_d;  // generic staging for the other stage calls
+};
+
+}  // namespace uvo
+
+struct uvo_ctx {
+  uvo::Ctx c;
+  uvo::StageScratch scratch;
+  uvo::FrontEnd fe;  // front end used by the stage-level uvo_detect_features
+  uvo::PinnedBuf<int> pinned_counts;
+};

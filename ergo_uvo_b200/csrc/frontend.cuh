@@ -1,0 +1,99 @@
+// frontend.cuh -- device-resident per-image front end: K1 gray+undistort -> K2 CLAHE -> K3 integral -> K4-K7 SURF
+// for one or two images of identical size (the stereo pair is batched through every kernel: blockIdx.y = image).
+#pragma once
+#include "common.cuh"
+#include "imgprep.cuh"
+#include "surf.cuh"
+
+namespace uvo {
+
+struct FrontEnd {
+  int w = 0, h = 0, n_img = 0, capacity = 0;
+  size_t gpitch = 0;
+  SurfGeom geom{};
+  bool geom_valid = false;
+  double geom_thr = -1;
+  int geom_oct = 0, geom_lay = 0;
+  DevBuf<uint8_t> gray[2];
+  DevBuf<int32_t> sum[2];
+  DevBuf<uvo_keypoint> raw[2], kps[2];
+  DevBuf<float> desc[2];
+  DevBuf<int> counters;  // 4 ints per image
+  DevBuf<unsigned int> hist;
+  DevBuf<uint8_t> lut;
+  DevBuf<uvo_keypoint> tmp_kps;
+  DevBuf<float> tmp_desc;
+
+  void init(int w_, int h_, int n_img_, int capacity_) {
+    UVO_REQUIRE(w_ > 0 && h_ > 0 && (n_img_ == 1 || n_img_ == 2) && capacity_ > 0, "FrontEnd::init: bad geometry");
+    if (w_ != w || h_ != h) geom_valid = false;
+    w = w_;
+    h = h_;
+    n_img = std::max(n_img, n_img_);
+    capacity = std::max(capacity, capacity_);
+    gpitch = ((size_t)w + 15) & ~(size_t)15;
+    for (int i = 0; i < n_img; i++) {
+      gray[i].ensure(gpitch * h);
+      sum[i].ensure((size_t)(w + 1) * (h + 1));
+      raw[i].ensure(capacity);
+      kps[i].ensure(capacity);
+      desc[i].ensure((size_t)capacity * 64);
+    }
+    counters.ensure(8);
+    hist.ensure(2 * 64 * 256);
+    lut.ensure(2 * 64 * 256);
+  }
+
+  SurfBatch batch(int first, int count) const {
+    SurfBatch b{};
+    b.n_img = count;
+    for (int i = 0; i < count; i++) {
+      SurfImage& im = b.im[i];
+      im.img = gray[first + i].get();
+      im.pitch = gpitch;
+      im.sum = sum[first + i].get();
+      im.raw = raw[first + i].get();
+      im.kps = kps[first + i].get();
+      im.desc = desc[first + i].get();
+      im.counters = counters.get() + 4 * (first + i);
+    }
+    return b;
+  }
+
+  // get_image for image `idx` from a device-resident 3-channel source
+  void prep(Ctx& c, int idx, const uint8_t* d_src3, size_t spitch, const uvo_camera& cam, int clahe, int clip_limit) {
+    launch_gray_undistort(c, d_src3, spitch, w, h, make_undistort_params(cam), gray[idx].get(), gpitch);
+    if (clahe) {
+      ClaheGeom g = make_clahe_geom(w, h, (double)clip_limit, 8, 8);
+      launch_clahe(c, gray[idx].get(), gpitch, w, h, g, hist.get() + idx * 64 * 256, lut.get() + idx * 64 * 256,
+                   gray[idx].get(), gpitch);
+    }
+  }
+
+  // SURF::detectAndCompute on images [first, first+count)
+  void surf(Ctx& c, int first, int count, const uvo_params& p) {
+    UVO_REQUIRE(!p.surf_extended, "SURF extended (128-d) descriptors are not implemented");
+    if (!geom_valid || geom_thr != (double)p.surf_min_hessian || geom_oct != p.surf_octaves ||
+        geom_lay != p.surf_octave_layers) {
+      geom = make_surf_geom(w, h, (double)p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers);
+      geom_valid = true;
+      geom_thr = (double)p.surf_min_hessian;
+      geom_oct = p.surf_octaves;
+      geom_lay = p.surf_octave_layers;
+    }
+    for (int i = 0; i < count; i++) launch_integral(c, gray[first + i].get(), gpitch, w, h, sum[first + i].get());
+    SurfBatch b = batch(first, count);
+    launch_surf_detect(c, geom, b, capacity);
+    launch_surf_sort(c, b, capacity);
+    launch_surf_describe(c, geom, b, capacity, p.surf_upright);
+    // describe can delete keypoints only in oriented mode or when the image is smaller than the largest
+    // gradient wavelet (2*round(2*264*1.2/9) = 142)
+    if (!p.surf_upright || std::min(w, h) + 1 < 142) {
+      tmp_kps.ensure((size_t)2 * capacity);
+      tmp_desc.ensure((size_t)2 * capacity * 64);
+      launch_surf_compact(c, b, capacity, tmp_kps.get(), tmp_desc.get());
+    }
+  }
+};
+
+}  // namespace uvo

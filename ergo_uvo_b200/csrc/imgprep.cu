@@ -1,0 +1,328 @@
+// imgprep.cu -- K1 gray+undistort, K2 CLAHE, K3 integral image.
+// Replaces get_image (reference VO_utility.cpp:337-379) and the integral() inside SURF::detectAndCompute
+// (VO_utility.cpp:118).  All three are integer / exactly-specified f32 pipelines: results are bit-identical to the
+// OpenCV CPU path (tests/test_gpu_imgprep.py compares against the oracle and committed cv2 fixtures).
+#include "imgprep.cuh"
+
+namespace uvo {
+
+// ------------------------------------------------------------------------------------------------ K1
+// One thread produces 4 consecutive output pixels.  The rectification map is evaluated per pixel in fp64 exactly
+// as cv::initUndistortRectifyMap does (closed form), quantised to 1/32 px, and the four bilinear taps
+// are converted to gray on the fly with cvtColor's 15-bit weights (C.1) -- the gray image is never materialised.
+// Algorithmic HBM bytes: read 3P (source, each byte touched ~once through L1/L2) + write P.
+__device__ __forceinline__ int gray_tap(const uint8_t* __restrict__ src, size_t pitch, int w, int h, int x, int y) {
+  if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return 0;  // BORDER_CONSTANT(0)
+  const uint8_t* p = src + (size_t)y * pitch + 3 * x;
+  return (9798 * (int)p[0] + 19235 * (int)p[1] + 3735 * (int)p[2] + 16384) >> 15;
+}
+
+__global__ void __launch_bounds__(256) k_gray_undistort(const uint8_t* __restrict__ src, size_t spitch, int w, int h,
+                                                        UndistortParams P, uint8_t* __restrict__ dst, size_t dpitch) {
+  const int j0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j0 >= w || i >= h) return;
+  uint8_t out[4];
+  const double bx = i * P.ir[1] + P.ir[2], by = i * P.ir[4] + P.ir[5], bw = i * P.ir[7] + P.ir[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int j = j0 + k;
+    double _x = j * P.ir[0] + bx, _y = j * P.ir[3] + by, _w = j * P.ir[6] + bw;
+    double iw = 1. / _w, x = _x * iw, y = _y * iw;
+    double x2 = x * x, y2 = y * y;
+    double r2 = x2 + y2, _2xy = 2 * x * y;
+    double kr = 1 + ((0 * r2 + P.k2) * r2 + P.k1) * r2;
+    double xd = x * kr + P.p1 * _2xy + P.p2 * (r2 + 2 * x2);
+    double yd = y * kr + P.p1 * (r2 + 2 * y2) + P.p2 * _2xy;
+    double u = P.fx * xd + P.u0, v = P.fy * yd + P.v0;
+    int iu = __double2int_rn(u * 32), iv = __double2int_rn(v * 32);
+    int sx = iu >> 5, sy = iv >> 5;
+    sx = min(max(sx, -32768), 32767);
+    sy = min(max(sy, -32768), 32767);
+    int fx = iu & 31, fy = iv & 31;
+    int acc = gray_tap(src, spitch, w, h, sx, sy) * ((32 - fy) * (32 - fx) * 32) +
+              gray_tap(src, spitch, w, h, sx + 1, sy) * ((32 - fy) * fx * 32) +
+              gray_tap(src, spitch, w, h, sx, sy + 1) * (fy * (32 - fx) * 32) +
+              gray_tap(src, spitch, w, h, sx + 1, sy + 1) * (fy * fx * 32);
+    int r = (acc + 16384) >> 15;
+    out[k] = (uint8_t)min(max(r, 0), 255);
+  }
+  uint8_t* d = dst + (size_t)i * dpitch + j0;
+  if (j0 + 3 < w && (dpitch & 3) == 0) {
+    *reinterpret_cast<uchar4*>(d) = make_uchar4(out[0], out[1], out[2], out[3]);
+  } else {
+    for (int k = 0; k < 4 && j0 + k < w; k++) d[k] = out[k];
+  }
+}
+
+// plain gray image -> undistorted gray (used by the stage-level API when the caller already holds a gray image)
+void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, int h, const UndistortParams& P,
+                           uint8_t* d_dst, size_t dpitch) {
+  dim3 block(32, 8);
+  dim3 grid(div_up(div_up(w, 4), 32), div_up(h, 8));
+  k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3, spitch, w, h, P, d_dst, dpitch);
+  UVO_LAUNCH_CHECK(c);
+}
+
+UndistortParams make_undistort_params(const uvo_camera& cam) {
+  UndistortParams P;
+  // (newK * I).inv(DECOMP_LU): cv::invert's closed form for 3x3 (cofactors times 1/det)
+  const double m[9] = {cam.nfx, 0, cam.ncx, 0, cam.nfy, cam.ncy, 0, 0, 1};
+  double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+             m[2] * (m[3] * m[7] - m[4] * m[6]);
+  d = 1. / d;
+  P.ir[0] = (m[4] * m[8] - m[5] * m[7]) * d;
+  P.ir[1] = (m[2] * m[7] - m[1] * m[8]) * d;
+  P.ir[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+  P.ir[3] = (m[5] * m[6] - m[3] * m[8]) * d;
+  P.ir[4] = (m[0] * m[8] - m[2] * m[6]) * d;
+  P.ir[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+  P.ir[6] = (m[3] * m[7] - m[4] * m[6]) * d;
+  P.ir[7] = (m[1] * m[6] - m[0] * m[7]) * d;
+  P.ir[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+  P.fx = cam.fx;
+  P.fy = cam.fy;
+  P.u0 = cam.cx;
+  P.v0 = cam.cy;
+  P.k1 = cam.k1;
+  P.k2 = cam.k2;
+  P.p1 = cam.p1;
+  P.p2 = cam.p2;
+  return P;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 CLAHE
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+// grid: (tiles_x*tiles_y, slices).  Each block histograms a horizontal slice of one tile in shared memory and
+// merges it into the tile's global histogram with 256 atomics.
+__global__ void __launch_bounds__(256) k_clahe_hist(const uint8_t* __restrict__ img, size_t pitch, int w, int h,
+                                                    ClaheGeom g, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int tile = blockIdx.x, txi = tile % g.tiles_x, tyi = tile / g.tiles_x;
+  const int rows_per = div_up_dev(g.th, gridDim.y);
+  const int y0 = tyi * g.th + blockIdx.y * rows_per, y1 = min(y0 + rows_per, (tyi + 1) * g.th);
+  const int x0 = txi * g.tw;
+  const int npx = (y1 - y0) * g.tw;
+  for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+    int y = y0 + t / g.tw, x = x0 + t % g.tw;
+    if (y >= h) y = reflect101(y, h);
+    if (x >= w) x = reflect101(x, w);
+    atomicAdd(&sh[img[(size_t)y * pitch + x]], 1u);
+  }
+  __syncthreads();
+  unsigned int v = sh[threadIdx.x];
+  if (v) atomicAdd(&hist[tile * 256 + threadIdx.x], v);
+}
+
+// one block (256 threads) per tile: clip, redistribute, cumulative sum, LUT (OpenCV clahe.cpp CLAHE_CalcLut_Body)
+__global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restrict__ hist, ClaheGeom g,
+                                                   uint8_t* __restrict__ lut) {
+  __shared__ int warp_sums[8];
+  __shared__ int s_total;
+  const int tile = blockIdx.x, b = threadIdx.x, lane = b & 31, wid = b >> 5;
+  int v = (int)hist[tile * 256 + b];
+  if (g.clip > 0) {
+    int excess = v > g.clip ? v - g.clip : 0;
+    if (v > g.clip) v = g.clip;
+    int e = excess;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == 0) warp_sums[wid] = e;
+    __syncthreads();
+    if (b == 0) {
+      int t = 0;
+      for (int k = 0; k < 8; k++) t += warp_sums[k];
+      s_total = t;
+    }
+    __syncthreads();
+    const int clipped = s_total;
+    const int batch = clipped / 256, residual = clipped - batch * 256;
+    v += batch;
+    if (residual != 0) {
+      const int step = max(256 / residual, 1);
+      if (b % step == 0 && b / step < residual) v += 1;
+    }
+    __syncthreads();
+  }
+  // inclusive scan over the 256 bins
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, s, o);
+    if (lane >= o) s += t;
+  }
+  if (lane == 31) warp_sums[wid] = s;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < wid; k++) base += warp_sums[k];
+  s += base;
+  float f = __fmul_rn((float)s, g.lut_scale);
+  int r = __float2int_rn(f);
+  lut[tile * 256 + b] = (uint8_t)min(max(r, 0), 255);
+}
+
+// bilinear blend of the four neighbouring tile LUTs (CLAHE_Interpolation_Body); 4 px per thread, in place allowed.
+// Optionally also emits the per-row inclusive prefix sums of the result (first half of the integral image, K3):
+// not fused here -- see k_integral_rows.
+__global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__ src, size_t spitch, int w, int h,
+                                                     ClaheGeom g, const uint8_t* __restrict__ lut,
+                                                     uint8_t* __restrict__ dst, size_t dpitch) {
+  const int j0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j0 >= w || y >= h) return;
+  const float tyf = __fsub_rn(__fmul_rn((float)y, g.inv_th), 0.5f);
+  int ty1 = (int)floorf(tyf), ty2 = ty1 + 1;
+  const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
+  ty1 = max(ty1, 0);
+  ty2 = min(ty2, g.tiles_y - 1);
+  const uint8_t* l1 = lut + (size_t)ty1 * g.tiles_x * 256;
+  const uint8_t* l2 = lut + (size_t)ty2 * g.tiles_x * 256;
+  uint8_t in[4], out[4];
+  const uint8_t* s = src + (size_t)y * spitch + j0;
+  const bool vec = (j0 + 3 < w) && ((spitch & 3) == 0) && ((dpitch & 3) == 0);
+  if (vec) {
+    uchar4 q = *reinterpret_cast<const uchar4*>(s);
+    in[0] = q.x; in[1] = q.y; in[2] = q.z; in[3] = q.w;
+  } else {
+    for (int k = 0; k < 4; k++) in[k] = (j0 + k < w) ? s[k] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = j0 + k;
+    const float txf = __fsub_rn(__fmul_rn((float)x, g.inv_tw), 0.5f);
+    int tx1 = (int)floorf(txf), tx2 = tx1 + 1;
+    const float xa = __fsub_rn(txf, (float)tx1), xa1 = __fsub_rn(1.0f, xa);
+    tx1 = max(tx1, 0);
+    tx2 = min(tx2, g.tiles_x - 1);
+    const int v = in[k];
+    const float a = (float)l1[tx1 * 256 + v], b = (float)l1[tx2 * 256 + v];
+    const float c = (float)l2[tx1 * 256 + v], e = (float)l2[tx2 * 256 + v];
+    const float top = __fadd_rn(__fmul_rn(a, xa1), __fmul_rn(b, xa));
+    const float bot = __fadd_rn(__fmul_rn(c, xa1), __fmul_rn(e, xa));
+    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+    const int r = __float2int_rn(res);
+    out[k] = (uint8_t)min(max(r, 0), 255);
+  }
+  uint8_t* d = dst + (size_t)y * dpitch + j0;
+  if (vec) *reinterpret_cast<uchar4*>(d) = make_uchar4(out[0], out[1], out[2], out[3]);
+  else
+    for (int k = 0; k < 4 && j0 + k < w; k++) d[k] = out[k];
+}
+
+ClaheGeom make_clahe_geom(int w, int h, double clip_limit, int tiles_x, int tiles_y) {
+  ClaheGeom g;
+  int pw = w, ph = h;
+  if (w % tiles_x != 0 || h % tiles_y != 0) {
+    pw = w + (tiles_x - (w % tiles_x));
+    ph = h + (tiles_y - (h % tiles_y));
+  }
+  g.tiles_x = tiles_x;
+  g.tiles_y = tiles_y;
+  g.tw = pw / tiles_x;
+  g.th = ph / tiles_y;
+  const int area = g.tw * g.th;
+  g.clip = 0;
+  if (clip_limit > 0.0) {
+    g.clip = (int)(clip_limit * area / 256);
+    if (g.clip < 1) g.clip = 1;
+  }
+  g.lut_scale = (float)255 / area;
+  g.inv_tw = 1.0f / g.tw;
+  g.inv_th = 1.0f / g.th;
+  return g;
+}
+
+void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g,
+                  unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_dst, size_t dpitch) {
+  const int tiles = g.tiles_x * g.tiles_y;
+  UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles, c.stream));
+  int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
+  k_clahe_hist<<<dim3(tiles, slices), 256, 0, c.stream>>>(d_src, spitch, w, h, g, d_hist);
+  UVO_LAUNCH_CHECK(c);
+  k_clahe_lut<<<tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);
+  UVO_LAUNCH_CHECK(c);
+  dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8));
+  k_clahe_apply<<<grid, block, 0, c.stream>>>(d_src, spitch, w, h, g, d_lut, d_dst, dpitch);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 integral
+// Pass 1: one warp per image row; inclusive prefix along the row, written to sum[(i+1)][1..w]; also zeroes column 0
+// and (warp 0) row 0.  Pass 2: column prefix in place, each block owns 32 columns x 32 row segments.
+__global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* __restrict__ img, size_t pitch, int w, int h,
+                                                       int32_t* __restrict__ sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int sw = w + 1;
+  if (warp == 0)
+    for (int j = lane; j < sw; j += 32) sum[j] = 0;
+  if (warp >= h) return;
+  const uint8_t* row = img + (size_t)warp * pitch;
+  int32_t* out = sum + (size_t)(warp + 1) * sw;
+  if (lane == 0) out[0] = 0;
+  int carry = 0;
+  for (int base = 0; base < w; base += 128) {
+    const int j = base + lane * 4;
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (j + 3 < w && (pitch & 3) == 0) {
+      uchar4 q = *reinterpret_cast<const uchar4*>(row + j);
+      v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
+    } else {
+      if (j < w) v0 = row[j];
+      if (j + 1 < w) v1 = row[j + 1];
+      if (j + 2 < w) v2 = row[j + 2];
+      if (j + 3 < w) v3 = row[j + 3];
+    }
+    v1 += v0; v2 += v1; v3 += v2;
+    int s = v3;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    const int excl = s - v3 + carry;
+    if (j < w) out[j + 1] = v0 + excl;
+    if (j + 1 < w) out[j + 2] = v1 + excl;
+    if (j + 2 < w) out[j + 3] = v2 + excl;
+    if (j + 3 < w) out[j + 4] = v3 + excl;
+    carry += __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+
+// block = 32 (columns) x 32 (row segments).  Segment totals -> exclusive scan in smem -> second sweep adds.
+__global__ void __launch_bounds__(1024) k_integral_cols(int32_t* __restrict__ sum, int w, int h) {
+  __shared__ int32_t tot[32][33];
+  const int sw = w + 1;
+  const int col = 1 + blockIdx.x * 32 + threadIdx.x;
+  const int seg = threadIdx.y;
+  const int rows_per = (h + 31) / 32;
+  const int r0 = 1 + seg * rows_per, r1 = min(r0 + rows_per, h + 1);
+  int32_t acc = 0;
+  if (col < sw)
+    for (int r = r0; r < r1; r++) acc += sum[(size_t)r * sw + col];
+  tot[seg][threadIdx.x] = acc;
+  __syncthreads();
+  int32_t run = 0;
+  for (int k = 0; k < seg; k++) run += tot[k][threadIdx.x];
+  if (col < sw)
+    for (int r = r0; r < r1; r++) {
+      run += sum[(size_t)r * sw + col];
+      sum[(size_t)r * sw + col] = run;
+    }
+}
+
+void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum) {
+  const int warps_per_block = 8;
+  k_integral_rows<<<div_up(h, warps_per_block), 32 * warps_per_block, 0, c.stream>>>(d_img, pitch, w, h, d_sum);
+  UVO_LAUNCH_CHECK(c);
+  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, w, h);
+  UVO_LAUNCH_CHECK(c);
+}
+
+}  // namespace uvo

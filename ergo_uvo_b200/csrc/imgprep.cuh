@@ -1,0 +1,31 @@
+// imgprep.cuh -- internal interface of the image-preparation kernels (K1-K3).
+#pragma once
+#include "common.cuh"
+
+namespace uvo {
+
+struct UndistortParams {
+  double ir[9];            // inverse of the new camera matrix
+  double fx, fy, u0, v0;   // original camera matrix
+  double k1, k2, p1, p2;   // distortion
+};
+
+struct ClaheGeom {
+  int tiles_x, tiles_y, tw, th, clip;
+  float lut_scale, inv_tw, inv_th;
+};
+
+__host__ __device__ static inline int div_up_dev(int a, int b) { return (a + b - 1) / b; }
+
+UndistortParams make_undistort_params(const uvo_camera& cam);
+ClaheGeom make_clahe_geom(int w, int h, double clip_limit, int tiles_x, int tiles_y);
+
+void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, int h, const UndistortParams& P,
+                           uint8_t* d_dst, size_t dpitch);
+// d_hist: tiles*256 u32 scratch, d_lut: tiles*256 u8 scratch; src and dst may alias
+void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, unsigned int* d_hist,
+                  uint8_t* d_lut, uint8_t* d_dst, size_t dpitch);
+// d_sum: (h+1) x (w+1) int32, dense
+void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum);
+
+}  // namespace uvo

@@ -1,0 +1,647 @@
+// surf.cu -- K4..K7: SURF detectAndCompute on sm_100a (see surf.cuh).
+//
+// Behaviour follows OpenCV-contrib's CPU SURF as restated in SURVEY.md Appendix A (the reference only calls it:
+// VO_utility.cpp:117-118).  Design differences from the CPU code (none changes a result bit):
+//   * the 20 det/trace maps are never written to HBM: one block computes the 5 layers of an octave for a 32x16 tile
+//     (+1 halo) straight from the L2-resident integral image into shared memory and runs the 3x3x3 non-max
+//     suppression + interpolation on it.  `trace` is not computed at all (its only use, KeyPoint::class_id, is
+//     reset to -1 by detectAndCompute);
+//   * detections are appended with an atomic counter and put into OpenCV's total order by a rank sort, so the
+//     output order is deterministic regardless of the append order;
+//   * descriptors: one block per keypoint does window extraction + INTER_AREA 21x21 resize + Haar + 4x4x4 sums.
+// Every floating-point step keeps the CPU operation order (compiled with -fmad=false).
+#include <cfloat>
+#include <cmath>
+
+#include "surf.cuh"
+
+namespace uvo {
+
+// getGaussianKernel(13, 2.5, CV_32F) and getGaussianKernel(20, 3.3, CV_32F) (values checked against cv2 and the
+// oracle in tests/test_oracle_surf.py::test_gaussian_tables)
+static const float kGOri[13] = {0x1.282748p-7f,  0x1.64ff86p-6f, 0x1.6eb6e4p-5f, 0x1.40ff98p-4f, 0x1.dedf96p-4f,
+                                0x1.30623ap-3f,  0x1.49bc24p-3f, 0x1.30623ap-3f, 0x1.dedf96p-4f, 0x1.40ff98p-4f,
+                                0x1.6eb6e4p-5f,  0x1.64ff86p-6f, 0x1.282748p-7f};
+static const float kGDesc[20] = {0x1.f6898ep-10f, 0x1.1f18f6p-8f, 0x1.2b4118p-7f, 0x1.1c8ee8p-6f, 0x1.edafecp-6f,
+                                 0x1.86ae6p-5f,   0x1.1a0a9cp-4f, 0x1.737ecap-4f, 0x1.be6398p-4f, 0x1.eef842p-4f,
+                                 0x1.eef842p-4f,  0x1.be6398p-4f, 0x1.737ecap-4f, 0x1.1a0a9cp-4f, 0x1.86ae6p-5f,
+                                 0x1.edafecp-6f,  0x1.1c8ee8p-6f, 0x1.2b4118p-7f, 0x1.1f18f6p-8f, 0x1.f6898ep-10f};
+
+__constant__ float c_DW[400];      // DW[i*20+j] = G_desc[i]*G_desc[j]
+__constant__ float c_aptw[128];    // orientation sample weights (113 used)
+__constant__ signed char c_apt[128][2];
+static bool g_tables_uploaded[64] = {};
+
+static void upload_tables(Ctx& c) {
+  if (c.device < 64 && g_tables_uploaded[c.device]) return;
+  float DW[400];
+  for (int i = 0; i < 20; i++)
+    for (int j = 0; j < 20; j++) DW[i * 20 + j] = kGDesc[i] * kGDesc[j];
+  float aptw[128] = {};
+  signed char apt[128][2] = {};
+  int n = 0;
+  for (int i = -6; i <= 6; i++)
+    for (int j = -6; j <= 6; j++)
+      if (i * i + j * j <= 36) {
+        apt[n][0] = (signed char)i;
+        apt[n][1] = (signed char)j;
+        aptw[n++] = kGOri[i + 6] * kGOri[j + 6];
+      }
+  UVO_CUDA(cudaMemcpyToSymbolAsync(c_DW, DW, sizeof(DW), 0, cudaMemcpyHostToDevice, c.stream));
+  UVO_CUDA(cudaMemcpyToSymbolAsync(c_aptw, aptw, sizeof(aptw), 0, cudaMemcpyHostToDevice, c.stream));
+  UVO_CUDA(cudaMemcpyToSymbolAsync(c_apt, apt, sizeof(apt), 0, cudaMemcpyHostToDevice, c.stream));
+  UVO_CUDA(cudaStreamSynchronize(c.stream));
+  if (c.device < 64) g_tables_uploaded[c.device] = true;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry (host)
+static inline int cv_roundf_h(float v) { return (int)nearbyintf(v); }
+
+static void resize_haar_h(const int src[][5], SurfBox* dst, int n, int old_size, int new_size, int width_step) {
+  float ratio = (float)new_size / old_size;
+  for (int k = 0; k < n; k++) {
+    int dx1 = cv_roundf_h(ratio * src[k][0]), dy1 = cv_roundf_h(ratio * src[k][1]);
+    int dx2 = cv_roundf_h(ratio * src[k][2]), dy2 = cv_roundf_h(ratio * src[k][3]);
+    dst[k].p0 = dy1 * width_step + dx1;
+    dst[k].p1 = dy2 * width_step + dx1;
+    dst[k].p2 = dy1 * width_step + dx2;
+    dst[k].p3 = dy2 * width_step + dx2;
+    dst[k].w = src[k][4] / ((float)(dx2 - dx1) * (dy2 - dy1));
+  }
+}
+
+SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, int n_layers) {
+  static const int dx_s[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
+  static const int dy_s[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
+  static const int dxy_s[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
+  if (n_octaves < 1 || n_octaves > SURF_MAX_OCTAVES || n_layers < 1 || n_layers + 2 > SURF_MAX_LAYERS)
+    throw InvalidArg{"SURF: supported range is 1..4 octaves and 1..3 octave layers", UVO_ERR_UNSUPPORTED};
+  SurfGeom g{};
+  g.w = w;
+  g.h = h;
+  g.n_octaves = n_octaves;
+  g.n_layers = n_layers;
+  g.thr = (float)hessian_threshold;
+  int tile_begin = 0;
+  for (int o = 0; o < n_octaves; o++) {
+    SurfOctave& O = g.oct[o];
+    O.step = 1 << o;
+    O.lrows = h / O.step;
+    O.lcols = w / O.step;
+    O.tiles_x = div_up(std::max(O.lcols, 1), SURF_TILE_W);
+    O.tiles_y = div_up(std::max(O.lrows, 1), SURF_TILE_H);
+    O.tile_begin = tile_begin;
+    tile_begin += O.tiles_x * O.tiles_y;
+    for (int l = 0; l < n_layers + 2; l++) {
+      SurfLayer& L = O.layer[l];
+      L.size = (9 + 6 * l) << o;
+      L.margin = (L.size / 2) / O.step;
+      if (L.size > h || L.size > w) {
+        L.samples_i = L.samples_j = 0;  // calcLayerDetAndTrace returns early
+      } else {
+        L.samples_i = 1 + (h - L.size) / O.step;
+        L.samples_j = 1 + (w - L.size) / O.step;
+      }
+      resize_haar_h(dx_s, L.box + 0, 3, 9, L.size, w + 1);
+      resize_haar_h(dy_s, L.box + 3, 3, 9, L.size, w + 1);
+      resize_haar_h(dxy_s, L.box + 6, 4, 9, L.size, w + 1);
+    }
+    for (int l = 1; l <= n_layers; l++) O.nms_margin[l] = (O.layer[l + 1].size / 2) / O.step + 1;
+  }
+  g.total_tiles = tile_begin;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------ K4+K5
+__device__ __forceinline__ float haar3(const int* __restrict__ o, const SurfBox* __restrict__ f) {
+  double d = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    int v = (int)((unsigned)__ldg(o + f[k].p0) + (unsigned)__ldg(o + f[k].p3) - (unsigned)__ldg(o + f[k].p1) -
+                  (unsigned)__ldg(o + f[k].p2));
+    d = __dadd_rn(d, (double)__fmul_rn((float)v, f[k].w));
+  }
+  return (float)d;
+}
+__device__ __forceinline__ float haar4(const int* __restrict__ o, const SurfBox* __restrict__ f) {
+  double d = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int v = (int)((unsigned)__ldg(o + f[k].p0) + (unsigned)__ldg(o + f[k].p3) - (unsigned)__ldg(o + f[k].p1) -
+                  (unsigned)__ldg(o + f[k].p2));
+    d = __dadd_rn(d, (double)__fmul_rn((float)v, f[k].w));
+  }
+  return (float)d;
+}
+
+__device__ __forceinline__ float det_at(const int* __restrict__ sum, int scols, const SurfLayer& L, int step, int i,
+                                        int j) {
+  const int si = i - L.margin, sj = j - L.margin;
+  if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
+  const int* o = sum + (size_t)(si * step) * scols + sj * step;
+  const float dx = haar3(o, L.box + 0), dy = haar3(o, L.box + 3), dxy = haar4(o, L.box + 6);
+  return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
+}
+
+// interpolateKeypoint: 3x3 Cramer solve in f32 (Matx33f::solve(DECOMP_LU))
+__device__ __forceinline__ bool interpolate_keypoint(const float N[3][9], int step, int ds, float& px, float& py,
+                                                     float& psize) {
+  const float b0 = -(N[1][5] - N[1][3]) / 2, b1 = -(N[1][7] - N[1][1]) / 2, b2 = -(N[2][4] - N[0][4]) / 2;
+  const float a00 = N[1][3] - 2 * N[1][4] + N[1][5];
+  const float a01 = (N[1][8] - N[1][6] - N[1][2] + N[1][0]) / 4;
+  const float a02 = (N[2][5] - N[2][3] - N[0][5] + N[0][3]) / 4;
+  const float a10 = a01;
+  const float a11 = N[1][1] - 2 * N[1][4] + N[1][7];
+  const float a12 = (N[2][7] - N[2][1] - N[0][7] + N[0][1]) / 4;
+  const float a20 = a02, a21 = a12;
+  const float a22 = N[0][4] - 2 * N[1][4] + N[2][4];
+  float d = a00 * (a11 * a22 - a21 * a12) - a01 * (a10 * a22 - a20 * a12) + a02 * (a10 * a21 - a20 * a11);
+  float x0 = 0, x1 = 0, x2 = 0;
+  if (d != 0) {
+    d = 1 / d;
+    x0 = d * (b0 * (a11 * a22 - a12 * a21) - a01 * (b1 * a22 - a12 * b2) + a02 * (b1 * a21 - a11 * b2));
+    x1 = d * (a00 * (b1 * a22 - a12 * b2) - b0 * (a10 * a22 - a12 * a20) + a02 * (a10 * b2 - b1 * a20));
+    x2 = d * (a00 * (a11 * b2 - b1 * a21) - a01 * (a10 * b2 - b1 * a20) + b0 * (a10 * a21 - a11 * a20));
+  }
+  const bool ok = (x0 != 0 || x1 != 0 || x2 != 0) && fabsf(x0) <= 1 && fabsf(x1) <= 1 && fabsf(x2) <= 1;
+  if (ok) {
+    px += x0 * step;
+    py += x1 * step;
+    psize = (float)__float2int_rn(psize + x2 * ds);
+  }
+  return ok;
+}
+
+constexpr int TW = SURF_TILE_W, TH = SURF_TILE_H;
+
+__global__ void __launch_bounds__(256) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
+                                                     int capacity) {
+  __shared__ float sdet[SURF_MAX_LAYERS][TH + 2][TW + 2];
+  const SurfImage& im = b.im[blockIdx.y];
+  int t = blockIdx.x, o = 0;
+  while (o + 1 < g.n_octaves && t >= g.oct[o + 1].tile_begin) o++;
+  const SurfOctave& O = g.oct[o];
+  t -= O.tile_begin;
+  const int ti0 = (t / O.tiles_x) * TH, tj0 = (t % O.tiles_x) * TW;
+  const int nl = g.n_layers + 2;
+  const int scols = g.w + 1;
+  const int step = O.step;
+  constexpr int PLANE = (TH + 2) * (TW + 2);
+  for (int idx = threadIdx.x; idx < nl * PLANE; idx += blockDim.x) {
+    const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+    sdet[l][y][x] = det_at(im.sum, scols, O.layer[l], step, ti0 + y - 1, tj0 + x - 1);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < g.n_layers * TH * TW; idx += blockDim.x) {
+    const int m = 1 + idx / (TH * TW), r = idx % (TH * TW), y = r / TW, x = r % TW;
+    const int i = ti0 + y, j = tj0 + x;
+    const int margin = O.nms_margin[m];
+    if (i < margin || i >= O.lrows - margin || j < margin || j >= O.lcols - margin) continue;
+    const float val0 = sdet[m][y + 1][x + 1];
+    if (!(val0 > g.thr)) continue;
+    float N[3][9];
+    bool is_max = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int q = 0; q < 9; q++) {
+        const float v = sdet[m - 1 + a][y + q / 3][x + q % 3];
+        N[a][q] = v;
+        if (!(a == 1 && q == 4) && !(val0 > v)) is_max = false;
+      }
+    if (!is_max) continue;
+    const int size = O.layer[m].size;
+    const int sum_i = step * (i - (size / 2) / step), sum_j = step * (j - (size / 2) / step);
+    float py = (float)sum_i + (float)(size - 1) * 0.5f;
+    float px = (float)sum_j + (float)(size - 1) * 0.5f;
+    float psize = (float)size;
+    const int ds = size - O.layer[m - 1].size;
+    if (!interpolate_keypoint(N, step, ds, px, py, psize)) continue;
+    const int slot = atomicAdd(&im.counters[0], 1);
+    if (slot < capacity) {
+      uvo_keypoint k;
+      k.x = px;
+      k.y = py;
+      k.size = psize;
+      k.angle = -1.f;
+      k.response = val0;
+      k.octave = o;
+      k.class_id = -1;
+      im.raw[slot] = k;
+    }
+  }
+}
+
+void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity) {
+  upload_tables(c);
+  for (int i = 0; i < b.n_img; i++) UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
+  k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(g, b, capacity);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------ K6 sort
+// KeypointGreater: response desc, size desc, octave desc, y desc, x asc
+__device__ __forceinline__ bool kp_precedes(float ra, float sa, int oa, float ya, float xa, float rb, float sb,
+                                            int ob, float yb, float xb) {
+  if (ra > rb) return true;
+  if (ra < rb) return false;
+  if (sa > sb) return true;
+  if (sa < sb) return false;
+  if (oa > ob) return true;
+  if (oa < ob) return false;
+  if (ya > yb) return true;
+  if (ya < yb) return false;
+  return xa < xb;
+}
+
+__global__ void __launch_bounds__(256) k_surf_rank(const __grid_constant__ SurfBatch b, int capacity) {
+  __shared__ float4 s_k[256];
+  __shared__ int s_o[256];
+  const SurfImage& im = b.im[blockIdx.y];
+  const int n = min(im.counters[0], capacity);
+  if (blockIdx.x == 0 && threadIdx.x == 0) im.counters[1] = n;
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  uvo_keypoint me{};
+  if (i < n) me = im.raw[i];
+  int rank = 0;
+  for (int base = 0; base < n; base += 256) {
+    const int j = base + threadIdx.x;
+    if (j < n) {
+      const uvo_keypoint k = im.raw[j];
+      s_k[threadIdx.x] = make_float4(k.response, k.size, k.y, k.x);
+      s_o[threadIdx.x] = k.octave;
+    }
+    __syncthreads();
+    const int m = min(256, n - base);
+    if (i < n)
+      for (int q = 0; q < m; q++) {
+        const float4 k = s_k[q];
+        const int jo = s_o[q];
+        const bool before = kp_precedes(k.x, k.y, jo, k.z, k.w, me.response, me.size, me.octave, me.y, me.x);
+        const bool same = (k.x == me.response) && (k.y == me.size) && (jo == me.octave) && (k.z == me.y) && (k.w == me.x);
+        rank += (before || (same && (base + q) < i)) ? 1 : 0;
+      }
+    __syncthreads();
+  }
+  if (i < n) im.kps[rank] = me;
+}
+
+void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity) {
+  k_surf_rank<<<dim3(div_up(capacity, 256), b.n_img), 256, 0, c.stream>>>(b, capacity);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------ K7 descriptors
+// INTER_AREA table of one destination index (OpenCV computeResizeAreaTab): optional left partial cell, full cells
+// [sx1, sx2), optional right partial cell.
+struct AreaSpan {
+  int sx1, sx2;
+  bool has_l, has_r;
+  float a_l, a_f, a_r;
+};
+__device__ __forceinline__ AreaSpan area_span(int d, int ssize, double scale) {
+  AreaSpan s;
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  s.sx1 = sx1;
+  s.sx2 = sx2;
+  s.has_l = (sx1 - fsx1 > 1e-3);
+  s.a_l = (float)((sx1 - fsx1) / cell);
+  s.a_f = (float)(1.0 / cell);
+  s.has_r = (fsx2 - sx2 > 1e-3);
+  s.a_r = (float)(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
+  return s;
+}
+
+struct WinSampler {
+  const uint8_t* img;
+  size_t pitch;
+  int w, h;
+  bool upright;
+  // upright: WIN[i][j] = img(clamp(start_y - j), clamp(start_x + i))
+  int start_x, start_y;
+  // oriented: bilinear / nearest sampling along the rotated frame (A.4 "Window")
+  float fstart_x, fstart_y, sin_dir, cos_dir;
+  int win_size;
+  __device__ __forceinline__ int at(int i, int j) const {
+    if (upright) {
+      const int x = min(max(start_x + i, 0), w - 1), y = min(max(start_y - j, 0), h - 1);
+      return __ldg(img + (size_t)y * pitch + x);
+    }
+    // OpenCV accumulates start_x += sin_dir (f32) per row i and pixel_x += cos_dir (f64) per column j
+    float sx = fstart_x, sy = fstart_y;
+    for (int q = 0; q < i; q++) {
+      sx = __fadd_rn(sx, sin_dir);
+      sy = __fadd_rn(sy, cos_dir);
+    }
+    double pxl = sx, pyl = sy;
+    for (int q = 0; q < j; q++) {
+      pxl = __dadd_rn(pxl, (double)cos_dir);
+      pyl = __dsub_rn(pyl, (double)sin_dir);
+    }
+    const int ix = (int)floor(pxl), iy = (int)floor(pyl);
+    if ((unsigned)ix < (unsigned)(w - 1) && (unsigned)iy < (unsigned)(h - 1)) {
+      const float a = (float)(pxl - ix), bb = (float)(pyl - iy);
+      const uint8_t* p = img + (size_t)iy * pitch + ix;
+      const float p00 = (float)__ldg(p), p01 = (float)__ldg(p + 1), p10 = (float)__ldg(p + pitch),
+                  p11 = (float)__ldg(p + pitch + 1);
+      const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, bb);
+      float v = __fmul_rn(__fmul_rn(p00, ia), ib);
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(p01, a), ib));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(p10, ia), bb));
+      v = __fadd_rn(v, __fmul_rn(__fmul_rn(p11, a), bb));
+      return (int)(uint8_t)__float2int_rn(v);
+    }
+    const int x = min(max(__double2int_rn(pxl), 0), w - 1), y = min(max(__double2int_rn(pyl), 0), h - 1);
+    return __ldg(img + (size_t)y * pitch + x);
+  }
+};
+
+// cv::fastAtan2 polynomial (degrees)
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+  const float p1 = 0.9997878412794807f * (float)(180 / M_PI), p3 = -0.3258083974640975f * (float)(180 / M_PI),
+              p5 = 0.1555786518463281f * (float)(180 / M_PI), p7 = -0.04432655554792128f * (float)(180 / M_PI);
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  } else {
+    c = ax / (ay + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+constexpr int DESC_THREADS = 128;
+
+// One block per keypoint (grid-stride).  Shared: 21x21 patch, 2x400 gradients, 64-vector.
+__global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_constant__ SurfGeom g,
+                                                                const __grid_constant__ SurfBatch b,
+                                                                int upright) {
+  __shared__ int s_patch[21][21];
+  __shared__ float s_dx[400], s_dy[400];
+  __shared__ float s_vec[64];
+  __shared__ float s_scale;
+  __shared__ float s_X[128], s_Y[128], s_ang[128];
+  __shared__ int s_nangle;
+  __shared__ float s_dir;
+  const SurfImage& im = b.im[blockIdx.y];
+  const int n = im.counters[1];
+  const int w = g.w, h = g.h, srows = h + 1, scols = w + 1;
+  const int tid = threadIdx.x;
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    const uvo_keypoint kp = im.kps[k];
+    const float size = kp.size, cx = kp.x, cy = kp.y;
+    const float s = __fdiv_rn(__fmul_rn(size, 1.2f), 9.0f);
+    const int gws = 2 * __float2int_rn(__fmul_rn(2.f, s));
+    if (srows < gws || scols < gws) {  // gradient wavelet larger than the image: mark for deletion
+      if (tid == 0) im.kps[k].size = -1.f;
+      continue;
+    }
+    float dir = 270.f;
+    if (!upright) {
+      // ---- dominant orientation (A.4): Haar responses on a radius-6s disc, 60-degree sliding window ----
+      if (tid == 0) s_nangle = 0;
+      __syncthreads();
+      // resizeHaarPattern(dx_s/dy_s, 4 -> gws): boxes {0,0,2,4,-1},{2,0,4,4,1} and {0,0,4,2,1},{0,2,4,4,-1}
+      const float ratio = (float)gws / 4;
+      const int c2 = __float2int_rn(__fmul_rn(ratio, 2.f)), c4 = __float2int_rn(__fmul_rn(ratio, 4.f));
+      const float wx = 1.f / ((float)(c2 - 0) * (c4 - 0));   // |w| of every box (all are c2 x c4 or c4 x c2)
+      // samples are visited in table order; order of X/Y entries must match the CPU (sequential append), so one
+      // warp-free pass computes validity, a prefix gives the slot.
+      float vX = 0.f, vY = 0.f;
+      bool valid = false;
+      if (tid < 113) {
+        const int x = __float2int_rn(__fsub_rn(__fadd_rn(cx, __fmul_rn((float)c_apt[tid][0], s)), (float)(gws - 1) / 2));
+        const int y = __float2int_rn(__fsub_rn(__fadd_rn(cy, __fmul_rn((float)c_apt[tid][1], s)), (float)(gws - 1) / 2));
+        if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
+          valid = true;
+          const int* o = im.sum + (size_t)y * scols + x;
+          auto box = [&](int x1, int y1, int x2, int y2) -> int {
+            return (int)((unsigned)__ldg(o + y1 * scols + x1) + (unsigned)__ldg(o + y2 * scols + x2) -
+                         (unsigned)__ldg(o + y2 * scols + x1) - (unsigned)__ldg(o + y1 * scols + x2));
+          };
+          double dxv = 0, dyv = 0;
+          dxv = __dadd_rn(dxv, (double)__fmul_rn((float)box(0, 0, c2, c4), -wx));
+          dxv = __dadd_rn(dxv, (double)__fmul_rn((float)box(c2, 0, c4, c4), wx));
+          dyv = __dadd_rn(dyv, (double)__fmul_rn((float)box(0, 0, c4, c2), wx));
+          dyv = __dadd_rn(dyv, (double)__fmul_rn((float)box(0, c2, c4, c4), -wx));
+          vX = __fmul_rn((float)dxv, c_aptw[tid]);
+          vY = __fmul_rn((float)dyv, c_aptw[tid]);
+        }
+      }
+      // ordered compaction over the 128 threads (4 warps)
+      __shared__ int s_wcnt[4];
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      const int lane = tid & 31, wid = tid >> 5;
+      if (lane == 0) s_wcnt[wid] = __popc(bal);
+      __syncthreads();
+      int off = 0;
+      for (int q = 0; q < wid; q++) off += s_wcnt[q];
+      if (valid) {
+        const int slot = off + __popc(bal & ((1u << lane) - 1));
+        s_X[slot] = vX;
+        s_Y[slot] = vY;
+        s_ang[slot] = fast_atan2_deg(vY, vX);  // cv::phase(X, Y, angle, true)
+      }
+      if (tid == 0) s_nangle = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+      __syncthreads();
+      const int nangle = s_nangle;
+      if (nangle == 0) {
+        if (tid == 0) im.kps[k].size = -1.f;
+        __syncthreads();
+        continue;
+      }
+      // 72 window positions; thread t evaluates window i = 5t sequentially over samples (CPU order), then the
+      // first-best-wins arg max is taken in window order.
+      __shared__ float s_mod[72], s_sx[72], s_sy[72];
+      if (tid < 72) {
+        const int i = tid * 5;
+        float sumx = 0, sumy = 0;
+        for (int j = 0; j < nangle; j++) {
+          const int d = abs(__float2int_rn(s_ang[j]) - i);
+          if (d < 30 || d > 330) {
+            sumx = __fadd_rn(sumx, s_X[j]);
+            sumy = __fadd_rn(sumy, s_Y[j]);
+          }
+        }
+        s_sx[tid] = sumx;
+        s_sy[tid] = sumy;
+        s_mod[tid] = __fadd_rn(__fmul_rn(sumx, sumx), __fmul_rn(sumy, sumy));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float bestx = 0, besty = 0, best = 0;
+        for (int q = 0; q < 72; q++)
+          if (s_mod[q] > best) {
+            best = s_mod[q];
+            bestx = s_sx[q];
+            besty = s_sy[q];
+          }
+        s_dir = fast_atan2_deg(-besty, bestx);
+      }
+      __syncthreads();
+      dir = s_dir;
+    }
+
+    // ---- window geometry ----
+    const int win_size = (int)__fmul_rn(21.f, s);
+    WinSampler ws;
+    ws.img = im.img;
+    ws.pitch = im.pitch;
+    ws.w = w;
+    ws.h = h;
+    ws.upright = upright != 0;
+    ws.win_size = win_size;
+    const float win_offset = -(float)(win_size - 1) / 2;
+    if (upright) {
+      ws.start_x = __float2int_rn(__fadd_rn(cx, win_offset));
+      ws.start_y = __float2int_rn(__fsub_rn(cy, win_offset));
+    } else {
+      const float ddir = __fmul_rn(dir, (float)(M_PI / 180));
+      // std::sin/std::cos(float) on the CPU are (nearly) correctly rounded; go through fp64 to match them
+      ws.sin_dir = -(float)sin((double)ddir);
+      ws.cos_dir = (float)cos((double)ddir);
+      ws.fstart_x = __fadd_rn(__fadd_rn(cx, __fmul_rn(win_offset, ws.cos_dir)), __fmul_rn(win_offset, ws.sin_dir));
+      ws.fstart_y = __fadd_rn(__fsub_rn(cy, __fmul_rn(win_offset, ws.sin_dir)), __fmul_rn(win_offset, ws.cos_dir));
+    }
+
+    // ---- resize(win -> 21x21, INTER_AREA) ----
+    const double inv_scale = (double)21 / win_size;
+    const double scale = 1. / inv_scale;
+    int iscale = __double2int_rn(scale);
+    const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
+    for (int t = tid; t < 441; t += DESC_THREADS) {
+      const int py = t / 21, px = t - py * 21;
+      int out;
+      if (win_size == 21) {
+        out = ws.at(py, px);
+      } else if (area_fast) {
+        int acc = 0;
+        for (int ky = 0; ky < iscale; ky++)
+          for (int kx = 0; kx < iscale; kx++) {
+            const int sy = py * iscale + ky, sx = px * iscale + kx;
+            if (sy < win_size && sx < win_size) acc += ws.at(sy, sx);
+          }
+        if (iscale == 2) out = (acc + 2) >> 2;
+        else out = min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
+      } else {
+        const AreaSpan ys = area_span(py, win_size, scale), xs = area_span(px, win_size, scale);
+        float sum = 0.f;
+        bool first = true;
+        auto row = [&](int sy, float beta) {
+          float buf = 0.f;
+          if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx1 - 1), xs.a_l));
+          for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, sx), xs.a_f));
+          if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx2), xs.a_r));
+          if (first) {
+            sum = __fmul_rn(beta, buf);
+            first = false;
+          } else {
+            sum = __fadd_rn(sum, __fmul_rn(beta, buf));
+          }
+        };
+        if (ys.has_l) row(ys.sx1 - 1, ys.a_l);
+        for (int sy = ys.sx1; sy < ys.sx2; sy++) row(sy, ys.a_f);
+        if (ys.has_r) row(ys.sx2, ys.a_r);
+        out = min(max(__float2int_rn(sum), 0), 255);
+      }
+      s_patch[py][px] = out;
+    }
+    __syncthreads();
+    // ---- Haar gradients with Gaussian weights ----
+    for (int t = tid; t < 400; t += DESC_THREADS) {
+      const int i = t / 20, j = t - i * 20;
+      const float dw = c_DW[t];
+      s_dx[t] = __fmul_rn((float)(s_patch[i][j + 1] - s_patch[i][j] + s_patch[i + 1][j + 1] - s_patch[i + 1][j]), dw);
+      s_dy[t] = __fmul_rn((float)(s_patch[i + 1][j] - s_patch[i][j] + s_patch[i + 1][j + 1] - s_patch[i][j + 1]), dw);
+    }
+    __syncthreads();
+    // ---- 4x4 cells x (sum dx, sum dy, sum |dx|, sum |dy|), y-major over each 5x5 cell ----
+    if (tid < 64) {
+      const int cell = tid >> 2, comp = tid & 3, ci = cell >> 2, cj = cell & 3;
+      float v = 0.f;
+      for (int y = ci * 5; y < ci * 5 + 5; y++)
+        for (int x = cj * 5; x < cj * 5 + 5; x++) {
+          const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
+          const float add = comp == 0 ? tx : comp == 1 ? ty : comp == 2 ? fabsf(tx) : fabsf(ty);
+          v = __fadd_rn(v, add);
+        }
+      s_vec[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double sq = 0;
+      for (int q = 0; q < 64; q++) sq = __dadd_rn(sq, (double)__fmul_rn(s_vec[q], s_vec[q]));
+      s_scale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
+      im.kps[k].angle = dir;
+    }
+    __syncthreads();
+    if (tid < 64) im.desc[(size_t)k * 64 + tid] = __fmul_rn(s_vec[tid], s_scale);
+    __syncthreads();
+  }
+}
+
+void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright) {
+  upload_tables(c);
+  const int blocks = std::min(capacity, 8 * c.sm_count);
+  k_surf_describe<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------ compaction
+// single block per image: ordered removal of keypoints marked size <= 0
+__global__ void __launch_bounds__(1024) k_surf_compact(const __grid_constant__ SurfBatch b, uvo_keypoint* tmp_kps, float* tmp_desc,
+                                                       int capacity) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const SurfImage& im = b.im[blockIdx.x];
+  uvo_keypoint* tk = tmp_kps + (size_t)blockIdx.x * capacity;
+  float* td = tmp_desc + (size_t)blockIdx.x * capacity * 64;
+  const int n = im.counters[1];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int k = base + tid;
+    const bool keep = k < n && im.kps[k].size > 0.f;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int q = 0; q < wid; q++) off += s_warp[q];
+    if (keep) {
+      const int dst = off + __popc(bal & ((1u << lane) - 1));
+      tk[dst] = im.kps[k];
+      for (int q = 0; q < 64; q++) td[(size_t)dst * 64 + q] = im.desc[(size_t)k * 64 + q];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int q = 0; q < 32; q++) tot += s_warp[q];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  const int m = s_base;
+  __syncthreads();
+  for (int k = tid; k < m; k += 1024) im.kps[k] = tk[k];
+  for (int q = tid; q < m * 64; q += 1024) im.desc[q] = td[q];
+  if (tid == 0) im.counters[1] = m;
+}
+
+void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc) {
+  k_surf_compact<<<b.n_img, 1024, 0, c.stream>>>(b, tmp_kps, tmp_desc, capacity);
+  UVO_LAUNCH_CHECK(c);
+}
+
+}  // namespace uvo

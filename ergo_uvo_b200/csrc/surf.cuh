@@ -1,0 +1,63 @@
+// surf.cuh -- internal interface of the SURF kernels (K4-K7): Hessian box-filter pyramid fused with
+// 3x3x3 non-max suppression + interpolation, total-order sort, (orientation) and 64-d descriptors.
+// Replaces SURF::create(...)->detectAndCompute (reference VO_utility.cpp:117-118).
+#pragma once
+#include "common.cuh"
+
+namespace uvo {
+
+constexpr int SURF_MAX_LAYERS = 5;   // nOctaveLayers + 2
+constexpr int SURF_MAX_OCTAVES = 4;
+constexpr int SURF_TILE_W = 32, SURF_TILE_H = 16;
+
+struct SurfBox {
+  int p0, p1, p2, p3;  // offsets into the integral image (row stride w+1), as resizeHaarPattern computes them
+  float w;
+};
+
+struct SurfLayer {
+  int size, margin, samples_i, samples_j;
+  SurfBox box[10];  // Dx[0..2], Dy[0..2], Dxy[0..3]
+};
+
+struct SurfOctave {
+  int step, lrows, lcols, tiles_x, tiles_y, tile_begin;  // tile_begin: first block index of this octave
+  int nms_margin[SURF_MAX_LAYERS];                         // for middle layers 1..n_layers
+  SurfLayer layer[SURF_MAX_LAYERS];
+};
+
+struct SurfGeom {
+  int w, h, n_octaves, n_layers, total_tiles;
+  float thr;
+  SurfOctave oct[SURF_MAX_OCTAVES];
+};
+
+SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, int n_layers);
+
+// Per-image device state of one detectAndCompute.  All buffers are sized once for `capacity` keypoints.
+struct SurfImage {
+  const uint8_t* img = nullptr;   // gray image (device)
+  size_t pitch = 0;
+  const int32_t* sum = nullptr;   // integral (h+1)x(w+1)
+  uvo_keypoint* raw = nullptr;    // unordered detections
+  uvo_keypoint* kps = nullptr;    // sorted (OpenCV order), compacted
+  float* desc = nullptr;          // capacity x 64
+  int* counters = nullptr;        // [0] raw count (may exceed capacity => overflow), [1] final count, [2..3] spare
+};
+
+struct SurfBatch {
+  SurfImage im[2];
+  int n_img;
+};
+
+// detection (pyramid + NMS + interpolation) for n_img images of identical geometry, appends to raw[]/counters[0]
+void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity);
+// rank sort raw -> kps in KeypointGreater order, sets counters[1] = min(counters[0], capacity)
+void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity);
+// upright/oriented 64-d descriptors for kps[0..counters[1]); sets angle; marks deleted keypoints with size=-1
+void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright);
+// order-preserving removal of keypoints with size <= 0 (only needed when describe can delete: oriented mode or
+// images smaller than the largest gradient wavelet)
+void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc);
+
+}  // namespace uvo

@@ -1,0 +1,293 @@
+"""Python mirror of the reference's `uvo_libraries` function API over the C ABI (include/uvo_c.h).
+
+Function names and argument meaning follow uvo_libraries/include/uvo_libraries/VO_utility.h:96-117 so the parity
+tests read like calls into the reference; numpy arrays stand in for cv::Mat / std::vector.  The configuration
+globals of VO_utility.h:25-89 are the fields of `Params`.  Every function runs on the GPU through libuvo_b200.so;
+nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"),
+     ("class_id", "<i4")])
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+
+__all__ = ["Context", "default_params", "make_camera", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO"]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(v, n=None):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    return a
+
+
+def _k4(K):
+    K = np.asarray(K, dtype=np.float64)
+    if K.shape == (3, 3):
+        return np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
+    return _f64(K, 4)
+
+
+def default_params(stereo=True):
+    p = L.Params()
+    L.load().uvo_default_params(1 if stereo else 0, C.byref(p))
+    return p
+
+
+def make_camera(K, D, newK):
+    """cameraMatrix (3x3), distortionCoeff (k1,k2,p1,p2), newCamMatrix (3x3) -> uvo_camera."""
+    K = np.asarray(K, dtype=np.float64)
+    newK = np.asarray(newK, dtype=np.float64)
+    D = _f64(D, 4)
+    return L.Camera(K[0, 0], K[1, 1], K[0, 2], K[1, 2], D[0], D[1], D[2], D[3], newK[0, 0], newK[1, 1], newK[0, 2],
+                    newK[1, 2])
+
+
+class Context:
+    """One uvo_ctx per (GPU, stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.uvo_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != L.UVO_OK:
+            raise L.UvoError(rc, "uvo_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.params = default_params(True)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.uvo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != L.UVO_OK:
+            raise L.UvoError(rc, self.lib.uvo_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.lib.uvo_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.uvo_ctx_launch_count(self.h))
+
+    def synchronize(self):
+        self._ck(self.lib.uvo_ctx_synchronize(self.h))
+
+    # ------------------------------------------------------------------ VO_utility.h:105
+    def get_image(self, current_img, cameraMatrix, distortionCoeff, newCamMatrix):
+        """Mat get_image(current_img, cameraMatrix, distortionCoeff, newCamMatrix); CLAHE_CORRECTION / CLIP_LIMIT are
+        read from self.params like the reference reads its globals (VO_utility.cpp:352-357)."""
+        img = np.ascontiguousarray(current_img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("get_image expects a 3-channel image (cvtColor RGB2GRAY throws otherwise)")
+        h, w, _ = img.shape
+        cam = make_camera(cameraMatrix, distortionCoeff, newCamMatrix)
+        out = np.empty((h, w), np.uint8)
+        self._ck(self.lib.uvo_get_image(self.h, _p(img), w, h, C.c_size_t(3 * w), C.byref(cam),
+                                        int(self.params.clahe), int(self.params.clip_limit), _p(out),
+                                        C.c_size_t(w)))
+        return out
+
+    def integral(self, gray):
+        g = np.ascontiguousarray(gray, dtype=np.uint8)
+        h, w = g.shape
+        out = np.empty((h + 1, w + 1), np.int32)
+        self._ck(self.lib.uvo_integral(self.h, _p(g), w, h, C.c_size_t(w), _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ VO_utility.h:100
+    def detect_features(self, img, capacity=None):
+        """void detect_features(Mat img, vector<KeyPoint>&, Mat&) -> (keypoints, descriptors)."""
+        g = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = g.shape
+        cap = int(capacity or self.params.max_features)
+        dim = 128 if self.params.surf_extended else 64
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, dim), np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.uvo_detect_features(self.h, _p(g), w, h, C.c_size_t(w), C.byref(self.params), _p(kps),
+                                              _p(desc), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # ------------------------------------------------------------------ VO_utility.h:109-110
+    def match_features(self, keypoints1, keypoints2, descriptors1, descriptors2, with_points=False):
+        """5-arg overload returns matches; with_points=True is the 7-arg overload (also keypoints*_conv)."""
+        d1 = np.ascontiguousarray(descriptors1, dtype=np.float32)
+        d2 = np.ascontiguousarray(descriptors2, dtype=np.float32)
+        n1, n2 = d1.shape[0], d2.shape[0]
+        dim = d1.shape[1] if d1.ndim == 2 else 64
+        out = np.zeros(max(n1, 1), DMATCH_DTYPE)
+        n = C.c_int(0)
+        self._ck(self.lib.uvo_match_features(self.h, _p(d1), n1, _p(d2), n2, dim,
+                                             C.c_float(self.params.lowe_ratio), _p(out), C.byref(n)))
+        m = out[:n.value].copy()
+        if not with_points:
+            return m
+        p1 = np.stack([keypoints1["x"][m["queryIdx"]], keypoints1["y"][m["queryIdx"]]], -1).astype(np.float32)
+        p2 = np.stack([keypoints2["x"][m["trainIdx"]], keypoints2["y"][m["trainIdx"]]], -1).astype(np.float32)
+        return m, p1, p2
+
+    def knn_match2(self, descriptors1, descriptors2):
+        d1 = np.ascontiguousarray(descriptors1, dtype=np.float32)
+        d2 = np.ascontiguousarray(descriptors2, dtype=np.float32)
+        out = np.zeros((d1.shape[0], 2), DMATCH_DTYPE)
+        self._ck(self.lib.uvo_knn_match2(self.h, _p(d1), d1.shape[0], _p(d2), d2.shape[0], d1.shape[1], _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ VO_utility.h:116
+    def select_estimation_method(self, keypoints1_conv, keypoints2_conv):
+        p1 = np.ascontiguousarray(keypoints1_conv, np.float32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(keypoints2_conv, np.float32).reshape(-1, 2)
+        r = C.c_int(0)
+        self._ck(self.lib.uvo_select_estimation_method(self.h, _p(p1), _p(p2), p1.shape[0],
+                                                       int(self.params.distance), C.byref(r)))
+        return bool(r.value)
+
+    # ------------------------------------------------------------------ node-direct cv:: calls
+    def triangulatePoints(self, P1, P2, pts1, pts2):
+        P1 = _f64(P1, 12)
+        P2 = _f64(P2, 12)
+        a = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        out = np.empty((4, a.shape[0]), np.float32)
+        self._ck(self.lib.uvo_triangulate_points(self.h, _p(P1), _p(P2), _p(a), _p(b), a.shape[0], _p(out)))
+        return out
+
+    def solvePnPRansac(self, objectPoints, imagePoints, cameraMatrix, iterationsCount=None, reprojectionError=None,
+                       confidence=None):
+        X = np.ascontiguousarray(objectPoints, np.float64).reshape(-1, 3)
+        x = np.ascontiguousarray(imagePoints, np.float32).reshape(-1, 2)
+        n = X.shape[0]
+        rvec = np.zeros(3)
+        tvec = np.zeros(3)
+        inl = np.empty(max(n, 1), np.int32)
+        ni = C.c_int(0)
+        hyp = C.c_int(0)
+        p = self.params
+        self._ck(self.lib.uvo_solve_pnp_ransac(
+            self.h, _p(X), _p(x), n, _p(_k4(cameraMatrix)), int(iterationsCount or p.iterations_count),
+            C.c_float(reprojectionError if reprojectionError is not None else p.reprojection_error),
+            C.c_double(confidence if confidence is not None else p.confidence), _p(rvec), _p(tvec), _p(inl),
+            C.byref(ni), C.byref(hyp)))
+        return ni.value > 0, rvec, tvec, inl[:ni.value].copy(), hyp.value
+
+    # ------------------------------------------------------------------ VO_utility.h:102
+    def extract_3Dpoints(self, keypoints1_conv, keypoints2_conv, R1, t1, R2, t2, cameraMatrix1, cameraMatrix2,
+                         points4D):
+        a = np.ascontiguousarray(keypoints1_conv, np.float32).reshape(-1, 2)
+        b = np.ascontiguousarray(keypoints2_conv, np.float32).reshape(-1, 2)
+        n = a.shape[0]
+        p4 = np.ascontiguousarray(points4D, np.float32)
+        pts = np.empty((max(n, 1), 3), np.float64)
+        idx = np.empty(max(n, 1), np.int32)
+        m = C.c_int(0)
+        p = self.params
+        self._ck(self.lib.uvo_extract_3dpoints(self.h, _p(a), _p(b), n, _p(_f64(R1, 9)), _p(_f64(t1, 3)),
+                                               _p(_f64(R2, 9)), _p(_f64(t2, 3)), _p(_k4(cameraMatrix1)),
+                                               _p(_k4(cameraMatrix2)), _p(p4), C.c_double(p.reprojection_tolerance),
+                                               int(p.min_num_3dpoints), _p(pts), _p(idx), C.byref(m)))
+        return pts[:m.value].copy(), idx[:m.value].copy()
+
+    # ------------------------------------------------------------------ VO_utility.h:97-98
+    def compute_scale_factor(self, distance, good_prevCam_points, R, t):
+        """convert_3Dpoints_camera + compute_scale_factor (visual_odometry.h:365-368)."""
+        pts = np.ascontiguousarray(good_prevCam_points, np.float64).reshape(-1, 3)
+        sf = C.c_double(0)
+        self._ck(self.lib.uvo_scale_factor(self.h, _p(pts), pts.shape[0], _p(_f64(R, 9)), _p(_f64(t, 3)),
+                                           C.c_float(distance), C.byref(sf)))
+        return sf.value
+
+
+class StereoVO:
+    """Device-resident replay of visual_odometry_node::stereo_VO (visual_odometry.h:406-741)."""
+
+    def __init__(self, ctx, width, height, cam_left, cam_right, R_right, t_right, params=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.params = params or ctx.params
+        h = C.c_void_p()
+        ctx._ck(self.lib.uvo_stereo_create(ctx.h, width, height, C.byref(cam_left), C.byref(cam_right),
+                                           _p(_f64(R_right, 9)), _p(_f64(t_right, 3)), C.byref(self.params),
+                                           C.byref(h)))
+        self.h = h
+        self.width, self.height = width, height
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.uvo_stereo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def frame(self, left3, right3, dt):
+        """Host images (h x w x 3 u8) in, StereoResult out."""
+        l = np.ascontiguousarray(left3, np.uint8)
+        r = np.ascontiguousarray(right3, np.uint8)
+        res = L.StereoResult()
+        self.ctx._ck(self.lib.uvo_stereo_frame(self.h, _p(l), _p(r), C.c_size_t(3 * self.width), C.c_double(dt),
+                                               C.byref(res)))
+        return res
+
+    def frame_device(self, left_ptr, right_ptr, pitch, dt):
+        res = L.StereoResult()
+        self.ctx._ck(self.lib.uvo_stereo_frame_device(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                                      C.c_size_t(pitch), C.c_double(dt), C.byref(res)))
+        return res
+
+    def enqueue_device(self, left_ptr, right_ptr, pitch, dt):
+        self.ctx._ck(self.lib.uvo_stereo_enqueue_device(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                                        C.c_size_t(pitch), C.c_double(dt)))
+
+    def collect(self):
+        res = L.StereoResult()
+        self.ctx._ck(self.lib.uvo_stereo_collect(self.h, C.byref(res)))
+        return res
+
+    def last_keypoints(self, right=False):
+        cap = int(self.params.max_features)
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 64), np.float32)
+        n = C.c_int(0)
+        self.ctx._ck(self.lib.uvo_stereo_last_keypoints(self.h, int(right), _p(kps), _p(desc), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def last_matches(self, temporal=False):
+        cap = int(self.params.max_features)
+        m = np.zeros(cap, DMATCH_DTYPE)
+        n = C.c_int(0)
+        self.ctx._ck(self.lib.uvo_stereo_last_matches(self.h, int(temporal), _p(m), cap, C.byref(n)))
+        return m[:n.value].copy()
+
+    def last_inliers(self):
+        cap = int(self.params.max_features)
+        a = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        self.ctx._ck(self.lib.uvo_stereo_last_inliers(self.h, _p(a), cap, C.byref(n)))
+        return a[:n.value].copy()
+
+    def stage_ms(self):
+        ms = (C.c_float * L.UVO_N_STAGES)()
+        self.ctx._ck(self.lib.uvo_stereo_stage_ms(self.h, ms))
+        names = [self.lib.uvo_stage_name(i).decode() for i in range(L.UVO_N_STAGES)]
+        return dict(zip(names, list(ms)))

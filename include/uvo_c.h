@@ -1,0 +1,221 @@
+/*
+ * uvo_c.h -- C ABI of the B200-native UVO hot path (libuvo_b200.so).
+ *
+ * Drop-in boundary for the per-frame feature front-end and pose inner loop of team-ergo-unipi/ergo_uvo.
+ * The reference exposes this path as C++ free functions of the catkin library `uvo_libraries`
+ * (uvo_libraries/include/uvo_libraries/VO_utility.h:96-117) operating on cv::Mat / std::vector by value, plus three
+ * cv:: calls made by the node itself (uvo/include/visual_odometry.h:355,:631,:647,:673).  Each entry point below
+ * names the reference interface it replaces.  No OpenCV, ROS or torch types cross this boundary: plain pointers,
+ * sizes and POD structs only.  shim/VO_utility_shim.cpp shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns UVO_OK (0) or a negative uvo_status; uvo_last_error(ctx) gives the message;
+ *   - there is NO CPU fallback: without a CUDA device uvo_ctx_create fails with UVO_ERR_NO_DEVICE;
+ *   - "_host" pointers are host memory (pinned or pageable); the call copies H2D/D2H on the ctx stream and returns
+ *     after the stream is synchronised; handles (uvo_stereo) keep all per-frame state device-resident;
+ *   - images are row-major u8 with an explicit pitch in bytes; matrices are row-major double.
+ */
+#ifndef UVO_C_H
+#define UVO_C_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UVO_API __attribute__((visibility("default")))
+
+typedef enum {
+  UVO_OK = 0,
+  UVO_ERR_NO_DEVICE = -1,
+  UVO_ERR_CUDA = -2,
+  UVO_ERR_INVALID = -3,
+  UVO_ERR_CAPACITY = -4,
+  UVO_ERR_UNSUPPORTED = -5
+} uvo_status;
+
+typedef struct uvo_ctx uvo_ctx;
+
+/* cv::KeyPoint layout (28 B) -- VO_utility.h:100 `vector<KeyPoint>&` */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} uvo_keypoint;
+
+/* cv::DMatch layout (16 B) -- VO_utility.h:109 `vector<DMatch>&` */
+typedef struct {
+  int32_t queryIdx, trainIdx, imgIdx;
+  float distance;
+} uvo_dmatch;
+
+/* Camera model: the globals fx,fy,ccx,ccy,k1,k2,p1,p2 (VO_utility.h:31-36) after resize_camera_matrix
+ * (VO_utility.cpp:658-675) plus the new camera matrix it returns. */
+typedef struct {
+  double fx, fy, cx, cy;     /* cameraMatrix */
+  double k1, k2, p1, p2;     /* distortionCoeff */
+  double nfx, nfy, ncx, ncy; /* newCamMatrix (getOptimalNewCameraMatrix, alpha = 0) */
+} uvo_camera;
+
+/* The mutable parameter globals of VO_utility.h:38-89, read by the shim at call time. */
+typedef struct {
+  int32_t clahe;                  /* CLAHE_CORRECTION */
+  int32_t clip_limit;             /* CLIP_LIMIT */
+  int32_t distance;               /* DISTANCE */
+  double lowe_ratio;              /* LOWE_RATIO_THRESHOLD */
+  int32_t essential_method;       /* ESSENTIAL_OUTLIER_METHOD (4 = LMEDS, 8 = RANSAC) */
+  double essential_max_iters;     /* ESSENTIAL_MAX_ITERS */
+  double essential_confidence;    /* ESSENTIAL_CONFIDENCE */
+  double essential_threshold;     /* ESSENTIAL_THRESHOLD */
+  int32_t homography_method;      /* HOMOGRAPHY_OUTLIER_METHOD */
+  double homography_max_iters;    /* HOMOGRAPHY_MAX_ITERS */
+  double homography_confidence;   /* HOMOGRAPHY_CONFIDENCE */
+  double homography_threshold;    /* HOMOGRAPHY_THRESHOLD */
+  double homography_distance;     /* HOMOGRAPHY_DISTANCE */
+  double vpf_threshold;           /* VPF_THRESHOLD */
+  double reprojection_tolerance;  /* REPROJECTION_TOLERANCE */
+  int32_t min_num_features;       /* MIN_NUM_FEATURES */
+  int32_t min_num_3dpoints;       /* MIN_NUM_3DPOINTS */
+  int32_t min_num_inliers;        /* MIN_NUM_INLIERS */
+  int32_t iterations_count;       /* ITERATIONS_COUNT */
+  double reprojection_error;      /* REPROJECTION_ERROR_THRESHOLD */
+  double confidence;              /* CONFIDENCE */
+  int32_t pnp_method_flag;        /* PNP_METHOD_FLAG (1 = SOLVEPNP_EPNP, the only one implemented) */
+  int32_t surf_min_hessian;       /* SURF_MIN_HESSIAN */
+  int32_t surf_octaves;           /* SURF_OCTAVES_NUMBER (4) */
+  int32_t surf_octave_layers;     /* SURF_OCTAVES_LAYERS (3) */
+  int32_t surf_extended;          /* SURF_EXTENDED (0) */
+  int32_t surf_upright;           /* SURF_UPRIGHT */
+  int32_t max_features;           /* capacity of device keypoint buffers (not in the reference: it has no cap;
+                                     exceeding it returns UVO_ERR_CAPACITY instead of truncating) */
+} uvo_params;
+
+/* ---------------------------------------------------------------------------------------------------- context */
+/* One context per (GPU, stream).  `cuda_stream` may be NULL (the context creates its own non-blocking stream) or a
+ * cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream). */
+UVO_API int uvo_ctx_create(int device, void* cuda_stream, uvo_ctx** out);
+UVO_API void uvo_ctx_destroy(uvo_ctx* ctx);
+UVO_API const char* uvo_last_error(const uvo_ctx* ctx);
+UVO_API const char* uvo_version(void);
+UVO_API void* uvo_ctx_stream(uvo_ctx* ctx);
+UVO_API int uvo_ctx_synchronize(uvo_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+UVO_API int64_t uvo_ctx_launch_count(const uvo_ctx* ctx);
+/* fills every field with the shipped stereo (stereo!=0) or mono YAML values
+ * (uvo/config/stereo_VO_parameters.yaml:8-47, mono_VO_parameters.yaml:2-49) */
+UVO_API void uvo_default_params(int stereo, uvo_params* out);
+/* pinned host memory helpers for callers without a CUDA runtime of their own */
+UVO_API void* uvo_host_alloc(size_t bytes);
+UVO_API void uvo_host_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------------- K1-K3 */
+/* Mat get_image(const Mat&, const Mat&, const Mat&, const Mat&)  -- VO_utility.h:105, VO_utility.cpp:337-379.
+ * Native-size branch: cvtColor(RGB2GRAY) + undistort + optional CLAHE(8x8).  src is 3-channel interleaved u8. */
+UVO_API int uvo_get_image(uvo_ctx* ctx, const uint8_t* src3_host, int width, int height, size_t src_pitch,
+                          const uvo_camera* cam, int clahe, int clip_limit, uint8_t* dst_host, size_t dst_pitch);
+/* integral(img, sum, CV_32S) as built inside SURF::detectAndCompute (VO_utility.cpp:118): (h+1) x (w+1) int32 */
+UVO_API int uvo_integral(uvo_ctx* ctx, const uint8_t* gray_host, int width, int height, size_t pitch,
+                         int32_t* sum_host);
+
+/* ---------------------------------------------------------------------------------------------------- K4-K7 */
+/* void detect_features(Mat img, vector<KeyPoint>&, Mat& descriptors) -- VO_utility.h:100, VO_utility.cpp:114-119:
+ * SURF::create(hess, octaves, layers, extended, upright)->detectAndCompute.  Keypoints come back in OpenCV's order
+ * (response desc, size desc, octave desc, y desc, x asc); descriptors row-major n x 64 f32. */
+UVO_API int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray_host, int width, int height, size_t pitch,
+                                const uvo_params* prm, uvo_keypoint* kps_host, float* desc_host, int capacity,
+                                int* count);
+
+/* ---------------------------------------------------------------------------------------------------- K8 */
+/* void match_features(vector<KeyPoint>, vector<KeyPoint>, Mat d1, Mat d2, vector<DMatch>&) -- VO_utility.h:109-110,
+ * VO_utility.cpp:515-573: BFMatcher(NORM_L2).knnMatch(k=2) + Lowe ratio.  Matches in query order. `dim` = 64. */
+UVO_API int uvo_match_features(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2,
+                               int dim, float ratio, uvo_dmatch* matches_host, int* count);
+/* raw knnMatch(k=2) rows (2 per query; trainIdx = -1 where n2 < 2) */
+UVO_API int uvo_knn_match2(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2, int dim,
+                           uvo_dmatch* knn_host);
+
+/* ---------------------------------------------------------------------------------------------------- K9, K11, K12 */
+/* bool select_estimation_method(const vector<Point2f>&, const vector<Point2f>&) -- VO_utility.cpp:725-748 */
+UVO_API int uvo_select_estimation_method(uvo_ctx* ctx, const float* pts1_host, const float* pts2_host, int n,
+                                         int distance, int* use_essential);
+/* cv::triangulatePoints(P1, P2, pts1, pts2, points4D) -- visual_odometry.h:355, :631; out is 4 x n f32 */
+UVO_API int uvo_triangulate_points(uvo_ctx* ctx, const double P1[12], const double P2[12], const float* pts1_host,
+                                   const float* pts2_host, int n, float* points4d_host);
+/* void extract_3Dpoints(...) -- VO_utility.h:102, VO_utility.cpp:188-237. K1,K2 = fx,fy,cx,cy.
+ * out_points: M' x 3 f64, out_idx: M' i32 (capacity n each). */
+UVO_API int uvo_extract_3dpoints(uvo_ctx* ctx, const float* kp1_host, const float* kp2_host, int n,
+                                 const double R1[9], const double t1[3], const double R2[9], const double t2[3],
+                                 const double K1[4], const double K2[4], const float* points4d_host,
+                                 double reprojection_tolerance, int min_num_3dpoints, double* out_points_host,
+                                 int32_t* out_idx_host, int* count);
+/* convert_3Dpoints_camera + compute_scale_factor -- VO_utility.cpp:23-63 (visual_odometry.h:365-368) */
+UVO_API int uvo_scale_factor(uvo_ctx* ctx, const double* points_nx3_host, int n, const double R[9],
+                             const double t[3], float range, double* scale_factor);
+
+/* ---------------------------------------------------------------------------------------------------- K10 */
+/* cv::solvePnPRansac(X, x, K, 0-dist, rvec, tvec, false, iters, err, conf, inliers, SOLVEPNP_EPNP)
+ * -- visual_odometry.h:647-648.  X: n x 3 f64, x: n x 2 f32.  inliers ascending, *n_inliers = 0 on failure. */
+UVO_API int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X_host, const float* x_host, int n, const double K[4],
+                                 int iterations, float reprojection_error, double confidence, double rvec[3],
+                                 double tvec[3], int32_t* inliers_host, int* n_inliers, int* hyps_evaluated);
+/* findEssentialMat + extract_inliers + recoverPose -- VO_utility.cpp:147-149 */
+UVO_API int uvo_find_essential_mat(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n,
+                                   const double K[4], int method, double prob, double threshold, int max_iters,
+                                   double E[9], uint8_t* mask_host, int* hyps_evaluated);
+UVO_API int uvo_recover_pose(uvo_ctx* ctx, const double E[9], const float* p1_host, const float* p2_host, int n,
+                             const double K[4], double R[9], double t[3], uint8_t* mask_inout_host, int* n_good);
+/* findHomography -- VO_utility.cpp:152 */
+UVO_API int uvo_find_homography(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n, int method,
+                                double threshold, int max_iters, double confidence, double H[9],
+                                uint8_t* mask_host, int* hyps_evaluated);
+
+/* ---------------------------------------------------------------------------------------------------- frames */
+/* Device-resident replay of visual_odometry_node::stereo_VO's per-frame body (visual_odometry.h:526-740):
+ * one call per stereo pair; previous-frame state (after-stereo-match keypoints/descriptors, last t) lives on the
+ * GPU.  The first successful call initialises (visual_odometry.h:474-520) and reports initialised=1, valid=0. */
+typedef struct uvo_stereo uvo_stereo;
+
+typedef struct {
+  int32_t initialised;          /* vo_initialized */
+  int32_t valid;                /* successful_estimate.data */
+  int32_t n_left, n_right;      /* SURF keypoints */
+  int32_t n_stereo_matches;     /* results_match_curr.size() */
+  int32_t n_temporal_matches;   /* results_match_prev_curr.size() */
+  int32_t n_3d;                 /* good_prevCam_points.rows */
+  int32_t n_inliers;            /* inliers_idx.rows */
+  int32_t hyps_evaluated;       /* RANSAC iterations the reference loop would have run */
+  int32_t gate;                 /* 0 ok, else which "ASSUMING CONSTANT MOTION" branch fired (1..5) */
+  double rvec[3], tvec[3];      /* R_currCam_prevCam_Vec, t_currCam_prevCam (solvePnPRansac output) */
+  double t_prev_curr[3];        /* t_prevCam_currCam = -R^T t (stale on gate failure, visual_odometry.h:717) */
+  double velocity[3];           /* t_prevCam_currCam / dt (stereo_output_computation, :148-159) */
+} uvo_stereo_result;
+
+UVO_API int uvo_stereo_create(uvo_ctx* ctx, int width, int height, const uvo_camera* left, const uvo_camera* right,
+                              const double R_right[9], const double t_right[3], const uvo_params* prm,
+                              uvo_stereo** out);
+UVO_API void uvo_stereo_destroy(uvo_stereo* s);
+/* Host images in, 1 result struct out (H2D + D2H inside). */
+UVO_API int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3_host, const uint8_t* right3_host, size_t pitch,
+                             double dt, uvo_stereo_result* out);
+/* Same, images already resident in device memory (cudaMalloc'd, pitch bytes per row). */
+UVO_API int uvo_stereo_frame_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
+                                    size_t pitch, double dt, uvo_stereo_result* out);
+/* Asynchronous pair: enqueue a frame without waiting; results are collected in order. */
+UVO_API int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
+                                      size_t pitch, double dt);
+UVO_API int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out);
+/* Debug/parity taps of the last frame (device -> host copies of intermediate products). */
+UVO_API int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps_host, float* desc_host,
+                                      int capacity, int* count);
+UVO_API int uvo_stereo_last_matches(uvo_stereo* s, int temporal, uvo_dmatch* matches_host, int capacity,
+                                    int* count);
+UVO_API int uvo_stereo_last_inliers(uvo_stereo* s, int32_t* inliers_host, int capacity, int* count);
+/* per-stage device time of the last synchronous frame, in ms (CUDA events on the ctx stream) */
+#define UVO_N_STAGES 8
+UVO_API int uvo_stereo_stage_ms(uvo_stereo* s, float ms[UVO_N_STAGES]);
+UVO_API const char* uvo_stage_name(int i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UVO_C_H */

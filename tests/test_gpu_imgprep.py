@@ -1,0 +1,62 @@
+"""K1-K3 parity: CUDA get_image / integral vs the CPU oracle -- bit-exact (integer / exactly specified f32 work).
+Reference path: get_image, VO_utility.cpp:337-379; integral inside SURF::detectAndCompute, VO_utility.cpp:118."""
+import numpy as np
+import pytest
+
+from conftest import noise_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(w, h):
+    from tools import synth
+    K, D = synth.scaled_camera(synth.STEREO_YAML["left"], w, 1280)
+    K[1, 2] = h * 0.5 + 5
+    D = D.copy()
+    D[2:] = (0.001, -0.002)  # exercise the tangential terms too
+    return K, D, synth.optimal_new_camera_matrix(K, D, w, h)
+
+
+@pytest.mark.parametrize("w,h,clip", [(640, 480, 3), (1280, 1024, 8), (333, 251, 8), (336, 251, 3), (64, 48, 2)])
+def test_get_image_bit_exact(ctx, oracle, w, h, clip):
+    img = noise_image(h, w, seed=w + h, channels=3)
+    K, D, newK = _cams(w, h)
+    ctx.params.clahe, ctx.params.clip_limit = 1, clip
+    got = ctx.get_image(img, K, D, newK)
+    ref = oracle.get_image(img, K, D, newK, True, float(clip))
+    assert got.shape == ref.shape
+    assert int((got != ref).sum()) == 0
+
+
+def test_get_image_no_clahe(ctx, oracle):
+    w, h = 640, 480
+    img = noise_image(h, w, seed=5, channels=3)
+    K, D, newK = _cams(w, h)
+    ctx.params.clahe = 0
+    got = ctx.get_image(img, K, D, newK)
+    ctx.params.clahe = 1
+    assert int((got != oracle.get_image(img, K, D, newK, False, 0.0)).sum()) == 0
+
+
+def test_get_image_rejects_gray_input(ctx):
+    with pytest.raises(ValueError):
+        ctx.get_image(np.zeros((48, 64), np.uint8), np.eye(3), np.zeros(4), np.eye(3))
+
+
+@pytest.mark.parametrize("w,h", [(1280, 1024), (641, 479), (31, 7), (2448, 2048)])
+def test_integral_bit_exact(ctx, oracle, w, h):
+    g = noise_image(h, w, seed=11)
+    if w == 2448:
+        g[:] = 255  # maximum-size case: largest sums stay below 2^31
+    got = ctx.integral(g)
+    assert int((got != oracle.integral(g)).sum()) == 0
+
+
+def test_get_image_golden(ctx):
+    """committed cv2 fixture (tools/make_golden.py): gray+undistort+CLAHE of a 320x240 image"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "imgprep_320x240.npz"))
+    ctx.params.clahe, ctx.params.clip_limit = 1, int(z["clip"])
+    got = ctx.get_image(z["img"], z["K"], z["D"], z["newK"])
+    assert int((got != z["out"]).sum()) == 0
+    assert int((ctx.integral(z["out"]) != z["integral"]).sum()) == 0
