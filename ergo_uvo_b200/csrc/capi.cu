@@ -4,8 +4,25 @@
 #include <cstring>
 
 #include "capi_internal.cuh"
+#include "match.cuh"
+#include "pose.cuh"
 
 using namespace uvo;
+
+// bump allocator over one grow-only device buffer, for the stage-level calls below
+struct Arena {
+  uint8_t* base;
+  size_t off = 0, cap;
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += n * sizeof(T);
+    if (off > cap) throw InvalidArg{"internal: stage arena too small", UVO_ERR_INVALID};
+    return p;
+  }
+};
+
 
 extern "C" {
 
@@ -180,6 +197,214 @@ int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t 
       UVO_CUDA(cudaStreamSynchronize(c.stream));
     }
     *count = n;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ K8
+static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, float ratio,
+                       uvo_dmatch* matches, int* count, uvo_dmatch* knn_out) {
+  UVO_REQUIRE(dim == 64, "matcher: only 64-d SURF descriptors are supported");
+  UVO_REQUIRE(n1 >= 0 && n2 >= 0 && (n1 == 0 || d1) && (n2 == 0 || d2), "matcher: bad argument");
+  Ctx& c = ctx->c;
+  UVO_CUDA(cudaSetDevice(c.device));
+  if (count) *count = 0;
+  if (n1 == 0) return;
+  StageScratch& s = ctx->scratch;
+  s.bytes_a.ensure(sizeof(float) * 64 * (size_t)n1);
+  s.bytes_b.ensure(sizeof(float) * 64 * (size_t)std::max(n2, 1));
+  s.bytes_c.ensure(sizeof(Knn2) * (size_t)(MATCH_SPLITS + 1) * n1);
+  s.bytes_d.ensure(sizeof(uvo_dmatch) * (size_t)n1 + 16);
+  UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), d1, sizeof(float) * 64 * (size_t)n1, cudaMemcpyHostToDevice, c.stream));
+  if (n2 > 0)
+    UVO_CUDA(cudaMemcpyAsync(s.bytes_b.get(), d2, sizeof(float) * 64 * (size_t)n2, cudaMemcpyHostToDevice, c.stream));
+  MatchArgs a{};
+  a.q = (const float*)s.bytes_a.get();
+  a.t = (const float*)s.bytes_b.get();
+  a.nq = n1;
+  a.nt = n2;
+  a.ratio = ratio;
+  a.partial = (Knn2*)s.bytes_c.get();
+  a.knn = a.partial + (size_t)MATCH_SPLITS * n1;
+  a.n_matches = (int*)s.bytes_d.get();
+  a.matches = (uvo_dmatch*)(s.bytes_d.get() + 16);
+  launch_match(c, a);
+  ctx->pinned_counts.ensure(8);
+  UVO_CUDA(cudaMemcpyAsync(ctx->pinned_counts.p, a.n_matches, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  std::vector<Knn2> knn;
+  if (knn_out) {
+    knn.resize(n1);
+    UVO_CUDA(cudaMemcpyAsync(knn.data(), a.knn, sizeof(Knn2) * n1, cudaMemcpyDeviceToHost, c.stream));
+  }
+  UVO_CUDA(cudaStreamSynchronize(c.stream));
+  const int n = ctx->pinned_counts.p[0];
+  if (matches && n > 0) {
+    UVO_CUDA(cudaMemcpyAsync(matches, a.matches, sizeof(uvo_dmatch) * n, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  if (count) *count = n;
+  if (knn_out)
+    for (int i = 0; i < n1; i++) {
+      knn_out[2 * i] = uvo_dmatch{i, knn[i].i0, 0, knn[i].i0 >= 0 ? knn[i].d0 : 0.f};
+      knn_out[2 * i + 1] = uvo_dmatch{i, knn[i].i1, 0, knn[i].i1 >= 0 ? knn[i].d1 : 0.f};
+    }
+}
+
+int uvo_match_features(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, float ratio,
+                       uvo_dmatch* matches, int* count) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(matches && count, "uvo_match_features: null output");
+    match_host(ctx, d1, n1, d2, n2, dim, ratio, matches, count, nullptr);
+  });
+}
+
+int uvo_knn_match2(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, uvo_dmatch* knn) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(knn, "uvo_knn_match2: null output");
+    match_host(ctx, d1, n1, d2, n2, dim, 0.f, nullptr, nullptr, knn);
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ K11, K12, K10c
+int uvo_triangulate_points(uvo_ctx* ctx, const double P1[12], const double P2[12], const float* pts1,
+                           const float* pts2, int n, float* out4) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(P1 && P2 && n >= 0 && (n == 0 || (pts1 && pts2 && out4)), "uvo_triangulate_points: bad argument");
+    if (n == 0) return;
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    ctx->scratch.bytes_a.ensure((size_t)n * 8 * sizeof(float) + 1024);
+    Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+    float* d1 = ar.take<float>(2 * (size_t)n);
+    float* d2 = ar.take<float>(2 * (size_t)n);
+    float* d4 = ar.take<float>(4 * (size_t)n);
+    UVO_CUDA(cudaMemcpyAsync(d1, pts1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(d2, pts2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    TriangulateArgs a{};
+    memcpy(a.P1, P1, sizeof(a.P1));
+    memcpy(a.P2, P2, sizeof(a.P2));
+    a.pts1 = d1;
+    a.pts2 = d2;
+    a.n = n;
+    a.out4 = d4;
+    a.stride = n;
+    launch_triangulate(c, a);
+    UVO_CUDA(cudaMemcpyAsync(out4, d4, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int uvo_extract_3dpoints(uvo_ctx* ctx, const float* kp1, const float* kp2, int n, const double R1[9],
+                         const double t1[3], const double R2[9], const double t2[3], const double K1[4],
+                         const double K2[4], const float* p4, double tol, int min3d, double* out_pts,
+                         int32_t* out_idx, int* count) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(count && n >= 0 && R1 && t1 && R2 && t2 && K1 && K2, "uvo_extract_3dpoints: bad argument");
+    *count = 0;
+    if (n == 0) return;
+    UVO_REQUIRE(kp1 && kp2 && p4 && out_pts && out_idx, "uvo_extract_3dpoints: null buffer");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    ctx->scratch.bytes_a.ensure((size_t)n * 128 + 4096);
+    Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+    float* dk1 = ar.take<float>(2 * (size_t)n);
+    float* dk2 = ar.take<float>(2 * (size_t)n);
+    float* d4 = ar.take<float>(4 * (size_t)n);
+    Extract3dArgs a{};
+    a.kp1 = dk1;
+    a.kp2 = dk2;
+    a.p4 = d4;
+    a.stride = n;
+    a.n = n;
+    memcpy(a.R1, R1, sizeof(a.R1));
+    memcpy(a.t1, t1, sizeof(a.t1));
+    memcpy(a.R2, R2, sizeof(a.R2));
+    memcpy(a.t2, t2, sizeof(a.t2));
+    memcpy(a.K1, K1, sizeof(a.K1));
+    memcpy(a.K2, K2, sizeof(a.K2));
+    a.tol = tol;
+    a.min3d = min3d;
+    a.out_pts = ar.take<double>(3 * (size_t)n);
+    a.out_idx = ar.take<int32_t>(n);
+    a.tmp_pts = ar.take<double>(3 * (size_t)n);
+    a.tmp_idx = ar.take<int32_t>(n);
+    a.out_count = ar.take<int>(1);
+    UVO_CUDA(cudaMemcpyAsync(dk1, kp1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(dk2, kp2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(d4, p4, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, c.stream));
+    launch_extract3d(c, a);
+    ctx->pinned_counts.ensure(8);
+    UVO_CUDA(cudaMemcpyAsync(ctx->pinned_counts.p, a.out_count, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    const int m = ctx->pinned_counts.p[0];
+    if (m > 0) {
+      UVO_CUDA(cudaMemcpyAsync(out_pts, a.out_pts, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, c.stream));
+      UVO_CUDA(cudaMemcpyAsync(out_idx, a.out_idx, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, c.stream));
+      UVO_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    *count = m;
+  });
+}
+
+int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X, const float* x, int n, const double K[4], int iterations,
+                         float reproj_err, double confidence, double rvec[3], double tvec[3], int32_t* inliers,
+                         int* n_inliers, int* hyps_evaluated) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(K && rvec && tvec && n_inliers && n >= 0, "uvo_solve_pnp_ransac: bad argument");
+    UVO_REQUIRE(confidence > 0 && confidence < 1, "uvo_solve_pnp_ransac: confidence must be in (0,1)");  // CV_Assert
+    *n_inliers = 0;
+    if (hyps_evaluated) *hyps_evaluated = 0;
+    if (n < 5) return;  // OpenCV asserts npoints >= 4 and uses P3P for 4: outside the reference configuration
+    UVO_REQUIRE(X && x && inliers, "uvo_solve_pnp_ransac: null buffer");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    const int iters = std::max(iterations, 1);
+    ctx->scratch.bytes_a.ensure((size_t)n * 64 + (size_t)iters * 160 + 8192);
+    Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+    PnpArgs a{};
+    double* dX = ar.take<double>(3 * (size_t)n);
+    float* dx = ar.take<float>(2 * (size_t)n);
+    a.X = dX;
+    a.x = dx;
+    a.n = n;
+    memcpy(a.K, K, sizeof(a.K));
+    a.iterations = iterations;
+    a.reproj_err = reproj_err;
+    a.confidence = confidence;
+    a.min_points = -1;
+    a.result = ar.take<double>(8);
+    a.inliers = ar.take<int32_t>(n);
+    a.n_inliers = ar.take<int>(1);
+    a.hyps = ar.take<int>(1);
+    a.subsets = ar.take<int32_t>((size_t)iters * 5);
+    a.hyp_model = ar.take<double>((size_t)iters * 15);
+    a.hyp_good = ar.take<int>(iters);
+    a.xs = ar.take<float>(2 * (size_t)n);
+    a.Xf = ar.take<float>(3 * (size_t)n);
+    a.best = ar.take<int>(2);
+    UVO_CUDA(cudaMemcpyAsync(dX, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    launch_pnp_ransac(c, a);
+    double res[8];
+    int cnt[2];
+    UVO_CUDA(cudaMemcpyAsync(res, a.result, sizeof(double) * 7, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(&cnt[0], a.n_inliers, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(&cnt[1], a.hyps, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < 3; i++) {
+      rvec[i] = res[i];
+      tvec[i] = res[3 + i];
+    }
+    if (hyps_evaluated) *hyps_evaluated = cnt[1];
+    if (res[6] != 0.0 && cnt[0] > 0) {
+      UVO_CUDA(cudaMemcpyAsync(inliers, a.inliers, sizeof(int32_t) * cnt[0], cudaMemcpyDeviceToHost, c.stream));
+      UVO_CUDA(cudaStreamSynchronize(c.stream));
+      *n_inliers = cnt[0];
+    }
   });
 }
 

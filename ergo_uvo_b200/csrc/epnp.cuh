@@ -1,0 +1,335 @@
+// epnp.cuh -- EPnP (Lepetit, Moreno-Noguer, Fua) as OpenCV's calib3d/src/epnp.cpp runs it inside
+// cv::solvePnP(..., SOLVEPNP_EPNP), split into point-independent pieces (small dense algebra on one thread) and
+// per-point pieces, so that the same code serves the 5-point RANSAC kernel (one hypothesis per thread) and the
+// block-cooperative refit on all inliers.  Replaces the solver behind cv::solvePnPRansac
+// (reference visual_odometry.h:647-648).
+#pragma once
+#include "linalg.cuh"
+
+namespace uvo {
+
+struct EpnpCam {
+  double fu, fv, uc, vc;
+};
+
+__device__ __forceinline__ double dot3(const double* a, const double* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+__device__ __forceinline__ double dist2_3(const double* a, const double* b) {
+  return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+}
+
+// choose_control_points + the inverse used by compute_barycentric_coordinates.
+// c0 = centroid, cov = sum (p-c0)(p-c0)^T over the n points.
+__device__ inline void epnp_control_points(const double c0[3], const double cov[9], int n, double cws[4][3],
+                                           double ci[9]) {
+  double dc[3], Vt[9];
+  jacobi_svd<3>(cov, 3, 3, dc, nullptr, Vt);
+  for (int j = 0; j < 3; j++) cws[0][j] = c0[j];
+  for (int i = 1; i < 4; i++) {
+    const double k = sqrt(dc[i - 1] / n);
+    for (int j = 0; j < 3; j++) cws[i][j] = cws[0][j] + k * Vt[(i - 1) * 3 + j];
+  }
+  double cc[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 1; j < 4; j++) cc[3 * i + j - 1] = cws[j][i] - cws[0][i];
+  svd_invert3(cc, ci);
+}
+
+__device__ __forceinline__ void epnp_alphas(const double p[3], const double cws[4][3], const double ci[9],
+                                            double a[4]) {
+  for (int j = 0; j < 3; j++)
+    a[1 + j] = ci[3 * j] * (p[0] - cws[0][0]) + ci[3 * j + 1] * (p[1] - cws[0][1]) + ci[3 * j + 2] * (p[2] - cws[0][2]);
+  a[0] = 1.0f - a[1] - a[2] - a[3];
+}
+
+__device__ __forceinline__ void epnp_m_rows(const double a[4], double u, double v, const EpnpCam& cam, double M1[12],
+                                            double M2[12]) {
+  for (int k = 0; k < 4; k++) {
+    M1[3 * k] = a[k] * cam.fu;
+    M1[3 * k + 1] = 0.0;
+    M1[3 * k + 2] = a[k] * (cam.uc - u);
+    M2[3 * k] = 0.0;
+    M2[3 * k + 1] = a[k] * cam.fv;
+    M2[3 * k + 2] = a[k] * (cam.vc - v);
+  }
+}
+
+// Householder QR least squares, a transcription of epnp::qr_solve (6 x 4)
+__device__ inline void epnp_qr_solve(double* A, int nr, int nc, double* b, double* X) {
+  double A1[6], A2[6];
+  double* ppAkk = A;
+  for (int k = 0; k < nc; k++) {
+    double* ppAik1 = ppAkk;
+    double eta = fabs(*ppAik1);
+    for (int i = k + 1; i < nr; i++) {
+      const double elt = fabs(*ppAik1);
+      if (eta < elt) eta = elt;
+      ppAik1 += nc;
+    }
+    if (eta == 0) {
+      A1[k] = A2[k] = 0.0;
+      return;
+    }
+    double* ppAik2 = ppAkk;
+    double sum2 = 0.0;
+    const double inv_eta = 1. / eta;
+    for (int i = k; i < nr; i++) {
+      *ppAik2 *= inv_eta;
+      sum2 += *ppAik2 * *ppAik2;
+      ppAik2 += nc;
+    }
+    double sigma = sqrt(sum2);
+    if (*ppAkk < 0) sigma = -sigma;
+    *ppAkk += sigma;
+    A1[k] = sigma * *ppAkk;
+    A2[k] = -eta * sigma;
+    for (int j = k + 1; j < nc; j++) {
+      double* ppAik = ppAkk;
+      double sum = 0;
+      for (int i = k; i < nr; i++) {
+        sum += *ppAik * ppAik[j - k];
+        ppAik += nc;
+      }
+      const double tau = sum / A1[k];
+      ppAik = ppAkk;
+      for (int i = k; i < nr; i++) {
+        ppAik[j - k] -= tau * *ppAik;
+        ppAik += nc;
+      }
+    }
+    ppAkk += nc + 1;
+  }
+  double* ppAjj = A;
+  for (int j = 0; j < nc; j++) {
+    double* ppAij = ppAjj;
+    double tau = 0;
+    for (int i = j; i < nr; i++) {
+      tau += *ppAij * b[i];
+      ppAij += nc;
+    }
+    tau /= A1[j];
+    ppAij = ppAjj;
+    for (int i = j; i < nr; i++) {
+      b[i] -= tau * *ppAij;
+      ppAij += nc;
+    }
+    ppAjj += nc + 1;
+  }
+  X[nc - 1] = b[nc - 1] / A2[nc - 1];
+  for (int i = nc - 2; i >= 0; i--) {
+    double* ppAij = A + i * nc + (i + 1);
+    double sum = 0;
+    for (int j = i + 1; j < nc; j++) {
+      sum += *ppAij * X[j];
+      ppAij++;
+    }
+    X[i] = (b[i] - sum) / A2[i];
+  }
+}
+
+// From MtM (12x12) and the control points: the null-space rows `ut` (12x12, rows sorted by descending singular
+// value) and the three beta candidates (N = 1, 2, 3 approximations, each refined by 5 Gauss-Newton steps).
+__device__ inline void epnp_betas(const double* mtm, const double cws[4][3], double* ut, double Betas[3][4]) {
+  double d[12];
+  jacobi_svd<12>(mtm, 12, 12, d, nullptr, ut);
+  // compute_L_6x10
+  double l[60], rho[6];
+  {
+    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+    double dv[4][6][3];
+    for (int i = 0; i < 4; i++) {
+      int a = 0, b = 1;
+      for (int j = 0; j < 6; j++) {
+        dv[i][j][0] = v[i][3 * a] - v[i][3 * b];
+        dv[i][j][1] = v[i][3 * a + 1] - v[i][3 * b + 1];
+        dv[i][j][2] = v[i][3 * a + 2] - v[i][3 * b + 2];
+        b++;
+        if (b > 3) {
+          a++;
+          b = a + 1;
+        }
+      }
+    }
+    for (int i = 0; i < 6; i++) {
+      double* row = l + 10 * i;
+      row[0] = dot3(dv[0][i], dv[0][i]);
+      row[1] = 2.0f * dot3(dv[0][i], dv[1][i]);
+      row[2] = dot3(dv[1][i], dv[1][i]);
+      row[3] = 2.0f * dot3(dv[0][i], dv[2][i]);
+      row[4] = 2.0f * dot3(dv[1][i], dv[2][i]);
+      row[5] = dot3(dv[2][i], dv[2][i]);
+      row[6] = 2.0f * dot3(dv[0][i], dv[3][i]);
+      row[7] = 2.0f * dot3(dv[1][i], dv[3][i]);
+      row[8] = 2.0f * dot3(dv[2][i], dv[3][i]);
+      row[9] = dot3(dv[3][i], dv[3][i]);
+    }
+  }
+  rho[0] = dist2_3(cws[0], cws[1]);
+  rho[1] = dist2_3(cws[0], cws[2]);
+  rho[2] = dist2_3(cws[0], cws[3]);
+  rho[3] = dist2_3(cws[1], cws[2]);
+  rho[4] = dist2_3(cws[1], cws[3]);
+  rho[5] = dist2_3(cws[2], cws[3]);
+  for (int which = 1; which <= 3; which++) {
+    double* betas = Betas[which - 1];
+    const int cols1[4] = {0, 1, 3, 6}, cols23[5] = {0, 1, 2, 3, 4};
+    const int nc = which == 1 ? 4 : which == 2 ? 3 : 5;
+    double A[30], x[5];
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < nc; j++) A[i * nc + j] = l[10 * i + (which == 1 ? cols1[j] : cols23[j])];
+    svd_solve6(A, 6, nc, rho, x);
+    if (which == 1) {
+      if (x[0] < 0) {
+        betas[0] = sqrt(-x[0]);
+        betas[1] = -x[1] / betas[0];
+        betas[2] = -x[2] / betas[0];
+        betas[3] = -x[3] / betas[0];
+      } else {
+        betas[0] = sqrt(x[0]);
+        betas[1] = x[1] / betas[0];
+        betas[2] = x[2] / betas[0];
+        betas[3] = x[3] / betas[0];
+      }
+    } else {
+      if (x[0] < 0) {
+        betas[0] = sqrt(-x[0]);
+        betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+      } else {
+        betas[0] = sqrt(x[0]);
+        betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
+      }
+      if (x[1] < 0) betas[0] = -betas[0];
+      betas[2] = which == 3 ? x[3] / betas[0] : 0.0;
+      betas[3] = 0.0;
+    }
+    // gauss_newton, 5 iterations
+    for (int it = 0; it < 5; it++) {
+      double GA[24], gb[6], gx[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 6; i++) {
+        const double* rowL = l + i * 10;
+        double* rowA = GA + i * 4;
+        rowA[0] = 2 * rowL[0] * betas[0] + rowL[1] * betas[1] + rowL[3] * betas[2] + rowL[6] * betas[3];
+        rowA[1] = rowL[1] * betas[0] + 2 * rowL[2] * betas[1] + rowL[4] * betas[2] + rowL[7] * betas[3];
+        rowA[2] = rowL[3] * betas[0] + rowL[4] * betas[1] + 2 * rowL[5] * betas[2] + rowL[8] * betas[3];
+        rowA[3] = rowL[6] * betas[0] + rowL[7] * betas[1] + rowL[8] * betas[2] + 2 * rowL[9] * betas[3];
+        gb[i] = rho[i] - (rowL[0] * betas[0] * betas[0] + rowL[1] * betas[0] * betas[1] + rowL[2] * betas[1] * betas[1] +
+                          rowL[3] * betas[0] * betas[2] + rowL[4] * betas[1] * betas[2] + rowL[5] * betas[2] * betas[2] +
+                          rowL[6] * betas[0] * betas[3] + rowL[7] * betas[1] * betas[3] + rowL[8] * betas[2] * betas[3] +
+                          rowL[9] * betas[3] * betas[3]);
+      }
+      epnp_qr_solve(GA, 6, 4, gb, gx);
+      for (int i = 0; i < 4; i++) betas[i] += gx[i];
+    }
+  }
+}
+
+__device__ inline void epnp_ccs(const double betas[4], const double* ut, double ccs[4][3]) {
+  for (int i = 0; i < 4; i++) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
+  for (int i = 0; i < 4; i++) {
+    const double* v = ut + 12 * (11 - i);
+    for (int j = 0; j < 4; j++)
+      for (int k = 0; k < 3; k++) ccs[j][k] += betas[i] * v[3 * j + k];
+  }
+}
+
+__device__ __forceinline__ void epnp_pc(const double a[4], const double ccs[4][3], double sign, double pc[3]) {
+  for (int j = 0; j < 3; j++) pc[j] = sign * (a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j]);
+}
+
+// estimate_R_and_t from the centroids and ABt = sum (pc-pc0)(pw-pw0)^T
+__device__ inline void epnp_rt_from_abt(const double abt[9], const double pc0[3], const double pw0[3], double R[9],
+                                        double t[3]) {
+  double d[3], U[9], Vt[9];
+  jacobi_svd<3>(abt, 3, 3, d, U, Vt);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[i * 3 + j] = U[i * 3] * Vt[j] + U[i * 3 + 1] * Vt[3 + j] + U[i * 3 + 2] * Vt[6 + j];
+  const double det = R[0] * R[4] * R[8] + R[1] * R[5] * R[6] + R[2] * R[3] * R[7] - R[2] * R[4] * R[6] -
+                     R[1] * R[3] * R[8] - R[0] * R[5] * R[7];
+  if (det < 0) {
+    R[6] = -R[6];
+    R[7] = -R[7];
+    R[8] = -R[8];
+  }
+  t[0] = pc0[0] - dot3(R + 0, pw0);
+  t[1] = pc0[1] - dot3(R + 3, pw0);
+  t[2] = pc0[2] - dot3(R + 6, pw0);
+}
+
+__device__ __forceinline__ double epnp_reproj1(const double R[9], const double t[3], const double pw[3], double u,
+                                               double v, const EpnpCam& cam) {
+  const double Xc = dot3(R + 0, pw) + t[0], Yc = dot3(R + 3, pw) + t[1], inv_Zc = 1.0 / (dot3(R + 6, pw) + t[2]);
+  const double ue = cam.uc + cam.fu * Xc * inv_Zc, ve = cam.vc + cam.fv * Yc * inv_Zc;
+  return sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
+}
+
+// Whole EPnP for a small set held by one thread (n <= 5): the RANSAC minimal solver.
+// pws: n x 3, us: n x 2 (pixel coordinates as epnp::init_points builds them).
+__device__ inline void epnp_small(const double* pws, const double* us, int n, const EpnpCam& cam, double R[9],
+                                  double t[3]) {
+  double c0[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < 3; j++) c0[j] += pws[3 * i + j];
+  for (int j = 0; j < 3; j++) c0[j] /= n;
+  double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    const double d[3] = {pws[3 * i] - c0[0], pws[3 * i + 1] - c0[1], pws[3 * i + 2] - c0[2]};
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) cov[a * 3 + b] += d[a] * d[b];
+  }
+  double cws[4][3], ci[9];
+  epnp_control_points(c0, cov, n, cws, ci);
+  double alphas[5][4];
+  double mtm[144];
+  for (int i = 0; i < 144; i++) mtm[i] = 0;
+  for (int i = 0; i < n; i++) {
+    epnp_alphas(pws + 3 * i, cws, ci, alphas[i]);
+    double M1[12], M2[12];
+    epnp_m_rows(alphas[i], us[2 * i], us[2 * i + 1], cam, M1, M2);
+    for (int a = 0; a < 12; a++)
+      for (int b = 0; b < 12; b++) mtm[a * 12 + b] += M1[a] * M1[b] + M2[a] * M2[b];
+  }
+  double ut[144], Betas[3][4];
+  epnp_betas(mtm, cws, ut, Betas);
+  double best_err = 0;
+  for (int w = 0; w < 3; w++) {
+    double ccs[4][3], pcs[5][3];
+    epnp_ccs(Betas[w], ut, ccs);
+    for (int i = 0; i < n; i++) epnp_pc(alphas[i], ccs, 1.0, pcs[i]);
+    if (pcs[0][2] < 0.0)  // solve_for_sign
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < 3; j++) pcs[i][j] = -pcs[i][j];
+    double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < 3; j++) {
+        pc0[j] += pcs[i][j];
+        pw0[j] += pws[3 * i + j];
+      }
+    for (int j = 0; j < 3; j++) {
+      pc0[j] /= n;
+      pw0[j] /= n;
+    }
+    double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+      const double* pw = pws + 3 * i;
+      for (int j = 0; j < 3; j++) {
+        abt[3 * j] += (pcs[i][j] - pc0[j]) * (pw[0] - pw0[0]);
+        abt[3 * j + 1] += (pcs[i][j] - pc0[j]) * (pw[1] - pw0[1]);
+        abt[3 * j + 2] += (pcs[i][j] - pc0[j]) * (pw[2] - pw0[2]);
+      }
+    }
+    double Rw[9], tw[3];
+    epnp_rt_from_abt(abt, pc0, pw0, Rw, tw);
+    double sum2 = 0.0;
+    for (int i = 0; i < n; i++) sum2 += epnp_reproj1(Rw, tw, pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
+    const double err = sum2 / n;
+    // N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
+    if (w == 0 || err < best_err) {
+      best_err = err;
+      for (int i = 0; i < 9; i++) R[i] = Rw[i];
+      for (int i = 0; i < 3; i++) t[i] = tw[i];
+    }
+  }
+}
+
+}  // namespace uvo

@@ -1,0 +1,79 @@
+// pose.cuh -- K9-K12: triangulation, 3-D point filtering, PnP-RANSAC (EPnP), scale helpers.
+#pragma once
+#include "common.cuh"
+#include "match.cuh"
+
+namespace uvo {
+
+// raw outputs of cv::RNG(0xFFFFFFFFFFFFFFFF): RANSACPointSetRegistrator::run re-seeds with the same constant on
+// every call, so the 32-bit stream is a fixed table; only `% count` and the duplicate redraws are data dependent.
+constexpr int RNG_TABLE_SIZE = 1 << 18;
+const uint32_t* rng_table_device(Ctx& c);  // lazily uploaded, one per device
+
+struct TriangulateArgs {
+  double P1[12], P2[12];
+  const float* pts1;   // n x 2 (used when matches == nullptr)
+  const float* pts2;
+  // gather mode (stereo frame): point i = kps1[matches[i].queryIdx].pt / kps2[matches[i].queryIdx].pt
+  const uvo_dmatch* matches;
+  const uvo_keypoint* kps1;
+  const uvo_keypoint* kps2;
+  const int* n_dev;    // device count (nullable)
+  int n;               // count or capacity
+  float* out4;         // 4 x stride f32
+  int stride;          // row stride of out4 (>= n)
+  float* pts1_out;     // optional: gathered points (n x 2) for later stages
+  float* pts2_out;
+};
+void launch_triangulate(Ctx& c, const TriangulateArgs& a);
+
+struct Extract3dArgs {
+  const float* kp1;     // n x 2
+  const float* kp2;
+  const float* p4;      // 4 x stride
+  int stride;
+  const int* n_dev;
+  int n;
+  double R1[9], t1[3], R2[9], t2[3], K1[4], K2[4];
+  double tol;
+  int min3d;
+  double* out_pts;      // n x 3
+  int32_t* out_idx;     // n
+  int* out_count;       // device
+  // scratch (n each)
+  double* tmp_pts;
+  int32_t* tmp_idx;
+};
+void launch_extract3d(Ctx& c, const Extract3dArgs& a);
+
+struct PnpArgs {
+  const double* X;       // n x 3 f64 (down-cast to f32 inside, as solvePnPRansac does)
+  const float* x;        // n x 2 f32 (used when x_idx == nullptr)
+  // gather mode: x[i] = kps[matches[idx[i]].trainIdx].pt
+  const int32_t* x_idx;
+  const uvo_dmatch* matches;
+  const uvo_keypoint* kps;
+  const int* n_dev;
+  int n;                 // count or capacity
+  double K[4];
+  int iterations;
+  float reproj_err;
+  double confidence;
+  int min_points;        // gate: run only if n > min_points (stereo frame: MIN_NUM_3DPOINTS); -1 = always
+  // outputs (device)
+  double* result;        // [0..2] rvec, [3..5] tvec, [6] ok
+  int32_t* inliers;      // n
+  int* n_inliers;        // device
+  int* hyps;             // device: iterations the sequential loop would have run
+  // scratch
+  int32_t* subsets;      // iterations x 5
+  double* hyp_model;     // iterations x 15 (R 9, t 3, rvec 3)
+  int* hyp_good;         // iterations
+  float* xs;             // n x 2 gathered image points
+  float* Xf;             // n x 3 f32 object points
+  int* best;             // [0] best hypothesis, [1] best count
+};
+void launch_pnp_ransac(Ctx& c, const PnpArgs& a);
+size_t pnp_scratch_bytes(int n, int iterations);
+
+}  // namespace uvo

@@ -17,15 +17,13 @@
 
 namespace uvo {
 
-// getGaussianKernel(13, 2.5, CV_32F) and getGaussianKernel(20, 3.3, CV_32F) (values checked against cv2 and the
+// getGaussianKernel(13, 2.5f, CV_32F) and getGaussianKernel(20, (double)3.3f, CV_32F) -- SURF_DESC_SIGMA is a float
+// constant in OpenCV, so sigma is 3.2999999523..., not 3.3 (values checked against cv2 and the
 // oracle in tests/test_oracle_surf.py::test_gaussian_tables)
 static const float kGOri[13] = {0x1.282748p-7f,  0x1.64ff86p-6f, 0x1.6eb6e4p-5f, 0x1.40ff98p-4f, 0x1.dedf96p-4f,
                                 0x1.30623ap-3f,  0x1.49bc24p-3f, 0x1.30623ap-3f, 0x1.dedf96p-4f, 0x1.40ff98p-4f,
                                 0x1.6eb6e4p-5f,  0x1.64ff86p-6f, 0x1.282748p-7f};
-static const float kGDesc[20] = {0x1.f6898ep-10f, 0x1.1f18f6p-8f, 0x1.2b4118p-7f, 0x1.1c8ee8p-6f, 0x1.edafecp-6f,
-                                 0x1.86ae6p-5f,   0x1.1a0a9cp-4f, 0x1.737ecap-4f, 0x1.be6398p-4f, 0x1.eef842p-4f,
-                                 0x1.eef842p-4f,  0x1.be6398p-4f, 0x1.737ecap-4f, 0x1.1a0a9cp-4f, 0x1.86ae6p-5f,
-                                 0x1.edafecp-6f,  0x1.1c8ee8p-6f, 0x1.2b4118p-7f, 0x1.1f18f6p-8f, 0x1.f6898ep-10f};
+static const float kGDesc[20] = {0x1.f6898ap-10f, 0x1.1f18f4p-8f, 0x1.2b4116p-7f, 0x1.1c8ee8p-6f, 0x1.edafecp-6f, 0x1.86ae60p-5f, 0x1.1a0a9cp-4f, 0x1.737ecap-4f, 0x1.be639ap-4f, 0x1.eef842p-4f, 0x1.eef842p-4f, 0x1.be639ap-4f, 0x1.737ecap-4f, 0x1.1a0a9cp-4f, 0x1.86ae60p-5f, 0x1.edafecp-6f, 0x1.1c8ee8p-6f, 0x1.2b4116p-7f, 0x1.1f18f4p-8f, 0x1.f6898ap-10f};
 
 __constant__ float c_DW[400];      // DW[i*20+j] = G_desc[i]*G_desc[j]
 __constant__ float c_aptw[128];    // orientation sample weights (113 used)

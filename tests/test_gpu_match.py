@@ -1,0 +1,76 @@
+"""K8 parity: CUDA brute-force kNN(k=2) + Lowe ratio vs the CPU oracle and the committed cv2 fixture -- indices,
+order, distances and match lists bit-exact.  Reference path: match_features, VO_utility.cpp:515-573."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _descs(n, seed, dup_from=None, noise=0.03):
+    rs = np.random.RandomState(seed)
+    d = np.abs(rs.randn(n, 64)).astype(np.float32)
+    if dup_from is not None:
+        m = min(n, len(dup_from)) // 2
+        idx = rs.permutation(len(dup_from))[:m]
+        d[:m] = dup_from[idx] + noise * rs.randn(m, 64).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return d
+
+
+def test_knn_golden_cv2(ctx):
+    z = np.load(os.path.join(GOLD, "matcher_300x400.npz"))
+    k = ctx.knn_match2(z["q"], z["t"])
+    assert np.array_equal(k["trainIdx"], z["idx"])
+    assert np.array_equal(k["distance"].view(np.uint32), z["dist"].view(np.uint32))
+    assert np.array_equal(k["queryIdx"][:, 0], np.arange(300))
+
+
+@pytest.mark.parametrize("nq,nt,ratio", [(4096, 4096, 0.8), (1000, 3333, 0.7), (8192, 8192, 0.7), (129, 65, 0.8), (5, 2, 0.9)])
+def test_match_features_vs_oracle(ctx, oracle, nq, nt, ratio):
+    t = _descs(nt, 1)
+    q = _descs(nq, 2, dup_from=t)
+    ctx.params.lowe_ratio = ratio
+    m = ctx.match_features(None, None, q, t)
+    mo = oracle.match_features(q, t, ratio)
+    assert len(mo) > 0 or nq < 10
+    assert m.tobytes() == mo.tobytes()
+    k = ctx.knn_match2(q, t)
+    ko = oracle.knn2(q, t)
+    assert k.tobytes() == ko.tobytes()
+    ctx.params.lowe_ratio = 0.8
+
+
+def test_match_ties_pick_lower_train_index(ctx, oracle):
+    t = _descs(300, 3)
+    t[200] = t[10]
+    t[250] = t[10]
+    q = t[[10, 11, 12]].copy()
+    k = ctx.knn_match2(q, t)
+    assert list(k["trainIdx"][0]) == [10, 200]
+    assert k.tobytes() == oracle.knn2(q, t).tobytes()
+
+
+def test_match_edge_cases(ctx, oracle):
+    q = _descs(10, 4)
+    assert len(ctx.match_features(None, None, q[:0], q)) == 0          # empty query set
+    assert len(ctx.match_features(None, None, q, q[:0])) == 0          # empty train set
+    assert len(ctx.match_features(None, None, q, q[:1])) == 0          # 1 train row: reference UB, defined as no match
+    k = ctx.knn_match2(q, q[:1])
+    assert np.all(k["trainIdx"][:, 0] == 0) and np.all(k["trainIdx"][:, 1] == -1)
+
+
+def test_match_7arg_overload_points(ctx, oracle):
+    """7-arg overload (VO_utility.cpp:551-573) also returns the matched Point2f pairs"""
+    import ergo_uvo_b200 as U
+    t = _descs(500, 5)
+    q = _descs(400, 6, dup_from=t)
+    rs = np.random.RandomState(0)
+    k1 = np.zeros(400, U.KEYPOINT_DTYPE)
+    k2 = np.zeros(500, U.KEYPOINT_DTYPE)
+    k1["x"], k1["y"] = rs.rand(400) * 640, rs.rand(400) * 480
+    k2["x"], k2["y"] = rs.rand(500) * 640, rs.rand(500) * 480
+    m, p1, p2 = ctx.match_features(k1, k2, q, t, with_points=True)
+    assert np.array_equal(p1[:, 0], k1["x"][m["queryIdx"]]) and np.array_equal(p2[:, 1], k2["y"][m["trainIdx"]])
