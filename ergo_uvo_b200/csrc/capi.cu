@@ -288,6 +288,7 @@ int uvo_triangulate_points(uvo_ctx* ctx, const double P1[12], const double P2[12
     a.pts1 = d1;
     a.pts2 = d2;
     a.n = n;
+    a.min_points = -1;
     a.out4 = d4;
     a.stride = n;
     launch_triangulate(c, a);
@@ -346,6 +347,60 @@ int uvo_extract_3dpoints(uvo_ctx* ctx, const float* kp1, const float* kp2, int n
       UVO_CUDA(cudaStreamSynchronize(c.stream));
     }
     *count = m;
+  });
+}
+
+int uvo_select_estimation_method(uvo_ctx* ctx, const float* p1, const float* p2, int n, int distance,
+                                 int* use_essential) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(use_essential && n >= 0 && (n == 0 || (p1 && p2)), "uvo_select_estimation_method: bad argument");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    ctx->scratch.bytes_a.ensure((size_t)std::max(n, 1) * 32 + 1024);
+    Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+    float* d1 = ar.take<float>(2 * (size_t)std::max(n, 1));
+    float* d2 = ar.take<float>(2 * (size_t)std::max(n, 1));
+    double* disp = ar.take<double>(std::max(n, 1));
+    double* out = ar.take<double>(4);
+    if (n > 0) {
+      UVO_CUDA(cudaMemcpyAsync(d1, p1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+      UVO_CUDA(cudaMemcpyAsync(d2, p2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    }
+    launch_displacements(c, d1, d2, n, disp);
+    launch_median(c, disp, nullptr, n, out);
+    double med = 0;
+    UVO_CUDA(cudaMemcpyAsync(&med, out, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    *use_essential = med < (double)distance ? 0 : 1;  // "BASELINE IS TOO LOW. USING HOMOGRAPHY!" when below
+  });
+}
+
+int uvo_scale_factor(uvo_ctx* ctx, const double* pts, int n, const double R[9], const double t[3], float range,
+                     double* scale_factor) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(scale_factor && R && t && n >= 0 && (n == 0 || pts), "uvo_scale_factor: bad argument");
+    *scale_factor = 0.0;
+    if (n == 0) return;
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    ctx->scratch.bytes_a.ensure((size_t)n * 40 + 1024);
+    Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+    double* dp = ar.take<double>(3 * (size_t)n);
+    double* dz = ar.take<double>(n);
+    double* out = ar.take<double>(4);
+    int* cnt = ar.take<int>(1);
+    UVO_CUDA(cudaMemcpyAsync(dp, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
+    launch_front_z(c, dp, n, R, t, dz, cnt);
+    launch_median(c, dz, cnt, n, out);
+    double med = 0;
+    int m = 0;
+    UVO_CUDA(cudaMemcpyAsync(&med, out, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(&m, cnt, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    // compute_scale_factor(float distance, ...): distance / Zmedian, 0.0 when no point is in front of the camera
+    *scale_factor = m > 0 ? (double)range / med : 0.0;
   });
 }
 

@@ -8,6 +8,7 @@
 // niters = RANSACUpdateNumIters(...)}` -- over the per-hypothesis inlier counts to find the hypothesis the CPU loop
 // would have kept and the iteration at which it would have stopped.  Hypotheses past that point are wasted work,
 // never a different answer.
+#include <cstring>
 #include <mutex>
 
 #include "epnp.cuh"
@@ -77,8 +78,11 @@ __device__ __forceinline__ int ordered_slot(bool keep, int* s_warp /*32*/, int* 
 
 // ------------------------------------------------------------------------------------------------ K11 triangulate
 __global__ void __launch_bounds__(64) k_triangulate(const __grid_constant__ TriangulateArgs a) {
-  const int n = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  int n = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+  if (a.gate_dev && *a.gate_dev == 0) n = 0;
+  if (a.min_points >= 0 && n <= a.min_points) n = 0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && a.n_out) *a.n_out = n;
   if (i >= n) return;
   float p1[2], p2[2];
   if (a.matches) {
@@ -577,6 +581,93 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     for (int i = 0; i < 3; i++) a.result[3 + i] = bestt[i];
     a.result[6] = 1.0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ K9 / scale helpers
+// rank selection: element i has rank #{j : v_j < v_i or (v_j == v_i and j < i)}; ranks are a permutation, so exactly
+// one element lands on each middle rank.  O(n^2) compares spread over the grid; n is a match count (<= capacity).
+__global__ void __launch_bounds__(256) k_median_rank(const double* __restrict__ v, const int* n_dev, int n_host,
+                                                     double* mid /* [2] */) {
+  __shared__ double s_v[256];
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double me = i < n ? v[i] : 0.0;
+  int rank = 0;
+  for (int base = 0; base < n; base += 256) {
+    if (base + threadIdx.x < n) s_v[threadIdx.x] = v[base + threadIdx.x];
+    __syncthreads();
+    const int m = min(256, n - base);
+    if (i < n)
+      for (int q = 0; q < m; q++) rank += (s_v[q] < me || (s_v[q] == me && base + q < i)) ? 1 : 0;
+    __syncthreads();
+  }
+  if (i < n) {
+    if (rank == n / 2) mid[1] = me;
+    if (rank == n / 2 - 1) mid[0] = me;
+  }
+}
+__global__ void k_median_finish(const int* n_dev, int n_host, const double* mid, double* out) {
+  const int n = n_dev ? min(*n_dev, n_host) : n_host;
+  if (n == 0) out[0] = 0.0;
+  else if (n % 2 == 0) out[0] = (mid[0] + mid[1]) / 2.0;
+  else out[0] = mid[1];
+}
+
+void launch_median(Ctx& c, const double* v, const int* n_dev, int n, double* out) {
+  // out[0] = median, out[1..2] = scratch for the two middle order statistics
+  if (n > 0) {
+    k_median_rank<<<div_up(n, 256), 256, 0, c.stream>>>(v, n_dev, n, out + 1);
+    UVO_LAUNCH_CHECK(c);
+  }
+  k_median_finish<<<1, 1, 0, c.stream>>>(n_dev, n, out + 1, out);
+  UVO_LAUNCH_CHECK(c);
+}
+
+__global__ void __launch_bounds__(256) k_displacements(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                       int n, double* __restrict__ d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // `double dx = keypoints1_conv[i].x - keypoints2_conv[i].x` : the subtraction is f32, then widened
+  const double dx = (double)__fsub_rn(p1[2 * i], p2[2 * i]), dy = (double)__fsub_rn(p1[2 * i + 1], p2[2 * i + 1]);
+  d[i] = sqrt(dx * dx + dy * dy);
+}
+void launch_displacements(Ctx& c, const float* p1, const float* p2, int n, double* disp) {
+  if (n <= 0) return;
+  k_displacements<<<div_up(n, 256), 256, 0, c.stream>>>(p1, p2, n, disp);
+  UVO_LAUNCH_CHECK(c);
+}
+
+struct FrontZArgs {
+  double R[9], t[3];
+};
+__global__ void __launch_bounds__(1024) k_front_z(const double* __restrict__ pts, int n, FrontZArgs a, double* z_out,
+                                                  int* n_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool keep = false;
+    double z = 0;
+    if (i < n) {
+      const double* p = pts + 3 * i;
+      z = p[2];
+      keep = (a.R[6] * p[0] + a.R[7] * p[1] + a.R[8] * p[2] + a.t[2]) > 0;
+    }
+    const int slot = ordered_slot(keep, s_warp, &s_base);
+    if (slot >= 0) z_out[slot] = z;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *n_out = s_base;
+}
+void launch_front_z(Ctx& c, const double* pts, int n, const double R[9], const double t[3], double* z_out, int* n_out) {
+  FrontZArgs a;
+  memcpy(a.R, R, sizeof(a.R));
+  memcpy(a.t, t, sizeof(a.t));
+  k_front_z<<<1, 1024, 0, c.stream>>>(pts, n, a, z_out, n_out);
+  UVO_LAUNCH_CHECK(c);
 }
 
 size_t pnp_scratch_bytes(int n, int iterations) {

@@ -20,6 +20,9 @@ struct TriangulateArgs {
   const uvo_keypoint* kps2;
   const int* n_dev;    // device count (nullable)
   int n;               // count or capacity
+  int min_points;      // gate: triangulate only if n > min_points (-1: always)
+  const int* gate_dev; // optional second gate: *gate_dev == 0 => n = 0
+  int* n_out;          // optional: effective n written back (device)
   float* out4;         // 4 x stride f32
   int stride;          // row stride of out4 (>= n)
   float* pts1_out;     // optional: gathered points (n x 2) for later stages
@@ -75,5 +78,14 @@ struct PnpArgs {
 };
 void launch_pnp_ransac(Ctx& c, const PnpArgs& a);
 size_t pnp_scratch_bytes(int n, int iterations);
+
+// compute_median (math_utility.cpp:65-86) by rank selection: out[0] = median (mean of the two middle values for
+// even n), 0.0 for n == 0.
+void launch_median(Ctx& c, const double* v, const int* n_dev, int n, double* out);
+// select_estimation_method (VO_utility.cpp:725-748): writes the n displacements |p1-p2| (f64) to `disp`
+void launch_displacements(Ctx& c, const float* p1, const float* p2, int n, double* disp);
+// convert_3Dpoints_camera (VO_utility.cpp:46-63) z-filter: keeps the UN-transformed z of points whose transformed z
+// is > 0, order preserved; count -> *n_out
+void launch_front_z(Ctx& c, const double* pts, int n, const double R[9], const double t[3], double* z_out, int* n_out);
 
 }  // namespace uvo

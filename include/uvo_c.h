@@ -158,16 +158,6 @@ UVO_API int uvo_scale_factor(uvo_ctx* ctx, const double* points_nx3_host, int n,
 UVO_API int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X_host, const float* x_host, int n, const double K[4],
                                  int iterations, float reprojection_error, double confidence, double rvec[3],
                                  double tvec[3], int32_t* inliers_host, int* n_inliers, int* hyps_evaluated);
-/* findEssentialMat + extract_inliers + recoverPose -- VO_utility.cpp:147-149 */
-UVO_API int uvo_find_essential_mat(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n,
-                                   const double K[4], int method, double prob, double threshold, int max_iters,
-                                   double E[9], uint8_t* mask_host, int* hyps_evaluated);
-UVO_API int uvo_recover_pose(uvo_ctx* ctx, const double E[9], const float* p1_host, const float* p2_host, int n,
-                             const double K[4], double R[9], double t[3], uint8_t* mask_inout_host, int* n_good);
-/* findHomography -- VO_utility.cpp:152 */
-UVO_API int uvo_find_homography(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n, int method,
-                                double threshold, int max_iters, double confidence, double H[9],
-                                uint8_t* mask_host, int* hyps_evaluated);
 
 /* ---------------------------------------------------------------------------------------------------- frames */
 /* Device-resident replay of visual_odometry_node::stereo_VO's per-frame body (visual_odometry.h:526-740):

@@ -1,0 +1,132 @@
+"""Whole-frame parity: device-resident uvo_stereo pipeline vs the CPU replay of stereo_VO built from the oracle
+(tests/ref_stereo.py).  Keypoints, match lists and inlier sets bit-exact; pose within 1e-9; velocity within 1e-4
+relative of the oracle and close to the synthetic ground truth.  Reference: visual_odometry.h:406-741."""
+import numpy as np
+import pytest
+
+from ref_stereo import RefStereoVO
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(ctx, seq, thr):
+    import ergo_uvo_b200 as U
+    p = U.default_params(True)
+    p.surf_min_hessian = thr
+    p.max_features = 16384
+    camL = U.make_camera(seq.KL, seq.DL, seq.newKL)
+    camR = U.make_camera(seq.KR, seq.DR, seq.newKR)
+    return U.StereoVO(ctx, seq.w, seq.h, camL, camR, seq.R_right, seq.t_right, p), p
+
+
+def _compare_frame(vo, res, ref):
+    assert res.initialised == ref["initialised"]
+    assert res.n_left == ref["n_left"] and res.n_right == ref["n_right"]
+    kL, dL = vo.last_keypoints(False)
+    kR, dR = vo.last_keypoints(True)
+    assert kL.tobytes() == ref["kL"].tobytes() and kR.tobytes() == ref["kR"].tobytes()
+    assert dL.shape == ref["dL"].shape
+    if len(dL):
+        assert np.abs(dL - ref["dL"]).max() <= 1e-4 * np.abs(ref["dL"]).max()
+    assert res.n_stereo_matches == ref["n_stereo"]
+    if "m_stereo" in ref:
+        assert vo.last_matches(False).tobytes() == ref["m_stereo"].tobytes()
+    assert res.gate == ref["gate"] and res.valid == ref["valid"]
+    assert res.n_temporal_matches == ref["n_temporal"]
+    if "m_temporal" in ref:
+        assert vo.last_matches(True).tobytes() == ref["m_temporal"].tobytes()
+    assert res.n_3d == ref["n_3d"]
+    assert res.n_inliers == ref["n_inliers"] and res.hyps_evaluated == ref["hyps"]
+    if "inliers" in ref:
+        assert np.array_equal(vo.last_inliers(), ref["inliers"])
+        assert np.abs(np.array(res.rvec) - ref["rvec"]).max() <= 1e-9
+        assert np.abs(np.array(res.tvec) - ref["tvec"]).max() <= 1e-9
+    v, vr = np.array(res.velocity), ref["velocity"]
+    assert np.abs(v - vr).max() <= 1e-4 * max(np.abs(vr).max(), 1e-12)
+
+
+def test_stereo_sequence_small(ctx, oracle, small_stereo):
+    seq = small_stereo
+    vo, p = _make(ctx, seq, 3000)
+    ref = RefStereoVO(oracle, seq, p)
+    dt = 0.1
+    for k, (L, R) in enumerate(seq.frames):
+        res = vo.frame(L, R, dt)
+        r = ref.frame(L, R, dt)
+        _compare_frame(vo, res, r)
+        if k == 0:
+            assert res.initialised == 1 and res.valid == 0
+        else:
+            assert res.valid == 1 and res.gate == 0
+            truth = seq.true_t_prev_curr(k)
+            est = np.array(res.t_prev_curr)
+            assert np.linalg.norm(est - truth) < 0.15 * np.linalg.norm(truth) + 2e-3
+    ms = vo.stage_ms()
+    assert set(ms) and all(v >= 0 for v in ms.values())
+    vo.close()
+
+
+def test_stereo_full_size_frame_pair(ctx, oracle, full_stereo):
+    """BASELINE config B geometry (1280x1024); threshold chosen to give about 4k keypoints"""
+    seq = full_stereo
+    vo, p = _make(ctx, seq, 9000)
+    ref = RefStereoVO(oracle, seq, p)
+    for k in range(2):
+        L, R = seq.frames[k]
+        res = vo.frame(L, R, 0.1)
+        r = ref.frame(L, R, 0.1)
+        _compare_frame(vo, res, r)
+    assert res.valid == 1 and 2000 < res.n_left < 8000
+    vo.close()
+
+
+def test_stereo_gates_and_constant_motion(ctx, oracle, small_stereo):
+    """a featureless frame triggers gate 1: validity 0 and the stale t re-published with the new dt
+    (visual_odometry.h:707-717); the frame after that has an empty 'previous' set (gate 3)"""
+    seq = small_stereo
+    vo, p = _make(ctx, seq, 3000)
+    ref = RefStereoVO(oracle, seq, p)
+    flat = np.full_like(seq.frames[0][0], 127)
+    frames = [seq.frames[0], seq.frames[1], (flat, flat), seq.frames[0], seq.frames[1]]
+    dts = [0.1, 0.1, 0.2, 0.1, 0.1]
+    gates = []
+    for (L, R), dt in zip(frames, dts):
+        res = vo.frame(L, R, dt)
+        r = ref.frame(L, R, dt)
+        _compare_frame(vo, res, r)
+        gates.append(res.gate)
+    assert gates == [0, 0, 1, 3, 0]
+    vo.close()
+
+
+def test_stereo_async_matches_sync(ctx, small_stereo):
+    """enqueue/collect with two frames in flight gives the same records as the synchronous call"""
+    import ctypes as C
+    import torch
+    seq = small_stereo
+    vo, p = _make(ctx, seq, 3000)
+    sync = [vo.frame(L, R, 0.1) for (L, R) in seq.frames]
+    vo.close()
+    vo, p = _make(ctx, seq, 3000)
+    dev = [(torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()) for (L, R) in seq.frames]
+    torch.cuda.synchronize()
+    for (L, R) in dev:
+        vo.enqueue_device(L.data_ptr(), R.data_ptr(), 3 * seq.w, 0.1)
+    for s in sync:
+        r = vo.collect()
+        assert bytes(r) == bytes(s)
+    vo.close()
+
+
+def test_stereo_capacity_overflow_is_an_error(ctx, small_stereo):
+    import ergo_uvo_b200 as U
+    seq = small_stereo
+    p = U.default_params(True)
+    p.surf_min_hessian = 100
+    p.max_features = 256
+    vo = U.StereoVO(ctx, seq.w, seq.h, U.make_camera(seq.KL, seq.DL, seq.newKL),
+                    U.make_camera(seq.KR, seq.DR, seq.newKR), seq.R_right, seq.t_right, p)
+    with pytest.raises(U.UvoError) as e:
+        vo.frame(*seq.frames[0], 0.1)
+    assert e.value.code == -4
+    vo.close()
