@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- stereo UVO frames/sec on B200 (BASELINE.json config[1]: stereo 1280x1024, ~4k SURF features/image,
+3D-to-2D solvePnPRansac), with the kernel roofline and the CPU baseline beside it.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the CPU path -- the oracle port -- on the host cores)
+
+A step = one stereo frame through the whole hot path (get_image x2 -> SURF x2 -> stereo match -> temporal match ->
+triangulate -> extract_3Dpoints -> solvePnPRansac -> velocity).
+  value : frames/s with the input images already resident in HBM (device-resident ring larger than L2), frames
+          enqueued asynchronously through the C ABI, timed with CUDA events on the library's stream.
+  e2e   : frames/s through the reference-facing call uvo_stereo_frame with HOST (pinned) images: H2D of both images
+          and D2H of the result record inside the timed region, one synchronous call per frame.
+Multi-GPU: VO is sequential within a stream, so ranks run independent sequences (seed 1300+rank) -- replicas,
+no collective on the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1280, 1024
+TARGET_KP = 4096
+N_DISTINCT = 8       # rendered stereo pairs; the sequence ping-pongs through them (0..7,6..1,0..)
+RING = 28            # device-resident pairs (2 ping-pong cycles, 220 MB > 126 MB L2)
+
+
+def pingpong(i, n):
+    period = 2 * n - 2
+    j = i % period
+    return j if j < n else period - j
+
+
+def clocks_sampler(stop, out, gpu_index):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                              str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarise_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(names, f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def make_sequence(seed, n_frames=N_DISTINCT):
+    from tools import synth
+    return synth.StereoSequence(W, H, n_frames=n_frames, seed=seed, tex_size=2048)
+
+
+def pick_threshold(ctx, U, seq):
+    """bisect the integer SURF threshold on frame 0 (GPU path) for TARGET_KP +- 2 % keypoints, then freeze it"""
+    g = ctx.get_image(seq.frames[0][0], seq.KL, seq.DL, seq.newKL)
+    lo, hi = 100, 200000
+    ctx.params.max_features = 1 << 16
+    best = None
+    while lo < hi:
+        mid = (lo + hi) // 2
+        ctx.params.surf_min_hessian = mid
+        n = len(ctx.detect_features(g)[0])
+        if best is None or abs(n - TARGET_KP) < abs(best[1] - TARGET_KP):
+            best = (mid, n)
+        if abs(n - TARGET_KP) <= 0.02 * TARGET_KP:
+            break
+        if n > TARGET_KP:
+            lo = mid + 1
+        else:
+            hi = mid
+    return best
+
+
+def pick_threshold_cpu(seq):
+    """same rule as pick_threshold, evaluated with the CPU path (reference arm only)"""
+    from oracle import oracle as O
+    g = O.get_image(seq.frames[0][0], seq.KL, seq.DL, seq.newKL, True, 8.0)
+    lo, hi, best = 100, 200000, None
+    while lo < hi:
+        mid = (lo + hi) // 2
+        n = len(O.surf_detect_and_compute(g, mid)[0])
+        if best is None or abs(n - TARGET_KP) < abs(best[1] - TARGET_KP):
+            best = (mid, n)
+        if abs(n - TARGET_KP) <= 0.02 * TARGET_KP:
+            break
+        if n > TARGET_KP:
+            lo = mid + 1
+        else:
+            hi = mid
+    return best[0]
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def cpu_frames(seq, thr, n_frames, params=None):
+    """the reference's CPU path (oracle port of the OpenCV calls) on n_frames consecutive frames; returns seconds per
+    frame (steady state: the initialisation frame is not counted)"""
+    from oracle import oracle as O
+    from oracle.ref_stereo import RefStereoVO
+    import ergo_uvo_b200._lib as L
+    p = params or default_params_cpu(thr)
+    ref = RefStereoVO(O, seq, p)
+    ref.frame(*seq.frames[0], 0.1)  # initialisation frame
+    t0 = time.perf_counter()
+    valid = 0
+    for k in range(1, n_frames + 1):
+        r = ref.frame(*seq.frames[pingpong(k, len(seq.frames))], 0.1)
+        valid += r["valid"]
+    dt = time.perf_counter() - t0
+    return dt / n_frames, valid
+
+
+def default_params_cpu(thr):
+    """uvo_params with the shipped stereo YAML values, without touching the CUDA library"""
+    import ctypes as C
+    from ergo_uvo_b200 import _lib as L
+    p = L.Params()
+    p.clahe, p.clip_limit, p.distance, p.lowe_ratio = 1, 8, 10, 0.8
+    p.reprojection_tolerance, p.min_num_features, p.min_num_3dpoints, p.min_num_inliers = 3.0, 5, 5, 5
+    p.iterations_count, p.reprojection_error, p.confidence, p.pnp_method_flag = 1000, 1.0, 0.99, 1
+    p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers, p.surf_extended, p.surf_upright = thr, 4, 3, 0, 1
+    p.max_features = 16384
+    return p
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    seq = make_sequence(1300, n_frames=4)
+    thr = args.threshold or pick_threshold_cpu(seq)
+    cores = min(16, os.cpu_count() or 1)
+    for _ in range(max(args.warmup, 0)):
+        cpu_frames(seq, thr, 1)
+    spf, valid = cpu_frames(seq, thr, max(args.steps, 1))
+    fps = 1.0 / spf
+    line = {
+        "impl": "reference", "metric": "stereo_uvo_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spf * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
+        "data": "synthetic",
+        "config": {"workload": "stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML",
+                   "surf_min_hessian": thr},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} consecutive stereo frames of the same synthetic sequence through the "
+                                   "oracle port of the OpenCV CPU path (SURF restated, not OpenCV)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "valid_frames": valid,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import ergo_uvo_b200 as U
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(device=local)
+    ctx = U.Context(local, stream=stream.cuda_stream)
+
+    seq = make_sequence(1300 + rank)
+    if args.threshold:
+        thr, n0 = args.threshold, -1
+    else:
+        thr, n0 = pick_threshold(ctx, U, seq)
+    p = U.default_params(True)
+    p.surf_min_hessian = thr
+    p.max_features = 16384
+    camL = U.make_camera(seq.KL, seq.DL, seq.newKL)
+    camR = U.make_camera(seq.KR, seq.DR, seq.newKR)
+    vo = U.StereoVO(ctx, W, H, camL, camR, seq.R_right, seq.t_right, p)
+
+    # device ring (inputs resident in HBM, larger than L2) and pinned host ring
+    pitch = 3 * W
+    dev_ring = [(torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][0]).cuda(),
+                 torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][1]).cuda()) for i in range(RING)]
+    host_ring = [(torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][0]).pin_memory(),
+                  torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][1]).pin_memory()) for i in range(RING)]
+    torch.cuda.synchronize()
+    dt_frame = 0.1
+    inflight = 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_device(n, start):
+        valid = 0
+        q = 0
+        for i in range(n):
+            L, R = dev_ring[(start + i) % RING]
+            vo.enqueue_device(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
+            q += 1
+            if q >= inflight:
+                valid += vo.collect().valid
+                q -= 1
+        while q:
+            valid += vo.collect().valid
+            q -= 1
+        return valid
+
+    def run_host(n, start):
+        valid = 0
+        for i in range(n):
+            L, R = host_ring[(start + i) % RING]
+            res = vo.lib  # noqa: F841
+            r = U.StereoResult()
+            import ctypes as C
+            rc = vo.lib.uvo_stereo_frame(vo.h, C.c_void_p(L.data_ptr()), C.c_void_p(R.data_ptr()), C.c_size_t(pitch),
+                                         C.c_double(dt_frame), C.byref(r))
+            ctx._ck(rc)
+            valid += r.valid
+        return valid
+
+    # ---- device-resident throughput (value)
+    pos = 0
+    run_device(max(args.warmup, 3), pos)
+    pos += max(args.warmup, 3)
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        valid_dev = run_device(args.steps, pos)
+        e1.record(stream)
+    barrier()
+    launches = ctx.launches - launches0
+    ms_dev = e0.elapsed_time(e1)
+    pos += args.steps
+
+    # ---- end-to-end through the host-buffer call (e2e)
+    run_host(3, pos)
+    pos += 3
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        valid_host = run_host(args.steps, pos)
+        e1.record(stream)
+    barrier()
+    ms_host = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    pos += args.steps
+    stop.set()
+    sampler.join(timeout=3)
+
+    # ---- per-kernel CUDA-event timing (roofline leg): same workload, events around every launch
+    kern = {}
+    stage = {}
+    if rank == 0:
+        ctx.kernel_timing(True)
+        n_prof = min(args.steps, 50)
+        run_device(n_prof, pos)
+        rep = ctx.kernel_report()
+        ctx.kernel_timing(False)
+        kern = {k: {"launches_per_frame": c / n_prof, "ms_per_frame": ms / n_prof, "us_per_launch": 1e3 * ms / c}
+                for k, (c, ms) in rep.items()}
+        L, R = dev_ring[(pos + n_prof) % RING]
+        vo.frame_device(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
+        stage = vo.stage_ms()
+    res_last = None
+    kl, _ = vo.last_keypoints(False)
+    kr, _ = vo.last_keypoints(True)
+
+    # ---- max over ranks
+    t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device="cuda")
+    v = torch.tensor([float(valid_dev), float(valid_host)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    ms_dev, ms_host = t.tolist()
+    total_frames = args.steps * world
+    value = total_frames / (ms_dev * 1e-3)
+    e2e = total_frames / (ms_host * 1e-3)
+
+    if rank == 0:
+        hbm, tf_burst, tf_sus, which = load_peaks()
+        n_kp = (len(kl) + len(kr)) / 2.0
+        P = W * H
+        # algorithmic bytes / flops per launch of each kernel (DESIGN.md "Kernels")
+        algo = {
+            "k_gray_undistort": ("hbm", 4.0 * P), "k_clahe_hist": ("hbm", 1.0 * P), "k_clahe_apply": ("hbm", 2.0 * P),
+            "k_integral_rows": ("hbm", 5.0 * P), "k_integral_cols": ("hbm", 8.0 * P),
+            "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_describe": ("hbm", 2 * n_kp * (40 * 40 + 256)),
+            "k_knn2_partial": ("tensor", 2.0 * n_kp * n_kp * 64),
+        }
+        roof = None
+        if kern:
+            top = max(kern.items(), key=lambda kv: kv[1]["ms_per_frame"])
+            name, kt = top
+            bound, per_launch = algo.get(name, ("hbm", None))
+            if per_launch is not None:
+                sec = kt["us_per_launch"] * 1e-6
+                if bound == "hbm":
+                    ach = per_launch / sec / 1e9
+                    roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                            "frac": ach / hbm, "traffic": None, "peak_source": which,
+                            "algorithmic_bytes_per_launch": per_launch, "us_per_launch": kt["us_per_launch"]}
+                else:
+                    ach = per_launch / sec / 1e12
+                    roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
+                            "frac": ach / tf_sus, "traffic": None, "peak_source": which + " (sustained bf16)",
+                            "algorithmic_flops_per_launch": per_launch, "us_per_launch": kt["us_per_launch"],
+                            "note": "exact f32 CUDA-core kernel measured against the tensor roofline SURVEY 8d assigns"}
+        # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
+        cpu = None
+        if not args.no_cpu:
+            n_cpu = 4
+            spf, _ = cpu_frames(seq, thr, n_cpu, params=p)
+            cpu = {"value": 1.0 / spf, "unit": "frames/s", "cores": min(16, os.cpu_count() or 1), "kind": "port",
+                   "sample": f"{n_cpu} consecutive stereo frames (after the init frame) of this run's sequence through "
+                             "the oracle port of the OpenCV CPU path; SURF restated, not OpenCV",
+                   "host_cpus": os.cpu_count()}
+        line = {
+            "metric": "stereo_uvo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
+            "data": "synthetic",
+            "config": {"workload": "stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo "
+                                   "YAML (BASELINE config[1]); one independent sequence per GPU",
+                       "width": W, "height": H, "surf_min_hessian": thr, "keypoints_per_image": n_kp,
+                       "sequences_per_gpu": 1, "frames_in_flight": inflight,
+                       "l2": f"inputs larger than L2: ring of {RING} device-resident stereo pairs "
+                             f"({RING * 2 * 3 * P / 1e6:.0f} MB), each read once per {RING} frames"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * 3 * P,
+                    "d2h_bytes_per_step": int(__import__('ctypes').sizeof(U.StereoResult)),
+                    "ms_per_step": ms_host / args.steps, "api": "uvo_stereo_frame (host pinned images, synchronous)"},
+            "gpu_launches": int(launches),
+            "launches_per_frame": launches / float(args.steps),
+            "valid_frames": {"device": int(v[0].item()), "host": int(v[1].item()), "of": total_frames},
+            "clocks": summarise_clocks(samples),
+            "roofline": roof, "cpu_baseline": cpu,
+            "stage_ms": stage, "kernels": kern,
+        }
+        print(json.dumps(line))
+    vo.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--threshold", type=int, default=0, help="SURF min_hessian (0: bisect for ~4096 keypoints)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded sample: ~2 s of CPU work per frame
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -77,6 +77,8 @@ def load():
     lib.uvo_ctx_synchronize.argtypes = [C.c_void_p]
     lib.uvo_ctx_launch_count.restype = C.c_int64
     lib.uvo_ctx_launch_count.argtypes = [C.c_void_p]
+    lib.uvo_ctx_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.uvo_ctx_kernel_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.uvo_default_params.argtypes = [C.c_int, C.POINTER(Params)]
     lib.uvo_default_params.restype = None
     lib.uvo_host_alloc.restype = C.c_void_p

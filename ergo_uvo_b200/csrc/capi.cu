@@ -74,6 +74,54 @@ const char* uvo_last_error(const uvo_ctx* ctx) { return ctx ? ctx->c.err.c_str()
 void* uvo_ctx_stream(uvo_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 int64_t uvo_ctx_launch_count(const uvo_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+int uvo_ctx_kernel_timing(uvo_ctx* ctx, int enable) {
+  if (!ctx) return UVO_ERR_INVALID;
+  cudaStreamSynchronize(ctx->c.stream);
+  for (auto& r : ctx->c.kt.recs) {
+    ctx->c.kt.pool.push_back(r.a);
+    ctx->c.kt.pool.push_back(r.b);
+  }
+  ctx->c.kt.recs.clear();
+  ctx->c.kt.enabled = enable != 0;
+  return UVO_OK;
+}
+
+int uvo_ctx_kernel_report(uvo_ctx* ctx, char* buf, size_t buflen) {
+  if (!ctx || !buf || buflen == 0) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    struct Acc {
+      const char* name;
+      int count;
+      double ms;
+    };
+    std::vector<Acc> acc;
+    for (auto& r : ctx->c.kt.recs) {
+      float ms = 0.f;
+      UVO_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      bool found = false;
+      for (auto& a : acc)
+        if (strcmp(a.name, r.name) == 0) {
+          a.count++;
+          a.ms += ms;
+          found = true;
+          break;
+        }
+      if (!found) acc.push_back({r.name, 1, (double)ms});
+      ctx->c.kt.pool.push_back(r.a);
+      ctx->c.kt.pool.push_back(r.b);
+    }
+    ctx->c.kt.recs.clear();
+    size_t off = 0;
+    buf[0] = 0;
+    for (auto& a : acc) {
+      int n = snprintf(buf + off, buflen - off, "%s %d %.6f\n", a.name, a.count, a.ms);
+      if (n < 0 || (size_t)n >= buflen - off) break;
+      off += n;
+    }
+  });
+}
+
 int uvo_ctx_synchronize(uvo_ctx* ctx) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] { UVO_CUDA(cudaStreamSynchronize(ctx->c.stream)); });

@@ -13,6 +13,28 @@
 
 namespace uvo {
 
+// optional per-kernel CUDA-event timing (bench.py's roofline leg): every launch is bracketed by two events on the
+// launching stream; durations are summed per kernel name when the results are read.
+struct KernelTimer {
+  bool enabled = false;
+  struct Rec {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -20,6 +42,24 @@ struct Ctx {
   int sm_count = 148;
   int64_t launches = 0;
   std::string err;
+  KernelTimer kt;
+  const char* pending_name = nullptr;
+  cudaEvent_t pending_ev = nullptr;
+  // call right before a kernel launch
+  void kbegin(const char* name) {
+    if (!kt.enabled) return;
+    pending_name = name;
+    pending_ev = kt.get();
+    cudaEventRecord(pending_ev, stream);
+  }
+  void kend() {
+    launches++;
+    if (!kt.enabled || !pending_name) return;
+    cudaEvent_t b = kt.get();
+    cudaEventRecord(b, stream);
+    kt.recs.push_back({pending_name, pending_ev, b});
+    pending_name = nullptr;
+  }
 };
 
 struct CudaError {
@@ -37,9 +77,10 @@ struct CudaError {
 
 #define UVO_LAUNCH_CHECK(ctx)  \
   do {                         \
-    (ctx).launches++;          \
+    (ctx).kend();              \
     UVO_CUDA(cudaGetLastError()); \
   } while (0)
+#define UVO_KERNEL(ctx, name) (ctx).kbegin(name)
 
 struct InvalidArg {
   std::string msg;

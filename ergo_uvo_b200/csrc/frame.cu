@@ -263,6 +263,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   s->fe.surf(c, 0, 2, p);
   const int* cL = s->fe.counters.get();
   const int* cR = s->fe.counters.get() + 4;
+  UVO_KERNEL(c, "k_gate_features");
   k_gate_features<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, g);
   UVO_LAUNCH_CHECK(c);
   mark(3);
@@ -281,6 +282,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ms.n_matches = &ctrl->n_stereo;
   launch_match(c, ms);
   // 4. gathers (:569-579)
+  UVO_KERNEL(c, "k_gather_after_stereo");
   k_gather_after_stereo<<<2 * c.sm_count, 256, 0, c.stream>>>(s->m_stereo.get(), ctrl, pctrl, s->state.get(),
                                                             s->fe.kps[0].get(), s->fe.kps[1].get(),
                                                             s->fe.desc[0].get(), s->kL_as[cur].get(),
@@ -375,6 +377,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   mark(7);
   // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
   ResultParams rp{g, dt};
+  UVO_KERNEL(c, "k_frame_result");
   k_frame_result<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, s->state.get(), s->pnp_result.get(), s->small.get(),
                                         s->small.get() + 1, s->d_result.get() + slot, rp);
   UVO_LAUNCH_CHECK(c);

@@ -60,6 +60,7 @@ void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, 
                            uint8_t* d_dst, size_t dpitch) {
   dim3 block(32, 8);
   dim3 grid(div_up(div_up(w, 4), 32), div_up(h, 8));
+  UVO_KERNEL(c, "k_gray_undistort");
   k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3, spitch, w, h, P, d_dst, dpitch);
   UVO_LAUNCH_CHECK(c);
 }
@@ -244,11 +245,14 @@ void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, con
   const int tiles = g.tiles_x * g.tiles_y;
   UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles, c.stream));
   int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
+  UVO_KERNEL(c, "k_clahe_hist");
   k_clahe_hist<<<dim3(tiles, slices), 256, 0, c.stream>>>(d_src, spitch, w, h, g, d_hist);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_clahe_lut");
   k_clahe_lut<<<tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);
   UVO_LAUNCH_CHECK(c);
   dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8));
+  UVO_KERNEL(c, "k_clahe_apply");
   k_clahe_apply<<<grid, block, 0, c.stream>>>(d_src, spitch, w, h, g, d_lut, d_dst, dpitch);
   UVO_LAUNCH_CHECK(c);
 }
@@ -319,8 +323,10 @@ __global__ void __launch_bounds__(1024) k_integral_cols(int32_t* __restrict__ su
 
 void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum) {
   const int warps_per_block = 8;
+  UVO_KERNEL(c, "k_integral_rows");
   k_integral_rows<<<div_up(h, warps_per_block), 32 * warps_per_block, 0, c.stream>>>(d_img, pitch, w, h, d_sum);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_integral_cols");
   k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, w, h);
   UVO_LAUNCH_CHECK(c);
 }

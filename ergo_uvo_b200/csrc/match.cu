@@ -134,8 +134,10 @@ void launch_match(Ctx& c, const MatchArgs& a) {
     UVO_CUDA(cudaMemsetAsync(a.n_matches, 0, sizeof(int), c.stream));
     return;
   }
+  UVO_KERNEL(c, "k_knn2_partial");
   k_knn2_partial<<<dim3(div_up(a.nq, QB), MATCH_SPLITS), QB, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_knn2_merge");
   k_knn2_merge<<<1, 1024, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
 }

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(64) k_triangulate(const __grid_constant__ Tria
 
 void launch_triangulate(Ctx& c, const TriangulateArgs& a) {
   if (a.n <= 0) return;
+  UVO_KERNEL(c, "k_triangulate");
   k_triangulate<<<div_up(a.n, 64), 64, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
 }
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(1024) k_extract3d(const __grid_constant__ Extr
 }
 
 void launch_extract3d(Ctx& c, const Extract3dArgs& a) {
+  UVO_KERNEL(c, "k_extract3d");
   k_extract3d<<<1, 1024, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
 }
@@ -617,9 +619,11 @@ __global__ void k_median_finish(const int* n_dev, int n_host, const double* mid,
 void launch_median(Ctx& c, const double* v, const int* n_dev, int n, double* out) {
   // out[0] = median, out[1..2] = scratch for the two middle order statistics
   if (n > 0) {
+    UVO_KERNEL(c, "k_median_rank");
     k_median_rank<<<div_up(n, 256), 256, 0, c.stream>>>(v, n_dev, n, out + 1);
     UVO_LAUNCH_CHECK(c);
   }
+  UVO_KERNEL(c, "k_median_finish");
   k_median_finish<<<1, 1, 0, c.stream>>>(n_dev, n, out + 1, out);
   UVO_LAUNCH_CHECK(c);
 }
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(256) k_displacements(const float* __restrict__
 }
 void launch_displacements(Ctx& c, const float* p1, const float* p2, int n, double* disp) {
   if (n <= 0) return;
+  UVO_KERNEL(c, "k_displacements");
   k_displacements<<<div_up(n, 256), 256, 0, c.stream>>>(p1, p2, n, disp);
   UVO_LAUNCH_CHECK(c);
 }
@@ -666,6 +671,7 @@ void launch_front_z(Ctx& c, const double* pts, int n, const double R[9], const d
   FrontZArgs a;
   memcpy(a.R, R, sizeof(a.R));
   memcpy(a.t, t, sizeof(a.t));
+  UVO_KERNEL(c, "k_front_z");
   k_front_z<<<1, 1024, 0, c.stream>>>(pts, n, a, z_out, n_out);
   UVO_LAUNCH_CHECK(c);
 }
@@ -681,17 +687,23 @@ void launch_pnp_ransac(Ctx& c, const PnpArgs& a) {
   const int iters = std::max(a.iterations, 1);
   UVO_REQUIRE((size_t)iters * 8 < (size_t)RNG_TABLE_SIZE, "solvePnPRansac: iterationsCount too large for the RNG table");
   if (a.n > 0) {
+    UVO_KERNEL(c, "k_pnp_prepare");
     k_pnp_prepare<<<std::min(div_up(a.n, 256), 4 * c.sm_count), 256, 0, c.stream>>>(a);
     UVO_LAUNCH_CHECK(c);
   }
+  UVO_KERNEL(c, "k_pnp_subsets");
   k_pnp_subsets<<<1, 32, 0, c.stream>>>(a, rng);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_pnp_hyp");
   k_pnp_hyp<<<div_up(iters, 32), 32, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_pnp_score");
   k_pnp_score<<<iters, 256, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_pnp_scan");
   k_pnp_scan<<<1, 32, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_pnp_finalize");
   k_pnp_finalize<<<1, REFIT_THREADS, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
 }

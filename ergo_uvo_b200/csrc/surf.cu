@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(256) k_surf_detect(const __grid_constant__ Sur
 void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity) {
   upload_tables(c);
   for (int i = 0; i < b.n_img; i++) UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
+  UVO_KERNEL(c, "k_surf_detect");
   k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(g, b, capacity);
   UVO_LAUNCH_CHECK(c);
 }
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(256) k_surf_rank(const __grid_constant__ SurfB
 }
 
 void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity) {
+  UVO_KERNEL(c, "k_surf_rank");
   k_surf_rank<<<dim3(div_up(capacity, 256), b.n_img), 256, 0, c.stream>>>(b, capacity);
   UVO_LAUNCH_CHECK(c);
 }
@@ -592,6 +594,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
 void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright) {
   upload_tables(c);
   const int blocks = std::min(capacity, 8 * c.sm_count);
+  UVO_KERNEL(c, "k_surf_describe");
   k_surf_describe<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright);
   UVO_LAUNCH_CHECK(c);
 }
@@ -638,6 +641,7 @@ __global__ void __launch_bounds__(1024) k_surf_compact(const __grid_constant__ S
 }
 
 void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc) {
+  UVO_KERNEL(c, "k_surf_compact");
   k_surf_compact<<<b.n_img, 1024, 0, c.stream>>>(b, tmp_kps, tmp_desc, capacity);
   UVO_LAUNCH_CHECK(c);
 }

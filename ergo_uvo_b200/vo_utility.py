@@ -87,6 +87,19 @@ class Context:
     def launches(self):
         return int(self.lib.uvo_ctx_launch_count(self.h))
 
+    def kernel_timing(self, enable):
+        self._ck(self.lib.uvo_ctx_kernel_timing(self.h, int(enable)))
+
+    def kernel_report(self):
+        """{kernel name: (launches, total_ms)} since timing was enabled / last report"""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.uvo_ctx_kernel_report(self.h, buf, C.c_size_t(len(buf))))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
     def synchronize(self):
         self._ck(self.lib.uvo_ctx_synchronize(self.h))
 

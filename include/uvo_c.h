@@ -101,6 +101,10 @@ UVO_API void* uvo_ctx_stream(uvo_ctx* ctx);
 UVO_API int uvo_ctx_synchronize(uvo_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 UVO_API int64_t uvo_ctx_launch_count(const uvo_ctx* ctx);
+/* Diagnostics for bench.py's roofline leg: when enabled every kernel launch is bracketed by CUDA events on the
+ * context stream; uvo_ctx_kernel_report writes one line per kernel name, "<name> <launches> <total_ms>", and resets. */
+UVO_API int uvo_ctx_kernel_timing(uvo_ctx* ctx, int enable);
+UVO_API int uvo_ctx_kernel_report(uvo_ctx* ctx, char* buf, size_t buflen);
 /* fills every field with the shipped stereo (stereo!=0) or mono YAML values
  * (uvo/config/stereo_VO_parameters.yaml:8-47, mono_VO_parameters.yaml:2-49) */
 UVO_API void uvo_default_params(int stereo, uvo_params* out);

@@ -4,7 +4,7 @@ relative of the oracle and close to the synthetic ground truth.  Reference: visu
 import numpy as np
 import pytest
 
-from ref_stereo import RefStereoVO
+from oracle.ref_stereo import RefStereoVO
 
 pytestmark = pytest.mark.gpu
 
