@@ -28,6 +28,8 @@ struct FrameCtrl {  // device-side control block, one per in-flight frame parity
   int n_3d;         // good_prevCam_points.rows
   int n_inliers, hyps;
   int overflow;
+  int nL, nR;       // SURF keypoint counts (copied here: the front-end counters are reused by the next frame)
+  int was_init;     // vo_initialized before this frame
 };
 
 struct FrameState {  // persists across frames (device)
@@ -42,6 +44,8 @@ struct GateParams {
 // after SURF: gate 1 (visual_odometry.h:556) and capacity check
 __global__ void k_gate_features(const int* cL, const int* cR, FrameCtrl* ctrl, GateParams g) {
   const int nL = min(cL[1], g.capacity), nR = min(cR[1], g.capacity);
+  ctrl->nL = nL;
+  ctrl->nR = nR;
   ctrl->overflow = (cL[0] > g.capacity || cR[0] > g.capacity) ? 1 : 0;
   ctrl->nq_stereo = (nL >= g.min_features && nR >= g.min_features) ? nL : 0;
 }
@@ -61,7 +65,10 @@ __global__ void __launch_bounds__(256) k_gather_after_stereo(const uvo_dmatch* _
     ctrl->n_as = n_as;
     // the triangular match only runs inside `if (results_match_curr.size() > MIN_NUM_FEATURES)` and once the node is
     // initialised
-    ctrl->nq_temporal = (n_as > 0 && st->vo_init) ? prev_ctrl->n_as : 0;
+    const int was_init = st->vo_init;
+    ctrl->was_init = was_init;
+    ctrl->nq_temporal = (n_as > 0 && was_init) ? prev_ctrl->n_as : 0;
+    if (n_as > 0) st->vo_init = 1;  // the pose stage runs on a side stream: the next frame must already see this
   }
   const int total = n_as * 16;  // float4 chunks of the descriptors
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -81,14 +88,14 @@ struct ResultParams {
 };
 
 // gates 3-5 (visual_odometry.h:626, :634, :665), Rodrigues + t_prevCam_currCam = -R^T t (:673-675), velocity (:148-159)
-__global__ void k_frame_result(const int* cL, const int* cR, FrameCtrl* ctrl, FrameState* st, const double* pnp_result,
-                               const int* n_inl_dev, const int* hyps_dev, uvo_stereo_result* out, ResultParams p) {
+__global__ void k_frame_result(FrameCtrl* ctrl, FrameState* st, const double* pnp_result, const int* n_inl_dev,
+                               const int* hyps_dev, uvo_stereo_result* out, ResultParams p) {
   const GateParams& g = p.g;
   uvo_stereo_result r;
   memset(&r, 0, sizeof(r));
-  const int was_init = st->vo_init;
-  r.n_left = min(cL[1], g.capacity);
-  r.n_right = min(cR[1], g.capacity);
+  const int was_init = ctrl->was_init;
+  r.n_left = ctrl->nL;
+  r.n_right = ctrl->nR;
   r.n_stereo_matches = ctrl->n_stereo;
   r.n_temporal_matches = ctrl->nq_temporal > 0 ? ctrl->n_temporal : 0;
   const bool tri = r.n_temporal_matches > g.min_features;
@@ -121,8 +128,7 @@ __global__ void k_frame_result(const int* cL, const int* cR, FrameCtrl* ctrl, Fr
     r.gate = gate == -1 ? -1 : 0;
     r.valid = 0;
   }
-  if (ctrl->n_as > 0) st->vo_init = 1;
-  r.initialised = st->vo_init;
+  r.initialised = (was_init || ctrl->n_as > 0) ? 1 : 0;
   for (int i = 0; i < 3; i++) {
     r.t_prev_curr[i] = st->t_prev_curr[i];  // stale value is re-published on gate failure (:717)
     r.velocity[i] = st->t_prev_curr[i] / p.dt;
@@ -153,10 +159,16 @@ struct uvo_stereo {
   DevBuf<uvo_dmatch> m_stereo, m_temporal;
   DevBuf<Knn2> knn_scratch;
   DevBuf<float> pts1, pts2, X4;
-  DevBuf<double> good_pts, tmp_pts, pnp_result;
-  DevBuf<int32_t> good_idx, tmp_idx, inliers;
-  DevBuf<int> small;  // [0] n_stereo is in ctrl; here: [0] n_inliers [1] hyps [2..3] best
-  DevBuf<uint8_t> pnp_scratch;
+  DevBuf<double> good_pts, tmp_pts;
+  DevBuf<int32_t> good_idx, tmp_idx;
+  // pose stage (side stream), double-buffered by frame parity
+  DevBuf<double> pnp_result[2];
+  DevBuf<int32_t> inliers[2];
+  DevBuf<int> small[2];  // [0] n_inliers [1] hyps [2..3] best
+  DevBuf<uint8_t> pnp_scratch[2];
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main[2] = {}, ev_side[2] = {};  // hand-over main -> side, and side done, per parity
+  bool side_used[2] = {false, false};
   DevBuf<uvo_stereo_result> d_result;  // ring
   PinnedBuf<uvo_stereo_result> h_result;
   static constexpr int RING = 8;
@@ -172,6 +184,11 @@ struct uvo_stereo {
     for (auto& p : pending) cudaEventDestroy(p.second);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+      if (ev_main[i]) cudaEventDestroy(ev_main[i]);
+      if (ev_side[i]) cudaEventDestroy(ev_side[i]);
+    }
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -229,12 +246,17 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
   s->tmp_pts.ensure(3 * (size_t)cap);
   s->good_idx.ensure(cap);
   s->tmp_idx.ensure(cap);
-  s->inliers.ensure(cap);
-  s->pnp_result.ensure(8);
-  s->small.ensure(8);
-  UVO_CUDA(cudaMemsetAsync(s->small.get(), 0, 8 * sizeof(int), c.stream));
-  UVO_CUDA(cudaMemsetAsync(s->pnp_result.get(), 0, 8 * sizeof(double), c.stream));
-  s->pnp_scratch.ensure(pnp_scratch_bytes(cap, prm->iterations_count) + 4096);
+  for (int i = 0; i < 2; i++) {
+    s->inliers[i].ensure(cap);
+    s->pnp_result[i].ensure(8);
+    s->small[i].ensure(8);
+    UVO_CUDA(cudaMemsetAsync(s->small[i].get(), 0, 8 * sizeof(int), c.stream));
+    UVO_CUDA(cudaMemsetAsync(s->pnp_result[i].get(), 0, 8 * sizeof(double), c.stream));
+    s->pnp_scratch[i].ensure(pnp_scratch_bytes(cap, prm->iterations_count) + 4096);
+    UVO_CUDA(cudaEventCreateWithFlags(&s->ev_main[i], cudaEventDisableTiming));
+    UVO_CUDA(cudaEventCreateWithFlags(&s->ev_side[i], cudaEventDisableTiming));
+  }
+  UVO_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   s->d_result.ensure(uvo_stereo::RING);
   s->h_result.ensure(uvo_stereo::RING);
   for (auto& e : s->ev) UVO_CUDA(cudaEventCreate(&e));
@@ -254,6 +276,8 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   auto mark = [&](int i) {
     if (s->timing) UVO_CUDA(cudaEventRecord(s->ev[i], c.stream));
   };
+  // frame t reuses the control block and pose scratch of frame t-2: its pose stage (side stream) must be done
+  if (s->side_used[cur]) UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_side[cur], 0));
   mark(1);
   // 1. get_image x2 (visual_odometry.h:542-543)
   s->fe.prep(c, 0, dL, pitch, s->cam[0], p.clahe, p.clip_limit);
@@ -354,14 +378,14 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   pa.reproj_err = (float)p.reprojection_error;
   pa.confidence = p.confidence;
   pa.min_points = p.min_num_3dpoints;  // if (good_prevCam_points.rows > MIN_NUM_3DPOINTS)
-  pa.result = s->pnp_result.get();
-  pa.inliers = s->inliers.get();
-  pa.n_inliers = s->small.get();
-  pa.hyps = s->small.get() + 1;
-  pa.best = s->small.get() + 2;
+  pa.result = s->pnp_result[cur].get();
+  pa.inliers = s->inliers[cur].get();
+  pa.n_inliers = s->small[cur].get();
+  pa.hyps = s->small[cur].get() + 1;
+  pa.best = s->small[cur].get() + 2;
   {
     const int iters = std::max(p.iterations_count, 1);
-    uint8_t* b = s->pnp_scratch.get();
+    uint8_t* b = s->pnp_scratch[cur].get();
     auto take = [&](size_t bytes) {
       uint8_t* r = b;
       b += (bytes + 255) & ~(size_t)255;
@@ -373,17 +397,33 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     pa.xs = (float*)take(sizeof(float) * 2 * cap);
     pa.Xf = (float*)take(sizeof(float) * 3 * cap);
   }
-  launch_pnp_ransac(c, pa);
-  mark(7);
-  // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
-  ResultParams rp{g, dt};
-  UVO_KERNEL(c, "k_frame_result");
-  k_frame_result<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, s->state.get(), s->pnp_result.get(), s->small.get(),
-                                        s->small.get() + 1, s->d_result.get() + slot, rp);
-  UVO_LAUNCH_CHECK(c);
-  UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
-                           cudaMemcpyDeviceToHost, c.stream));
-  mark(8);
+  // the gathers (which read buffers the next frame overwrites) and the subset stream stay on the main stream; the
+  // long, narrow part of the pose stage -- hypotheses, scoring, bookkeeping, refit, result -- moves to a side stream so
+  // that it overlaps the next frame's front end (it only touches its own parity of the pose scratch)
+  launch_pnp_prepare(c, pa);
+  UVO_CUDA(cudaEventRecord(s->ev_main[cur], c.stream));
+  cudaStream_t main_stream = c.stream;
+  c.stream = s->side;
+  try {
+    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_main[cur], 0));
+    launch_pnp_solve(c, pa);
+    mark(7);
+    // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
+    ResultParams rp{g, dt};
+    UVO_KERNEL(c, "k_frame_result");
+    k_frame_result<<<1, 1, 0, c.stream>>>(ctrl, s->state.get(), s->pnp_result[cur].get(), s->small[cur].get(),
+                                          s->small[cur].get() + 1, s->d_result.get() + slot, rp);
+    UVO_LAUNCH_CHECK(c);
+    UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
+                             cudaMemcpyDeviceToHost, c.stream));
+    mark(8);
+    UVO_CUDA(cudaEventRecord(s->ev_side[cur], c.stream));
+    s->side_used[cur] = true;
+  } catch (...) {
+    c.stream = main_stream;
+    throw;
+  }
+  c.stream = main_stream;
   // 14. carry curr -> prev (:723-733): swap the after-stereo buffers
   s->parity ^= 1;
   s->frame_no++;
@@ -409,6 +449,7 @@ void uvo_stereo_destroy(uvo_stereo* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->c.device);
   cudaStreamSynchronize(s->ctx->c.stream);
+  if (s->side) cudaStreamSynchronize(s->side);
   delete s;
 }
 
@@ -423,7 +464,7 @@ int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* d
     stereo_enqueue(s, dL, dR, pitch, dt, slot);
     cudaEvent_t e;
     UVO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    UVO_CUDA(cudaEventRecord(e, c.stream));
+    UVO_CUDA(cudaEventRecord(e, s->side));
     s->pending.emplace_back(slot, e);
   });
 }
@@ -514,10 +555,12 @@ int uvo_stereo_last_inliers(uvo_stereo* s, int32_t* inl, int capacity, int* coun
   return guarded(&s->ctx->c, [&] {
     Ctx& c = s->ctx->c;
     int n = 0;
-    UVO_CUDA(cudaMemcpyAsync(&n, s->small.get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    const int last = s->parity ^ 1;
+    UVO_CUDA(cudaStreamSynchronize(s->side));
+    UVO_CUDA(cudaMemcpyAsync(&n, s->small[last].get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     UVO_CUDA(cudaStreamSynchronize(c.stream));
     UVO_REQUIRE(n <= capacity, "uvo_stereo_last_inliers: capacity too small");
-    if (n > 0 && inl) UVO_CUDA(cudaMemcpy(inl, s->inliers.get(), sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (n > 0 && inl) UVO_CUDA(cudaMemcpy(inl, s->inliers[last].get(), sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
     *count = n;
   });
 }

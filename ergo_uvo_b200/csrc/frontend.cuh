@@ -19,6 +19,7 @@ struct FrontEnd {
   DevBuf<uvo_keypoint> raw[2], kps[2];
   DevBuf<float> desc[2];
   DevBuf<int> counters;  // 4 ints per image
+  DevBuf<int> rank[2];
   DevBuf<unsigned int> hist;
   DevBuf<uint8_t> lut;
   DevBuf<uvo_keypoint> tmp_kps;
@@ -38,6 +39,7 @@ struct FrontEnd {
       raw[i].ensure(capacity);
       kps[i].ensure(capacity);
       desc[i].ensure((size_t)capacity * 64);
+      rank[i].ensure(capacity);
     }
     counters.ensure(8);
     hist.ensure(2 * 64 * 256);
@@ -55,6 +57,7 @@ struct FrontEnd {
       im.raw = raw[first + i].get();
       im.kps = kps[first + i].get();
       im.desc = desc[first + i].get();
+      im.rank = rank[first + i].get();
       im.counters = counters.get() + 4 * (first + i);
     }
     return b;

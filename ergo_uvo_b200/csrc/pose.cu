@@ -682,7 +682,7 @@ size_t pnp_scratch_bytes(int n, int iterations) {
          (size_t)n * 3 * sizeof(float) + 64;
 }
 
-void launch_pnp_ransac(Ctx& c, const PnpArgs& a) {
+void launch_pnp_prepare(Ctx& c, const PnpArgs& a) {
   const uint32_t* rng = rng_table_device(c);
   const int iters = std::max(a.iterations, 1);
   UVO_REQUIRE((size_t)iters * 8 < (size_t)RNG_TABLE_SIZE, "solvePnPRansac: iterationsCount too large for the RNG table");
@@ -694,6 +694,10 @@ void launch_pnp_ransac(Ctx& c, const PnpArgs& a) {
   UVO_KERNEL(c, "k_pnp_subsets");
   k_pnp_subsets<<<1, 32, 0, c.stream>>>(a, rng);
   UVO_LAUNCH_CHECK(c);
+}
+
+void launch_pnp_solve(Ctx& c, const PnpArgs& a) {
+  const int iters = std::max(a.iterations, 1);
   UVO_KERNEL(c, "k_pnp_hyp");
   k_pnp_hyp<<<div_up(iters, 32), 32, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
@@ -706,6 +710,11 @@ void launch_pnp_ransac(Ctx& c, const PnpArgs& a) {
   UVO_KERNEL(c, "k_pnp_finalize");
   k_pnp_finalize<<<1, REFIT_THREADS, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
+}
+
+void launch_pnp_ransac(Ctx& c, const PnpArgs& a) {
+  launch_pnp_prepare(c, a);
+  launch_pnp_solve(c, a);
 }
 
 }  // namespace uvo

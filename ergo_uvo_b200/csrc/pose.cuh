@@ -76,7 +76,11 @@ struct PnpArgs {
   float* Xf;             // n x 3 f32 object points
   int* best;             // [0] best hypothesis, [1] best count
 };
-void launch_pnp_ransac(Ctx& c, const PnpArgs& a);
+void launch_pnp_ransac(Ctx& c, const PnpArgs& a);   // = prepare + solve
+// the two halves, for callers that split them over streams: prepare gathers the correspondences and rebuilds the
+// subset stream; solve runs hypotheses, scoring, the sequential bookkeeping replay and the refit
+void launch_pnp_prepare(Ctx& c, const PnpArgs& a);
+void launch_pnp_solve(Ctx& c, const PnpArgs& a);
 size_t pnp_scratch_bytes(int n, int iterations);
 
 // compute_median (math_utility.cpp:65-86) by rank selection: out[0] = median (mean of the two middle values for

@@ -232,7 +232,10 @@ __global__ void __launch_bounds__(256) k_surf_detect(const __grid_constant__ Sur
 
 void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity) {
   upload_tables(c);
-  for (int i = 0; i < b.n_img; i++) UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
+  for (int i = 0; i < b.n_img; i++) {
+    UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
+    UVO_CUDA(cudaMemsetAsync(b.im[i].rank, 0, (size_t)capacity * sizeof(int), c.stream));
+  }
   UVO_KERNEL(c, "k_surf_detect");
   k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(g, b, capacity);
   UVO_LAUNCH_CHECK(c);
@@ -253,42 +256,52 @@ __device__ __forceinline__ bool kp_precedes(float ra, float sa, int oa, float ya
   return xa < xb;
 }
 
+// 2-D rank sort: block (bi, bj) adds to rank[i] the number of keys of j-tile bj that precede key i.  Ranks are a
+// permutation (full ties broken by raw index), so the scatter needs no atomics and the output order is exactly
+// std::sort(KeypointGreater)'s for distinct keys.
 __global__ void __launch_bounds__(256) k_surf_rank(const __grid_constant__ SurfBatch b, int capacity) {
   __shared__ float4 s_k[256];
   __shared__ int s_o[256];
+  const SurfImage& im = b.im[blockIdx.z];
+  const int n = min(im.counters[0], capacity);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) im.counters[1] = n;
+  const int i0 = blockIdx.x * 256, j0 = blockIdx.y * 256;
+  if (i0 >= n || j0 >= n) return;
+  const int i = i0 + threadIdx.x, j = j0 + threadIdx.x;
+  if (j < n) {
+    const uvo_keypoint k = im.raw[j];
+    s_k[threadIdx.x] = make_float4(k.response, k.size, k.y, k.x);
+    s_o[threadIdx.x] = k.octave;
+  }
+  __syncthreads();
+  if (i >= n) return;
+  const uvo_keypoint me = im.raw[i];
+  const int m = min(256, n - j0);
+  int rank = 0;
+  for (int q = 0; q < m; q++) {
+    const float4 k = s_k[q];
+    const int jo = s_o[q];
+    const bool before = kp_precedes(k.x, k.y, jo, k.z, k.w, me.response, me.size, me.octave, me.y, me.x);
+    const bool same = (k.x == me.response) && (k.y == me.size) && (jo == me.octave) && (k.z == me.y) && (k.w == me.x);
+    rank += (before || (same && (j0 + q) < i)) ? 1 : 0;
+  }
+  if (rank) atomicAdd(&im.rank[i], rank);
+}
+
+__global__ void __launch_bounds__(256) k_surf_scatter(const __grid_constant__ SurfBatch b, int capacity) {
   const SurfImage& im = b.im[blockIdx.y];
   const int n = min(im.counters[0], capacity);
-  if (blockIdx.x == 0 && threadIdx.x == 0) im.counters[1] = n;
-  if ((int)(blockIdx.x * blockDim.x) >= n) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  uvo_keypoint me{};
-  if (i < n) me = im.raw[i];
-  int rank = 0;
-  for (int base = 0; base < n; base += 256) {
-    const int j = base + threadIdx.x;
-    if (j < n) {
-      const uvo_keypoint k = im.raw[j];
-      s_k[threadIdx.x] = make_float4(k.response, k.size, k.y, k.x);
-      s_o[threadIdx.x] = k.octave;
-    }
-    __syncthreads();
-    const int m = min(256, n - base);
-    if (i < n)
-      for (int q = 0; q < m; q++) {
-        const float4 k = s_k[q];
-        const int jo = s_o[q];
-        const bool before = kp_precedes(k.x, k.y, jo, k.z, k.w, me.response, me.size, me.octave, me.y, me.x);
-        const bool same = (k.x == me.response) && (k.y == me.size) && (jo == me.octave) && (k.z == me.y) && (k.w == me.x);
-        rank += (before || (same && (base + q) < i)) ? 1 : 0;
-      }
-    __syncthreads();
-  }
-  if (i < n) im.kps[rank] = me;
+  if (i < n) im.kps[im.rank[i]] = im.raw[i];
 }
 
 void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity) {
+  const int tiles = div_up(capacity, 256);
   UVO_KERNEL(c, "k_surf_rank");
-  k_surf_rank<<<dim3(div_up(capacity, 256), b.n_img), 256, 0, c.stream>>>(b, capacity);
+  k_surf_rank<<<dim3(tiles, tiles, b.n_img), 256, 0, c.stream>>>(b, capacity);
+  UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_surf_scatter");
+  k_surf_scatter<<<dim3(tiles, b.n_img), 256, 0, c.stream>>>(b, capacity);
   UVO_LAUNCH_CHECK(c);
 }
 
@@ -382,12 +395,15 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int DESC_THREADS = 128;
+constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows go one output row at a time
 
 // One block per keypoint (grid-stride).  Shared: 21x21 patch, 2x400 gradients, 64-vector.
 __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_constant__ SurfGeom g,
                                                                 const __grid_constant__ SurfBatch b,
                                                                 int upright) {
   __shared__ int s_patch[21][21];
+  __shared__ AreaSpan s_span[21];
+  __shared__ float s_buf[DESC_BUF_ROWS * 21];
   __shared__ float s_dx[400], s_dy[400];
   __shared__ float s_vec[64];
   __shared__ float s_scale;
@@ -518,44 +534,121 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
     // ---- resize(win -> 21x21, INTER_AREA) ----
     const double inv_scale = (double)21 / win_size;
     const double scale = 1. / inv_scale;
-    int iscale = __double2int_rn(scale);
+    const int iscale = __double2int_rn(scale);
     const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
-    for (int t = tid; t < 441; t += DESC_THREADS) {
-      const int py = t / 21, px = t - py * 21;
-      int out;
-      if (win_size == 21) {
-        out = ws.at(py, px);
-      } else if (area_fast) {
-        int acc = 0;
-        for (int ky = 0; ky < iscale; ky++)
-          for (int kx = 0; kx < iscale; kx++) {
-            const int sy = py * iscale + ky, sx = px * iscale + kx;
-            if (sy < win_size && sx < win_size) acc += ws.at(sy, sx);
-          }
-        if (iscale == 2) out = (acc + 2) >> 2;
-        else out = min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
-      } else {
-        const AreaSpan ys = area_span(py, win_size, scale), xs = area_span(px, win_size, scale);
+    if (tid < 21) s_span[tid] = area_span(tid, win_size, scale);  // same table for rows and columns (square window)
+    __syncthreads();
+    if (win_size == 21) {
+      for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t / 21][t % 21] = ws.at(t / 21, t % 21);
+    } else if (upright) {
+      // Separable form of OpenCV's ResizeArea_Invoker, exactly its arithmetic order: pass 1 reduces every window row
+      // i along j into buf[i][dx] (consecutive threads take consecutive i == consecutive image x: coalesced, each
+      // window pixel is read once), pass 2 accumulates beta * buf over the rows of each dy.  Windows taller than the
+      // shared buffer are processed one dy at a time.
+      const uint8_t* __restrict__ img = im.img;
+      const size_t pitch = im.pitch;
+      const int sx0 = ws.start_x, sy0 = ws.start_y;
+      auto pix = [&](int i, int j) -> int {
+        const int x = min(max(sx0 + i, 0), w - 1), y = min(max(sy0 - j, 0), h - 1);
+        return __ldg(img + (size_t)y * pitch + x);
+      };
+      auto row_reduce = [&](int i, int dx) -> float {  // buf[dx] of window row i
+        if (area_fast) {
+          int acc = 0;
+          for (int j = dx * iscale; j < dx * iscale + iscale; j++) acc += pix(i, j);
+          return __int_as_float(acc);
+        }
+        const AreaSpan xs = s_span[dx];
+        float buf = 0.f;
+        if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, xs.sx1 - 1), xs.a_l));
+        for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, sx), xs.a_f));
+        if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, xs.sx2), xs.a_r));
+        return buf;
+      };
+      auto col_reduce = [&](int dy, int dx, int row0) -> int {  // PATCH[dy][dx] from s_buf rows (offset row0)
+        if (area_fast) {
+          int acc = 0;
+          for (int i = dy * iscale; i < dy * iscale + iscale; i++) acc += __float_as_int(s_buf[(i - row0) * 21 + dx]);
+          if (iscale == 2) return (acc + 2) >> 2;
+          return min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
+        }
+        const AreaSpan ys = s_span[dy];
         float sum = 0.f;
         bool first = true;
-        auto row = [&](int sy, float beta) {
-          float buf = 0.f;
-          if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx1 - 1), xs.a_l));
-          for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, sx), xs.a_f));
-          if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx2), xs.a_r));
-          if (first) {
-            sum = __fmul_rn(beta, buf);
-            first = false;
-          } else {
-            sum = __fadd_rn(sum, __fmul_rn(beta, buf));
-          }
+        auto add = [&](int i, float beta) {
+          const float v = __fmul_rn(beta, s_buf[(i - row0) * 21 + dx]);
+          sum = first ? v : __fadd_rn(sum, v);
+          first = false;
         };
-        if (ys.has_l) row(ys.sx1 - 1, ys.a_l);
-        for (int sy = ys.sx1; sy < ys.sx2; sy++) row(sy, ys.a_f);
-        if (ys.has_r) row(ys.sx2, ys.a_r);
-        out = min(max(__float2int_rn(sum), 0), 255);
+        if (ys.has_l) add(ys.sx1 - 1, ys.a_l);
+        for (int i = ys.sx1; i < ys.sx2; i++) add(i, ys.a_f);
+        if (ys.has_r) add(ys.sx2, ys.a_r);
+        return min(max(__float2int_rn(sum), 0), 255);
+      };
+      if (win_size <= DESC_BUF_ROWS) {
+        for (int t = tid; t < win_size * 21; t += DESC_THREADS) {
+          const int dx = t / win_size, i = t - dx * win_size;
+          s_buf[i * 21 + dx] = row_reduce(i, dx);
+        }
+        __syncthreads();
+        for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t / 21][t % 21] = col_reduce(t / 21, t % 21, 0);
+      } else {
+        for (int dy = 0; dy < 21; dy++) {
+          int r0, r1;  // window rows feeding this dy
+          if (area_fast) {
+            r0 = dy * iscale;
+            r1 = r0 + iscale;
+          } else {
+            const AreaSpan ys = s_span[dy];
+            r0 = ys.has_l ? ys.sx1 - 1 : ys.sx1;
+            r1 = ys.has_r ? ys.sx2 + 1 : ys.sx2;
+          }
+          const int nr = r1 - r0;
+          for (int t = tid; t < nr * 21; t += DESC_THREADS) {
+            const int dx = t / nr, r = t - dx * nr;
+            s_buf[r * 21 + dx] = row_reduce(r0 + r, dx);
+          }
+          __syncthreads();
+          if (tid < 21) s_patch[dy][tid] = col_reduce(dy, tid, r0);
+          __syncthreads();
+        }
       }
-      s_patch[py][px] = out;
+    } else {
+      for (int t = tid; t < 441; t += DESC_THREADS) {
+        const int py = t / 21, px = t - py * 21;
+        int out;
+        if (area_fast) {
+          int acc = 0;
+          for (int ky = 0; ky < iscale; ky++)
+            for (int kx = 0; kx < iscale; kx++) {
+              const int sy = py * iscale + ky, sx = px * iscale + kx;
+              if (sy < win_size && sx < win_size) acc += ws.at(sy, sx);
+            }
+          if (iscale == 2) out = (acc + 2) >> 2;
+          else out = min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
+        } else {
+          const AreaSpan ys = s_span[py], xs = s_span[px];
+          float sum = 0.f;
+          bool first = true;
+          auto row = [&](int sy, float beta) {
+            float buf = 0.f;
+            if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx1 - 1), xs.a_l));
+            for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, sx), xs.a_f));
+            if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)ws.at(sy, xs.sx2), xs.a_r));
+            if (first) {
+              sum = __fmul_rn(beta, buf);
+              first = false;
+            } else {
+              sum = __fadd_rn(sum, __fmul_rn(beta, buf));
+            }
+          };
+          if (ys.has_l) row(ys.sx1 - 1, ys.a_l);
+          for (int sy = ys.sx1; sy < ys.sx2; sy++) row(sy, ys.a_f);
+          if (ys.has_r) row(ys.sx2, ys.a_r);
+          out = min(max(__float2int_rn(sum), 0), 255);
+        }
+        s_patch[py][px] = out;
+      }
     }
     __syncthreads();
     // ---- Haar gradients with Gaussian weights ----

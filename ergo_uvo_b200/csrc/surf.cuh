@@ -42,6 +42,7 @@ struct SurfImage {
   uvo_keypoint* raw = nullptr;    // unordered detections
   uvo_keypoint* kps = nullptr;    // sorted (OpenCV order), compacted
   float* desc = nullptr;          // capacity x 64
+  int* rank = nullptr;            // capacity ints, zeroed per frame (rank sort accumulator)
   int* counters = nullptr;        // [0] raw count (may exceed capacity => overflow), [1] final count, [2..3] spare
 };
 
