@@ -78,6 +78,23 @@ def summarise_clocks(lines):
             "samples": len(sm)}
 
 
+def aggregate_over_ranks(dist, ms_list, count_list, device):
+    """multi-GPU reduction used by the bench: MAX over ranks of each time, SUM over ranks of each count (replicas:
+    one independent sequence per rank, no data-path collective).  Works with nccl (cuda) and gloo (cpu)."""
+    import torch
+    t = torch.tensor(ms_list, dtype=torch.float64, device=device)
+    v = torch.tensor(count_list, dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    return t.tolist(), v.tolist()
+
+
+def sequence_seed(rank):
+    """independent camera sequence per rank (seeds 1300+g)"""
+    return 1300 + int(rank)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,7 +225,7 @@ def run_gpu(args):
     stream = torch.cuda.Stream(device=local)
     ctx = U.Context(local, stream=stream.cuda_stream)
 
-    seq = make_sequence(1300 + rank)
+    seq = make_sequence(sequence_seed(rank))
     if args.threshold:
         thr, n0 = args.threshold, -1
     else:
@@ -316,12 +333,8 @@ def run_gpu(args):
     kr, _ = vo.last_keypoints(True)
 
     # ---- max over ranks
-    t = torch.tensor([ms_dev, ms_host], dtype=torch.float64, device="cuda")
-    v = torch.tensor([float(valid_dev), float(valid_host)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(v, op=dist.ReduceOp.SUM)
-    ms_dev, ms_host = t.tolist()
+    (ms_dev, ms_host), v = aggregate_over_ranks(dist if world > 1 else None, [ms_dev, ms_host],
+                                                [float(valid_dev), float(valid_host)], "cuda")
     total_frames = args.steps * world
     value = total_frames / (ms_dev * 1e-3)
     e2e = total_frames / (ms_host * 1e-3)
@@ -380,7 +393,7 @@ def run_gpu(args):
                     "ms_per_step": ms_host / args.steps, "api": "uvo_stereo_frame (host pinned images, synchronous)"},
             "gpu_launches": int(launches),
             "launches_per_frame": launches / float(args.steps),
-            "valid_frames": {"device": int(v[0].item()), "host": int(v[1].item()), "of": total_frames},
+            "valid_frames": {"device": int(v[0]), "host": int(v[1]), "of": total_frames},
             "clocks": summarise_clocks(samples),
             "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage, "kernels": kern,

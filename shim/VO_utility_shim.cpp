@@ -1,0 +1,170 @@
+// shim/VO_utility_shim.cpp -- reference-side binding (NOT compiled in this repository: it needs the OpenCV C++ and
+// ROS headers the reference builds against).
+//
+// Drop-in replacement translation unit for uvo_libraries/src/VO_utility.cpp: it defines the same C++ free functions
+// with the same signatures (uvo_libraries/include/uvo_libraries/VO_utility.h:96-117), reads the same header-defined
+// parameter globals (VO_utility.h:25-89) at call time, and forwards the arithmetic to libuvo_b200.so through the C ABI
+// of include/uvo_c.h.  Outputs are appended (push_back), never cleared, exactly like the reference
+// (VO_utility.cpp:538, :216-217).  Link: add_library(uvo_libraries math_utility.cpp VO_utility_shim.cpp) +
+// target_link_libraries(uvo_libraries uvo_b200 ${catkin_LIBRARIES}).
+#include "uvo_libraries/VO_utility.h"
+
+#include "uvo_c.h"
+
+namespace {
+uvo_ctx* ctx() {  // lazy process-wide context: the reference API has no init/teardown
+  static uvo_ctx* c = nullptr;
+  if (!c && uvo_ctx_create(0, nullptr, &c) != UVO_OK) {
+    ROS_FATAL("uvo_b200: no CUDA device (there is no CPU fallback)");
+    throw cv::Exception(cv::Error::GpuNotSupported, "uvo_b200: no CUDA device", __func__, __FILE__, __LINE__);
+  }
+  return c;
+}
+void check(int rc) {
+  if (rc != UVO_OK) throw cv::Exception(cv::Error::StsError, uvo_last_error(ctx()), "uvo_b200", __FILE__, __LINE__);
+}
+uvo_params params_from_globals() {
+  uvo_params p;
+  uvo_default_params(1, &p);
+  p.clahe = CLAHE_CORRECTION;
+  p.clip_limit = CLIP_LIMIT;
+  p.distance = DISTANCE;
+  p.lowe_ratio = LOWE_RATIO_THRESHOLD;
+  p.reprojection_tolerance = REPROJECTION_TOLERANCE;
+  p.min_num_features = MIN_NUM_FEATURES;
+  p.min_num_3dpoints = MIN_NUM_3DPOINTS;
+  p.min_num_inliers = MIN_NUM_INLIERS;
+  p.iterations_count = ITERATIONS_COUNT;
+  p.reprojection_error = REPROJECTION_ERROR_THRESHOLD;
+  p.confidence = CONFIDENCE;
+  p.pnp_method_flag = PNP_METHOD_FLAG;
+  p.surf_min_hessian = SURF_MIN_HESSIAN;
+  p.surf_octaves = SURF_OCTAVES_NUMBER;
+  p.surf_octave_layers = SURF_OCTAVES_LAYERS;
+  p.surf_extended = SURF_EXTENDED;
+  p.surf_upright = SURF_UPRIGHT;
+  return p;
+}
+void K4(const Mat& K, double k[4]) {
+  k[0] = K.at<double>(0, 0);
+  k[1] = K.at<double>(1, 1);
+  k[2] = K.at<double>(0, 2);
+  k[3] = K.at<double>(1, 2);
+}
+}  // namespace
+
+// VO_utility.cpp:337-379 (native-size branch; the INTER_AREA pre-resize branch stays on cv::resize)
+Mat get_image(const Mat& current_img, const Mat& cameraMatrix, const Mat& distortionCoeff, const Mat& newCamMatrix) {
+  Mat src = current_img;
+  const double ratio = (double)src.cols / (double)DESIRED_WIDTH;
+  const int desired_height = (int)(src.rows / ratio);
+  if (!(src.cols == DESIRED_WIDTH && src.rows == desired_height))
+    resize(current_img, src, Size(DESIRED_WIDTH, desired_height), 0, 0, INTER_AREA);
+  CV_Assert(src.type() == CV_8UC3);  // cvtColor(RGB2GRAY) throws on anything else
+  uvo_camera cam;
+  double k[4], nk[4];
+  K4(cameraMatrix, k);
+  K4(newCamMatrix, nk);
+  cam = {k[0], k[1], k[2], k[3], distortionCoeff.at<double>(0), distortionCoeff.at<double>(1),
+         distortionCoeff.at<double>(2), distortionCoeff.at<double>(3), nk[0], nk[1], nk[2], nk[3]};
+  Mat out(src.rows, src.cols, CV_8UC1);
+  check(uvo_get_image(ctx(), src.data, src.cols, src.rows, src.step, &cam, CLAHE_CORRECTION, CLIP_LIMIT, out.data,
+                      out.step));
+  return out;
+}
+
+// VO_utility.cpp:91-126 (SURF branch; the other detectors stay on OpenCV)
+void detect_features(Mat img, vector<KeyPoint>& keypoints, Mat& descriptors) {
+  CV_Assert(FEATURE_DETECTOR == "SURF" && img.type() == CV_8UC1);
+  uvo_params p = params_from_globals();
+  std::vector<uvo_keypoint> k(p.max_features);
+  Mat d(p.max_features, 64, CV_32F);
+  int n = 0;
+  check(uvo_detect_features(ctx(), img.data, img.cols, img.rows, img.step, &p, k.data(), d.ptr<float>(),
+                            p.max_features, &n));
+  static_assert(sizeof(uvo_keypoint) == sizeof(KeyPoint), "cv::KeyPoint layout");
+  keypoints.assign(reinterpret_cast<KeyPoint*>(k.data()), reinterpret_cast<KeyPoint*>(k.data()) + n);
+  descriptors = d.rowRange(0, n).clone();
+  ROS_INFO("FEATURES EXTRACTED - CURR. IMAGE: %lu", keypoints.size());
+}
+
+// VO_utility.cpp:515-543
+void match_features(vector<KeyPoint> keypoints1, vector<KeyPoint> keypoints2, Mat descriptors1, Mat descriptors2,
+                    vector<DMatch>& matches) {
+  std::vector<uvo_dmatch> m(std::max(descriptors1.rows, 1));
+  int n = 0;
+  check(uvo_match_features(ctx(), descriptors1.ptr<float>(), descriptors1.rows, descriptors2.ptr<float>(),
+                           descriptors2.rows, 64, (float)LOWE_RATIO_THRESHOLD, m.data(), &n));
+  ROS_INFO("MATCHES BEFORE LOWE'S RATIO: %d", descriptors1.rows);
+  for (int i = 0; i < n; i++) matches.push_back(DMatch(m[i].queryIdx, m[i].trainIdx, m[i].imgIdx, m[i].distance));
+  ROS_INFO("MATCHES AFTER LOWE'S RATIO: %lu", matches.size());
+}
+
+// VO_utility.cpp:551-573
+void match_features(vector<KeyPoint> keypoints1, vector<KeyPoint> keypoints2, Mat descriptors1, Mat descriptors2,
+                    vector<DMatch>& matches, vector<Point2f>& keypoints1_conv, vector<Point2f>& keypoints2_conv) {
+  const size_t first = matches.size();
+  match_features(keypoints1, keypoints2, descriptors1, descriptors2, matches);
+  for (size_t i = first; i < matches.size(); i++) {
+    keypoints1_conv.push_back(keypoints1[matches[i].queryIdx].pt);
+    keypoints2_conv.push_back(keypoints2[matches[i].trainIdx].pt);
+  }
+}
+
+// VO_utility.cpp:188-237
+void extract_3Dpoints(vector<Point2f> keypoints1_conv, vector<Point2f> keypoints2_conv, Mat R1, Mat t1, Mat R2, Mat t2,
+                      Mat cameraMatrix1, Mat cameraMatrix2, Mat points4D, Mat& very_good_cam1_points,
+                      Mat& very_good_indexes) {
+  const int n = (int)keypoints1_conv.size();
+  CV_Assert(points4D.type() == CV_32F && points4D.rows == 4 && points4D.isContinuous());
+  std::vector<double> pts(3 * (size_t)std::max(n, 1));
+  std::vector<int32_t> idx(std::max(n, 1));
+  double k1[4], k2[4];
+  K4(cameraMatrix1, k1);
+  K4(cameraMatrix2, k2);
+  int m = 0;
+  check(uvo_extract_3dpoints(ctx(), &keypoints1_conv[0].x, &keypoints2_conv[0].x, n, R1.ptr<double>(),
+                             t1.ptr<double>(), R2.ptr<double>(), t2.ptr<double>(), k1, k2, points4D.ptr<float>(),
+                             REPROJECTION_TOLERANCE, MIN_NUM_3DPOINTS, pts.data(), idx.data(), &m));
+  for (int i = 0; i < m; i++) {
+    very_good_indexes.push_back(idx[i]);
+    very_good_cam1_points.push_back(Mat(1, 3, CV_64F, &pts[3 * i]).clone());
+  }
+}
+
+// VO_utility.cpp:725-748
+bool select_estimation_method(const vector<Point2f>& keypoints1_conv, const vector<Point2f>& keypoints2_conv) {
+  int use_e = 1;
+  check(uvo_select_estimation_method(ctx(), &keypoints1_conv[0].x, &keypoints2_conv[0].x, (int)keypoints1_conv.size(),
+                                     DISTANCE, &use_e));
+  if (!use_e) ROS_INFO("BASELINE IS TOO LOW. USING HOMOGRAPHY!");
+  return use_e != 0;
+}
+
+// The three cv:: calls the node makes directly (visual_odometry.h:355/:631, :647, :673) are not part of
+// uvo_libraries.  Under a strictly unchanged node they stay on OpenCV unless this object also interposes them; the
+// one-line node patch is to call these instead:
+namespace uvo_shim {
+void triangulatePoints(const Mat& P1, const Mat& P2, const vector<Point2f>& a, const vector<Point2f>& b, Mat& out4) {
+  out4.create(4, (int)a.size(), CV_32F);
+  check(uvo_triangulate_points(ctx(), P1.ptr<double>(), P2.ptr<double>(), &a[0].x, &b[0].x, (int)a.size(),
+                               out4.ptr<float>()));
+}
+bool solvePnPRansac(const Mat& X /* Nx3 CV_64F */, const vector<Point2f>& x, const Mat& K, Mat& rvec, Mat& tvec,
+                    int iters, float err, double conf, Mat& inliers) {
+  double k[4];
+  K4(K, k);
+  std::vector<int32_t> inl(std::max(X.rows, 1));
+  int n = 0, hyps = 0;
+  rvec.create(3, 1, CV_64F);
+  tvec.create(3, 1, CV_64F);
+  check(uvo_solve_pnp_ransac(ctx(), X.ptr<double>(), &x[0].x, X.rows, k, iters, err, conf, rvec.ptr<double>(),
+                             tvec.ptr<double>(), inl.data(), &n, &hyps));
+  inliers = n ? Mat(n, 1, CV_32S, inl.data()).clone() : Mat();
+  return n > 0;
+}
+}  // namespace uvo_shim
+
+// compute_projection_matrix, convert_from_homogeneous_coords, extract_inliers, reproject_errors,
+// resize_camera_matrix, select_desired_*, the parameter loaders and show_matches carry no hot arithmetic and are
+// compiled unchanged from the reference's VO_utility.cpp.
