@@ -141,38 +141,56 @@ __global__ void k_frame_result(FrameCtrl* ctrl, FrameState* st, const double* pn
 static const char* kStageNames[UVO_N_STAGES] = {"h2d",        "get_image",    "surf", "match_stereo", "match_temporal",
                                                 "triangulate+extract3d", "pnp_ransac", "result+d2h"};
 
+// One lane = every buffer one frame needs + its own stream.  Frame t runs entirely on lane t % N_LANES, so the kernels
+// of up to N_LANES consecutive frames are in flight on the GPU at once: the front end of frame t+1 (which does not
+// depend on frame t at all) fills the SMs the narrow, latency-bound stages of frame t (rank sort, merges, RANSAC
+// hypotheses, refit) leave idle.  Cross-lane order is restored with events exactly where the node's recurrence needs it:
+//   gather(t)        after gather(t-1)        (vo_initialized, previous n_as)
+//   temporal match/triangulate(t) read the after-stereo sets of lane (t-1)
+//   gather(t)        after triangulate(t-N_LANES+1)   (lane t's after-stereo sets are still being read by the frame after
+//                                                      the one that last used this lane)
+//   result(t)        after result(t-1)        (t_prevCam_currCam carried across gate failures)
+struct Lane {
+  cudaStream_t stream = nullptr;
+  FrontEnd fe;
+  DevBuf<uint8_t> src[2];  // staging for host images
+  DevBuf<uvo_keypoint> kL_as, kR_as;
+  DevBuf<float> dL_as;
+  DevBuf<FrameCtrl> ctrl;
+  DevBuf<uvo_dmatch> m_stereo, m_temporal;
+  DevBuf<Knn2> knn_scratch;
+  DevBuf<float> pts1, pts2, X4;
+  DevBuf<double> good_pts, tmp_pts;
+  DevBuf<int32_t> good_idx, tmp_idx;
+  DevBuf<double> pnp_result;
+  DevBuf<int32_t> inliers;
+  DevBuf<int> small;  // [0] n_inliers [1] hyps [2..3] best
+  DevBuf<uint8_t> pnp_scratch;
+  cudaEvent_t ev_gather = nullptr, ev_consumed = nullptr, ev_result = nullptr;
+  bool used = false;
+  ~Lane() {
+    if (ev_gather) cudaEventDestroy(ev_gather);
+    if (ev_consumed) cudaEventDestroy(ev_consumed);
+    if (ev_result) cudaEventDestroy(ev_result);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
 struct uvo_stereo {
+  static constexpr int N_LANES = 4;
+  static constexpr int RING = 8;
   uvo_ctx* ctx = nullptr;
   int w = 0, h = 0, cap = 0;
   uvo_camera cam[2];
   uvo_params prm;
   double R_right[9], t_right[3];
   double P_left[12], P_right[12];  // P_eye_using_left_as_world, P_using_left_as_world (visual_odometry.h:460-462)
-  FrontEnd fe;
-  DevBuf<uint8_t> src[2];
+  Lane lane[N_LANES];
   size_t src_pitch = 0;
-  // double-buffered after-stereo sets: [parity]
-  DevBuf<uvo_keypoint> kL_as[2], kR_as[2];
-  DevBuf<float> dL_as[2];
-  DevBuf<FrameCtrl> ctrl;  // 2
   DevBuf<FrameState> state;
-  DevBuf<uvo_dmatch> m_stereo, m_temporal;
-  DevBuf<Knn2> knn_scratch;
-  DevBuf<float> pts1, pts2, X4;
-  DevBuf<double> good_pts, tmp_pts;
-  DevBuf<int32_t> good_idx, tmp_idx;
-  // pose stage (side stream), double-buffered by frame parity
-  DevBuf<double> pnp_result[2];
-  DevBuf<int32_t> inliers[2];
-  DevBuf<int> small[2];  // [0] n_inliers [1] hyps [2..3] best
-  DevBuf<uint8_t> pnp_scratch[2];
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_main[2] = {}, ev_side[2] = {};  // hand-over main -> side, and side done, per parity
-  bool side_used[2] = {false, false};
   DevBuf<uvo_stereo_result> d_result;  // ring
   PinnedBuf<uvo_stereo_result> h_result;
-  static constexpr int RING = 8;
-  int parity = 0;
+  cudaEvent_t ev_in = nullptr;  // caller's work on the ctx stream -> lanes
   long frame_no = 0;
   std::deque<std::pair<int, cudaEvent_t>> pending;  // (slot, done event)
   cudaEvent_t ev[UVO_N_STAGES + 1] = {};
@@ -180,15 +198,13 @@ struct uvo_stereo {
   float stage_ms[UVO_N_STAGES] = {};
   bool has_timing = false;
 
+  Lane& last_lane() { return lane[(int)((frame_no + N_LANES - 1) % N_LANES)]; }
+
   ~uvo_stereo() {
     for (auto& p : pending) cudaEventDestroy(p.second);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
-      if (ev_main[i]) cudaEventDestroy(ev_main[i]);
-      if (ev_side[i]) cudaEventDestroy(ev_side[i]);
-    }
-    if (side) cudaStreamDestroy(side);
+    if (ev_in) cudaEventDestroy(ev_in);
   }
 };
 
@@ -224,102 +240,127 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
   proj(KL, I, z, s->P_left);
   proj(KR, R_right, t_right, s->P_right);
   const int cap = s->cap;
-  s->fe.init(w, h, 2, cap);
   s->src_pitch = ((size_t)3 * w + 15) & ~(size_t)15;
-  for (int i = 0; i < 2; i++) {
-    s->src[i].ensure(s->src_pitch * h);
-    s->kL_as[i].ensure(cap);
-    s->kR_as[i].ensure(cap);
-    s->dL_as[i].ensure((size_t)cap * 64);
+  for (Lane& l : s->lane) {
+    UVO_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    l.fe.init(w, h, 2, cap);
+    l.kL_as.ensure(cap);
+    l.kR_as.ensure(cap);
+    l.dL_as.ensure((size_t)cap * 64);
+    l.ctrl.ensure(1);
+    UVO_CUDA(cudaMemsetAsync(l.ctrl.get(), 0, sizeof(FrameCtrl), c.stream));
+    l.m_stereo.ensure(cap);
+    l.m_temporal.ensure(cap);
+    l.knn_scratch.ensure((size_t)(MATCH_SPLITS + 1) * cap);
+    l.pts1.ensure(2 * (size_t)cap);
+    l.pts2.ensure(2 * (size_t)cap);
+    l.X4.ensure(4 * (size_t)cap);
+    l.good_pts.ensure(3 * (size_t)cap);
+    l.tmp_pts.ensure(3 * (size_t)cap);
+    l.good_idx.ensure(cap);
+    l.tmp_idx.ensure(cap);
+    l.inliers.ensure(cap);
+    l.pnp_result.ensure(8);
+    l.small.ensure(8);
+    UVO_CUDA(cudaMemsetAsync(l.small.get(), 0, 8 * sizeof(int), c.stream));
+    UVO_CUDA(cudaMemsetAsync(l.pnp_result.get(), 0, 8 * sizeof(double), c.stream));
+    l.pnp_scratch.ensure(pnp_scratch_bytes(cap, prm->iterations_count) + 4096);
+    UVO_CUDA(cudaEventCreateWithFlags(&l.ev_gather, cudaEventDisableTiming));
+    UVO_CUDA(cudaEventCreateWithFlags(&l.ev_consumed, cudaEventDisableTiming));
+    UVO_CUDA(cudaEventCreateWithFlags(&l.ev_result, cudaEventDisableTiming));
   }
-  s->ctrl.ensure(2);
   s->state.ensure(1);
-  UVO_CUDA(cudaMemsetAsync(s->ctrl.get(), 0, 2 * sizeof(FrameCtrl), c.stream));
   UVO_CUDA(cudaMemsetAsync(s->state.get(), 0, sizeof(FrameState), c.stream));
-  s->m_stereo.ensure(cap);
-  s->m_temporal.ensure(cap);
-  s->knn_scratch.ensure((size_t)(MATCH_SPLITS + 1) * cap);
-  s->pts1.ensure(2 * (size_t)cap);
-  s->pts2.ensure(2 * (size_t)cap);
-  s->X4.ensure(4 * (size_t)cap);
-  s->good_pts.ensure(3 * (size_t)cap);
-  s->tmp_pts.ensure(3 * (size_t)cap);
-  s->good_idx.ensure(cap);
-  s->tmp_idx.ensure(cap);
-  for (int i = 0; i < 2; i++) {
-    s->inliers[i].ensure(cap);
-    s->pnp_result[i].ensure(8);
-    s->small[i].ensure(8);
-    UVO_CUDA(cudaMemsetAsync(s->small[i].get(), 0, 8 * sizeof(int), c.stream));
-    UVO_CUDA(cudaMemsetAsync(s->pnp_result[i].get(), 0, 8 * sizeof(double), c.stream));
-    s->pnp_scratch[i].ensure(pnp_scratch_bytes(cap, prm->iterations_count) + 4096);
-    UVO_CUDA(cudaEventCreateWithFlags(&s->ev_main[i], cudaEventDisableTiming));
-    UVO_CUDA(cudaEventCreateWithFlags(&s->ev_side[i], cudaEventDisableTiming));
-  }
-  UVO_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   s->d_result.ensure(uvo_stereo::RING);
   s->h_result.ensure(uvo_stereo::RING);
+  UVO_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
   for (auto& e : s->ev) UVO_CUDA(cudaEventCreate(&e));
   rng_table_device(c);
   UVO_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// enqueue every kernel of one frame on the ctx stream; images already on the device
-static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt, int slot) {
+// enqueue every kernel of one frame on its lane's stream.  Images: device pointers (host == nullptr) or pinned/pageable
+// host pointers that are first copied into the lane's staging buffers on the same stream.
+static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt, int slot,
+                           bool from_host) {
   Ctx& c = s->ctx->c;
   const uvo_params& p = s->prm;
   const int cap = s->cap;
-  const int cur = s->parity, prv = s->parity ^ 1;
-  FrameCtrl* ctrl = s->ctrl.get() + cur;
-  FrameCtrl* pctrl = s->ctrl.get() + prv;
+  constexpr int NL = uvo_stereo::N_LANES;
+  const int li = (int)(s->frame_no % NL);
+  Lane& L = s->lane[li];
+  Lane& PL = s->lane[(li + NL - 1) % NL];   // lane of frame t-1
+  Lane& NX = s->lane[(li + 1) % NL];        // lane of frame t-NL+1: the last reader of this lane's after-stereo sets
+  FrameCtrl* ctrl = L.ctrl.get();
+  FrameCtrl* pctrl = PL.ctrl.get();
   const GateParams g{p.min_num_features, p.min_num_3dpoints, p.min_num_inliers, cap};
+  cudaStream_t caller_stream = c.stream;
+  // whatever the caller enqueued on the context stream (e.g. the production of the device images) comes first
+  UVO_CUDA(cudaEventRecord(s->ev_in, caller_stream));
+  UVO_CUDA(cudaStreamWaitEvent(L.stream, s->ev_in, 0));
+  c.stream = L.stream;
+  struct Restore {
+    Ctx& c;
+    cudaStream_t st;
+    ~Restore() { c.stream = st; }
+  } restore{c, caller_stream};
   auto mark = [&](int i) {
     if (s->timing) UVO_CUDA(cudaEventRecord(s->ev[i], c.stream));
   };
-  // frame t reuses the control block and pose scratch of frame t-2: its pose stage (side stream) must be done
-  if (s->side_used[cur]) UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_side[cur], 0));
+  mark(0);
+  if (from_host) {
+    UVO_CUDA(cudaMemcpy2DAsync(L.src[0].get(), s->src_pitch, dL, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
+                               c.stream));
+    UVO_CUDA(cudaMemcpy2DAsync(L.src[1].get(), s->src_pitch, dR, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
+                               c.stream));
+    dL = L.src[0].get();
+    dR = L.src[1].get();
+    pitch = s->src_pitch;
+  }
   mark(1);
   // 1. get_image x2 (visual_odometry.h:542-543)
-  s->fe.prep(c, 0, dL, pitch, s->cam[0], p.clahe, p.clip_limit);
-  s->fe.prep(c, 1, dR, pitch, s->cam[1], p.clahe, p.clip_limit);
+  L.fe.prep(c, 0, dL, pitch, s->cam[0], p.clahe, p.clip_limit);
+  L.fe.prep(c, 1, dR, pitch, s->cam[1], p.clahe, p.clip_limit);
   mark(2);
   // 2. detect_features x2 (:548-549), both images batched through each kernel
-  s->fe.surf(c, 0, 2, p);
-  const int* cL = s->fe.counters.get();
-  const int* cR = s->fe.counters.get() + 4;
+  L.fe.surf(c, 0, 2, p);
+  const int* cL = L.fe.counters.get();
+  const int* cR = L.fe.counters.get() + 4;
   UVO_KERNEL(c, "k_gate_features");
   k_gate_features<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, g);
   UVO_LAUNCH_CHECK(c);
   mark(3);
   // 3. match_features(curr_left, curr_right) (:558)
   MatchArgs ms{};
-  ms.q = s->fe.desc[0].get();
-  ms.t = s->fe.desc[1].get();
+  ms.q = L.fe.desc[0].get();
+  ms.t = L.fe.desc[1].get();
   ms.nq_dev = &ctrl->nq_stereo;
   ms.nt_dev = cR + 1;
   ms.nq = cap;
   ms.nt = cap;
   ms.ratio = (float)p.lowe_ratio;
-  ms.partial = s->knn_scratch.get();
-  ms.knn = s->knn_scratch.get() + (size_t)MATCH_SPLITS * cap;
-  ms.matches = s->m_stereo.get();
+  ms.partial = L.knn_scratch.get();
+  ms.knn = L.knn_scratch.get() + (size_t)MATCH_SPLITS * cap;
+  ms.matches = L.m_stereo.get();
   ms.n_matches = &ctrl->n_stereo;
   launch_match(c, ms);
-  // 4. gathers (:569-579)
+  // 4. gathers (:569-579).  From here on the frame depends on its predecessor.
+  if (PL.used) UVO_CUDA(cudaStreamWaitEvent(c.stream, PL.ev_gather, 0));
+  if (NX.used && &NX != &PL) UVO_CUDA(cudaStreamWaitEvent(c.stream, NX.ev_consumed, 0));
   UVO_KERNEL(c, "k_gather_after_stereo");
-  k_gather_after_stereo<<<2 * c.sm_count, 256, 0, c.stream>>>(s->m_stereo.get(), ctrl, pctrl, s->state.get(),
-                                                            s->fe.kps[0].get(), s->fe.kps[1].get(),
-                                                            s->fe.desc[0].get(), s->kL_as[cur].get(),
-                                                            s->kR_as[cur].get(), s->dL_as[cur].get(), g);
+  k_gather_after_stereo<<<2 * c.sm_count, 256, 0, c.stream>>>(L.m_stereo.get(), ctrl, pctrl, s->state.get(),
+                                                            L.fe.kps[0].get(), L.fe.kps[1].get(), L.fe.desc[0].get(),
+                                                            L.kL_as.get(), L.kR_as.get(), L.dL_as.get(), g);
   UVO_LAUNCH_CHECK(c);
+  UVO_CUDA(cudaEventRecord(L.ev_gather, c.stream));
   mark(4);
   // 5. triangular match: prev-left-after-stereo (query) vs all current left features (train) (:592)
   MatchArgs mt = ms;
-  mt.q = s->dL_as[prv].get();
-  mt.t = s->fe.desc[0].get();
+  mt.q = PL.dL_as.get();
+  mt.t = L.fe.desc[0].get();
   mt.nq_dev = &ctrl->nq_temporal;
   mt.nt_dev = cL + 1;
-  mt.matches = s->m_temporal.get();
+  mt.matches = L.m_temporal.get();
   mt.n_matches = &ctrl->n_temporal;
   launch_match(c, mt);
   mark(5);
@@ -327,23 +368,24 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   TriangulateArgs ta{};
   memcpy(ta.P1, s->P_left, sizeof(ta.P1));
   memcpy(ta.P2, s->P_right, sizeof(ta.P2));
-  ta.matches = s->m_temporal.get();
-  ta.kps1 = s->kL_as[prv].get();
-  ta.kps2 = s->kR_as[prv].get();
+  ta.matches = L.m_temporal.get();
+  ta.kps1 = PL.kL_as.get();
+  ta.kps2 = PL.kR_as.get();
   ta.n_dev = &ctrl->n_temporal;
   ta.n = cap;
   ta.min_points = p.min_num_features;  // if (results_match_prev_curr.size() > MIN_NUM_FEATURES)
   ta.gate_dev = &ctrl->nq_temporal;
-  ta.out4 = s->X4.get();
+  ta.out4 = L.X4.get();
   ta.stride = cap;
-  ta.pts1_out = s->pts1.get();
-  ta.pts2_out = s->pts2.get();
+  ta.pts1_out = L.pts1.get();
+  ta.pts2_out = L.pts2.get();
   ta.n_out = &ctrl->n_tri;
   launch_triangulate(c, ta);
+  UVO_CUDA(cudaEventRecord(L.ev_consumed, c.stream));  // the previous frame's after-stereo sets are no longer needed
   Extract3dArgs ea{};
-  ea.kp1 = s->pts1.get();
-  ea.kp2 = s->pts2.get();
-  ea.p4 = s->X4.get();
+  ea.kp1 = L.pts1.get();
+  ea.kp2 = L.pts2.get();
+  ea.p4 = L.X4.get();
   ea.stride = cap;
   ea.n_dev = &ctrl->n_tri;
   ea.n = cap;
@@ -358,19 +400,19 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   memcpy(ea.K2, KR, sizeof(KR));
   ea.tol = p.reprojection_tolerance;
   ea.min3d = p.min_num_3dpoints;
-  ea.out_pts = s->good_pts.get();
-  ea.out_idx = s->good_idx.get();
+  ea.out_pts = L.good_pts.get();
+  ea.out_idx = L.good_idx.get();
   ea.out_count = &ctrl->n_3d;
-  ea.tmp_pts = s->tmp_pts.get();
-  ea.tmp_idx = s->tmp_idx.get();
+  ea.tmp_pts = L.tmp_pts.get();
+  ea.tmp_idx = L.tmp_idx.get();
   launch_extract3d(c, ea);
   mark(6);
   // 9-10. solvePnPRansac(good_prevCam_points, curr left keypoints of the surviving matches) (:638-648)
   PnpArgs pa{};
-  pa.X = s->good_pts.get();
-  pa.x_idx = s->good_idx.get();
-  pa.matches = s->m_temporal.get();
-  pa.kps = s->fe.kps[0].get();
+  pa.X = L.good_pts.get();
+  pa.x_idx = L.good_idx.get();
+  pa.matches = L.m_temporal.get();
+  pa.kps = L.fe.kps[0].get();
   pa.n_dev = &ctrl->n_3d;
   pa.n = cap;
   memcpy(pa.K, KL, sizeof(KL));
@@ -378,14 +420,14 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   pa.reproj_err = (float)p.reprojection_error;
   pa.confidence = p.confidence;
   pa.min_points = p.min_num_3dpoints;  // if (good_prevCam_points.rows > MIN_NUM_3DPOINTS)
-  pa.result = s->pnp_result[cur].get();
-  pa.inliers = s->inliers[cur].get();
-  pa.n_inliers = s->small[cur].get();
-  pa.hyps = s->small[cur].get() + 1;
-  pa.best = s->small[cur].get() + 2;
+  pa.result = L.pnp_result.get();
+  pa.inliers = L.inliers.get();
+  pa.n_inliers = L.small.get();
+  pa.hyps = L.small.get() + 1;
+  pa.best = L.small.get() + 2;
   {
     const int iters = std::max(p.iterations_count, 1);
-    uint8_t* b = s->pnp_scratch[cur].get();
+    uint8_t* b = L.pnp_scratch.get();
     auto take = [&](size_t bytes) {
       uint8_t* r = b;
       b += (bytes + 255) & ~(size_t)255;
@@ -397,35 +439,25 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     pa.xs = (float*)take(sizeof(float) * 2 * cap);
     pa.Xf = (float*)take(sizeof(float) * 3 * cap);
   }
-  // the gathers (which read buffers the next frame overwrites) and the subset stream stay on the main stream; the
-  // long, narrow part of the pose stage -- hypotheses, scoring, bookkeeping, refit, result -- moves to a side stream so
-  // that it overlaps the next frame's front end (it only touches its own parity of the pose scratch)
-  launch_pnp_prepare(c, pa);
-  UVO_CUDA(cudaEventRecord(s->ev_main[cur], c.stream));
-  cudaStream_t main_stream = c.stream;
-  c.stream = s->side;
-  try {
-    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_main[cur], 0));
-    launch_pnp_solve(c, pa);
-    mark(7);
-    // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
-    ResultParams rp{g, dt};
-    UVO_KERNEL(c, "k_frame_result");
-    k_frame_result<<<1, 1, 0, c.stream>>>(ctrl, s->state.get(), s->pnp_result[cur].get(), s->small[cur].get(),
-                                          s->small[cur].get() + 1, s->d_result.get() + slot, rp);
-    UVO_LAUNCH_CHECK(c);
-    UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
-                             cudaMemcpyDeviceToHost, c.stream));
-    mark(8);
-    UVO_CUDA(cudaEventRecord(s->ev_side[cur], c.stream));
-    s->side_used[cur] = true;
-  } catch (...) {
-    c.stream = main_stream;
-    throw;
-  }
-  c.stream = main_stream;
-  // 14. carry curr -> prev (:723-733): swap the after-stereo buffers
-  s->parity ^= 1;
+  launch_pnp_ransac(c, pa);
+  mark(7);
+  // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
+  if (PL.used) UVO_CUDA(cudaStreamWaitEvent(c.stream, PL.ev_result, 0));
+  ResultParams rp{g, dt};
+  UVO_KERNEL(c, "k_frame_result");
+  k_frame_result<<<1, 1, 0, c.stream>>>(ctrl, s->state.get(), L.pnp_result.get(), L.small.get(), L.small.get() + 1,
+                                        s->d_result.get() + slot, rp);
+  UVO_LAUNCH_CHECK(c);
+  UVO_CUDA(cudaEventRecord(L.ev_result, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
+                           cudaMemcpyDeviceToHost, c.stream));
+  mark(8);
+  cudaEvent_t done;
+  UVO_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  UVO_CUDA(cudaEventRecord(done, c.stream));
+  s->pending.emplace_back(slot, done);
+  L.used = true;
+  // 14. carry curr -> prev (:723-733): the next frame reads this lane's after-stereo sets
   s->frame_no++;
 }
 
@@ -449,24 +481,33 @@ void uvo_stereo_destroy(uvo_stereo* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->c.device);
   cudaStreamSynchronize(s->ctx->c.stream);
-  if (s->side) cudaStreamSynchronize(s->side);
+  for (Lane& l : s->lane)
+    if (l.stream) cudaStreamSynchronize(l.stream);
   delete s;
 }
 
-int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt) {
+static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t* R, size_t pitch, double dt,
+                                  bool from_host) {
   if (!s) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
-    UVO_REQUIRE(dL && dR && pitch >= (size_t)3 * s->w && dt != 0.0, "uvo_stereo_enqueue_device: bad argument");
-    UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING, "too many frames in flight: call uvo_stereo_collect");
+    UVO_REQUIRE(L && R && pitch >= (size_t)3 * s->w && dt != 0.0, "uvo_stereo_enqueue: bad argument");
+    UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING,
+                "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
     Ctx& c = s->ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
+    if (from_host)
+      for (int i = 0; i < 2; i++) s->lane[s->frame_no % uvo_stereo::N_LANES].src[i].ensure(s->src_pitch * s->h);
     const int slot = (int)(s->frame_no % uvo_stereo::RING);
-    stereo_enqueue(s, dL, dR, pitch, dt, slot);
-    cudaEvent_t e;
-    UVO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    UVO_CUDA(cudaEventRecord(e, s->side));
-    s->pending.emplace_back(slot, e);
+    stereo_enqueue(s, L, R, pitch, dt, slot, from_host);
   });
+}
+
+int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt) {
+  return stereo_enqueue_checked(s, dL, dR, pitch, dt, false);
+}
+
+int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3, const uint8_t* right3, size_t pitch, double dt) {
+  return stereo_enqueue_checked(s, left3, right3, pitch, dt, true);
 }
 
 int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out) {
@@ -483,53 +524,55 @@ int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out) {
   });
 }
 
-int uvo_stereo_frame_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt,
-                            uvo_stereo_result* out) {
+static int stereo_frame_sync(uvo_stereo* s, const uint8_t* L, const uint8_t* R, size_t pitch, double dt,
+                             uvo_stereo_result* out, bool from_host) {
   if (!s || !out) return UVO_ERR_INVALID;
+  if (!s->pending.empty()) {
+    s->ctx->c.err = "uvo_stereo_frame: frames are still in flight (collect them first)";
+    return UVO_ERR_INVALID;
+  }
   s->timing = true;
-  int rc = uvo_stereo_enqueue_device(s, dL, dR, pitch, dt);
+  int rc = stereo_enqueue_checked(s, L, R, pitch, dt, from_host);
   s->timing = false;
   if (rc != UVO_OK) return rc;
   rc = uvo_stereo_collect(s, out);
   if (rc == UVO_OK || rc == UVO_ERR_CAPACITY) {
-    s->stage_ms[0] = 0.f;
-    for (int i = 1; i < UVO_N_STAGES; i++) cudaEventElapsedTime(&s->stage_ms[i], s->ev[i], s->ev[i + 1]);
+    for (int i = 0; i < UVO_N_STAGES; i++) cudaEventElapsedTime(&s->stage_ms[i], s->ev[i], s->ev[i + 1]);
     s->has_timing = true;
   }
   return rc;
 }
 
+int uvo_stereo_frame_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt,
+                            uvo_stereo_result* out) {
+  return stereo_frame_sync(s, dL, dR, pitch, dt, out, false);
+}
+
 int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3, const uint8_t* right3, size_t pitch, double dt,
                      uvo_stereo_result* out) {
-  if (!s || !out) return UVO_ERR_INVALID;
-  int rc = guarded(&s->ctx->c, [&] {
-    UVO_REQUIRE(left3 && right3 && pitch >= (size_t)3 * s->w, "uvo_stereo_frame: bad argument");
-    Ctx& c = s->ctx->c;
-    UVO_CUDA(cudaSetDevice(c.device));
-    UVO_CUDA(cudaEventRecord(s->ev[0], c.stream));
-    UVO_CUDA(cudaMemcpy2DAsync(s->src[0].get(), s->src_pitch, left3, pitch, (size_t)3 * s->w, s->h,
-                               cudaMemcpyHostToDevice, c.stream));
-    UVO_CUDA(cudaMemcpy2DAsync(s->src[1].get(), s->src_pitch, right3, pitch, (size_t)3 * s->w, s->h,
-                               cudaMemcpyHostToDevice, c.stream));
-  });
-  if (rc != UVO_OK) return rc;
-  rc = uvo_stereo_frame_device(s, s->src[0].get(), s->src[1].get(), s->src_pitch, dt, out);
-  if (rc == UVO_OK) cudaEventElapsedTime(&s->stage_ms[0], s->ev[0], s->ev[1]);
-  return rc;
+  return stereo_frame_sync(s, left3, right3, pitch, dt, out, true);
+}
+
+int uvo_stereo_max_in_flight(void) { return uvo_stereo::RING; }
+
+// the debug taps read the buffers of the most recent frame; they wait for every lane first
+static void stereo_quiesce(uvo_stereo* s) {
+  for (Lane& l : s->lane) UVO_CUDA(cudaStreamSynchronize(l.stream));
 }
 
 int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps, float* desc, int capacity, int* count) {
   if (!s || !count) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
-    Ctx& c = s->ctx->c;
+    UVO_REQUIRE(s->frame_no > 0, "no frame has been processed yet");
+    stereo_quiesce(s);
+    Lane& L = s->last_lane();
     const int idx = right ? 1 : 0;
     int cnt[4];
-    UVO_CUDA(cudaMemcpyAsync(cnt, s->fe.counters.get() + 4 * idx, sizeof(cnt), cudaMemcpyDeviceToHost, c.stream));
-    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    UVO_CUDA(cudaMemcpy(cnt, L.fe.counters.get() + 4 * idx, sizeof(cnt), cudaMemcpyDeviceToHost));
     const int n = std::min(cnt[1], s->cap);
     UVO_REQUIRE(n <= capacity, "uvo_stereo_last_keypoints: capacity too small");
-    if (n > 0 && kps) UVO_CUDA(cudaMemcpy(kps, s->fe.kps[idx].get(), sizeof(uvo_keypoint) * n, cudaMemcpyDeviceToHost));
-    if (n > 0 && desc) UVO_CUDA(cudaMemcpy(desc, s->fe.desc[idx].get(), sizeof(float) * 64 * n, cudaMemcpyDeviceToHost));
+    if (n > 0 && kps) UVO_CUDA(cudaMemcpy(kps, L.fe.kps[idx].get(), sizeof(uvo_keypoint) * n, cudaMemcpyDeviceToHost));
+    if (n > 0 && desc) UVO_CUDA(cudaMemcpy(desc, L.fe.desc[idx].get(), sizeof(float) * 64 * n, cudaMemcpyDeviceToHost));
     *count = n;
   });
 }
@@ -537,14 +580,15 @@ int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps, float
 int uvo_stereo_last_matches(uvo_stereo* s, int temporal, uvo_dmatch* m, int capacity, int* count) {
   if (!s || !count) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
-    Ctx& c = s->ctx->c;
+    UVO_REQUIRE(s->frame_no > 0, "no frame has been processed yet");
+    stereo_quiesce(s);
+    Lane& L = s->last_lane();
     FrameCtrl fc;
-    UVO_CUDA(cudaMemcpyAsync(&fc, s->ctrl.get() + (s->parity ^ 1), sizeof(fc), cudaMemcpyDeviceToHost, c.stream));
-    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    UVO_CUDA(cudaMemcpy(&fc, L.ctrl.get(), sizeof(fc), cudaMemcpyDeviceToHost));
     const int n = temporal ? (fc.nq_temporal > 0 ? fc.n_temporal : 0) : fc.n_stereo;
     UVO_REQUIRE(n <= capacity, "uvo_stereo_last_matches: capacity too small");
     if (n > 0 && m)
-      UVO_CUDA(cudaMemcpy(m, temporal ? s->m_temporal.get() : s->m_stereo.get(), sizeof(uvo_dmatch) * n,
+      UVO_CUDA(cudaMemcpy(m, temporal ? L.m_temporal.get() : L.m_stereo.get(), sizeof(uvo_dmatch) * n,
                           cudaMemcpyDeviceToHost));
     *count = n;
   });
@@ -553,14 +597,13 @@ int uvo_stereo_last_matches(uvo_stereo* s, int temporal, uvo_dmatch* m, int capa
 int uvo_stereo_last_inliers(uvo_stereo* s, int32_t* inl, int capacity, int* count) {
   if (!s || !count) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
-    Ctx& c = s->ctx->c;
+    UVO_REQUIRE(s->frame_no > 0, "no frame has been processed yet");
+    stereo_quiesce(s);
+    Lane& L = s->last_lane();
     int n = 0;
-    const int last = s->parity ^ 1;
-    UVO_CUDA(cudaStreamSynchronize(s->side));
-    UVO_CUDA(cudaMemcpyAsync(&n, s->small[last].get(), sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    UVO_CUDA(cudaMemcpy(&n, L.small.get(), sizeof(int), cudaMemcpyDeviceToHost));
     UVO_REQUIRE(n <= capacity, "uvo_stereo_last_inliers: capacity too small");
-    if (n > 0 && inl) UVO_CUDA(cudaMemcpy(inl, s->inliers[last].get(), sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (n > 0 && inl) UVO_CUDA(cudaMemcpy(inl, L.inliers.get(), sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
     *count = n;
   });
 }

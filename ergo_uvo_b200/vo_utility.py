@@ -272,6 +272,14 @@ class StereoVO:
         self.ctx._ck(self.lib.uvo_stereo_enqueue_device(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
                                                         C.c_size_t(pitch), C.c_double(dt)))
 
+    def enqueue_host(self, left_ptr, right_ptr, pitch, dt):
+        """host (pinned) image pointers; the H2D copies are enqueued with the frame"""
+        self.ctx._ck(self.lib.uvo_stereo_enqueue_host(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                                      C.c_size_t(pitch), C.c_double(dt)))
+
+    def max_in_flight(self):
+        return int(self.lib.uvo_stereo_max_in_flight())
+
     def collect(self):
         res = L.StereoResult()
         self.ctx._ck(self.lib.uvo_stereo_collect(self.h, C.byref(res)))

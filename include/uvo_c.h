@@ -194,9 +194,16 @@ UVO_API int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3_host, const uin
 /* Same, images already resident in device memory (cudaMalloc'd, pitch bytes per row). */
 UVO_API int uvo_stereo_frame_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
                                     size_t pitch, double dt, uvo_stereo_result* out);
-/* Asynchronous pair: enqueue a frame without waiting; results are collected in order. */
+/* Asynchronous calls: enqueue a frame without waiting; results are collected in order.  Consecutive frames run on
+ * separate CUDA streams inside the library (the front end of frame t+1 does not depend on frame t), so keeping 2-4
+ * frames in flight is what fills the GPU; at most uvo_stereo_max_in_flight() frames may be pending.
+ * _host: images in host memory (pinned for a truly asynchronous copy); the H2D copies are part of the enqueued work and
+ * the buffers may be reused once the frame has been collected. */
 UVO_API int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
                                       size_t pitch, double dt);
+UVO_API int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3_host, const uint8_t* right3_host,
+                                    size_t pitch, double dt);
+UVO_API int uvo_stereo_max_in_flight(void);
 UVO_API int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out);
 /* Debug/parity taps of the last frame (device -> host copies of intermediate products). */
 UVO_API int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps_host, float* desc_host,

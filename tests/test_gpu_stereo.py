@@ -130,3 +130,31 @@ def test_stereo_capacity_overflow_is_an_error(ctx, small_stereo):
         vo.frame(*seq.frames[0], 0.1)
     assert e.value.code == -4
     vo.close()
+
+
+def test_stereo_host_async_pipeline_matches_sync(ctx, small_stereo):
+    """uvo_stereo_enqueue_host with several frames in flight (frames overlap on separate lanes/streams inside the
+    library) returns exactly the records of the one-frame-at-a-time synchronous call, over more frames than lanes"""
+    import torch
+    seq = small_stereo
+    order = [k % len(seq.frames) for k in range(11)]
+    vo, p = _make(ctx, seq, 3000)
+    sync = [vo.frame(*seq.frames[k], 0.1) for k in order]
+    vo.close()
+    vo, p = _make(ctx, seq, 3000)
+    pinned = [(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory()) for (L, R) in seq.frames]
+    got, q = [], 0
+    for k in order:
+        L, R = pinned[k]
+        vo.enqueue_host(L.data_ptr(), R.data_ptr(), 3 * seq.w, 0.1)
+        q += 1
+        if q >= 4:
+            got.append(vo.collect())
+            q -= 1
+    while q:
+        got.append(vo.collect())
+        q -= 1
+    assert vo.max_in_flight() >= 4
+    for a, b in zip(got, sync):
+        assert bytes(a) == bytes(b)
+    vo.close()
