@@ -260,7 +260,8 @@ static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
   StageScratch& s = ctx->scratch;
   s.bytes_a.ensure(sizeof(float) * 64 * (size_t)n1);
   s.bytes_b.ensure(sizeof(float) * 64 * (size_t)std::max(n2, 1));
-  s.bytes_c.ensure(sizeof(Knn2) * (size_t)(MATCH_SPLITS + 1) * n1);
+  s.bytes_c.ensure(match_scratch_bytes(n1, std::max(n2, 1)));
+  UVO_CUDA(cudaMemsetAsync(s.bytes_c.get(), 0, match_scratch_bytes(n1, std::max(n2, 1)), c.stream));
   s.bytes_d.ensure(sizeof(uvo_dmatch) * (size_t)n1 + 16);
   UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), d1, sizeof(float) * 64 * (size_t)n1, cudaMemcpyHostToDevice, c.stream));
   if (n2 > 0)
@@ -271,13 +272,13 @@ static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
   a.nq = n1;
   a.nt = n2;
   a.ratio = ratio;
-  a.partial = (Knn2*)s.bytes_c.get();
-  a.knn = a.partial + (size_t)MATCH_SPLITS * n1;
+  match_bind_scratch(a, s.bytes_c.get(), n1, std::max(n2, 1));
   a.n_matches = (int*)s.bytes_d.get();
   a.matches = (uvo_dmatch*)(s.bytes_d.get() + 16);
   launch_match(c, a);
   ctx->pinned_counts.ensure(8);
   UVO_CUDA(cudaMemcpyAsync(ctx->pinned_counts.p, a.n_matches, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(ctx->pinned_counts.p + 1, a.n_fallback, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   std::vector<Knn2> knn;
   if (knn_out) {
     knn.resize(n1);
@@ -285,6 +286,7 @@ static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
   }
   UVO_CUDA(cudaStreamSynchronize(c.stream));
   const int n = ctx->pinned_counts.p[0];
+  ctx->last_match_fallbacks = ctx->pinned_counts.p[1];
   if (matches && n > 0) {
     UVO_CUDA(cudaMemcpyAsync(matches, a.matches, sizeof(uvo_dmatch) * n, cudaMemcpyDeviceToHost, c.stream));
     UVO_CUDA(cudaStreamSynchronize(c.stream));
@@ -312,6 +314,12 @@ int uvo_knn_match2(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n
     UVO_REQUIRE(knn, "uvo_knn_match2: null output");
     match_host(ctx, d1, n1, d2, n2, dim, 0.f, nullptr, nullptr, knn);
   });
+}
+
+int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count) {
+  if (!ctx || !count) return UVO_ERR_INVALID;
+  *count = ctx->last_match_fallbacks;
+  return UVO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ K11, K12, K10c

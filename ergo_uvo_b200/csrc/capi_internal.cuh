@@ -21,4 +21,5 @@ struct uvo_ctx {
   uvo::StageScratch scratch;
   uvo::FrontEnd fe;  // front end used by the stage-level uvo_detect_features
   uvo::PinnedBuf<int> pinned_counts;
+  int last_match_fallbacks = 0;  // queries of the last matcher call that took the exact full-scan path
 };

@@ -158,7 +158,7 @@ struct Lane {
   DevBuf<float> dL_as;
   DevBuf<FrameCtrl> ctrl;
   DevBuf<uvo_dmatch> m_stereo, m_temporal;
-  DevBuf<Knn2> knn_scratch;
+  DevBuf<uint8_t> knn_scratch;
   DevBuf<float> pts1, pts2, X4;
   DevBuf<double> good_pts, tmp_pts;
   DevBuf<int32_t> good_idx, tmp_idx;
@@ -247,11 +247,13 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
     l.kL_as.ensure(cap);
     l.kR_as.ensure(cap);
     l.dL_as.ensure((size_t)cap * 64);
+    UVO_CUDA(cudaMemsetAsync(l.dL_as.get(), 0, (size_t)cap * 64 * sizeof(float), c.stream));
     l.ctrl.ensure(1);
     UVO_CUDA(cudaMemsetAsync(l.ctrl.get(), 0, sizeof(FrameCtrl), c.stream));
     l.m_stereo.ensure(cap);
     l.m_temporal.ensure(cap);
-    l.knn_scratch.ensure((size_t)(MATCH_SPLITS + 1) * cap);
+    l.knn_scratch.ensure(match_scratch_bytes(cap, cap));
+    UVO_CUDA(cudaMemsetAsync(l.knn_scratch.get(), 0, match_scratch_bytes(cap, cap), c.stream));
     l.pts1.ensure(2 * (size_t)cap);
     l.pts2.ensure(2 * (size_t)cap);
     l.X4.ensure(4 * (size_t)cap);
@@ -339,8 +341,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ms.nq = cap;
   ms.nt = cap;
   ms.ratio = (float)p.lowe_ratio;
-  ms.partial = L.knn_scratch.get();
-  ms.knn = L.knn_scratch.get() + (size_t)MATCH_SPLITS * cap;
+  match_bind_scratch(ms, L.knn_scratch.get(), cap, cap);
   ms.matches = L.m_stereo.get();
   ms.n_matches = &ctrl->n_stereo;
   launch_match(c, ms);

@@ -38,7 +38,10 @@ struct FrontEnd {
       sum[i].ensure((size_t)(w + 1) * (h + 1));
       raw[i].ensure(capacity);
       kps[i].ensure(capacity);
+      const bool fresh = desc[i].n < (size_t)capacity * 64;
       desc[i].ensure((size_t)capacity * 64);
+      // rows past the live count are read (and ignored) by the matcher's TMA tiles: keep them finite
+      if (fresh) UVO_CUDA(cudaMemset(desc[i].get(), 0, (size_t)capacity * 64 * sizeof(float)));
       rank[i].ensure(capacity);
     }
     counters.ensure(8);

@@ -1,20 +1,168 @@
-// match.cu -- K8 exact matcher.  Distances are accumulated in exactly the f32 order OpenCV's normL2Sqr_ uses in its
-// baseline build (4 accumulators x 4 lanes, separate multiply and add, ((d0+d1)+d2)+d3 then (s0+s2)+(s1+s3)), so the
-// distances -- and therefore indices, tie order and ratio-test outcome -- are bit-identical to BFMatcher
-// (pinned by tests/golden/matcher_300x400.npz).
+// match.cu -- K8 matcher: brute-force L2 kNN (k = 2) + Lowe ratio test, bit-identical to BFMatcher(NORM_L2).knnMatch.
 //
-// k_knn2_partial: grid (query blocks, MATCH_SPLITS train slices); one thread owns one query (64 floats in
-// registers), the block streams its slice of the train set through shared memory (broadcast LDS.128).
-// k_knn2_merge: merges the slices in ascending train order, applies the ratio test and compacts the survivors in
-// query order (single block, ballot scan) -- order-preserving, no atomics.
+// Five kernels per call:
+//
+//  k_knn_prep    -|t|^2/2 per train row and max |t|^2.
+//  k_knn_tc      the Nq x Nt descriptor similarity matrix on the 5th-gen tensor cores.  One CTA owns a 128-query
+//                tile and a contiguous chunk of train tiles.  A TMA producer warp streams 128 x 64 f32 train tiles
+//                (two SWIZZLE_128B atoms of 32 floats) through a 4-stage shared-memory ring; one elected thread issues
+//                tcgen05.mma.kind::tf32 (M = 128, N = 128, 8 k-steps of 8) into one of four 128-column TMEM
+//                accumulators; sixteen epilogue warps read the accumulators back with tcgen05.ld (each thread owns
+//                one query row and a quarter of the tile's columns), add -|t|^2/2 and keep the four largest
+//                similarities per (row, column quarter) with a branch-free bitonic network on index-carrying keys.
+//                The matrix itself is never written anywhere.
+//  k_knn_rerank  one warp per query: the candidates (4 per list, <= 128) are re-evaluated with exactly the f32
+//                arithmetic OpenCV's normL2Sqr_ uses (4 accumulators x 4 lanes, separate multiply and add,
+//                ((d0+d1)+d2)+d3 then (s0+s2)+(s1+s3), pinned by tests/golden/matcher_300x400.npz), and the best two
+//                are selected with BatchDistInvoker's tie rule (lower train index first).  The TF32 pass only has to
+//                be good enough to *contain* the true top two: every non-candidate j of a list has a key <= that
+//                list's 4th key, so its exact squared distance is >= |q|^2 - 2*T - eps, where eps bounds the TF32
+//                truncation and key quantisation error.  If the exact second-best does not
+//                beat that bound the query is flagged.
+//  k_knn_exact   flagged queries (measured: ~0.1 % on the stereo workload) are re-done by an exact scan of the whole
+//                train set, one block each -- so the result is exact by construction, not statistically.
+//  k_knn_compact ratio test + order-preserving compaction of the survivors in query order (single block, scan;
+//                no atomics).
+//
+// Reference: match_features, VO_utility.cpp:515-573.
+#include <cuda.h>
+
 #include <cfloat>
 
 #include "match.cuh"
 
 namespace uvo {
 
-constexpr int QB = 128;  // queries per block (one per thread)
-constexpr int TT = 64;   // train rows staged per tile
+// ------------------------------------------------------------------------------------------------ geometry
+constexpr int TILE = 128;          // queries per CTA == train rows per MMA tile
+constexpr int STAGES = 4;          // shared-memory ring depth (train tiles)
+constexpr int ACC = 4;             // TMEM accumulator buffers of 128 columns (4 x 128 = all 512 columns)
+constexpr int ATOM_BYTES = TILE * 128;     // one SWIZZLE_128B atom: 128 rows x 32 floats
+constexpr int TILE_BYTES = 2 * ATOM_BYTES; // 128 rows x 64 floats
+constexpr int MAX_CHUNK_TILES = 32;        // train tiles per CTA at most (bounds the -|t|^2/2 table in smem)
+constexpr int EPI_WARPS = 16;
+constexpr int TC_THREADS = 32 * (2 + EPI_WARPS);  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..17 epilogue
+constexpr int TOPK = MATCH_TOPK;
+constexpr int MATCH_MAX_LISTS = MATCH_MAX_CHUNKS * 4;  // (chunk, column quarter) candidate lists per query
+constexpr int SMEM_A = 0;
+constexpr int SMEM_B = SMEM_A + TILE_BYTES;
+constexpr int SMEM_HB = SMEM_B + STAGES * TILE_BYTES;
+constexpr int SMEM_BAR = SMEM_HB + MAX_CHUNK_TILES * TILE * 4;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to align the base to 1024 B (SWIZZLE_128B requirement)
+
+// number of train chunks (grid.y CTAs that do work) for ntq query tiles and ntt train tiles; the same formula runs
+// on the device in k_knn_tc and k_knn_rerank.
+__host__ __device__ inline int chunk_count(int ntq, int ntt, int sms) {
+  int n = sms / (ntq > 0 ? ntq : 1);
+  if (n < 1) n = 1;
+  const int need = (ntt + MAX_CHUNK_TILES - 1) / MAX_CHUNK_TILES;
+  if (n < need) n = need;
+  if (n > MATCH_MAX_CHUNKS) n = MATCH_MAX_CHUNKS;
+  if (n > ntt) n = ntt > 0 ? ntt : 1;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a protocol error traps (cudaErrorLaunchFailure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0;; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO = 1 (unused for
+// swizzled K-major), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((TILE >> 3) << 17) | ((TILE >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------ exact arithmetic
+// squared L2 distance of two 64-float rows in the accumulation order of OpenCV's normL2Sqr_ (baseline SIMD build)
+__device__ __forceinline__ float l2sqr64_cv(const float4* __restrict__ q, const float4* __restrict__ t) {
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int it = 0; it < 4; it++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 tv = t[it * 4 + k], qv = q[it * 4 + k];
+      float d;
+      d = __fsub_rn(qv.x, tv.x); acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(d, d));
+      d = __fsub_rn(qv.y, tv.y); acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(d, d));
+      d = __fsub_rn(qv.z, tv.z); acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(d, d));
+      d = __fsub_rn(qv.w, tv.w); acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(d, d));
+    }
+  const float s0 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[1].x), acc[2].x), acc[3].x);
+  const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].y, acc[1].y), acc[2].y), acc[3].y);
+  const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].z, acc[1].z), acc[2].z), acc[3].z);
+  const float s3 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].w, acc[1].w), acc[2].w), acc[3].w);
+  return __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
+}
 
 __device__ __forceinline__ void knn2_insert(Knn2& b, float d, int j) {
   // BatchDistInvoker insertion: candidates arrive in ascending j; strict comparisons keep the lower index on ties
@@ -31,102 +179,425 @@ __device__ __forceinline__ void knn2_insert(Knn2& b, float d, int j) {
   }
 }
 
-__global__ void __launch_bounds__(QB) k_knn2_partial(const __grid_constant__ MatchArgs a) {
-  __shared__ float4 s_t[TT][16];
-  const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
-  const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
-  if ((int)(blockIdx.x * QB) >= nq) return;
-  const int qi = blockIdx.x * QB + threadIdx.x;
-  const bool active = qi < nq;
-  // slice of the train set handled by this block (multiple of TT so tiles never straddle slices)
-  const int per = ((nt + MATCH_SPLITS - 1) / MATCH_SPLITS + TT - 1) / TT * TT;
-  const int t0 = blockIdx.y * per, t1 = min(t0 + per, nt);
-  float4 q[16];
-  if (active) {
-    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)qi * 64);
+// (distance, index) packed so that unsigned comparison == (distance asc, index asc); distances are >= 0 or NaN
+__device__ __forceinline__ unsigned long long knn_key(float d, int j) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+}
+constexpr unsigned long long KEY_NONE = ~0ull;
+
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) q[k] = qp[k];
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long x = __shfl_xor_sync(0xffffffffu, k, o);
+    k = x < k ? x : k;
   }
-  Knn2 best{FLT_MAX, FLT_MAX, -1, -1};
-  for (int base = t0; base < t1; base += TT) {
-    const int m = min(TT, t1 - base);
-    __syncthreads();
-    for (int e = threadIdx.x; e < m * 16; e += QB)
-      s_t[e >> 4][e & 15] = reinterpret_cast<const float4*>(a.t + (size_t)base * 64)[e];
-    __syncthreads();
-    if (active) {
-      for (int j = 0; j < m; j++) {
-        float4 acc[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int it = 0; it < 4; it++)
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float4 tv = s_t[j][it * 4 + k], qv = q[it * 4 + k];
-            float d;
-            d = __fsub_rn(qv.x, tv.x); acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(d, d));
-            d = __fsub_rn(qv.y, tv.y); acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(d, d));
-            d = __fsub_rn(qv.z, tv.z); acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(d, d));
-            d = __fsub_rn(qv.w, tv.w); acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(d, d));
-          }
-        const float s0 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].x, acc[1].x), acc[2].x), acc[3].x);
-        const float s1 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].y, acc[1].y), acc[2].y), acc[3].y);
-        const float s2 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].z, acc[1].z), acc[2].z), acc[3].z);
-        const float s3 = __fadd_rn(__fadd_rn(__fadd_rn(acc[0].w, acc[1].w), acc[2].w), acc[3].w);
-        const float d2 = __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
-        knn2_insert(best, __fsqrt_rn(d2), base + j);
-      }
-    }
-  }
-  if (active) a.partial[(size_t)blockIdx.y * a.nq + qi] = best;
+  return k;
 }
 
-__global__ void __launch_bounds__(1024) k_knn2_merge(const __grid_constant__ MatchArgs a) {
+// ------------------------------------------------------------------------------------------------ k_knn_prep
+// hb[j] = -|t_j|^2 / 2 for every train row, max |t|^2 (for the error bound); 16 lanes per row, coalesced
+__global__ void __launch_bounds__(256) k_knn_prep(const __grid_constant__ MatchArgs a) {
+  const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
+  const int sub = threadIdx.x & 15;
+  float n2max = 0.f;
+  for (int j = (blockIdx.x * 256 + threadIdx.x) >> 4; j < nt; j += (gridDim.x * 256) >> 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.t + (size_t)j * 64) + sub);
+    float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (sub == 0) a.hb[j] = -0.5f * s;
+    n2max = fmaxf(n2max, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2max = fmaxf(n2max, __shfl_xor_sync(0xffffffffu, n2max, o));
+  if ((threadIdx.x & 31) == 0 && n2max > 0.f) atomicMax(a.tn2max, __float_as_uint(n2max));
+}
+
+// ------------------------------------------------------------------------------------------------ k_knn_tc
+// Candidate keys: the similarity as an f32 whose low KEY_BITS mantissa bits are replaced by the column's position in
+// the list (tile-in-chunk << 5 | column-in-quarter).  Keys order like the similarities up to a relative perturbation
+// of 2^-13 (accounted for in the error bound), are unique inside a list, and make top-4 maintenance a branch-free
+// FMNMX network.
+constexpr int KEY_BITS = 10;
+constexpr uint32_t KEY_MASK = (1u << KEY_BITS) - 1;
+constexpr float HB_PAD = -1e30f;  // -|t|^2/2 of a column past the end of the train set: finite, below everything
+
+#define UVO_CE(hi, lo)                \
+  do {                                \
+    const float _h = fmaxf(hi, lo);   \
+    lo = fminf(hi, lo);               \
+    hi = _h;                          \
+  } while (0)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+         const __grid_constant__ MatchArgs a, const int sms) {
+  extern __shared__ uint8_t smem_raw[];
+  const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
+  const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
+  const int ntq = (nq + TILE - 1) / TILE, ntt = (nt + TILE - 1) / TILE;
+  if ((int)blockIdx.x >= ntq) return;  // uniform per CTA, before any barrier or TMEM allocation
+  const int n_chunks = chunk_count(ntq, ntt, sms);
+  if ((int)blockIdx.y >= n_chunks) return;
+  const int per = (ntt + n_chunks - 1) / n_chunks;
+  const int tile0 = blockIdx.y * per;
+  const int ntile = max(0, min(ntt, tile0 + per) - tile0);
+  const int row0 = blockIdx.x * TILE;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base + SMEM_A, sB = base + SMEM_B;
+  float* s_hb = reinterpret_cast<float*>(smem + SMEM_HB);
+  const uint32_t bar = base + SMEM_BAR;
+  // barriers (8 B each): full[STAGES], empty[STAGES], A landed, accumulator full[ACC], accumulator empty[ACC]
+  const uint32_t bar_full = bar, bar_empty = bar + 8 * STAGES, bar_a = bar + 8 * (2 * STAGES);
+  const uint32_t bar_tfull = bar_a + 8, bar_tempty = bar_tfull + 8 * ACC;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 1 + 2 * ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_t) : "memory");
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_a, 1);
+    for (int i = 0; i < ACC; i++) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM by launch bounds + shared-memory footprint)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, TILE_BYTES);
+      tma_load_2d(sA, &map_q, 0, row0, bar_a);
+      tma_load_2d(sA + ATOM_BYTES, &map_q, 32, row0, bar_a);
+      for (int i = 0; i < ntile; i++) {
+        const int st = i % STAGES;
+        mbar_wait(bar_empty + 8 * st, ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
+        const uint32_t dst = sB + st * TILE_BYTES;
+        tma_load_2d(dst, &map_t, 0, (tile0 + i) * TILE, bar_full + 8 * st);
+        tma_load_2d(dst + ATOM_BYTES, &map_t, 32, (tile0 + i) * TILE, bar_full + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      mbar_wait(bar_a, 0);
+      for (int i = 0; i < ntile; i++) {
+        const int st = i % STAGES, ab = i % ACC;
+        mbar_wait(bar_tempty + 8 * ab, ((i / ACC) & 1) ^ 1);
+        mbar_wait(bar_full + 8 * st, (i / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t bs = sB + st * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {  // 8 k-steps of 8 floats (32 B); 4 per swizzle atom
+          const uint32_t off = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
+          tc_mma_tf32(tmem + ab * TILE, smem_desc_sw128(sA + off), smem_desc_sw128(bs + off), IDESC_TF32_128x128,
+                      k > 0);
+        }
+        tc_commit(bar_empty + 8 * st);   // smem stage reusable once these MMAs have read it
+        tc_commit(bar_tfull + 8 * ab);   // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps; warp w reads TMEM lanes 32*(w%4).. (its query rows) and the column quarter
+    // (w-2)/4 of every tile: 32 accumulator columns per tile per thread =====
+    const int e = threadIdx.x - 64;        // 0..511
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int cq = (warp - 2) >> 2;        // column quarter 0..3
+    const int row = quarter * 32 + lane;   // query row inside the tile == TMEM lane
+    for (int col = e; col < ntile * TILE; col += EPI_WARPS * 32) {
+      const int j = tile0 * TILE + col;
+      s_hb[col] = j < nt ? a.hb[j] : HB_PAD;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    float l0 = -INFINITY, l1 = -INFINITY, l2 = -INFINITY, l3 = -INFINITY;  // the list, descending
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + cq * 32;
+    for (int i = 0; i < ntile; i++) {
+      const int ab = i % ACC;
+      mbar_wait(bar_tfull + 8 * ab, (i / ACC) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(lane_addr + ab * TILE, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * ab);  // values are in registers: the accumulator can be overwritten
+      const float4* hb4 = reinterpret_cast<const float4*>(s_hb + i * TILE + cq * 32);
+      const uint32_t tbits = (uint32_t)i << 5;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float4 h = hb4[k];
+        float x0 = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * k + 0]) + h.x) & ~KEY_MASK) | (tbits + 4 * k + 0));
+        float x1 = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * k + 1]) + h.y) & ~KEY_MASK) | (tbits + 4 * k + 1));
+        float x2 = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * k + 2]) + h.z) & ~KEY_MASK) | (tbits + 4 * k + 2));
+        float x3 = __uint_as_float((__float_as_uint(__uint_as_float(r[4 * k + 3]) + h.w) & ~KEY_MASK) | (tbits + 4 * k + 3));
+        // sort the four new keys (descending) -- independent of the list, so off the critical path
+        UVO_CE(x0, x1);
+        UVO_CE(x2, x3);
+        UVO_CE(x0, x2);
+        UVO_CE(x1, x3);
+        UVO_CE(x1, x2);
+        // bitonic merge: the top four of the union, then re-sort the bitonic sequence
+        l0 = fmaxf(l0, x3);
+        l1 = fmaxf(l1, x2);
+        l2 = fmaxf(l2, x1);
+        l3 = fmaxf(l3, x0);
+        UVO_CE(l0, l2);
+        UVO_CE(l1, l3);
+        UVO_CE(l0, l1);
+        UVO_CE(l2, l3);
+      }
+    }
+    if (row0 + row < nq) {
+      const size_t o = ((size_t)(row0 + row) * MATCH_MAX_LISTS + blockIdx.y * 4 + cq) * TOPK;
+      *reinterpret_cast<float4*>(a.cand + o) = make_float4(l0, l1, l2, l3);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_knn_rerank
+constexpr int RR_WARPS = 8;
+
+__device__ __forceinline__ Knn2 knn2_from_keys(unsigned long long b0, unsigned long long b1) {
+  Knn2 r{FLT_MAX, FLT_MAX, -1, -1};
+  if (b0 != KEY_NONE) {
+    r.d0 = __uint_as_float((unsigned)(b0 >> 32));
+    r.i0 = (int)(unsigned)b0;
+  }
+  if (b1 != KEY_NONE) {
+    r.d1 = __uint_as_float((unsigned)(b1 >> 32));
+    r.i1 = (int)(unsigned)b1;
+  }
+  return r;
+}
+
+// one warp per query: exact distances of the candidates, exact top two, completeness check
+__global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_constant__ MatchArgs a, const int sms) {
+  const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
+  const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
+  const int ntq = (nq + TILE - 1) / TILE, ntt = (nt + TILE - 1) / TILE;
+  const int n_chunks = chunk_count(ntq, ntt, sms);
+  const int per = (ntt + n_chunks - 1) / n_chunks;
+  const int n_cand = nt > 0 ? n_chunks * 4 * TOPK : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int qi = blockIdx.x * RR_WARPS + warp; qi < nq; qi += gridDim.x * RR_WARPS) {
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)qi * 64);
+    unsigned long long k0 = KEY_NONE, k1 = KEY_NONE;  // this lane's best two (distance, index) keys
+    float tmax = -INFINITY;                           // max over the lists of their 4th similarity
+    for (int c = lane; c < n_cand; c += 32) {
+      const float key = a.cand[(size_t)qi * MATCH_MAX_LISTS * TOPK + c];
+      const bool present = key > 0.5f * HB_PAD;       // -inf: empty slot; ~HB_PAD: column past the end
+      if ((c & (TOPK - 1)) == TOPK - 1 && present) tmax = fmaxf(tmax, key);
+      if (present) {
+        const int list = c / TOPK, chunk = list >> 2, cq = list & 3;
+        const uint32_t kb = __float_as_uint(key) & KEY_MASK;
+        const int j = (chunk * per + (int)(kb >> 5)) * TILE + cq * 32 + (int)(kb & 31);
+        const float d = __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64)));
+        const unsigned long long key2 = knn_key(d, j);
+        if (key2 < k0) {
+          k1 = k0;
+          k0 = key2;
+        } else if (key2 < k1) {
+          k1 = key2;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const unsigned long long b0 = warp_min_key(k0);
+    const unsigned long long b1 = warp_min_key(k0 == b0 ? k1 : k0);  // keys are unique (index in the low word)
+    float nq2 = 0.f;
+    if (lane < 16) {
+      const float4 v = qp[lane];
+      nq2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nq2 += __shfl_xor_sync(0xffffffffu, nq2, o);
+    // Completeness: a non-candidate of list l has key <= that list's 4th key, hence true similarity
+    // <= tmax * (1 +- 2^-13) + tf32 error, hence exact d^2 >= |q|^2 - 2 tmax - eps.  tmax == -inf: no list was
+    // full, every train row is a candidate.
+    bool ok = tmax == -INFINITY;
+    if (!ok && b1 != KEY_NONE) {
+      const double d1 = (double)__uint_as_float((unsigned)(b1 >> 32));
+      const double tn2 = (double)__uint_as_float(*a.tn2max);
+      const double qt = sqrt((double)nq2 * tn2);
+      const double bound = (double)nq2 - 2.0 * (double)tmax;
+      const double eps = (MATCH_TF32_EPS + 4e-5) * qt + 4e-5 * ((double)nq2 + tn2)  // tf32 operands, f32 sums
+                         + 2.0 * 1.3e-4 * (qt + 0.5 * tn2);                         // key quantisation, 2^-13 |s|
+      ok = d1 * d1 * (1.0 + 1e-6) + eps < bound;  // false for NaN anywhere
+    }
+    if (lane == 0) {
+      if (ok)
+        a.knn[qi] = knn2_from_keys(b0, b1);
+      else
+        a.fb_list[atomicAdd(a.n_flagged, 1)] = qi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_knn_exact
+// exact scan of the whole train set for the (rare) queries whose candidate set could not be proven complete: one
+// block per flagged query, every thread a strided slice of the train rows
+constexpr int EX_THREADS = 512;
+
+__global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant__ MatchArgs a) {
+  __shared__ Knn2 s_part[EX_THREADS / 32];
+  const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
+  const int nf = *a.n_flagged;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+    const int fq = a.fb_list[f];
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)fq * 64);
+    Knn2 best{FLT_MAX, FLT_MAX, -1, -1};
+    int j = threadIdx.x;
+    for (; j + EX_THREADS < nt; j += 2 * EX_THREADS) {  // two rows in flight
+      const float d0 = l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64));
+      const float d1 = l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)(j + EX_THREADS) * 64));
+      knn2_insert(best, __fsqrt_rn(d0), j);
+      knn2_insert(best, __fsqrt_rn(d1), j + EX_THREADS);
+    }
+    if (j < nt) knn2_insert(best, __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64))), j);
+    // merge by (distance, index): the global second is the winner's second or somebody else's first
+    unsigned long long k0 = best.i0 >= 0 ? knn_key(best.d0, best.i0) : KEY_NONE;
+    unsigned long long k1 = best.i1 >= 0 ? knn_key(best.d1, best.i1) : KEY_NONE;
+    unsigned long long b0 = warp_min_key(k0);
+    unsigned long long b1 = warp_min_key(k0 == b0 && b0 != KEY_NONE ? k1 : k0);
+    if (lane == 0) s_part[warp] = knn2_from_keys(b0, b1);
+    __syncthreads();
+    if (warp == 0) {
+      Knn2 p{FLT_MAX, FLT_MAX, -1, -1};
+      if (lane < EX_THREADS / 32) p = s_part[lane];
+      k0 = p.i0 >= 0 ? knn_key(p.d0, p.i0) : KEY_NONE;
+      k1 = p.i1 >= 0 ? knn_key(p.d1, p.i1) : KEY_NONE;
+      b0 = warp_min_key(k0);
+      b1 = warp_min_key(k0 == b0 && b0 != KEY_NONE ? k1 : k0);
+      if (lane == 0) a.knn[fq] = knn2_from_keys(b0, b1);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k_knn_compact
+// ratio test + order-preserving compaction (single block; thread t owns a contiguous run of queries)
+__global__ void __launch_bounds__(1024) k_knn_compact(const __grid_constant__ MatchArgs a) {
   __shared__ int s_warp[32];
-  __shared__ int s_base;
   const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int base = 0; base < nq; base += 1024) {
-    const int qi = base + tid;
-    bool keep = false;
-    Knn2 best{FLT_MAX, FLT_MAX, -1, -1};
-    if (qi < nq) {
-      for (int s = 0; s < MATCH_SPLITS; s++) {  // ascending train order
-        const Knn2 p = a.partial[(size_t)s * a.nq + qi];
-        if (p.i0 >= 0) knn2_insert(best, p.d0, p.i0);
-        if (p.i1 >= 0) knn2_insert(best, p.d1, p.i1);
-      }
-      a.knn[qi] = best;
-      // reference: knn[i][0].distance < ratio * knn[i][1].distance; fewer than 2 train rows => no match (the
-      // reference would read out of bounds there)
-      keep = nt >= 2 && best.i1 >= 0 && best.d0 < __fmul_rn(a.ratio, best.d1);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    int off = s_base;
-    for (int k = 0; k < wid; k++) off += s_warp[k];
-    if (keep) {
-      uvo_dmatch m;
-      m.queryIdx = qi;
-      m.trainIdx = best.i0;
-      m.imgIdx = 0;
-      m.distance = best.d0;
-      a.matches[off + __popc(bal & ((1u << lane) - 1))] = m;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int k = 0; k < 32; k++) tot += s_warp[k];
-      s_base += tot;
-    }
-    __syncthreads();
+  const int per = (nq + 1023) / 1024;  // <= 32 (capacity <= 32768)
+  const int q0 = tid * per, q1 = min(nq, q0 + per);
+  unsigned keep = 0;
+  for (int qi = q0; qi < q1; qi++) {
+    const Knn2 b = a.knn[qi];
+    // reference: knn[i][0].distance < ratio * knn[i][1].distance; fewer than 2 train rows => no match (the
+    // reference would read out of bounds there)
+    if (nt >= 2 && b.i1 >= 0 && b.d0 < __fmul_rn(a.ratio, b.d1)) keep |= 1u << (qi - q0);
   }
-  if (tid == 0) *a.n_matches = s_base;
+  const int cnt = __popc(keep);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    s_warp[lane] = w;  // inclusive totals
+  }
+  __syncthreads();
+  int off = (wid > 0 ? s_warp[wid - 1] : 0) + incl - cnt;
+  for (int qi = q0; qi < q1; qi++)
+    if (keep >> (qi - q0) & 1u) {
+      const Knn2 b = a.knn[qi];
+      a.matches[off++] = uvo_dmatch{qi, b.i0, 0, b.d0};
+    }
+  if (tid == 0) {
+    *a.n_matches = s_warp[31];
+    *a.n_fallback += *a.n_flagged;  // statistics; then reset the per-call state for the next call on this scratch
+    *a.n_flagged = 0;
+    *a.tn2max = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    UVO_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess)
+      throw InvalidArg{"cuTensorMapEncodeTiled is not available from this driver", UVO_ERR_CUDA};
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// rows x 64 f32 row-major, boxes of 128 rows x 32 floats (one SWIZZLE_128B atom); rows past the end read as zero
+static CUtensorMap make_desc_map(const float* base, int rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)(rows > 0 ? rows : 1)};
+  const cuuint64_t strides[1] = {64 * sizeof(float)};
+  const cuuint32_t box[2] = {32, TILE};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw InvalidArg{"cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")", UVO_ERR_CUDA};
+  return m;
+}
+
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+size_t match_scratch_bytes(int cap_q, int cap_t) {
+  return align256((size_t)cap_q * MATCH_MAX_LISTS * TOPK * sizeof(float)) + align256((size_t)cap_t * sizeof(float)) +
+         align256((size_t)cap_q * sizeof(Knn2)) + align256((size_t)cap_q * sizeof(int)) + 256;
+}
+
+void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
+  uint8_t* p = (uint8_t*)scratch;
+  a.cand = (float*)p;
+  p += align256((size_t)cap_q * MATCH_MAX_LISTS * TOPK * sizeof(float));
+  a.hb = (float*)p;
+  p += align256((size_t)cap_t * sizeof(float));
+  a.knn = (Knn2*)p;
+  p += align256((size_t)cap_q * sizeof(Knn2));
+  a.fb_list = (int*)p;
+  p += align256((size_t)cap_q * sizeof(int));
+  a.n_flagged = (int*)p;
+  a.n_fallback = (int*)(p + 16);
+  a.tn2max = (unsigned*)(p + 32);
 }
 
 void launch_match(Ctx& c, const MatchArgs& a) {
@@ -134,11 +605,31 @@ void launch_match(Ctx& c, const MatchArgs& a) {
     UVO_CUDA(cudaMemsetAsync(a.n_matches, 0, sizeof(int), c.stream));
     return;
   }
-  UVO_KERNEL(c, "k_knn2_partial");
-  k_knn2_partial<<<dim3(div_up(a.nq, QB), MATCH_SPLITS), QB, 0, c.stream>>>(a);
+  UVO_REQUIRE(a.nt <= MATCH_MAX_CHUNKS * MAX_CHUNK_TILES * TILE && a.nq <= 32768,
+              "matcher: more than 32768 descriptors in one set");
+  UVO_REQUIRE(((uintptr_t)a.q & 15) == 0 && ((uintptr_t)a.t & 15) == 0, "matcher: descriptors must be 16-byte aligned");
+  static bool attr_done = false;
+  if (!attr_done) {
+    UVO_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    attr_done = true;
+  }
+  if (a.nt > 0) {
+    UVO_KERNEL(c, "k_knn_prep");
+    k_knn_prep<<<std::min(div_up(a.nt, 16), 2 * c.sm_count), 256, 0, c.stream>>>(a);
+    UVO_LAUNCH_CHECK(c);
+    const CUtensorMap mq = make_desc_map(a.q, a.nq), mt = make_desc_map(a.t, a.nt);
+    UVO_KERNEL(c, "k_knn_tc");
+    k_knn_tc<<<dim3(div_up(a.nq, TILE), MATCH_MAX_CHUNKS), TC_THREADS, SMEM_ALLOC, c.stream>>>(mq, mt, a, c.sm_count);
+    UVO_LAUNCH_CHECK(c);
+  }
+  UVO_KERNEL(c, "k_knn_rerank");
+  k_knn_rerank<<<std::min(div_up(a.nq, RR_WARPS), 8 * c.sm_count), RR_WARPS * 32, 0, c.stream>>>(a, c.sm_count);
   UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_knn2_merge");
-  k_knn2_merge<<<1, 1024, 0, c.stream>>>(a);
+  UVO_KERNEL(c, "k_knn_exact");
+  k_knn_exact<<<c.sm_count, EX_THREADS, 0, c.stream>>>(a);
+  UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_knn_compact");
+  k_knn_compact<<<1, 1024, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
 }
 

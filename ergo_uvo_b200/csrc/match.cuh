@@ -11,21 +11,34 @@ struct Knn2 {  // per query: best and second-best (distance, train index); idx =
   int i0, i1;
 };
 
-constexpr int MATCH_SPLITS = 8;
+constexpr int MATCH_MAX_CHUNKS = 8;  // train-set chunks (grid.y of the tensor-core kernel)
+constexpr int MATCH_TOPK = 4;        // candidates kept per (query, chunk, column quarter)
+// |tf32-pass similarity - exact| <= 2^-9 |q||t| (both operands truncated to 10 mantissa bits) => 2^-8 on d^2; 1 % slack
+constexpr double MATCH_TF32_EPS = 0.00390625 * 1.01;
 
 struct MatchArgs {
-  const float* q;      // nq x 64
+  const float* q;      // nq x 64, 16-byte aligned
   const float* t;      // nt x 64
   const int* nq_dev;   // device counts (nullable: use nq/nt)
   const int* nt_dev;
   int nq, nt;          // host-known counts or upper bounds (capacity) when *_dev is set
   float ratio;
-  Knn2* partial;       // MATCH_SPLITS x capacity scratch
-  Knn2* knn;           // capacity: merged result (always written)
+  // scratch (match_bind_scratch)
+  float* cand;         // capacity x 32 lists x MATCH_TOPK candidate keys (similarity with the column in the low bits)
+  float* hb;           // train capacity: -|t|^2 / 2
+  Knn2* knn;           // capacity: exact result per query (always written)
+  int* fb_list;        // capacity: queries whose candidate set could not be proven complete (this call)
+  int* n_flagged;      // ... and how many
+  int* n_fallback;     // cumulative n_flagged (statistics)
+  unsigned* tn2max;    // float bits of max |t|^2 of the current call (reset by k_knn_compact)
+  // outputs
   uvo_dmatch* matches; // capacity: ratio-test survivors in query order
   int* n_matches;      // device counter
 };
 
+// bytes of scratch for `cap` queries; the buffer must be zero-filled once after allocation
+size_t match_scratch_bytes(int cap_q, int cap_t);
+void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t);
 void launch_match(Ctx& c, const MatchArgs& a);
 
 }  // namespace uvo

@@ -164,6 +164,11 @@ class Context:
         self._ck(self.lib.uvo_knn_match2(self.h, _p(d1), d1.shape[0], _p(d2), d2.shape[0], d1.shape[1], _p(out)))
         return out
 
+    def match_last_fallbacks(self):
+        n = C.c_int(0)
+        self._ck(self.lib.uvo_match_last_fallbacks(self.h, C.byref(n)))
+        return n.value
+
     # ------------------------------------------------------------------ VO_utility.h:116
     def select_estimation_method(self, keypoints1_conv, keypoints2_conv):
         p1 = np.ascontiguousarray(keypoints1_conv, np.float32).reshape(-1, 2)

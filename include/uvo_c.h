@@ -137,6 +137,10 @@ UVO_API int uvo_match_features(uvo_ctx* ctx, const float* desc1_host, int n1, co
 /* raw knnMatch(k=2) rows (2 per query; trainIdx = -1 where n2 < 2) */
 UVO_API int uvo_knn_match2(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2, int dim,
                            uvo_dmatch* knn_host);
+/* diagnostics: how many queries of the last uvo_match_features / uvo_knn_match2 call on this context were resolved
+ * by the exact full scan because the tensor-core candidate set could not be proven complete (results are exact
+ * either way; this is a performance counter) */
+UVO_API int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count);
 
 /* ---------------------------------------------------------------------------------------------------- K9, K11, K12 */
 /* bool select_estimation_method(const vector<Point2f>&, const vector<Point2f>&) -- VO_utility.cpp:725-748 */

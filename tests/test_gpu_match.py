@@ -74,3 +74,42 @@ def test_match_7arg_overload_points(ctx, oracle):
     k2["x"], k2["y"] = rs.rand(500) * 640, rs.rand(500) * 480
     m, p1, p2 = ctx.match_features(k1, k2, q, t, with_points=True)
     assert np.array_equal(p1[:, 0], k1["x"][m["queryIdx"]]) and np.array_equal(p2[:, 1], k2["y"][m["trainIdx"]])
+
+
+def test_match_forced_exact_scan(ctx, oracle):
+    """train rows that the TF32 pass cannot separate (hundreds of near-duplicates of every query): the candidate set
+    cannot be proven complete, the exact full scan must take over, and the answer is still bit-identical"""
+    rs = np.random.RandomState(7)
+    base = _descs(8, 8)
+    t = np.repeat(base, 200, axis=0) + (1e-4 * rs.randn(1600, 64)).astype(np.float32)
+    q = base + (1e-4 * rs.randn(8, 64)).astype(np.float32)
+    k = ctx.knn_match2(q, t)
+    assert ctx.match_last_fallbacks() > 0
+    assert k.tobytes() == oracle.knn2(q, t).tobytes()
+
+
+def test_match_unnormalised_descriptors(ctx, oracle):
+    """the error bound scales with |q| max|t|: descriptors far from unit norm stay exact"""
+    rs = np.random.RandomState(9)
+    t = (rs.randn(700, 64) * 37.0).astype(np.float32)
+    q = (t[rs.permutation(700)[:300]] + rs.randn(300, 64) * 5.0).astype(np.float32)
+    k = ctx.knn_match2(q, t)
+    assert k.tobytes() == oracle.knn2(q, t).tobytes()
+
+
+def test_match_fallback_is_rare_on_descriptor_like_data(ctx):
+    t = _descs(4096, 1)
+    q = _descs(4096, 2, dup_from=t)
+    ctx.knn_match2(q, t)
+    assert ctx.match_last_fallbacks() <= 4096 // 20
+
+
+@pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 127, 128, 129, 257])
+def test_match_small_train_sets(ctx, oracle, nt):
+    t = _descs(nt, 11)
+    q = _descs(130, 12)
+    k = ctx.knn_match2(q, t)
+    ko = oracle.knn2(q, t)
+    assert np.array_equal(k["trainIdx"], ko["trainIdx"])
+    valid = ko["trainIdx"] >= 0
+    assert np.array_equal(k["distance"][valid].view(np.uint32), ko["distance"][valid].view(np.uint32))
