@@ -392,7 +392,16 @@ __device__ __forceinline__ Knn2 knn2_from_keys(unsigned long long b0, unsigned l
   return r;
 }
 
-// one warp per query: exact distances of the candidates, exact top two, completeness check
+// per-query bound on |(|q|^2 - 2 key) - D| for every (query, train) pair, D = the f32 value normL2Sqr_ computes:
+// tf32 truncation of both operands (2^-8 |q||t|), f32 accumulation on either side, key quantisation (2^-13 |s|,
+// |s| <= |q||t| + |t|^2/2); 1 % slack on top
+__device__ __forceinline__ float match_eps(float nq2, float tn2) {
+  const float qt = sqrtf(nq2 * tn2);
+  return 1.01f * (((float)MATCH_TF32_EPS + 4e-5f) * qt + 4e-5f * (nq2 + tn2) + 2.6e-4f * (qt + 0.5f * tn2));
+}
+
+// one warp per query: prune the candidates by their approximate keys, exact distances of the survivors, exact top
+// two, completeness check
 __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_constant__ MatchArgs a, const int sms) {
   const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
@@ -400,18 +409,57 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
   const int n_chunks = chunk_count(ntq, ntt, sms);
   const int per = (ntt + n_chunks - 1) / n_chunks;
   const int n_cand = nt > 0 ? n_chunks * 4 * TOPK : 0;
+  const float tn2 = __uint_as_float(*a.tn2max);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int qi = blockIdx.x * RR_WARPS + warp; qi < nq; qi += gridDim.x * RR_WARPS) {
     const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)qi * 64);
+    float nq2 = 0.f;
+    if (lane < 16) {
+      const float4 v = qp[lane];
+      nq2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nq2 += __shfl_xor_sync(0xffffffffu, nq2, o);
+    const float eps = match_eps(nq2, tn2);
+    // this lane's candidate keys: c = lane + 32 u  (n_cand <= 128)
+    float key[4];
+    float m1 = -INFINITY, m2 = -INFINITY;  // lane-local largest two present keys
+    float tmax = -INFINITY;                // max over the lists of their 4th key
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int c = lane + 32 * u;
+      float k = -INFINITY;
+      if (c < n_cand) k = a.cand[(size_t)qi * MATCH_MAX_LISTS * TOPK + c];
+      if (!(k > 0.5f * HB_PAD)) k = -INFINITY;  // -inf: empty slot; ~HB_PAD: column past the end; NaN: never
+      key[u] = k;
+      if ((c & (TOPK - 1)) == TOPK - 1) tmax = fmaxf(tmax, k);
+      if (k > m1) {
+        m2 = m1;
+        m1 = k;
+      } else if (k > m2) {
+        m2 = k;
+      }
+    }
+    float w1 = m1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      w1 = fmaxf(w1, __shfl_xor_sync(0xffffffffu, w1, o));
+    }
+    // second largest key of the warp (if the largest occurs twice this under-estimates, which only prunes less)
+    float w2 = m1 == w1 ? m2 : m1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w2 = fmaxf(w2, __shfl_xor_sync(0xffffffffu, w2, o));
+    // A candidate whose key is more than eps below the second largest key is farther (in exact arithmetic) than
+    // both holders of the two largest keys: it cannot be among the best two.
+    const float cut = w2 - eps;  // -inf when fewer than two candidates: nothing is pruned
     unsigned long long k0 = KEY_NONE, k1 = KEY_NONE;  // this lane's best two (distance, index) keys
-    float tmax = -INFINITY;                           // max over the lists of their 4th similarity
-    for (int c = lane; c < n_cand; c += 32) {
-      const float key = a.cand[(size_t)qi * MATCH_MAX_LISTS * TOPK + c];
-      const bool present = key > 0.5f * HB_PAD;       // -inf: empty slot; ~HB_PAD: column past the end
-      if ((c & (TOPK - 1)) == TOPK - 1 && present) tmax = fmaxf(tmax, key);
-      if (present) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (key[u] >= cut && key[u] > -INFINITY) {
+        const int c = lane + 32 * u;
         const int list = c / TOPK, chunk = list >> 2, cq = list & 3;
-        const uint32_t kb = __float_as_uint(key) & KEY_MASK;
+        const uint32_t kb = __float_as_uint(key[u]) & KEY_MASK;
         const int j = (chunk * per + (int)(kb >> 5)) * TILE + cq * 32 + (int)(kb & 31);
         const float d = __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64)));
         const unsigned long long key2 = knn_key(d, j);
@@ -423,29 +471,14 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
     const unsigned long long b0 = warp_min_key(k0);
     const unsigned long long b1 = warp_min_key(k0 == b0 ? k1 : k0);  // keys are unique (index in the low word)
-    float nq2 = 0.f;
-    if (lane < 16) {
-      const float4 v = qp[lane];
-      nq2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nq2 += __shfl_xor_sync(0xffffffffu, nq2, o);
-    // Completeness: a non-candidate of list l has key <= that list's 4th key, hence true similarity
-    // <= tmax * (1 +- 2^-13) + tf32 error, hence exact d^2 >= |q|^2 - 2 tmax - eps.  tmax == -inf: no list was
-    // full, every train row is a candidate.
+    // Completeness: a non-candidate of a list has a key <= that list's 4th key <= tmax, so its exact squared distance
+    // is >= |q|^2 - 2 tmax - eps.  tmax == -inf: no list was full, every train row is a candidate.
     bool ok = tmax == -INFINITY;
     if (!ok && b1 != KEY_NONE) {
-      const double d1 = (double)__uint_as_float((unsigned)(b1 >> 32));
-      const double tn2 = (double)__uint_as_float(*a.tn2max);
-      const double qt = sqrt((double)nq2 * tn2);
-      const double bound = (double)nq2 - 2.0 * (double)tmax;
-      const double eps = (MATCH_TF32_EPS + 4e-5) * qt + 4e-5 * ((double)nq2 + tn2)  // tf32 operands, f32 sums
-                         + 2.0 * 1.3e-4 * (qt + 0.5 * tn2);                         // key quantisation, 2^-13 |s|
-      ok = d1 * d1 * (1.0 + 1e-6) + eps < bound;  // false for NaN anywhere
+      const float d1 = __uint_as_float((unsigned)(b1 >> 32));
+      ok = d1 * d1 * (1.f + 1e-6f) + eps < nq2 - 2.f * tmax;  // false for NaN anywhere
     }
     if (lane == 0) {
       if (ok)
@@ -457,27 +490,25 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ k_knn_exact
-// exact scan of the whole train set for the (rare) queries whose candidate set could not be proven complete: one
-// block per flagged query, every thread a strided slice of the train rows
-constexpr int EX_THREADS = 512;
+// exact scan of the whole train set for the (rare) queries whose candidate set could not be proven complete.  Grid
+// (EX_SLICES, y): block (s, y) scans slice s of the train rows for flagged queries y, y + gridDim.y, ...; the last
+// block to finish a query merges the EX_SLICES partial results (threadfence + counter).
+constexpr int EX_THREADS = 256;
 
 __global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant__ MatchArgs a) {
   __shared__ Knn2 s_part[EX_THREADS / 32];
+  __shared__ int s_last;
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
   const int nf = *a.n_flagged;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+  const int rows = (nt + MATCH_EX_SLICES - 1) / MATCH_EX_SLICES;
+  const int j0 = blockIdx.x * rows, j1 = min(nt, j0 + rows);
+  for (int f = blockIdx.y; f < nf; f += gridDim.y) {
     const int fq = a.fb_list[f];
     const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)fq * 64);
     Knn2 best{FLT_MAX, FLT_MAX, -1, -1};
-    int j = threadIdx.x;
-    for (; j + EX_THREADS < nt; j += 2 * EX_THREADS) {  // two rows in flight
-      const float d0 = l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64));
-      const float d1 = l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)(j + EX_THREADS) * 64));
-      knn2_insert(best, __fsqrt_rn(d0), j);
-      knn2_insert(best, __fsqrt_rn(d1), j + EX_THREADS);
-    }
-    if (j < nt) knn2_insert(best, __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64))), j);
+    for (int j = j0 + threadIdx.x; j < j1; j += EX_THREADS)
+      knn2_insert(best, __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64))), j);
     // merge by (distance, index): the global second is the winner's second or somebody else's first
     unsigned long long k0 = best.i0 >= 0 ? knn_key(best.d0, best.i0) : KEY_NONE;
     unsigned long long k1 = best.i1 >= 0 ? knn_key(best.d1, best.i1) : KEY_NONE;
@@ -492,7 +523,25 @@ __global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant_
       k1 = p.i1 >= 0 ? knn_key(p.d1, p.i1) : KEY_NONE;
       b0 = warp_min_key(k0);
       b1 = warp_min_key(k0 == b0 && b0 != KEY_NONE ? k1 : k0);
-      if (lane == 0) a.knn[fq] = knn2_from_keys(b0, b1);
+      if (lane == 0) {
+        a.ex_part[(size_t)f * MATCH_EX_SLICES + blockIdx.x] = knn2_from_keys(b0, b1);
+        __threadfence();
+        s_last = atomicAdd(&a.ex_done[f], 1) == MATCH_EX_SLICES - 1;
+      }
+      __syncwarp();
+      if (s_last) {  // warp-uniform (shared): this block saw every other slice's partial
+        __threadfence();
+        Knn2 p2{FLT_MAX, FLT_MAX, -1, -1};
+        if (lane < MATCH_EX_SLICES) p2 = a.ex_part[(size_t)f * MATCH_EX_SLICES + lane];
+        k0 = p2.i0 >= 0 ? knn_key(p2.d0, p2.i0) : KEY_NONE;
+        k1 = p2.i1 >= 0 ? knn_key(p2.d1, p2.i1) : KEY_NONE;
+        b0 = warp_min_key(k0);
+        b1 = warp_min_key(k0 == b0 && b0 != KEY_NONE ? k1 : k0);
+        if (lane == 0) {
+          a.knn[fq] = knn2_from_keys(b0, b1);
+          a.ex_done[f] = 0;  // self-cleaning for the next call
+        }
+      }
     }
     __syncthreads();
   }
@@ -582,7 +631,8 @@ static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 size_t match_scratch_bytes(int cap_q, int cap_t) {
   return align256((size_t)cap_q * MATCH_MAX_LISTS * TOPK * sizeof(float)) + align256((size_t)cap_t * sizeof(float)) +
-         align256((size_t)cap_q * sizeof(Knn2)) + align256((size_t)cap_q * sizeof(int)) + 256;
+         align256((size_t)cap_q * sizeof(Knn2)) + 2 * align256((size_t)cap_q * sizeof(int)) +
+         align256((size_t)cap_q * MATCH_EX_SLICES * sizeof(Knn2)) + 256;
 }
 
 void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
@@ -595,6 +645,10 @@ void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
   p += align256((size_t)cap_q * sizeof(Knn2));
   a.fb_list = (int*)p;
   p += align256((size_t)cap_q * sizeof(int));
+  a.ex_done = (int*)p;
+  p += align256((size_t)cap_q * sizeof(int));
+  a.ex_part = (Knn2*)p;
+  p += align256((size_t)cap_q * MATCH_EX_SLICES * sizeof(Knn2));
   a.n_flagged = (int*)p;
   a.n_fallback = (int*)(p + 16);
   a.tn2max = (unsigned*)(p + 32);
@@ -626,7 +680,7 @@ void launch_match(Ctx& c, const MatchArgs& a) {
   k_knn_rerank<<<std::min(div_up(a.nq, RR_WARPS), 8 * c.sm_count), RR_WARPS * 32, 0, c.stream>>>(a, c.sm_count);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_knn_exact");
-  k_knn_exact<<<c.sm_count, EX_THREADS, 0, c.stream>>>(a);
+  k_knn_exact<<<dim3(MATCH_EX_SLICES, 16), EX_THREADS, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_knn_compact");
   k_knn_compact<<<1, 1024, 0, c.stream>>>(a);

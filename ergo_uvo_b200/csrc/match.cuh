@@ -12,6 +12,7 @@ struct Knn2 {  // per query: best and second-best (distance, train index); idx =
 };
 
 constexpr int MATCH_MAX_CHUNKS = 8;  // train-set chunks (grid.y of the tensor-core kernel)
+constexpr int MATCH_EX_SLICES = 16;  // train-set slices per flagged query in the exact scan
 constexpr int MATCH_TOPK = 4;        // candidates kept per (query, chunk, column quarter)
 // |tf32-pass similarity - exact| <= 2^-9 |q||t| (both operands truncated to 10 mantissa bits) => 2^-8 on d^2; 1 % slack
 constexpr double MATCH_TF32_EPS = 0.00390625 * 1.01;
@@ -29,6 +30,8 @@ struct MatchArgs {
   Knn2* knn;           // capacity: exact result per query (always written)
   int* fb_list;        // capacity: queries whose candidate set could not be proven complete (this call)
   int* n_flagged;      // ... and how many
+  int* ex_done;        // capacity: per flagged query, slices finished (self-cleaning)
+  Knn2* ex_part;       // capacity x MATCH_EX_SLICES partial results of the exact scan
   int* n_fallback;     // cumulative n_flagged (statistics)
   unsigned* tn2max;    // float bits of max |t|^2 of the current call (reset by k_knn_compact)
   // outputs
