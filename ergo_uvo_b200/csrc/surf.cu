@@ -103,6 +103,18 @@ SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, i
       resize_haar_h(dx_s, L.box + 0, 3, 9, L.size, w + 1);
       resize_haar_h(dy_s, L.box + 3, 3, 9, L.size, w + 1);
       resize_haar_h(dxy_s, L.box + 6, 4, 9, L.size, w + 1);
+      {
+        const float ratio = (float)L.size / 9;
+        const int ws = w + 1;
+        L.xx_row[0] = cv_roundf_h(ratio * 2) * ws;
+        L.xx_row[1] = cv_roundf_h(ratio * 7) * ws;
+        L.yy_col[0] = cv_roundf_h(ratio * 2);
+        L.yy_col[1] = cv_roundf_h(ratio * 7);
+        for (int k = 0; k < 4; k++) {
+          L.xx_col[k] = cv_roundf_h(ratio * (3 * k));
+          L.yy_row[k] = cv_roundf_h(ratio * (3 * k)) * ws;
+        }
+      }
     }
     for (int l = 1; l <= n_layers; l++) O.nms_margin[l] = (O.layer[l + 1].size / 2) / O.step + 1;
   }
@@ -137,7 +149,29 @@ __device__ __forceinline__ float det_at(const int* __restrict__ sum, int scols, 
   const int si = i - L.margin, sj = j - L.margin;
   if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
   const int* o = sum + (size_t)(si * step) * scols + sj * step;
-  const float dx = haar3(o, L.box + 0), dy = haar3(o, L.box + 3), dxy = haar4(o, L.box + 6);
+  // Dxx / Dyy: 8 shared corners each (same integers, same f32 products, same f64 sums as box-by-box evaluation)
+  unsigned A[4], B[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    A[k] = (unsigned)__ldg(o + L.xx_row[0] + L.xx_col[k]);
+    B[k] = (unsigned)__ldg(o + L.xx_row[1] + L.xx_col[k]);
+  }
+  double d = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A[k] + B[k + 1] - B[k] - A[k + 1]), L.box[k].w));
+  const float dx = (float)d;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    A[k] = (unsigned)__ldg(o + L.yy_row[k] + L.yy_col[0]);
+    B[k] = (unsigned)__ldg(o + L.yy_row[k] + L.yy_col[1]);
+  }
+  d = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A[k] + B[k + 1] - A[k + 1] - B[k]), L.box[3 + k].w));
+  const float dy = (float)d;
+  const float dxy = haar4(o, L.box + 6);
   return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
 
@@ -172,61 +206,144 @@ __device__ __forceinline__ bool interpolate_keypoint(const float N[3][9], int st
 
 constexpr int TW = SURF_TILE_W, TH = SURF_TILE_H;
 
-__global__ void __launch_bounds__(256) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
+// Lazy pyramid: only the middle layers 1..n_layers are evaluated everywhere (a keypoint needs det > threshold in a
+// middle layer).  The two outer layers are needed solely as NMS neighbours of the few positions that already beat
+// their 8 in-layer neighbours and the adjacent middle layers, so they are evaluated on demand, 9 samples per such
+// candidate, spread over the block.  Every det value that is computed is computed exactly as before.
+constexpr int DET_LIST = 192;  // candidates needing an outer layer, per block (overflow is handled in-thread)
+
+struct DetCand {
+  short m, y, x, alive;
+};
+
+__device__ __noinline__ void emit_keypoint(const SurfOctave& O, const SurfImage& im, const float N[3][9], int m,
+                                              int i, int j, int o, int capacity) {
+  const int step = O.step;
+  const int size = O.layer[m].size;
+  const int sum_i = step * (i - (size / 2) / step), sum_j = step * (j - (size / 2) / step);
+  float py = (float)sum_i + (float)(size - 1) * 0.5f;
+  float px = (float)sum_j + (float)(size - 1) * 0.5f;
+  float psize = (float)size;
+  const int ds = size - O.layer[m - 1].size;
+  if (!interpolate_keypoint(N, step, ds, px, py, psize)) return;
+  const int slot = atomicAdd(&im.counters[0], 1);
+  if (slot < capacity) {
+    uvo_keypoint k;
+    k.x = px;
+    k.y = py;
+    k.size = psize;
+    k.angle = -1.f;
+    k.response = N[1][4];
+    k.octave = o;
+    k.class_id = -1;
+    im.raw[slot] = k;
+  }
+}
+
+__global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
                                                      int capacity) {
-  __shared__ float sdet[SURF_MAX_LAYERS][TH + 2][TW + 2];
+  // sdet[l] holds pyramid layer l + 1 (the middle layers)
+  __shared__ float sdet[SURF_MAX_LAYERS - 2][TH + 2][TW + 2];
+  __shared__ DetCand s_cand[DET_LIST];
+  __shared__ float s_outer[DET_LIST][9];
+  __shared__ int s_ncand;
   const SurfImage& im = b.im[blockIdx.y];
   int t = blockIdx.x, o = 0;
   while (o + 1 < g.n_octaves && t >= g.oct[o + 1].tile_begin) o++;
   const SurfOctave& O = g.oct[o];
   t -= O.tile_begin;
   const int ti0 = (t / O.tiles_x) * TH, tj0 = (t % O.tiles_x) * TW;
-  const int nl = g.n_layers + 2;
+  const int nmid = g.n_layers;
   const int scols = g.w + 1;
   const int step = O.step;
   constexpr int PLANE = (TH + 2) * (TW + 2);
-  for (int idx = threadIdx.x; idx < nl * PLANE; idx += blockDim.x) {
+  if (threadIdx.x == 0) s_ncand = 0;
+  for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
     const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
-    sdet[l][y][x] = det_at(im.sum, scols, O.layer[l], step, ti0 + y - 1, tj0 + x - 1);
+    sdet[l][y][x] = det_at(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < g.n_layers * TH * TW; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < nmid * TH * TW; idx += blockDim.x) {
     const int m = 1 + idx / (TH * TW), r = idx % (TH * TW), y = r / TW, x = r % TW;
     const int i = ti0 + y, j = tj0 + x;
     const int margin = O.nms_margin[m];
     if (i < margin || i >= O.lrows - margin || j < margin || j >= O.lcols - margin) continue;
-    const float val0 = sdet[m][y + 1][x + 1];
+    const float val0 = sdet[m - 1][y + 1][x + 1];
     if (!(val0 > g.thr)) continue;
     float N[3][9];
     bool is_max = true;
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+    for (int a = 0; a < 3; a++) {
+      const int l = m - 1 + a;  // pyramid layer of this plane
+      if (l < 1 || l > nmid) continue;
 #pragma unroll
       for (int q = 0; q < 9; q++) {
-        const float v = sdet[m - 1 + a][y + q / 3][x + q % 3];
+        const float v = sdet[l - 1][y + q / 3][x + q % 3];
         N[a][q] = v;
         if (!(a == 1 && q == 4) && !(val0 > v)) is_max = false;
       }
-    if (!is_max) continue;
-    const int size = O.layer[m].size;
-    const int sum_i = step * (i - (size / 2) / step), sum_j = step * (j - (size / 2) / step);
-    float py = (float)sum_i + (float)(size - 1) * 0.5f;
-    float px = (float)sum_j + (float)(size - 1) * 0.5f;
-    float psize = (float)size;
-    const int ds = size - O.layer[m - 1].size;
-    if (!interpolate_keypoint(N, step, ds, px, py, psize)) continue;
-    const int slot = atomicAdd(&im.counters[0], 1);
-    if (slot < capacity) {
-      uvo_keypoint k;
-      k.x = px;
-      k.y = py;
-      k.size = psize;
-      k.angle = -1.f;
-      k.response = val0;
-      k.octave = o;
-      k.class_id = -1;
-      im.raw[slot] = k;
     }
+    if (!is_max) continue;
+    if (m > 1 && m < nmid) {  // all three planes are middle layers
+      emit_keypoint(O, im, N, m, i, j, o, capacity);
+      continue;
+    }
+    const int slot = atomicAdd(&s_ncand, 1);
+    if (slot < DET_LIST) {
+      s_cand[slot] = DetCand{(short)m, (short)y, (short)x, 1};
+    } else {  // list full: finish this candidate here
+#pragma unroll
+      for (int a = 0; a < 3; a += 2) {
+        const int l = m - 1 + a;
+        if (l >= 1 && l <= nmid) continue;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          const float v = det_at(im.sum, scols, O.layer[l], step, i - 1 + q / 3, j - 1 + q % 3);
+          N[a][q] = v;
+          if (!(val0 > v)) is_max = false;
+        }
+      }
+      if (is_max) emit_keypoint(O, im, N, m, i, j, o, capacity);
+    }
+  }
+  __syncthreads();
+  const int ncand = min(s_ncand, DET_LIST);
+  // outer-layer samples of the listed candidates: 9 per (candidate, outer plane); with a single middle layer a
+  // candidate needs both outer planes, handled as two passes
+  for (int pass = 0; pass < 2; pass++) {
+    for (int idx = threadIdx.x; idx < ncand * 9; idx += blockDim.x) {
+      const int c = idx / 9, q = idx - c * 9;
+      const DetCand cd = s_cand[c];
+      const int l = pass == 0 ? (cd.m == 1 ? 0 : -1) : (cd.m == nmid ? nmid + 1 : -1);
+      if (l < 0) continue;
+      const float v = det_at(im.sum, scols, O.layer[l], step, ti0 + cd.y - 1 + q / 3, tj0 + cd.x - 1 + q % 3);
+      s_outer[c][q] = v;
+      if (!(sdet[cd.m - 1][cd.y + 1][cd.x + 1] > v)) s_cand[c].alive = 0;  // benign race: all writers store 0
+    }
+    __syncthreads();
+    // finish candidates whose last missing plane was this pass's
+    for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+      const DetCand cd = s_cand[c];
+      const bool needs0 = cd.m == 1, needs1 = cd.m == nmid;
+      const bool last = pass == 1 ? needs1 : (needs0 && !needs1);
+      if (!last || !cd.alive) continue;
+      float N[3][9];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int l = cd.m - 1 + a;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          if (l >= 1 && l <= nmid)
+            N[a][q] = sdet[l - 1][cd.y + q / 3][cd.x + q % 3];
+          else if (l == nmid + 1 || !needs1)
+            N[a][q] = s_outer[c][q];  // the plane evaluated in this pass
+          else
+            N[a][q] = det_at(im.sum, scols, O.layer[0], step, ti0 + cd.y - 1 + q / 3, tj0 + cd.x - 1 + q % 3);
+        }
+      }
+      emit_keypoint(O, im, N, cd.m, ti0 + cd.y, tj0 + cd.x, o, capacity);
+    }
+    __syncthreads();
   }
 }
 

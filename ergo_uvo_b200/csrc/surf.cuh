@@ -18,6 +18,10 @@ struct SurfBox {
 struct SurfLayer {
   int size, margin, samples_i, samples_j;
   SurfBox box[10];  // Dx[0..2], Dy[0..2], Dxy[0..3]
+  // The three Dxx (Dyy) boxes share edges, so their 12 corners are 8 distinct integral samples: two rows x four
+  // columns (four rows x two columns).  Offsets as resizeHaarPattern rounds them, rows pre-multiplied by w+1.
+  int xx_row[2], xx_col[4];
+  int yy_row[4], yy_col[2];
 };
 
 struct SurfOctave {
