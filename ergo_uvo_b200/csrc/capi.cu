@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "capi_internal.cuh"
+#include "twoview.cuh"
 #include "match.cuh"
 #include "pose.cuh"
 
@@ -320,6 +321,212 @@ int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count) {
   if (!ctx || !count) return UVO_ERR_INVALID;
   *count = ctx->last_match_fallbacks;
   return UVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K10a / K10b
+namespace {
+struct TwoViewDev {  // device copies of the correspondences + result slots, carved from the stage scratch
+  float* p1;
+  float* p2;
+  uint8_t* mask;
+  double* model;   // 9
+  int* n_inl;
+  double* Rt;      // 14
+  uint8_t* mask2;  // recoverPose output mask
+  uint8_t* flags;
+  double* cand;    // 49
+  int* counts;     // 4
+  void* robust;    // robust scratch
+};
+
+TwoViewDev twoview_stage(uvo_ctx* ctx, const float* p1, const float* p2, int n, int iters, int kind) {
+  Ctx& c = ctx->c;
+  UVO_CUDA(cudaSetDevice(c.device));
+  const size_t need = (size_t)n * 32 + robust_scratch_bytes(n, std::max(iters, 1), kind) + 16384;
+  ctx->scratch.bytes_a.ensure(need);
+  Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
+  TwoViewDev d{};
+  d.p1 = ar.take<float>(2 * (size_t)std::max(n, 1));
+  d.p2 = ar.take<float>(2 * (size_t)std::max(n, 1));
+  d.mask = ar.take<uint8_t>(std::max(n, 1));
+  d.mask2 = ar.take<uint8_t>(std::max(n, 1));
+  d.flags = ar.take<uint8_t>(std::max(n, 1));
+  d.model = ar.take<double>(16);
+  d.n_inl = ar.take<int>(4);
+  d.Rt = ar.take<double>(16);
+  d.cand = ar.take<double>(64);
+  d.counts = ar.take<int>(4);
+  d.robust = ar.take<uint8_t>(robust_scratch_bytes(n, std::max(iters, 1), kind));
+  if (n > 0) {
+    UVO_CUDA(cudaMemcpyAsync(d.p1, p1, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(d.p2, p2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+  }
+  return d;
+}
+
+// findHomography / findEssentialMat on staged device points; results copied back
+void robust_host(uvo_ctx* ctx, const float* p1, const float* p2, int n, int kind, const double* K, int method,
+                 double threshold, int max_iters, double confidence, double model[9], uint8_t* mask, int* n_inliers,
+                 int* hyps, int* ok) {
+  UVO_REQUIRE(n >= 0 && (n == 0 || (p1 && p2)) && model, "two-view estimation: bad argument");
+  UVO_REQUIRE(method == TV_RANSAC || method == TV_LMEDS, "two-view estimation: method must be 8 (RANSAC) or 4 (LMEDS)");
+  UVO_REQUIRE(confidence > 0 && confidence < 1, "two-view estimation: confidence must be in (0, 1)");
+  const int mp = kind == TV_ESSENTIAL ? 5 : 4;
+  for (int k = 0; k < 9; k++) model[k] = 0;
+  if (n_inliers) *n_inliers = 0;
+  if (hyps) *hyps = 0;
+  if (ok) *ok = 0;
+  if (n < mp) {
+    if (mask)
+      for (int i = 0; i < n; i++) mask[i] = 0;
+    return;
+  }
+  Ctx& c = ctx->c;
+  RobustArgs a{};
+  a.kind = kind;
+  a.method = method;
+  a.n = n;
+  a.iters = robust_iterations(method, mp, confidence, max_iters);
+  a.confidence = confidence;
+  if (kind == TV_ESSENTIAL) {
+    for (int k = 0; k < 4; k++) a.K[k] = K[k];
+    a.threshold = threshold / ((K[0] + K[1]) / 2);
+  } else {
+    a.threshold = threshold <= 0 ? 3.0 : threshold;
+  }
+  TwoViewDev d = twoview_stage(ctx, p1, p2, n, a.iters, kind);
+  a.p1 = d.p1;
+  a.p2 = d.p2;
+  robust_bind_scratch(a, d.robust);
+  a.model_out = d.model;
+  a.mask = d.mask;
+  a.n_inliers = d.n_inl;
+  launch_robust(c, a);
+  ctx->pinned_counts.ensure(8);
+  int* pc = ctx->pinned_counts.p;
+  UVO_CUDA(cudaMemcpyAsync(pc, a.ctl, 6 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(pc + 6, d.n_inl, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(model, d.model, 9 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  if (mask) UVO_CUDA(cudaMemcpyAsync(mask, d.mask, n, cudaMemcpyDeviceToHost, c.stream));
+  UVO_CUDA(cudaStreamSynchronize(c.stream));
+  if (n_inliers) *n_inliers = pc[6];
+  if (hyps) *hyps = pc[4];
+  if (ok) *ok = pc[5];
+}
+
+void recover_pose_host(uvo_ctx* ctx, const double model[9], const float* p1, const float* p2, int n, const double K[4],
+                       int from_h, double dist, uint8_t* mask_inout, double R[9], double t[3], int* good, int* found) {
+  UVO_REQUIRE(model && K && R && t && n >= 0 && (n == 0 || (p1 && p2)), "recover pose: bad argument");
+  Ctx& c = ctx->c;
+  TwoViewDev d = twoview_stage(ctx, p1, p2, n, 1, TV_HOMOGRAPHY);
+  UVO_CUDA(cudaMemcpyAsync(d.model, model, 9 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  if (mask_inout && n > 0) UVO_CUDA(cudaMemcpyAsync(d.mask, mask_inout, n, cudaMemcpyHostToDevice, c.stream));
+  RecoverPoseArgs a{};
+  a.p1 = d.p1;
+  a.p2 = d.p2;
+  a.n = n;
+  for (int k = 0; k < 4; k++) a.K[k] = K[k];
+  a.from_homography = from_h;
+  a.model = d.model;
+  a.mask_in = (mask_inout && !from_h) ? d.mask : nullptr;
+  a.distance_thresh = dist;
+  a.cand = d.cand;
+  a.flags = d.flags;
+  a.counts = d.counts;
+  a.Rt = d.Rt;
+  a.mask_out = from_h ? nullptr : d.mask2;
+  launch_recover_pose(c, a);
+  double h[14];
+  UVO_CUDA(cudaMemcpyAsync(h, d.Rt, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  if (mask_inout && !from_h && n > 0) UVO_CUDA(cudaMemcpyAsync(mask_inout, d.mask2, n, cudaMemcpyDeviceToHost, c.stream));
+  UVO_CUDA(cudaStreamSynchronize(c.stream));
+  if (h[13] != 0) {
+    for (int k = 0; k < 9; k++) R[k] = h[k];
+    for (int k = 0; k < 3; k++) t[k] = h[9 + k];
+  }
+  if (good) *good = (int)h[12];
+  if (found) *found = h[13] != 0;
+}
+}  // namespace
+
+int uvo_find_homography(uvo_ctx* ctx, const float* p1, const float* p2, int n, int method, double threshold,
+                        int max_iters, double confidence, double H[9], uint8_t* mask, int* n_inliers, int* hyps,
+                        int* ok) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    robust_host(ctx, p1, p2, n, TV_HOMOGRAPHY, nullptr, method, threshold, max_iters, confidence, H, mask, n_inliers,
+                hyps, ok);
+  });
+}
+
+int uvo_find_essential_mat(uvo_ctx* ctx, const float* p1, const float* p2, int n, const double K[4], int method,
+                           double prob, double threshold, int max_iters, double E[9], uint8_t* mask, int* n_inliers,
+                           int* hyps, int* ok) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(K, "uvo_find_essential_mat: null camera");
+    robust_host(ctx, p1, p2, n, TV_ESSENTIAL, K, method, threshold, max_iters, prob, E, mask, n_inliers, hyps, ok);
+  });
+}
+
+int uvo_recover_pose(uvo_ctx* ctx, const double E[9], const float* p1, const float* p2, int n, const double K[4],
+                     uint8_t* mask_inout, double R[9], double t[3], int* good) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c,
+                 [&] { recover_pose_host(ctx, E, p1, p2, n, K, 0, 50.0, mask_inout, R, t, good, nullptr); });
+}
+
+int uvo_recover_pose_homography(uvo_ctx* ctx, const double H[9], const float* p1, const float* p2, int n,
+                                const double K[4], double homography_distance, double R[9], double t[3], int* good,
+                                int* found) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    recover_pose_host(ctx, H, p1, p2, n, K, 1, homography_distance, nullptr, R, t, good, found);
+  });
+}
+
+int uvo_estimate_relative_pose(uvo_ctx* ctx, const float* p1, const float* p2, int n, const double K[4],
+                               const uvo_params* prm, int* use_essential, double R[9], double t[3],
+                               uint8_t* inlier_mask, int* n_inliers, int* success) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(prm && use_essential && K && R && t && success && n >= 0, "uvo_estimate_relative_pose: bad argument");
+    *success = 0;
+    if (n_inliers) *n_inliers = 0;
+    std::vector<uint8_t> mask((size_t)std::max(n, 1)), shrunk;
+    bool switched = false;
+    for (;;) {  // while (!estimate_completed), VO_utility.cpp:140
+      int valid = 0, cnt = 0, hyps = 0, ok = 0;
+      double M[9];
+      if (*use_essential) {
+        robust_host(ctx, p1, p2, n, TV_ESSENTIAL, K, prm->essential_method, prm->essential_threshold,
+                    (int)prm->essential_max_iters, prm->essential_confidence, M, mask.data(), &cnt, &hyps, &ok);
+        shrunk = mask;  // recoverPose shrinks its own copy; extract_inliers already used the findEssentialMat mask
+        int good = 0;
+        if (ok) recover_pose_host(ctx, M, p1, p2, n, K, 0, 50.0, shrunk.data(), R, t, &good, nullptr);
+        for (int i = 0; i < n; i++) valid += shrunk[i] != 0;
+        if (!ok) valid = 0;
+      } else {
+        robust_host(ctx, p1, p2, n, TV_HOMOGRAPHY, nullptr, prm->homography_method, prm->homography_threshold,
+                    (int)prm->homography_max_iters, prm->homography_confidence, M, mask.data(), &cnt, &hyps, &ok);
+        int good = 0, found = 0;
+        // the reference hands ALL matches to recover_pose_homography, not the inliers (VO_utility.cpp:154, App. D-2)
+        if (ok) recover_pose_host(ctx, M, p1, p2, n, K, 1, prm->homography_distance, nullptr, R, t, &good, &found);
+        valid = cnt;
+      }
+      if (inlier_mask)
+        for (int i = 0; i < n; i++) inlier_mask[i] = mask[i];
+      if (n_inliers) *n_inliers = cnt;
+      const double vpf = n > 0 ? (double)valid / n : 0.0;
+      if (vpf >= prm->vpf_threshold && valid >= prm->min_num_inliers) {
+        *success = 1;
+        break;
+      }
+      if (switched) break;  // both methods failed
+      switched = true;
+      *use_essential = !*use_essential;
+    }
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ K11, K12, K10c

@@ -169,6 +169,73 @@ class Context:
         self._ck(self.lib.uvo_match_last_fallbacks(self.h, C.byref(n)))
         return n.value
 
+    # ------------------------------------------------------------------ K10a / K10b (VO_utility.cpp:134-180, :581-624)
+    @staticmethod
+    def _pts(p):
+        return np.ascontiguousarray(p, np.float32).reshape(-1, 2)
+
+    def findHomography(self, srcPoints, dstPoints, method=8, ransacReprojThreshold=3.0, maxIters=2000,
+                       confidence=0.995):
+        """cv::findHomography -> (H or None, mask uint8 n, hypotheses evaluated)"""
+        p1, p2 = self._pts(srcPoints), self._pts(dstPoints)
+        n = len(p1)
+        H = np.zeros(9)
+        mask = np.zeros(max(n, 1), np.uint8)
+        ni, hy, ok = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_find_homography(self.h, _p(p1), _p(p2), n, int(method), C.c_double(ransacReprojThreshold),
+                                              int(maxIters), C.c_double(confidence), _p(H), _p(mask), C.byref(ni),
+                                              C.byref(hy), C.byref(ok)))
+        return (H.reshape(3, 3) if ok.value else None), mask[:n], hy.value
+
+    def findEssentialMat(self, points1, points2, cameraMatrix, method=8, prob=0.999, threshold=1.0, maxIters=1000):
+        """cv::findEssentialMat -> (E or None, mask uint8 n, hypotheses evaluated)"""
+        p1, p2 = self._pts(points1), self._pts(points2)
+        n = len(p1)
+        E = np.zeros(9)
+        mask = np.zeros(max(n, 1), np.uint8)
+        ni, hy, ok = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_find_essential_mat(self.h, _p(p1), _p(p2), n, _p(_k4(cameraMatrix)), int(method),
+                                                 C.c_double(prob), C.c_double(threshold), int(maxIters), _p(E),
+                                                 _p(mask), C.byref(ni), C.byref(hy), C.byref(ok)))
+        return (E.reshape(3, 3) if ok.value else None), mask[:n], hy.value
+
+    def recoverPose(self, E, points1, points2, cameraMatrix, mask=None):
+        """cv::recoverPose -> (good, R, t, mask)"""
+        p1, p2 = self._pts(points1), self._pts(points2)
+        n = len(p1)
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        R, t = np.zeros(9), np.zeros(3)
+        m = np.ascontiguousarray(mask, np.uint8).reshape(-1).copy() if mask is not None else np.ones(max(n, 1), np.uint8)
+        good = C.c_int(0)
+        self._ck(self.lib.uvo_recover_pose(self.h, _p(E), _p(p1), _p(p2), n, _p(_k4(cameraMatrix)), _p(m), _p(R),
+                                           _p(t), C.byref(good)))
+        return good.value, R.reshape(3, 3), t, m[:n]
+
+    def recover_pose_homography(self, H, inliers1, inliers2, cameraMatrix):
+        """VO_utility.cpp:581-624 -> (max_good_points, R, t) with R, t None when no candidate has a good point"""
+        p1, p2 = self._pts(inliers1), self._pts(inliers2)
+        H = np.ascontiguousarray(H, np.float64).reshape(9)
+        R, t = np.zeros(9), np.zeros(3)
+        good, found = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_recover_pose_homography(self.h, _p(H), _p(p1), _p(p2), len(p1), _p(_k4(cameraMatrix)),
+                                                      C.c_double(self.params.homography_distance), _p(R), _p(t),
+                                                      C.byref(good), C.byref(found)))
+        if not found.value:
+            return good.value, None, None
+        return good.value, R.reshape(3, 3), t
+
+    def estimate_relative_pose(self, keypoints1_conv, keypoints2_conv, cameraMatrix, use_essential):
+        """VO_utility.cpp:134-180 -> (success, R, t, inlier mask of extract_inliers, use_essential after the call)"""
+        p1, p2 = self._pts(keypoints1_conv), self._pts(keypoints2_conv)
+        n = len(p1)
+        R, t = np.zeros(9), np.zeros(3)
+        mask = np.zeros(max(n, 1), np.uint8)
+        ue, ni, ok = C.c_int(1 if use_essential else 0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_estimate_relative_pose(self.h, _p(p1), _p(p2), n, _p(_k4(cameraMatrix)),
+                                                     C.byref(self.params), C.byref(ue), _p(R), _p(t), _p(mask),
+                                                     C.byref(ni), C.byref(ok)))
+        return bool(ok.value), R.reshape(3, 3), t, mask[:n], bool(ue.value)
+
     # ------------------------------------------------------------------ VO_utility.h:116
     def select_estimation_method(self, keypoints1_conv, keypoints2_conv):
         p1 = np.ascontiguousarray(keypoints1_conv, np.float32).reshape(-1, 2)

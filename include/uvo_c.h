@@ -167,6 +167,39 @@ UVO_API int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X_host, const float
                                  int iterations, float reprojection_error, double confidence, double rvec[3],
                                  double tvec[3], int32_t* inliers_host, int* n_inliers, int* hyps_evaluated);
 
+/* ---------------------------------------------------------------------------------------------------- K10a / K10b */
+/* cv::findHomography(p1, p2, method, ransacReprojThreshold, mask, maxIters, confidence) -- VO_utility.cpp:152.
+ * p1, p2: n x 2 f32 (host).  method: 8 = RANSAC, 4 = LMEDS.  H (row-major, H[8] = 1) is the model re-fitted on the
+ * inliers of the best hypothesis and LM-refined; mask is the refined model's mask at the threshold (OpenCV 4.13
+ * behaviour, see oracle/twoview.py).  *ok = 0 (H zeroed, mask zeroed) when no model is found. */
+UVO_API int uvo_find_homography(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n, int method,
+                                double threshold, int max_iters, double confidence, double H[9], uint8_t* mask_host,
+                                int* n_inliers, int* hyps_evaluated, int* ok);
+/* cv::findEssentialMat(p1, p2, K, method, prob, threshold, maxIters, mask) -- VO_utility.cpp:147.  K = fx, fy, cx, cy.
+ * Nister 5-point hypotheses; E is the best hypothesis (unit Frobenius norm), mask its inliers. */
+UVO_API int uvo_find_essential_mat(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n, const double K[4],
+                                   int method, double prob, double threshold, int max_iters, double E[9],
+                                   uint8_t* mask_host, int* n_inliers, int* hyps_evaluated, int* ok);
+/* cv::recoverPose(E, p1, p2, K, R, t, mask) -- VO_utility.cpp:149: cheirality vote (distanceThresh = 50) over the 4
+ * decompositions; mask_inout (nullable) is AND-ed in and overwritten with the winner's validity, *good = its count. */
+UVO_API int uvo_recover_pose(uvo_ctx* ctx, const double E[9], const float* p1_host, const float* p2_host, int n,
+                             const double K[4], uint8_t* mask_inout_host, double R[9], double t[3], int* good);
+/* int recover_pose_homography(H, inliers1, inliers2, K, R, t) -- VO_utility.h / VO_utility.cpp:581-624:
+ * decomposeHomographyMat + triangulation vote (0 < z < HOMOGRAPHY_DISTANCE), t normalised.  Returns the vote count
+ * in *good; *found = 0 (R, t untouched = zero) when no candidate has a good point.  The reference reads the f32
+ * depth through at<double> (undefined behaviour); this implements the evident intent. */
+UVO_API int uvo_recover_pose_homography(uvo_ctx* ctx, const double H[9], const float* p1_host, const float* p2_host,
+                                        int n, const double K[4], double homography_distance, double R[9],
+                                        double t[3], int* good, int* found);
+/* void estimate_relative_pose(kp1, kp2, K, R, t, inliers1, inliers2, inlier_matches, success) -- VO_utility.h:101,
+ * VO_utility.cpp:134-180: essential or homography branch chosen by *use_essential_inout (the sticky global,
+ * VO_utility.h:89), VPF / MIN_NUM_INLIERS gate, one switch of method on failure.  inlier_mask_host receives the mask
+ * extract_inliers used (the findEssentialMat / findHomography mask, BEFORE recoverPose shrinks it). */
+UVO_API int uvo_estimate_relative_pose(uvo_ctx* ctx, const float* p1_host, const float* p2_host, int n,
+                                       const double K[4], const uvo_params* prm, int* use_essential_inout,
+                                       double R[9], double t[3], uint8_t* inlier_mask_host, int* n_inliers,
+                                       int* success);
+
 /* ---------------------------------------------------------------------------------------------------- frames */
 /* Device-resident replay of visual_odometry_node::stereo_VO's per-frame body (visual_odometry.h:526-740):
  * one call per stereo pair; previous-frame state (after-stereo-match keypoints/descriptors, last t) lives on the

@@ -610,7 +610,7 @@ def recover_pose_homography(H, p1, p2, K, homography_distance):
     for i, (R, t, _n) in enumerate(cands):
         X = _triangulate_h(P0, K @ np.c_[R, t], p1, p2).astype(F32)  # triangulatePoints returns f32 for f32 input
         with np.errstate(divide="ignore", invalid="ignore"):
-            z = (X[2] / np.where(X[3] != 0, X[3], F32(1))).astype(np.float64)
+            z = (X[2] / X[3]).astype(np.float64)  # convert_from_homogeneous_coords: plain f32 division
         good = int(((z > 0) & (z < homography_distance)).sum())
         if good > best_good:
             best, best_good = i, good
