@@ -4,5 +4,5 @@ The product is the C-ABI shared library `libuvo_b200.so` (include/uvo_c.h, sourc
 This package is the thin Python binding used by tests/ and bench.py; `vo_utility` mirrors the reference's
 `uvo_libraries` function API (uvo_libraries/include/uvo_libraries/VO_utility.h:96-117).
 """
-from ._lib import Camera, Params, StereoResult, UvoError, load, SO_PATH  # noqa: F401
+from ._lib import Camera, MonoResult, Params, StereoResult, UvoError, load, SO_PATH  # noqa: F401
 from .vo_utility import *  # noqa: F401,F403

@@ -53,6 +53,15 @@ class StereoResult(C.Structure):
     ]
 
 
+class MonoResult(C.Structure):
+    _fields_ = [
+        ("initialised", C.c_int32), ("skipped", C.c_int32), ("published", C.c_int32), ("valid", C.c_int32),
+        ("used_essential", C.c_int32), ("n_keypoints", C.c_int32), ("n_matches", C.c_int32), ("n_inliers", C.c_int32),
+        ("n_3d", C.c_int32), ("reserved", C.c_int32),
+        ("R", C.c_double * 9), ("t", C.c_double * 3), ("scale_factor", C.c_double), ("velocity", C.c_double * 3),
+    ]
+
+
 _lib = None
 
 

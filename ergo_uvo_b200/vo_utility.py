@@ -16,7 +16,7 @@ KEYPOINT_DTYPE = np.dtype(
      ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
-__all__ = ["Context", "default_params", "make_camera", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO"]
+__all__ = ["Context", "default_params", "make_camera", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
 
 
 def _p(a):
@@ -384,3 +384,34 @@ class StereoVO:
         self.ctx._ck(self.lib.uvo_stereo_stage_ms(self.h, ms))
         names = [self.lib.uvo_stage_name(i).decode() for i in range(L.UVO_N_STAGES)]
         return dict(zip(names, list(ms)))
+
+
+class MonoVO:
+    """visual_odometry_node::mono_VO's per-frame body (visual_odometry.h:247-397) behind uvo_mono."""
+
+    def __init__(self, ctx, width, height, cam, params=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.params = params or default_params(False)
+        h = C.c_void_p()
+        ctx._ck(self.lib.uvo_mono_create(ctx.h, width, height, C.byref(cam), C.byref(self.params), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.uvo_mono_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def frame(self, img3, dt, distance):
+        """Host image (h x w x 3 u8) + altimeter range in, MonoResult out."""
+        img = np.ascontiguousarray(img3, np.uint8)
+        res = L.MonoResult()
+        self.ctx._ck(self.lib.uvo_mono_frame(self.h, _p(img), C.c_size_t(img.strides[0]), C.c_double(dt),
+                                             C.c_double(distance), C.byref(res)))
+        return res

@@ -253,6 +253,36 @@ UVO_API int uvo_stereo_last_inliers(uvo_stereo* s, int32_t* inliers_host, int ca
 UVO_API int uvo_stereo_stage_ms(uvo_stereo* s, float ms[UVO_N_STAGES]);
 UVO_API const char* uvo_stage_name(int i);
 
+/* ---------------------------------------------------------------------------------------------------- mono frames */
+/* visual_odometry_node::mono_VO's per-frame body (visual_odometry.h:247-397) behind one handle: get_image ->
+ * detect_features -> match_features(7-arg) -> select_estimation_method -> estimate_relative_pose -> triangulatePoints
+ * -> extract_3Dpoints -> convert_3Dpoints_camera / compute_scale_factor -> mono_output_computation.  Previous-frame
+ * keypoints / descriptors, the sticky use_essential flag and the last R, t, SF ("ASSUMING CONSTANT MOTION",
+ * visual_odometry.h:343-382) live in the handle. */
+typedef struct uvo_mono uvo_mono;
+
+typedef struct {
+  int32_t initialised;     /* vo_initialized */
+  int32_t skipped;         /* a "SKIP IMAGE" gate fired: nothing is published for this frame */
+  int32_t published;       /* mono_output_computation ran */
+  int32_t valid;           /* successful_estimate.data */
+  int32_t used_essential;  /* use_essential after estimate_relative_pose */
+  int32_t n_keypoints, n_matches, n_inliers, n_3d;
+  int32_t reserved;
+  double R[9], t[3];       /* R_currCam_prevCam, t_currCam_prevCam (unit norm) */
+  double scale_factor;     /* SF */
+  double velocity[3];      /* -SF * R^T t / dt */
+} uvo_mono_result;
+
+UVO_API int uvo_mono_create(uvo_ctx* ctx, int width, int height, const uvo_camera* cam, const uvo_params* prm,
+                            uvo_mono** out);
+UVO_API void uvo_mono_destroy(uvo_mono* m);
+/* one image (3-channel interleaved u8, host) + the altimeter range of that instant (visual_odometry.h:367) */
+UVO_API int uvo_mono_frame(uvo_mono* m, const uint8_t* img3_host, size_t pitch, double dt, double range,
+                           uvo_mono_result* out);
+UVO_API int uvo_mono_frame_device(uvo_mono* m, const uint8_t* img3_dev, size_t pitch, double dt, double range,
+                                  uvo_mono_result* out);
+
 #ifdef __cplusplus
 }
 #endif
