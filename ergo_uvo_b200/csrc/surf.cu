@@ -512,7 +512,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int DESC_THREADS = 128;
-constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows go one output row at a time
+constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows are streamed in chunks
 
 // One block per keypoint (grid-stride).  Shared: 21x21 patch, 2x400 gradients, 64-vector.
 __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_constant__ SurfGeom g,
@@ -521,6 +521,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
   __shared__ int s_patch[21][21];
   __shared__ AreaSpan s_span[21];
   __shared__ float s_buf[DESC_BUF_ROWS * 21];
+  __shared__ float s_acc[441];
   __shared__ float s_dx[400], s_dy[400];
   __shared__ float s_vec[64];
   __shared__ float s_scale;
@@ -658,77 +659,82 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
     if (win_size == 21) {
       for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t / 21][t % 21] = ws.at(t / 21, t % 21);
     } else if (upright) {
-      // Separable form of OpenCV's ResizeArea_Invoker, exactly its arithmetic order: pass 1 reduces every window row
-      // i along j into buf[i][dx] (consecutive threads take consecutive i == consecutive image x: coalesced, each
-      // window pixel is read once), pass 2 accumulates beta * buf over the rows of each dy.  Windows taller than the
-      // shared buffer are processed one dy at a time.
+      // Separable form of OpenCV's ResizeArea_Invoker in exactly its arithmetic order.  Pass 1: one work item per
+      // (window row i, group of 7 destination columns); the item walks its 7 cells along j -- image rows -- in
+      // increasing j, so every window pixel is read once (a pixel shared by two partial cells twice), consecutive
+      // threads read consecutive image x (coalesced) and the f32 sums are accumulated in the CPU order.  Pass 2
+      // accumulates beta * buf over the window rows of each destination row, streaming over chunks of
+      // DESC_BUF_ROWS rows with the 441 running sums kept in shared memory (0 + v == v exactly, so starting from
+      // zero equals OpenCV's "first row assigns").
       const uint8_t* __restrict__ img = im.img;
       const size_t pitch = im.pitch;
       const int sx0 = ws.start_x, sy0 = ws.start_y;
-      auto pix = [&](int i, int j) -> int {
-        const int x = min(max(sx0 + i, 0), w - 1), y = min(max(sy0 - j, 0), h - 1);
-        return __ldg(img + (size_t)y * pitch + x);
-      };
-      auto row_reduce = [&](int i, int dx) -> float {  // buf[dx] of window row i
-        if (area_fast) {
-          int acc = 0;
-          for (int j = dx * iscale; j < dx * iscale + iscale; j++) acc += pix(i, j);
-          return __int_as_float(acc);
-        }
-        const AreaSpan xs = s_span[dx];
-        float buf = 0.f;
-        if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, xs.sx1 - 1), xs.a_l));
-        for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, sx), xs.a_f));
-        if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)pix(i, xs.sx2), xs.a_r));
-        return buf;
-      };
-      auto col_reduce = [&](int dy, int dx, int row0) -> int {  // PATCH[dy][dx] from s_buf rows (offset row0)
-        if (area_fast) {
-          int acc = 0;
-          for (int i = dy * iscale; i < dy * iscale + iscale; i++) acc += __float_as_int(s_buf[(i - row0) * 21 + dx]);
-          if (iscale == 2) return (acc + 2) >> 2;
-          return min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
-        }
-        const AreaSpan ys = s_span[dy];
-        float sum = 0.f;
-        bool first = true;
-        auto add = [&](int i, float beta) {
-          const float v = __fmul_rn(beta, s_buf[(i - row0) * 21 + dx]);
-          sum = first ? v : __fadd_rn(sum, v);
-          first = false;
-        };
-        if (ys.has_l) add(ys.sx1 - 1, ys.a_l);
-        for (int i = ys.sx1; i < ys.sx2; i++) add(i, ys.a_f);
-        if (ys.has_r) add(ys.sx2, ys.a_r);
-        return min(max(__float2int_rn(sum), 0), 255);
-      };
-      if (win_size <= DESC_BUF_ROWS) {
-        for (int t = tid; t < win_size * 21; t += DESC_THREADS) {
-          const int dx = t / win_size, i = t - dx * win_size;
-          s_buf[i * 21 + dx] = row_reduce(i, dx);
+      const bool interior_y = (sy0 - (win_size - 1) >= 0) && (sy0 <= h - 1);
+      for (int t = tid; t < 441; t += DESC_THREADS) s_acc[t] = 0.f;
+      for (int c0 = 0; c0 < win_size; c0 += DESC_BUF_ROWS) {
+        const int rows = min(win_size - c0, DESC_BUF_ROWS);
+        __syncthreads();  // s_acc zeroed / previous chunk's pass 2 done with s_buf
+        for (int t = tid; t < rows * 3; t += DESC_THREADS) {
+          const int grp = t / rows, il = t - grp * rows;
+          const int x = min(max(sx0 + c0 + il, 0), w - 1);
+          const uint8_t* col = img + x;
+          auto pix = [&](int j) -> int {
+            const int y = interior_y ? (sy0 - j) : min(max(sy0 - j, 0), h - 1);
+            return __ldg(col + (size_t)y * pitch);
+          };
+          float* dst = s_buf + il * 21 + grp * 7;
+          if (area_fast) {
+#pragma unroll 1
+            for (int d = 0; d < 7; d++) {
+              const int j0 = (grp * 7 + d) * iscale;
+              int acc = 0;
+              for (int j = j0; j < j0 + iscale; j++) acc += pix(j);
+              dst[d] = __int_as_float(acc);
+            }
+          } else {
+#pragma unroll 1
+            for (int d = 0; d < 7; d++) {
+              const AreaSpan xs = s_span[grp * 7 + d];
+              float buf = 0.f;
+              if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)pix(xs.sx1 - 1), xs.a_l));
+              for (int j = xs.sx1; j < xs.sx2; j++) buf = __fadd_rn(buf, __fmul_rn((float)pix(j), xs.a_f));
+              if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)pix(xs.sx2), xs.a_r));
+              dst[d] = buf;
+            }
+          }
         }
         __syncthreads();
-        for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t / 21][t % 21] = col_reduce(t / 21, t % 21, 0);
-      } else {
-        for (int dy = 0; dy < 21; dy++) {
-          int r0, r1;  // window rows feeding this dy
+        for (int t = tid; t < 441; t += DESC_THREADS) {
+          const int dy = t / 21, dx = t - dy * 21;
           if (area_fast) {
-            r0 = dy * iscale;
-            r1 = r0 + iscale;
+            const int lo = max(dy * iscale, c0), hi = min(dy * iscale + iscale, c0 + rows);
+            int acc = __float_as_int(s_acc[t]);
+            for (int i = lo; i < hi; i++) acc += __float_as_int(s_buf[(i - c0) * 21 + dx]);
+            s_acc[t] = __int_as_float(acc);
           } else {
             const AreaSpan ys = s_span[dy];
-            r0 = ys.has_l ? ys.sx1 - 1 : ys.sx1;
-            r1 = ys.has_r ? ys.sx2 + 1 : ys.sx2;
+            const int first = ys.has_l ? ys.sx1 - 1 : ys.sx1, last = ys.has_r ? ys.sx2 + 1 : ys.sx2;  // [first, last)
+            const int lo = max(first, c0), hi = min(last, c0 + rows);
+            float sum = s_acc[t];
+            for (int i = lo; i < hi; i++) {
+              const float beta = (i < ys.sx1) ? ys.a_l : (i < ys.sx2 ? ys.a_f : ys.a_r);
+              sum = __fadd_rn(sum, __fmul_rn(beta, s_buf[(i - c0) * 21 + dx]));
+            }
+            s_acc[t] = sum;
           }
-          const int nr = r1 - r0;
-          for (int t = tid; t < nr * 21; t += DESC_THREADS) {
-            const int dx = t / nr, r = t - dx * nr;
-            s_buf[r * 21 + dx] = row_reduce(r0 + r, dx);
-          }
-          __syncthreads();
-          if (tid < 21) s_patch[dy][tid] = col_reduce(dy, tid, r0);
-          __syncthreads();
         }
+      }
+      __syncthreads();
+      for (int t = tid; t < 441; t += DESC_THREADS) {
+        int outv;
+        if (area_fast) {
+          const int acc = __float_as_int(s_acc[t]);
+          if (iscale == 2) outv = (acc + 2) >> 2;
+          else outv = min(max(__float2int_rn(__fmul_rn((float)acc, 1.f / (float)(iscale * iscale))), 0), 255);
+        } else {
+          outv = min(max(__float2int_rn(s_acc[t]), 0), 255);
+        }
+        s_patch[t / 21][t % 21] = outv;
       }
     } else {
       for (int t = tid; t < 441; t += DESC_THREADS) {
