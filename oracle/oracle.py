@@ -267,38 +267,3 @@ def epnp(X, x, K):
     t = np.empty(3)
     lib().orc_epnp(_p(X), _p(x), X.shape[0], _p(_k4(K)), _p(R), _p(t))
     return R, t
-
-
-def find_essential_mat(p1, p2, K, method=8, prob=0.999, threshold=1.0, max_iters=1000):
-    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
-    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
-    n = p1.shape[0]
-    E = np.zeros((3, 3))
-    mask = np.zeros(n, np.uint8)
-    hyp = C.c_int(0)
-    ok = lib().orc_find_essential_mat(_p(p1), _p(p2), n, _p(_k4(K)), method, C.c_double(prob),
-                                      C.c_double(threshold), max_iters, _p(E), _p(mask), C.byref(hyp))
-    return ok, E, mask, hyp.value
-
-
-def recover_pose(E, p1, p2, K, mask):
-    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
-    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
-    E = np.ascontiguousarray(E, np.float64)
-    mask = np.ascontiguousarray(mask, np.uint8).copy()
-    R = np.zeros((3, 3))
-    t = np.zeros(3)
-    good = lib().orc_recover_pose(_p(E), _p(p1), _p(p2), p1.shape[0], _p(_k4(K)), _p(R), _p(t), _p(mask))
-    return good, R, t, mask
-
-
-def find_homography(p1, p2, method=8, threshold=3.0, max_iters=2000, confidence=0.995):
-    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
-    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
-    n = p1.shape[0]
-    H = np.zeros((3, 3))
-    mask = np.zeros(n, np.uint8)
-    hyp = C.c_int(0)
-    ok = lib().orc_find_homography(_p(p1), _p(p2), n, method, C.c_double(threshold), max_iters,
-                                   C.c_double(confidence), _p(H), _p(mask), C.byref(hyp))
-    return ok, H, mask, hyp.value

@@ -106,13 +106,8 @@ int orc_solve_pnp_ransac_epnp(const double* X, const float* x, int n, const doub
 /* EPnP on a given set (cv::solvePnP(..., SOLVEPNP_EPNP)); X n x3 f64, x n x2 f64 */
 void orc_epnp(const double* X, const double* x, int n, const double K[4], double R[9], double t[3]);
 
-/* ---- K10a/K10b: mono relative pose (VO_utility.cpp:134-180, :581-624) ---- */
-int orc_find_essential_mat(const float* p1, const float* p2, int n, const double K[4], int method, double prob,
-                           double threshold, int max_iters, double E[9], uint8_t* mask, int* hyps_evaluated);
-int orc_recover_pose(const double E[9], const float* p1, const float* p2, int n, const double K[4], double R[9],
-                     double t[3], uint8_t* mask /* in/out */);
-int orc_find_homography(const float* p1, const float* p2, int n, int method, double threshold, int max_iters,
-                        double confidence, double H[9], uint8_t* mask, int* hyps_evaluated);
+/* K10a / K10b (findEssentialMat, findHomography, recoverPose, decomposeHomographyMat) are restated in numpy:
+ * oracle/twoview.py, pinned to cv2 4.13 (tests/test_oracle_twoview.py, tests/golden/twoview.npz). */
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,16 @@ uvo_params params_from_globals() {
   p.surf_octave_layers = SURF_OCTAVES_LAYERS;
   p.surf_extended = SURF_EXTENDED;
   p.surf_upright = SURF_UPRIGHT;
+  p.essential_method = ESSENTIAL_OUTLIER_METHOD;
+  p.essential_max_iters = ESSENTIAL_MAX_ITERS;
+  p.essential_confidence = ESSENTIAL_CONFIDENCE;
+  p.essential_threshold = ESSENTIAL_THRESHOLD;
+  p.homography_method = HOMOGRAPHY_OUTLIER_METHOD;
+  p.homography_max_iters = HOMOGRAPHY_MAX_ITERS;
+  p.homography_confidence = HOMOGRAPHY_CONFIDENCE;
+  p.homography_threshold = HOMOGRAPHY_THRESHOLD;
+  p.homography_distance = HOMOGRAPHY_DISTANCE;
+  p.vpf_threshold = VPF_THRESHOLD;
   return p;
 }
 void K4(const Mat& K, double k[4]) {
@@ -139,6 +149,57 @@ bool select_estimation_method(const vector<Point2f>& keypoints1_conv, const vect
                                      DISTANCE, &use_e));
   if (!use_e) ROS_INFO("BASELINE IS TOO LOW. USING HOMOGRAPHY!");
   return use_e != 0;
+}
+
+// VO_utility.cpp:134-180.  findEssentialMat + recoverPose / findHomography + recover_pose_homography, the VPF and
+// MIN_NUM_INLIERS gate and the single switch of method all run behind one C call; `use_essential` is the sticky
+// global of VO_utility.h:89 and is updated in place exactly as the reference does (:175).
+void estimate_relative_pose(vector<Point2f> keypoints1_conv, vector<Point2f> keypoints2_conv, Mat cameraMatrix,
+                            Mat& R_currCam_prevCam, Mat& t_currCam_prevCam, vector<Point2f>& inliers1,
+                            vector<Point2f>& inliers2, vector<DMatch>& inlier_matches, bool& success) {
+  const int n = (int)keypoints1_conv.size();
+  double k[4];
+  K4(cameraMatrix, k);
+  uvo_params p = params_from_globals();
+  std::vector<uint8_t> mask(std::max(n, 1));
+  int ue = use_essential ? 1 : 0, n_inl = 0, ok = 0;
+  if (R_currCam_prevCam.empty()) R_currCam_prevCam = Mat::eye(3, 3, CV_64F);
+  if (t_currCam_prevCam.empty()) t_currCam_prevCam = Mat::zeros(3, 1, CV_64F);
+  check(uvo_estimate_relative_pose(ctx(), n ? &keypoints1_conv[0].x : nullptr, n ? &keypoints2_conv[0].x : nullptr, n,
+                                   k, &p, &ue, R_currCam_prevCam.ptr<double>(), t_currCam_prevCam.ptr<double>(),
+                                   mask.data(), &n_inl, &ok));
+  if ((ue != 0) != use_essential) ROS_WARN("###### SWITCHING METHOD ######");
+  use_essential = ue != 0;
+  success = ok != 0;
+  if (!success) ROS_WARN("###### BOTH METHODS FAILED ######");
+  // extract_inliers (VO_utility.cpp:306-329)
+  inliers1.clear();
+  inliers2.clear();
+  inlier_matches.clear();
+  for (int i = 0; i < n; i++)
+    if (mask[i]) {
+      inliers1.push_back(keypoints1_conv[i]);
+      inliers2.push_back(keypoints2_conv[i]);
+      DMatch m;
+      m.queryIdx = (int)inliers1.size() - 1;
+      m.trainIdx = (int)inliers2.size() - 1;
+      inlier_matches.push_back(m);
+    }
+}
+
+// VO_utility.cpp:581-624
+int recover_pose_homography(Mat H, vector<Point2f> inliers1, vector<Point2f> inliers2, Mat cameraMatrix, Mat& R, Mat& t) {
+  double k[4], Rm[9] = {0}, tv[3] = {0};
+  K4(cameraMatrix, k);
+  int good = 0, found = 0;
+  const int n = (int)inliers1.size();
+  check(uvo_recover_pose_homography(ctx(), H.ptr<double>(), n ? &inliers1[0].x : nullptr, n ? &inliers2[0].x : nullptr,
+                                    n, k, HOMOGRAPHY_DISTANCE, Rm, tv, &good, &found));
+  if (found) {
+    R = Mat(3, 3, CV_64F, Rm).clone();
+    t = Mat(3, 1, CV_64F, tv).clone();
+  }
+  return good;
 }
 
 // The three cv:: calls the node makes directly (visual_odometry.h:355/:631, :647, :673) are not part of
