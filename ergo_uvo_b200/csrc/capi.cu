@@ -200,6 +200,62 @@ int uvo_get_image(uvo_ctx* ctx, const uint8_t* src3, int w, int h, size_t spitch
   });
 }
 
+int uvo_resize_area(uvo_ctx* ctx, const uint8_t* src, int sw, int sh, size_t spitch, int channels, uint8_t* dst, int dw,
+                    int dh, size_t dpitch) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(src && dst && sw > 0 && sh > 0 && dw > 0 && dh > 0 && (channels == 1 || channels == 3) &&
+                    spitch >= (size_t)sw * channels && dpitch >= (size_t)dw * channels,
+                "uvo_resize_area: bad argument");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    StageScratch& s = ctx->scratch;
+    const size_t dp = ((size_t)dw * channels + 15) & ~(size_t)15;
+    s.src3.ensure(spitch * sh);
+    s.bytes_b.ensure(dp * dh);
+    s.bytes_d.ensure(sizeof(AreaCell) * (size_t)(dw + dh));
+    UVO_CUDA(cudaMemcpyAsync(s.src3.get(), src, spitch * sh, cudaMemcpyHostToDevice, c.stream));
+    launch_resize_area(c, s.src3.get(), spitch, sw, sh, channels, s.bytes_b.get(), dp, dw, dh, (AreaCell*)s.bytes_d.get());
+    UVO_CUDA(cudaMemcpy2DAsync(dst, dpitch, s.bytes_b.get(), dp, (size_t)dw * channels, dh, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int uvo_get_image_resized(uvo_ctx* ctx, const uint8_t* src3, int w, int h, size_t spitch, int desired_width,
+                          const uvo_camera* cam, int clahe, int clip_limit, uint8_t* dst, size_t dpitch, int* out_w,
+                          int* out_h) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(src3 && dst && cam && w > 0 && h > 0 && desired_width > 0 && desired_width <= w,
+                "uvo_get_image_resized: bad argument");
+    // VO_utility.cpp:339-342
+    const double ratio = (double)w / (double)desired_width;
+    const int dw = desired_width, dh = (int)(h / ratio);
+    UVO_REQUIRE(dh > 0 && spitch >= (size_t)3 * w && dpitch >= (size_t)dw, "uvo_get_image_resized: bad pitch / size");
+    if (out_w) *out_w = dw;
+    if (out_h) *out_h = dh;
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    StageScratch& s = ctx->scratch;
+    const size_t rp = ((size_t)3 * dw + 15) & ~(size_t)15, gp = ((size_t)dw + 3) & ~(size_t)3;
+    s.src3.ensure(spitch * h);
+    s.bytes_b.ensure(rp * dh);
+    s.bytes_d.ensure(sizeof(AreaCell) * (size_t)(dw + dh));
+    s.gray.ensure(gp * dh);
+    s.hist.ensure(64 * 256);
+    s.lut.ensure(64 * 256);
+    UVO_CUDA(cudaMemcpyAsync(s.src3.get(), src3, spitch * h, cudaMemcpyHostToDevice, c.stream));
+    launch_resize_area(c, s.src3.get(), spitch, w, h, 3, s.bytes_b.get(), rp, dw, dh, (AreaCell*)s.bytes_d.get());
+    launch_gray_undistort(c, s.bytes_b.get(), rp, dw, dh, make_undistort_params(*cam), s.gray.get(), gp);
+    if (clahe) {
+      ClaheGeom g = make_clahe_geom(dw, dh, (double)clip_limit, 8, 8);
+      launch_clahe(c, s.gray.get(), gp, dw, dh, g, s.hist.get(), s.lut.get(), s.gray.get(), gp);
+    }
+    UVO_CUDA(cudaMemcpy2DAsync(dst, dpitch, s.gray.get(), gp, dw, dh, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
 int uvo_integral(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t pitch, int32_t* sum) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {

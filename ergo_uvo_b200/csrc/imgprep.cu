@@ -2,6 +2,9 @@
 // Replaces get_image (reference VO_utility.cpp:337-379) and the integral() inside SURF::detectAndCompute
 // (VO_utility.cpp:118).  All three are integer / exactly-specified f32 pipelines: results are bit-identical to the
 // OpenCV CPU path (tests/test_gpu_imgprep.py compares against the oracle and committed cv2 fixtures).
+#include <cfloat>
+#include <cmath>
+
 #include "imgprep.cuh"
 
 namespace uvo {
@@ -328,6 +331,99 @@ void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, i
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
   k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, w, h);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// ------------------------------------------------------------------------------------------------ K0 INTER_AREA
+// OpenCV's ResizeArea_Invoker / ResizeAreaFast for u8 (imgproc/src/resize.cpp): scale in fp64, weights
+// stored as f32, horizontal accumulation per source row in table order, then vertical accumulation, rint + saturate;
+// integer scales in both directions take the block-sum path ((s + 2) >> 2 for 2x2, rint(s * (1.f / area)) otherwise).
+__global__ void k_area_tab(int ssize, int dsize, double scale, AreaCell* __restrict__ tab) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dsize) return;
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  AreaCell t;
+  t.sx1 = sx1;
+  t.sx2 = sx2;
+  t.has_l = (sx1 - fsx1 > 1e-3) ? 1 : 0;
+  t.a_l = (float)((sx1 - fsx1) / cell);
+  t.a_f = (float)(1.0 / cell);
+  t.has_r = (fsx2 - sx2 > 1e-3) ? 1 : 0;
+  t.a_r = (float)(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
+  tab[d] = t;
+}
+
+__global__ void __launch_bounds__(256) k_resize_area(const uint8_t* __restrict__ src, size_t spitch, int sw, int sh,
+                                                     int cn, uint8_t* __restrict__ dst, size_t dpitch, int dw, int dh,
+                                                     const AreaCell* __restrict__ xtab,
+                                                     const AreaCell* __restrict__ ytab, int iscale_x, int iscale_y,
+                                                     int fast) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // element of the destination row: dx * cn + c
+  const int dy = blockIdx.y;
+  if (e >= dw * cn) return;
+  const int dx = e / cn, ch = e - dx * cn;
+  int outv;
+  if (fast) {
+    int sum = 0;
+    for (int ky = 0; ky < iscale_y; ky++) {
+      const int sy = dy * iscale_y + ky;
+      if (sy >= sh) break;
+      const uint8_t* S = src + (size_t)sy * spitch + ch;
+      for (int kx = 0; kx < iscale_x; kx++) {
+        const int sx = dx * iscale_x + kx;
+        if (sx < sw) sum += __ldg(S + sx * cn);
+      }
+    }
+    if (iscale_x == 2 && iscale_y == 2) outv = (sum + 2) >> 2;
+    else outv = min(max(__float2int_rn(__fmul_rn((float)sum, 1.f / (float)(iscale_x * iscale_y))), 0), 255);
+  } else {
+    const AreaCell xs = xtab[dx], ys = ytab[dy];
+    float sum = 0.f;
+    bool first = true;
+    auto row = [&](int sy, float beta) {
+      const uint8_t* S = src + (size_t)sy * spitch + ch;
+      float buf = 0.f;
+      if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)__ldg(S + (xs.sx1 - 1) * cn), xs.a_l));
+      for (int sx = xs.sx1; sx < xs.sx2; sx++) buf = __fadd_rn(buf, __fmul_rn((float)__ldg(S + sx * cn), xs.a_f));
+      if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)__ldg(S + xs.sx2 * cn), xs.a_r));
+      sum = first ? __fmul_rn(beta, buf) : __fadd_rn(sum, __fmul_rn(beta, buf));
+      first = false;
+    };
+    if (ys.has_l) row(ys.sx1 - 1, ys.a_l);
+    for (int sy = ys.sx1; sy < ys.sx2; sy++) row(sy, ys.a_f);
+    if (ys.has_r) row(ys.sx2, ys.a_r);
+    outv = min(max(__float2int_rn(sum), 0), 255);
+  }
+  dst[(size_t)dy * dpitch + e] = (uint8_t)outv;
+}
+
+void launch_resize_area(Ctx& c, const uint8_t* d_src, size_t spitch, int sw, int sh, int cn, uint8_t* d_dst,
+                        size_t dpitch, int dw, int dh, AreaCell* d_tab) {
+  if (sw == dw && sh == dh) {
+    UVO_CUDA(cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, (size_t)sw * cn, sh, cudaMemcpyDeviceToDevice, c.stream));
+    return;
+  }
+  UVO_REQUIRE(dw <= sw && dh <= sh, "resize: INTER_AREA enlargement is not implemented (the reference only shrinks)");
+  // cv::resize derives inv_scale = dsize / ssize and hal::resize inverts it again (scale = 1. / inv_scale)
+  const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
+  const double scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+  const int isx = std::max((int)nearbyint(scale_x), 1), isy = std::max((int)nearbyint(scale_y), 1);
+  const int fast = (fabs(scale_x - isx) < DBL_EPSILON && fabs(scale_y - isy) < DBL_EPSILON) ? 1 : 0;
+  if (!fast) {
+    UVO_KERNEL(c, "k_area_tab");
+    k_area_tab<<<div_up(dw, 128), 128, 0, c.stream>>>(sw, dw, scale_x, d_tab);
+    UVO_LAUNCH_CHECK(c);
+    UVO_KERNEL(c, "k_area_tab");
+    k_area_tab<<<div_up(dh, 128), 128, 0, c.stream>>>(sh, dh, scale_y, d_tab + dw);
+    UVO_LAUNCH_CHECK(c);
+  }
+  UVO_KERNEL(c, "k_resize_area");
+  k_resize_area<<<dim3(div_up(dw * cn, 256), dh), 256, 0, c.stream>>>(d_src, spitch, sw, sh, cn, d_dst, dpitch, dw, dh,
+                                                                     d_tab, d_tab + dw, isx, isy, fast);
   UVO_LAUNCH_CHECK(c);
 }
 

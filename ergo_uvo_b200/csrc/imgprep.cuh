@@ -25,6 +25,15 @@ void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, 
 // d_hist: tiles*256 u32 scratch, d_lut: tiles*256 u8 scratch; src and dst may alias
 void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, unsigned int* d_hist,
                   uint8_t* d_lut, uint8_t* d_dst, size_t dpitch);
+// K0: cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_AREA) for interleaved u8 images with `cn` channels (the
+// pre-scaling branch of get_image, reference VO_utility.cpp:362-363).  d_tab: (dw + dh) AreaCell scratch.
+struct AreaCell {  // one destination index of computeResizeAreaTab: optional left partial cell, full cells
+  int sx1, sx2;    // [sx1, sx2), optional right partial cell
+  int has_l, has_r;
+  float a_l, a_f, a_r;
+};
+void launch_resize_area(Ctx& c, const uint8_t* d_src, size_t spitch, int sw, int sh, int cn, uint8_t* d_dst,
+                        size_t dpitch, int dw, int dh, AreaCell* d_tab);
 // d_sum: (h+1) x (w+1) int32, dense
 void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum);
 

@@ -118,6 +118,29 @@ class Context:
                                         C.c_size_t(w)))
         return out
 
+    def resize_area(self, img, dw, dh):
+        """cv::resize(img, (dw, dh), interpolation=INTER_AREA), u8, 1 or 3 channels"""
+        img = np.ascontiguousarray(img, np.uint8)
+        cn = 1 if img.ndim == 2 else img.shape[2]
+        out = np.empty((dh, dw) if cn == 1 else (dh, dw, cn), np.uint8)
+        self._ck(self.lib.uvo_resize_area(self.h, _p(img), img.shape[1], img.shape[0], C.c_size_t(img.strides[0]), cn,
+                                          _p(out), dw, dh, C.c_size_t(out.strides[0])))
+        return out
+
+    def get_image_resized(self, current_img, desired_width, cameraMatrix, distortionCoeff, newCamMatrix):
+        """get_image with DESIRED_WIDTH != image width (VO_utility.cpp:339-376); the camera is the resized one"""
+        img = np.ascontiguousarray(current_img, np.uint8)
+        h, w = img.shape[:2]
+        dh = int(h / (w / desired_width))
+        out = np.empty((dh, desired_width), np.uint8)
+        cam = make_camera(cameraMatrix, distortionCoeff, newCamMatrix)
+        ow, oh = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_get_image_resized(self.h, _p(img), w, h, C.c_size_t(img.strides[0]), int(desired_width),
+                                                C.byref(cam), int(self.params.clahe), int(self.params.clip_limit),
+                                                _p(out), C.c_size_t(out.strides[0]), C.byref(ow), C.byref(oh)))
+        assert (ow.value, oh.value) == (desired_width, dh)
+        return out
+
     def integral(self, gray):
         g = np.ascontiguousarray(gray, dtype=np.uint8)
         h, w = g.shape

@@ -117,6 +117,15 @@ UVO_API void uvo_host_free(void* p);
  * Native-size branch: cvtColor(RGB2GRAY) + undistort + optional CLAHE(8x8).  src is 3-channel interleaved u8. */
 UVO_API int uvo_get_image(uvo_ctx* ctx, const uint8_t* src3_host, int width, int height, size_t src_pitch,
                           const uvo_camera* cam, int clahe, int clip_limit, uint8_t* dst_host, size_t dst_pitch);
+/* K0: the pre-scaling branch of get_image (VO_utility.cpp:339-342, :362-376): cv::resize(INTER_AREA) to
+ * DESIRED_WIDTH x int(h / (w / DESIRED_WIDTH)), then the same gray / undistort / CLAHE chain.  `cam` is the camera
+ * AFTER resize_camera_matrix (VO_utility.cpp:658-675).  dst must hold *out_h rows of dpitch bytes. */
+UVO_API int uvo_get_image_resized(uvo_ctx* ctx, const uint8_t* src3_host, int width, int height, size_t src_pitch,
+                                  int desired_width, const uvo_camera* cam, int clahe, int clip_limit,
+                                  uint8_t* dst_host, size_t dst_pitch, int* out_width, int* out_height);
+/* cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_AREA) for u8 images with 1 or 3 interleaved channels (shrinking) */
+UVO_API int uvo_resize_area(uvo_ctx* ctx, const uint8_t* src_host, int src_width, int src_height, size_t src_pitch,
+                            int channels, uint8_t* dst_host, int dst_width, int dst_height, size_t dst_pitch);
 /* integral(img, sum, CV_32S) as built inside SURF::detectAndCompute (VO_utility.cpp:118): (h+1) x (w+1) int32 */
 UVO_API int uvo_integral(uvo_ctx* ctx, const uint8_t* gray_host, int width, int height, size_t pitch,
                          int32_t* sum_host);

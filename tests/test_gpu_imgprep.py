@@ -60,3 +60,29 @@ def test_get_image_golden(ctx):
     got = ctx.get_image(z["img"], z["K"], z["D"], z["newK"])
     assert int((got != z["out"]).sum()) == 0
     assert int((ctx.integral(z["out"]) != z["integral"]).sum()) == 0
+
+
+@pytest.mark.parametrize("sw,sh,dw", [(2564, 2048, 640), (1282, 1024, 640), (1280, 1024, 640), (1000, 750, 333),
+                                      (2448, 2048, 1280), (641, 480, 640), (1920, 1080, 640)])
+def test_resize_area_matches_oracle(ctx, oracle, sw, sh, dw):
+    """K0 (VO_utility.cpp:362-363): cv::resize(INTER_AREA), 3-channel; the oracle is bit-exact with cv2 on these sizes
+    (tests/test_oracle_imgprep.py::test_resize_area_3ch_cv2)"""
+    rs = np.random.RandomState(sw + sh)
+    img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+    dh = int(sh / (sw / dw))
+    assert np.array_equal(ctx.resize_area(img, dw, dh), oracle.resize_area(img, dw, dh))
+    g = img[:, :, 1].copy()
+    assert np.array_equal(ctx.resize_area(g, dw, dh), oracle.resize_area(g, dw, dh))
+
+
+def test_get_image_resized_branch(ctx, oracle):
+    """whole pre-scaling branch of get_image: resize -> gray -> undistort -> CLAHE at DESIRED_WIDTH = 640"""
+    from tools import synth
+    seq = synth.MonoSequence(1282, 962, n_frames=1, tex_size=1024)
+    small = synth.MonoSequence(640, 480, n_frames=1, tex_size=1024)  # camera model at the working resolution
+    img = seq.frames[0]
+    dh = int(962 / (1282 / 640))
+    out = ctx.get_image_resized(img, 640, small.K, small.D, small.newK)
+    ref = oracle.get_image(oracle.resize_area(img, 640, dh), small.K, small.D, small.newK, True,
+                           float(ctx.params.clip_limit))
+    assert out.shape == (dh, 640) and np.array_equal(out, ref)

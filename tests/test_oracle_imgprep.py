@@ -68,3 +68,15 @@ def test_optimal_new_camera_matrix_close_to_cv2():
     mine = synth.optimal_new_camera_matrix(K, D, 1280, 1024)
     ref, _ = cv2.getOptimalNewCameraMatrix(K, D, (1280, 1024), 0, (1280, 1024), 0)
     assert np.abs(mine - ref).max() < 1e-3 * ref[0, 0]  # cv2's undistortPoints stops after 5 iterations; ours converges
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+@pytest.mark.parametrize("sw,sh,dw", [(2564, 2048, 640), (1282, 1024, 640), (1280, 1024, 640), (1000, 750, 333),
+                                      (641, 480, 640)])
+def test_resize_area_3ch_cv2(oracle, sw, sh, dw):
+    """K0: the pre-scaling cv::resize(INTER_AREA) of get_image (VO_utility.cpp:362-363), 3 interleaved channels,
+    different x / y scales -- bit-exact with cv2"""
+    rs = np.random.RandomState(sw)
+    img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+    dh = int(sh / (sw / dw))
+    assert np.array_equal(oracle.resize_area(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA))
