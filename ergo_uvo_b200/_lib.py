@@ -40,6 +40,8 @@ class Params(C.Structure):
         ("pnp_method_flag", C.c_int32), ("surf_min_hessian", C.c_int32), ("surf_octaves", C.c_int32),
         ("surf_octave_layers", C.c_int32), ("surf_extended", C.c_int32), ("surf_upright", C.c_int32),
         ("max_features", C.c_int32),
+        ("stereo_gate", C.c_int32), ("stereo_max_epipolar_dy", C.c_double), ("stereo_min_disparity", C.c_double),
+        ("stereo_max_disparity", C.c_double),
     ]
 
 

@@ -172,6 +172,10 @@ void uvo_default_params(int stereo, uvo_params* p) {
   p->surf_extended = 0;
   p->surf_upright = 1;
   p->max_features = 16384;
+  p->stereo_gate = 0;  // the reference has no epipolar / disparity gate (VO_utility.cpp:515-573): off by default
+  p->stereo_max_epipolar_dy = 2.0;
+  p->stereo_min_disparity = 0.0;
+  p->stereo_max_disparity = 1e9;
 }
 
 // ------------------------------------------------------------------------------------------------ K1-K3
@@ -306,8 +310,14 @@ int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t 
 }
 
 // ------------------------------------------------------------------------------------------------ K8
+struct HostGate {  // optional stereo gate of uvo_match_features_gated
+  const uvo_keypoint* k1;
+  const uvo_keypoint* k2;
+  float dy, dmin, dmax;
+};
+
 static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, float ratio,
-                       uvo_dmatch* matches, int* count, uvo_dmatch* knn_out) {
+                       uvo_dmatch* matches, int* count, uvo_dmatch* knn_out, const HostGate* gate = nullptr) {
   UVO_REQUIRE(dim == 64, "matcher: only 64-d SURF descriptors are supported");
   UVO_REQUIRE(n1 >= 0 && n2 >= 0 && (n1 == 0 || d1) && (n2 == 0 || d2), "matcher: bad argument");
   Ctx& c = ctx->c;
@@ -330,6 +340,19 @@ static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
   a.nt = n2;
   a.ratio = ratio;
   match_bind_scratch(a, s.bytes_c.get(), n1, std::max(n2, 1));
+  if (gate && n2 > 0) {
+    const size_t b1 = sizeof(uvo_keypoint) * (size_t)n1, b2 = sizeof(uvo_keypoint) * (size_t)n2;
+    s.bytes_e.ensure(b1 + b2 + 32);
+    uint8_t* base = s.bytes_e.get();
+    const size_t off2 = (b1 + 15) & ~(size_t)15;
+    UVO_CUDA(cudaMemcpyAsync(base, gate->k1, b1, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(base + off2, gate->k2, b2, cudaMemcpyHostToDevice, c.stream));
+    a.gate_kq = (const uvo_keypoint*)base;
+    a.gate_kt = (const uvo_keypoint*)(base + off2);
+    a.gate_dy = gate->dy;
+    a.gate_dmin = gate->dmin;
+    a.gate_dmax = gate->dmax;
+  }
   a.n_matches = (int*)s.bytes_d.get();
   a.matches = (uvo_dmatch*)(s.bytes_d.get() + 16);
   launch_match(c, a);
@@ -362,6 +385,18 @@ int uvo_match_features(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
   return guarded(&ctx->c, [&] {
     UVO_REQUIRE(matches && count, "uvo_match_features: null output");
     match_host(ctx, d1, n1, d2, n2, dim, ratio, matches, count, nullptr);
+  });
+}
+
+int uvo_match_features_gated(uvo_ctx* ctx, const uvo_keypoint* k1, const float* d1, int n1, const uvo_keypoint* k2,
+                             const float* d2, int n2, int dim, float ratio, float max_dy, float min_disp,
+                             float max_disp, uvo_dmatch* matches, int* count) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(matches && count, "uvo_match_features_gated: null output");
+    UVO_REQUIRE((n1 == 0 || k1) && (n2 == 0 || k2), "uvo_match_features_gated: null keypoints");
+    const HostGate g{k1, k2, max_dy, min_disp, max_disp};
+    match_host(ctx, d1, n1, d2, n2, dim, ratio, matches, count, nullptr, &g);
   });
 }
 

@@ -341,6 +341,13 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ms.nq = cap;
   ms.nt = cap;
   ms.ratio = (float)p.lowe_ratio;
+  if (p.stereo_gate) {  // off in the reference's configuration (uvo_params.stereo_gate)
+    ms.gate_kq = L.fe.kps[0].get();
+    ms.gate_kt = L.fe.kps[1].get();
+    ms.gate_dy = (float)p.stereo_max_epipolar_dy;
+    ms.gate_dmin = (float)p.stereo_min_disparity;
+    ms.gate_dmax = (float)p.stereo_max_disparity;
+  }
   match_bind_scratch(ms, L.knn_scratch.get(), cap, cap);
   ms.matches = L.m_stereo.get();
   ms.n_matches = &ctrl->n_stereo;
@@ -357,6 +364,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   mark(4);
   // 5. triangular match: prev-left-after-stereo (query) vs all current left features (train) (:592)
   MatchArgs mt = ms;
+  mt.gate_kq = mt.gate_kt = nullptr;  // the gate is a stereo (rectified pair) constraint only
   mt.q = PL.dL_as.get();
   mt.t = L.fe.desc[0].get();
   mt.nq_dev = &ctrl->nq_temporal;

@@ -561,7 +561,13 @@ __global__ void __launch_bounds__(1024) k_knn_compact(const __grid_constant__ Ma
     const Knn2 b = a.knn[qi];
     // reference: knn[i][0].distance < ratio * knn[i][1].distance; fewer than 2 train rows => no match (the
     // reference would read out of bounds there)
-    if (nt >= 2 && b.i1 >= 0 && b.d0 < __fmul_rn(a.ratio, b.d1)) keep |= 1u << (qi - q0);
+    bool ok = nt >= 2 && b.i1 >= 0 && b.d0 < __fmul_rn(a.ratio, b.d1);
+    if (ok && a.gate_kq) {
+      const uvo_keypoint kq = a.gate_kq[qi], kt = a.gate_kt[b.i0];
+      const float dy = fabsf(__fsub_rn(kq.y, kt.y)), disp = __fsub_rn(kq.x, kt.x);
+      ok = dy <= a.gate_dy && disp >= a.gate_dmin && disp <= a.gate_dmax;
+    }
+    if (ok) keep |= 1u << (qi - q0);
   }
   const int cnt = __popc(keep);
   int incl = cnt;

@@ -24,6 +24,11 @@ struct MatchArgs {
   const int* nt_dev;
   int nq, nt;          // host-known counts or upper bounds (capacity) when *_dev is set
   float ratio;
+  // optional stereo epipolar / disparity gate applied with the ratio test (off when gate_kq == nullptr):
+  // keep iff |y_q - y_t| <= gate_dy and gate_dmin <= x_q - x_t <= gate_dmax
+  const uvo_keypoint* gate_kq;
+  const uvo_keypoint* gate_kt;
+  float gate_dy, gate_dmin, gate_dmax;
   // scratch (match_bind_scratch)
   float* cand;         // capacity x 32 lists x MATCH_TOPK candidate keys (similarity with the column in the low bits)
   float* hb;           // train capacity: -|t|^2 / 2

@@ -381,7 +381,10 @@ __global__ void __launch_bounds__(256) k_surf_rank(const __grid_constant__ SurfB
   __shared__ int s_o[256];
   const SurfImage& im = b.im[blockIdx.z];
   const int n = min(im.counters[0], capacity);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) im.counters[1] = n;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    im.counters[1] = n;
+    im.counters[2] = 0;  // k_surf_describe's work-queue head
+  }
   const int i0 = blockIdx.x * 256, j0 = blockIdx.y * 256;
   if (i0 >= n || j0 >= n) return;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.x;
@@ -445,6 +448,12 @@ __device__ __forceinline__ AreaSpan area_span(int d, int ssize, double scale) {
   s.has_r = (fsx2 - sx2 > 1e-3);
   s.a_r = (float)(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
   return s;
+}
+
+// exact u8 -> f32 of byte `i` of a word without the quarter-rate I2F.U8: PRMT builds the float 2^23 + byte, one FADD
+// removes the 2^23 (both exact)
+__device__ __forceinline__ float byte_to_float(unsigned v, int i) {
+  return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540u | (unsigned)i)), 8388608.f);
 }
 
 struct WinSampler {
@@ -511,7 +520,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-constexpr int DESC_THREADS = 128;
+#ifndef UVO_DESC_THREADS
+#define UVO_DESC_THREADS 256
+#endif
+constexpr int DESC_THREADS = UVO_DESC_THREADS;
 constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows are streamed in chunks
 
 // One block per keypoint (grid-stride).  Shared: 21x21 patch, 2x400 gradients, 64-vector.
@@ -532,7 +544,15 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
   const int n = im.counters[1];
   const int w = g.w, h = g.h, srows = h + 1, scols = w + 1;
   const int tid = threadIdx.x;
-  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+  __shared__ int s_next;
+  // dynamic queue (counters[2], zeroed with the other counters before detection): window areas span 21^2 .. 576^2
+  // pixels, so a static assignment leaves most blocks waiting for the one that drew the largest windows
+  for (;;) {
+    if (tid == 0) s_next = atomicAdd(&im.counters[2], 1);
+    __syncthreads();
+    const int k = s_next;
+    __syncthreads();
+    if (k >= n) break;
     const uvo_keypoint kp = im.kps[k];
     const float size = kp.size, cx = kp.x, cy = kp.y;
     const float s = __fdiv_rn(__fmul_rn(size, 1.2f), 9.0f);
@@ -573,8 +593,8 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
           vY = __fmul_rn((float)dyv, c_aptw[tid]);
         }
       }
-      // ordered compaction over the 128 threads (4 warps)
-      __shared__ int s_wcnt[4];
+      // ordered compaction over the block's warps
+      __shared__ int s_wcnt[DESC_THREADS / 32];
       const unsigned bal = __ballot_sync(0xffffffffu, valid);
       const int lane = tid & 31, wid = tid >> 5;
       if (lane == 0) s_wcnt[wid] = __popc(bal);
@@ -587,7 +607,11 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
         s_Y[slot] = vY;
         s_ang[slot] = fast_atan2_deg(vY, vX);  // cv::phase(X, Y, angle, true)
       }
-      if (tid == 0) s_nangle = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+      if (tid == 0) {
+        int tot = 0;
+        for (int q = 0; q < DESC_THREADS / 32; q++) tot += s_wcnt[q];
+        s_nangle = tot;
+      }
       __syncthreads();
       const int nangle = s_nangle;
       if (nangle == 0) {
@@ -670,10 +694,71 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
       const size_t pitch = im.pitch;
       const int sx0 = ws.start_x, sy0 = ws.start_y;
       const bool interior_y = (sy0 - (win_size - 1) >= 0) && (sy0 <= h - 1);
+      const bool fast_words = interior_y && sx0 >= 0 && sx0 + win_size <= w && (pitch & 3) == 0 &&
+                              ((uintptr_t)img & 3) == 0;
       for (int t = tid; t < 441; t += DESC_THREADS) s_acc[t] = 0.f;
       for (int c0 = 0; c0 < win_size; c0 += DESC_BUF_ROWS) {
         const int rows = min(win_size - c0, DESC_BUF_ROWS);
         __syncthreads();  // s_acc zeroed / previous chunk's pass 2 done with s_buf
+        if (fast_words) {
+          // Interior window, 4-byte aligned image rows: one work item per (aligned group of 4 image columns = 4 window
+          // rows, destination cell d).  The item walks the cell's pixels down image y with one 32-bit load per step
+          // and keeps four independent f32 chains (one per window row), each in OpenCV's order.
+          const int x_first = sx0 + c0, xa = x_first & ~3;
+          const int ncg = ((x_first + rows - 1) >> 2) - (xa >> 2) + 1;
+          for (int t = tid; t < ncg * 21; t += DESC_THREADS) {
+            const int d = t / ncg, m = t - d * ncg;
+            const int xw = xa + 4 * m, il0 = xw - x_first;
+            const uint8_t* p0 = img + (size_t)sy0 * pitch + xw;  // pixel row j lives at p0 - j * pitch
+            float r0, r1, r2, r3;
+            if (area_fast) {
+              const int j0 = d * iscale;
+              const uint8_t* p = p0 - (size_t)j0 * pitch;
+              int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+              for (int j = 0; j < iscale; j++) {
+                const unsigned v = __ldg((const unsigned*)p);
+                p -= pitch;
+                a0 += v & 0xffu;
+                a1 += (v >> 8) & 0xffu;
+                a2 += (v >> 16) & 0xffu;
+                a3 += v >> 24;
+              }
+              r0 = __int_as_float(a0);
+              r1 = __int_as_float(a1);
+              r2 = __int_as_float(a2);
+              r3 = __int_as_float(a3);
+            } else {
+              const AreaSpan xs = s_span[d];
+              float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+              auto step = [&](const uint8_t* q, float a) {
+                const unsigned v = __ldg((const unsigned*)q);
+                b0 = __fadd_rn(b0, __fmul_rn(byte_to_float(v, 0), a));
+                b1 = __fadd_rn(b1, __fmul_rn(byte_to_float(v, 1), a));
+                b2 = __fadd_rn(b2, __fmul_rn(byte_to_float(v, 2), a));
+                b3 = __fadd_rn(b3, __fmul_rn(byte_to_float(v, 3), a));
+              };
+              const uint8_t* p = p0 - (size_t)xs.sx1 * pitch;
+              if (xs.has_l) step(p + pitch, xs.a_l);
+              const int nfull = xs.sx2 - xs.sx1;
+#pragma unroll 4
+              for (int j = 0; j < nfull; j++) {
+                step(p, xs.a_f);
+                p -= pitch;
+              }
+              if (xs.has_r) step(p, xs.a_r);
+              r0 = b0;
+              r1 = b1;
+              r2 = b2;
+              r3 = b3;
+            }
+            float* dst = s_buf + il0 * 21 + d;
+            if ((unsigned)il0 < (unsigned)rows) dst[0] = r0;
+            if ((unsigned)(il0 + 1) < (unsigned)rows) dst[21] = r1;
+            if ((unsigned)(il0 + 2) < (unsigned)rows) dst[42] = r2;
+            if ((unsigned)(il0 + 3) < (unsigned)rows) dst[63] = r3;
+          }
+        } else
         for (int t = tid; t < rows * 3; t += DESC_THREADS) {
           const int grp = t / rows, il = t - grp * rows;
           const int x = min(max(sx0 + c0 + il, 0), w - 1);

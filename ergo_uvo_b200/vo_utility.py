@@ -163,16 +163,25 @@ class Context:
         return kps[:n.value].copy(), desc[:n.value].copy()
 
     # ------------------------------------------------------------------ VO_utility.h:109-110
-    def match_features(self, keypoints1, keypoints2, descriptors1, descriptors2, with_points=False):
-        """5-arg overload returns matches; with_points=True is the 7-arg overload (also keypoints*_conv)."""
+    def match_features(self, keypoints1, keypoints2, descriptors1, descriptors2, with_points=False, gate=None):
+        """5-arg overload returns matches; with_points=True is the 7-arg overload (also keypoints*_conv).
+        gate=(max_dy, min_disparity, max_disparity) adds the stereo epipolar / disparity gate (not in the reference,
+        off by default; uvo_match_features_gated)."""
         d1 = np.ascontiguousarray(descriptors1, dtype=np.float32)
         d2 = np.ascontiguousarray(descriptors2, dtype=np.float32)
         n1, n2 = d1.shape[0], d2.shape[0]
         dim = d1.shape[1] if d1.ndim == 2 else 64
         out = np.zeros(max(n1, 1), DMATCH_DTYPE)
         n = C.c_int(0)
-        self._ck(self.lib.uvo_match_features(self.h, _p(d1), n1, _p(d2), n2, dim,
-                                             C.c_float(self.params.lowe_ratio), _p(out), C.byref(n)))
+        if gate is not None:
+            k1 = np.ascontiguousarray(keypoints1, dtype=KEYPOINT_DTYPE)
+            k2 = np.ascontiguousarray(keypoints2, dtype=KEYPOINT_DTYPE)
+            self._ck(self.lib.uvo_match_features_gated(
+                self.h, _p(k1), _p(d1), n1, _p(k2), _p(d2), n2, dim, C.c_float(self.params.lowe_ratio),
+                C.c_float(gate[0]), C.c_float(gate[1]), C.c_float(gate[2]), _p(out), C.byref(n)))
+        else:
+            self._ck(self.lib.uvo_match_features(self.h, _p(d1), n1, _p(d2), n2, dim,
+                                                 C.c_float(self.params.lowe_ratio), _p(out), C.byref(n)))
         m = out[:n.value].copy()
         if not with_points:
             return m

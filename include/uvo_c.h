@@ -88,6 +88,15 @@ typedef struct {
   int32_t surf_upright;           /* SURF_UPRIGHT */
   int32_t max_features;           /* capacity of device keypoint buffers (not in the reference: it has no cap;
                                      exceeding it returns UVO_ERR_CAPACITY instead of truncating) */
+  /* Stereo epipolar / disparity gate on the left-right match (visual_odometry.h:558).  NOT in the reference, whose
+   * match_features applies the ratio test only (VO_utility.cpp:515-573): default 0 = OFF, which is what parity with
+   * the reference requires.  When on, a ratio-test survivor (left keypoint q, right keypoint t) is kept iff
+   * |y_q - y_t| <= stereo_max_epipolar_dy and stereo_min_disparity <= x_q - x_t <= stereo_max_disparity
+   * (rectified pair, f32 compares). */
+  int32_t stereo_gate;
+  double stereo_max_epipolar_dy;
+  double stereo_min_disparity;
+  double stereo_max_disparity;
 } uvo_params;
 
 /* ---------------------------------------------------------------------------------------------------- context */
@@ -143,6 +152,13 @@ UVO_API int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray_host, int widt
  * VO_utility.cpp:515-573: BFMatcher(NORM_L2).knnMatch(k=2) + Lowe ratio.  Matches in query order. `dim` = 64. */
 UVO_API int uvo_match_features(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2,
                                int dim, float ratio, uvo_dmatch* matches_host, int* count);
+/* match_features followed by the optional stereo epipolar / disparity gate described at uvo_params.stereo_gate
+ * (north_star; the reference has no such gate, so the node's drop-in path calls uvo_match_features).  kps1 / kps2
+ * are the keypoints of the query (left) / train (right) descriptors. */
+UVO_API int uvo_match_features_gated(uvo_ctx* ctx, const uvo_keypoint* kps1_host, const float* desc1_host, int n1,
+                                     const uvo_keypoint* kps2_host, const float* desc2_host, int n2, int dim,
+                                     float ratio, float max_epipolar_dy, float min_disparity, float max_disparity,
+                                     uvo_dmatch* matches_host, int* count);
 /* raw knnMatch(k=2) rows (2 per query; trainIdx = -1 where n2 < 2) */
 UVO_API int uvo_knn_match2(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2, int dim,
                            uvo_dmatch* knn_host);

@@ -3,6 +3,15 @@ functions.  Test infrastructure: the checker for the device-resident uvo_stereo 
 import numpy as np
 
 
+def stereo_gate(matches, kq, kt, max_dy, min_disp, max_disp):
+    """keep iff |y_q - y_t| <= max_dy and min_disp <= x_q - x_t <= max_disp, all in f32 (uvo_params.stereo_gate)"""
+    q, t = matches["queryIdx"], matches["trainIdx"]
+    dy = np.abs(kq["y"][q].astype(np.float32) - kt["y"][t].astype(np.float32))
+    disp = kq["x"][q].astype(np.float32) - kt["x"][t].astype(np.float32)
+    keep = (dy <= np.float32(max_dy)) & (disp >= np.float32(min_disp)) & (disp <= np.float32(max_disp))
+    return matches[keep]
+
+
 class RefStereoVO:
     def __init__(self, O, seq, params):
         self.O = O
@@ -30,6 +39,8 @@ class RefStereoVO:
         gate = 0
         if len(kL) >= p.min_num_features and len(kR) >= p.min_num_features:
             ms = O.match_features(dL, dR, np.float32(p.lowe_ratio))
+            if getattr(p, "stereo_gate", 0):  # optional epipolar / disparity gate (not in the reference; off by default)
+                ms = stereo_gate(ms, kL, kR, p.stereo_max_epipolar_dy, p.stereo_min_disparity, p.stereo_max_disparity)
             out["m_stereo"] = ms
             out["n_stereo"] = len(ms)
             if len(ms) > p.min_num_features:

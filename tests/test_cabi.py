@@ -45,6 +45,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(U.Camera) == 96
     p = U.default_params(True)
     assert (p.clip_limit, p.lowe_ratio, p.reprojection_tolerance, p.surf_min_hessian) == (8, 0.8, 3.0, 1500)
+    assert p.stereo_gate == 0 and U.default_params(False).stereo_gate == 0  # the reference has no stereo gate
     m = U.default_params(False)
     assert (m.clip_limit, m.lowe_ratio, m.reprojection_tolerance, m.surf_min_hessian, m.min_num_features) == \
         (3, 0.7, 0.1, 50, 20)

@@ -113,3 +113,28 @@ def test_match_small_train_sets(ctx, oracle, nt):
     assert np.array_equal(k["trainIdx"], ko["trainIdx"])
     valid = ko["trainIdx"] >= 0
     assert np.array_equal(k["distance"][valid].view(np.uint32), ko["distance"][valid].view(np.uint32))
+
+
+def test_match_features_gated(ctx, oracle):
+    """uvo_match_features_gated == ratio-test matches filtered by the epipolar / disparity predicate (f32)."""
+    import ergo_uvo_b200 as U
+    from oracle.ref_stereo import stereo_gate
+    rng = np.random.RandomState(5)
+    t = _descs(700, 1)
+    q = _descs(600, 2, dup_from=t)
+    kq = np.zeros(600, U.KEYPOINT_DTYPE)
+    kt = np.zeros(700, U.KEYPOINT_DTYPE)
+    kq["x"], kq["y"] = rng.uniform(0, 640, 600), rng.uniform(0, 480, 600)
+    kt["x"], kt["y"] = rng.uniform(0, 640, 700), rng.uniform(0, 480, 700)
+    ctx.params.lowe_ratio = 0.9
+    full = oracle.match_features(q, t, np.float32(0.9))
+    # make about half of the matched pairs satisfy the gate
+    for m in full[::2]:
+        kt["y"][m["trainIdx"]] = kq["y"][m["queryIdx"]] + np.float32(0.75)
+        kt["x"][m["trainIdx"]] = kq["x"][m["queryIdx"]] - np.float32(20.5)
+    got = ctx.match_features(kq, kt, q, t, gate=(1.0, 2.0, 100.0))
+    want = stereo_gate(full, kq, kt, 1.0, 2.0, 100.0)
+    assert 0 < len(want) < len(full)
+    assert got.tobytes() == want.tobytes()
+    assert ctx.match_features(kq, kt, q, t).tobytes() == full.tobytes()
+    ctx.params.lowe_ratio = 0.8

@@ -45,6 +45,34 @@ def _compare_frame(vo, res, ref):
     assert np.abs(v - vr).max() <= 1e-4 * max(np.abs(vr).max(), 1e-12)
 
 
+def test_stereo_sequence_with_epipolar_disparity_gate(ctx, oracle, small_stereo):
+    """north_star's optional stereo gate (off by default, absent from the reference): the device pipeline with the gate
+    on equals the CPU replay with the same filter applied to the left-right match list, and the gate does remove
+    matches on this sequence."""
+    seq = small_stereo
+    vo, p = _make(ctx, seq, 3000)
+    vo.close()
+    import ergo_uvo_b200 as U
+    p.stereo_gate = 1
+    p.stereo_max_epipolar_dy = 1.5
+    p.stereo_min_disparity = 1.0
+    p.stereo_max_disparity = 400.0
+    camL = U.make_camera(seq.KL, seq.DL, seq.newKL)
+    camR = U.make_camera(seq.KR, seq.DR, seq.newKR)
+    vo = U.StereoVO(ctx, seq.w, seq.h, camL, camR, seq.R_right, seq.t_right, p)
+    ref = RefStereoVO(oracle, seq, p)
+    p0 = U.default_params(True)
+    assert p0.stereo_gate == 0
+    removed = 0
+    for k, (L, R) in enumerate(seq.frames[:3]):
+        res = vo.frame(L, R, 0.1)
+        r = ref.frame(L, R, 0.1)
+        _compare_frame(vo, res, r)
+        ungated = oracle.match_features(r["dL"], r["dR"], np.float32(p.lowe_ratio))
+        removed += len(ungated) - r["n_stereo"]
+    assert removed > 0
+
+
 def test_stereo_sequence_small(ctx, oracle, small_stereo):
     seq = small_stereo
     vo, p = _make(ctx, seq, 3000)
