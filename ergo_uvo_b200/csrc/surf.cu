@@ -175,6 +175,62 @@ __device__ __forceinline__ float det_at(const int* __restrict__ sum, int scols, 
   return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
 
+// ---- octave 0 from a shared-memory tile of the integral image ----------------------------------------------------
+// With the integral tile in shared memory at a compile-time pitch and the layer size a template parameter, every one
+// of the 32 corner reads of a det sample is a single LDS with an immediate offset (the global path spends an LDC, an
+// add and a 64-bit multiply-add per corner).  Same integers, same f32 products, same f64 sums as det_at.
+__host__ __device__ constexpr int cround_c(float v) {  // cvRound for v >= 0 (ties to even), usable in constant expressions
+  const int f = (int)v;
+  const float d = v - (float)f;
+  return d > 0.5f ? f + 1 : (d < 0.5f ? f : f + (f & 1));
+}
+template <int SIZE>
+__host__ __device__ constexpr int haar_off(int k) {  // resizeHaarPattern: cvRound(ratio * k), ratio = (float)SIZE / 9
+  return cround_c((float)SIZE / 9 * (float)k);
+}
+constexpr int T0_MAXM = 13;                                 // margin of the largest middle layer (size 27) at step 1
+constexpr int T0_ROWS = SURF_TILE_H + 2 + 27, T0_COLS = SURF_TILE_W + 2 + 27;  // 45 x 61 integral samples
+
+template <int SIZE>
+__device__ __forceinline__ float det_tile0(const int* __restrict__ T, const SurfLayer& L, int i, int j, int y, int x) {
+  constexpr int M = SIZE / 2;
+  const int si = i - M, sj = j - M;
+  if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
+  const int* o = T + (y + T0_MAXM - M) * T0_COLS + (x + T0_MAXM - M);
+  constexpr int c0 = haar_off<SIZE>(0), c1 = haar_off<SIZE>(1), c2 = haar_off<SIZE>(2), c3 = haar_off<SIZE>(3),
+                c4 = haar_off<SIZE>(4), c5 = haar_off<SIZE>(5), c6 = haar_off<SIZE>(6), c7 = haar_off<SIZE>(7),
+                c8 = haar_off<SIZE>(8), c9 = haar_off<SIZE>(9);
+  auto at = [&](int r, int c) -> unsigned { return (unsigned)o[r * T0_COLS + c]; };
+  double d = 0;
+  {
+    const unsigned A0 = at(c2, c0), A1 = at(c2, c3), A2 = at(c2, c6), A3 = at(c2, c9);
+    const unsigned B0 = at(c7, c0), B1 = at(c7, c3), B2 = at(c7, c6), B3 = at(c7, c9);
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A0 + B1 - B0 - A1), L.box[0].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A1 + B2 - B1 - A2), L.box[1].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A2 + B3 - B2 - A3), L.box[2].w));
+  }
+  const float dx = (float)d;
+  d = 0;
+  {
+    const unsigned A0 = at(c0, c2), A1 = at(c3, c2), A2 = at(c6, c2), A3 = at(c9, c2);
+    const unsigned B0 = at(c0, c7), B1 = at(c3, c7), B2 = at(c6, c7), B3 = at(c9, c7);
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A0 + B1 - A1 - B0), L.box[3].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A1 + B2 - A2 - B1), L.box[4].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A2 + B3 - A3 - B2), L.box[5].w));
+  }
+  const float dy = (float)d;
+  d = 0;
+  {
+    // Dxy boxes {1,1,4,4} {5,1,8,4} {1,5,4,8} {5,5,8,8} as (x1, y1, x2, y2): p0 + p3 - p1 - p2
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(at(c1, c1) + at(c4, c4) - at(c4, c1) - at(c1, c4)), L.box[6].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(at(c1, c5) + at(c4, c8) - at(c4, c5) - at(c1, c8)), L.box[7].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(at(c5, c1) + at(c8, c4) - at(c8, c1) - at(c5, c4)), L.box[8].w));
+    d = __dadd_rn(d, (double)__fmul_rn((float)(int)(at(c5, c5) + at(c8, c8) - at(c8, c5) - at(c5, c8)), L.box[9].w));
+  }
+  const float dxy = (float)d;
+  return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
+}
+
 // interpolateKeypoint: 3x3 Cramer solve in f32 (Matx33f::solve(DECOMP_LU))
 __device__ __forceinline__ bool interpolate_keypoint(const float N[3][9], int step, int ds, float& px, float& py,
                                                      float& psize) {
@@ -258,9 +314,31 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
   const int step = O.step;
   constexpr int PLANE = (TH + 2) * (TW + 2);
   if (threadIdx.x == 0) s_ncand = 0;
-  for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
-    const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
-    sdet[l][y][x] = det_at(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1);
+  if (o == 0) {
+    // octave 0 (three quarters of all samples): stage the integral tile once, then evaluate from shared memory
+    __shared__ int s_tile[T0_ROWS * T0_COLS];
+    const int R0 = ti0 - 1 - T0_MAXM, C0 = tj0 - 1 - T0_MAXM;
+    for (int idx = threadIdx.x; idx < T0_ROWS * T0_COLS; idx += blockDim.x) {
+      const int ry = idx / T0_COLS, rx = idx - ry * T0_COLS;
+      const int gy = R0 + ry, gx = C0 + rx;
+      s_tile[idx] = ((unsigned)gy <= (unsigned)g.h && (unsigned)gx <= (unsigned)g.w)
+                        ? __ldg(im.sum + (size_t)gy * scols + gx) : 0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
+      const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+      const int i = ti0 + y - 1, j = tj0 + x - 1;
+      float v;
+      if (l == 0) v = det_tile0<15>(s_tile, O.layer[1], i, j, y, x);
+      else if (l == 1) v = det_tile0<21>(s_tile, O.layer[2], i, j, y, x);
+      else v = det_tile0<27>(s_tile, O.layer[3], i, j, y, x);
+      sdet[l][y][x] = v;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
+      const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+      sdet[l][y][x] = det_at(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1);
+    }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < nmid * TH * TW; idx += blockDim.x) {
@@ -347,8 +425,27 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
   }
 }
 
+// the compile-time corner offsets of the shared-memory path must be the ones resizeHaarPattern computes at run time
+template <int SIZE>
+static bool tile0_offsets_match(const SurfLayer& L, int ws) {
+  if (L.size != SIZE) return false;
+  const float ratio = (float)SIZE / 9;
+  for (int k = 0; k < 10; k++)
+    if (cv_roundf_h(ratio * k) != haar_off<SIZE>(k)) return false;
+  return L.box[6].p0 == haar_off<SIZE>(1) * ws + haar_off<SIZE>(1) && L.box[9].p3 == haar_off<SIZE>(8) * ws + haar_off<SIZE>(8) &&
+         L.xx_col[3] == haar_off<SIZE>(9) && L.yy_row[1] == haar_off<SIZE>(3) * ws;
+}
+
 void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity) {
   upload_tables(c);
+  {
+    const SurfOctave& O = g.oct[0];
+    const int ws = g.w + 1;
+    bool ok = O.step == 1 && tile0_offsets_match<15>(O.layer[1], ws);
+    if (g.n_layers >= 2) ok = ok && tile0_offsets_match<21>(O.layer[2], ws);
+    if (g.n_layers >= 3) ok = ok && tile0_offsets_match<27>(O.layer[3], ws);
+    if (!ok) throw InvalidArg{"SURF: octave-0 tile geometry mismatch (internal)", UVO_ERR_UNSUPPORTED};
+  }
   for (int i = 0; i < b.n_img; i++) {
     UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
     UVO_CUDA(cudaMemsetAsync(b.im[i].rank, 0, (size_t)capacity * sizeof(int), c.stream));
