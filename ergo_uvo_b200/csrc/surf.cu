@@ -448,7 +448,6 @@ void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capac
   }
   for (int i = 0; i < b.n_img; i++) {
     UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
-    UVO_CUDA(cudaMemsetAsync(b.im[i].rank, 0, (size_t)capacity * sizeof(int), c.stream));
   }
   UVO_KERNEL(c, "k_surf_detect");
   k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(g, b, capacity);
@@ -512,8 +511,100 @@ __global__ void __launch_bounds__(256) k_surf_scatter(const __grid_constant__ Su
   if (i < n) im.kps[im.rank[i]] = im.raw[i];
 }
 
+// Block sort (capacity <= SORT_BLOCK_MAX): one 1024-thread block per image sorts (response, raw index) pairs with a
+// bitonic network in shared memory -- N log^2 N compare-exchanges on one SM instead of the N^2 compares of the rank
+// sort on all of them -- then repairs runs of equal responses with the full KeypointGreater comparator (rare; same
+// tie rule as the rank sort: identical keys keep raw-index order) and writes the keypoints out in order.
+constexpr int SORT_BLOCK_MAX = 16384;
+
+__device__ __forceinline__ bool kp_precedes(const uvo_keypoint& a, const uvo_keypoint& b) {
+  return kp_precedes(a.response, a.size, a.octave, a.y, a.x, b.response, b.size, b.octave, b.y, b.x);
+}
+
+__global__ void __launch_bounds__(1024) k_surf_sort_block(const __grid_constant__ SurfBatch b, int capacity) {
+  extern __shared__ unsigned long long s_key[];  // (monotone response bits << 32) | ~raw index; 0 = padding
+  const SurfImage& im = b.im[blockIdx.x];
+  const int n = min(im.counters[0], capacity);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    im.counters[1] = n;
+    im.counters[2] = 0;  // k_surf_describe's work-queue head
+  }
+  int P = 2;
+  while (P < n) P <<= 1;
+  for (int i = tid; i < P; i += 1024) {
+    unsigned long long key = 0ull;
+    if (i < n) {
+      const unsigned r = __float_as_uint(im.raw[i].response);
+      const unsigned mono = (r & 0x80000000u) ? ~r : (r | 0x80000000u);
+      key = ((unsigned long long)mono << 32) | (unsigned)(~(unsigned)i);
+    }
+    s_key[i] = key;
+  }
+  __syncthreads();
+  // descending bitonic sort
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (P >> 1); t += 1024) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+        const unsigned long long a = s_key[lo], c = s_key[hi];
+        const bool desc = (lo & k) == 0;
+        if ((a < c) == desc) {
+          s_key[lo] = c;
+          s_key[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // repair runs of equal response (insertion sort by the full comparator; the run head does the work)
+  for (int p0 = tid; p0 < n; p0 += 1024) {
+    const unsigned r = (unsigned)(s_key[p0] >> 32);
+    const bool head = (p0 == 0 || (unsigned)(s_key[p0 - 1] >> 32) != r) && p0 + 1 < n &&
+                      (unsigned)(s_key[p0 + 1] >> 32) == r;
+    if (!head) continue;
+    int q = p0 + 1;
+    while (q < n && (unsigned)(s_key[q] >> 32) == r) q++;
+    for (int a = p0 + 1; a < q; a++) {
+      const unsigned long long ka = s_key[a];
+      const uvo_keypoint A = im.raw[~(unsigned)ka];
+      int c = a - 1;
+      while (c >= p0 && kp_precedes(A, im.raw[~(unsigned)s_key[c]])) {
+        s_key[c + 1] = s_key[c];
+        c--;
+      }
+      s_key[c + 1] = ka;
+    }
+  }
+  __syncthreads();
+  // ordered write-out, word-wise (a keypoint is 7 words)
+  const int* src = (const int*)im.raw;
+  int* dst = (int*)im.kps;
+  for (int w = tid; w < n * 7; w += 1024) {
+    const int p = w / 7, f = w - p * 7;
+    dst[w] = src[(size_t)(~(unsigned)s_key[p]) * 7 + f];
+  }
+}
+
 void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity) {
+  if (capacity <= SORT_BLOCK_MAX) {
+    int P = 2;
+    while (P < capacity) P <<= 1;
+    const size_t smem = (size_t)P * sizeof(unsigned long long);
+    static bool attr_set[64] = {};
+    if (c.device >= 64 || !attr_set[c.device]) {
+      UVO_CUDA(cudaFuncSetAttribute(k_surf_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    SORT_BLOCK_MAX * (int)sizeof(unsigned long long)));
+      if (c.device < 64) attr_set[c.device] = true;
+    }
+    UVO_KERNEL(c, "k_surf_sort_block");
+    k_surf_sort_block<<<b.n_img, 1024, smem, c.stream>>>(b, capacity);
+    UVO_LAUNCH_CHECK(c);
+    return;
+  }
   const int tiles = div_up(capacity, 256);
+  for (int i = 0; i < b.n_img; i++)
+    UVO_CUDA(cudaMemsetAsync(b.im[i].rank, 0, (size_t)capacity * sizeof(int), c.stream));
   UVO_KERNEL(c, "k_surf_rank");
   k_surf_rank<<<dim3(tiles, tiles, b.n_img), 256, 0, c.stream>>>(b, capacity);
   UVO_LAUNCH_CHECK(c);
@@ -644,19 +735,24 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
   __shared__ int s_next;
   // dynamic queue (counters[2], zeroed with the other counters before detection): window areas span 21^2 .. 576^2
   // pixels, so a static assignment leaves most blocks waiting for the one that drew the largest windows
+  if (tid == 0) s_next = atomicAdd(&im.counters[2], 1);
+  __syncthreads();
   for (;;) {
-    if (tid == 0) s_next = atomicAdd(&im.counters[2], 1);
-    __syncthreads();
     const int k = s_next;
     __syncthreads();
     if (k >= n) break;
+    // the next queue slot is requested now and published at the end of this keypoint, so the atomic's round trip
+    // overlaps the work instead of heading every keypoint
+    int k_next = 0;
+    if (tid == 0) k_next = atomicAdd(&im.counters[2], 1);
+    do {
     const uvo_keypoint kp = im.kps[k];
     const float size = kp.size, cx = kp.x, cy = kp.y;
     const float s = __fdiv_rn(__fmul_rn(size, 1.2f), 9.0f);
     const int gws = 2 * __float2int_rn(__fmul_rn(2.f, s));
     if (srows < gws || scols < gws) {  // gradient wavelet larger than the image: mark for deletion
       if (tid == 0) im.kps[k].size = -1.f;
-      continue;
+      break;
     }
     float dir = 270.f;
     if (!upright) {
@@ -713,8 +809,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
       const int nangle = s_nangle;
       if (nangle == 0) {
         if (tid == 0) im.kps[k].size = -1.f;
-        __syncthreads();
-        continue;
+        break;
       }
       // 72 window positions; thread t evaluates window i = 5t sequentially over samples (CPU order), then the
       // first-best-wins arg max is taken in window order.
@@ -985,6 +1080,8 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
     }
     __syncthreads();
     if (tid < 64) im.desc[(size_t)k * 64 + tid] = __fmul_rn(s_vec[tid], s_scale);
+    } while (0);
+    if (tid == 0) s_next = k_next;
     __syncthreads();
   }
 }
