@@ -245,7 +245,7 @@ def run_gpu(args):
                   torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][1]).pin_memory()) for i in range(RING)]
     torch.cuda.synchronize()
     dt_frame = 0.1
-    inflight = 4
+    inflight = args.inflight
 
     def barrier():
         if world > 1:
@@ -446,6 +446,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--threshold", type=int, default=0, help="SURF min_hessian (0: bisect for ~4096 keypoints)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--inflight", type=int, default=8, help="frames kept in flight per sequence (<= the library's lanes)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:

@@ -177,8 +177,8 @@ struct Lane {
 };
 
 struct uvo_stereo {
-  static constexpr int N_LANES = 4;
-  static constexpr int RING = 8;
+  static constexpr int N_LANES = 8;
+  static constexpr int RING = 16;
   uvo_ctx* ctx = nullptr;
   int w = 0, h = 0, cap = 0;
   uvo_camera cam[2];
