@@ -18,6 +18,7 @@ struct FrontEnd {
   DevBuf<int32_t> sum[2];
   DevBuf<uvo_keypoint> raw[2], kps[2];
   DevBuf<float> desc[2];
+  DevBuf<uint8_t> patch[2];
   DevBuf<int> counters;  // 4 ints per image
   DevBuf<int> rank[2];
   DevBuf<unsigned int> hist;
@@ -43,6 +44,7 @@ struct FrontEnd {
       // rows past the live count are read (and ignored) by the matcher's TMA tiles: keep them finite
       if (fresh) UVO_CUDA(cudaMemset(desc[i].get(), 0, (size_t)capacity * 64 * sizeof(float)));
       rank[i].ensure(capacity);
+      patch[i].ensure((size_t)capacity * 448);
     }
     counters.ensure(8);
     hist.ensure(2 * 64 * 256);
@@ -60,6 +62,7 @@ struct FrontEnd {
       im.raw = raw[first + i].get();
       im.kps = kps[first + i].get();
       im.desc = desc[first + i].get();
+      im.patch = patch[first + i].get();
       im.rank = rank[first + i].get();
       im.counters = counters.get() + 4 * (first + i);
     }

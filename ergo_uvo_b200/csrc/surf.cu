@@ -713,28 +713,32 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 #endif
 constexpr int DESC_THREADS = UVO_DESC_THREADS;
 constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows are streamed in chunks
+constexpr int PATCH_STRIDE = 448;   // bytes per keypoint in SurfImage::patch (441 used)
 
-// One block per keypoint (grid-stride).  Shared: 21x21 patch, 2x400 gradients, 64-vector.
-__global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_constant__ SurfGeom g,
-                                                                const __grid_constant__ SurfBatch b,
-                                                                int upright) {
-  __shared__ int s_patch[21][21];
+// K7 runs as two kernels.  k_surf_patch (one block per keypoint, dynamic queue) does the wide part: (orientation,)
+// window extraction and the INTER_AREA resize to the 21x21 u8 patch, which it writes to global memory.
+// k_surf_vector (one warp per keypoint) does the narrow part: Haar gradients, 4x4x4 sums, L2 normalisation.  Keeping
+// the narrow phases out of the block-per-keypoint kernel is what lets its 256 threads stay busy.
+#ifndef UVO_DESC_MINB
+#define UVO_DESC_MINB 4
+#endif
+__global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(const __grid_constant__ SurfGeom g,
+                                                             const __grid_constant__ SurfBatch b, int upright) {
+  __shared__ int s_patch[441];
   __shared__ AreaSpan s_span[21];
   __shared__ float s_buf[DESC_BUF_ROWS * 21];
   __shared__ float s_acc[441];
-  __shared__ float s_dx[400], s_dy[400];
-  __shared__ float s_vec[64];
-  __shared__ float s_scale;
   __shared__ float s_X[128], s_Y[128], s_ang[128];
   __shared__ int s_nangle;
   __shared__ float s_dir;
+  __shared__ int s_next;
+  __shared__ int s_iscale, s_area_fast;
   const SurfImage& im = b.im[blockIdx.y];
   const int n = im.counters[1];
   const int w = g.w, h = g.h, srows = h + 1, scols = w + 1;
   const int tid = threadIdx.x;
-  __shared__ int s_next;
-  // dynamic queue (counters[2], zeroed with the other counters before detection): window areas span 21^2 .. 576^2
-  // pixels, so a static assignment leaves most blocks waiting for the one that drew the largest windows
+  // dynamic queue (counters[2], zeroed by the sort kernel): window areas span 21^2 .. 576^2 pixels, so a static
+  // assignment leaves most blocks waiting for the one that drew the largest windows
   if (tid == 0) s_next = atomicAdd(&im.counters[2], 1);
   __syncthreads();
   for (;;) {
@@ -843,6 +847,8 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
       dir = s_dir;
     }
 
+
+    if (tid == 0) im.kps[k].angle = dir;
     // ---- window geometry ----
     const int win_size = (int)__fmul_rn(21.f, s);
     WinSampler ws;
@@ -866,137 +872,124 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
     }
 
     // ---- resize(win -> 21x21, INTER_AREA) ----
-    const double inv_scale = (double)21 / win_size;
-    const double scale = 1. / inv_scale;
-    const int iscale = __double2int_rn(scale);
-    const bool area_fast = fabs(scale - iscale) < DBL_EPSILON;
-    if (tid < 21) s_span[tid] = area_span(tid, win_size, scale);  // same table for rows and columns (square window)
+    // scale / iscale / is_area_fast exactly as cv::resize derives them (fp64); only 21 threads need the divisions
+    if (tid < 21) {
+      const double inv_scale = (double)21 / win_size;
+      const double scale = 1. / inv_scale;
+      s_span[tid] = area_span(tid, win_size, scale);  // same table for rows and columns (square window)
+      if (tid == 0) {
+        const int isc = __double2int_rn(scale);
+        s_iscale = isc;
+        s_area_fast = fabs(scale - isc) < DBL_EPSILON;
+      }
+    }
     __syncthreads();
+    const int iscale = s_iscale;
+    const bool area_fast = s_area_fast != 0;
     if (win_size == 21) {
-      for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t / 21][t % 21] = ws.at(t / 21, t % 21);
+      for (int t = tid; t < 441; t += DESC_THREADS) s_patch[t] = ws.at(t / 21, t % 21);
     } else if (upright) {
-      // Separable form of OpenCV's ResizeArea_Invoker in exactly its arithmetic order.  Pass 1: one work item per
-      // (window row i, group of 7 destination columns); the item walks its 7 cells along j -- image rows -- in
-      // increasing j, so every window pixel is read once (a pixel shared by two partial cells twice), consecutive
-      // threads read consecutive image x (coalesced) and the f32 sums are accumulated in the CPU order.  Pass 2
-      // accumulates beta * buf over the window rows of each destination row, streaming over chunks of
-      // DESC_BUF_ROWS rows with the 441 running sums kept in shared memory (0 + v == v exactly, so starting from
-      // zero equals OpenCV's "first row assigns").
+      // Separable form of OpenCV's ResizeArea_Invoker in exactly its arithmetic order (window row i <-> image x,
+      // window column j <-> image y descending).  Pass 1: one work item per (aligned group of 4 image columns = 4
+      // window rows, destination cell d); the item walks the cell's pixels down image y with one 32-bit load per
+      // step and keeps four independent f32 chains, each accumulated in the CPU order.  Pass 2 accumulates
+      // beta * buf over the window rows of each destination row, streaming over chunks of DESC_BUF_ROWS rows with
+      // the 441 running sums kept in shared memory (0 + v == v exactly, so starting from zero equals OpenCV's
+      // "first row assigns").  Gray images are pitch-aligned to 16 bytes (FrontEnd), so word loads are aligned;
+      // columns / rows outside the image replicate the border exactly like the CPU's clamped window extraction.
       const uint8_t* __restrict__ img = im.img;
-      const size_t pitch = im.pitch;
+      const int pitch = (int)im.pitch;
       const int sx0 = ws.start_x, sy0 = ws.start_y;
       const bool interior_y = (sy0 - (win_size - 1) >= 0) && (sy0 <= h - 1);
-      const bool fast_words = interior_y && sx0 >= 0 && sx0 + win_size <= w && (pitch & 3) == 0 &&
-                              ((uintptr_t)img & 3) == 0;
       for (int t = tid; t < 441; t += DESC_THREADS) s_acc[t] = 0.f;
       for (int c0 = 0; c0 < win_size; c0 += DESC_BUF_ROWS) {
         const int rows = min(win_size - c0, DESC_BUF_ROWS);
         __syncthreads();  // s_acc zeroed / previous chunk's pass 2 done with s_buf
-        if (fast_words) {
-          // Interior window, 4-byte aligned image rows: one work item per (aligned group of 4 image columns = 4 window
-          // rows, destination cell d).  The item walks the cell's pixels down image y with one 32-bit load per step
-          // and keeps four independent f32 chains (one per window row), each in OpenCV's order.
-          const int x_first = sx0 + c0, xa = x_first & ~3;
-          const int ncg = ((x_first + rows - 1) >> 2) - (xa >> 2) + 1;
-          for (int t = tid; t < ncg * 21; t += DESC_THREADS) {
-            const int d = t / ncg, m = t - d * ncg;
-            const int xw = xa + 4 * m, il0 = xw - x_first;
-            const uint8_t* p0 = img + (size_t)sy0 * pitch + xw;  // pixel row j lives at p0 - j * pitch
-            float r0, r1, r2, r3;
-            if (area_fast) {
-              const int j0 = d * iscale;
-              const uint8_t* p = p0 - (size_t)j0 * pitch;
-              int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const int x_first = sx0 + c0, xa = x_first & ~3;
+        const int ncg = ((x_first + rows - 1) >> 2) - (xa >> 2) + 1;
+        const unsigned inv_ncg = ncg > 1 ? 0xffffffffu / (unsigned)ncg + 1u : 0u;  // ceil(2^32 / ncg)
+        for (int t = tid; t < ncg * 21; t += DESC_THREADS) {
+          const int d = ncg > 1 ? (int)__umulhi((unsigned)t, inv_ncg) : t, m = t - d * ncg;  // t / ncg (t < 2^24)
+          const int xw = xa + 4 * m, il0 = xw - x_first;
+          const bool x_in = xw >= 0 && xw + 3 <= w - 1;
+          // pixels of window column j for this item's four window rows, as one little-endian word
+          auto load4 = [&](int j) -> unsigned {
+            int y = sy0 - j;
+            if (!interior_y) y = min(max(y, 0), h - 1);
+            const uint8_t* row = img + (size_t)y * pitch;
+            if (x_in) return __ldg((const unsigned*)(row + xw));
+            unsigned v = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) v |= (unsigned)__ldg(row + min(max(xw + q, 0), w - 1)) << (8 * q);
+            return v;
+          };
+          float r0, r1, r2, r3;
+          if (area_fast) {
+            const int j0 = d * iscale;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll 4
-              for (int j = 0; j < iscale; j++) {
-                const unsigned v = __ldg((const unsigned*)p);
-                p -= pitch;
-                a0 += v & 0xffu;
-                a1 += (v >> 8) & 0xffu;
-                a2 += (v >> 16) & 0xffu;
-                a3 += v >> 24;
-              }
-              r0 = __int_as_float(a0);
-              r1 = __int_as_float(a1);
-              r2 = __int_as_float(a2);
-              r3 = __int_as_float(a3);
-            } else {
-              const AreaSpan xs = s_span[d];
-              float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-              auto step = [&](const uint8_t* q, float a) {
-                const unsigned v = __ldg((const unsigned*)q);
-                b0 = __fadd_rn(b0, __fmul_rn(byte_to_float(v, 0), a));
-                b1 = __fadd_rn(b1, __fmul_rn(byte_to_float(v, 1), a));
-                b2 = __fadd_rn(b2, __fmul_rn(byte_to_float(v, 2), a));
-                b3 = __fadd_rn(b3, __fmul_rn(byte_to_float(v, 3), a));
-              };
-              const uint8_t* p = p0 - (size_t)xs.sx1 * pitch;
-              if (xs.has_l) step(p + pitch, xs.a_l);
+            for (int j = 0; j < iscale; j++) {
+              const unsigned v = load4(j0 + j);
+              a0 += v & 0xffu;
+              a1 += (v >> 8) & 0xffu;
+              a2 += (v >> 16) & 0xffu;
+              a3 += v >> 24;
+            }
+            r0 = __int_as_float(a0);
+            r1 = __int_as_float(a1);
+            r2 = __int_as_float(a2);
+            r3 = __int_as_float(a3);
+          } else {
+            const AreaSpan xs = s_span[d];
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            auto step = [&](unsigned v, float a) {
+              b0 = __fadd_rn(b0, __fmul_rn(byte_to_float(v, 0), a));
+              b1 = __fadd_rn(b1, __fmul_rn(byte_to_float(v, 1), a));
+              b2 = __fadd_rn(b2, __fmul_rn(byte_to_float(v, 2), a));
+              b3 = __fadd_rn(b3, __fmul_rn(byte_to_float(v, 3), a));
+            };
+            if (xs.has_l) step(load4(xs.sx1 - 1), xs.a_l);
+            if (interior_y && x_in) {
+              const uint8_t* p = img + (size_t)(sy0 - xs.sx1) * pitch + xw;
               const int nfull = xs.sx2 - xs.sx1;
 #pragma unroll 4
               for (int j = 0; j < nfull; j++) {
-                step(p, xs.a_f);
+                step(__ldg((const unsigned*)p), xs.a_f);
                 p -= pitch;
               }
-              if (xs.has_r) step(p, xs.a_r);
-              r0 = b0;
-              r1 = b1;
-              r2 = b2;
-              r3 = b3;
+            } else {
+              for (int j = xs.sx1; j < xs.sx2; j++) step(load4(j), xs.a_f);
             }
-            float* dst = s_buf + il0 * 21 + d;
-            if ((unsigned)il0 < (unsigned)rows) dst[0] = r0;
-            if ((unsigned)(il0 + 1) < (unsigned)rows) dst[21] = r1;
-            if ((unsigned)(il0 + 2) < (unsigned)rows) dst[42] = r2;
-            if ((unsigned)(il0 + 3) < (unsigned)rows) dst[63] = r3;
+            if (xs.has_r) step(load4(xs.sx2), xs.a_r);
+            r0 = b0;
+            r1 = b1;
+            r2 = b2;
+            r3 = b3;
           }
-        } else
-        for (int t = tid; t < rows * 3; t += DESC_THREADS) {
-          const int grp = t / rows, il = t - grp * rows;
-          const int x = min(max(sx0 + c0 + il, 0), w - 1);
-          const uint8_t* col = img + x;
-          auto pix = [&](int j) -> int {
-            const int y = interior_y ? (sy0 - j) : min(max(sy0 - j, 0), h - 1);
-            return __ldg(col + (size_t)y * pitch);
-          };
-          float* dst = s_buf + il * 21 + grp * 7;
-          if (area_fast) {
-#pragma unroll 1
-            for (int d = 0; d < 7; d++) {
-              const int j0 = (grp * 7 + d) * iscale;
-              int acc = 0;
-              for (int j = j0; j < j0 + iscale; j++) acc += pix(j);
-              dst[d] = __int_as_float(acc);
-            }
-          } else {
-#pragma unroll 1
-            for (int d = 0; d < 7; d++) {
-              const AreaSpan xs = s_span[grp * 7 + d];
-              float buf = 0.f;
-              if (xs.has_l) buf = __fadd_rn(buf, __fmul_rn((float)pix(xs.sx1 - 1), xs.a_l));
-              for (int j = xs.sx1; j < xs.sx2; j++) buf = __fadd_rn(buf, __fmul_rn((float)pix(j), xs.a_f));
-              if (xs.has_r) buf = __fadd_rn(buf, __fmul_rn((float)pix(xs.sx2), xs.a_r));
-              dst[d] = buf;
-            }
-          }
+          float* dst = s_buf + il0 * 21 + d;
+          if ((unsigned)il0 < (unsigned)rows) dst[0] = r0;
+          if ((unsigned)(il0 + 1) < (unsigned)rows) dst[21] = r1;
+          if ((unsigned)(il0 + 2) < (unsigned)rows) dst[42] = r2;
+          if ((unsigned)(il0 + 3) < (unsigned)rows) dst[63] = r3;
         }
         __syncthreads();
         for (int t = tid; t < 441; t += DESC_THREADS) {
           const int dy = t / 21, dx = t - dy * 21;
+          const float* col = s_buf + dx - c0 * 21;  // col[i * 21] = buf of window row i
           if (area_fast) {
             const int lo = max(dy * iscale, c0), hi = min(dy * iscale + iscale, c0 + rows);
             int acc = __float_as_int(s_acc[t]);
-            for (int i = lo; i < hi; i++) acc += __float_as_int(s_buf[(i - c0) * 21 + dx]);
+            for (int i = lo; i < hi; i++) acc += __float_as_int(col[i * 21]);
             s_acc[t] = __int_as_float(acc);
           } else {
             const AreaSpan ys = s_span[dy];
-            const int first = ys.has_l ? ys.sx1 - 1 : ys.sx1, last = ys.has_r ? ys.sx2 + 1 : ys.sx2;  // [first, last)
-            const int lo = max(first, c0), hi = min(last, c0 + rows);
+            const int c1 = c0 + rows;
             float sum = s_acc[t];
-            for (int i = lo; i < hi; i++) {
-              const float beta = (i < ys.sx1) ? ys.a_l : (i < ys.sx2 ? ys.a_f : ys.a_r);
-              sum = __fadd_rn(sum, __fmul_rn(beta, s_buf[(i - c0) * 21 + dx]));
-            }
+            if (ys.has_l && ys.sx1 - 1 >= c0 && ys.sx1 - 1 < c1)
+              sum = __fadd_rn(sum, __fmul_rn(ys.a_l, col[(ys.sx1 - 1) * 21]));
+            const int lo = max(ys.sx1, c0), hi = min(ys.sx2, c1);
+            for (int i = lo; i < hi; i++) sum = __fadd_rn(sum, __fmul_rn(ys.a_f, col[i * 21]));
+            if (ys.has_r && ys.sx2 >= c0 && ys.sx2 < c1) sum = __fadd_rn(sum, __fmul_rn(ys.a_r, col[ys.sx2 * 21]));
             s_acc[t] = sum;
           }
         }
@@ -1011,7 +1004,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
         } else {
           outv = min(max(__float2int_rn(s_acc[t]), 0), 255);
         }
-        s_patch[t / 21][t % 21] = outv;
+        s_patch[t] = outv;
       }
     } else {
       for (int t = tid; t < 441; t += DESC_THREADS) {
@@ -1047,50 +1040,96 @@ __global__ void __launch_bounds__(DESC_THREADS) k_surf_describe(const __grid_con
           if (ys.has_r) row(ys.sx2, ys.a_r);
           out = min(max(__float2int_rn(sum), 0), 255);
         }
-        s_patch[py][px] = out;
+        s_patch[py * 21 + px] = out;
       }
     }
     __syncthreads();
-    // ---- Haar gradients with Gaussian weights ----
-    for (int t = tid; t < 400; t += DESC_THREADS) {
-      const int i = t / 20, j = t - i * 20;
-      const float dw = c_DW[t];
-      s_dx[t] = __fmul_rn((float)(s_patch[i][j + 1] - s_patch[i][j] + s_patch[i + 1][j + 1] - s_patch[i + 1][j]), dw);
-      s_dy[t] = __fmul_rn((float)(s_patch[i + 1][j] - s_patch[i][j] + s_patch[i + 1][j + 1] - s_patch[i][j + 1]), dw);
+    {
+      uint8_t* dstp = im.patch + (size_t)k * PATCH_STRIDE;
+      for (int t = tid; t < 441; t += DESC_THREADS) dstp[t] = (uint8_t)s_patch[t];
     }
-    __syncthreads();
-    // ---- 4x4 cells x (sum dx, sum dy, sum |dx|, sum |dy|), y-major over each 5x5 cell ----
-    if (tid < 64) {
-      const int cell = tid >> 2, comp = tid & 3, ci = cell >> 2, cj = cell & 3;
-      float v = 0.f;
-      for (int y = ci * 5; y < ci * 5 + 5; y++)
-        for (int x = cj * 5; x < cj * 5 + 5; x++) {
-          const float tx = s_dx[y * 20 + x], ty = s_dy[y * 20 + x];
-          const float add = comp == 0 ? tx : comp == 1 ? ty : comp == 2 ? fabsf(tx) : fabsf(ty);
-          v = __fadd_rn(v, add);
-        }
-      s_vec[tid] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double sq = 0;
-      for (int q = 0; q < 64; q++) sq = __dadd_rn(sq, (double)__fmul_rn(s_vec[q], s_vec[q]));
-      s_scale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
-      im.kps[k].angle = dir;
-    }
-    __syncthreads();
-    if (tid < 64) im.desc[(size_t)k * 64 + tid] = __fmul_rn(s_vec[tid], s_scale);
     } while (0);
     if (tid == 0) s_next = k_next;
     __syncthreads();
   }
 }
 
+// Descriptor vector from the 21x21 patch: one warp per keypoint.
+constexpr int VEC_WARPS = 8;
+__global__ void __launch_bounds__(VEC_WARPS * 32) k_surf_vector(const __grid_constant__ SurfBatch b) {
+  __shared__ __align__(16) uint8_t s_p[VEC_WARPS][PATCH_STRIDE];
+  __shared__ __align__(16) float s_dx[VEC_WARPS][400];
+  __shared__ float s_dy[VEC_WARPS][400];
+  __shared__ float s_dw[400];  // the Gaussian table: lanes index it divergently, which constant memory serialises
+  const SurfImage& im = b.im[blockIdx.y];
+  const int n = im.counters[1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < 400; t += VEC_WARPS * 32) s_dw[t] = c_DW[t];
+  __syncthreads();
+  uint8_t* P = s_p[wid];
+  float* DX = s_dx[wid];
+  float* DY = s_dy[wid];
+  for (int k = blockIdx.x * VEC_WARPS + wid; k < n; k += gridDim.x * VEC_WARPS) {
+    if (!(im.kps[k].size > 0.f)) continue;  // marked for deletion by k_surf_patch (warp-uniform)
+    const unsigned* src = (const unsigned*)(im.patch + (size_t)k * PATCH_STRIDE);
+    for (int t = lane; t < PATCH_STRIDE / 4; t += 32) ((unsigned*)P)[t] = __ldg(src + t);
+    __syncwarp();
+    // ---- Haar gradients with Gaussian weights ----
+    for (int t = lane; t < 400; t += 32) {
+      const int i = t / 20, j = t - i * 20;
+      const int p00 = P[i * 21 + j], p01 = P[i * 21 + j + 1], p10 = P[i * 21 + 21 + j], p11 = P[i * 21 + 21 + j + 1];
+      const float dw = s_dw[t];
+      DX[t] = __fmul_rn((float)(p01 - p00 + p11 - p10), dw);
+      DY[t] = __fmul_rn((float)(p10 - p00 + p11 - p01), dw);
+    }
+    __syncwarp();
+    // ---- 4x4 cells x (sum dx, sum dy, sum |dx|, sum |dy|), y-major over each 5x5 cell ----
+    float v2[2];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int q = lane + 32 * half;
+      const int cell = q >> 2, comp = q & 3, ci = cell >> 2, cj = cell & 3;
+      const float* srcv = ((comp & 1) ? DY : DX) + ci * 100 + cj * 5;
+      const bool use_abs = comp >= 2;
+      float e[25];
+#pragma unroll
+      for (int y = 0; y < 5; y++)
+#pragma unroll
+        for (int x = 0; x < 5; x++) e[y * 5 + x] = srcv[y * 20 + x];
+      float v = 0.f;
+#pragma unroll
+      for (int q2 = 0; q2 < 25; q2++) v = __fadd_rn(v, use_abs ? fabsf(e[q2]) : e[q2]);
+      v2[half] = v;
+    }
+    __syncwarp();  // every lane is done reading DX / DY: DX is reused for the fp64 squares
+    double* SQ = (double*)DX;
+    SQ[lane] = (double)__fmul_rn(v2[0], v2[0]);
+    SQ[lane + 32] = (double)__fmul_rn(v2[1], v2[1]);
+    __syncwarp();
+    // ---- L2 normalisation: the squares are summed sequentially in fp64, as the CPU does ----
+    float scale = 0.f;
+    if (lane == 0) {
+      double sq = 0;
+#pragma unroll
+      for (int q = 0; q < 64; q++) sq = __dadd_rn(sq, SQ[q]);
+      scale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
+    }
+    scale = __shfl_sync(0xffffffffu, scale, 0);
+    im.desc[(size_t)k * 64 + lane] = __fmul_rn(v2[0], scale);
+    im.desc[(size_t)k * 64 + 32 + lane] = __fmul_rn(v2[1], scale);
+    __syncwarp();
+  }
+}
+
 void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright) {
   upload_tables(c);
   const int blocks = std::min(capacity, 8 * c.sm_count);
-  UVO_KERNEL(c, "k_surf_describe");
-  k_surf_describe<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright);
+  UVO_KERNEL(c, "k_surf_patch");
+  k_surf_patch<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright);
+  UVO_LAUNCH_CHECK(c);
+  const int vblocks = std::min(div_up(capacity, VEC_WARPS), 4 * c.sm_count);
+  UVO_KERNEL(c, "k_surf_vector");
+  k_surf_vector<<<dim3(vblocks, b.n_img), VEC_WARPS * 32, 0, c.stream>>>(b);
   UVO_LAUNCH_CHECK(c);
 }
 

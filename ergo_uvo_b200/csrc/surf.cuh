@@ -46,6 +46,7 @@ struct SurfImage {
   uvo_keypoint* raw = nullptr;    // unordered detections
   uvo_keypoint* kps = nullptr;    // sorted (OpenCV order), compacted
   float* desc = nullptr;          // capacity x 64
+  uint8_t* patch = nullptr;       // capacity x 448: the 21x21 u8 descriptor patches (k_surf_patch -> k_surf_vector)
   int* rank = nullptr;            // capacity ints, zeroed per frame (rank sort accumulator)
   int* counters = nullptr;        // [0] raw count (may exceed capacity => overflow), [1] final count, [2..3] spare
 };
