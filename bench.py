@@ -158,12 +158,14 @@ def cpu_frames(seq, thr, n_frames, params=None):
     p = params or default_params_cpu(thr)
     ref = RefStereoVO(O, seq, p)
     ref.frame(*seq.frames[0], 0.1)  # initialisation frame
+    ref.stage_s = {k: 0.0 for k in ref.stage_s}
     t0 = time.perf_counter()
     valid = 0
     for k in range(1, n_frames + 1):
         r = ref.frame(*seq.frames[pingpong(k, len(seq.frames))], 0.1)
         valid += r["valid"]
     dt = time.perf_counter() - t0
+    cpu_frames.last_stage_ms = {k: 1e3 * v / n_frames for k, v in ref.stage_s.items()}
     return dt / n_frames, valid
 
 
@@ -200,7 +202,8 @@ def run_reference(args):
                    "surf_min_hessian": thr},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} consecutive stereo frames of the same synthetic sequence through the "
-                                   "oracle port of the OpenCV CPU path (SURF restated, not OpenCV)"},
+                                   "oracle port of the OpenCV CPU path (SURF restated, not OpenCV)",
+                         "stage_ms": getattr(cpu_frames, "last_stage_ms", None)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "valid_frames": valid,
     }
@@ -359,9 +362,15 @@ def run_gpu(args):
         algo = {
             "k_gray_undistort": ("hbm", 4.0 * P), "k_clahe_hist": ("hbm", 1.0 * P), "k_clahe_apply": ("hbm", 2.0 * P),
             "k_integral_rows": ("hbm", 5.0 * P), "k_integral_cols": ("hbm", 8.0 * P),
-            "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_describe": ("hbm", 2 * n_kp * (40 * 40 + 256)),
+            "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_patch": ("hbm", 2 * n_kp * (40 * 40 + 256)),
             "k_knn_tc": ("tensor", 2.0 * n_kp * n_kp * 64),
         }
+        # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this same command
+        # (profiles/ncu_traffic.json, written by tools/ncu_summary.py); null when the kernel was not captured
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
         roof = None
         top_overall = max(kern.items(), key=lambda kv: kv[1]["ms_per_frame"])[0] if kern else None
         cands = {k: v for k, v in kern.items() if k in algo}
@@ -376,12 +385,12 @@ def run_gpu(args):
                 if bound == "hbm":
                     ach = per_launch / sec / 1e9
                     roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                            "frac": ach / hbm, "traffic": None, "peak_source": which,
+                            "frac": ach / hbm, "traffic": traffic.get(name), "peak_source": which,
                             "algorithmic_bytes_per_launch": per_launch, "us_per_launch": kt["us_per_launch"]}
                 else:
                     ach = per_launch / sec / 1e12
                     roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                            "frac": ach / tf_sus, "traffic": None, "peak_source": which + " (sustained bf16)",
+                            "frac": ach / tf_sus, "traffic": traffic.get(name), "peak_source": which + " (sustained bf16)",
                             "algorithmic_flops_per_launch": per_launch, "us_per_launch": kt["us_per_launch"],
                             "note": "tcgen05 kind::tf32 (nominal dense peak is half of bf16's); peak quoted is the "
                                     "measured bf16 figure as the profiling recipe prescribes"}
@@ -405,7 +414,8 @@ def run_gpu(args):
             cpu = {"value": 1.0 / spf, "unit": "frames/s", "cores": min(16, os.cpu_count() or 1), "kind": "port",
                    "sample": f"{n_cpu} consecutive stereo frames (after the init frame) of this run's sequence through "
                              "the oracle port of the OpenCV CPU path; SURF restated, not OpenCV",
-                   "host_cpus": os.cpu_count()}
+                   "host_cpus": os.cpu_count(),
+                   "stage_ms": getattr(cpu_frames, "last_stage_ms", None)}
         line = {
             "metric": "stereo_uvo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,

@@ -16,7 +16,7 @@ KEYPOINT_DTYPE = np.dtype(
      ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
-__all__ = ["Context", "default_params", "make_camera", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
+__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
 
 
 def _p(a):
@@ -50,6 +50,21 @@ def make_camera(K, D, newK):
     D = _f64(D, 4)
     return L.Camera(K[0, 0], K[1, 1], K[0, 2], K[1, 2], D[0], D[1], D[2], D[3], newK[0, 0], newK[1, 1], newK[0, 2],
                     newK[1, 2])
+
+
+def resize_camera_matrix(original_width, original_height, desired_width, cameraMatrix, distortionCoeff):
+    """resize_camera_matrix (VO_utility.h:112, VO_utility.cpp:658-675), host-only: returns (scaled cameraMatrix,
+    newCamMatrix, (width, height)); getOptimalNewCameraMatrix(alpha=0) is restated in the library (camera.cu)."""
+    lib = L.load()
+    K = np.array(cameraMatrix, dtype=np.float64).reshape(3, 3).copy()
+    D = _f64(distortionCoeff, 4)
+    newK = np.zeros(9)
+    ow, oh = C.c_int(0), C.c_int(0)
+    rc = lib.uvo_resize_camera_matrix(int(original_width), int(original_height), int(desired_width), _p(K), _p(D),
+                                      _p(newK), C.byref(ow), C.byref(oh))
+    if rc != L.UVO_OK:
+        raise L.UvoError(rc, "uvo_resize_camera_matrix: bad camera / size")
+    return K, newK.reshape(3, 3), (ow.value, oh.value)
 
 
 class Context:

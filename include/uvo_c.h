@@ -121,6 +121,17 @@ UVO_API void uvo_default_params(int stereo, uvo_params* out);
 UVO_API void* uvo_host_alloc(size_t bytes);
 UVO_API void uvo_host_free(void* p);
 
+/* ---------------------------------------------------------------------------------------------------- camera set-up */
+/* cv::getOptimalNewCameraMatrix(K, D, Size(w, h), 0, Size(w, h), 0) as resize_camera_matrix calls it
+ * (VO_utility.cpp:674): host-only, no GPU.  K, newK: 3x3 row-major; D = k1, k2, p1, p2. */
+UVO_API int uvo_optimal_new_camera_matrix(const double K[9], const double D[4], int width, int height,
+                                          double newK[9]);
+/* void resize_camera_matrix(Mat original_image, Mat& cameraMatrix, Mat distortionCoeff, Mat& newCamMatrix)
+ * -- VO_utility.h:112, VO_utility.cpp:658-675: scales K by DESIRED_WIDTH / original width (skew kept, K[2][2] = 1)
+ * in place and returns the new camera matrix for the DESIRED_WIDTH x int(h / ratio) image.  Host-only. */
+UVO_API int uvo_resize_camera_matrix(int original_width, int original_height, int desired_width, double K_inout[9],
+                                     const double D[4], double newK[9], int* out_width, int* out_height);
+
 /* ---------------------------------------------------------------------------------------------------- K1-K3 */
 /* Mat get_image(const Mat&, const Mat&, const Mat&, const Mat&)  -- VO_utility.h:105, VO_utility.cpp:337-379.
  * Native-size branch: cvtColor(RGB2GRAY) + undistort + optional CLAHE(8x8).  src is 3-channel interleaved u8. */

@@ -63,24 +63,41 @@ void K4(const Mat& K, double k[4]) {
 }
 }  // namespace
 
-// VO_utility.cpp:337-379 (native-size branch; the INTER_AREA pre-resize branch stays on cv::resize)
+// VO_utility.cpp:337-379: both branches (native size, and INTER_AREA pre-resize to DESIRED_WIDTH) on the GPU
 Mat get_image(const Mat& current_img, const Mat& cameraMatrix, const Mat& distortionCoeff, const Mat& newCamMatrix) {
-  Mat src = current_img;
+  const Mat& src = current_img;
+  CV_Assert(src.type() == CV_8UC3);  // cvtColor(RGB2GRAY) throws on anything else
   const double ratio = (double)src.cols / (double)DESIRED_WIDTH;
   const int desired_height = (int)(src.rows / ratio);
-  if (!(src.cols == DESIRED_WIDTH && src.rows == desired_height))
-    resize(current_img, src, Size(DESIRED_WIDTH, desired_height), 0, 0, INTER_AREA);
-  CV_Assert(src.type() == CV_8UC3);  // cvtColor(RGB2GRAY) throws on anything else
   uvo_camera cam;
   double k[4], nk[4];
   K4(cameraMatrix, k);
   K4(newCamMatrix, nk);
   cam = {k[0], k[1], k[2], k[3], distortionCoeff.at<double>(0), distortionCoeff.at<double>(1),
          distortionCoeff.at<double>(2), distortionCoeff.at<double>(3), nk[0], nk[1], nk[2], nk[3]};
-  Mat out(src.rows, src.cols, CV_8UC1);
-  check(uvo_get_image(ctx(), src.data, src.cols, src.rows, src.step, &cam, CLAHE_CORRECTION, CLIP_LIMIT, out.data,
-                      out.step));
+  if (src.cols == DESIRED_WIDTH && src.rows == desired_height) {
+    Mat out(src.rows, src.cols, CV_8UC1);
+    check(uvo_get_image(ctx(), src.data, src.cols, src.rows, src.step, &cam, CLAHE_CORRECTION, CLIP_LIMIT, out.data,
+                        out.step));
+    return out;
+  }
+  Mat out(desired_height, DESIRED_WIDTH, CV_8UC1);
+  int ow = 0, oh = 0;
+  check(uvo_get_image_resized(ctx(), src.data, src.cols, src.rows, src.step, DESIRED_WIDTH, &cam, CLAHE_CORRECTION,
+                              CLIP_LIMIT, out.data, out.step, &ow, &oh));
   return out;
+}
+
+// VO_utility.cpp:658-675: host-only (no OpenCV needed: uvo_optimal_new_camera_matrix restates
+// getOptimalNewCameraMatrix(alpha = 0) bit-exactly)
+void resize_camera_matrix(Mat original_image, Mat& cameraMatrix, Mat distortionCoeff, Mat& newCamMatrix) {
+  CV_Assert(cameraMatrix.type() == CV_64F && cameraMatrix.isContinuous());
+  double D[4] = {distortionCoeff.at<double>(0), distortionCoeff.at<double>(1), distortionCoeff.at<double>(2),
+                 distortionCoeff.at<double>(3)};
+  newCamMatrix.create(3, 3, CV_64F);
+  int ow = 0, oh = 0;
+  check(uvo_resize_camera_matrix(original_image.cols, original_image.rows, DESIRED_WIDTH, cameraMatrix.ptr<double>(), D,
+                                 newCamMatrix.ptr<double>(), &ow, &oh));
 }
 
 // VO_utility.cpp:91-126 (SURF branch; the other detectors stay on OpenCV)
@@ -227,5 +244,5 @@ bool solvePnPRansac(const Mat& X /* Nx3 CV_64F */, const vector<Point2f>& x, con
 }  // namespace uvo_shim
 
 // compute_projection_matrix, convert_from_homogeneous_coords, extract_inliers, reproject_errors,
-// resize_camera_matrix, select_desired_*, the parameter loaders and show_matches carry no hot arithmetic and are
+// select_desired_*, the parameter loaders and show_matches carry no hot arithmetic and are
 // compiled unchanged from the reference's VO_utility.cpp.

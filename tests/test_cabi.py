@@ -68,3 +68,37 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "surf.cu" or "the oracle" in txt.lower(), f
                 assert "import oracle" not in txt and "from oracle" not in txt and "uvo_oracle" not in txt, f
+
+
+def test_optimal_new_camera_matrix_matches_cv2():
+    """uvo_optimal_new_camera_matrix / uvo_resize_camera_matrix (host-only, VO_utility.cpp:658-675) against
+    cv2.getOptimalNewCameraMatrix(alpha=0): bit-exact on random 4-coefficient cameras at every BASELINE resolution."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    import ergo_uvo_b200 as U
+    lib = U.load()
+    rs = np.random.RandomState(0)
+    for (w, h) in [(640, 480), (1280, 1024), (1920, 1080), (2448, 2048), (641, 513)]:
+        for _ in range(10):
+            f = w * rs.uniform(0.7, 1.3)
+            K = np.array([[f, 0, w / 2 + rs.uniform(-20, 20)], [0, f * rs.uniform(0.95, 1.05), h / 2 + rs.uniform(-20, 20)],
+                          [0, 0, 1.0]])
+            D = np.array([rs.uniform(-0.3, 0.1), rs.uniform(-0.05, 0.1), rs.uniform(-2e-3, 2e-3), rs.uniform(-2e-3, 2e-3)])
+            ref, _ = cv2.getOptimalNewCameraMatrix(K, D, (w, h), 0, (w, h), False)
+            out = np.zeros(9)
+            assert lib.uvo_optimal_new_camera_matrix(K.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), w, h,
+                                                     out.ctypes.data_as(C.c_void_p)) == 0
+            assert np.array_equal(out.reshape(3, 3), ref)
+    # resize_camera_matrix: 2560x2048 camera scaled to DESIRED_WIDTH 640 (the shipped mono set-up)
+    K = np.array([[2400.0, 0.5, 1275.0], [0, 2410.0, 1030.0], [0, 0, 1.0]])
+    D = np.array([-0.2, 0.05, 1e-3, -5e-4])
+    Kio, newK = K.copy(), np.zeros(9)
+    ow, oh = C.c_int(0), C.c_int(0)
+    assert lib.uvo_resize_camera_matrix(2560, 2048, 640, Kio.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p),
+                                        newK.ctypes.data_as(C.c_void_p), C.byref(ow), C.byref(oh)) == 0
+    assert (ow.value, oh.value) == (640, 512)
+    Ks = K * (1.0 / 4.0)
+    Ks[0, 1], Ks[2, 2] = 0.5, 1.0
+    assert np.array_equal(Kio, Ks)
+    ref, _ = cv2.getOptimalNewCameraMatrix(Ks, D, (640, 512), 0, (640, 512), False)
+    assert np.array_equal(newK.reshape(3, 3), ref)

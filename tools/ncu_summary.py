@@ -29,6 +29,17 @@ def main():
         out.append(e)
     json.dump(out, open(dst, "w"), indent=1)
     print(f"{len(out)} kernels -> {dst}")
+    if len(sys.argv) > 3:  # third argument: traffic table (bench.py's roofline.traffic), mean DRAM bytes per launch
+        acc = {}
+        ir, iw, iu = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), None
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in data:
+            name = r[hdr.index("Kernel Name")].split("(")[0]
+            b = float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+            acc.setdefault(name, []).append(b)
+        tr = {"source": src.split("/")[-1], "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in acc.items()}}
+        json.dump(tr, open(sys.argv[3], "w"), indent=1)
+        print(f"traffic of {len(acc)} kernels -> {sys.argv[3]}")
 
 
 if __name__ == "__main__":
