@@ -24,7 +24,7 @@ __device__ __forceinline__ double dist2_3(const double* a, const double* b) {
 __device__ inline void epnp_control_points(const double c0[3], const double cov[9], int n, double cws[4][3],
                                            double ci[9]) {
   double dc[3], Vt[9];
-  jacobi_svd<3>(cov, 3, 3, dc, nullptr, Vt);
+  jacobi_svd<3, 3, 3>(cov, 3, 3, dc, nullptr, Vt);
   for (int j = 0; j < 3; j++) cws[0][j] = c0[j];
   for (int i = 1; i < 4; i++) {
     const double k = sqrt(dc[i - 1] / n);
@@ -128,99 +128,55 @@ __device__ inline void epnp_qr_solve(double* A, int nr, int nc, double* b, doubl
   }
 }
 
-// From MtM (12x12) and the control points: the null-space rows `ut` (12x12, rows sorted by descending singular
-// value) and the three beta candidates (N = 1, 2, 3 approximations, each refined by 5 Gauss-Newton steps).
-__device__ inline void epnp_betas(const double* mtm, const double cws[4][3], double* ut, double Betas[3][4]) {
-  double d[12];
-  jacobi_svd<12>(mtm, 12, 12, d, nullptr, ut);
-  // compute_L_6x10
-  double l[60], rho[6];
-  {
-    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
-    double dv[4][6][3];
-    for (int i = 0; i < 4; i++) {
-      int a = 0, b = 1;
-      for (int j = 0; j < 6; j++) {
-        dv[i][j][0] = v[i][3 * a] - v[i][3 * b];
-        dv[i][j][1] = v[i][3 * a + 1] - v[i][3 * b + 1];
-        dv[i][j][2] = v[i][3 * a + 2] - v[i][3 * b + 2];
-        b++;
-        if (b > 3) {
-          a++;
-          b = a + 1;
-        }
-      }
-    }
-    for (int i = 0; i < 6; i++) {
-      double* row = l + 10 * i;
-      row[0] = dot3(dv[0][i], dv[0][i]);
-      row[1] = 2.0f * dot3(dv[0][i], dv[1][i]);
-      row[2] = dot3(dv[1][i], dv[1][i]);
-      row[3] = 2.0f * dot3(dv[0][i], dv[2][i]);
-      row[4] = 2.0f * dot3(dv[1][i], dv[2][i]);
-      row[5] = dot3(dv[2][i], dv[2][i]);
-      row[6] = 2.0f * dot3(dv[0][i], dv[3][i]);
-      row[7] = 2.0f * dot3(dv[1][i], dv[3][i]);
-      row[8] = 2.0f * dot3(dv[2][i], dv[3][i]);
-      row[9] = dot3(dv[3][i], dv[3][i]);
-    }
-  }
-  rho[0] = dist2_3(cws[0], cws[1]);
-  rho[1] = dist2_3(cws[0], cws[2]);
-  rho[2] = dist2_3(cws[0], cws[3]);
-  rho[3] = dist2_3(cws[1], cws[2]);
-  rho[4] = dist2_3(cws[1], cws[3]);
-  rho[5] = dist2_3(cws[2], cws[3]);
-  for (int which = 1; which <= 3; which++) {
-    double* betas = Betas[which - 1];
-    const int cols1[4] = {0, 1, 3, 6}, cols23[5] = {0, 1, 2, 3, 4};
-    const int nc = which == 1 ? 4 : which == 2 ? 3 : 5;
-    double A[30], x[5];
-    for (int i = 0; i < 6; i++)
-      for (int j = 0; j < nc; j++) A[i * nc + j] = l[10 * i + (which == 1 ? cols1[j] : cols23[j])];
-    svd_solve6(A, 6, nc, rho, x);
-    if (which == 1) {
-      if (x[0] < 0) {
-        betas[0] = sqrt(-x[0]);
-        betas[1] = -x[1] / betas[0];
-        betas[2] = -x[2] / betas[0];
-        betas[3] = -x[3] / betas[0];
-      } else {
-        betas[0] = sqrt(x[0]);
-        betas[1] = x[1] / betas[0];
-        betas[2] = x[2] / betas[0];
-        betas[3] = x[3] / betas[0];
-      }
+// One of the three beta candidates (which = 1, 2, 3: the N = 1, 2, 3 approximations), refined by 5 Gauss-Newton steps
+__device__ inline void epnp_betas_which(const double* l, const double* rho, int which, double betas[4]) {
+  const int cols1[4] = {0, 1, 3, 6}, cols23[5] = {0, 1, 2, 3, 4};
+  const int nc = which == 1 ? 4 : which == 2 ? 3 : 5;
+  double A[30], x[5];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < nc; j++) A[i * nc + j] = l[10 * i + (which == 1 ? cols1[j] : cols23[j])];
+  svd_solve6(A, 6, nc, rho, x);
+  if (which == 1) {
+    if (x[0] < 0) {
+      betas[0] = sqrt(-x[0]);
+      betas[1] = -x[1] / betas[0];
+      betas[2] = -x[2] / betas[0];
+      betas[3] = -x[3] / betas[0];
     } else {
-      if (x[0] < 0) {
-        betas[0] = sqrt(-x[0]);
-        betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
-      } else {
-        betas[0] = sqrt(x[0]);
-        betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
-      }
-      if (x[1] < 0) betas[0] = -betas[0];
-      betas[2] = which == 3 ? x[3] / betas[0] : 0.0;
-      betas[3] = 0.0;
+      betas[0] = sqrt(x[0]);
+      betas[1] = x[1] / betas[0];
+      betas[2] = x[2] / betas[0];
+      betas[3] = x[3] / betas[0];
     }
-    // gauss_newton, 5 iterations
-    for (int it = 0; it < 5; it++) {
-      double GA[24], gb[6], gx[4] = {0, 0, 0, 0};
-      for (int i = 0; i < 6; i++) {
-        const double* rowL = l + i * 10;
-        double* rowA = GA + i * 4;
-        rowA[0] = 2 * rowL[0] * betas[0] + rowL[1] * betas[1] + rowL[3] * betas[2] + rowL[6] * betas[3];
-        rowA[1] = rowL[1] * betas[0] + 2 * rowL[2] * betas[1] + rowL[4] * betas[2] + rowL[7] * betas[3];
-        rowA[2] = rowL[3] * betas[0] + rowL[4] * betas[1] + 2 * rowL[5] * betas[2] + rowL[8] * betas[3];
-        rowA[3] = rowL[6] * betas[0] + rowL[7] * betas[1] + rowL[8] * betas[2] + 2 * rowL[9] * betas[3];
-        gb[i] = rho[i] - (rowL[0] * betas[0] * betas[0] + rowL[1] * betas[0] * betas[1] + rowL[2] * betas[1] * betas[1] +
-                          rowL[3] * betas[0] * betas[2] + rowL[4] * betas[1] * betas[2] + rowL[5] * betas[2] * betas[2] +
-                          rowL[6] * betas[0] * betas[3] + rowL[7] * betas[1] * betas[3] + rowL[8] * betas[2] * betas[3] +
-                          rowL[9] * betas[3] * betas[3]);
-      }
-      epnp_qr_solve(GA, 6, 4, gb, gx);
-      for (int i = 0; i < 4; i++) betas[i] += gx[i];
+  } else {
+    if (x[0] < 0) {
+      betas[0] = sqrt(-x[0]);
+      betas[1] = (x[2] < 0) ? sqrt(-x[2]) : 0.0;
+    } else {
+      betas[0] = sqrt(x[0]);
+      betas[1] = (x[2] > 0) ? sqrt(x[2]) : 0.0;
     }
+    if (x[1] < 0) betas[0] = -betas[0];
+    betas[2] = which == 3 ? x[3] / betas[0] : 0.0;
+    betas[3] = 0.0;
+  }
+  // gauss_newton, 5 iterations
+  for (int it = 0; it < 5; it++) {
+    double GA[24], gb[6], gx[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) {
+      const double* rowL = l + i * 10;
+      double* rowA = GA + i * 4;
+      rowA[0] = 2 * rowL[0] * betas[0] + rowL[1] * betas[1] + rowL[3] * betas[2] + rowL[6] * betas[3];
+      rowA[1] = rowL[1] * betas[0] + 2 * rowL[2] * betas[1] + rowL[4] * betas[2] + rowL[7] * betas[3];
+      rowA[2] = rowL[3] * betas[0] + rowL[4] * betas[1] + 2 * rowL[5] * betas[2] + rowL[8] * betas[3];
+      rowA[3] = rowL[6] * betas[0] + rowL[7] * betas[1] + rowL[8] * betas[2] + 2 * rowL[9] * betas[3];
+      gb[i] = rho[i] - (rowL[0] * betas[0] * betas[0] + rowL[1] * betas[0] * betas[1] + rowL[2] * betas[1] * betas[1] +
+                        rowL[3] * betas[0] * betas[2] + rowL[4] * betas[1] * betas[2] + rowL[5] * betas[2] * betas[2] +
+                        rowL[6] * betas[0] * betas[3] + rowL[7] * betas[1] * betas[3] + rowL[8] * betas[2] * betas[3] +
+                        rowL[9] * betas[3] * betas[3]);
+    }
+    epnp_qr_solve(GA, 6, 4, gb, gx);
+    for (int i = 0; i < 4; i++) betas[i] += gx[i];
   }
 }
 
@@ -241,7 +197,7 @@ __device__ __forceinline__ void epnp_pc(const double a[4], const double ccs[4][3
 __device__ inline void epnp_rt_from_abt(const double abt[9], const double pc0[3], const double pw0[3], double R[9],
                                         double t[3]) {
   double d[3], U[9], Vt[9];
-  jacobi_svd<3>(abt, 3, 3, d, U, Vt);
+  jacobi_svd<3, 3, 3>(abt, 3, 3, d, U, Vt);
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) R[i * 3 + j] = U[i * 3] * Vt[j] + U[i * 3 + 1] * Vt[3 + j] + U[i * 3 + 2] * Vt[6 + j];
   const double det = R[0] * R[4] * R[8] + R[1] * R[5] * R[6] + R[2] * R[3] * R[7] - R[2] * R[4] * R[6] -
@@ -263,10 +219,44 @@ __device__ __forceinline__ double epnp_reproj1(const double R[9], const double t
   return sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
 }
 
-// Whole EPnP for a small set held by one thread (n <= 5): the RANSAC minimal solver.
-// pws: n x 3, us: n x 2 (pixel coordinates as epnp::init_points builds them).
-__device__ inline void epnp_small(const double* pws, const double* us, int n, const EpnpCam& cam, double R[9],
-                                  double t[3]) {
+// compute_R_and_t for one beta candidate on a small set (n <= 5): camera-frame points from the control points,
+// sign fix, absolute orientation, mean reprojection error.  Returns the error; Rw / tw receive the pose.
+__device__ inline double epnp_candidate(const double* pws, const double* us, int n, const double (*alphas)[4],
+                                        const double betas[4], const double* ut, const EpnpCam& cam, double Rw[9],
+                                        double tw[3]) {
+  double ccs[4][3], pcs[5][3];
+  epnp_ccs(betas, ut, ccs);
+  for (int i = 0; i < n; i++) epnp_pc(alphas[i], ccs, 1.0, pcs[i]);
+  if (pcs[0][2] < 0.0)  // solve_for_sign
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < 3; j++) pcs[i][j] = -pcs[i][j];
+  double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < 3; j++) {
+      pc0[j] += pcs[i][j];
+      pw0[j] += pws[3 * i + j];
+    }
+  for (int j = 0; j < 3; j++) {
+    pc0[j] /= n;
+    pw0[j] /= n;
+  }
+  double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    const double* pw = pws + 3 * i;
+    for (int j = 0; j < 3; j++) {
+      abt[3 * j] += (pcs[i][j] - pc0[j]) * (pw[0] - pw0[0]);
+      abt[3 * j + 1] += (pcs[i][j] - pc0[j]) * (pw[1] - pw0[1]);
+      abt[3 * j + 2] += (pcs[i][j] - pc0[j]) * (pw[2] - pw0[2]);
+    }
+  }
+  epnp_rt_from_abt(abt, pc0, pw0, Rw, tw);
+  double sum2 = 0.0;
+  for (int i = 0; i < n; i++) sum2 += epnp_reproj1(Rw, tw, pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
+  return sum2 / n;
+}
+
+// centroid, covariance, control points and barycentric coordinates of a small set (n <= 5)
+__device__ inline void epnp_small_setup(const double* pws, int n, double cws[4][3], double ci[9], double (*alphas)[4]) {
   double c0[3] = {0, 0, 0};
   for (int i = 0; i < n; i++)
     for (int j = 0; j < 3; j++) c0[j] += pws[3 * i + j];
@@ -277,59 +267,43 @@ __device__ inline void epnp_small(const double* pws, const double* us, int n, co
     for (int a = 0; a < 3; a++)
       for (int b = 0; b < 3; b++) cov[a * 3 + b] += d[a] * d[b];
   }
-  double cws[4][3], ci[9];
   epnp_control_points(c0, cov, n, cws, ci);
-  double alphas[5][4];
-  double mtm[144];
-  for (int i = 0; i < 144; i++) mtm[i] = 0;
-  for (int i = 0; i < n; i++) {
-    epnp_alphas(pws + 3 * i, cws, ci, alphas[i]);
-    double M1[12], M2[12];
-    epnp_m_rows(alphas[i], us[2 * i], us[2 * i + 1], cam, M1, M2);
-    for (int a = 0; a < 12; a++)
-      for (int b = 0; b < 12; b++) mtm[a * 12 + b] += M1[a] * M1[b] + M2[a] * M2[b];
+  for (int i = 0; i < n; i++) epnp_alphas(pws + 3 * i, cws, ci, alphas[i]);
+}
+
+// row i (0..5) of compute_L_6x10: control-point pair (a, b) in the order (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+__device__ inline void epnp_L_row(const double* ut, int i, double* row) {
+  const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+  const int a = pa[i], b = pb[i];
+  double dv[4][3];
+  for (int x = 0; x < 4; x++) {
+    const double* v = ut + 12 * (11 - x);
+    dv[x][0] = v[3 * a] - v[3 * b];
+    dv[x][1] = v[3 * a + 1] - v[3 * b + 1];
+    dv[x][2] = v[3 * a + 2] - v[3 * b + 2];
   }
-  double ut[144], Betas[3][4];
-  epnp_betas(mtm, cws, ut, Betas);
-  double best_err = 0;
-  for (int w = 0; w < 3; w++) {
-    double ccs[4][3], pcs[5][3];
-    epnp_ccs(Betas[w], ut, ccs);
-    for (int i = 0; i < n; i++) epnp_pc(alphas[i], ccs, 1.0, pcs[i]);
-    if (pcs[0][2] < 0.0)  // solve_for_sign
-      for (int i = 0; i < n; i++)
-        for (int j = 0; j < 3; j++) pcs[i][j] = -pcs[i][j];
-    double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
-    for (int i = 0; i < n; i++)
-      for (int j = 0; j < 3; j++) {
-        pc0[j] += pcs[i][j];
-        pw0[j] += pws[3 * i + j];
-      }
-    for (int j = 0; j < 3; j++) {
-      pc0[j] /= n;
-      pw0[j] /= n;
-    }
-    double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < n; i++) {
-      const double* pw = pws + 3 * i;
-      for (int j = 0; j < 3; j++) {
-        abt[3 * j] += (pcs[i][j] - pc0[j]) * (pw[0] - pw0[0]);
-        abt[3 * j + 1] += (pcs[i][j] - pc0[j]) * (pw[1] - pw0[1]);
-        abt[3 * j + 2] += (pcs[i][j] - pc0[j]) * (pw[2] - pw0[2]);
-      }
-    }
-    double Rw[9], tw[3];
-    epnp_rt_from_abt(abt, pc0, pw0, Rw, tw);
-    double sum2 = 0.0;
-    for (int i = 0; i < n; i++) sum2 += epnp_reproj1(Rw, tw, pws + 3 * i, us[2 * i], us[2 * i + 1], cam);
-    const double err = sum2 / n;
-    // N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
-    if (w == 0 || err < best_err) {
-      best_err = err;
-      for (int i = 0; i < 9; i++) R[i] = Rw[i];
-      for (int i = 0; i < 3; i++) t[i] = tw[i];
-    }
-  }
+  row[0] = dot3(dv[0], dv[0]);
+  row[1] = 2.0f * dot3(dv[0], dv[1]);
+  row[2] = dot3(dv[1], dv[1]);
+  row[3] = 2.0f * dot3(dv[0], dv[2]);
+  row[4] = 2.0f * dot3(dv[1], dv[2]);
+  row[5] = dot3(dv[2], dv[2]);
+  row[6] = 2.0f * dot3(dv[0], dv[3]);
+  row[7] = 2.0f * dot3(dv[1], dv[3]);
+  row[8] = 2.0f * dot3(dv[2], dv[3]);
+  row[9] = dot3(dv[3], dv[3]);
+}
+__device__ inline double epnp_rho_entry(const double cws[4][3], int i) {
+  const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+  return dist2_3(cws[pa[i]], cws[pb[i]]);
+}
+
+// element `a` (0..11) of the two rows of M a point contributes (epnp_m_rows, one element at a time)
+__device__ __forceinline__ void epnp_m_elem(const double al[4], double u, double v, const EpnpCam& cam, int a,
+                                            double& m1, double& m2) {
+  const int k = a / 3, r = a - 3 * k;
+  m1 = r == 0 ? al[k] * cam.fu : (r == 1 ? 0.0 : al[k] * (cam.uc - u));
+  m2 = r == 0 ? 0.0 : (r == 1 ? al[k] * cam.fv : al[k] * (cam.vc - v));
 }
 
 }  // namespace uvo

@@ -8,8 +8,11 @@
 namespace uvo {
 
 // A: m x n row-major, m,n <= MAXD.  A = U diag(w) Vt, w descending.  U: m x n (may be null), Vt: n x n.
-template <int MAXD>
-__device__ void jacobi_svd(const double* A, int m, int n, double* w, double* U, double* Vt) {
+// CM / CN: compile-time copies of m / n (0 = run-time).  With both known the k-loops unroll, so the loads of a pair's two
+// rows are issued back to back instead of one per trip of a serial loop; the arithmetic and its order are unchanged.
+template <int MAXD, int CM = 0, int CN = 0>
+__device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, double* U, double* Vt) {
+  const int m = CM ? CM : m_rt, n = CN ? CN : n_rt;
   double At[MAXD * MAXD], V[MAXD * MAXD], W[MAXD];
   for (int i = 0; i < n; i++)
     for (int k = 0; k < m; k++) At[i * m + k] = A[k * n + i];
@@ -28,6 +31,7 @@ __device__ void jacobi_svd(const double* A, int m, int n, double* w, double* U, 
         double* Ai = At + i * m;
         double* Aj = At + j * m;
         double a = W[i], p = 0, b = W[j];
+#pragma unroll
         for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
         p *= 2;
@@ -42,6 +46,7 @@ __device__ void jacobi_svd(const double* A, int m, int n, double* w, double* U, 
           s = p / (gamma * c * 2);
         }
         a = b = 0;
+#pragma unroll
         for (int k = 0; k < m; k++) {
           const double t0 = c * Ai[k] + s * Aj[k];
           const double t1 = -s * Ai[k] + c * Aj[k];
@@ -55,6 +60,7 @@ __device__ void jacobi_svd(const double* A, int m, int n, double* w, double* U, 
         changed = true;
         double* Vi = V + i * n;
         double* Vj = V + j * n;
+#pragma unroll
         for (int k = 0; k < n; k++) {
           const double t0 = c * Vi[k] + s * Vj[k];
           const double t1 = -s * Vi[k] + c * Vj[k];
@@ -122,6 +128,164 @@ __device__ void jacobi_svd(const double* A, int m, int n, double* w, double* U, 
         for (int k = 0; k < m; k++) U[k * n + i] = 0;
     }
   }
+}
+
+// Eigen-decomposition of a symmetric N x N matrix by the cyclic two-sided Jacobi method: A = Vt^T diag(w) Vt, w
+// descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional null space (5-point
+// minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30 sweeps; with the
+// absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet another basis of
+// that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels and the CPU oracle
+// run this same sequence of IEEE operations (no FMA, sqrt and divide correctly rounded on both).
+template <int N>
+__device__ void jacobi_eigh(const double* A, double* w, double* Vt) {
+  // S: full symmetric working copy, Vr: rows converge to the eigenvectors
+  double S[N * N], Vr[N * N], W[N];
+  for (int i = 0; i < N * N; i++) S[i] = A[i];
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < N; k++) Vr[i * N + k] = (k == i) ? 1.0 : 0.0;
+  double tr = 0;
+  for (int i = 0; i < N; i++) tr += fabs(S[i * N + i]);
+  const double thr = tr * DBL_EPSILON;  // absolute: an off-diagonal entry below eps * trace is left alone
+  for (int sweep = 0; sweep < 30; sweep++) {
+    bool changed = false;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++) {
+        const double apq = S[p * N + q];
+        if (fabs(apq) <= thr) continue;
+        const double app = S[p * N + p], aqq = S[q * N + q];
+        const double theta = (aqq - app) / (2 * apq);
+        const double r = sqrt(theta * theta + 1);
+        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
+        const double c = 1 / sqrt(t * t + 1), s = t * c;
+        S[p * N + p] = app - t * apq;
+        S[q * N + q] = aqq + t * apq;
+        S[p * N + q] = 0;
+        S[q * N + p] = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          if (k == p || k == q) continue;
+          const double skp = S[k * N + p], skq = S[k * N + q];
+          const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
+          S[k * N + p] = np_;
+          S[p * N + k] = np_;
+          S[k * N + q] = nq_;
+          S[q * N + k] = nq_;
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const double vp = Vr[p * N + k], vq = Vr[q * N + k];
+          Vr[p * N + k] = c * vp - s * vq;
+          Vr[q * N + k] = s * vp + c * vq;
+        }
+        changed = true;
+      }
+    if (!changed) break;
+  }
+  for (int i = 0; i < N; i++) W[i] = S[i * N + i];
+  for (int i = 0; i < N - 1; i++) {  // selection sort, descending
+    int j = i;
+    for (int k = i + 1; k < N; k++)
+      if (W[j] < W[k]) j = k;
+    if (i != j) {
+      double tmp = W[i];
+      W[i] = W[j];
+      W[j] = tmp;
+      for (int k = 0; k < N; k++) {
+        tmp = Vr[i * N + k];
+        Vr[i * N + k] = Vr[j * N + k];
+        Vr[j * N + k] = tmp;
+      }
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    w[i] = W[i];
+    for (int k = 0; k < N; k++) Vt[i * N + k] = Vr[i * N + k];
+  }
+}
+
+// jacobi_eigh spread over a group of GL >= N lanes of one warp (`gl` = lane index inside the group, `gmask` = the
+// group's lane mask; every lane of the group calls with the same arguments).  S (N x N, holds A on entry, destroyed)
+// and Vr / Vt (N x N each) live in shared memory.  The two-sided rotation has no reductions: every element update is
+// an independent expression, so handing element k to lane k leaves each IEEE operation -- and therefore every output
+// bit -- exactly as in the one-thread version (and the CPU oracle), while a rotation costs ~40 instructions of latency
+// instead of ~300.
+template <int N>
+__device__ void jacobi_eigh_group(double* S, double* Vr, double* w, double* Vt, int gl, unsigned gmask) {
+  if (gl < N)
+    for (int k = 0; k < N; k++) Vr[gl * N + k] = (k == gl) ? 1.0 : 0.0;
+  double tr = 0;
+  for (int i = 0; i < N; i++) tr += fabs(S[i * N + i]);
+  const double thr = tr * DBL_EPSILON;
+  __syncwarp(gmask);
+  for (int sweep = 0; sweep < 30; sweep++) {
+    bool changed = false;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++) {
+        const double apq = S[p * N + q];
+        if (fabs(apq) <= thr) continue;  // group-uniform
+        const double app = S[p * N + p], aqq = S[q * N + q];
+        const double theta = (aqq - app) / (2 * apq);
+        const double r = sqrt(theta * theta + 1);
+        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
+        const double c = 1 / sqrt(t * t + 1), s = t * c;
+        double skp = 0, skq = 0, vp = 0, vq = 0;
+        const int k = gl;
+        if (k < N) {
+          skp = S[k * N + p];
+          skq = S[k * N + q];
+          vp = Vr[p * N + k];
+          vq = Vr[q * N + k];
+        }
+        __syncwarp(gmask);  // every lane has read this rotation's inputs
+        if (k < N) {
+          if (k != p && k != q) {
+            const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
+            S[k * N + p] = np_;
+            S[p * N + k] = np_;
+            S[k * N + q] = nq_;
+            S[q * N + k] = nq_;
+          }
+          Vr[p * N + k] = c * vp - s * vq;
+          Vr[q * N + k] = s * vp + c * vq;
+        }
+        if (gl == 0) {
+          S[p * N + p] = app - t * apq;
+          S[q * N + q] = aqq + t * apq;
+          S[p * N + q] = 0;
+          S[q * N + p] = 0;
+        }
+        __syncwarp(gmask);
+        changed = true;
+      }
+    if (!changed) break;
+  }
+  // selection sort (descending) of the eigenvalues; the row swaps are applied as one permutation
+  int perm[N];
+  {
+    double W[N];
+    for (int i = 0; i < N; i++) {
+      W[i] = S[i * N + i];
+      perm[i] = i;
+    }
+    for (int i = 0; i < N - 1; i++) {
+      int j = i;
+      for (int k = i + 1; k < N; k++)
+        if (W[j] < W[k]) j = k;
+      if (i != j) {
+        const double tw = W[i];
+        W[i] = W[j];
+        W[j] = tw;
+        const int tp = perm[i];
+        perm[i] = perm[j];
+        perm[j] = tp;
+      }
+    }
+    if (gl == 0)
+      for (int i = 0; i < N; i++) w[i] = W[i];
+  }
+  if (gl < N)
+    for (int i = 0; i < N; i++) Vt[i * N + gl] = Vr[perm[i] * N + gl];
+  __syncwarp(gmask);
 }
 
 // least-squares / pseudo-inverse solve via SVD (cvSolve CV_SVD); m <= 6, n <= 6

@@ -289,15 +289,29 @@ __global__ void __launch_bounds__(32) k_pnp_subsets(const __grid_constant__ PnpA
   }
 }
 
-// one EPnP hypothesis per thread (PnPRansacCallback::runKernel): the 5 correspondences arrive as f32, image points
-// are normalised with undistortPoints (f32 round trip), the pose goes R -> rvec (Rodrigues) and is stored together
-// with the rotation matrix projectPoints rebuilds from rvec.
-__global__ void __launch_bounds__(32) k_pnp_hyp(const __grid_constant__ PnpArgs a) {
+// One EPnP hypothesis (PnPRansacCallback::runKernel) per group of HYP_GL lanes.  The 5 correspondences arrive as f32,
+// image points are normalised with undistortPoints (f32 round trip), the pose goes R -> rvec (Rodrigues) and is stored
+// together with the rotation matrix projectPoints rebuilds from rvec.  Inside a group: the small set-up algebra is
+// done redundantly by every lane, M^T M is accumulated 9 entries per lane, the 12 x 12 eigen-decomposition is
+// lane-parallel (jacobi_eigh_group), lanes 0..5 / 6..11 build L / rho, and lanes 0..2 each refine one of the three
+// beta candidates and its pose.  Every value is produced by the same IEEE operations in the same order as the
+// one-thread restatement in the oracle, so the split changes latency, not bits.
+constexpr int HYP_GL = 16;
+constexpr int HYP_PER_BLOCK = 8;
+
+__global__ void __launch_bounds__(HYP_GL* HYP_PER_BLOCK) k_pnp_hyp(const __grid_constant__ PnpArgs a) {
+  __shared__ double s_S[HYP_PER_BLOCK][144], s_Vr[HYP_PER_BLOCK][144], s_ut[HYP_PER_BLOCK][144];
+  __shared__ double s_w[HYP_PER_BLOCK][12], s_l[HYP_PER_BLOCK][60], s_rho[HYP_PER_BLOCK][6];
+  __shared__ double s_al[HYP_PER_BLOCK][5][4];
   const int n = pnp_n(a);
   if (n < 5) return;
   const int iters = (n == 5) ? 1 : max(a.iterations, 1);
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= iters) return;
+  const int g = threadIdx.x / HYP_GL, gl = threadIdx.x % HYP_GL;
+  const int h = blockIdx.x * HYP_PER_BLOCK + g;
+  if (h >= iters) return;  // whole group
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane & ~(HYP_GL - 1);
+  const unsigned gmask = ((1u << HYP_GL) - 1u) << gbase;
   EpnpCam cam{a.K[0], a.K[1], a.K[2], a.K[3]};
   const double ifx = 1. / a.K[0], ify = 1. / a.K[1];
   double pws[15], us[10];
@@ -309,14 +323,54 @@ __global__ void __launch_bounds__(32) k_pnp_hyp(const __grid_constant__ PnpArgs 
     us[2 * k] = xn * cam.fu + cam.uc;
     us[2 * k + 1] = yn * cam.fv + cam.vc;
   }
-  double R[9], t[3], rvec[3], R2[9];
-  epnp_small(pws, us, 5, cam, R, t);
-  rodrigues_mat2vec(R, rvec);
-  rodrigues_vec2mat(rvec, R2);
-  double* m = a.hyp_model + (size_t)h * 15;
-  for (int i = 0; i < 9; i++) m[i] = R2[i];
-  for (int i = 0; i < 3; i++) m[9 + i] = t[i];
-  for (int i = 0; i < 3; i++) m[12 + i] = rvec[i];
+  double cws[4][3], ci[9];
+  double(*alphas)[4] = s_al[g];
+  {
+    double al[5][4];
+    epnp_small_setup(pws, 5, cws, ci, al);  // every lane computes the same values
+    if (gl == 0)
+      for (int i = 0; i < 5; i++)
+        for (int k = 0; k < 4; k++) alphas[i][k] = al[i][k];
+  }
+  __syncwarp(gmask);
+  // M^T M, each entry summed over the points in index order
+  for (int e = gl; e < 144; e += HYP_GL) {
+    const int ra = e / 12, rb = e - 12 * ra;
+    double acc = 0;
+    for (int i = 0; i < 5; i++) {
+      double m1a, m2a, m1b, m2b;
+      epnp_m_elem(alphas[i], us[2 * i], us[2 * i + 1], cam, ra, m1a, m2a);
+      epnp_m_elem(alphas[i], us[2 * i], us[2 * i + 1], cam, rb, m1b, m2b);
+      acc += m1a * m1b + m2a * m2b;
+    }
+    s_S[g][e] = acc;
+  }
+  __syncwarp(gmask);
+  jacobi_eigh_group<12>(s_S[g], s_Vr[g], s_w[g], s_ut[g], gl, gmask);
+  if (gl < 6) epnp_L_row(s_ut[g], gl, s_l[g] + 10 * gl);
+  else if (gl < 12) s_rho[g][gl - 6] = epnp_rho_entry(cws, gl - 6);
+  __syncwarp(gmask);
+  double err = 0, Rw[9], tw[3];
+  if (gl < 3) {
+    double betas[4];
+    epnp_betas_which(s_l[g], s_rho[g], gl + 1, betas);
+    err = epnp_candidate(pws, us, 5, alphas, betas, s_ut[g], cam, Rw, tw);
+  }
+  // N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
+  const double e1 = __shfl_sync(gmask, err, gbase + 0), e2 = __shfl_sync(gmask, err, gbase + 1),
+               e3 = __shfl_sync(gmask, err, gbase + 2);
+  int N = 1;
+  if (e2 < e1) N = 2;
+  if (e3 < (N == 1 ? e1 : e2)) N = 3;
+  if (gl == N - 1) {
+    double rvec[3], R2[9];
+    rodrigues_mat2vec(Rw, rvec);
+    rodrigues_vec2mat(rvec, R2);
+    double* m = a.hyp_model + (size_t)h * 15;
+    for (int i = 0; i < 9; i++) m[i] = R2[i];
+    for (int i = 0; i < 3; i++) m[9 + i] = tw[i];
+    for (int i = 0; i < 3; i++) m[12 + i] = rvec[i];
+  }
 }
 
 // PnPRansacCallback::computeError + findInliers for one point
@@ -418,7 +472,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
   __shared__ double s_red[32 * 9], s_out[9];
   __shared__ double s_cws[4][3], s_ci[9], s_ut[144], s_betas[3][4], s_ccs[4][3], s_R[9], s_t[3];
   __shared__ double s_rows[REFIT_TILE][24];
-  __shared__ double s_mtm[144];
+  __shared__ double s_mtm[144], s_Vr[144], s_w[12], s_l[60], s_rho[6];
   __shared__ double s_sign;
   const int tid = threadIdx.x;
   const int n = pnp_n(a);
@@ -511,7 +565,14 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
   }
   if (tid < 144) s_mtm[tid] = mt;
   __syncthreads();
-  if (tid == 0) epnp_betas(s_mtm, s_cws, s_ut, s_betas);
+  // eigenvectors of M^T M lane-parallel on warp 0, L / rho on lanes 0..11, one beta candidate per lane 0..2
+  if (tid < 32) {
+    jacobi_eigh_group<12>(s_mtm, s_Vr, s_w, s_ut, tid, 0xffffffffu);
+    if (tid < 6) epnp_L_row(s_ut, tid, s_l + 10 * tid);
+    else if (tid < 12) s_rho[tid - 6] = epnp_rho_entry(s_cws, tid - 6);
+    __syncwarp();
+    if (tid < 3) epnp_betas_which(s_l, s_rho, tid + 1, s_betas[tid]);
+  }
   __syncthreads();
   double best_err = 0, bestR[9], bestt[3];
   for (int w = 0; w < 3; w++) {
@@ -699,7 +760,7 @@ void launch_pnp_prepare(Ctx& c, const PnpArgs& a) {
 void launch_pnp_solve(Ctx& c, const PnpArgs& a) {
   const int iters = std::max(a.iterations, 1);
   UVO_KERNEL(c, "k_pnp_hyp");
-  k_pnp_hyp<<<div_up(iters, 32), 32, 0, c.stream>>>(a);
+  k_pnp_hyp<<<div_up(iters, HYP_PER_BLOCK), HYP_GL * HYP_PER_BLOCK, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_pnp_score");
   k_pnp_score<<<iters, 256, 0, c.stream>>>(a);

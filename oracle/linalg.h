@@ -119,6 +119,77 @@ inline void jacobi_svd(const double* A, int m, int n, double* w, double* U, doub
   }
 }
 
+// Eigen-decomposition of a symmetric N x N matrix by the cyclic two-sided Jacobi method: A = Vt^T diag(w) Vt, w
+// descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional null space (5-point
+// minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30 sweeps; with the
+// absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet another basis of
+// that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels and the CPU oracle
+// run this same sequence of IEEE operations (no FMA, sqrt and divide correctly rounded on both).
+template <int N>
+inline void jacobi_eigh(const double* A, double* w, double* Vt) {
+  // S: full symmetric working copy, Vr: rows converge to the eigenvectors
+  double S[N * N], Vr[N * N], W[N];
+  for (int i = 0; i < N * N; i++) S[i] = A[i];
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < N; k++) Vr[i * N + k] = (k == i) ? 1.0 : 0.0;
+  double tr = 0;
+  for (int i = 0; i < N; i++) tr += std::fabs(S[i * N + i]);
+  const double thr = tr * DBL_EPSILON;  // absolute: an off-diagonal entry below eps * trace is left alone
+  for (int sweep = 0; sweep < 30; sweep++) {
+    bool changed = false;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++) {
+        const double apq = S[p * N + q];
+        if (std::fabs(apq) <= thr) continue;
+        const double app = S[p * N + p], aqq = S[q * N + q];
+        const double theta = (aqq - app) / (2 * apq);
+        const double r = std::sqrt(theta * theta + 1);
+        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
+        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        S[p * N + p] = app - t * apq;
+        S[q * N + q] = aqq + t * apq;
+        S[p * N + q] = 0;
+        S[q * N + p] = 0;
+        for (int k = 0; k < N; k++) {
+          if (k == p || k == q) continue;
+          const double skp = S[k * N + p], skq = S[k * N + q];
+          const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
+          S[k * N + p] = np_;
+          S[p * N + k] = np_;
+          S[k * N + q] = nq_;
+          S[q * N + k] = nq_;
+        }
+        for (int k = 0; k < N; k++) {
+          const double vp = Vr[p * N + k], vq = Vr[q * N + k];
+          Vr[p * N + k] = c * vp - s * vq;
+          Vr[q * N + k] = s * vp + c * vq;
+        }
+        changed = true;
+      }
+    if (!changed) break;
+  }
+  for (int i = 0; i < N; i++) W[i] = S[i * N + i];
+  for (int i = 0; i < N - 1; i++) {  // selection sort, descending
+    int j = i;
+    for (int k = i + 1; k < N; k++)
+      if (W[j] < W[k]) j = k;
+    if (i != j) {
+      double tmp = W[i];
+      W[i] = W[j];
+      W[j] = tmp;
+      for (int k = 0; k < N; k++) {
+        tmp = Vr[i * N + k];
+        Vr[i * N + k] = Vr[j * N + k];
+        Vr[j * N + k] = tmp;
+      }
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    w[i] = W[i];
+    for (int k = 0; k < N; k++) Vt[i * N + k] = Vr[i * N + k];
+  }
+}
+
 // least-squares / pseudo-inverse solve of A x = b via SVD (cvSolve(..., CV_SVD)); A m x n, b m, x n
 inline void svd_solve(const double* A, int m, int n, const double* b, double* x) {
   std::vector<double> w(n), U((size_t)m * n), Vt((size_t)n * n);

@@ -438,11 +438,10 @@ struct Epnp {
       for (int a = 0; a < 12; a++)
         for (int b = 0; b < 12; b++) mtm[a * 12 + b] += M1[a] * M1[b] + M2[a] * M2[b];
     }
-    double d[12], U[144], Vt[144], ut[144];
-    jacobi_svd(mtm, 12, 12, d, U, Vt);
-    // CV_SVD_U_T of a symmetric PSD matrix: rows = eigenvectors; taken from V^T so that the null space (rank(M) =
-    // 10 for 5 points) is a proper orthonormal basis
-    for (int i = 0; i < 144; i++) ut[i] = Vt[i];
+    // CV_SVD_U_T of the symmetric PSD M^T M: rows = eigenvectors by descending eigenvalue (linalg.h: jacobi_eigh; the
+    // null space -- rank(M) = 10 for 5 points -- comes out as a proper orthonormal basis)
+    double d[12], ut[144];
+    jacobi_eigh<12>(mtm, d, ut);
     double l[60], rho[6];
     compute_L_6x10(ut, l);
     compute_rho(rho);
