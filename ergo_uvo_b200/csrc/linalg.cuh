@@ -136,72 +136,7 @@ __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, doubl
 // absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet another basis of
 // that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels and the CPU oracle
 // run this same sequence of IEEE operations (no FMA, sqrt and divide correctly rounded on both).
-template <int N>
-__device__ void jacobi_eigh(const double* A, double* w, double* Vt) {
-  // S: full symmetric working copy, Vr: rows converge to the eigenvectors
-  double S[N * N], Vr[N * N], W[N];
-  for (int i = 0; i < N * N; i++) S[i] = A[i];
-  for (int i = 0; i < N; i++)
-    for (int k = 0; k < N; k++) Vr[i * N + k] = (k == i) ? 1.0 : 0.0;
-  double tr = 0;
-  for (int i = 0; i < N; i++) tr += fabs(S[i * N + i]);
-  const double thr = tr * DBL_EPSILON;  // absolute: an off-diagonal entry below eps * trace is left alone
-  for (int sweep = 0; sweep < 30; sweep++) {
-    bool changed = false;
-    for (int p = 0; p < N - 1; p++)
-      for (int q = p + 1; q < N; q++) {
-        const double apq = S[p * N + q];
-        if (fabs(apq) <= thr) continue;
-        const double app = S[p * N + p], aqq = S[q * N + q];
-        const double theta = (aqq - app) / (2 * apq);
-        const double r = sqrt(theta * theta + 1);
-        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
-        const double c = 1 / sqrt(t * t + 1), s = t * c;
-        S[p * N + p] = app - t * apq;
-        S[q * N + q] = aqq + t * apq;
-        S[p * N + q] = 0;
-        S[q * N + p] = 0;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-          if (k == p || k == q) continue;
-          const double skp = S[k * N + p], skq = S[k * N + q];
-          const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
-          S[k * N + p] = np_;
-          S[p * N + k] = np_;
-          S[k * N + q] = nq_;
-          S[q * N + k] = nq_;
-        }
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-          const double vp = Vr[p * N + k], vq = Vr[q * N + k];
-          Vr[p * N + k] = c * vp - s * vq;
-          Vr[q * N + k] = s * vp + c * vq;
-        }
-        changed = true;
-      }
-    if (!changed) break;
-  }
-  for (int i = 0; i < N; i++) W[i] = S[i * N + i];
-  for (int i = 0; i < N - 1; i++) {  // selection sort, descending
-    int j = i;
-    for (int k = i + 1; k < N; k++)
-      if (W[j] < W[k]) j = k;
-    if (i != j) {
-      double tmp = W[i];
-      W[i] = W[j];
-      W[j] = tmp;
-      for (int k = 0; k < N; k++) {
-        tmp = Vr[i * N + k];
-        Vr[i * N + k] = Vr[j * N + k];
-        Vr[j * N + k] = tmp;
-      }
-    }
-  }
-  for (int i = 0; i < N; i++) {
-    w[i] = W[i];
-    for (int k = 0; k < N; k++) Vt[i * N + k] = Vr[i * N + k];
-  }
-}
+// (the one-thread form of this routine is oracle/linalg.h: jacobi_eigh)
 
 // jacobi_eigh spread over a group of GL >= N lanes of one warp (`gl` = lane index inside the group, `gmask` = the
 // group's lane mask; every lane of the group calls with the same arguments).  S (N x N, holds A on entry, destroyed)
@@ -224,10 +159,13 @@ __device__ void jacobi_eigh_group(double* S, double* Vr, double* w, double* Vt, 
         const double apq = S[p * N + q];
         if (fabs(apq) <= thr) continue;  // group-uniform
         const double app = S[p * N + p], aqq = S[q * N + q];
-        const double theta = (aqq - app) / (2 * apq);
-        const double r = sqrt(theta * theta + 1);
-        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
-        const double c = 1 / sqrt(t * t + 1), s = t * c;
+        // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), c = 1 / sqrt(t^2 + 1), s = t c with theta = d / x, written
+        // so that only two square roots and one reciprocal are on the dependent chain
+        const double d = aqq - app, x = 2 * apq;
+        const double rr = sqrt(d * d + x * x);
+        const double u = fabs(d) + rr, xs = d >= 0 ? x : -x;
+        const double ih = 1 / sqrt(x * x + u * u);
+        const double t = xs / u, c = u * ih, s = xs * ih;
         double skp = 0, skq = 0, vp = 0, vq = 0;
         const int k = gl;
         if (k < N) {
@@ -306,10 +244,22 @@ __device__ inline void svd_solve6(const double* A, int m, int n, const double* b
 }
 
 __device__ inline void svd_invert3(const double A[9], double Ainv[9]) {
+  // cvInvert(CV_SVD) column by column (x_c = pinv(A) e_c); the decomposition of A is computed once and reused -- it
+  // is a deterministic function of A, so this equals three independent svd_solve6 calls bit for bit
+  double w[3], U[9], Vt[9];
+  jacobi_svd<3, 3, 3>(A, 3, 3, w, U, Vt);
+  double thr = 0;
+  for (int i = 0; i < 3; i++) thr += w[i];
+  thr *= DBL_EPSILON * 2;
   for (int c = 0; c < 3; c++) {
-    double e[3] = {0, 0, 0}, x[3];
-    e[c] = 1;
-    svd_solve6(A, 3, 3, e, x);
+    double x[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+      if (w[i] <= thr) continue;
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += U[k * 3 + i] * (k == c ? 1.0 : 0.0);
+      s /= w[i];
+      for (int k = 0; k < 3; k++) x[k] += s * Vt[i * 3 + k];
+    }
     for (int r = 0; r < 3; r++) Ainv[r * 3 + c] = x[r];
   }
 }

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(32) k_pnp_subsets(const __grid_constant__ PnpA
 // lane-parallel (jacobi_eigh_group), lanes 0..5 / 6..11 build L / rho, and lanes 0..2 each refine one of the three
 // beta candidates and its pose.  Every value is produced by the same IEEE operations in the same order as the
 // one-thread restatement in the oracle, so the split changes latency, not bits.
-constexpr int HYP_GL = 16;
+constexpr int HYP_GL = 16;  // (one warp per hypothesis was measured slower: 305 vs 281 us, and it crowds the SMs)
 constexpr int HYP_PER_BLOCK = 8;
 
 __global__ void __launch_bounds__(HYP_GL* HYP_PER_BLOCK) k_pnp_hyp(const __grid_constant__ PnpArgs a) {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(HYP_GL* HYP_PER_BLOCK) k_pnp_hyp(const __grid_
   if (h >= iters) return;  // whole group
   const int lane = threadIdx.x & 31;
   const int gbase = lane & ~(HYP_GL - 1);
-  const unsigned gmask = ((1u << HYP_GL) - 1u) << gbase;
+  const unsigned gmask = (HYP_GL == 32 ? 0xffffffffu : ((1u << (HYP_GL & 31)) - 1u)) << gbase;
   EpnpCam cam{a.K[0], a.K[1], a.K[2], a.K[3]};
   const double ifx = 1. / a.K[0], ify = 1. / a.K[1];
   double pws[15], us[10];

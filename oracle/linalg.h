@@ -142,10 +142,13 @@ inline void jacobi_eigh(const double* A, double* w, double* Vt) {
         const double apq = S[p * N + q];
         if (std::fabs(apq) <= thr) continue;
         const double app = S[p * N + p], aqq = S[q * N + q];
-        const double theta = (aqq - app) / (2 * apq);
-        const double r = std::sqrt(theta * theta + 1);
-        const double t = theta >= 0 ? 1 / (theta + r) : 1 / (theta - r);
-        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        // t = sgn(theta) / (|theta| + std::sqrt(theta^2 + 1)), c = 1 / std::sqrt(t^2 + 1), s = t c with theta = d / x, written
+        // so that only two square roots and one reciprocal are on the dependent chain
+        const double d = aqq - app, x = 2 * apq;
+        const double rr = std::sqrt(d * d + x * x);
+        const double u = std::fabs(d) + rr, xs = d >= 0 ? x : -x;
+        const double ih = 1 / std::sqrt(x * x + u * u);
+        const double t = xs / u, c = u * ih, s = xs * ih;
         S[p * N + p] = app - t * apq;
         S[q * N + q] = aqq + t * apq;
         S[p * N + q] = 0;
