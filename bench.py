@@ -224,6 +224,10 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL is used for the barrier / MAX-over-ranks only; keep its "NCCL version ..." banner (printed to stdout when
+        # NCCL_DEBUG=VERSION) away from the one JSON line this script prints
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     ctx = U.Context(local, stream=stream.cuda_stream)
@@ -255,6 +259,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue_s = [0.0, 0]  # host time inside the enqueue call (kernel launches, copies, event waits), calls
+
     def run_device(n, start, inflight=inflight, ring=None, host=False):
         ring = ring or dev_ring
         enq = vo.enqueue_host if host else vo.enqueue_device
@@ -262,7 +268,10 @@ def run_gpu(args):
         q = 0
         for i in range(n):
             L, R = ring[(start + i) % RING]
+            t_enq = time.perf_counter()
             enq(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
+            host_enqueue_s[0] += time.perf_counter() - t_enq
+            host_enqueue_s[1] += 1
             q += 1
             if q >= inflight:
                 valid += vo.collect().valid
@@ -433,6 +442,7 @@ def run_gpu(args):
                     "api": f"uvo_stereo_enqueue_host + uvo_stereo_collect (pinned host images, {inflight} frames in "
                            "flight; H2D of both images and D2H of the result record inside the timed region)",
                     "sync_frame_latency_ms": sync_ms},
+            "host_enqueue_us_per_frame": 1e6 * host_enqueue_s[0] / max(host_enqueue_s[1], 1),
             "gpu_launches": int(launches),
             "launches_per_frame": launches / float(args.steps),
             "valid_frames": {"device": int(v[0]), "host": int(v[1]), "of": total_frames},

@@ -1,9 +1,12 @@
 """Per-stage microbenchmarks for the other BASELINE.json configurations, GPU (through the C ABI, HOST buffers, copies
 inside the timed region) beside the CPU (cv2 where the wheel has the function, the oracle port for SURF):
 
+  A  mono UVO 640x480 synthetic seabed sequence + synthetic range, shipped mono YAML (SURF + BF match + essential /
+     homography LMedS): uvo_mono frames/s beside the CPU replay (oracle port)
   C  SURF extract + BF kNN match: 1920x1080 frames, ~8k features, ratio 0.7
   D  batched RANSAC sweep: 4096 hypotheses x 10 000 correspondences for 5-point essential, homography and PnP
      (confidence 1 - 2^-53 and 75 % outliers keep every hypothesis alive)
+  E  one stereo sequence at 2448x2048 on one GPU (the per-GPU unit of the 8-GPU configuration), frames/s
 
     python tools/microbench.py [--out profiles/microbench_rNN.json]
 
@@ -32,6 +35,85 @@ def med(fn, reps, warm=2):
         fn()
         ts.append(time.perf_counter() - t0)
     return 1e3 * statistics.median(ts)
+
+
+def config_a(ctx, n_frames=24):
+    import ergo_uvo_b200 as U
+    from oracle import oracle as O
+    from oracle.ref_mono import RefMonoVO
+    from tools import synth
+    seq = synth.MonoSequence(640, 480, n_frames=n_frames, tex_size=2048, velocity=(0.05, 0.01, 0.005))
+    p = U.default_params(False)
+    cam = U.make_camera(seq.K, seq.D, seq.newK)
+    out = {"width": 640, "height": 480, "frames": n_frames, "params": "mono_VO_parameters.yaml (SURF 50, LMedS)"}
+    for rep in range(2):  # second pass is the measured one (first warms allocations)
+        vo = U.MonoVO(ctx, 640, 480, cam, p)
+        t0 = time.perf_counter()
+        res = [vo.frame(seq.frames[k], 0.1, seq.ranges[k]) for k in range(n_frames)]
+        dt = time.perf_counter() - t0
+        vo.close()
+    out["gpu_frames_per_s"] = n_frames / dt
+    out["keypoints_per_frame"] = float(np.mean([r.n_keypoints for r in res]))
+    out["published"] = int(sum(r.published for r in res))
+    out["used_essential"] = int(sum(r.used_essential for r in res if r.published))
+    n_cpu = min(n_frames, 6)
+    ref = RefMonoVO(O, seq, p)
+    t0 = time.perf_counter()
+    for k in range(n_cpu):
+        ref.frame(seq.frames[k], 0.1, seq.ranges[k])
+    out["cpu_frames_per_s(oracle port)"] = n_cpu / (time.perf_counter() - t0)
+    out["cpu_sample"] = f"first {n_cpu} frames"
+    return out
+
+
+def config_e(ctx, n_frames=60):
+    import ergo_uvo_b200 as U
+    from tools import synth
+    W, H = 2448, 2048
+    seq = synth.StereoSequence(W, H, n_frames=6, seed=1300, tex_size=4096)
+    p = U.default_params(True)
+    # threshold for ~4k keypoints per image, as in config B
+    g = ctx.get_image(seq.frames[0][0], seq.KL, seq.DL, seq.newKL)
+    lo, hi, thr = 100, 400000, None
+    ctx.params.max_features = 1 << 15
+    while lo < hi:
+        thr = (lo + hi) // 2
+        ctx.params.surf_min_hessian = thr
+        n = len(ctx.detect_features(g)[0])
+        if abs(n - 4096) <= 0.03 * 4096:
+            break
+        lo, hi = (thr + 1, hi) if n > 4096 else (lo, thr)
+    ctx.params.max_features = 16384
+    p.surf_min_hessian = thr
+    p.max_features = 16384
+    vo = U.StereoVO(ctx, W, H, U.make_camera(seq.KL, seq.DL, seq.newKL), U.make_camera(seq.KR, seq.DR, seq.newKR),
+                    seq.R_right, seq.t_right, p)
+    import torch
+    order = [0, 1, 2, 3, 4, 5, 4, 3, 2, 1]
+    host = [(torch.from_numpy(seq.frames[i][0]).pin_memory(), torch.from_numpy(seq.frames[i][1]).pin_memory())
+            for i in range(6)]
+
+    def run(n):
+        q, valid = 0, 0
+        for k in range(n):
+            L, R = host[order[k % len(order)]]
+            vo.enqueue_host(L.data_ptr(), R.data_ptr(), 3 * W, 0.1)
+            q += 1
+            if q >= 8:
+                valid += vo.collect().valid
+                q -= 1
+        while q:
+            valid += vo.collect().valid
+            q -= 1
+        return valid
+    run(16)
+    t0 = time.perf_counter()
+    valid = run(n_frames)
+    dt = time.perf_counter() - t0
+    vo.close()
+    return {"width": W, "height": H, "surf_min_hessian": thr, "frames": n_frames, "valid": int(valid),
+            "e2e_frames_per_s": n_frames / dt, "h2d_bytes_per_frame": 2 * 3 * W * H,
+            "api": "uvo_stereo_enqueue_host + uvo_stereo_collect, 8 frames in flight, pinned host images"}
 
 
 def config_c(ctx, reps):
@@ -132,6 +214,10 @@ def main():
     ctx = U.Context(0)
     res = {"host_cpus": os.cpu_count(),
            "timing": "wall clock around synchronous C-ABI calls with host buffers (H2D/D2H inside); median"}
+    if args.only in ("", "A"):
+        res["config_A"] = config_a(ctx)
+    if args.only in ("", "E"):
+        res["config_E"] = config_e(ctx)
     if args.only in ("", "C"):
         res["config_C"] = config_c(ctx, args.reps)
     if args.only in ("", "D"):
