@@ -715,6 +715,41 @@ constexpr int DESC_THREADS = UVO_DESC_THREADS;
 constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows are streamed in chunks
 constexpr int PATCH_STRIDE = 448;   // bytes per keypoint in SurfImage::patch (441 used)
 
+// INTER_AREA tables by window size.  The 21 AreaSpan entries, iscale and is_area_fast are functions of win_size alone
+// (fp64 divisions, ceil / floor); they are tabulated once per device by the same device code the kernel would run, so
+// a keypoint's prologue is a 600-byte load instead of a chain of fp64 divisions on 21 of the block's 256 threads.
+constexpr int SPAN_TAB_MAX = 1024;  // window sizes < SPAN_TAB_MAX are tabulated (the largest SURF window is ~740)
+struct SpanTable {
+  AreaSpan span[SPAN_TAB_MAX][21];
+  int iscale[SPAN_TAB_MAX];
+  int area_fast[SPAN_TAB_MAX];
+};
+__global__ void k_span_table(SpanTable* tab) {
+  const int win = blockIdx.x, d = threadIdx.x;
+  if (win < 21 || d >= 21) return;
+  const double inv_scale = (double)21 / win;
+  const double scale = 1. / inv_scale;
+  tab->span[win][d] = area_span(d, win, scale);
+  if (d == 0) {
+    const int isc = __double2int_rn(scale);
+    tab->iscale[win] = isc;
+    tab->area_fast[win] = fabs(scale - isc) < DBL_EPSILON;
+  }
+}
+static SpanTable* g_span_tab[64] = {};
+static const SpanTable* span_table(Ctx& c) {
+  if (c.device >= 64) return nullptr;
+  if (!g_span_tab[c.device]) {
+    SpanTable* t = nullptr;
+    UVO_CUDA(cudaMalloc(&t, sizeof(SpanTable)));  // lives as long as the process, like the constant tables
+    k_span_table<<<SPAN_TAB_MAX, 32, 0, c.stream>>>(t);
+    UVO_CUDA(cudaGetLastError());
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    g_span_tab[c.device] = t;
+  }
+  return g_span_tab[c.device];
+}
+
 // K7 runs as two kernels.  k_surf_patch (one block per keypoint, dynamic queue) does the wide part: (orientation,)
 // window extraction and the INTER_AREA resize to the 21x21 u8 patch, which it writes to global memory.
 // k_surf_vector (one warp per keypoint) does the narrow part: Haar gradients, 4x4x4 sums, L2 normalisation.  Keeping
@@ -723,7 +758,8 @@ constexpr int PATCH_STRIDE = 448;   // bytes per keypoint in SurfImage::patch (4
 #define UVO_DESC_MINB 4
 #endif
 __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(const __grid_constant__ SurfGeom g,
-                                                             const __grid_constant__ SurfBatch b, int upright) {
+                                                             const __grid_constant__ SurfBatch b, int upright,
+                                                             const SpanTable* __restrict__ tab) {
   __shared__ int s_patch[441];
   __shared__ AreaSpan s_span[21];
   __shared__ float s_buf[DESC_BUF_ROWS * 21];
@@ -874,13 +910,21 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
     // ---- resize(win -> 21x21, INTER_AREA) ----
     // scale / iscale / is_area_fast exactly as cv::resize derives them (fp64); only 21 threads need the divisions
     if (tid < 21) {
-      const double inv_scale = (double)21 / win_size;
-      const double scale = 1. / inv_scale;
-      s_span[tid] = area_span(tid, win_size, scale);  // same table for rows and columns (square window)
-      if (tid == 0) {
-        const int isc = __double2int_rn(scale);
-        s_iscale = isc;
-        s_area_fast = fabs(scale - isc) < DBL_EPSILON;
+      if (tab && win_size < SPAN_TAB_MAX) {
+        s_span[tid] = tab->span[win_size][tid];
+        if (tid == 0) {
+          s_iscale = tab->iscale[win_size];
+          s_area_fast = tab->area_fast[win_size];
+        }
+      } else {
+        const double inv_scale = (double)21 / win_size;
+        const double scale = 1. / inv_scale;
+        s_span[tid] = area_span(tid, win_size, scale);  // same table for rows and columns (square window)
+        if (tid == 0) {
+          const int isc = __double2int_rn(scale);
+          s_iscale = isc;
+          s_area_fast = fabs(scale - isc) < DBL_EPSILON;
+        }
       }
     }
     __syncthreads();
@@ -1123,9 +1167,10 @@ __global__ void __launch_bounds__(VEC_WARPS * 32) k_surf_vector(const __grid_con
 
 void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright) {
   upload_tables(c);
+  const SpanTable* tab = span_table(c);
   const int blocks = std::min(capacity, 8 * c.sm_count);
   UVO_KERNEL(c, "k_surf_patch");
-  k_surf_patch<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright);
+  k_surf_patch<<<dim3(blocks, b.n_img), DESC_THREADS, 0, c.stream>>>(g, b, upright, tab);
   UVO_LAUNCH_CHECK(c);
   const int vblocks = std::min(div_up(capacity, VEC_WARPS), 4 * c.sm_count);
   UVO_KERNEL(c, "k_surf_vector");
