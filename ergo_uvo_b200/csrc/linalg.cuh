@@ -10,7 +10,11 @@ namespace uvo {
 // A: m x n row-major, m,n <= MAXD.  A = U diag(w) Vt, w descending.  U: m x n (may be null), Vt: n x n.
 // CM / CN: compile-time copies of m / n (0 = run-time).  With both known the k-loops unroll, so the loads of a pair's two
 // rows are issued back to back instead of one per trip of a serial loop; the arithmetic and its order are unchanged.
-template <int MAXD, int CM = 0, int CN = 0>
+// NULL_FLOOR: additionally leave a pair alone when |p| <= 16 eps^2 max|column|^2, i.e. when both columns are numerically
+// null.  A rank-deficient input (the 5 x 9 epipolar system: 4 null columns) otherwise keeps rotating round-off among
+// its null columns for all 30 sweeps -- the relative test never fires there -- without changing the null space they
+// span.  Off (the OpenCV rule alone) wherever the oracle restates the same SVD bit for bit.
+template <int MAXD, int CM = 0, int CN = 0, bool NULL_FLOOR = false>
 __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, double* U, double* Vt) {
   const int m = CM ? CM : m_rt, n = CN ? CN : n_rt;
   double At[MAXD * MAXD], V[MAXD * MAXD], W[MAXD];
@@ -23,6 +27,11 @@ __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, doubl
     for (int k = 0; k < n; k++) V[i * n + k] = (k == i) ? 1.0 : 0.0;
   }
   const double eps = DBL_EPSILON * 10;
+  double null_floor = 0;
+  if (NULL_FLOOR) {
+    for (int i = 0; i < n; i++) null_floor = fmax(null_floor, W[i]);
+    null_floor *= 16 * DBL_EPSILON * DBL_EPSILON;
+  }
   const int max_iter = m > 30 ? m : 30;
   for (int iter = 0; iter < max_iter; iter++) {
     bool changed = false;
@@ -34,6 +43,7 @@ __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, doubl
 #pragma unroll
         for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
+        if (NULL_FLOOR && fabs(p) <= null_floor) continue;
         p *= 2;
         const double beta = a - b, gamma = hypot(p, beta);
         double c, s;

@@ -155,7 +155,26 @@ __global__ void __launch_bounds__(32) k_tv_hyp(const __grid_constant__ RobustArg
     a.n_models[h] = ok ? 1 : 0;
     if (ok)
       for (int k = 0; k < 9; k++) a.models[(size_t)h * 9 + k] = H[k];
-  } else {
+  }
+}
+
+// Nister 5-point hypotheses: one hypothesis per group of TVE_GL lanes.  Lane 0 builds the constraint polynomial
+// (null space of the 5 x 9 system, the ten cubic constraints, Gauss-Jordan, det B(z)); the ten roots are then iterated
+// one per lane, and each real root is turned into its essential matrix on its own lane; models are stored in root
+// order, as the one-thread loop did.
+constexpr int TVE_GL = 16;
+constexpr int TVE_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(TVE_GL* TVE_PER_BLOCK) k_tv_hyp_e(const __grid_constant__ RobustArgs a) {
+  __shared__ double s_EE[TVE_PER_BLOCK][36], s_B[TVE_PER_BLOCK][3][13], s_c11[TVE_PER_BLOCK][11];
+  __shared__ Cx s_roots[TVE_PER_BLOCK][10];
+  __shared__ int s_ok[TVE_PER_BLOCK];
+  const int g = threadIdx.x / TVE_GL, gl = threadIdx.x % TVE_GL;
+  const int h = blockIdx.x * TVE_PER_BLOCK + g;
+  if (h >= a.ctl[0]) return;  // whole group
+  const int lane = threadIdx.x & 31, gbase = lane & ~(TVE_GL - 1);
+  const unsigned gmask = ((1u << TVE_GL) - 1u) << gbase;
+  if (gl == 0) {
     double q1[10], q2[10];
     for (int k = 0; k < 5; k++) {
       const int i = a.subsets[(size_t)h * 5 + k];
@@ -164,8 +183,23 @@ __global__ void __launch_bounds__(32) k_tv_hyp(const __grid_constant__ RobustArg
       q2[2 * k] = a.q[4 * i + 2];
       q2[2 * k + 1] = a.q[4 * i + 3];
     }
-    a.n_models[h] = five_point(q1, q2, a.models + (size_t)h * TV_MAX_MODELS * 9);
+    s_ok[g] = five_point_poly(q1, q2, s_EE[g], s_B[g], s_c11[g]) ? 1 : 0;
   }
+  __syncwarp(gmask);
+  if (!s_ok[g]) {
+    if (gl == 0) a.n_models[h] = 0;
+    return;
+  }
+  const int nr = solve_poly_dk_group(s_c11[g], 10, s_roots[g], gl, gmask);
+  double Ev[9];
+  const bool have = gl < nr && five_point_model(s_roots[g][gl], s_B[g], s_EE[g], Ev);
+  const unsigned bal = (__ballot_sync(gmask, have) >> gbase) & ((1u << TVE_GL) - 1u);
+  if (have) {
+    const int slot = __popc(bal & ((1u << gl) - 1u));
+    double* out = a.models + ((size_t)h * TV_MAX_MODELS + slot) * 9;
+    for (int e = 0; e < 9; e++) out[e] = Ev[e];
+  }
+  if (gl == 0) a.n_models[h] = __popc(bal);
 }
 
 // ------------------------------------------------------------------------------------------------ scoring
@@ -753,8 +787,13 @@ void launch_robust(Ctx& c, const RobustArgs& a) {
   UVO_KERNEL(c, "k_tv_subsets");
   k_tv_subsets<<<1, 32, 0, c.stream>>>(a, rng);
   UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_tv_hyp");
-  k_tv_hyp<<<div_up(a.iters, 32), 32, 0, c.stream>>>(a);
+  if (a.kind == TV_ESSENTIAL) {
+    UVO_KERNEL(c, "k_tv_hyp_e");
+    k_tv_hyp_e<<<div_up(a.iters, TVE_PER_BLOCK), TVE_GL * TVE_PER_BLOCK, 0, c.stream>>>(a);
+  } else {
+    UVO_KERNEL(c, "k_tv_hyp");
+    k_tv_hyp<<<div_up(a.iters, 32), 32, 0, c.stream>>>(a);
+  }
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_tv_score");
   k_tv_score<<<dim3(a.iters, mph), 256, 0, c.stream>>>(a);

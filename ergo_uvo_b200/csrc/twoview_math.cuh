@@ -255,6 +255,55 @@ __device__ int solve_poly_dk(const double* coeffs, int n, Cx* roots) {
   return n;
 }
 
+// The same iteration with one root per lane of a group (`roots` in shared memory, `gl` = lane in the group, every lane
+// of the group calls).  All roots of a sweep are updated from the previous sweep's values (the simultaneous
+// Weierstrass form; cv::solvePoly updates in place), which reaches the same fixed point: the roots agree with the
+// sequential iteration to rounding, and a sweep costs one root's latency instead of ten.  Polynomials with a
+// near-vanishing leading coefficient (a root at infinity) take hundreds of sweeps either way; that tail is why the
+// one-thread form spent 90 % of the 5-point kernel here.
+__device__ int solve_poly_dk_group(const double* coeffs, int n, Cx* roots, int gl, unsigned gmask) {
+  while (n > 0 && coeffs[n] == 0) n--;
+  if (n <= 0) return 0;
+  if (gl == 0) {
+    Cx p{1, 0};
+    const Cx r{1, 1};
+    for (int i = 0; i < n; i++) {
+      roots[i] = p;
+      p = cmul(p, r);
+    }
+  }
+  __syncwarp(gmask);
+  for (int iter = 0; iter < 600; iter++) {
+    Cx p{0, 0}, num{0, 0};
+    if (gl < n) {
+      p = roots[gl];
+      num = Cx{coeffs[n], 0};
+      Cx den{coeffs[n], 0};
+      for (int j = 0; j < n; j++) {
+        num = cmul(num, p);
+        num.re += coeffs[n - j - 1];
+        if (j != gl) {
+          const Cx d = csub(p, roots[j]);
+          if (d.re != 0 || d.im != 0) den = cmul(den, d);
+        }
+      }
+      num = cdiv(num, den);
+    }
+    double diff = gl < n ? fmax(fabs(num.re), fabs(num.im)) : 0.0;
+    double scale = gl < n ? fmax(fabs(p.re), fabs(p.im)) : 0.0;
+    __syncwarp(gmask);  // every lane has read the previous sweep's roots
+    if (gl < n) roots[gl] = csub(p, num);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) {
+      diff = fmax(diff, __shfl_xor_sync(gmask, diff, o));
+      scale = fmax(scale, __shfl_xor_sync(gmask, scale, o));
+    }
+    __syncwarp(gmask);
+    if (!(diff > 1e-15 * fmax(scale, 1e-3))) break;
+  }
+  return n;
+}
+
 // p (degree da) * q (degree db) -> out (degree da + db); arrays indexed by power (lowest first)
 __device__ __forceinline__ void poly_mul(const double* p, int da, const double* q, int db, double* out) {
   for (int i = 0; i <= da + db; i++) out[i] = 0;
@@ -262,9 +311,10 @@ __device__ __forceinline__ void poly_mul(const double* p, int da, const double* 
     for (int j = 0; j <= db; j++) out[i + j] += p[i] * q[j];
 }
 
-// EMEstimatorCallback::runKernel: q1, q2 = 5 normalised correspondences (x, y); E_out: up to 10 row-major 3 x 3
-// matrices of unit Frobenius norm.  Returns the number of models.
-__device__ int five_point(const double* q1, const double* q2, double* E_out) {
+// EMEstimatorCallback::runKernel, first half: q1, q2 = 5 normalised correspondences (x, y) -> the null-space basis EE
+// (4 x 9), the 3 x 13 matrix B(z) and the degree-10 determinant polynomial c11 (lowest power first).  Returns false
+// when the 10 x 10 elimination meets a vanishing pivot (no model).  One thread.
+__device__ bool five_point_poly(const double* q1, const double* q2, double* EE_out, double (*B)[13], double* c11) {
   // epipolar rows x2^T E x1 = 0 with E row-major
   double Q[45];
   for (int i = 0; i < 5; i++) {
@@ -273,8 +323,9 @@ __device__ int five_point(const double* q1, const double* q2, double* E_out) {
       for (int c = 0; c < 3; c++) Q[i * 9 + 3 * r + c] = a[r] * b[c];
   }
   double w9[9], Vt[81];
-  jacobi_svd<9>(Q, 5, 9, w9, nullptr, Vt);
+  jacobi_svd<9, 5, 9, true>(Q, 5, 9, w9, nullptr, Vt);
   const double* EE = Vt + 5 * 9;  // null-space basis E0..E3 (rows 5..8 of Vt)
+  for (int i = 0; i < 36; i++) EE_out[i] = EE[i];
   // linear forms of the nine entries
   double L[9][4];
   for (int e = 0; e < 9; e++)
@@ -320,7 +371,7 @@ __device__ int five_point(const double* q1, const double* q2, double* E_out) {
     int piv = col;
     for (int r = col + 1; r < 10; r++)
       if (fabs(A[r][col]) > fabs(A[piv][col])) piv = r;
-    if (fabs(A[piv][col]) < DBL_MIN) return 0;
+    if (fabs(A[piv][col]) < DBL_MIN) return false;
     if (piv != col)
       for (int c = 0; c < 20; c++) {
         const double t = A[col][c];
@@ -338,7 +389,6 @@ __device__ int five_point(const double* q1, const double* q2, double* E_out) {
   }
   // B (3 x 13): <x^2 z> - z <x^2>, <y^2 z> - z <y^2>, <x y z> - z <x y>; columns [x z3, x z2, x z, x | y z3 .. y |
   // z4, z3, z2, z, 1]
-  double B[3][13];
   for (int i = 0; i < 3; i++) {
     const double* r1 = A[2 * i + 4] + 10;
     const double* r2 = A[2 * i + 5] + 10;
@@ -366,7 +416,6 @@ __device__ int five_point(const double* q1, const double* q2, double* E_out) {
     P[i][0][4] = P[i][1][4] = 0;
     for (int k = 0; k < 5; k++) P[i][2][k] = B[i][12 - k];
   }
-  double c11[11];
   for (int k = 0; k < 11; k++) c11[k] = 0;
   {
     double m[8], t[11];
@@ -385,34 +434,34 @@ __device__ int five_point(const double* q1, const double* q2, double* E_out) {
     add_term(P[0][1], 3, P[1][0], P[2][2], 3, 4, P[2][0], P[1][2], -1.0);
     add_term(P[0][2], 4, P[1][0], P[2][1], 3, 3, P[1][1], P[2][0], 1.0);
   }
-  Cx roots[10];
-  const int nr = solve_poly_dk(c11, 10, roots);
-  int count = 0;
-  for (int i = 0; i < nr && count < 10; i++) {
-    if (fabs(roots[i].im) > 1e-10) continue;
-    const double z1 = roots[i].re, z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
-    double Bz[9];
-    for (int j = 0; j < 3; j++) {
-      const double* br = B[j];
-      Bz[3 * j + 0] = br[0] * z3 + br[1] * z2 + br[2] * z1 + br[3];
-      Bz[3 * j + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
-      Bz[3 * j + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
-    }
-    double w3[3], vt3[9];
-    jacobi_svd<3>(Bz, 3, 3, w3, nullptr, vt3);  // SVD::solveZ: right singular vector of the smallest singular value
-    const double* xy1 = vt3 + 6;
-    if (fabs(xy1[2]) < 1e-10) continue;
-    const double xs = xy1[0] / xy1[2], ys = xy1[1] / xy1[2];
-    double nrm = 0, Ev[9];
-    for (int e = 0; e < 9; e++) {
-      Ev[e] = EE[e] * xs + EE[9 + e] * ys + EE[18 + e] * z1 + EE[27 + e];
-      nrm += Ev[e] * Ev[e];
-    }
-    nrm = 1. / sqrt(nrm);
-    for (int e = 0; e < 9; e++) E_out[count * 9 + e] = Ev[e] * nrm;
-    count++;
+  return true;
+}
+
+// second half, per root z of det B(z): back substitution through the null vector of B(z) (SVD::solveZ) to one
+// essential matrix of unit Frobenius norm.  Returns false for complex roots and degenerate null vectors.
+__device__ bool five_point_model(Cx root, const double (*B)[13], const double* EE, double* Ev_out) {
+  if (fabs(root.im) > 1e-10) return false;
+  const double z1 = root.re, z2 = z1 * z1, z3 = z2 * z1, z4 = z3 * z1;
+  double Bz[9];
+  for (int j = 0; j < 3; j++) {
+    const double* br = B[j];
+    Bz[3 * j + 0] = br[0] * z3 + br[1] * z2 + br[2] * z1 + br[3];
+    Bz[3 * j + 1] = br[4] * z3 + br[5] * z2 + br[6] * z1 + br[7];
+    Bz[3 * j + 2] = br[8] * z4 + br[9] * z3 + br[10] * z2 + br[11] * z1 + br[12];
   }
-  return count;
+  double w3[3], vt3[9];
+  jacobi_svd<3>(Bz, 3, 3, w3, nullptr, vt3);  // SVD::solveZ: right singular vector of the smallest singular value
+  const double* xy1 = vt3 + 6;
+  if (fabs(xy1[2]) < 1e-10) return false;
+  const double xs = xy1[0] / xy1[2], ys = xy1[1] / xy1[2];
+  double nrm = 0, Ev[9];
+  for (int e = 0; e < 9; e++) {
+    Ev[e] = EE[e] * xs + EE[9 + e] * ys + EE[18 + e] * z1 + EE[27 + e];
+    nrm += Ev[e] * Ev[e];
+  }
+  nrm = 1. / sqrt(nrm);
+  for (int e = 0; e < 9; e++) Ev_out[e] = Ev[e] * nrm;
+  return true;
 }
 
 // EMEstimatorCallback::computeError for one normalised correspondence: f64 Sampson distance cast to f32
