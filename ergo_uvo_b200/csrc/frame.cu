@@ -311,10 +311,15 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   };
   mark(0);
   if (from_host) {
-    UVO_CUDA(cudaMemcpy2DAsync(L.src[0].get(), s->src_pitch, dL, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
-                               c.stream));
-    UVO_CUDA(cudaMemcpy2DAsync(L.src[1].get(), s->src_pitch, dR, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
-                               c.stream));
+    if (pitch == s->src_pitch) {  // contiguous on both sides: one flat copy per image
+      UVO_CUDA(cudaMemcpyAsync(L.src[0].get(), dL, pitch * s->h, cudaMemcpyHostToDevice, c.stream));
+      UVO_CUDA(cudaMemcpyAsync(L.src[1].get(), dR, pitch * s->h, cudaMemcpyHostToDevice, c.stream));
+    } else {
+      UVO_CUDA(cudaMemcpy2DAsync(L.src[0].get(), s->src_pitch, dL, pitch, (size_t)3 * s->w, s->h,
+                                 cudaMemcpyHostToDevice, c.stream));
+      UVO_CUDA(cudaMemcpy2DAsync(L.src[1].get(), s->src_pitch, dR, pitch, (size_t)3 * s->w, s->h,
+                                 cudaMemcpyHostToDevice, c.stream));
+    }
     dL = L.src[0].get();
     dR = L.src[1].get();
     pitch = s->src_pitch;

@@ -7,16 +7,32 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
+
+// rows [0, n) split over the host threads, like OpenCV's parallel_for_ over stripes: every output element is an
+// independent function of the inputs, so the result does not depend on the split
+template <class F>
+static void parallel_rows(int n, F f) {
+  const unsigned nt = std::max(1u, std::min({16u, std::thread::hardware_concurrency(), (unsigned)std::max(n / 16, 1)}));
+  if (nt == 1) {
+    f(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++) th.emplace_back([=] { f((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); });
+  for (auto& x : th) x.join();
+}
 
 static inline int round_half_even(double v) { return (int)std::nearbyint(v); }  // cvRound (default FE_TONEAREST)
 static inline uint8_t sat_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 // ---- cvtColor(COLOR_RGB2GRAY), u8: VO_utility.cpp:347 ; SURVEY C.1 ----
 extern "C" void orc_gray(const uint8_t* s, int w, int h, uint8_t* d) {
-  const size_t n = (size_t)w * h;
-  for (size_t i = 0; i < n; i++)
-    d[i] = (uint8_t)((9798 * s[3 * i] + 19235 * s[3 * i + 1] + 3735 * s[3 * i + 2] + 16384) >> 15);
+  parallel_rows(h, [=](int r0, int r1) {
+    for (size_t i = (size_t)r0 * w; i < (size_t)r1 * w; i++)
+      d[i] = (uint8_t)((9798 * s[3 * i] + 19235 * s[3 * i + 1] + 3735 * s[3 * i + 2] + 16384) >> 15);
+  });
 }
 
 // 3x3 inverse as cv::invert(DECOMP_LU) does for n==3 (cofactors * 1/det, in double).
@@ -43,7 +59,8 @@ extern "C" void orc_undistort_map(const double K[4], const double D[4], const do
   inv3x3(A, ir);
   const double fx = K[0], fy = K[1], u0 = K[2], v0 = K[3];
   const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3];
-  for (int i = 0; i < h; i++) {
+  parallel_rows(h, [=](int r0, int r1) {
+  for (int i = r0; i < r1; i++) {
     for (int j = 0; j < w; j++) {
       double _x = j * ir[0] + (i * ir[1] + ir[2]);
       double _y = j * ir[3] + (i * ir[4] + ir[5]);
@@ -65,13 +82,15 @@ extern "C" void orc_undistort_map(const double K[4], const double D[4], const do
       mfr[(size_t)i * w + j] = (uint16_t)(((iv & 31) << 5) | (iu & 31));
     }
   }
+  });
 }
 
 // ---- remap INTER_LINEAR fixed point, BORDER_CONSTANT 0: SURVEY C.3 ----
 // weights for fractions (fx,fy)/32 are exact: (32-fy)(32-fx)*32 etc. sum to 32768, so the table fix-up never fires.
 extern "C" void orc_remap_bilinear(const uint8_t* s, int w, int h, const int16_t* mxy, const uint16_t* mfr,
                                    uint8_t* d) {
-  for (int i = 0; i < h; i++)
+  parallel_rows(h, [=](int r0, int r1) {
+  for (int i = r0; i < r1; i++)
     for (int j = 0; j < w; j++) {
       size_t o = (size_t)i * w + j;
       int sx = mxy[2 * o], sy = mxy[2 * o + 1];
@@ -84,6 +103,7 @@ extern "C" void orc_remap_bilinear(const uint8_t* s, int w, int h, const int16_t
       int acc = px(sx, sy) * w00 + px(sx + 1, sy) * w01 + px(sx, sy + 1) * w10 + px(sx + 1, sy + 1) * w11;
       d[o] = sat_u8((acc + 16384) >> 15);
     }
+  });
 }
 
 extern "C" void orc_undistort(const uint8_t* g, int w, int h, const double K[4], const double D[4],
@@ -120,7 +140,9 @@ extern "C" void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, i
   }
   const float lut_scale = (float)255 / area;
   std::vector<uint8_t> lut((size_t)tx * ty * 256);
-  for (int t = 0; t < tx * ty; t++) {
+  uint8_t* lutp = lut.data();
+  parallel_rows(tx * ty, [=](int t0, int t1) {
+  for (int t = t0; t < t1; t++) {
     int tyi = t / tx, txi = t % tx;
     int hist[256];
     std::memset(hist, 0, sizeof(hist));
@@ -147,12 +169,15 @@ extern "C" void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, i
     for (int i = 0; i < 256; i++) {
       sum += hist[i];
       float v = (float)sum * lut_scale;
-      lut[(size_t)t * 256 + i] = sat_u8(round_half_even(v));
+      lutp[(size_t)t * 256 + i] = sat_u8(round_half_even(v));
     }
   }
+  });
   std::vector<uint8_t> out((size_t)w * h);
+  uint8_t* outp = out.data();
   const float inv_tw = 1.0f / tw, inv_th = 1.0f / th;
-  for (int y = 0; y < h; y++) {
+  parallel_rows(h, [=](int y0, int y1) {
+  for (int y = y0; y < y1; y++) {
     float tyf = y * inv_th - 0.5f;
     int ty1 = (int)std::floor(tyf), ty2 = ty1 + 1;
     float ya = tyf - ty1, ya1 = 1.0f - ya;
@@ -165,12 +190,13 @@ extern "C" void orc_clahe(const uint8_t* src, int w, int h, double clip_limit, i
       tx1 = std::max(tx1, 0);
       tx2 = std::min(tx2, tx - 1);
       int v = src[(size_t)y * w + x];
-      float a = lut[((size_t)ty1 * tx + tx1) * 256 + v], b = lut[((size_t)ty1 * tx + tx2) * 256 + v];
-      float c = lut[((size_t)ty2 * tx + tx1) * 256 + v], e = lut[((size_t)ty2 * tx + tx2) * 256 + v];
+      float a = lutp[((size_t)ty1 * tx + tx1) * 256 + v], b = lutp[((size_t)ty1 * tx + tx2) * 256 + v];
+      float c = lutp[((size_t)ty2 * tx + tx1) * 256 + v], e = lutp[((size_t)ty2 * tx + tx2) * 256 + v];
       float res = (a * xa1 + b * xa) * ya1 + (c * xa1 + e * xa) * ya;
-      out[(size_t)y * w + x] = sat_u8(round_half_even(res));
+      outp[(size_t)y * w + x] = sat_u8(round_half_even(res));
     }
   }
+  });
   std::memcpy(dst, out.data(), out.size());
 }
 
