@@ -309,6 +309,27 @@ int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t 
   });
 }
 
+// K6 alone (parity tap): SURF's final keypoint order on caller-provided keypoints
+int uvo_sort_keypoints(uvo_ctx* ctx, const uvo_keypoint* kps_in, int n, int capacity, uvo_keypoint* kps_out) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(n >= 0 && capacity >= std::max(n, 1) && (n == 0 || (kps_in && kps_out)), "uvo_sort_keypoints: bad argument");
+    if (n == 0) return;
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    FrontEnd& fe = ctx->fe;
+    fe.init(std::max(fe.w, 16), std::max(fe.h, 16), 1, capacity);
+    const int cap = fe.capacity;  // buffers (and the sort variant chosen) follow the front end's capacity
+    SurfBatch b = fe.batch(0, 1);
+    UVO_CUDA(cudaMemcpyAsync(b.im[0].raw, kps_in, sizeof(uvo_keypoint) * n, cudaMemcpyHostToDevice, c.stream));
+    const int counters[4] = {n, 0, 0, 0};
+    UVO_CUDA(cudaMemcpyAsync(b.im[0].counters, counters, sizeof(counters), cudaMemcpyHostToDevice, c.stream));
+    launch_surf_sort(c, b, cap);
+    UVO_CUDA(cudaMemcpyAsync(kps_out, b.im[0].kps, sizeof(uvo_keypoint) * n, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
 // ------------------------------------------------------------------------------------------------ K8
 struct HostGate {  // optional stereo gate of uvo_match_features_gated
   const uvo_keypoint* k1;

@@ -177,6 +177,13 @@ class Context:
                                               _p(desc), cap, C.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()
 
+    def sort_keypoints(self, keypoints, capacity=None):
+        """K6 parity tap: keypoints in SURF's final order (uvo_sort_keypoints)"""
+        k = np.ascontiguousarray(keypoints, dtype=KEYPOINT_DTYPE)
+        out = np.zeros(max(len(k), 1), KEYPOINT_DTYPE)
+        self._ck(self.lib.uvo_sort_keypoints(self.h, _p(k), len(k), int(capacity or max(len(k), 64)), _p(out)))
+        return out[:len(k)]
+
     # ------------------------------------------------------------------ VO_utility.h:109-110
     def match_features(self, keypoints1, keypoints2, descriptors1, descriptors2, with_points=False, gate=None):
         """5-arg overload returns matches; with_points=True is the 7-arg overload (also keypoints*_conv).

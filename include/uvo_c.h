@@ -158,6 +158,12 @@ UVO_API int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray_host, int widt
                                 const uvo_params* prm, uvo_keypoint* kps_host, float* desc_host, int capacity,
                                 int* count);
 
+/* Parity tap for K6: the total order SURF::detectAndCompute leaves its keypoints in (KeypointGreater: response desc,
+ * size desc, octave desc, y desc, x asc; identical keys keep their input order).  `capacity` >= n selects the device
+ * buffers' size and with it the sort variant (single-block bitonic sort up to 16 384, rank sort above). */
+UVO_API int uvo_sort_keypoints(uvo_ctx* ctx, const uvo_keypoint* kps_in_host, int n, int capacity,
+                               uvo_keypoint* kps_out_host);
+
 /* ---------------------------------------------------------------------------------------------------- K8 */
 /* void match_features(vector<KeyPoint>, vector<KeyPoint>, Mat d1, Mat d2, vector<DMatch>&) -- VO_utility.h:109-110,
  * VO_utility.cpp:515-573: BFMatcher(NORM_L2).knnMatch(k=2) + Lowe ratio.  Matches in query order. `dim` = 64. */

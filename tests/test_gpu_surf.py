@@ -75,3 +75,25 @@ def test_surf_oriented_matches_oracle(ctx, oracle):
     assert np.array_equal(k["angle"], ko["angle"])
     close = (np.abs(d - do).max(axis=1) <= 1e-4 * np.abs(do).max())
     assert close.mean() > 0.999
+
+
+@pytest.mark.parametrize("n,capacity", [(1, 64), (2, 64), (37, 64), (1000, 4096), (4097, 8192), (9000, 16384),
+                                        (3000, 20000)])
+def test_keypoint_sort_with_ties(ctx, n, capacity):
+    """K6 in isolation on adversarial input: responses quantised to a handful of values so that most of the order is
+    decided by the tie-breakers (size desc, octave desc, y desc, x asc), plus fully identical keypoints, which must
+    keep their input order.  capacity <= 16384 runs the single-block bitonic sort, above it the rank sort."""
+    import ergo_uvo_b200 as U
+    rs = np.random.RandomState(n)
+    k = np.zeros(n, U.KEYPOINT_DTYPE)
+    k["response"] = rs.randint(0, 6, n).astype(np.float32) * 1000 + 500
+    k["size"] = rs.choice([15, 21, 27, 30], n).astype(np.float32)
+    k["octave"] = rs.randint(0, 3, n)
+    k["y"] = rs.randint(0, 8, n).astype(np.float32)
+    k["x"] = rs.randint(0, 8, n).astype(np.float32)
+    k["class_id"] = np.arange(n)  # not part of the key: identifies the input position
+    k["angle"] = -1
+    got = ctx.sort_keypoints(k, capacity)
+    order = sorted(range(n), key=lambda i: (-k["response"][i], -k["size"][i], -k["octave"][i], -k["y"][i], k["x"][i], i))
+    assert np.array_equal(got["class_id"], np.array(order))
+    assert got.tobytes() == k[order].tobytes()
