@@ -417,7 +417,7 @@ def run_gpu(args):
                                    "frac": per_launch / sec / 1e12 / tf_sus}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
             n_cpu = 4
             spf, _ = cpu_frames(seq, thr, n_cpu, params=p)
             cpu = {"value": 1.0 / spf, "unit": "frames/s", "cores": min(16, os.cpu_count() or 1), "kind": "port",
