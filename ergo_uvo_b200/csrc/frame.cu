@@ -153,7 +153,6 @@ static const char* kStageNames[UVO_N_STAGES] = {"h2d",        "get_image",    "s
 struct Lane {
   cudaStream_t stream = nullptr;
   FrontEnd fe;
-  DevBuf<uint8_t> src[2];  // staging for host images
   DevBuf<uvo_keypoint> kL_as, kR_as;
   DevBuf<float> dL_as;
   DevBuf<FrameCtrl> ctrl;
@@ -191,6 +190,11 @@ struct uvo_stereo {
   DevBuf<uvo_stereo_result> d_result;  // ring
   PinnedBuf<uvo_stereo_result> h_result;
   cudaEvent_t ev_in = nullptr;  // caller's work on the ctx stream -> lanes
+  // host images: copied on a dedicated stream into a ring of staging pairs (one per result slot) so that the H2D of a
+  // new frame does not queue behind the previous frame of its lane; the lane waits on the slot's event
+  cudaStream_t copy_stream = nullptr;
+  DevBuf<uint8_t> stage[RING][2];
+  cudaEvent_t ev_copied[RING] = {};
   long frame_no = 0;
   std::deque<std::pair<int, cudaEvent_t>> pending;  // (slot, done event)
   cudaEvent_t ev[UVO_N_STAGES + 1] = {};
@@ -205,6 +209,9 @@ struct uvo_stereo {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
+    for (auto& e : ev_copied)
+      if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 
@@ -311,17 +318,23 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   };
   mark(0);
   if (from_host) {
+    uint8_t* stL = s->stage[slot][0].get();
+    uint8_t* stR = s->stage[slot][1].get();
+    // the caller's stream order still applies to the host buffers (ev_in), the lane's previous frame does not
+    UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
     if (pitch == s->src_pitch) {  // contiguous on both sides: one flat copy per image
-      UVO_CUDA(cudaMemcpyAsync(L.src[0].get(), dL, pitch * s->h, cudaMemcpyHostToDevice, c.stream));
-      UVO_CUDA(cudaMemcpyAsync(L.src[1].get(), dR, pitch * s->h, cudaMemcpyHostToDevice, c.stream));
+      UVO_CUDA(cudaMemcpyAsync(stL, dL, pitch * s->h, cudaMemcpyHostToDevice, s->copy_stream));
+      UVO_CUDA(cudaMemcpyAsync(stR, dR, pitch * s->h, cudaMemcpyHostToDevice, s->copy_stream));
     } else {
-      UVO_CUDA(cudaMemcpy2DAsync(L.src[0].get(), s->src_pitch, dL, pitch, (size_t)3 * s->w, s->h,
-                                 cudaMemcpyHostToDevice, c.stream));
-      UVO_CUDA(cudaMemcpy2DAsync(L.src[1].get(), s->src_pitch, dR, pitch, (size_t)3 * s->w, s->h,
-                                 cudaMemcpyHostToDevice, c.stream));
+      UVO_CUDA(cudaMemcpy2DAsync(stL, s->src_pitch, dL, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
+                                 s->copy_stream));
+      UVO_CUDA(cudaMemcpy2DAsync(stR, s->src_pitch, dR, pitch, (size_t)3 * s->w, s->h, cudaMemcpyHostToDevice,
+                                 s->copy_stream));
     }
-    dL = L.src[0].get();
-    dR = L.src[1].get();
+    UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
+    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_copied[slot], 0));
+    dL = stL;
+    dR = stR;
     pitch = s->src_pitch;
   }
   mark(1);
@@ -509,9 +522,16 @@ static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t
                 "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
     Ctx& c = s->ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
-    if (from_host)
-      for (int i = 0; i < 2; i++) s->lane[s->frame_no % uvo_stereo::N_LANES].src[i].ensure(s->src_pitch * s->h);
     const int slot = (int)(s->frame_no % uvo_stereo::RING);
+    if (from_host && !s->copy_stream) {
+      // first host frame: the copy stream and the whole staging ring at once (one allocation hiccup, not RING of
+      // them).  Slot k's previous user (frame_no - RING) has always been collected before it is reused.
+      UVO_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < uvo_stereo::RING; k++) {
+        for (int i = 0; i < 2; i++) s->stage[k][i].ensure(s->src_pitch * s->h);
+        UVO_CUDA(cudaEventCreateWithFlags(&s->ev_copied[k], cudaEventDisableTiming));
+      }
+    }
     stereo_enqueue(s, L, R, pitch, dt, slot, from_host);
   });
 }
