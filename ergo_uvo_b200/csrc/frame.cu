@@ -339,11 +339,15 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   }
   mark(1);
   // 1. get_image x2 (visual_odometry.h:542-543)
+  // (running the right image's preparation on a second stream beside the left one's was measured: -48 us of frame
+  // latency, but -9 % end-to-end throughput with 8 frames in flight -- the lanes already provide the overlap)
   L.fe.prep(c, 0, dL, pitch, s->cam[0], p.clahe, p.clip_limit);
+  L.fe.integral(c, 0);
   L.fe.prep(c, 1, dR, pitch, s->cam[1], p.clahe, p.clip_limit);
+  L.fe.integral(c, 1);
   mark(2);
   // 2. detect_features x2 (:548-549), both images batched through each kernel
-  L.fe.surf(c, 0, 2, p);
+  L.fe.surf(c, 0, 2, p, /*with_integral=*/false);
   const int* cL = L.fe.counters.get();
   const int* cR = L.fe.counters.get() + 4;
   UVO_KERNEL(c, "k_gate_features");

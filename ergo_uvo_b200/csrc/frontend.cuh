@@ -79,8 +79,12 @@ struct FrontEnd {
     }
   }
 
-  // SURF::detectAndCompute on images [first, first+count)
-  void surf(Ctx& c, int first, int count, const uvo_params& p) {
+  // integral image of slot `idx` (the first step of SURF::detectAndCompute)
+  void integral(Ctx& c, int idx) { launch_integral(c, gray[idx].get(), gpitch, w, h, sum[idx].get()); }
+
+  // SURF::detectAndCompute on images [first, first+count); `with_integral` = false when the caller already ran
+  // integral() for those slots (the stereo pipeline does, per image, on two streams)
+  void surf(Ctx& c, int first, int count, const uvo_params& p, bool with_integral = true) {
     UVO_REQUIRE(!p.surf_extended, "SURF extended (128-d) descriptors are not implemented");
     if (!geom_valid || geom_thr != (double)p.surf_min_hessian || geom_oct != p.surf_octaves ||
         geom_lay != p.surf_octave_layers) {
@@ -90,7 +94,8 @@ struct FrontEnd {
       geom_oct = p.surf_octaves;
       geom_lay = p.surf_octave_layers;
     }
-    for (int i = 0; i < count; i++) launch_integral(c, gray[first + i].get(), gpitch, w, h, sum[first + i].get());
+    if (with_integral)
+      for (int i = 0; i < count; i++) integral(c, first + i);
     SurfBatch b = batch(first, count);
     launch_surf_detect(c, geom, b, capacity);
     launch_surf_sort(c, b, capacity);

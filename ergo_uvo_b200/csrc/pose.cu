@@ -469,11 +469,10 @@ constexpr int REFIT_TILE = 64;
 __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_constant__ PnpArgs a) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
-  __shared__ double s_red[32 * 9], s_out[9];
-  __shared__ double s_cws[4][3], s_ci[9], s_ut[144], s_betas[3][4], s_ccs[4][3], s_R[9], s_t[3];
+  __shared__ double s_red[32 * 27], s_out[27];
+  __shared__ double s_cws[4][3], s_ci[9], s_ut[144], s_betas[3][4], s_ccs3[3][4][3], s_R3[3][9], s_t3[3][3], s_sign3[3];
   __shared__ double s_rows[REFIT_TILE][24];
   __shared__ double s_mtm[144], s_Vr[144], s_w[12], s_l[60], s_rho[6];
-  __shared__ double s_sign;
   const int tid = threadIdx.x;
   const int n = pnp_n(a);
   const int best_h = a.best[0];
@@ -574,68 +573,79 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     if (tid < 3) epnp_betas_which(s_l, s_rho, tid + 1, s_betas[tid]);
   }
   __syncthreads();
-  double best_err = 0, bestR[9], bestt[3];
-  for (int w = 0; w < 3; w++) {
-    if (tid == 0) {
-      epnp_ccs(s_betas[w], s_ut, s_ccs);
+  // the three beta candidates go through compute_R_and_t together: one pass over the inliers accumulates all three
+  // sums (the barycentric coordinates of a point are shared), the one-thread steps run on lanes 0..2 of warp 0.  Per
+  // candidate the operations and their order are those of a loop over the candidates.
+  if (tid < 3) {
+    const int w = tid;
+    epnp_ccs(s_betas[w], s_ut, s_ccs3[w]);
+    double al[4], pc[3];
+    point(0, pw, u, v);
+    epnp_alphas(pw, s_cws, s_ci, al);
+    epnp_pc(al, s_ccs3[w], 1.0, pc);
+    s_sign3[w] = pc[2] < 0.0 ? -1.0 : 1.0;  // solve_for_sign
+  }
+  __syncthreads();
+  double pc0[3][3];
+  {
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = tid; k < ni; k += blockDim.x) {
       double al[4], pc[3];
-      point(0, pw, u, v);
+      point(k, pw, u, v);
       epnp_alphas(pw, s_cws, s_ci, al);
-      epnp_pc(al, s_ccs, 1.0, pc);
-      s_sign = pc[2] < 0.0 ? -1.0 : 1.0;  // solve_for_sign
-    }
-    __syncthreads();
-    const double sign = s_sign;
-    double pc0[3];
-    {
-      double acc[3] = {0, 0, 0};
-      for (int k = tid; k < ni; k += blockDim.x) {
-        double al[4], pc[3];
-        point(k, pw, u, v);
-        epnp_alphas(pw, s_cws, s_ci, al);
-        epnp_pc(al, s_ccs, sign, pc);
-        for (int cc = 0; cc < 3; cc++) acc[cc] += pc[cc];
+#pragma unroll
+      for (int w = 0; w < 3; w++) {
+        epnp_pc(al, s_ccs3[w], s_sign3[w], pc);
+        for (int cc = 0; cc < 3; cc++) acc[3 * w + cc] += pc[cc];
       }
-      block_reduce_sum<3>(acc, s_red, s_out);
-      for (int cc = 0; cc < 3; cc++) pc0[cc] = s_out[cc] / ni;
     }
-    __syncthreads();
-    {
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int k = tid; k < ni; k += blockDim.x) {
-        double al[4], pc[3];
-        point(k, pw, u, v);
-        epnp_alphas(pw, s_cws, s_ci, al);
-        epnp_pc(al, s_ccs, sign, pc);
+    block_reduce_sum<9>(acc, s_red, s_out);
+    for (int w = 0; w < 3; w++)
+      for (int cc = 0; cc < 3; cc++) pc0[w][cc] = s_out[3 * w + cc] / ni;
+  }
+  __syncthreads();
+  {
+    double acc[27];
+    for (int i = 0; i < 27; i++) acc[i] = 0;
+    for (int k = tid; k < ni; k += blockDim.x) {
+      double al[4], pc[3];
+      point(k, pw, u, v);
+      epnp_alphas(pw, s_cws, s_ci, al);
+#pragma unroll
+      for (int w = 0; w < 3; w++) {
+        epnp_pc(al, s_ccs3[w], s_sign3[w], pc);
         for (int j = 0; j < 3; j++) {
-          acc[3 * j] += (pc[j] - pc0[j]) * (pw[0] - c0[0]);
-          acc[3 * j + 1] += (pc[j] - pc0[j]) * (pw[1] - c0[1]);
-          acc[3 * j + 2] += (pc[j] - pc0[j]) * (pw[2] - c0[2]);
+          acc[9 * w + 3 * j] += (pc[j] - pc0[w][j]) * (pw[0] - c0[0]);
+          acc[9 * w + 3 * j + 1] += (pc[j] - pc0[w][j]) * (pw[1] - c0[1]);
+          acc[9 * w + 3 * j + 2] += (pc[j] - pc0[w][j]) * (pw[2] - c0[2]);
         }
       }
-      block_reduce_sum<9>(acc, s_red, s_out);
     }
-    if (tid == 0) {
-      double abt[9];
-      for (int i = 0; i < 9; i++) abt[i] = s_out[i];
-      epnp_rt_from_abt(abt, pc0, c0, s_R, s_t);
+    block_reduce_sum<27>(acc, s_red, s_out);
+  }
+  if (tid < 3) {
+    double abt[9];
+    for (int i = 0; i < 9; i++) abt[i] = s_out[9 * tid + i];
+    epnp_rt_from_abt(abt, pc0[tid], c0, s_R3[tid], s_t3[tid]);
+  }
+  __syncthreads();
+  {
+    double acc[3] = {0, 0, 0};
+    for (int k = tid; k < ni; k += blockDim.x) {
+      point(k, pw, u, v);
+#pragma unroll
+      for (int w = 0; w < 3; w++) acc[w] += epnp_reproj1(s_R3[w], s_t3[w], pw, u, v, cam);
     }
-    __syncthreads();
-    {
-      double acc[1] = {0};
-      for (int k = tid; k < ni; k += blockDim.x) {
-        point(k, pw, u, v);
-        acc[0] += epnp_reproj1(s_R, s_t, pw, u, v, cam);
-      }
-      block_reduce_sum<1>(acc, s_red, s_out);
-    }
-    const double err = s_out[0] / ni;
+    block_reduce_sum<3>(acc, s_red, s_out);
+  }
+  double best_err = 0, bestR[9], bestt[3];
+  for (int w = 0; w < 3; w++) {
+    const double err = s_out[w] / ni;
     if (w == 0 || err < best_err) {
       best_err = err;
-      for (int i = 0; i < 9; i++) bestR[i] = s_R[i];
-      for (int i = 0; i < 3; i++) bestt[i] = s_t[i];
+      for (int i = 0; i < 9; i++) bestR[i] = s_R3[w][i];
+      for (int i = 0; i < 3; i++) bestt[i] = s_t3[w][i];
     }
-    __syncthreads();
   }
   if (tid == 0) {
     double rvec[3];
