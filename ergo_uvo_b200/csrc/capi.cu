@@ -204,6 +204,24 @@ int uvo_get_image(uvo_ctx* ctx, const uint8_t* src3, int w, int h, size_t spitch
   });
 }
 
+int uvo_demosaic_bggr2bgr(uvo_ctx* ctx, const uint8_t* bayer, int w, int h, size_t spitch, uint8_t* bgr, size_t dpitch) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(bayer && bgr && w >= 3 && h >= 3 && spitch >= (size_t)w && dpitch >= (size_t)3 * w,
+                "uvo_demosaic_bggr2bgr: bad argument (needs w, h >= 3)");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    StageScratch& s = ctx->scratch;
+    const size_t sp = ((size_t)w + 15) & ~(size_t)15, dp = ((size_t)3 * w + 15) & ~(size_t)15;
+    s.bytes_a.ensure(sp * h);
+    s.src3.ensure(dp * h);
+    UVO_CUDA(cudaMemcpy2DAsync(s.bytes_a.get(), sp, bayer, spitch, w, h, cudaMemcpyHostToDevice, c.stream));
+    launch_demosaic_bggr(c, s.bytes_a.get(), sp, w, h, s.src3.get(), dp);
+    UVO_CUDA(cudaMemcpy2DAsync(bgr, dpitch, s.src3.get(), dp, (size_t)3 * w, h, cudaMemcpyDeviceToHost, c.stream));
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
 int uvo_resize_area(uvo_ctx* ctx, const uint8_t* src, int sw, int sh, size_t spitch, int channels, uint8_t* dst, int dw,
                     int dh, size_t dpitch) {
   if (!ctx) return UVO_ERR_INVALID;

@@ -194,6 +194,8 @@ struct uvo_stereo {
   // new frame does not queue behind the previous frame of its lane; the lane waits on the slot's event
   cudaStream_t copy_stream = nullptr;
   DevBuf<uint8_t> stage[RING][2];
+  DevBuf<uint8_t> stage_bayer[RING][2];  // 1-channel staging of uvo_stereo_enqueue_host_bayer (allocated on first use)
+  size_t bayer_pitch = 0;
   cudaEvent_t ev_copied[RING] = {};
   long frame_no = 0;
   std::deque<std::pair<int, cudaEvent_t>> pending;  // (slot, done event)
@@ -290,8 +292,11 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
 
 // enqueue every kernel of one frame on its lane's stream.  Images: device pointers (host == nullptr) or pinned/pageable
 // host pointers that are first copied into the lane's staging buffers on the same stream.
+enum { SRC_DEVICE = 0, SRC_HOST_BGR = 1, SRC_HOST_BAYER = 2 };
+
 static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt, int slot,
-                           bool from_host) {
+                           int src_mode) {
+  const bool from_host = src_mode != SRC_DEVICE;
   Ctx& c = s->ctx->c;
   const uvo_params& p = s->prm;
   const int cap = s->cap;
@@ -317,7 +322,21 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     if (s->timing) UVO_CUDA(cudaEventRecord(s->ev[i], c.stream));
   };
   mark(0);
-  if (from_host) {
+  if (src_mode == SRC_HOST_BAYER) {
+    // 1-channel bayer images: a third of the bytes over PCIe, demosaiced on the lane's stream into the slot's staging pair
+    UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
+    for (int i = 0; i < 2; i++)
+      UVO_CUDA(cudaMemcpy2DAsync(s->stage_bayer[slot][i].get(), s->bayer_pitch, i == 0 ? dL : dR, pitch, s->w, s->h,
+                                 cudaMemcpyHostToDevice, s->copy_stream));
+    UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
+    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_copied[slot], 0));
+    for (int i = 0; i < 2; i++)
+      launch_demosaic_bggr(c, s->stage_bayer[slot][i].get(), s->bayer_pitch, s->w, s->h, s->stage[slot][i].get(),
+                           s->src_pitch);
+    dL = s->stage[slot][0].get();
+    dR = s->stage[slot][1].get();
+    pitch = s->src_pitch;
+  } else if (from_host) {
     uint8_t* stL = s->stage[slot][0].get();
     uint8_t* stR = s->stage[slot][1].get();
     // the caller's stream order still applies to the host buffers (ev_in), the lane's previous frame does not
@@ -518,10 +537,13 @@ void uvo_stereo_destroy(uvo_stereo* s) {
 }
 
 static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t* R, size_t pitch, double dt,
-                                  bool from_host) {
+                                  int src_mode) {
   if (!s) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
-    UVO_REQUIRE(L && R && pitch >= (size_t)3 * s->w && dt != 0.0, "uvo_stereo_enqueue: bad argument");
+    const bool from_host = src_mode != SRC_DEVICE;
+    UVO_REQUIRE(L && R && pitch >= (size_t)(src_mode == SRC_HOST_BAYER ? 1 : 3) * s->w && dt != 0.0,
+                "uvo_stereo_enqueue: bad argument");
+    UVO_REQUIRE(src_mode != SRC_HOST_BAYER || (s->w >= 3 && s->h >= 3), "bayer input needs w, h >= 3");
     UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING,
                 "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
     Ctx& c = s->ctx->c;
@@ -536,16 +558,25 @@ static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t
         UVO_CUDA(cudaEventCreateWithFlags(&s->ev_copied[k], cudaEventDisableTiming));
       }
     }
-    stereo_enqueue(s, L, R, pitch, dt, slot, from_host);
+    if (src_mode == SRC_HOST_BAYER && !s->bayer_pitch) {
+      s->bayer_pitch = ((size_t)s->w + 15) & ~(size_t)15;
+      for (int k = 0; k < uvo_stereo::RING; k++)
+        for (int i = 0; i < 2; i++) s->stage_bayer[k][i].ensure(s->bayer_pitch * s->h);
+    }
+    stereo_enqueue(s, L, R, pitch, dt, slot, src_mode);
   });
 }
 
 int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt) {
-  return stereo_enqueue_checked(s, dL, dR, pitch, dt, false);
+  return stereo_enqueue_checked(s, dL, dR, pitch, dt, SRC_DEVICE);
 }
 
 int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3, const uint8_t* right3, size_t pitch, double dt) {
-  return stereo_enqueue_checked(s, left3, right3, pitch, dt, true);
+  return stereo_enqueue_checked(s, left3, right3, pitch, dt, SRC_HOST_BGR);
+}
+
+int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1, const uint8_t* right1, size_t pitch, double dt) {
+  return stereo_enqueue_checked(s, left1, right1, pitch, dt, SRC_HOST_BAYER);
 }
 
 int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out) {
@@ -570,7 +601,7 @@ static int stereo_frame_sync(uvo_stereo* s, const uint8_t* L, const uint8_t* R, 
     return UVO_ERR_INVALID;
   }
   s->timing = true;
-  int rc = stereo_enqueue_checked(s, L, R, pitch, dt, from_host);
+  int rc = stereo_enqueue_checked(s, L, R, pitch, dt, from_host ? SRC_HOST_BGR : SRC_DEVICE);
   s->timing = false;
   if (rc != UVO_OK) return rc;
   rc = uvo_stereo_collect(s, out);

@@ -95,6 +95,51 @@ UndistortParams make_undistort_params(const uvo_camera& cam) {
   return P;
 }
 
+// ------------------------------------------------------------------------------------------------ Bayer demosaic
+// cvtColor(COLOR_BayerBGGR2BGR) as from_ros_to_cv_image applies it to bayer-format camera messages (reference
+// math_utility.cpp:161-164): OpenCV's bilinear demosaic -- rounded means of the 2 or 4 nearest samples of a colour at
+// the interior pixels, first / last column and row copied from their neighbours.  One thread per 4 output pixels;
+// the 3 x 6 neighbourhood is read through L1.  Bytes: read P, write 3P.
+__global__ void __launch_bounds__(256) k_demosaic_bggr(const uint8_t* __restrict__ src, size_t spitch, int w, int h,
+                                                       uint8_t* __restrict__ dst, size_t dpitch) {
+  const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x0 >= w || y >= h) return;
+  const int yc = min(max(y, 1), h - 2);
+  const uint8_t* r0 = src + (size_t)(yc - 1) * spitch;
+  const uint8_t* r1 = src + (size_t)yc * spitch;
+  const uint8_t* r2 = src + (size_t)(yc + 1) * spitch;
+  const bool ey = (yc & 1) == 0;
+  uint8_t* o = dst + (size_t)y * dpitch + 3 * x0;
+  for (int k = 0; k < 4 && x0 + k < w; k++) {
+    const int xc = min(max(x0 + k, 1), w - 2);
+    const int a = r0[xc - 1], b = r0[xc], c = r0[xc + 1], d = r1[xc - 1], v = r1[xc], e = r1[xc + 1], f = r2[xc - 1],
+              g = r2[xc], i = r2[xc + 1];
+    const int cross = (b + g + d + e + 2) >> 2, diag = (a + c + f + i + 2) >> 2, hor = (d + e + 1) >> 1,
+              ver = (b + g + 1) >> 1;
+    const bool ex = (xc & 1) == 0;
+    int B, G, R;
+    if (ey == ex) {  // blue (even, even) or red (odd, odd) site
+      G = cross;
+      B = ey ? v : diag;
+      R = ey ? diag : v;
+    } else {  // green site: blue row (even y) or red row
+      G = v;
+      B = ey ? hor : ver;
+      R = ey ? ver : hor;
+    }
+    o[3 * k] = (uint8_t)B;
+    o[3 * k + 1] = (uint8_t)G;
+    o[3 * k + 2] = (uint8_t)R;
+  }
+}
+
+void launch_demosaic_bggr(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, uint8_t* d_dst3, size_t dpitch) {
+  dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8));
+  UVO_KERNEL(c, "k_demosaic_bggr");
+  k_demosaic_bggr<<<grid, block, 0, c.stream>>>(d_src, spitch, w, h, d_dst3, dpitch);
+  UVO_LAUNCH_CHECK(c);
+}
+
 // ------------------------------------------------------------------------------------------------ K2 CLAHE
 __device__ __forceinline__ int reflect101(int p, int len) {
   if (len == 1) return 0;

@@ -22,6 +22,8 @@ ClaheGeom make_clahe_geom(int w, int h, double clip_limit, int tiles_x, int tile
 
 void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, int h, const UndistortParams& P,
                            uint8_t* d_dst, size_t dpitch);
+// cvtColor(COLOR_BayerBGGR2BGR): 1-channel bayer (w, h >= 3) -> 3-channel interleaved BGR
+void launch_demosaic_bggr(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, uint8_t* d_dst3, size_t dpitch);
 // d_hist: tiles*256 u32 scratch, d_lut: tiles*256 u8 scratch; src and dst may alias
 void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, unsigned int* d_hist,
                   uint8_t* d_lut, uint8_t* d_dst, size_t dpitch);

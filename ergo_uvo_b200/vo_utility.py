@@ -133,6 +133,15 @@ class Context:
                                         C.c_size_t(w)))
         return out
 
+    def demosaic_bggr2bgr(self, bayer):
+        """cv::cvtColor(bayer, COLOR_BayerBGGR2BGR) as from_ros_to_cv_image applies it (math_utility.cpp:161-164)"""
+        b = np.ascontiguousarray(bayer, np.uint8)
+        h, w = b.shape
+        out = np.empty((h, w, 3), np.uint8)
+        self._ck(self.lib.uvo_demosaic_bggr2bgr(self.h, _p(b), w, h, C.c_size_t(b.strides[0]), _p(out),
+                                                C.c_size_t(out.strides[0])))
+        return out
+
     def resize_area(self, img, dw, dh):
         """cv::resize(img, (dw, dh), interpolation=INTER_AREA), u8, 1 or 3 channels"""
         img = np.ascontiguousarray(img, np.uint8)
@@ -402,6 +411,11 @@ class StereoVO:
         """host (pinned) image pointers; the H2D copies are enqueued with the frame"""
         self.ctx._ck(self.lib.uvo_stereo_enqueue_host(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
                                                       C.c_size_t(pitch), C.c_double(dt)))
+
+    def enqueue_host_bayer(self, left_ptr, right_ptr, pitch, dt):
+        """host pointers to 1-channel BGGR bayer images (demosaiced on the device, uvo_stereo_enqueue_host_bayer)"""
+        self.ctx._ck(self.lib.uvo_stereo_enqueue_host_bayer(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                                            C.c_size_t(pitch), C.c_double(dt)))
 
     def max_in_flight(self):
         return int(self.lib.uvo_stereo_max_in_flight())

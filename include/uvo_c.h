@@ -132,6 +132,14 @@ UVO_API int uvo_optimal_new_camera_matrix(const double K[9], const double D[4], 
 UVO_API int uvo_resize_camera_matrix(int original_width, int original_height, int desired_width, double K_inout[9],
                                      const double D[4], double newK[9], int* out_width, int* out_height);
 
+/* ---------------------------------------------------------------------------------------------------- ingest */
+/* cvtColor(image, image, COLOR_BayerBGGR2BGR) -- the demosaic from_ros_to_cv_image applies to bayer-format camera
+ * messages (math_utility.h:27, math_utility.cpp:161-164), bit-exact with OpenCV's bilinear demosaic.  bayer: 1-channel
+ * u8 (w, h >= 3); bgr: 3-channel interleaved u8.  The stereo handle can take bayer images directly
+ * (uvo_stereo_enqueue_host_bayer), which cuts the host-to-device traffic of a frame to a third. */
+UVO_API int uvo_demosaic_bggr2bgr(uvo_ctx* ctx, const uint8_t* bayer_host, int width, int height, size_t src_pitch,
+                                  uint8_t* bgr_host, size_t dst_pitch);
+
 /* ---------------------------------------------------------------------------------------------------- K1-K3 */
 /* Mat get_image(const Mat&, const Mat&, const Mat&, const Mat&)  -- VO_utility.h:105, VO_utility.cpp:337-379.
  * Native-size branch: cvtColor(RGB2GRAY) + undistort + optional CLAHE(8x8).  src is 3-channel interleaved u8. */
@@ -282,6 +290,10 @@ UVO_API int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* left3_dev, c
                                       size_t pitch, double dt);
 UVO_API int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3_host, const uint8_t* right3_host,
                                     size_t pitch, double dt);
+/* same with 1-channel BGGR bayer images (pitch >= width): demosaiced on the device before get_image, as the node's
+ * image callback does on the CPU (visual_odometry.h:88-91 -> from_ros_to_cv_image) */
+UVO_API int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1_host, const uint8_t* right1_host,
+                                          size_t pitch, double dt);
 UVO_API int uvo_stereo_max_in_flight(void);
 UVO_API int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out);
 /* Debug/parity taps of the last frame (device -> host copies of intermediate products). */

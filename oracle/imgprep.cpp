@@ -208,6 +208,34 @@ extern "C" void orc_get_image(const uint8_t* src3, int w, int h, const double K[
   if (clahe) orc_clahe(dst, w, h, clip_limit, 8, 8, dst);
 }
 
+// ---- cvtColor(COLOR_BayerBGGR2BGR), u8 (from_ros_to_cv_image, math_utility.cpp:161-164): OpenCV's bilinear demosaic.
+// Interior pixels (1 <= y <= h-2, 1 <= x <= w-2): the missing colours are rounded means of the 2 or 4 nearest samples
+// of that colour; the first / last column then copy their neighbour column and the first / last row their neighbour
+// row.  Pinned bit-exact against cv2 4.13 (tests/test_oracle_imgprep.py).  Sites: (even, even) blue, (odd, odd) red.
+extern "C" void orc_bayer_bggr2bgr(const uint8_t* s, int w, int h, uint8_t* d) {
+  auto at = [&](int y, int x) -> int { return s[(size_t)y * w + x]; };
+  parallel_rows(h, [=](int r0, int r1) {
+    for (int y = r0; y < r1; y++)
+      for (int x = 0; x < w; x++) {
+        const int yc = std::min(std::max(y, 1), h - 2), xc = std::min(std::max(x, 1), w - 2);
+        const int cross = (at(yc - 1, xc) + at(yc + 1, xc) + at(yc, xc - 1) + at(yc, xc + 1) + 2) >> 2;
+        const int diag = (at(yc - 1, xc - 1) + at(yc - 1, xc + 1) + at(yc + 1, xc - 1) + at(yc + 1, xc + 1) + 2) >> 2;
+        const int hor = (at(yc, xc - 1) + at(yc, xc + 1) + 1) >> 1, ver = (at(yc - 1, xc) + at(yc + 1, xc) + 1) >> 1;
+        const int v = at(yc, xc);
+        const bool ey = (yc & 1) == 0, ex = (xc & 1) == 0;
+        int B, G, R;
+        if (ey && ex) { B = v; G = cross; R = diag; }
+        else if (!ey && !ex) { B = diag; G = cross; R = v; }
+        else if (ey) { B = hor; G = v; R = ver; }
+        else { B = ver; G = v; R = hor; }
+        uint8_t* o = d + ((size_t)y * w + x) * 3;
+        o[0] = (uint8_t)B;
+        o[1] = (uint8_t)G;
+        o[2] = (uint8_t)R;
+      }
+  });
+}
+
 // ---- integral(CV_32S) ----
 extern "C" void orc_integral(const uint8_t* s, int w, int h, int32_t* sum) {
   const int sw = w + 1;

@@ -105,6 +105,15 @@ def integral(g):
     return out
 
 
+def bayer_bggr2bgr(bayer):
+    """cv2.cvtColor(bayer, COLOR_BayerBGGR2BGR) (from_ros_to_cv_image, math_utility.cpp:161-164)"""
+    b = np.ascontiguousarray(bayer, dtype=np.uint8)
+    h, w = b.shape
+    out = np.empty((h, w, 3), np.uint8)
+    lib().orc_bayer_bggr2bgr(_p(b), w, h, _p(out))
+    return out
+
+
 def resize_area(src, dw, dh):
     src = np.ascontiguousarray(src, dtype=np.uint8)
     sh, sw = src.shape[:2]

@@ -45,6 +45,8 @@ void orc_get_image(const uint8_t* src3, int w, int h, const double K[4], const d
                    int clahe, double clip_limit, uint8_t* dst);
 /* ---- K0: resize INTER_AREA (VO_utility.cpp:362-363), u8, cn channels ---- */
 void orc_resize_area(const uint8_t* src, int sw, int sh, int cn, uint8_t* dst, int dw, int dh);
+/* ---- before K0: cvtColor(COLOR_BayerBGGR2BGR) of from_ros_to_cv_image (math_utility.cpp:161-164); w, h >= 3 ---- */
+void orc_bayer_bggr2bgr(const uint8_t* src, int w, int h, uint8_t* dst3);
 /* ---- K3: integral(CV_32S): (h+1)x(w+1) ---- */
 void orc_integral(const uint8_t* src, int w, int h, int32_t* sum);
 

@@ -86,3 +86,11 @@ def test_get_image_resized_branch(ctx, oracle):
     ref = oracle.get_image(oracle.resize_area(img, 640, dh), small.K, small.D, small.newK, True,
                            float(ctx.params.clip_limit))
     assert out.shape == (dh, 640) and np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("h,w", [(3, 3), (4, 5), (7, 9), (480, 640), (1024, 1280), (1081, 1921)])
+def test_bayer_demosaic(ctx, oracle, h, w):
+    """uvo_demosaic_bggr2bgr == cvtColor(COLOR_BayerBGGR2BGR) (oracle pinned to cv2): interior means and the copied
+    border rows / columns, odd and even sizes"""
+    b = np.random.RandomState(h * w).randint(0, 256, (h, w)).astype(np.uint8)
+    assert np.array_equal(ctx.demosaic_bggr2bgr(b), oracle.bayer_bggr2bgr(b))

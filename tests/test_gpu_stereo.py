@@ -186,3 +186,31 @@ def test_stereo_host_async_pipeline_matches_sync(ctx, small_stereo):
     for a, b in zip(got, sync):
         assert bytes(a) == bytes(b)
     vo.close()
+
+
+def test_bayer_input_equals_demosaiced_input(ctx, oracle, small_stereo):
+    """uvo_stereo_enqueue_host_bayer(bayer) gives the same frames as uvo_stereo_frame on the images the CPU demosaic
+    (cvtColor BayerBGGR2BGR, as from_ros_to_cv_image does) produces from the same bayer data."""
+    seq = small_stereo
+
+    def mosaic(img3):  # sample a BGGR mosaic out of a colour image: (even, even) blue ... (odd, odd) red
+        m = img3[:, :, 1].copy()
+        m[0::2, 0::2] = img3[0::2, 0::2, 0]
+        m[1::2, 1::2] = img3[1::2, 1::2, 2]
+        return np.ascontiguousarray(m)
+    vo_a, p = _make(ctx, seq, 3000)
+    vo_b, _ = _make(ctx, seq, 3000)
+    for k, (L, R) in enumerate(seq.frames[:3]):
+        bl, br = mosaic(L), mosaic(R)
+        ra = vo_a.frame(oracle.bayer_bggr2bgr(bl), oracle.bayer_bggr2bgr(br), 0.1)
+        vo_b.enqueue_host_bayer(bl.ctypes.data, br.ctypes.data, bl.strides[0], 0.1)
+        rb = vo_b.collect()
+        for f in ("initialised", "valid", "n_left", "n_right", "n_stereo_matches", "n_temporal_matches", "n_3d",
+                  "n_inliers", "hyps_evaluated", "gate"):
+            assert getattr(ra, f) == getattr(rb, f), (k, f)
+        assert list(ra.rvec) == list(rb.rvec) and list(ra.tvec) == list(rb.tvec) and list(ra.velocity) == list(rb.velocity)
+        ka, _ = vo_a.last_keypoints(False)
+        kb, _ = vo_b.last_keypoints(False)
+        assert ka.tobytes() == kb.tobytes() and len(ka) > 100
+    vo_a.close()
+    vo_b.close()

@@ -80,3 +80,12 @@ def test_resize_area_3ch_cv2(oracle, sw, sh, dw):
     img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
     dh = int(sh / (sw / dw))
     assert np.array_equal(oracle.resize_area(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA))
+
+
+def test_bayer_demosaic_matches_cv2(oracle):
+    """cvtColor(COLOR_BayerBGGR2BGR) of from_ros_to_cv_image (math_utility.cpp:161-164): interior and border rule"""
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(3)
+    for (h, w) in [(3, 3), (4, 4), (5, 4), (7, 9), (12, 14), (13, 15), (480, 640), (1024, 1280)]:
+        b = rs.randint(0, 256, (h, w)).astype(np.uint8)
+        assert np.array_equal(oracle.bayer_bggr2bgr(b), cv2.cvtColor(b, cv2.COLOR_BayerBGGR2BGR)), (h, w)

@@ -28,13 +28,21 @@ def main():
              torch.from_numpy(seq.frames[order[i % len(order)]][1]).pin_memory()) for i in range(RING)]
     dev = [(a.cuda(), b.cuda()) for a, b in host]
 
+    def mosaic(t):  # BGGR mosaic sampled from the colour image (1 byte per pixel over PCIe instead of 3)
+        img = t.numpy()
+        m = img[:, :, 1].copy()
+        m[0::2, 0::2] = img[0::2, 0::2, 0]
+        m[1::2, 1::2] = img[1::2, 1::2, 2]
+        return torch.from_numpy(np.ascontiguousarray(m)).pin_memory()
+    bayer = [(mosaic(a), mosaic(b)) for a, b in host]
+
     def run(n, ring, enq, inflight=8):
         q = 0
         t_enq = t_col = 0.0
         for k in range(n):
             L, R = ring[k % RING]
             t0 = time.perf_counter()
-            enq(L.data_ptr(), R.data_ptr(), 3 * W, 0.1)
+            enq(L.data_ptr(), R.data_ptr(), L.stride(0), 0.1)
             t_enq += time.perf_counter() - t0
             q += 1
             if q >= inflight:
@@ -48,8 +56,10 @@ def main():
         return t_enq, t_col
     run(32, host, vo.enqueue_host)
     run(32, dev, vo.enqueue_device)
+    run(32, bayer, vo.enqueue_host_bayer)
     for r in range(reps):
-        for name, ring, enq in (("device", dev, vo.enqueue_device), ("host", host, vo.enqueue_host)):
+        for name, ring, enq in (("device", dev, vo.enqueue_device), ("host", host, vo.enqueue_host),
+                                ("bayer", bayer, vo.enqueue_host_bayer)):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             te, tc = run(n, ring, enq)
