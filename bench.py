@@ -224,10 +224,10 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL is used for the barrier / MAX-over-ranks only; keep its "NCCL version ..." banner (printed to stdout when
-        # NCCL_DEBUG=VERSION) away from the one JSON line this script prints
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL is used for the barrier / MAX-over-ranks only; its debug output (the "NCCL version ..." banner at
+        # NCCL_DEBUG=VERSION and above) goes to stdout by default: send it to stderr so that stdout carries the one
+        # JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     ctx = U.Context(local, stream=stream.cuda_stream)
