@@ -144,8 +144,16 @@ __device__ __forceinline__ float haar4(const int* __restrict__ o, const SurfBox*
   return (float)d;
 }
 
+// Lazy evaluation (LAZY = true): det = dx dy - 0.81 dxy^2 <= fl(dx dy), because the subtrahend (0.81f dxy) dxy is >= +0
+// and f32 subtraction is monotonic.  A sample with fl(dx dy) <= thr can therefore never pass `det > thr` as a centre,
+// it compares as smaller than any centre that does, and its exact value is needed only for the interpolation of a
+// local maximum next to it -- rare, and filled in cooperatively later.  The Dxy half of such a sample (16 of its 32
+// corner reads, 4 of its 10 fp64 terms) is skipped and DET_SKIPPED stored.  Every value that is used is exact.
+#define DET_SKIPPED (-INFINITY)
+
+template <bool LAZY = false>
 __device__ __forceinline__ float det_at(const int* __restrict__ sum, int scols, const SurfLayer& L, int step, int i,
-                                        int j) {
+                                        int j, float thr = 0.f) {
   const int si = i - L.margin, sj = j - L.margin;
   if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
   const int* o = sum + (size_t)(si * step) * scols + sj * step;
@@ -171,6 +179,7 @@ __device__ __forceinline__ float det_at(const int* __restrict__ sum, int scols, 
   for (int k = 0; k < 3; k++)
     d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A[k] + B[k + 1] - A[k + 1] - B[k]), L.box[3 + k].w));
   const float dy = (float)d;
+  if (LAZY && !(__fmul_rn(dx, dy) > thr)) return DET_SKIPPED;
   const float dxy = haar4(o, L.box + 6);
   return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
@@ -191,8 +200,9 @@ __host__ __device__ constexpr int haar_off(int k) {  // resizeHaarPattern: cvRou
 constexpr int T0_MAXM = 13;                                 // margin of the largest middle layer (size 27) at step 1
 constexpr int T0_ROWS = SURF_TILE_H + 2 + 27, T0_COLS = SURF_TILE_W + 2 + 27;  // 45 x 61 integral samples
 
-template <int SIZE>
-__device__ __forceinline__ float det_tile0(const int* __restrict__ T, const SurfLayer& L, int i, int j, int y, int x) {
+template <int SIZE, bool LAZY = false>
+__device__ __forceinline__ float det_tile0(const int* __restrict__ T, const SurfLayer& L, int i, int j, int y, int x,
+                                           float thr = 0.f) {
   constexpr int M = SIZE / 2;
   const int si = i - M, sj = j - M;
   if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
@@ -219,6 +229,7 @@ __device__ __forceinline__ float det_tile0(const int* __restrict__ T, const Surf
     d = __dadd_rn(d, (double)__fmul_rn((float)(int)(A2 + B3 - A3 - B2), L.box[5].w));
   }
   const float dy = (float)d;
+  if (LAZY && !(__fmul_rn(dx, dy) > thr)) return DET_SKIPPED;
   d = 0;
   {
     // Dxy boxes {1,1,4,4} {5,1,8,4} {1,5,4,8} {5,5,8,8} as (x1, y1, x2, y2): p0 + p3 - p1 - p2
@@ -313,10 +324,20 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
   const int scols = g.w + 1;
   const int step = O.step;
   constexpr int PLANE = (TH + 2) * (TW + 2);
+  __shared__ int s_tile[T0_ROWS * T0_COLS];
+  // exact value of middle layer lm (0-based) at tile position (y, x): the full evaluation of a skipped sample
+  auto mid_exact = [&](int lm, int y, int x) -> float {
+    const int i = ti0 + y - 1, j = tj0 + x - 1;
+    if (o == 0) {
+      if (lm == 0) return det_tile0<15>(s_tile, O.layer[1], i, j, y, x);
+      if (lm == 1) return det_tile0<21>(s_tile, O.layer[2], i, j, y, x);
+      return det_tile0<27>(s_tile, O.layer[3], i, j, y, x);
+    }
+    return det_at(im.sum, scols, O.layer[lm + 1], step, i, j);
+  };
   if (threadIdx.x == 0) s_ncand = 0;
   if (o == 0) {
     // octave 0 (three quarters of all samples): stage the integral tile once, then evaluate from shared memory
-    __shared__ int s_tile[T0_ROWS * T0_COLS];
     const int R0 = ti0 - 1 - T0_MAXM, C0 = tj0 - 1 - T0_MAXM;
     for (int idx = threadIdx.x; idx < T0_ROWS * T0_COLS; idx += blockDim.x) {
       const int ry = idx / T0_COLS, rx = idx - ry * T0_COLS;
@@ -329,18 +350,21 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
       const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
       const int i = ti0 + y - 1, j = tj0 + x - 1;
       float v;
-      if (l == 0) v = det_tile0<15>(s_tile, O.layer[1], i, j, y, x);
-      else if (l == 1) v = det_tile0<21>(s_tile, O.layer[2], i, j, y, x);
-      else v = det_tile0<27>(s_tile, O.layer[3], i, j, y, x);
+      if (l == 0) v = det_tile0<15, true>(s_tile, O.layer[1], i, j, y, x, g.thr);
+      else if (l == 1) v = det_tile0<21, true>(s_tile, O.layer[2], i, j, y, x, g.thr);
+      else v = det_tile0<27, true>(s_tile, O.layer[3], i, j, y, x, g.thr);
       sdet[l][y][x] = v;
     }
   } else {
     for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
       const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
-      sdet[l][y][x] = det_at(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1);
+      sdet[l][y][x] = det_at<true>(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1, g.thr);
     }
   }
   __syncthreads();
+  // local maxima among the middle layers.  A skipped neighbour is <= thr < val0, and DET_SKIPPED = -inf compares
+  // exactly like that.  Every maximum goes to the list; what it still misses (exact values of skipped neighbours,
+  // an outer plane) is computed by the whole block below.
   for (int idx = threadIdx.x; idx < nmid * TH * TW; idx += blockDim.x) {
     const int m = 1 + idx / (TH * TW), r = idx % (TH * TW), y = r / TW, x = r % TW;
     const int i = ti0 + y, j = tj0 + x;
@@ -348,37 +372,35 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
     if (i < margin || i >= O.lrows - margin || j < margin || j >= O.lcols - margin) continue;
     const float val0 = sdet[m - 1][y + 1][x + 1];
     if (!(val0 > g.thr)) continue;
-    float N[3][9];
     bool is_max = true;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       const int l = m - 1 + a;  // pyramid layer of this plane
       if (l < 1 || l > nmid) continue;
 #pragma unroll
-      for (int q = 0; q < 9; q++) {
-        const float v = sdet[l - 1][y + q / 3][x + q % 3];
-        N[a][q] = v;
-        if (!(a == 1 && q == 4) && !(val0 > v)) is_max = false;
-      }
+      for (int q = 0; q < 9; q++)
+        if (!(a == 1 && q == 4) && !(val0 > sdet[l - 1][y + q / 3][x + q % 3])) is_max = false;
     }
     if (!is_max) continue;
-    if (m > 1 && m < nmid) {  // all three planes are middle layers
-      emit_keypoint(O, im, N, m, i, j, o, capacity);
-      continue;
-    }
     const int slot = atomicAdd(&s_ncand, 1);
     if (slot < DET_LIST) {
       s_cand[slot] = DetCand{(short)m, (short)y, (short)x, 1};
     } else {  // list full: finish this candidate here
-#pragma unroll
-      for (int a = 0; a < 3; a += 2) {
+      float N[3][9];
+#pragma unroll 1
+      for (int a = 0; a < 3; a++) {
         const int l = m - 1 + a;
-        if (l >= 1 && l <= nmid) continue;
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < 9; q++) {
-          const float v = det_at(im.sum, scols, O.layer[l], step, i - 1 + q / 3, j - 1 + q % 3);
+          float v;
+          if (l >= 1 && l <= nmid) {
+            v = sdet[l - 1][y + q / 3][x + q % 3];
+            if (v == DET_SKIPPED) v = mid_exact(l - 1, y + q / 3, x + q % 3);
+          } else {
+            v = det_at(im.sum, scols, O.layer[l], step, i - 1 + q / 3, j - 1 + q % 3);
+            if (!(val0 > v)) is_max = false;
+          }
           N[a][q] = v;
-          if (!(val0 > v)) is_max = false;
         }
       }
       if (is_max) emit_keypoint(O, im, N, m, i, j, o, capacity);
@@ -386,6 +408,16 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
   }
   __syncthreads();
   const int ncand = min(s_ncand, DET_LIST);
+  // exact values of the skipped middle-layer neighbours of the listed maxima (27 slots per maximum)
+  for (int idx = threadIdx.x; idx < ncand * 27; idx += blockDim.x) {
+    const int c = idx / 27, r = idx - c * 27, a = r / 9, q = r - a * 9;
+    const DetCand cd = s_cand[c];
+    const int l = cd.m - 1 + a;
+    if (l < 1 || l > nmid) continue;
+    const int y = cd.y + q / 3, x = cd.x + q % 3;
+    if (sdet[l - 1][y][x] == DET_SKIPPED) sdet[l - 1][y][x] = mid_exact(l - 1, y, x);  // same bits from any writer
+  }
+  __syncthreads();
   // outer-layer samples of the listed candidates: 9 per (candidate, outer plane); with a single middle layer a
   // candidate needs both outer planes, handled as two passes
   for (int pass = 0; pass < 2; pass++) {
@@ -399,11 +431,11 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
       if (!(sdet[cd.m - 1][cd.y + 1][cd.x + 1] > v)) s_cand[c].alive = 0;  // benign race: all writers store 0
     }
     __syncthreads();
-    // finish candidates whose last missing plane was this pass's
+    // finish candidates whose last missing plane was this pass's (pass 0 also finishes those that need none)
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
       const DetCand cd = s_cand[c];
       const bool needs0 = cd.m == 1, needs1 = cd.m == nmid;
-      const bool last = pass == 1 ? needs1 : (needs0 && !needs1);
+      const bool last = pass == 1 ? needs1 : !needs1;
       if (!last || !cd.alive) continue;
       float N[3][9];
 #pragma unroll
