@@ -20,8 +20,14 @@ __device__ __forceinline__ int gray_tap(const uint8_t* __restrict__ src, size_t 
   return (9798 * (int)p[0] + 19235 * (int)p[1] + 3735 * (int)p[2] + 16384) >> 15;
 }
 
-__global__ void __launch_bounds__(256) k_gray_undistort(const uint8_t* __restrict__ src, size_t spitch, int w, int h,
-                                                        UndistortParams P, uint8_t* __restrict__ dst, size_t dpitch) {
+// blockIdx.z selects the image of a stereo pair (second pointer set / camera); single-image launches use z = 1
+__global__ void __launch_bounds__(256) k_gray_undistort(const uint8_t* src0, const uint8_t* src1,
+                                                        size_t spitch, int w, int h, const __grid_constant__ UndistortParams P0,
+                                                        const __grid_constant__ UndistortParams P1, uint8_t* dst0,
+                                                        uint8_t* dst1, size_t dpitch) {
+  const uint8_t* __restrict__ src = blockIdx.z ? src1 : src0;
+  uint8_t* __restrict__ dst = blockIdx.z ? dst1 : dst0;
+  const UndistortParams& P = blockIdx.z ? P1 : P0;
   const int j0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j0 >= w || i >= h) return;
@@ -64,7 +70,7 @@ void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, 
   dim3 block(32, 8);
   dim3 grid(div_up(div_up(w, 4), 32), div_up(h, 8));
   UVO_KERNEL(c, "k_gray_undistort");
-  k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3, spitch, w, h, P, d_dst, dpitch);
+  k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3, d_src3, spitch, w, h, P, P, d_dst, d_dst, dpitch);
   UVO_LAUNCH_CHECK(c);
 }
 
@@ -149,9 +155,12 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // grid: (tiles_x*tiles_y, slices).  Each block histograms a horizontal slice of one tile in shared memory and
 // merges it into the tile's global histogram with 256 atomics.
-__global__ void __launch_bounds__(256) k_clahe_hist(const uint8_t* __restrict__ img, size_t pitch, int w, int h,
-                                                    ClaheGeom g, unsigned int* __restrict__ hist) {
+__global__ void __launch_bounds__(256) k_clahe_hist(const uint8_t* img0, const uint8_t* img1,
+                                                    size_t pitch, int w, int h, ClaheGeom g,
+                                                    unsigned int* __restrict__ hist) {
   __shared__ unsigned int sh[256];
+  const uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
+  hist += (size_t)blockIdx.z * g.tiles_x * g.tiles_y * 256;  // the pair's histograms (and LUTs) are contiguous
   sh[threadIdx.x] = 0;
   __syncthreads();
   const int tile = blockIdx.x, txi = tile % g.tiles_x, tyi = tile / g.tiles_x;
@@ -220,9 +229,13 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restric
 // bilinear blend of the four neighbouring tile LUTs (CLAHE_Interpolation_Body); 4 px per thread, in place allowed.
 // Optionally also emits the per-row inclusive prefix sums of the result (first half of the integral image, K3):
 // not fused here -- see k_integral_rows.
-__global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* __restrict__ src, size_t spitch, int w, int h,
-                                                     ClaheGeom g, const uint8_t* __restrict__ lut,
-                                                     uint8_t* __restrict__ dst, size_t dpitch) {
+__global__ void __launch_bounds__(256) k_clahe_apply(const uint8_t* src0, const uint8_t* src1,
+                                                     size_t spitch, int w, int h, ClaheGeom g,
+                                                     const uint8_t* __restrict__ lut, uint8_t* dst0,
+                                                     uint8_t* dst1, size_t dpitch) {
+  const uint8_t* __restrict__ src = blockIdx.z ? src1 : src0;
+  uint8_t* __restrict__ dst = blockIdx.z ? dst1 : dst0;
+  lut += (size_t)blockIdx.z * g.tiles_x * g.tiles_y * 256;
   const int j0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (j0 >= w || y >= h) return;
@@ -294,22 +307,25 @@ void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, con
   UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles, c.stream));
   int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
   UVO_KERNEL(c, "k_clahe_hist");
-  k_clahe_hist<<<dim3(tiles, slices), 256, 0, c.stream>>>(d_src, spitch, w, h, g, d_hist);
+  k_clahe_hist<<<dim3(tiles, slices), 256, 0, c.stream>>>(d_src, d_src, spitch, w, h, g, d_hist);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_clahe_lut");
   k_clahe_lut<<<tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);
   UVO_LAUNCH_CHECK(c);
   dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8));
   UVO_KERNEL(c, "k_clahe_apply");
-  k_clahe_apply<<<grid, block, 0, c.stream>>>(d_src, spitch, w, h, g, d_lut, d_dst, dpitch);
+  k_clahe_apply<<<grid, block, 0, c.stream>>>(d_src, d_src, spitch, w, h, g, d_lut, d_dst, d_dst, dpitch);
   UVO_LAUNCH_CHECK(c);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 integral
 // Pass 1: one warp per image row; inclusive prefix along the row, written to sum[(i+1)][1..w]; also zeroes column 0
 // and (warp 0) row 0.  Pass 2: column prefix in place, each block owns 32 columns x 32 row segments.
-__global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* __restrict__ img, size_t pitch, int w, int h,
-                                                       int32_t* __restrict__ sum) {
+__global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* img0, const uint8_t* img1,
+                                                       size_t pitch, int w, int h, int32_t* sum0,
+                                                       int32_t* sum1) {
+  const uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
+  int32_t* __restrict__ sum = blockIdx.z ? sum1 : sum0;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int sw = w + 1;
   if (warp == 0)
@@ -348,8 +364,10 @@ __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* __restrict
 }
 
 // block = 32 (columns) x 32 (row segments).  Segment totals -> exclusive scan in smem -> second sweep adds.
-__global__ void __launch_bounds__(1024) k_integral_cols(int32_t* __restrict__ sum, int w, int h) {
+__global__ void __launch_bounds__(1024) k_integral_cols(int32_t* sum0, int32_t* sum1, int w,
+                                                        int h) {
   __shared__ int32_t tot[32][33];
+  int32_t* __restrict__ sum = blockIdx.z ? sum1 : sum0;
   const int sw = w + 1;
   const int col = 1 + blockIdx.x * 32 + threadIdx.x;
   const int seg = threadIdx.y;
@@ -372,10 +390,49 @@ __global__ void __launch_bounds__(1024) k_integral_cols(int32_t* __restrict__ su
 void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum) {
   const int warps_per_block = 8;
   UVO_KERNEL(c, "k_integral_rows");
-  k_integral_rows<<<div_up(h, warps_per_block), 32 * warps_per_block, 0, c.stream>>>(d_img, pitch, w, h, d_sum);
+  k_integral_rows<<<div_up(h, warps_per_block), 32 * warps_per_block, 0, c.stream>>>(d_img, d_img, pitch, w, h, d_sum,
+                                                                                      d_sum);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
-  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, w, h);
+  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, d_sum, w, h);
+  UVO_LAUNCH_CHECK(c);
+}
+
+// K1-K3 for both images of a stereo pair in one launch per kernel (blockIdx.z = image): half the launches, and the
+// narrow kernels (histograms, LUTs, the two scan passes) get twice the blocks.  d_hist / d_lut: 2 * tiles * 256.
+void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
+                      const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
+                      int32_t* d_sum[2]) {
+  {
+    dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
+    UVO_KERNEL(c, "k_gray_undistort");
+    k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3[0], d_src3[1], spitch, w, h, P[0], P[1], d_gray[0], d_gray[1],
+                                                   gpitch);
+    UVO_LAUNCH_CHECK(c);
+  }
+  if (clahe) {
+    const int tiles = g.tiles_x * g.tiles_y;
+    UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles * 2, c.stream));
+    int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
+    UVO_KERNEL(c, "k_clahe_hist");
+    k_clahe_hist<<<dim3(tiles, slices, 2), 256, 0, c.stream>>>(d_gray[0], d_gray[1], gpitch, w, h, g, d_hist);
+    UVO_LAUNCH_CHECK(c);
+    UVO_KERNEL(c, "k_clahe_lut");
+    k_clahe_lut<<<2 * tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);  // tile index runs over both images
+    UVO_LAUNCH_CHECK(c);
+    dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
+    UVO_KERNEL(c, "k_clahe_apply");
+    k_clahe_apply<<<grid, block, 0, c.stream>>>(d_gray[0], d_gray[1], gpitch, w, h, g, d_lut, d_gray[0], d_gray[1],
+                                                gpitch);
+    UVO_LAUNCH_CHECK(c);
+  }
+  const int warps_per_block = 8;
+  UVO_KERNEL(c, "k_integral_rows");
+  k_integral_rows<<<dim3(div_up(h, warps_per_block), 1, 2), 32 * warps_per_block, 0, c.stream>>>(
+      d_gray[0], d_gray[1], gpitch, w, h, d_sum[0], d_sum[1]);
+  UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_integral_cols");
+  k_integral_cols<<<dim3(div_up(w, 32), 1, 2), dim3(32, 32), 0, c.stream>>>(d_sum[0], d_sum[1], w, h);
   UVO_LAUNCH_CHECK(c);
 }
 

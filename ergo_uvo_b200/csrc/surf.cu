@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ 
     // finish candidates whose last missing plane was this pass's (pass 0 also finishes those that need none)
     for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
       const DetCand cd = s_cand[c];
-      const bool needs0 = cd.m == 1, needs1 = cd.m == nmid;
+      const bool needs1 = cd.m == nmid;
       const bool last = pass == 1 ? needs1 : !needs1;
       if (!last || !cd.alive) continue;
       float N[3][9];
