@@ -370,8 +370,10 @@ def run_gpu(args):
         P = W * H
         # algorithmic bytes / flops per launch of each kernel (DESIGN.md "Kernels")
         algo = {
-            "k_gray_undistort": ("hbm", 4.0 * P), "k_clahe_hist": ("hbm", 1.0 * P), "k_clahe_apply": ("hbm", 2.0 * P),
-            "k_integral_rows": ("hbm", 5.0 * P), "k_integral_cols": ("hbm", 8.0 * P),
+            # one launch covers both images of the pair (blockIdx.z = image)
+            "k_gray_undistort": ("hbm", 2 * 4.0 * P), "k_clahe_hist": ("hbm", 2 * 1.0 * P),
+            "k_clahe_apply": ("hbm", 2 * 2.0 * P), "k_integral_rows": ("hbm", 2 * 5.0 * P),
+            "k_integral_cols": ("hbm", 2 * 8.0 * P),
             "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_patch": ("hbm", 2 * n_kp * (40 * 40 + 256)),
             "k_knn_tc": ("tensor", 2.0 * n_kp * n_kp * 64),
         }
