@@ -983,9 +983,11 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
         __syncthreads();  // s_acc zeroed / previous chunk's pass 2 done with s_buf
         const int x_first = sx0 + c0, xa = x_first & ~3;
         const int ncg = ((x_first + rows - 1) >> 2) - (xa >> 2) + 1;
-        const unsigned inv_ncg = ncg > 1 ? 0xffffffffu / (unsigned)ncg + 1u : 0u;  // ceil(2^32 / ncg)
+        // t / ncg by a float reciprocal: (t + 0.5) / ncg is at least 0.5 / ncg (>= 0.01) away from any integer and
+        // t < 2^12, so the f32 rounding (relative 2^-23) cannot move the floor
+        const float inv_ncg = 1.0f / (float)ncg;
         for (int t = tid; t < ncg * 21; t += DESC_THREADS) {
-          const int d = ncg > 1 ? (int)__umulhi((unsigned)t, inv_ncg) : t, m = t - d * ncg;  // t / ncg (t < 2^24)
+          const int d = (int)(((float)t + 0.5f) * inv_ncg), m = t - d * ncg;
           const int xw = xa + 4 * m, il0 = xw - x_first;
           const bool x_in = xw >= 0 && xw + 3 <= w - 1;
           // pixels of window column j for this item's four window rows, as one little-endian word
@@ -1064,6 +1066,7 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
             if (ys.has_l && ys.sx1 - 1 >= c0 && ys.sx1 - 1 < c1)
               sum = __fadd_rn(sum, __fmul_rn(ys.a_l, col[(ys.sx1 - 1) * 21]));
             const int lo = max(ys.sx1, c0), hi = min(ys.sx2, c1);
+#pragma unroll 4
             for (int i = lo; i < hi; i++) sum = __fadd_rn(sum, __fmul_rn(ys.a_f, col[i * 21]));
             if (ys.has_r && ys.sx2 >= c0 && ys.sx2 < c1) sum = __fadd_rn(sum, __fmul_rn(ys.a_r, col[ys.sx2 * 21]));
             s_acc[t] = sum;
