@@ -227,6 +227,9 @@ def run_gpu(args):
         # NCCL is used for the barrier / MAX-over-ranks only; its debug output (the "NCCL version ..." banner at
         # NCCL_DEBUG=VERSION and above) goes to stdout by default: send it to stderr so that stdout carries the one
         # JSON line only
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
