@@ -307,7 +307,10 @@ __device__ __noinline__ void emit_keypoint(const SurfOctave& O, const SurfImage&
   }
 }
 
-__global__ void __launch_bounds__(256, 5) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
+#ifndef UVO_DET_MINB
+#define UVO_DET_MINB 6
+#endif
+__global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
                                                      int capacity) {
   // sdet[l] holds pyramid layer l + 1 (the middle layers)
   __shared__ float sdet[SURF_MAX_LAYERS - 2][TH + 2][TW + 2];
