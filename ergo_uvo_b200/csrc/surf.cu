@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
     // ---- resize(win -> 21x21, INTER_AREA) ----
     // scale / iscale / is_area_fast exactly as cv::resize derives them (fp64); only 21 threads need the divisions
     if (tid < 21) {
-      if (tab && win_size < SPAN_TAB_MAX) {
+      if (tab && win_size >= 21 && win_size < SPAN_TAB_MAX) {  // rows below 21 are never tabulated
         s_span[tid] = tab->span[win_size][tid];
         if (tid == 0) {
           s_iscale = tab->iscale[win_size];
