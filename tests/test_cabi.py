@@ -102,3 +102,37 @@ def test_optimal_new_camera_matrix_matches_cv2():
     assert np.array_equal(Kio, Ks)
     ref, _ = cv2.getOptimalNewCameraMatrix(Ks, D, (640, 512), 0, (640, 512), False)
     assert np.array_equal(newK.reshape(3, 3), ref)
+
+
+def test_ctypes_mirrors_have_the_header_sizes(tmp_path):
+    """the ctypes mirrors in ergo_uvo_b200/_lib.py against sizeof / offsetof from include/uvo_c.h compiled with gcc"""
+    import ergo_uvo_b200 as U
+    from ergo_uvo_b200 import _lib as L
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvo_c.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(uvo_params), sizeof(uvo_camera), sizeof(uvo_stereo_result), sizeof(uvo_mono_result),'
+                   'sizeof(uvo_keypoint), sizeof(uvo_dmatch), offsetof(uvo_params, stereo_gate),'
+                   'offsetof(uvo_params, max_features));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(L.Params), C.sizeof(L.Camera), C.sizeof(L.StereoResult), C.sizeof(L.MonoResult),
+            U.KEYPOINT_DTYPE.itemsize, U.DMATCH_DTYPE.itemsize, L.Params.stereo_gate.offset,
+            L.Params.max_features.offset]
+    assert got == want
+
+
+def test_lazy_dxy_bound_holds_in_f32():
+    """k_surf_detect skips the Dxy half of a sample when fl(dx dy) <= threshold.  That is exact because
+    det = fl(fl(dx dy) - fl(fl(0.81f dxy) dxy)) <= fl(dx dy): the subtrahend is >= +0 and IEEE subtraction is
+    monotonic.  Checked here on random and adversarial f32 values."""
+    import numpy as np
+    rs = np.random.RandomState(0)
+    f = np.float32
+    dx = np.concatenate([rs.randn(200000) * 300, rs.randn(1000) * 1e-3, [0, -0.0, 1e30, -1e30]]).astype(f)
+    dy = np.concatenate([rs.randn(200000) * 300, rs.randn(1000) * 1e3, [5, 7, 1e-30, 1e-30]]).astype(f)
+    dxy = np.concatenate([rs.randn(200000) * 200, rs.randn(1000) * 1e-20, [0, -0.0, 3, -3]]).astype(f)
+    p = (dx * dy).astype(f)
+    sub = ((f(0.81) * dxy).astype(f) * dxy).astype(f)
+    det = (p - sub).astype(f)
+    assert (sub >= 0).all() and (det <= p).all()
