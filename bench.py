@@ -166,7 +166,40 @@ def cpu_frames(seq, thr, n_frames, params=None):
         valid += r["valid"]
     dt = time.perf_counter() - t0
     cpu_frames.last_stage_ms = {k: 1e3 * v / n_frames for k, v in ref.stage_s.items()}
+    cpu_frames.last_stage_ms_cv2 = cv2_stage_ms(seq, r)
     return dt / n_frames, valid
+
+
+def cv2_stage_ms(seq, last):
+    """the stages OpenCV's Python wheel can run (no contrib SURF), on the same frame: get_image for the pair and one
+    BFMatcher knnMatch(k=2) on the frame's own descriptors -- the 'per-stage ms vs CPU OpenCV' column"""
+    try:
+        import cv2
+    except ImportError:
+        return None
+    import numpy as np
+    L, R = seq.frames[1 % len(seq.frames)]
+    clahe = cv2.createCLAHE(clipLimit=8.0, tileGridSize=(8, 8))
+
+    def get_image(img, K, D, newK):
+        g = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)
+        g = cv2.undistort(g, K, np.asarray(D, dtype=np.float64), None, newK)
+        return clahe.apply(g)
+
+    def best(fn, n=3):
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * min(ts)
+    out = {"cv2": cv2.__version__, "threads": cv2.getNumThreads(),
+           "get_image": best(lambda: (get_image(L, seq.KL, seq.DL, seq.newKL), get_image(R, seq.KR, seq.DR, seq.newKR)))}
+    if last is not None and "dL" in last and len(last["dL"]) and len(last["dR"]):
+        bf = cv2.BFMatcher(cv2.NORM_L2, False)
+        dL, dR = np.ascontiguousarray(last["dL"]), np.ascontiguousarray(last["dR"])
+        out["match_stereo"] = best(lambda: bf.knnMatch(dL, dR, 2), 2)
+    return out
 
 
 def default_params_cpu(thr):
@@ -203,7 +236,8 @@ def run_reference(args):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} consecutive stereo frames of the same synthetic sequence through the "
                                    "oracle port of the OpenCV CPU path (SURF restated, not OpenCV)",
-                         "stage_ms": getattr(cpu_frames, "last_stage_ms", None)},
+                         "stage_ms": getattr(cpu_frames, "last_stage_ms", None),
+                         "stage_ms_cv2": getattr(cpu_frames, "last_stage_ms_cv2", None)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "valid_frames": valid,
     }
@@ -430,7 +464,8 @@ def run_gpu(args):
                    "sample": f"{n_cpu} consecutive stereo frames (after the init frame) of this run's sequence through "
                              "the oracle port of the OpenCV CPU path; SURF restated, not OpenCV",
                    "host_cpus": os.cpu_count(),
-                   "stage_ms": getattr(cpu_frames, "last_stage_ms", None)}
+                   "stage_ms": getattr(cpu_frames, "last_stage_ms", None),
+                   "stage_ms_cv2": getattr(cpu_frames, "last_stage_ms_cv2", None)}
         line = {
             "metric": "stereo_uvo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
