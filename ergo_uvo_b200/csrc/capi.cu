@@ -320,7 +320,8 @@ int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t 
     const int n = pc[1];
     if (n > 0) {
       UVO_CUDA(cudaMemcpyAsync(kps, fe.kps[0].get(), sizeof(uvo_keypoint) * n, cudaMemcpyDeviceToHost, c.stream));
-      UVO_CUDA(cudaMemcpyAsync(desc, fe.desc[0].get(), sizeof(float) * 64 * n, cudaMemcpyDeviceToHost, c.stream));
+      const size_t dd = prm->surf_extended ? 128 : 64;
+      UVO_CUDA(cudaMemcpyAsync(desc, fe.desc[0].get(), sizeof(float) * dd * n, cudaMemcpyDeviceToHost, c.stream));
       UVO_CUDA(cudaStreamSynchronize(c.stream));
     }
     *count = n;
@@ -357,26 +358,29 @@ struct HostGate {  // optional stereo gate of uvo_match_features_gated
 
 static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, float ratio,
                        uvo_dmatch* matches, int* count, uvo_dmatch* knn_out, const HostGate* gate = nullptr) {
-  UVO_REQUIRE(dim == 64, "matcher: only 64-d SURF descriptors are supported");
+  if (dim != 64 && dim != 128)
+    throw InvalidArg{"matcher: descriptor rows must be 64 (SURF) or 128 (extended SURF) floats", UVO_ERR_UNSUPPORTED};
   UVO_REQUIRE(n1 >= 0 && n2 >= 0 && (n1 == 0 || d1) && (n2 == 0 || d2), "matcher: bad argument");
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
   if (count) *count = 0;
   if (n1 == 0) return;
   StageScratch& s = ctx->scratch;
-  s.bytes_a.ensure(sizeof(float) * 64 * (size_t)n1);
-  s.bytes_b.ensure(sizeof(float) * 64 * (size_t)std::max(n2, 1));
+  s.bytes_a.ensure(sizeof(float) * dim * (size_t)n1);
+  s.bytes_b.ensure(sizeof(float) * dim * (size_t)std::max(n2, 1));
   s.bytes_c.ensure(match_scratch_bytes(n1, std::max(n2, 1)));
   UVO_CUDA(cudaMemsetAsync(s.bytes_c.get(), 0, match_scratch_bytes(n1, std::max(n2, 1)), c.stream));
   s.bytes_d.ensure(sizeof(uvo_dmatch) * (size_t)n1 + 16);
-  UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), d1, sizeof(float) * 64 * (size_t)n1, cudaMemcpyHostToDevice, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), d1, sizeof(float) * dim * (size_t)n1, cudaMemcpyHostToDevice, c.stream));
   if (n2 > 0)
-    UVO_CUDA(cudaMemcpyAsync(s.bytes_b.get(), d2, sizeof(float) * 64 * (size_t)n2, cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(s.bytes_b.get(), d2, sizeof(float) * dim * (size_t)n2, cudaMemcpyHostToDevice, c.stream));
   MatchArgs a{};
   a.q = (const float*)s.bytes_a.get();
   a.t = (const float*)s.bytes_b.get();
   a.nq = n1;
   a.nt = n2;
+  a.dim = dim;
+  a.exact_only = ctx->match_exact_only;
   a.ratio = ratio;
   match_bind_scratch(a, s.bytes_c.get(), n1, std::max(n2, 1));
   if (gate && n2 > 0) {
@@ -450,6 +454,12 @@ int uvo_knn_match2(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n
 int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count) {
   if (!ctx || !count) return UVO_ERR_INVALID;
   *count = ctx->last_match_fallbacks;
+  return UVO_OK;
+}
+
+int uvo_match_exact_only(uvo_ctx* ctx, int enable) {
+  if (!ctx) return UVO_ERR_INVALID;
+  ctx->match_exact_only = enable != 0;
   return UVO_OK;
 }
 

@@ -222,6 +222,9 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
   UVO_REQUIRE(w > 0 && h > 0 && left && right && R_right && t_right && prm, "uvo_stereo_create: bad argument");
   UVO_REQUIRE(prm->pnp_method_flag == 1, "only SOLVEPNP_EPNP (pnp_method_flag = 1) is implemented");
   UVO_REQUIRE(prm->max_features >= 64, "max_features too small");
+  if (prm->surf_extended)  // the lane buffers and the gathers between the stages carry 64-float rows
+    throw InvalidArg{"uvo_stereo: extended (128-d) SURF descriptors are served by the stage-level calls only",
+                     UVO_ERR_UNSUPPORTED};
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
   s->ctx = ctx;

@@ -39,10 +39,11 @@ struct FrontEnd {
       sum[i].ensure((size_t)(w + 1) * (h + 1));
       raw[i].ensure(capacity);
       kps[i].ensure(capacity);
-      const bool fresh = desc[i].n < (size_t)capacity * 64;
-      desc[i].ensure((size_t)capacity * 64);
+      // sized for extended (128-d) rows; the row stride in use is 64 unless surf() is asked for extended descriptors
+      const bool fresh = desc[i].n < (size_t)capacity * 128;
+      desc[i].ensure((size_t)capacity * 128);
       // rows past the live count are read (and ignored) by the matcher's TMA tiles: keep them finite
-      if (fresh) UVO_CUDA(cudaMemset(desc[i].get(), 0, (size_t)capacity * 64 * sizeof(float)));
+      if (fresh) UVO_CUDA(cudaMemset(desc[i].get(), 0, (size_t)capacity * 128 * sizeof(float)));
       rank[i].ensure(capacity);
       patch[i].ensure((size_t)capacity * 448);
     }
@@ -96,7 +97,7 @@ struct FrontEnd {
   // SURF::detectAndCompute on images [first, first+count); `with_integral` = false when the caller already ran
   // integral() for those slots (the stereo pipeline does, per image, on two streams)
   void surf(Ctx& c, int first, int count, const uvo_params& p, bool with_integral = true) {
-    UVO_REQUIRE(!p.surf_extended, "SURF extended (128-d) descriptors are not implemented");
+    const int dd = p.surf_extended ? 128 : 64;  // floats per descriptor row (SURF::descriptorSize())
     if (!geom_valid || geom_thr != (double)p.surf_min_hessian || geom_oct != p.surf_octaves ||
         geom_lay != p.surf_octave_layers) {
       geom = make_surf_geom(w, h, (double)p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers);
@@ -110,13 +111,13 @@ struct FrontEnd {
     SurfBatch b = batch(first, count);
     launch_surf_detect(c, geom, b, capacity);
     launch_surf_sort(c, b, capacity);
-    launch_surf_describe(c, geom, b, capacity, p.surf_upright);
+    launch_surf_describe(c, geom, b, capacity, p.surf_upright, p.surf_extended);
     // describe can delete keypoints only in oriented mode or when the image is smaller than the largest
     // gradient wavelet (2*round(2*264*1.2/9) = 142)
     if (!p.surf_upright || std::min(w, h) + 1 < 142) {
       tmp_kps.ensure((size_t)2 * capacity);
-      tmp_desc.ensure((size_t)2 * capacity * 64);
-      launch_surf_compact(c, b, capacity, tmp_kps.get(), tmp_desc.get());
+      tmp_desc.ensure((size_t)2 * capacity * dd);
+      launch_surf_compact(c, b, capacity, tmp_kps.get(), tmp_desc.get(), dd);
     }
   }
 };

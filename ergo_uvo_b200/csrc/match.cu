@@ -4,9 +4,10 @@
 //
 //  k_knn_prep    -|t|^2/2 per train row and max |t|^2.
 //  k_knn_tc      the Nq x Nt descriptor similarity matrix on the 5th-gen tensor cores.  One CTA owns a 128-query
-//                tile and a contiguous chunk of train tiles.  A TMA producer warp streams 128 x 64 f32 train tiles
-//                (two SWIZZLE_128B atoms of 32 floats) through a 4-stage shared-memory ring; one elected thread issues
-//                tcgen05.mma.kind::tf32 (M = 128, N = 128, 8 k-steps of 8) into one of four 128-column TMEM
+//                tile and a contiguous chunk of train tiles.  A TMA producer warp streams 128 x D f32 train tiles
+//                (D / 32 SWIZZLE_128B atoms of 32 floats; D = 64, or 128 for extended SURF) through a 4-stage (D = 128:
+//                2-stage) shared-memory ring; one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = 128,
+//                D / 8 k-steps of 8) into one of four 128-column TMEM
 //                accumulators; sixteen epilogue warps read the accumulators back with tcgen05.ld (each thread owns
 //                one query row and a quarter of the tile's columns), add -|t|^2/2 and keep the four largest
 //                similarities per (row, column quarter) with a branch-free bitonic network on index-carrying keys.
@@ -35,21 +36,29 @@ namespace uvo {
 
 // ------------------------------------------------------------------------------------------------ geometry
 constexpr int TILE = 128;          // queries per CTA == train rows per MMA tile
-constexpr int STAGES = 4;          // shared-memory ring depth (train tiles)
 constexpr int ACC = 4;             // TMEM accumulator buffers of 128 columns (4 x 128 = all 512 columns)
 constexpr int ATOM_BYTES = TILE * 128;     // one SWIZZLE_128B atom: 128 rows x 32 floats
-constexpr int TILE_BYTES = 2 * ATOM_BYTES; // 128 rows x 64 floats
 constexpr int MAX_CHUNK_TILES = 32;        // train tiles per CTA at most (bounds the -|t|^2/2 table in smem)
 constexpr int EPI_WARPS = 16;
 constexpr int TC_THREADS = 32 * (2 + EPI_WARPS);  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..17 epilogue
 constexpr int TOPK = MATCH_TOPK;
 constexpr int MATCH_MAX_LISTS = MATCH_MAX_CHUNKS * 4;  // (chunk, column quarter) candidate lists per query
-constexpr int SMEM_A = 0;
-constexpr int SMEM_B = SMEM_A + TILE_BYTES;
-constexpr int SMEM_HB = SMEM_B + STAGES * TILE_BYTES;
-constexpr int SMEM_BAR = SMEM_HB + MAX_CHUNK_TILES * TILE * 4;
-constexpr int SMEM_TOTAL = SMEM_BAR + 256;
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to align the base to 1024 B (SWIZZLE_128B requirement)
+// shared-memory plan of k_knn_tc for D floats per descriptor row (64: SURF, 128: extended SURF).  A tile is D / 32
+// SWIZZLE_128B atoms; the 128-d ring is two stages deep so that query tile + ring + table stay under 227 KB.
+template <int D>
+struct TcGeom {
+  static_assert(D == 64 || D == 128, "descriptor rows are 64 or 128 floats");
+  static constexpr int ATOMS = D / 32;
+  static constexpr int TILE_BYTES = ATOMS * ATOM_BYTES;  // 128 rows x D floats
+  static constexpr int STAGES = D == 64 ? 4 : 2;         // shared-memory ring depth (train tiles)
+  static constexpr int SMEM_A = 0;
+  static constexpr int SMEM_B = SMEM_A + TILE_BYTES;
+  static constexpr int SMEM_HB = SMEM_B + STAGES * TILE_BYTES;
+  static constexpr int SMEM_BAR = SMEM_HB + MAX_CHUNK_TILES * TILE * 4;
+  static constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+  static constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to align the base to 1024 B (SWIZZLE_128B requirement)
+  static_assert(SMEM_ALLOC <= 227 * 1024, "k_knn_tc shared memory");
+};
 
 // number of train chunks (grid.y CTAs that do work) for ntq query tiles and ntt train tiles; the same formula runs
 // on the device in k_knn_tc and k_knn_rerank.
@@ -141,13 +150,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
 constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((TILE >> 3) << 17) | ((TILE >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------ exact arithmetic
-// squared L2 distance of two 64-float rows in the accumulation order of OpenCV's normL2Sqr_ (baseline SIMD build)
-__device__ __forceinline__ float l2sqr64_cv(const float4* __restrict__ q, const float4* __restrict__ t) {
+// squared L2 distance of two D-float rows in the accumulation order of OpenCV's normL2Sqr_ (baseline SIMD build:
+// the same four 4-lane accumulators run over all D / 16 groups of 16 floats)
+template <int D>
+__device__ __forceinline__ float l2sqr_cv(const float4* __restrict__ q, const float4* __restrict__ t) {
   float4 acc[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int it = 0; it < 4; it++)
+  for (int it = 0; it < D / 16; it++)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const float4 tv = t[it * 4 + k], qv = q[it * 4 + k];
@@ -196,13 +207,18 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 
 // ------------------------------------------------------------------------------------------------ k_knn_prep
 // hb[j] = -|t_j|^2 / 2 for every train row, max |t|^2 (for the error bound); 16 lanes per row, coalesced
+template <int D>
 __global__ void __launch_bounds__(256) k_knn_prep(const __grid_constant__ MatchArgs a) {
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
   const int sub = threadIdx.x & 15;
   float n2max = 0.f;
   for (int j = (blockIdx.x * 256 + threadIdx.x) >> 4; j < nt; j += (gridDim.x * 256) >> 4) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.t + (size_t)j * 64) + sub);
-    float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < D / 64; u++) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a.t + (size_t)j * D) + sub + 16 * u);
+      s += fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+    }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (sub == 0) a.hb[j] = -0.5f * s;
@@ -229,10 +245,13 @@ constexpr float HB_PAD = -1e30f;  // -|t|^2/2 of a column past the end of the tr
     hi = _h;                          \
   } while (0)
 
+template <int D>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
          const __grid_constant__ MatchArgs a, const int sms) {
   extern __shared__ uint8_t smem_raw[];
+  using G = TcGeom<D>;
+  constexpr int STAGES = G::STAGES, TILE_BYTES = G::TILE_BYTES, SMEM_BAR = G::SMEM_BAR;
   const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
   const int ntq = (nq + TILE - 1) / TILE, ntt = (nt + TILE - 1) / TILE;
@@ -246,8 +265,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sA = base + SMEM_A, sB = base + SMEM_B;
-  float* s_hb = reinterpret_cast<float*>(smem + SMEM_HB);
+  const uint32_t sA = base + G::SMEM_A, sB = base + G::SMEM_B;
+  float* s_hb = reinterpret_cast<float*>(smem + G::SMEM_HB);
   const uint32_t bar = base + SMEM_BAR;
   // barriers (8 B each): full[STAGES], empty[STAGES], A landed, accumulator full[ACC], accumulator empty[ACC]
   const uint32_t bar_full = bar, bar_empty = bar + 8 * STAGES, bar_a = bar + 8 * (2 * STAGES);
@@ -283,15 +302,16 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     // ===== TMA producer =====
     if (lane == 0) {
       mbar_expect_tx(bar_a, TILE_BYTES);
-      tma_load_2d(sA, &map_q, 0, row0, bar_a);
-      tma_load_2d(sA + ATOM_BYTES, &map_q, 32, row0, bar_a);
+#pragma unroll
+      for (int at = 0; at < G::ATOMS; at++) tma_load_2d(sA + at * ATOM_BYTES, &map_q, 32 * at, row0, bar_a);
       for (int i = 0; i < ntile; i++) {
         const int st = i % STAGES;
         mbar_wait(bar_empty + 8 * st, ((i / STAGES) & 1) ^ 1);
         mbar_expect_tx(bar_full + 8 * st, TILE_BYTES);
         const uint32_t dst = sB + st * TILE_BYTES;
-        tma_load_2d(dst, &map_t, 0, (tile0 + i) * TILE, bar_full + 8 * st);
-        tma_load_2d(dst + ATOM_BYTES, &map_t, 32, (tile0 + i) * TILE, bar_full + 8 * st);
+#pragma unroll
+        for (int at = 0; at < G::ATOMS; at++)
+          tma_load_2d(dst + at * ATOM_BYTES, &map_t, 32 * at, (tile0 + i) * TILE, bar_full + 8 * st);
       }
     }
   } else if (warp == 1) {
@@ -305,7 +325,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         tc_fence_after();
         const uint32_t bs = sB + st * TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {  // 8 k-steps of 8 floats (32 B); 4 per swizzle atom
+        for (int k = 0; k < D / 8; k++) {  // k-steps of 8 floats (32 B); 4 per swizzle atom
           const uint32_t off = (k >> 2) * ATOM_BYTES + (k & 3) * 32;
           tc_mma_tf32(tmem + ab * TILE, smem_desc_sw128(sA + off), smem_desc_sw128(bs + off), IDESC_TF32_128x128,
                       k > 0);
@@ -395,13 +415,15 @@ __device__ __forceinline__ Knn2 knn2_from_keys(unsigned long long b0, unsigned l
 // per-query bound on |(|q|^2 - 2 key) - D| for every (query, train) pair, D = the f32 value normL2Sqr_ computes:
 // tf32 truncation of both operands (2^-8 |q||t|), f32 accumulation on either side, key quantisation (2^-13 |s|,
 // |s| <= |q||t| + |t|^2/2); 1 % slack on top
-__device__ __forceinline__ float match_eps(float nq2, float tn2) {
+// acc: relative bound of the f32 accumulation over one row (4e-5 for 64 terms, twice that for 128)
+__device__ __forceinline__ float match_eps(float nq2, float tn2, float acc) {
   const float qt = sqrtf(nq2 * tn2);
-  return 1.01f * (((float)MATCH_TF32_EPS + 4e-5f) * qt + 4e-5f * (nq2 + tn2) + 2.6e-4f * (qt + 0.5f * tn2));
+  return 1.01f * (((float)MATCH_TF32_EPS + acc) * qt + acc * (nq2 + tn2) + 2.6e-4f * (qt + 0.5f * tn2));
 }
 
 // one warp per query: prune the candidates by their approximate keys, exact distances of the survivors, exact top
 // two, completeness check
+template <int D>
 __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_constant__ MatchArgs a, const int sms) {
   const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
   const int nt = a.nt_dev ? min(*a.nt_dev, a.nt) : a.nt;
@@ -412,15 +434,15 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
   const float tn2 = __uint_as_float(*a.tn2max);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int qi = blockIdx.x * RR_WARPS + warp; qi < nq; qi += gridDim.x * RR_WARPS) {
-    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)qi * 64);
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)qi * D);
     float nq2 = 0.f;
-    if (lane < 16) {
+    if (lane < D / 4) {
       const float4 v = qp[lane];
       nq2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nq2 += __shfl_xor_sync(0xffffffffu, nq2, o);
-    const float eps = match_eps(nq2, tn2);
+    const float eps = match_eps(nq2, tn2, 4e-5f * (D / 64));
     // this lane's candidate keys: c = lane + 32 u  (n_cand <= 128)
     float key[4];
     float m1 = -INFINITY, m2 = -INFINITY;  // lane-local largest two present keys
@@ -461,7 +483,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
         const int list = c / TOPK, chunk = list >> 2, cq = list & 3;
         const uint32_t kb = __float_as_uint(key[u]) & KEY_MASK;
         const int j = (chunk * per + (int)(kb >> 5)) * TILE + cq * 32 + (int)(kb & 31);
-        const float d = __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64)));
+        const float d = __fsqrt_rn(l2sqr_cv<D>(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * D)));
         const unsigned long long key2 = knn_key(d, j);
         if (key2 < k0) {
           k1 = k0;
@@ -495,6 +517,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) k_knn_rerank(const __grid_const
 // block to finish a query merges the EX_SLICES partial results (threadfence + counter).
 constexpr int EX_THREADS = 256;
 
+template <int D>
 __global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant__ MatchArgs a) {
   __shared__ Knn2 s_part[EX_THREADS / 32];
   __shared__ int s_last;
@@ -505,10 +528,10 @@ __global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant_
   const int j0 = blockIdx.x * rows, j1 = min(nt, j0 + rows);
   for (int f = blockIdx.y; f < nf; f += gridDim.y) {
     const int fq = a.fb_list[f];
-    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)fq * 64);
+    const float4* qp = reinterpret_cast<const float4*>(a.q + (size_t)fq * D);
     Knn2 best{FLT_MAX, FLT_MAX, -1, -1};
     for (int j = j0 + threadIdx.x; j < j1; j += EX_THREADS)
-      knn2_insert(best, __fsqrt_rn(l2sqr64_cv(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * 64))), j);
+      knn2_insert(best, __fsqrt_rn(l2sqr_cv<D>(qp, reinterpret_cast<const float4*>(a.t + (size_t)j * D))), j);
     // merge by (distance, index): the global second is the winner's second or somebody else's first
     unsigned long long k0 = best.i0 >= 0 ? knn_key(best.d0, best.i0) : KEY_NONE;
     unsigned long long k1 = best.i1 >= 0 ? knn_key(best.d1, best.i1) : KEY_NONE;
@@ -545,6 +568,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_knn_exact(const __grid_constant_
     }
     __syncthreads();
   }
+}
+
+// diagnostics route (MatchArgs::exact_only): every query is flagged, k_knn_exact does all the work
+__global__ void __launch_bounds__(256) k_knn_flag_all(const __grid_constant__ MatchArgs a) {
+  const int nq = a.nq_dev ? min(*a.nq_dev, a.nq) : a.nq;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nq; i += gridDim.x * 256) a.fb_list[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.n_flagged = nq;
 }
 
 // ------------------------------------------------------------------------------------------------ k_knn_compact
@@ -619,11 +649,11 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// rows x 64 f32 row-major, boxes of 128 rows x 32 floats (one SWIZZLE_128B atom); rows past the end read as zero
-static CUtensorMap make_desc_map(const float* base, int rows) {
+// rows x dim f32 row-major, boxes of 128 rows x 32 floats (one SWIZZLE_128B atom); rows past the end read as zero
+static CUtensorMap make_desc_map(const float* base, int rows, int dim) {
   CUtensorMap m;
-  const cuuint64_t dims[2] = {64, (cuuint64_t)(rows > 0 ? rows : 1)};
-  const cuuint64_t strides[1] = {64 * sizeof(float)};
+  const cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)(rows > 0 ? rows : 1)};
+  const cuuint64_t strides[1] = {(cuuint64_t)dim * sizeof(float)};
   const cuuint32_t box[2] = {32, TILE};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
@@ -660,6 +690,40 @@ void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
   a.tn2max = (unsigned*)(p + 32);
 }
 
+template <int D>
+static void launch_match_dim(Ctx& c, const MatchArgs& a) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    UVO_CUDA(cudaFuncSetAttribute(k_knn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeom<D>::SMEM_ALLOC));
+    attr_done = true;
+  }
+  if (a.exact_only) {
+    UVO_KERNEL(c, "k_knn_flag_all");
+    k_knn_flag_all<<<std::min(div_up(a.nq, 256), c.sm_count), 256, 0, c.stream>>>(a);
+    UVO_LAUNCH_CHECK(c);
+  } else if (a.nt > 0) {
+    UVO_KERNEL(c, "k_knn_prep");
+    k_knn_prep<D><<<std::min(div_up(a.nt, 16), 2 * c.sm_count), 256, 0, c.stream>>>(a);
+    UVO_LAUNCH_CHECK(c);
+    const CUtensorMap mq = make_desc_map(a.q, a.nq, D), mt = make_desc_map(a.t, a.nt, D);
+    UVO_KERNEL(c, "k_knn_tc");
+    k_knn_tc<D><<<dim3(div_up(a.nq, TILE), MATCH_MAX_CHUNKS), TC_THREADS, TcGeom<D>::SMEM_ALLOC, c.stream>>>(mq, mt, a,
+                                                                                                            c.sm_count);
+    UVO_LAUNCH_CHECK(c);
+  }
+  if (!a.exact_only) {
+    UVO_KERNEL(c, "k_knn_rerank");
+    k_knn_rerank<D><<<std::min(div_up(a.nq, RR_WARPS), 8 * c.sm_count), RR_WARPS * 32, 0, c.stream>>>(a, c.sm_count);
+    UVO_LAUNCH_CHECK(c);
+  }
+  UVO_KERNEL(c, "k_knn_exact");
+  k_knn_exact<D><<<dim3(MATCH_EX_SLICES, 16), EX_THREADS, 0, c.stream>>>(a);
+  UVO_LAUNCH_CHECK(c);
+  UVO_KERNEL(c, "k_knn_compact");
+  k_knn_compact<<<1, 1024, 0, c.stream>>>(a);
+  UVO_LAUNCH_CHECK(c);
+}
+
 void launch_match(Ctx& c, const MatchArgs& a) {
   if (a.nq <= 0) {
     UVO_CUDA(cudaMemsetAsync(a.n_matches, 0, sizeof(int), c.stream));
@@ -668,29 +732,12 @@ void launch_match(Ctx& c, const MatchArgs& a) {
   UVO_REQUIRE(a.nt <= MATCH_MAX_CHUNKS * MAX_CHUNK_TILES * TILE && a.nq <= 32768,
               "matcher: more than 32768 descriptors in one set");
   UVO_REQUIRE(((uintptr_t)a.q & 15) == 0 && ((uintptr_t)a.t & 15) == 0, "matcher: descriptors must be 16-byte aligned");
-  static bool attr_done = false;
-  if (!attr_done) {
-    UVO_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    attr_done = true;
-  }
-  if (a.nt > 0) {
-    UVO_KERNEL(c, "k_knn_prep");
-    k_knn_prep<<<std::min(div_up(a.nt, 16), 2 * c.sm_count), 256, 0, c.stream>>>(a);
-    UVO_LAUNCH_CHECK(c);
-    const CUtensorMap mq = make_desc_map(a.q, a.nq), mt = make_desc_map(a.t, a.nt);
-    UVO_KERNEL(c, "k_knn_tc");
-    k_knn_tc<<<dim3(div_up(a.nq, TILE), MATCH_MAX_CHUNKS), TC_THREADS, SMEM_ALLOC, c.stream>>>(mq, mt, a, c.sm_count);
-    UVO_LAUNCH_CHECK(c);
-  }
-  UVO_KERNEL(c, "k_knn_rerank");
-  k_knn_rerank<<<std::min(div_up(a.nq, RR_WARPS), 8 * c.sm_count), RR_WARPS * 32, 0, c.stream>>>(a, c.sm_count);
-  UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_knn_exact");
-  k_knn_exact<<<dim3(MATCH_EX_SLICES, 16), EX_THREADS, 0, c.stream>>>(a);
-  UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_knn_compact");
-  k_knn_compact<<<1, 1024, 0, c.stream>>>(a);
-  UVO_LAUNCH_CHECK(c);
+  if (a.dim == 64)
+    launch_match_dim<64>(c, a);
+  else if (a.dim == 128)
+    launch_match_dim<128>(c, a);
+  else
+    throw InvalidArg{"matcher: descriptor rows must be 64 (SURF) or 128 (extended SURF) floats", UVO_ERR_UNSUPPORTED};
 }
 
 }  // namespace uvo

@@ -18,11 +18,13 @@ constexpr int MATCH_TOPK = 4;        // candidates kept per (query, chunk, colum
 constexpr double MATCH_TF32_EPS = 0.00390625 * 1.01;
 
 struct MatchArgs {
-  const float* q;      // nq x 64, 16-byte aligned
-  const float* t;      // nt x 64
+  const float* q;      // nq x dim, 16-byte aligned
+  const float* t;      // nt x dim
   const int* nq_dev;   // device counts (nullable: use nq/nt)
   const int* nt_dev;
   int nq, nt;          // host-known counts or upper bounds (capacity) when *_dev is set
+  int dim = 64;        // floats per descriptor row: 64 (SURF) or 128 (extended SURF)
+  int exact_only = 0;  // diagnostics: skip the tensor-core pass, every query takes the exact full scan
   float ratio;
   // optional stereo epipolar / disparity gate applied with the ratio test (off when gate_kq == nullptr):
   // keep iff |y_q - y_t| <= gate_dy and gate_dmin <= x_q - x_t <= gate_dmax

@@ -217,6 +217,9 @@ int uvo_mono_create(uvo_ctx* ctx, int width, int height, const uvo_camera* cam, 
   const int rc = guarded(&ctx->c, [&] {
     UVO_REQUIRE(width > 0 && height > 0 && cam && prm, "uvo_mono_create: bad argument");
     UVO_REQUIRE(prm->max_features >= 64, "max_features too small");
+    if (prm->surf_extended)  // prev_desc and the matcher call of this handle carry 64-float rows
+      throw InvalidArg{"uvo_mono: extended (128-d) SURF descriptors are served by the stage-level calls only",
+                       UVO_ERR_UNSUPPORTED};
     Ctx& c = ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
     m->ctx = ctx;

@@ -1137,7 +1137,9 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
 }
 
 // Descriptor vector from the 21x21 patch: one warp per keypoint.
+// EXT = extended (128-d) descriptors: eight sums per 5x5 cell, split by the sign of the other gradient (A.4).
 constexpr int VEC_WARPS = 8;
+template <bool EXT>
 __global__ void __launch_bounds__(VEC_WARPS * 32) k_surf_vector(const __grid_constant__ SurfBatch b) {
   __shared__ __align__(16) uint8_t s_p[VEC_WARPS][PATCH_STRIDE];
   __shared__ __align__(16) float s_dx[VEC_WARPS][400];
@@ -1166,44 +1168,64 @@ __global__ void __launch_bounds__(VEC_WARPS * 32) k_surf_vector(const __grid_con
     }
     __syncwarp();
     // ---- 4x4 cells x (sum dx, sum dy, sum |dx|, sum |dy|), y-major over each 5x5 cell ----
-    float v2[2];
+    // extended: per cell (sum dx, sum |dx|) over dy >= 0, then over dy < 0, (sum dy, sum |dy|) over dx >= 0, then
+    // over dx < 0; an excluded sample leaves the running sum untouched, as the CPU's if / else does
+    constexpr int NV = EXT ? 4 : 2;  // outputs per lane
+    float v2[NV];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < NV; half++) {
       const int q = lane + 32 * half;
-      const int cell = q >> 2, comp = q & 3, ci = cell >> 2, cj = cell & 3;
-      const float* srcv = ((comp & 1) ? DY : DX) + ci * 100 + cj * 5;
-      const bool use_abs = comp >= 2;
-      float e[25];
-#pragma unroll
-      for (int y = 0; y < 5; y++)
-#pragma unroll
-        for (int x = 0; x < 5; x++) e[y * 5 + x] = srcv[y * 20 + x];
       float v = 0.f;
+      if (EXT) {
+        const int cell = q >> 3, comp = q & 7, ci = cell >> 2, cj = cell & 3;
+        const int o = ci * 100 + cj * 5;
+        const float* srcv = (comp & 4 ? DY : DX) + o;  // the summed gradient
+        const float* selv = (comp & 4 ? DX : DY) + o;  // the gradient whose sign selects
+        const bool use_abs = comp & 1, want_neg = comp & 2;
 #pragma unroll
-      for (int q2 = 0; q2 < 25; q2++) v = __fadd_rn(v, use_abs ? fabsf(e[q2]) : e[q2]);
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+          for (int x = 0; x < 5; x++) {
+            const float e = srcv[y * 20 + x];
+            const bool nonneg = selv[y * 20 + x] >= 0.f;  // false for NaN: the CPU's else branch
+            if (nonneg != want_neg) v = __fadd_rn(v, use_abs ? fabsf(e) : e);
+          }
+      } else {
+        const int cell = q >> 2, comp = q & 3, ci = cell >> 2, cj = cell & 3;
+        const float* srcv = ((comp & 1) ? DY : DX) + ci * 100 + cj * 5;
+        const bool use_abs = comp >= 2;
+        float e[25];
+#pragma unroll
+        for (int y = 0; y < 5; y++)
+#pragma unroll
+          for (int x = 0; x < 5; x++) e[y * 5 + x] = srcv[y * 20 + x];
+#pragma unroll
+        for (int q2 = 0; q2 < 25; q2++) v = __fadd_rn(v, use_abs ? fabsf(e[q2]) : e[q2]);
+      }
       v2[half] = v;
     }
     __syncwarp();  // every lane is done reading DX / DY: DX is reused for the fp64 squares
-    double* SQ = (double*)DX;
-    SQ[lane] = (double)__fmul_rn(v2[0], v2[0]);
-    SQ[lane + 32] = (double)__fmul_rn(v2[1], v2[1]);
+    double* SQ = (double*)DX;  // 32 * NV doubles <= 400 floats
+#pragma unroll
+    for (int half = 0; half < NV; half++) SQ[lane + 32 * half] = (double)__fmul_rn(v2[half], v2[half]);
     __syncwarp();
     // ---- L2 normalisation: the squares are summed sequentially in fp64, as the CPU does ----
     float scale = 0.f;
     if (lane == 0) {
       double sq = 0;
 #pragma unroll
-      for (int q = 0; q < 64; q++) sq = __dadd_rn(sq, SQ[q]);
+      for (int q = 0; q < 32 * NV; q++) sq = __dadd_rn(sq, SQ[q]);
       scale = (float)(1. / (sqrt(sq) + (double)FLT_EPSILON));
     }
     scale = __shfl_sync(0xffffffffu, scale, 0);
-    im.desc[(size_t)k * 64 + lane] = __fmul_rn(v2[0], scale);
-    im.desc[(size_t)k * 64 + 32 + lane] = __fmul_rn(v2[1], scale);
+#pragma unroll
+    for (int half = 0; half < NV; half++)
+      im.desc[(size_t)k * (32 * NV) + 32 * half + lane] = __fmul_rn(v2[half], scale);
     __syncwarp();
   }
 }
 
-void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright) {
+void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright, int extended) {
   upload_tables(c);
   const SpanTable* tab = span_table(c);
   const int blocks = std::min(capacity, 8 * c.sm_count);
@@ -1212,19 +1234,22 @@ void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int cap
   UVO_LAUNCH_CHECK(c);
   const int vblocks = std::min(div_up(capacity, VEC_WARPS), 4 * c.sm_count);
   UVO_KERNEL(c, "k_surf_vector");
-  k_surf_vector<<<dim3(vblocks, b.n_img), VEC_WARPS * 32, 0, c.stream>>>(b);
+  if (extended)
+    k_surf_vector<true><<<dim3(vblocks, b.n_img), VEC_WARPS * 32, 0, c.stream>>>(b);
+  else
+    k_surf_vector<false><<<dim3(vblocks, b.n_img), VEC_WARPS * 32, 0, c.stream>>>(b);
   UVO_LAUNCH_CHECK(c);
 }
 
 // ------------------------------------------------------------------------------------------------ compaction
 // single block per image: ordered removal of keypoints marked size <= 0
 __global__ void __launch_bounds__(1024) k_surf_compact(const __grid_constant__ SurfBatch b, uvo_keypoint* tmp_kps, float* tmp_desc,
-                                                       int capacity) {
+                                                       int capacity, int dd) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const SurfImage& im = b.im[blockIdx.x];
   uvo_keypoint* tk = tmp_kps + (size_t)blockIdx.x * capacity;
-  float* td = tmp_desc + (size_t)blockIdx.x * capacity * 64;
+  float* td = tmp_desc + (size_t)blockIdx.x * capacity * dd;
   const int n = im.counters[1];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
@@ -1240,7 +1265,7 @@ __global__ void __launch_bounds__(1024) k_surf_compact(const __grid_constant__ S
     if (keep) {
       const int dst = off + __popc(bal & ((1u << lane) - 1));
       tk[dst] = im.kps[k];
-      for (int q = 0; q < 64; q++) td[(size_t)dst * 64 + q] = im.desc[(size_t)k * 64 + q];
+      for (int q = 0; q < dd; q++) td[(size_t)dst * dd + q] = im.desc[(size_t)k * dd + q];
     }
     __syncthreads();
     if (tid == 0) {
@@ -1253,13 +1278,13 @@ __global__ void __launch_bounds__(1024) k_surf_compact(const __grid_constant__ S
   const int m = s_base;
   __syncthreads();
   for (int k = tid; k < m; k += 1024) im.kps[k] = tk[k];
-  for (int q = tid; q < m * 64; q += 1024) im.desc[q] = td[q];
+  for (int q = tid; q < m * dd; q += 1024) im.desc[q] = td[q];
   if (tid == 0) im.counters[1] = m;
 }
 
-void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc) {
+void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc, int dd) {
   UVO_KERNEL(c, "k_surf_compact");
-  k_surf_compact<<<b.n_img, 1024, 0, c.stream>>>(b, tmp_kps, tmp_desc, capacity);
+  k_surf_compact<<<b.n_img, 1024, 0, c.stream>>>(b, tmp_kps, tmp_desc, capacity, dd);
   UVO_LAUNCH_CHECK(c);
 }
 

@@ -45,7 +45,7 @@ struct SurfImage {
   const int32_t* sum = nullptr;   // integral (h+1)x(w+1)
   uvo_keypoint* raw = nullptr;    // unordered detections
   uvo_keypoint* kps = nullptr;    // sorted (OpenCV order), compacted
-  float* desc = nullptr;          // capacity x 64
+  float* desc = nullptr;          // capacity x 64 (capacity x 128 when extended)
   uint8_t* patch = nullptr;       // capacity x 448: the 21x21 u8 descriptor patches (k_surf_patch -> k_surf_vector)
   int* rank = nullptr;            // capacity ints, zeroed per frame (rank sort accumulator)
   int* counters = nullptr;        // [0] raw count (may exceed capacity => overflow), [1] final count, [2..3] spare
@@ -60,10 +60,12 @@ struct SurfBatch {
 void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity);
 // rank sort raw -> kps in KeypointGreater order, sets counters[1] = min(counters[0], capacity)
 void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity);
-// upright/oriented 64-d descriptors for kps[0..counters[1]); sets angle; marks deleted keypoints with size=-1
-void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright);
+// upright/oriented descriptors (64-d, or 128-d rows when `extended`) for kps[0..counters[1]); sets angle; marks
+// deleted keypoints with size=-1
+void launch_surf_describe(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity, int upright, int extended);
 // order-preserving removal of keypoints with size <= 0 (only needed when describe can delete: oriented mode or
 // images smaller than the largest gradient wavelet)
-void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc);
+// (dd = floats per descriptor row, 64 or 128)
+void launch_surf_compact(Ctx& c, const SurfBatch& b, int capacity, uvo_keypoint* tmp_kps, float* tmp_desc, int dd);
 
 }  // namespace uvo

@@ -227,6 +227,10 @@ class Context:
         self._ck(self.lib.uvo_knn_match2(self.h, _p(d1), d1.shape[0], _p(d2), d2.shape[0], d1.shape[1], _p(out)))
         return out
 
+    def match_exact_only(self, enable):
+        """diagnostics: route every query of the stage-level matcher calls through the exact full scan"""
+        self._ck(self.lib.uvo_match_exact_only(self.h, int(bool(enable))))
+
     def match_last_fallbacks(self):
         n = C.c_int(0)
         self._ck(self.lib.uvo_match_last_fallbacks(self.h, C.byref(n)))

@@ -161,7 +161,8 @@ UVO_API int uvo_integral(uvo_ctx* ctx, const uint8_t* gray_host, int width, int 
 /* ---------------------------------------------------------------------------------------------------- K4-K7 */
 /* void detect_features(Mat img, vector<KeyPoint>&, Mat& descriptors) -- VO_utility.h:100, VO_utility.cpp:114-119:
  * SURF::create(hess, octaves, layers, extended, upright)->detectAndCompute.  Keypoints come back in OpenCV's order
- * (response desc, size desc, octave desc, y desc, x asc); descriptors row-major n x 64 f32. */
+ * (response desc, size desc, octave desc, y desc, x asc); descriptors row-major n x 64 f32, or n x 128 when
+ * prm->surf_extended is set (SURF_EXTENDED, VO_utility.h:86) -- `desc_host` must hold capacity x 128 floats then. */
 UVO_API int uvo_detect_features(uvo_ctx* ctx, const uint8_t* gray_host, int width, int height, size_t pitch,
                                 const uvo_params* prm, uvo_keypoint* kps_host, float* desc_host, int capacity,
                                 int* count);
@@ -174,7 +175,8 @@ UVO_API int uvo_sort_keypoints(uvo_ctx* ctx, const uvo_keypoint* kps_in_host, in
 
 /* ---------------------------------------------------------------------------------------------------- K8 */
 /* void match_features(vector<KeyPoint>, vector<KeyPoint>, Mat d1, Mat d2, vector<DMatch>&) -- VO_utility.h:109-110,
- * VO_utility.cpp:515-573: BFMatcher(NORM_L2).knnMatch(k=2) + Lowe ratio.  Matches in query order. `dim` = 64. */
+ * VO_utility.cpp:515-573: BFMatcher(NORM_L2).knnMatch(k=2) + Lowe ratio.  Matches in query order. `dim` = 64, or 128
+ * for extended SURF descriptors (SURF_EXTENDED, VO_utility.h:86; anything else: UVO_ERR_UNSUPPORTED). */
 UVO_API int uvo_match_features(uvo_ctx* ctx, const float* desc1_host, int n1, const float* desc2_host, int n2,
                                int dim, float ratio, uvo_dmatch* matches_host, int* count);
 /* match_features followed by the optional stereo epipolar / disparity gate described at uvo_params.stereo_gate
@@ -191,6 +193,9 @@ UVO_API int uvo_knn_match2(uvo_ctx* ctx, const float* desc1_host, int n1, const 
  * by the exact full scan because the tensor-core candidate set could not be proven complete (results are exact
  * either way; this is a performance counter) */
 UVO_API int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count);
+/* diagnostics: when enabled, the stage-level matcher calls of this context skip the tensor-core candidate pass and
+ * resolve every query by the exact full scan (same results, much slower); tests use it to cross-check the two routes */
+UVO_API int uvo_match_exact_only(uvo_ctx* ctx, int enable);
 
 /* ---------------------------------------------------------------------------------------------------- K9, K11, K12 */
 /* bool select_estimation_method(const vector<Point2f>&, const vector<Point2f>&) -- VO_utility.cpp:725-748 */

@@ -19,11 +19,21 @@ def test_knn_golden(oracle):
     assert np.array_equal(k["distance"].view(np.uint32), z["dist"].view(np.uint32))  # bit-equal distances
 
 
+def test_knn_golden_128(oracle):
+    """extended-SURF rows (SURF_EXTENDED, VO_utility.h:86): fixture from cv2 4.13 (tools/make_golden.py matcher128)"""
+    z = np.load(os.path.join(GOLD, "matcher128_120x160.npz"))
+    k = oracle.knn2(z["q"], z["t"])
+    assert np.array_equal(k["trainIdx"], z["idx"])
+    assert np.array_equal(k["distance"].view(np.uint32), z["dist"].view(np.uint32))
+    assert not (z["idx"][:, 0] == 9).any()  # train rows 5 and 9 are identical: the lower index always comes first
+
+
 @pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
-def test_knn_live_cv2(oracle):
+@pytest.mark.parametrize("dim", [64, 128])
+def test_knn_live_cv2(oracle, dim):
     rs = np.random.RandomState(5)
-    a = np.abs(rs.randn(700, 64)).astype(np.float32)
-    b = np.abs(rs.randn(900, 64)).astype(np.float32)
+    a = np.abs(rs.randn(700, dim)).astype(np.float32)
+    b = np.abs(rs.randn(900, dim)).astype(np.float32)
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     kk = cv2.BFMatcher(cv2.NORM_L2).knnMatch(a, b, 2)

@@ -89,3 +89,22 @@ def test_upright_patch_is_cv2_resize_of_the_window(oracle):
         ii, jj = np.meshgrid(np.arange(ws), np.arange(ws), indexing="ij")
         win = g[np.clip(sy - jj, 0, 199), np.clip(sx + ii, 0, 239)]
         assert np.array_equal(patch, cv2.resize(np.ascontiguousarray(win), (21, 21), interpolation=cv2.INTER_AREA))
+
+
+def test_extended_descriptor_refines_the_standard_one(oracle):
+    """SURF_EXTENDED (VO_utility.h:86, VO_utility.cpp:117): the 128-d vector splits each of the four sums of a cell by
+    the sign of the other gradient, so pairwise sums of its entries give back the 64-d vector up to the normalisation
+    and f32 summation order; the keypoints do not depend on the flag."""
+    g = noise_image(240, 320, seed=9)
+    k64, d64 = oracle.surf_detect_and_compute(g, 200)
+    k128, d128 = oracle.surf_detect_and_compute(g, 200, extended=True)
+    assert len(k64) > 50 and k64.tobytes() == k128.tobytes()
+    assert d128.shape == (len(k64), 128)
+    assert np.allclose(np.linalg.norm(d128.astype(np.float64), axis=1), 1.0, atol=1e-5)
+    e = d128.astype(np.float64).reshape(-1, 16, 8)
+    s = np.stack([e[..., 0] + e[..., 2], e[..., 4] + e[..., 6], e[..., 1] + e[..., 3], e[..., 5] + e[..., 7]], -1)
+    s = s.reshape(-1, 64)
+    s /= np.linalg.norm(s, axis=1, keepdims=True)
+    assert np.abs(s - d64).max() < 1e-5
+    # |dx| sums dominate the signed ones, half by half
+    assert np.all(e[..., 1] >= np.abs(e[..., 0]) - 1e-6) and np.all(e[..., 7] >= np.abs(e[..., 6]) - 1e-6)

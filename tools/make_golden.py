@@ -61,6 +61,22 @@ def matcher():
     np.savez_compressed(os.path.join(OUT, "matcher_300x400.npz"), q=q, t=t, idx=idx2, dist=dist2)
 
 
+def matcher128():
+    """extended-SURF row length (SURF_EXTENDED, VO_utility.h:86): the same 4 x 4-lane accumulators run over 8 groups"""
+    rs = np.random.RandomState(22)
+    q = np.abs(rs.randn(120, 128)).astype(np.float32)
+    t = np.abs(rs.randn(160, 128)).astype(np.float32)
+    idx = rs.permutation(160)[:40]
+    q[:40] = t[idx] + 0.02 * rs.randn(40, 128).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    t[9] = t[5]
+    knn = cv2.BFMatcher(cv2.NORM_L2, False).knnMatch(q, t, 2)
+    idx2 = np.array([[m.trainIdx for m in row] for row in knn], np.int32)
+    dist2 = np.array([[m.distance for m in row] for row in knn], np.float32)
+    np.savez_compressed(os.path.join(OUT, "matcher128_120x160.npz"), q=q, t=t, idx=idx2, dist=dist2)
+
+
 def pose():
     rs = np.random.RandomState(11)
     n = 600
@@ -97,6 +113,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     imgprep()
     matcher()
+    matcher128()
     pose()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
