@@ -1,5 +1,6 @@
 // shim/VO_utility_shim.cpp -- reference-side binding (NOT compiled in this repository: it needs the OpenCV C++ and
-// ROS headers the reference builds against).
+// ROS headers the reference builds against; see INTEGRATION.md.  tests/test_shim_compiles.py type-checks it against
+// the reference's own VO_utility.h with the declaration-only stand-ins of shim/stubs).
 //
 // Drop-in replacement translation unit for uvo_libraries/src/VO_utility.cpp: it defines the same C++ free functions
 // with the same signatures (uvo_libraries/include/uvo_libraries/VO_utility.h:96-117), reads the same header-defined
@@ -105,7 +106,8 @@ void detect_features(Mat img, vector<KeyPoint>& keypoints, Mat& descriptors) {
   CV_Assert(FEATURE_DETECTOR == "SURF" && img.type() == CV_8UC1);
   uvo_params p = params_from_globals();
   std::vector<uvo_keypoint> k(p.max_features);
-  Mat d(p.max_features, 64, CV_32F);
+  const int dd = p.surf_extended ? 128 : 64;  // SURF::descriptorSize()
+  Mat d(p.max_features, dd, CV_32F);
   int n = 0;
   check(uvo_detect_features(ctx(), img.data, img.cols, img.rows, img.step, &p, k.data(), d.ptr<float>(),
                             p.max_features, &n));
@@ -120,8 +122,10 @@ void match_features(vector<KeyPoint> keypoints1, vector<KeyPoint> keypoints2, Ma
                     vector<DMatch>& matches) {
   std::vector<uvo_dmatch> m(std::max(descriptors1.rows, 1));
   int n = 0;
+  CV_Assert(descriptors1.type() == CV_32F && descriptors2.type() == CV_32F && descriptors1.isContinuous() &&
+            descriptors2.isContinuous() && (descriptors2.rows == 0 || descriptors1.cols == descriptors2.cols));
   check(uvo_match_features(ctx(), descriptors1.ptr<float>(), descriptors1.rows, descriptors2.ptr<float>(),
-                           descriptors2.rows, 64, (float)LOWE_RATIO_THRESHOLD, m.data(), &n));
+                           descriptors2.rows, descriptors1.cols, (float)LOWE_RATIO_THRESHOLD, m.data(), &n));
   ROS_INFO("MATCHES BEFORE LOWE'S RATIO: %d", descriptors1.rows);
   for (int i = 0; i < n; i++) matches.push_back(DMatch(m[i].queryIdx, m[i].trainIdx, m[i].imgIdx, m[i].distance));
   ROS_INFO("MATCHES AFTER LOWE'S RATIO: %lu", matches.size());
@@ -220,8 +224,9 @@ int recover_pose_homography(Mat H, vector<Point2f> inliers1, vector<Point2f> inl
 }
 
 // The three cv:: calls the node makes directly (visual_odometry.h:355/:631, :647, :673) are not part of
-// uvo_libraries.  Under a strictly unchanged node they stay on OpenCV unless this object also interposes them; the
-// one-line node patch is to call these instead:
+// uvo_libraries.  Under a strictly unchanged node they stay on OpenCV unless shim/cv_interpose.cpp (which defines
+// cv::triangulatePoints and cv::solvePnPRansac themselves) is linked in as well; the one-line node patch is to call
+// these instead:
 namespace uvo_shim {
 void triangulatePoints(const Mat& P1, const Mat& P2, const vector<Point2f>& a, const vector<Point2f>& b, Mat& out4) {
   out4.create(4, (int)a.size(), CV_32F);

@@ -1,0 +1,5 @@
+// Declaration-only stand-in (see shim/stubs/README.md)
+#pragma once
+namespace sensor_msgs {
+struct Image {};
+}  // namespace sensor_msgs
