@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) k_gather_after_stereo(const uvo_dmatch* _
                                                              const uvo_keypoint* __restrict__ kL,
                                                              const uvo_keypoint* __restrict__ kR,
                                                              const float* __restrict__ dL, uvo_keypoint* kL_as,
-                                                             uvo_keypoint* kR_as, float* dL_as, GateParams g) {
+                                                             uvo_keypoint* kR_as, float* dL_as, GateParams g,
+                                                             const int c4_shift) {
   const int ns = ctrl->nq_stereo > 0 ? ctrl->n_stereo : 0;
   const int n_as = ns > g.min_features ? ns : 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -70,11 +71,13 @@ __global__ void __launch_bounds__(256) k_gather_after_stereo(const uvo_dmatch* _
     ctrl->nq_temporal = (n_as > 0 && was_init) ? prev_ctrl->n_as : 0;
     if (n_as > 0) st->vo_init = 1;  // the pose stage runs on a side stream: the next frame must already see this
   }
-  const int total = n_as * 16;  // float4 chunks of the descriptors
+  // float4 chunks of the descriptors: 1 << c4_shift per row (16 for 64-float rows, 32 for extended 128-float rows)
+  const int total = n_as << c4_shift;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int i = e >> 4, q = e & 15;
+    const int i = e >> c4_shift, q = e & ((1 << c4_shift) - 1);
     const uvo_dmatch mm = m[i];
-    reinterpret_cast<float4*>(dL_as)[e] = reinterpret_cast<const float4*>(dL)[(size_t)mm.queryIdx * 16 + q];
+    reinterpret_cast<float4*>(dL_as)[e] =
+        reinterpret_cast<const float4*>(dL)[((size_t)mm.queryIdx << c4_shift) + q];
     if (q == 0) {
       kL_as[i] = kL[mm.queryIdx];
       kR_as[i] = kR[mm.trainIdx];
@@ -222,9 +225,6 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
   UVO_REQUIRE(w > 0 && h > 0 && left && right && R_right && t_right && prm, "uvo_stereo_create: bad argument");
   UVO_REQUIRE(prm->pnp_method_flag == 1, "only SOLVEPNP_EPNP (pnp_method_flag = 1) is implemented");
   UVO_REQUIRE(prm->max_features >= 64, "max_features too small");
-  if (prm->surf_extended)  // the lane buffers and the gathers between the stages carry 64-float rows
-    throw InvalidArg{"uvo_stereo: extended (128-d) SURF descriptors are served by the stage-level calls only",
-                     UVO_ERR_UNSUPPORTED};
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
   s->ctx = ctx;
@@ -258,8 +258,9 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
     l.fe.init(w, h, 2, cap);
     l.kL_as.ensure(cap);
     l.kR_as.ensure(cap);
-    l.dL_as.ensure((size_t)cap * 64);
-    UVO_CUDA(cudaMemsetAsync(l.dL_as.get(), 0, (size_t)cap * 64 * sizeof(float), c.stream));
+    const size_t dd = prm->surf_extended ? 128 : 64;  // floats per descriptor row (SURF_EXTENDED, VO_utility.h:86)
+    l.dL_as.ensure((size_t)cap * dd);
+    UVO_CUDA(cudaMemsetAsync(l.dL_as.get(), 0, (size_t)cap * dd * sizeof(float), c.stream));
     l.ctrl.ensure(1);
     UVO_CUDA(cudaMemsetAsync(l.ctrl.get(), 0, sizeof(FrameCtrl), c.stream));
     l.m_stereo.ensure(cap);
@@ -381,6 +382,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ms.nt_dev = cR + 1;
   ms.nq = cap;
   ms.nt = cap;
+  ms.dim = p.surf_extended ? 128 : 64;
   ms.ratio = (float)p.lowe_ratio;
   if (p.stereo_gate) {  // off in the reference's configuration (uvo_params.stereo_gate)
     ms.gate_kq = L.fe.kps[0].get();
@@ -399,7 +401,8 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   UVO_KERNEL(c, "k_gather_after_stereo");
   k_gather_after_stereo<<<2 * c.sm_count, 256, 0, c.stream>>>(L.m_stereo.get(), ctrl, pctrl, s->state.get(),
                                                             L.fe.kps[0].get(), L.fe.kps[1].get(), L.fe.desc[0].get(),
-                                                            L.kL_as.get(), L.kR_as.get(), L.dL_as.get(), g);
+                                                            L.kL_as.get(), L.kR_as.get(), L.dL_as.get(), g,
+                                                            p.surf_extended ? 5 : 4);
   UVO_LAUNCH_CHECK(c);
   UVO_CUDA(cudaEventRecord(L.ev_gather, c.stream));
   mark(4);
@@ -641,7 +644,8 @@ int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps, float
     const int n = std::min(cnt[1], s->cap);
     UVO_REQUIRE(n <= capacity, "uvo_stereo_last_keypoints: capacity too small");
     if (n > 0 && kps) UVO_CUDA(cudaMemcpy(kps, L.fe.kps[idx].get(), sizeof(uvo_keypoint) * n, cudaMemcpyDeviceToHost));
-    if (n > 0 && desc) UVO_CUDA(cudaMemcpy(desc, L.fe.desc[idx].get(), sizeof(float) * 64 * n, cudaMemcpyDeviceToHost));
+    const size_t dd = s->prm.surf_extended ? 128 : 64;
+    if (n > 0 && desc) UVO_CUDA(cudaMemcpy(desc, L.fe.desc[idx].get(), sizeof(float) * dd * n, cudaMemcpyDeviceToHost));
     *count = n;
   });
 }

@@ -54,6 +54,7 @@ static void mono_frame(uvo_mono* m, const uint8_t* img, size_t pitch, bool from_
   uvo_ctx* ctx = m->ctx;
   Ctx& c = ctx->c;
   const uvo_params& p = m->prm;
+  const size_t dd = p.surf_extended ? 128 : 64;  // floats per descriptor row
   UVO_CUDA(cudaSetDevice(c.device));
   memset(out, 0, sizeof(*out));
   const uint8_t* d_img = img;
@@ -77,7 +78,7 @@ static void mono_frame(uvo_mono* m, const uint8_t* img, size_t pitch, bool from_
     if (n_curr > 0) {
       UVO_CUDA(cudaMemcpyAsync(m->prev_kps.get(), m->fe.kps[0].get(), sizeof(uvo_keypoint) * n_curr,
                                cudaMemcpyDeviceToDevice, c.stream));
-      UVO_CUDA(cudaMemcpyAsync(m->prev_desc.get(), m->fe.desc[0].get(), sizeof(float) * 64 * n_curr,
+      UVO_CUDA(cudaMemcpyAsync(m->prev_desc.get(), m->fe.desc[0].get(), sizeof(float) * dd * n_curr,
                                cudaMemcpyDeviceToDevice, c.stream));
     }
     m->n_prev = n_curr;
@@ -115,6 +116,7 @@ static void mono_frame(uvo_mono* m, const uint8_t* img, size_t pitch, bool from_
     a.t = m->fe.desc[0].get();
     a.nq = m->n_prev;
     a.nt = n_curr;
+    a.dim = (int)dd;
     a.ratio = (float)p.lowe_ratio;
     match_bind_scratch(a, m->match_scratch.get(), m->cap, m->cap);
     a.matches = m->matches.get();
@@ -217,9 +219,6 @@ int uvo_mono_create(uvo_ctx* ctx, int width, int height, const uvo_camera* cam, 
   const int rc = guarded(&ctx->c, [&] {
     UVO_REQUIRE(width > 0 && height > 0 && cam && prm, "uvo_mono_create: bad argument");
     UVO_REQUIRE(prm->max_features >= 64, "max_features too small");
-    if (prm->surf_extended)  // prev_desc and the matcher call of this handle carry 64-float rows
-      throw InvalidArg{"uvo_mono: extended (128-d) SURF descriptors are served by the stage-level calls only",
-                       UVO_ERR_UNSUPPORTED};
     Ctx& c = ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
     m->ctx = ctx;
@@ -232,8 +231,9 @@ int uvo_mono_create(uvo_ctx* ctx, int width, int height, const uvo_camera* cam, 
     m->src_pitch = ((size_t)3 * width + 15) & ~(size_t)15;
     m->src.ensure(m->src_pitch * height);
     m->prev_kps.ensure(m->cap);
-    m->prev_desc.ensure((size_t)m->cap * 64);
-    UVO_CUDA(cudaMemsetAsync(m->prev_desc.get(), 0, (size_t)m->cap * 64 * sizeof(float), c.stream));
+    const size_t dd = prm->surf_extended ? 128 : 64;  // floats per descriptor row (SURF_EXTENDED, VO_utility.h:86)
+    m->prev_desc.ensure((size_t)m->cap * dd);
+    UVO_CUDA(cudaMemsetAsync(m->prev_desc.get(), 0, (size_t)m->cap * dd * sizeof(float), c.stream));
     m->match_scratch.ensure(match_scratch_bytes(m->cap, m->cap));
     UVO_CUDA(cudaMemsetAsync(m->match_scratch.get(), 0, match_scratch_bytes(m->cap, m->cap), c.stream));
     m->matches.ensure(m->cap);

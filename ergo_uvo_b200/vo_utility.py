@@ -432,7 +432,7 @@ class StereoVO:
     def last_keypoints(self, right=False):
         cap = int(self.params.max_features)
         kps = np.zeros(cap, KEYPOINT_DTYPE)
-        desc = np.zeros((cap, 64), np.float32)
+        desc = np.zeros((cap, 128 if self.params.surf_extended else 64), np.float32)
         n = C.c_int(0)
         self.ctx._ck(self.lib.uvo_stereo_last_keypoints(self.h, int(right), _p(kps), _p(desc), cap, C.byref(n)))
         return kps[:n.value].copy(), desc[:n.value].copy()

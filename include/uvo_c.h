@@ -301,7 +301,8 @@ UVO_API int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1_ho
                                           size_t pitch, double dt);
 UVO_API int uvo_stereo_max_in_flight(void);
 UVO_API int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out);
-/* Debug/parity taps of the last frame (device -> host copies of intermediate products). */
+/* Debug/parity taps of the last frame (device -> host copies of intermediate products).  Descriptor rows are 64
+ * floats, 128 when the handle was created with surf_extended. */
 UVO_API int uvo_stereo_last_keypoints(uvo_stereo* s, int right, uvo_keypoint* kps_host, float* desc_host,
                                       int capacity, int* count);
 UVO_API int uvo_stereo_last_matches(uvo_stereo* s, int temporal, uvo_dmatch* matches_host, int capacity,

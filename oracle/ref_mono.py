@@ -49,8 +49,8 @@ class RefMonoVO:
         O, p, s = self.O, self.p, self.seq
         out = dict(initialised=0, skipped=0, published=0, valid=0, n_matches=0, n_inliers=0, n_3d=0)
         g = O.get_image(img, s.K, s.D, s.newK, bool(p.clahe), float(p.clip_limit))
-        k, d = O.surf_detect_and_compute(g, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers, False,
-                                         bool(p.surf_upright))
+        k, d = O.surf_detect_and_compute(g, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers,
+                                         bool(p.surf_extended), bool(p.surf_upright))
         out["n_keypoints"] = len(k)
         prev, self.prev = self.prev, (k, d)
         if not self.init:

@@ -37,10 +37,10 @@ class RefStereoVO:
         gL = O.get_image(left, s.KL, s.DL, s.newKL, bool(p.clahe), float(p.clip_limit))
         gR = O.get_image(right, s.KR, s.DR, s.newKR, bool(p.clahe), float(p.clip_limit))
         t1 = time.perf_counter()
-        kL, dL = O.surf_detect_and_compute(gL, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers, False,
-                                           bool(p.surf_upright))
-        kR, dR = O.surf_detect_and_compute(gR, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers, False,
-                                           bool(p.surf_upright))
+        kL, dL = O.surf_detect_and_compute(gL, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers,
+                                           bool(p.surf_extended), bool(p.surf_upright))
+        kR, dR = O.surf_detect_and_compute(gR, p.surf_min_hessian, p.surf_octaves, p.surf_octave_layers,
+                                           bool(p.surf_extended), bool(p.surf_upright))
         t2 = time.perf_counter()
         self.stage_s["get_image"] += t1 - t0
         self.stage_s["surf"] += t2 - t1

@@ -129,24 +129,58 @@ def test_match_128_ties_duplicates_and_small_sets(ext_ctx, oracle):
     assert len(ext_ctx.match_features(None, None, q[:0], q)) == 0 and len(ext_ctx.match_features(None, None, q, q[:0])) == 0
 
 
-def test_unsupported_row_lengths_and_handles(ctx, small_stereo):
-    """rows other than 64 / 128 floats, and extended descriptors on the whole-frame handles (whose lane buffers carry
-    64-float rows), are refused with UVO_ERR_UNSUPPORTED -- never silently truncated"""
+def test_unsupported_row_lengths(ctx):
+    """rows other than 64 / 128 floats are refused with UVO_ERR_UNSUPPORTED -- never silently truncated"""
     import ergo_uvo_b200 as U
     d = _descs(20, 1, dim=32)
     with pytest.raises(U.UvoError) as e:
         ctx.knn_match2(d, d)
     assert e.value.code == -5
+
+
+def test_stereo_handle_extended(ctx, oracle, small_stereo):
+    """uvo_stereo created with surf_extended: lane buffers, the after-stereo gather and both matcher calls carry
+    128-float rows; every product of the frame equals the CPU replay of stereo_VO (visual_odometry.h:526-740)"""
+    import ergo_uvo_b200 as U
+    from oracle.ref_stereo import RefStereoVO
+    from test_gpu_stereo import _compare_frame
     seq = small_stereo
     p = U.default_params(True)
+    p.surf_min_hessian = 3000
+    p.max_features = 16384
     p.surf_extended = 1
     camL = U.make_camera(seq.KL, seq.DL, seq.newKL)
     camR = U.make_camera(seq.KR, seq.DR, seq.newKR)
-    with pytest.raises(U.UvoError) as e:
-        U.StereoVO(ctx, seq.w, seq.h, camL, camR, seq.R_right, seq.t_right, p)
-    assert e.value.code == -5
-    pm = U.default_params(False)
-    pm.surf_extended = 1
-    with pytest.raises(U.UvoError) as e:
-        U.MonoVO(ctx, seq.w, seq.h, camL, pm)
-    assert e.value.code == -5
+    vo = U.StereoVO(ctx, seq.w, seq.h, camL, camR, seq.R_right, seq.t_right, p)
+    ref = RefStereoVO(oracle, seq, p)
+    for k, (L, R) in enumerate(seq.frames):
+        res = vo.frame(L, R, 0.1)
+        r = ref.frame(L, R, 0.1)
+        assert r["dL"].shape[1] == 128
+        _compare_frame(vo, res, r)
+        assert res.valid == (1 if k else 0)
+    assert res.n_temporal_matches > 100 and res.n_inliers > 50
+    vo.close()
+
+
+def test_mono_handle_extended(ctx, oracle):
+    import ergo_uvo_b200 as U
+    from oracle.ref_mono import RefMonoVO
+    from tools import synth
+    seq = synth.MonoSequence(640, 480, n_frames=3, tex_size=1024, velocity=(0.02, 0.004, 0.0))
+    p = U.default_params(False)
+    p.surf_extended = 1
+    vo = U.MonoVO(ctx, 640, 480, U.make_camera(seq.K, seq.D, seq.newK), p)
+    ref = RefMonoVO(oracle, seq, p)
+    published = 0
+    for k in range(3):
+        r = vo.frame(seq.frames[k], 0.1, seq.ranges[k])
+        o = ref.frame(seq.frames[k], 0.1, seq.ranges[k])
+        for f in ("initialised", "skipped", "published", "valid", "n_keypoints", "n_matches", "n_inliers", "n_3d"):
+            assert getattr(r, f) == o[f], (k, f, getattr(r, f), o[f])
+        if o["published"]:
+            published += 1
+            assert np.abs(np.array(r.R).reshape(3, 3) - o["R"]).max() < 1e-6
+            assert np.abs(np.array(r.velocity) - o["velocity"]).max() <= 1e-6 * np.abs(o["velocity"]).max()
+    assert published == 2
+    vo.close()
