@@ -692,10 +692,10 @@ void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
 
 template <int D>
 static void launch_match_dim(Ctx& c, const MatchArgs& a) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_set[64] = {};  // function attributes are per device: one process may hold contexts on several GPUs
+  if (c.device >= 64 || !attr_set[c.device]) {
     UVO_CUDA(cudaFuncSetAttribute(k_knn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeom<D>::SMEM_ALLOC));
-    attr_done = true;
+    if (c.device < 64) attr_set[c.device] = true;
   }
   if (a.exact_only) {
     UVO_KERNEL(c, "k_knn_flag_all");
