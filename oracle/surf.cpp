@@ -13,9 +13,11 @@
 #include "uvo_oracle.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -60,8 +62,10 @@ const int dx_s[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
 const int dy_s[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
 const int dxy_s[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
 
-// sum: (h+1)x(w+1); det/trace: (h/step)x(w/step), pre-zeroed
-void calc_layer_det_trace(const int32_t* sum, int w, int h, int size, int step, float* det, float* trace) {
+// sum: (h+1)x(w+1); det/trace: (h/step)x(w/step), pre-zeroed.  Sample rows [row0, row1) of the layer (clamped to the
+// layer's sample rows): every sample is independent, so row ranges can run on different threads.
+void calc_layer_det_trace(const int32_t* sum, int w, int h, int size, int step, float* det, float* trace,
+                          int row0 = 0, int row1 = 1 << 30) {
   const int srows = h + 1, scols = w + 1;
   if (size > srows - 1 || size > scols - 1) return;
   SurfHF Dx[3], Dy[3], Dxy[4];
@@ -71,7 +75,7 @@ void calc_layer_det_trace(const int32_t* sum, int w, int h, int size, int step, 
   const int samples_i = 1 + (srows - 1 - size) / step, samples_j = 1 + (scols - 1 - size) / step;
   const int margin = (size / 2) / step;
   const int lcols = w / step;
-  for (int i = 0; i < samples_i; i++) {
+  for (int i = std::max(row0, 0); i < std::min(samples_i, row1); i++) {
     const int* sum_ptr = sum + (size_t)(i * step) * scols;
     float* det_ptr = det + (size_t)(i + margin) * lcols + margin;
     float* tr_ptr = trace + (size_t)(i + margin) * lcols + margin;
@@ -114,8 +118,15 @@ bool interpolate_keypoint(const float N9[3][9], int dx, int dy, int ds, orc_keyp
   return ok;
 }
 
-void find_maxima_in_layer(int w, int h, const std::vector<std::vector<float>>& dets,
-                          const std::vector<std::vector<float>>& traces, const std::vector<int>& sizes,
+// a layer map: (h/step) x (w/step) floats, zero-filled by the band workers before any sample is written
+struct LayerMap {
+  std::unique_ptr<float[]> p;
+  size_t n = 0;
+  float* data() const { return p.get(); }
+};
+
+void find_maxima_in_layer(int w, int h, const std::vector<LayerMap>& dets,
+                          const std::vector<LayerMap>& traces, const std::vector<int>& sizes,
                           std::vector<orc_keypoint>& kps, int octave, int layer, float thr, int step) {
   const int size = sizes[layer];
   const int lrows = h / step, lcols = w / step;
@@ -437,13 +448,14 @@ extern "C" int orc_surf_detect_and_compute(const uint8_t* img, int w, int h, dou
   std::vector<int32_t> sum((size_t)(w + 1) * (h + 1));
   orc_integral(img, w, h, sum.data());
   const int n_total = (n_layers + 2) * n_octaves, n_middle = n_layers * n_octaves;
-  std::vector<std::vector<float>> dets(n_total), traces(n_total);
+  std::vector<LayerMap> dets(n_total), traces(n_total);
   std::vector<int> sizes(n_total), steps(n_total), middle(n_middle);
   int index = 0, mi = 0, step = SAMPLE_STEP0;
   for (int o = 0; o < n_octaves; o++) {
     for (int l = 0; l < n_layers + 2; l++) {
-      dets[index].assign((size_t)(h / step) * (w / step), 0.f);
-      traces[index].assign((size_t)(h / step) * (w / step), 0.f);
+      dets[index].n = traces[index].n = (size_t)(h / step) * (w / step);
+      dets[index].p.reset(new float[dets[index].n]);  // uninitialised: zero-filled in parallel below
+      traces[index].p.reset(new float[traces[index].n]);
       sizes[index] = (HAAR_SIZE0 + HAAR_SIZE_INC * l) << o;
       steps[index] = step;
       if (0 < l && l <= n_layers) middle[mi++] = index;
@@ -451,19 +463,55 @@ extern "C" int orc_surf_detect_and_compute(const uint8_t* img, int w, int h, dou
     }
     step *= 2;
   }
+  const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   {
-    std::vector<std::thread> th;
+    // OpenCV runs one parallel_for_ item per layer (SURFBuildInvoker); the five octave-0 layers hold 3/4 of the
+    // samples, so the items here are 64-row bands of a layer, handed out from a shared counter, octave 0 first
+    struct Band { int layer, row0; };
+    std::vector<Band> bands;
     for (int i = 0; i < n_total; i++)
-      th.emplace_back([&, i] {
-        calc_layer_det_trace(sum.data(), w, h, sizes[i], steps[i], dets[i].data(), traces[i].data());
+      for (int r = 0; r < h / steps[i] + 1; r += 64) bands.push_back({i, r});
+    {  // phase 1: zero the maps (the unwritten borders read as 0), same bands
+      std::atomic<size_t> nz{0};
+      std::vector<std::thread> tz;
+      for (unsigned t = 0; t < n_thr; t++)
+        tz.emplace_back([&] {
+          for (size_t b = nz++; b < bands.size(); b = nz++) {
+            const int i = bands[b].layer, lcols = w / steps[i], lrows = h / steps[i];
+            const int r0 = std::min(bands[b].row0, lrows), r1 = std::min(bands[b].row0 + 64, lrows);
+            std::memset(dets[i].data() + (size_t)r0 * lcols, 0, sizeof(float) * (size_t)(r1 - r0) * lcols);
+            std::memset(traces[i].data() + (size_t)r0 * lcols, 0, sizeof(float) * (size_t)(r1 - r0) * lcols);
+          }
+        });
+      for (auto& t : tz) t.join();
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < n_thr; t++)
+      th.emplace_back([&] {
+        for (size_t b = next++; b < bands.size(); b = next++) {
+          const int i = bands[b].layer;
+          calc_layer_det_trace(sum.data(), w, h, sizes[i], steps[i], dets[i].data(), traces[i].data(), bands[b].row0,
+                               bands[b].row0 + 64);
+        }
       });
     for (auto& t : th) t.join();
   }
+  // one item per middle layer, as OpenCV's SURFFindInvoker; the per-layer lists are concatenated in layer order, which
+  // is the order the sequential loop produces (the sort below is a total order anyway)
   std::vector<orc_keypoint> kps;
   const float thr = (float)hessian_threshold;
-  for (int i = 0; i < n_middle; i++) {
-    int layer = middle[i], octave = i / n_layers;
-    find_maxima_in_layer(w, h, dets, traces, sizes, kps, octave, layer, thr, steps[layer]);
+  {
+    std::vector<std::vector<orc_keypoint>> per_layer(n_middle);
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < std::min<unsigned>(n_thr, n_middle); t++)
+      th.emplace_back([&] {
+        for (int i = next++; i < n_middle; i = next++)
+          find_maxima_in_layer(w, h, dets, traces, sizes, per_layer[i], i / n_layers, middle[i], thr, steps[middle[i]]);
+      });
+    for (auto& t : th) t.join();
+    for (auto& v : per_layer) kps.insert(kps.end(), v.begin(), v.end());
   }
   std::sort(kps.begin(), kps.end(), keypoint_greater);
   for (auto& k : kps) k.class_id = -1;  // detectAndCompute resets class_id (A.1)
