@@ -136,3 +136,13 @@ def test_lazy_dxy_bound_holds_in_f32():
     sub = ((f(0.81) * dxy).astype(f) * dxy).astype(f)
     det = (p - sub).astype(f)
     assert (sub >= 0).all() and (det <= p).all()
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md is the map from the C ABI to the reference interface: every exported function is named there"""
+    import re
+    h = open(os.path.join(ROOT, "include", "uvo_c.h")).read()
+    syms = sorted(set(re.findall(r"UVO_API\s+[\w\s\*]+?\b(uvo_\w+)\s*\(", h)))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert len(syms) > 40
+    assert [s for s in syms if s not in doc] == []
