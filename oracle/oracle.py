@@ -114,6 +114,20 @@ def bayer_bggr2bgr(bayer):
     return out
 
 
+def jpeg_decode(data):
+    """cv2.imdecode(data, IMREAD_UNCHANGED) for baseline JPEG (from_ros_to_cv_image, math_utility.cpp:154-173)"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().orc_jpeg_info(_p(buf), C.c_size_t(len(buf)), C.byref(w), C.byref(h), C.byref(c))
+    if rc < 0:
+        raise ValueError(f"orc_jpeg_info: {rc}")
+    out = np.empty((h.value, w.value) if c.value == 1 else (h.value, w.value, 3), np.uint8)
+    rc = lib().orc_jpeg_decode(_p(buf), C.c_size_t(len(buf)), _p(out))
+    if rc < 0:
+        raise ValueError(f"orc_jpeg_decode: {rc}")
+    return out
+
+
 def resize_area(src, dw, dh):
     src = np.ascontiguousarray(src, dtype=np.uint8)
     sh, sw = src.shape[:2]

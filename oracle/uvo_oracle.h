@@ -21,6 +21,7 @@
  */
 #ifndef UVO_ORACLE_H
 #define UVO_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -107,6 +108,12 @@ int orc_solve_pnp_ransac_epnp(const double* X, const float* x, int n, const doub
                               int32_t* inliers, int* hyps_evaluated);
 /* EPnP on a given set (cv::solvePnP(..., SOLVEPNP_EPNP)); X n x3 f64, x n x2 f64 */
 void orc_epnp(const double* X, const double* x, int n, const double K[4], double R[9], double t[3]);
+
+/* ---- ingest: JPEG decode of from_ros_to_cv_image (math_utility.cpp:154-173: cv_bridge::toCvCopy -> cv::imdecode) ---- */
+/* baseline / extended-sequential Huffman, 8-bit, 1 or 3 components.  0 on success, -1 corrupt, -2 unsupported. */
+int orc_jpeg_info(const uint8_t* data, size_t len, int* w, int* h, int* channels);
+/* out: h x w (1 component) or h x w x 3 BGR, as cv::imdecode(IMREAD_UNCHANGED) lays it out */
+int orc_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out);
 
 /* K10a / K10b (findEssentialMat, findHomography, recoverPose, decomposeHomographyMat) are restated in numpy:
  * oracle/twoview.py, pinned to cv2 4.13 (tests/test_oracle_twoview.py, tests/golden/twoview.npz). */

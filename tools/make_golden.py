@@ -77,6 +77,33 @@ def matcher128():
     np.savez_compressed(os.path.join(OUT, "matcher128_120x160.npz"), q=q, t=t, idx=idx2, dist=dist2)
 
 
+def jpeg():
+    """JPEG streams (encoded by cv2 / libjpeg-turbo) with cv2.imdecode(IMREAD_UNCHANGED) as the expected output:
+    the decode inside from_ros_to_cv_image (math_utility.cpp:154-173)"""
+    from scipy import ndimage
+    rs = np.random.RandomState(31)
+    a = ndimage.gaussian_filter(rs.rand(48, 64, 3).astype(np.float32), (1.2, 1.2, 0))
+    img = ((a - a.min()) / (a.max() - a.min()) * 255).astype(np.uint8)
+    img[10:20, 30:40] = (255, 0, 0)  # saturated patches exercise the range limit of the colour conversion
+    img[30:40, 5:15] = (0, 255, 255)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    out = {}
+    for name, src, flags in [
+        ("c420_rst2", img[:45, :61], [cv2.IMWRITE_JPEG_QUALITY, 80, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+                                      cv2.IMWRITE_JPEG_RST_INTERVAL, 2]),
+        ("c422", img[:45, :61], [cv2.IMWRITE_JPEG_QUALITY, 60, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]),
+        ("c444_opt", img, [cv2.IMWRITE_JPEG_QUALITY, 95, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
+                           cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+        ("c440", img[:47, :63], [cv2.IMWRITE_JPEG_QUALITY, 30, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440]),
+        ("gray", img[:45, :61, 1].copy(), [cv2.IMWRITE_JPEG_QUALITY, 85]),
+    ]:
+        ok, enc = cv2.imencode(".jpg", src, flags)
+        assert ok
+        out[name + "_jpg"] = enc.ravel()
+        out[name + "_img"] = cv2.imdecode(enc, cv2.IMREAD_UNCHANGED)
+    np.savez_compressed(os.path.join(OUT, "jpeg_64x48.npz"), **out)
+
+
 def pose():
     rs = np.random.RandomState(11)
     n = 600
@@ -114,6 +141,7 @@ def main():
     imgprep()
     matcher()
     matcher128()
+    jpeg()
     pose()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
