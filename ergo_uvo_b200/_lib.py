@@ -64,6 +64,15 @@ class MonoResult(C.Structure):
     ]
 
 
+class JpegLayout(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32),
+        ("h_samp", C.c_int32 * 3), ("v_samp", C.c_int32 * 3), ("blocks_x", C.c_int32 * 3), ("blocks_y", C.c_int32 * 3),
+        ("samples_x", C.c_int32 * 3), ("samples_y", C.c_int32 * 3),
+        ("coeff_offset", C.c_int64 * 3), ("coeff_total", C.c_int64), ("quant", (C.c_uint16 * 64) * 3),
+    ]
+
+
 _lib = None
 
 

@@ -1,0 +1,603 @@
+// jpeg.cu -- ingest: baseline JPEG decode, the cv::imdecode inside from_ros_to_cv_image (reference
+// math_utility.cpp:154-173: cv_bridge::toCvCopy(CompressedImage) -> cv::imdecode(IMREAD_UNCHANGED) -> libjpeg-turbo with
+// JDCT_ISLOW, fancy upsampling, YCbCr -> BGR).  SURVEY.md 8f-2.
+//
+// Split (the "hybrid" arrangement): the entropy-coded segment is a serial bit stream, so Huffman decoding runs on the
+// host (uvo_jpeg_entropy_decode: table-driven, 64-bit bit buffer) into planes of quantised coefficients; everything
+// after it is independent per block / per pixel and runs on the GPU:
+//   k_jpeg_idct   dequantisation + the 8x8 "islow" integer IDCT (13-bit constants, two passes, descale 11 / 18 bits):
+//                 eight threads per block, columns then rows through shared memory, one 8-byte store per sample row
+//   k_jpeg_color  chroma upsampling with libjpeg's triangle filters (h2v1, h2v2, h1v2; replication elsewhere and for
+//                 planes narrower than three samples) evaluated per output pixel from the component planes, then the
+//                 16-bit fixed-point YCbCr -> BGR conversion; interleaved u8 output
+// Integer arithmetic throughout, the same operations in the same order as libjpeg-turbo: results are bit-identical.
+// Not handled: progressive / arithmetic / lossless / 12-bit streams, CMYK, Adobe RGB -> UVO_ERR_UNSUPPORTED.
+#include <algorithm>
+#include <cstring>
+
+#include "capi_internal.cuh"
+
+using namespace uvo;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ host: parsing
+const uint8_t kNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+constexpr int FAST_BITS = 10;
+
+struct HuffTab {
+  bool present = false;
+  uint16_t fast[1 << FAST_BITS];  // (code length << 8) | symbol for codes of up to FAST_BITS bits, 0 = longer
+  int32_t maxcode[18];            // largest code of each length, -1 if none
+  int32_t valoff[17];             // huffval index of the first code of a length minus that code
+  uint8_t huffval[256];
+  void build(const uint8_t counts[16], const uint8_t* vals, int nv) {
+    memcpy(huffval, vals, nv);
+    memset(fast, 0, sizeof(fast));
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+      valoff[l] = k - code;
+      for (int i = 0; i < counts[l - 1]; i++, k++, code++)
+        if (l <= FAST_BITS) {
+          const int lo = code << (FAST_BITS - l), n = 1 << (FAST_BITS - l);
+          for (int j = 0; j < n; j++) fast[lo + j] = (uint16_t)((l << 8) | vals[k]);
+        }
+      maxcode[l] = counts[l - 1] ? code - 1 : -1;
+      code <<= 1;
+    }
+    maxcode[17] = 0x7fffffff;
+    present = true;
+  }
+};
+
+struct BitReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  uint64_t buf = 0;
+  int cnt = 0;
+  bool marker = false;  // a marker (or the end of the data) was reached: zeros are fed from there on
+  void refill() {
+    while (cnt <= 56) {
+      unsigned b = 0;
+      if (!marker && p < end) {
+        b = *p++;
+        if (b == 0xFF) {
+          if (p < end && *p == 0x00) {
+            p++;  // stuffed zero
+          } else {
+            p--;
+            marker = true;
+            b = 0;
+          }
+        }
+      }
+      buf |= (uint64_t)b << (56 - cnt);
+      cnt += 8;
+    }
+  }
+  unsigned peek(int n) const { return (unsigned)(buf >> (64 - n)); }
+  void skip(int n) {
+    buf <<= n;
+    cnt -= n;
+  }
+  void restart_at(const uint8_t* q) {
+    p = q;
+    buf = 0;
+    cnt = 0;
+    marker = false;
+  }
+};
+
+inline int huff_decode(BitReader& b, const HuffTab& h) {
+  if (b.cnt < 16) b.refill();
+  const unsigned e = h.fast[b.peek(FAST_BITS)];
+  if (e) {
+    b.skip(e >> 8);
+    return e & 255;
+  }
+  for (int l = FAST_BITS + 1; l <= 16; l++) {
+    const int code = (int)b.peek(l);
+    if (code <= h.maxcode[l]) {
+      b.skip(l);
+      return h.huffval[(code + h.valoff[l]) & 255];
+    }
+  }
+  b.skip(16);
+  return 0;  // not a code of this table (corrupt data): libjpeg carries on with a zero as well
+}
+
+inline int receive_extend(BitReader& b, int s) {
+  if (b.cnt < s) b.refill();
+  const int v = (int)b.peek(s);
+  b.skip(s);
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+struct CompInfo {
+  int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
+};
+
+struct Parser {
+  uvo_jpeg_layout L;
+  CompInfo comp[3];
+  HuffTab dc[4], ac[4];
+  uint16_t qt[4][64];
+  bool qt_present[4] = {false, false, false, false};
+  int hmax = 1, vmax = 1, restart = 0, adobe_transform = -1;
+  bool have_sof = false;
+
+  Parser() {
+    memset(&L, 0, sizeof(L));
+    memset(qt, 0, sizeof(qt));
+  }
+
+  // walks the marker segments; with `coef` decodes every scan into it, without stops at the first SOS
+  void run(const uint8_t* d, size_t len, int16_t* coef) {
+    if (!d || len < 4 || d[0] != 0xFF || d[1] != 0xD8) throw InvalidArg{"jpeg: not a JPEG stream (no SOI)", UVO_ERR_INVALID};
+    size_t i = 2;
+    while (i + 4 <= len) {
+      if (d[i] != 0xFF || d[i + 1] == 0xFF) {
+        i++;
+        continue;
+      }
+      const int m = d[i + 1];
+      i += 2;
+      if (m == 0xD9) break;                                    // EOI
+      if (m == 0x01 || m == 0x00 || (m >= 0xD0 && m <= 0xD7)) continue;  // stand-alone
+      const size_t seg = ((size_t)d[i] << 8) | d[i + 1];
+      if (seg < 2 || i + seg > len) throw InvalidArg{"jpeg: truncated marker segment", UVO_ERR_INVALID};
+      const uint8_t* s = d + i + 2;
+      const size_t n = seg - 2;
+      switch (m) {
+        case 0xDB: dqt(s, n); break;
+        case 0xC4: dht(s, n); break;
+        case 0xC0:
+        case 0xC1: sof(s, n); break;
+        case 0xDD:
+          if (n < 2) throw InvalidArg{"jpeg: bad DRI", UVO_ERR_INVALID};
+          restart = (s[0] << 8) | s[1];
+          break;
+        case 0xEE:
+          if (n >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_transform = s[11];
+          break;
+        case 0xDA: {
+          if (!have_sof) throw InvalidArg{"jpeg: SOS before SOF", UVO_ERR_INVALID};
+          if (!coef) {  // header only: report the quantisation tables as defined so far
+            for (int c = 0; c < L.components; c++)
+              if (qt_present[comp[c].tq]) memcpy(L.quant[c], qt[comp[c].tq], sizeof(L.quant[0]));
+            return;
+          }
+          const uint8_t* e = scan(s, n, d + i + seg, d + len, coef);
+          i = (size_t)(e - d);
+          continue;
+        }
+        default:
+          if (m >= 0xC2 && m <= 0xCF && m != 0xC8)
+            throw InvalidArg{"jpeg: only baseline / extended-sequential Huffman streams are supported", UVO_ERR_UNSUPPORTED};
+      }
+      i += seg;
+    }
+    if (!have_sof) throw InvalidArg{"jpeg: no frame header", UVO_ERR_INVALID};
+    if (L.components == 3 && adobe_transform == 0)
+      throw InvalidArg{"jpeg: Adobe RGB streams are not supported", UVO_ERR_UNSUPPORTED};
+  }
+
+  void dqt(const uint8_t* s, size_t n) {
+    size_t k = 0;
+    while (k < n) {
+      const int pq = s[k] >> 4, tq = s[k] & 15;
+      k++;
+      if (tq > 3 || pq > 1 || k + (pq ? 128 : 64) > n) throw InvalidArg{"jpeg: bad DQT", UVO_ERR_INVALID};
+      for (int j = 0; j < 64; j++) {
+        qt[tq][kNatural[j]] = pq ? (uint16_t)((s[k] << 8) | s[k + 1]) : s[k];
+        k += pq ? 2 : 1;
+      }
+      qt_present[tq] = true;
+    }
+  }
+
+  void dht(const uint8_t* s, size_t n) {
+    size_t k = 0;
+    while (k + 17 <= n) {
+      const int tc = s[k] >> 4, th = s[k] & 15;
+      int nv = 0;
+      for (int j = 0; j < 16; j++) nv += s[k + 1 + j];
+      if (th > 3 || tc > 1 || nv > 256 || k + 17 + nv > n) throw InvalidArg{"jpeg: bad DHT", UVO_ERR_INVALID};
+      (tc ? ac : dc)[th].build(s + k + 1, s + k + 17, nv);
+      k += 17 + nv;
+    }
+  }
+
+  void sof(const uint8_t* s, size_t n) {
+    if (n < 6) throw InvalidArg{"jpeg: bad SOF", UVO_ERR_INVALID};
+    if (s[0] != 8) throw InvalidArg{"jpeg: only 8-bit samples are supported", UVO_ERR_UNSUPPORTED};
+    L.height = (s[1] << 8) | s[2];
+    L.width = (s[3] << 8) | s[4];
+    L.components = s[5];
+    if (L.width <= 0 || L.height <= 0) throw InvalidArg{"jpeg: empty frame", UVO_ERR_INVALID};
+    if (L.components != 1 && L.components != 3)
+      throw InvalidArg{"jpeg: only 1- and 3-component streams are supported", UVO_ERR_UNSUPPORTED};
+    if (n < (size_t)(6 + 3 * L.components)) throw InvalidArg{"jpeg: bad SOF", UVO_ERR_INVALID};
+    for (int c = 0; c < L.components; c++) {
+      comp[c].id = s[6 + 3 * c];
+      comp[c].h = s[7 + 3 * c] >> 4;
+      comp[c].v = s[7 + 3 * c] & 15;
+      comp[c].tq = s[8 + 3 * c];
+      if (comp[c].h < 1 || comp[c].h > 4 || comp[c].v < 1 || comp[c].v > 4 || comp[c].tq > 3)
+        throw InvalidArg{"jpeg: bad component specification", UVO_ERR_INVALID};
+    }
+    if (L.components == 1) comp[0].h = comp[0].v = 1;  // a lone component is not subsampled (T.81 A.2.2)
+    for (int c = 0; c < L.components; c++) {
+      hmax = std::max(hmax, comp[c].h);
+      vmax = std::max(vmax, comp[c].v);
+    }
+    const int mcux = div_up(L.width, 8 * hmax), mcuy = div_up(L.height, 8 * vmax);
+    int64_t off = 0;
+    for (int c = 0; c < L.components; c++) {
+      if (hmax % comp[c].h || vmax % comp[c].v)
+        throw InvalidArg{"jpeg: fractional sampling ratios are not supported", UVO_ERR_UNSUPPORTED};
+      L.h_samp[c] = comp[c].h;
+      L.v_samp[c] = comp[c].v;
+      L.blocks_x[c] = mcux * comp[c].h;
+      L.blocks_y[c] = mcuy * comp[c].v;
+      L.samples_x[c] = div_up(L.width * comp[c].h, hmax);
+      L.samples_y[c] = div_up(L.height * comp[c].v, vmax);
+      L.coeff_offset[c] = off;
+      off += (int64_t)L.blocks_x[c] * L.blocks_y[c] * 64;
+    }
+    L.coeff_total = off;
+    have_sof = true;
+  }
+
+  // one scan: header at s, entropy-coded data from p; returns the position of the marker that ends it
+  const uint8_t* scan(const uint8_t* s, size_t n, const uint8_t* p, const uint8_t* end, int16_t* coef) {
+    const int ns = n ? s[0] : 0;
+    if (ns < 1 || ns > L.components || n < (size_t)(1 + 2 * ns + 3)) throw InvalidArg{"jpeg: bad SOS", UVO_ERR_INVALID};
+    int idx[3];
+    for (int j = 0; j < ns; j++) {
+      int c = -1;
+      for (int q = 0; q < L.components; q++)
+        if (comp[q].id == s[1 + 2 * j]) c = q;
+      if (c < 0) throw InvalidArg{"jpeg: SOS names an unknown component", UVO_ERR_INVALID};
+      comp[c].td = s[2 + 2 * j] >> 4;
+      comp[c].ta = s[2 + 2 * j] & 15;
+      if (comp[c].td > 3 || comp[c].ta > 3 || !dc[comp[c].td].present || !ac[comp[c].ta].present ||
+          !qt_present[comp[c].tq])
+        throw InvalidArg{"jpeg: scan refers to a table that was not defined", UVO_ERR_INVALID};
+      comp[c].pred = 0;
+      idx[j] = c;
+    }
+    // the quantisation tables in force at the first scan of a component are the ones the frame is decoded with
+    for (int j = 0; j < ns; j++) memcpy(L.quant[idx[j]], qt[comp[idx[j]].tq], sizeof(L.quant[0]));
+    int mcus_x, mcus_y;
+    if (ns == 1) {  // non-interleaved: one block per MCU, only the blocks that hold real samples
+      mcus_x = div_up(L.samples_x[idx[0]], 8);
+      mcus_y = div_up(L.samples_y[idx[0]], 8);
+    } else {
+      mcus_x = L.blocks_x[idx[0]] / comp[idx[0]].h;
+      mcus_y = L.blocks_y[idx[0]] / comp[idx[0]].v;
+    }
+    BitReader b{p, end};
+    int left = restart;
+    for (int my = 0; my < mcus_y; my++)
+      for (int mx = 0; mx < mcus_x; mx++) {
+        if (restart && left == 0) {
+          const uint8_t* q = b.p;  // the reader never moves past a marker: the RSTn is at or after b.p
+          while (q + 1 < end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+          if (q + 1 >= end) throw InvalidArg{"jpeg: missing restart marker", UVO_ERR_INVALID};
+          b.restart_at(q + 2);
+          for (int j = 0; j < ns; j++) comp[idx[j]].pred = 0;
+          left = restart;
+        }
+        for (int j = 0; j < ns; j++) {
+          CompInfo& c = comp[idx[j]];
+          const int ci = idx[j];
+          const int nbx = ns == 1 ? 1 : c.h, nby = ns == 1 ? 1 : c.v;
+          for (int by = 0; by < nby; by++)
+            for (int bx = 0; bx < nbx; bx++) {
+              const int X = mx * nbx + bx, Y = my * nby + by;
+              block(b, c, coef + L.coeff_offset[ci] + ((int64_t)Y * L.blocks_x[ci] + X) * 64);
+            }
+        }
+        if (restart) left--;
+      }
+    const uint8_t* q = b.p;  // the reader stops in front of a marker, so the next one is at or after b.p
+    while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0x00 && q[1] != 0xFF && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
+    return q;
+  }
+
+  void block(BitReader& b, CompInfo& c, int16_t* out) {
+    int s = huff_decode(b, dc[c.td]);
+    if (s > 15) throw InvalidArg{"jpeg: corrupt DC coefficient", UVO_ERR_INVALID};
+    c.pred += s ? receive_extend(b, s) : 0;
+    out[0] = (int16_t)c.pred;
+    const HuffTab& t = ac[c.ta];
+    for (int k = 1; k < 64;) {
+      const int rs = huff_decode(b, t);
+      s = rs & 15;
+      if (s == 0) {
+        if ((rs >> 4) != 15) break;  // end of block
+        k += 16;
+        continue;
+      }
+      k += rs >> 4;
+      if (k > 63) throw InvalidArg{"jpeg: corrupt AC run", UVO_ERR_INVALID};
+      out[kNatural[k]] = (int16_t)receive_extend(b, s);
+      k++;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ device
+struct IdctComp {
+  const int16_t* coef;  // blocks_y x blocks_x x 64, natural order
+  uint8_t* plane;       // (blocks_y * 8) rows, pitch = blocks_x * 8
+  int blocks_x, n_blocks, first;  // first: index of the component's first block in the launch
+  uint16_t quant[64];
+};
+struct IdctArgs {
+  IdctComp c[3];
+  int n_comp, total_blocks;
+};
+
+__device__ __forceinline__ int jdescale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+// libjpeg's post-IDCT range-limit table, indexed with the value masked to 10 bits
+__device__ __forceinline__ unsigned jrange(int v) {
+  const int i = v & 1023;
+  return (unsigned)(i < 128 ? i + 128 : i < 512 ? 255 : i < 896 ? 0 : i - 896);
+}
+
+// one 1-D pass of jpeg_idct_islow on eight inputs; results not yet descaled
+__device__ __forceinline__ void islow_1d(const int in[8], int out[8], const int even_shift) {
+  constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
+                F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+  int z2 = in[2], z3 = in[6];
+  int z1 = (z2 + z3) * F_0_541;
+  int tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+  int tmp0 = (in[0] + in[4]) << even_shift, tmp1 = (in[0] - in[4]) << even_shift;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = in[7];
+  tmp1 = in[5];
+  tmp2 = in[3];
+  tmp3 = in[1];
+  z1 = tmp0 + tmp3;
+  z2 = tmp1 + tmp2;
+  z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * F_1_175;
+  tmp0 *= F_0_298;
+  tmp1 *= F_2_053;
+  tmp2 *= F_3_072;
+  tmp3 *= F_1_501;
+  z1 *= -F_0_899;
+  z2 *= -F_2_562;
+  z3 *= -F_1_961;
+  z4 *= -F_0_390;
+  z3 += z5;
+  z4 += z5;
+  tmp0 += z1 + z3;
+  tmp1 += z2 + z4;
+  tmp2 += z2 + z3;
+  tmp3 += z1 + z4;
+  out[0] = tmp10 + tmp3;
+  out[7] = tmp10 - tmp3;
+  out[1] = tmp11 + tmp2;
+  out[6] = tmp11 - tmp2;
+  out[2] = tmp12 + tmp1;
+  out[5] = tmp12 - tmp1;
+  out[3] = tmp13 + tmp0;
+  out[4] = tmp13 - tmp0;
+}
+
+constexpr int IDCT_THREADS = 256, IDCT_BLOCKS = IDCT_THREADS / 8;  // JPEG blocks per thread block
+
+// eight threads per 8x8 block: thread t transforms column t (dequantising on the way in), then row t.  The zero-AC
+// shortcut of the CPU code is not needed: the full column pass yields dc * 4 exactly in that case.
+__global__ void __launch_bounds__(IDCT_THREADS) k_jpeg_idct(const __grid_constant__ IdctArgs a) {
+  __shared__ int s_ws[IDCT_BLOCKS][64 + 8];  // +8: rows of a block land on different banks in pass 2
+  const int t = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const int blk = blockIdx.x * IDCT_BLOCKS + g;
+  const bool live = blk < a.total_blocks;
+  int ci = 0;
+  if (live)
+    while (ci + 1 < a.n_comp && blk >= a.c[ci + 1].first) ci++;
+  const IdctComp& c = a.c[ci];
+  const int local = blk - c.first;
+  if (live) {
+    const int16_t* in = c.coef + (size_t)local * 64;
+    int v[8], o[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = (int)in[8 * r + t] * (int)c.quant[8 * r + t];
+    islow_1d(v, o, 13);
+#pragma unroll
+    for (int r = 0; r < 8; r++) s_ws[g][9 * r + t] = jdescale(o[r], 11);  // CONST_BITS - PASS1_BITS
+  }
+  __syncwarp();  // the eight threads of a block sit in one warp
+  if (live) {
+    int v[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = s_ws[g][9 * t + k];
+    islow_1d(v, o, 13);
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      lo |= jrange(jdescale(o[k], 18)) << (8 * k);  // CONST_BITS + PASS1_BITS + 3
+      hi |= jrange(jdescale(o[4 + k], 18)) << (8 * k);
+    }
+    const int by = local / c.blocks_x, bx = local - by * c.blocks_x;
+    uint8_t* dst = c.plane + ((size_t)(by * 8 + t) * c.blocks_x + bx) * 8;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  }
+}
+
+struct ColorComp {
+  const uint8_t* plane;
+  int pitch, dw, dh;   // real sample counts of the component
+  int hexp, vexp;      // expansion to full resolution
+};
+struct ColorArgs {
+  ColorComp c[3];
+  int w, h;
+  uint8_t* out;
+  size_t out_pitch;
+};
+
+// the component's value at full-resolution pixel (x, y): jdsample.c's fancy filters, replication otherwise
+__device__ __forceinline__ int jsample(const ColorComp& c, int x, int y) {
+  if (c.hexp == 1 && c.vexp == 1) return c.plane[(size_t)y * c.pitch + x];
+  const bool fancy = c.dw > 2;
+  if (c.hexp == 2 && c.vexp == 1 && fancy) {  // h2v1_fancy_upsample
+    const uint8_t* p = c.plane + (size_t)y * c.pitch;
+    const int i = x >> 1;
+    if (x & 1) return i == c.dw - 1 ? p[i] : (p[i] * 3 + p[i + 1] + 2) >> 2;
+    return i == 0 ? p[0] : (p[i] * 3 + p[i - 1] + 1) >> 2;
+  }
+  if (c.hexp == 2 && c.vexp == 2 && fancy) {  // h2v2_fancy_upsample
+    const int r = y >> 1, r1 = (y & 1) ? min(r + 1, c.dh - 1) : max(r - 1, 0);
+    const uint8_t* p0 = c.plane + (size_t)r * c.pitch;
+    const uint8_t* p1 = c.plane + (size_t)r1 * c.pitch;
+    const int i = x >> 1;
+    const int cs = p0[i] * 3 + p1[i];
+    if (x & 1) return i == c.dw - 1 ? (cs * 4 + 7) >> 4 : (cs * 3 + p0[i + 1] * 3 + p1[i + 1] + 7) >> 4;
+    return i == 0 ? (cs * 4 + 8) >> 4 : (cs * 3 + p0[i - 1] * 3 + p1[i - 1] + 8) >> 4;
+  }
+  if (c.hexp == 1 && c.vexp == 2) {  // h1v2_fancy_upsample
+    const int r = y >> 1, r1 = (y & 1) ? min(r + 1, c.dh - 1) : max(r - 1, 0);
+    return (c.plane[(size_t)r * c.pitch + x] * 3 + c.plane[(size_t)r1 * c.pitch + x] + ((y & 1) ? 2 : 1)) >> 2;
+  }
+  return c.plane[(size_t)(y / c.vexp) * c.pitch + x / c.hexp];
+}
+
+__device__ __forceinline__ unsigned jclamp(int v) { return (unsigned)min(max(v, 0), 255); }
+
+// jdcolor.c ycc_rgb_convert (SCALEBITS 16), written B, G, R
+__global__ void __launch_bounds__(256) k_jpeg_color(const __grid_constant__ ColorArgs a) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= a.w || y >= a.h) return;
+  const int Y = jsample(a.c[0], x, y), cb = jsample(a.c[1], x, y) - 128, cr = jsample(a.c[2], x, y) - 128;
+  constexpr int FIX_1_402 = 91881, FIX_1_772 = 116130, FIX_0_714 = 46802, FIX_0_344 = 22554;
+  const int r = Y + ((FIX_1_402 * cr + 32768) >> 16);
+  const int g = Y + ((-FIX_0_344 * cb + 32768 - FIX_0_714 * cr) >> 16);
+  const int b = Y + ((FIX_1_772 * cb + 32768) >> 16);
+  uint8_t* o = a.out + (size_t)y * a.out_pitch + 3 * (size_t)x;
+  o[0] = (uint8_t)jclamp(b);
+  o[1] = (uint8_t)jclamp(g);
+  o[2] = (uint8_t)jclamp(r);
+}
+
+}  // namespace
+
+extern "C" {
+
+int uvo_jpeg_info(const uint8_t* jpeg, size_t len, uvo_jpeg_layout* layout) {
+  if (!layout) return UVO_ERR_INVALID;
+  return guarded(nullptr, [&] {
+    Parser P;
+    P.run(jpeg, len, nullptr);
+    *layout = P.L;
+  });
+}
+
+int uvo_jpeg_entropy_decode(const uint8_t* jpeg, size_t len, int16_t* coeffs_host, size_t capacity,
+                            uvo_jpeg_layout* layout) {
+  if (!layout || !coeffs_host) return UVO_ERR_INVALID;
+  return guarded(nullptr, [&] {
+    Parser H;
+    H.run(jpeg, len, nullptr);
+    if ((size_t)H.L.coeff_total > capacity)
+      throw InvalidArg{"uvo_jpeg_entropy_decode: coefficient buffer too small", UVO_ERR_CAPACITY};
+    memset(coeffs_host, 0, sizeof(int16_t) * (size_t)H.L.coeff_total);
+    Parser P;
+    P.run(jpeg, len, coeffs_host);
+    *layout = P.L;
+  });
+}
+
+int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
+                    size_t out_capacity, int* width, int* height, int* channels) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    UVO_REQUIRE(jpeg && out_host && width && height && channels, "uvo_jpeg_decode: bad argument");
+    Ctx& c = ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    Parser H;
+    H.run(jpeg, len, nullptr);
+    const size_t total = (size_t)H.L.coeff_total;
+    const int W = H.L.width, Hh = H.L.height, nc = H.L.components;
+    if (out_pitch < (size_t)W * nc || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * nc)
+      throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
+    // host: entropy decoding into pinned memory
+    UVO_CUDA(cudaStreamSynchronize(c.stream));  // the pinned buffer may still feed the previous call's copy
+    ctx->jpeg_coef.ensure(total);
+    memset(ctx->jpeg_coef.p, 0, sizeof(int16_t) * total);
+    Parser P;
+    P.run(jpeg, len, ctx->jpeg_coef.p);
+    const uvo_jpeg_layout& L = P.L;
+    // device: coefficients, component planes, output
+    StageScratch& s = ctx->scratch;
+    s.bytes_a.ensure(sizeof(int16_t) * total);
+    size_t plane_bytes = 0, plane_off[3];
+    for (int k = 0; k < nc; k++) {
+      plane_off[k] = plane_bytes;
+      plane_bytes += (size_t)L.blocks_x[k] * L.blocks_y[k] * 64;
+    }
+    s.bytes_b.ensure(plane_bytes);
+    UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), ctx->jpeg_coef.p, sizeof(int16_t) * total, cudaMemcpyHostToDevice,
+                             c.stream));
+    IdctArgs ia{};
+    ia.n_comp = nc;
+    int first = 0;
+    for (int k = 0; k < nc; k++) {
+      ia.c[k].coef = (const int16_t*)s.bytes_a.get() + L.coeff_offset[k];
+      ia.c[k].plane = s.bytes_b.get() + plane_off[k];
+      ia.c[k].blocks_x = L.blocks_x[k];
+      ia.c[k].n_blocks = L.blocks_x[k] * L.blocks_y[k];
+      ia.c[k].first = first;
+      memcpy(ia.c[k].quant, L.quant[k], sizeof(ia.c[k].quant));
+      first += ia.c[k].n_blocks;
+    }
+    ia.total_blocks = first;
+    UVO_KERNEL(c, "k_jpeg_idct");
+    k_jpeg_idct<<<div_up(first, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
+    UVO_LAUNCH_CHECK(c);
+    if (nc == 1) {  // the luminance plane is the image
+      UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh,
+                                 cudaMemcpyDeviceToHost, c.stream));
+    } else {
+      const size_t dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
+      s.bytes_c.ensure(dpitch * Hh);
+      ColorArgs ca{};
+      int hmax = 1, vmax = 1;
+      for (int k = 0; k < 3; k++) {
+        hmax = std::max(hmax, L.h_samp[k]);
+        vmax = std::max(vmax, L.v_samp[k]);
+      }
+      for (int k = 0; k < 3; k++) {
+        ca.c[k].plane = ia.c[k].plane;
+        ca.c[k].pitch = L.blocks_x[k] * 8;
+        ca.c[k].dw = L.samples_x[k];
+        ca.c[k].dh = L.samples_y[k];
+        ca.c[k].hexp = hmax / L.h_samp[k];
+        ca.c[k].vexp = vmax / L.v_samp[k];
+      }
+      ca.w = W;
+      ca.h = Hh;
+      ca.out = s.bytes_c.get();
+      ca.out_pitch = dpitch;
+      UVO_KERNEL(c, "k_jpeg_color");
+      k_jpeg_color<<<dim3(div_up(W, 64), div_up(Hh, 4)), 256, 0, c.stream>>>(ca);
+      UVO_LAUNCH_CHECK(c);
+      UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s.bytes_c.get(), dpitch, (size_t)3 * W, Hh,
+                                 cudaMemcpyDeviceToHost, c.stream));
+    }
+    UVO_CUDA(cudaStreamSynchronize(c.stream));
+    *width = W;
+    *height = Hh;
+    *channels = nc;
+  });
+}
+
+}  // extern "C"

@@ -16,7 +16,7 @@ KEYPOINT_DTYPE = np.dtype(
      ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
-__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
+__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "jpeg_info", "jpeg_entropy_decode", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
 
 
 def _p(a):
@@ -65,6 +65,28 @@ def resize_camera_matrix(original_width, original_height, desired_width, cameraM
     if rc != L.UVO_OK:
         raise L.UvoError(rc, "uvo_resize_camera_matrix: bad camera / size")
     return K, newK.reshape(3, 3), (ow.value, oh.value)
+
+
+def jpeg_info(data):
+    """header of a JPEG stream (uvo_jpeg_info, host-only): the uvo_jpeg_layout of the decode inside
+    from_ros_to_cv_image (math_utility.cpp:154-173)"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    lay = L.JpegLayout()
+    rc = L.load().uvo_jpeg_info(_p(buf), C.c_size_t(len(buf)), C.byref(lay))
+    if rc != L.UVO_OK:
+        raise L.UvoError(rc, "uvo_jpeg_info: not a supported JPEG stream")
+    return lay
+
+
+def jpeg_entropy_decode(data):
+    """host half of the JPEG decode (uvo_jpeg_entropy_decode): (layout, int16 quantised coefficients)"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    lay = jpeg_info(data)
+    coef = np.empty(int(lay.coeff_total), np.int16)
+    rc = L.load().uvo_jpeg_entropy_decode(_p(buf), C.c_size_t(len(buf)), _p(coef), C.c_size_t(len(coef)), C.byref(lay))
+    if rc != L.UVO_OK:
+        raise L.UvoError(rc, "uvo_jpeg_entropy_decode: corrupt or unsupported JPEG stream")
+    return lay, coef
 
 
 class Context:
@@ -170,6 +192,18 @@ class Context:
         h, w = g.shape
         out = np.empty((h + 1, w + 1), np.int32)
         self._ck(self.lib.uvo_integral(self.h, _p(g), w, h, C.c_size_t(w), _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ math_utility.h:27
+    def jpeg_decode(self, data):
+        """the cv::imdecode(IMREAD_UNCHANGED) inside from_ros_to_cv_image: h x w (1 component) or h x w x 3 BGR"""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        lay = jpeg_info(data)
+        ch = 1 if lay.components == 1 else 3
+        out = np.empty((lay.height, lay.width) if ch == 1 else (lay.height, lay.width, 3), np.uint8)
+        w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_jpeg_decode(self.h, _p(buf), C.c_size_t(len(buf)), _p(out), C.c_size_t(lay.width * ch),
+                                          C.c_size_t(out.nbytes), C.byref(w), C.byref(h), C.byref(c)))
         return out
 
     # ------------------------------------------------------------------ VO_utility.h:100

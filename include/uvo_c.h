@@ -158,6 +158,31 @@ UVO_API int uvo_resize_area(uvo_ctx* ctx, const uint8_t* src_host, int src_width
 UVO_API int uvo_integral(uvo_ctx* ctx, const uint8_t* gray_host, int width, int height, size_t pitch,
                          int32_t* sum_host);
 
+/* ---------------------------------------------------------------------------------------------------- ingest: JPEG */
+/* The decode inside Mat from_ros_to_cv_image(const sensor_msgs::CompressedImage::ConstPtr&) -- math_utility.h:27,
+ * math_utility.cpp:154-173: cv_bridge::toCvCopy -> cv::imdecode(IMREAD_UNCHANGED) -> libjpeg-turbo (JDCT_ISLOW, fancy
+ * upsampling, YCbCr -> BGR).  Baseline / extended-sequential Huffman streams, 8-bit, 1 or 3 components; anything else
+ * returns UVO_ERR_UNSUPPORTED.  Entropy decoding runs on the host, the transform on the GPU (csrc/jpeg.cu). */
+typedef struct {
+  int32_t width, height, components;   /* components: 1 (e.g. a bayer mosaic) or 3 (YCbCr) */
+  int32_t h_samp[3], v_samp[3];        /* sampling factors of the frame header */
+  int32_t blocks_x[3], blocks_y[3];    /* 8x8 blocks per component row / column, padded to whole MCUs */
+  int32_t samples_x[3], samples_y[3];  /* real samples per component row / column (libjpeg's downsampled_width/height) */
+  int64_t coeff_offset[3];             /* index of the component's first coefficient in the coefficient buffer */
+  int64_t coeff_total;                 /* coefficients in all: sum of blocks_x * blocks_y * 64 */
+  uint16_t quant[3][64];               /* quantisation table per component, natural (row-major) order */
+} uvo_jpeg_layout;
+/* header only (host, no GPU): sizes for the caller's buffers */
+UVO_API int uvo_jpeg_info(const uint8_t* jpeg, size_t len, uvo_jpeg_layout* layout);
+/* host half (no GPU): Huffman decoding into quantised coefficients, int16, per component blocks_y x blocks_x x 64 in
+ * natural order at coeff_offset[c]; `capacity` in coefficients (>= coeff_total, else UVO_ERR_CAPACITY) */
+UVO_API int uvo_jpeg_entropy_decode(const uint8_t* jpeg, size_t len, int16_t* coeffs_host, size_t capacity,
+                                    uvo_jpeg_layout* layout);
+/* the whole decode: out_host is height x width (1 component) or height x width x 3 BGR, rows out_pitch bytes apart,
+ * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes */
+UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
+                            size_t out_capacity, int* width, int* height, int* channels);
+
 /* ---------------------------------------------------------------------------------------------------- K4-K7 */
 /* void detect_features(Mat img, vector<KeyPoint>&, Mat& descriptors) -- VO_utility.h:100, VO_utility.cpp:114-119:
  * SURF::create(hess, octaves, layers, extended, upright)->detectAndCompute.  Keypoints come back in OpenCV's order

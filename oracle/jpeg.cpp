@@ -474,6 +474,23 @@ extern "C" int orc_jpeg_info(const uint8_t* data, size_t len, int* w, int* h, in
   return 0;
 }
 
+// parity tap: the quantised coefficients after entropy decoding, component after component, each blocks_y x blocks_x
+// x 64 in natural order with the block grid padded to whole MCUs.  Returns the count (negative: error / too small).
+extern "C" long orc_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* out, size_t capacity) {
+  Decoder D;
+  const int rc = D.parse_and_decode(data, len);
+  if (rc < 0) return rc;
+  size_t total = 0;
+  for (int c = 0; c < D.nc; c++) total += D.comp[c].coef.size();
+  if (total > capacity) return -3;
+  size_t off = 0;
+  for (int c = 0; c < D.nc; c++) {
+    std::memcpy(out + off, D.comp[c].coef.data(), sizeof(int16_t) * D.comp[c].coef.size());
+    off += D.comp[c].coef.size();
+  }
+  return (long)total;
+}
+
 // out: h x w (1 component) or h x w x 3 BGR, as cv::imdecode(IMREAD_UNCHANGED) returns it
 extern "C" int orc_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out) {
   Decoder D;

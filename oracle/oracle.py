@@ -128,6 +128,22 @@ def jpeg_decode(data):
     return out
 
 
+def jpeg_coefficients(data):
+    """quantised coefficients after entropy decoding (parity tap for the product's host-side Huffman decoder)"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    cap = 1 << 20
+    while True:
+        out = np.empty(cap, np.int16)
+        lib().orc_jpeg_coefficients.restype = C.c_long
+        n = lib().orc_jpeg_coefficients(_p(buf), C.c_size_t(len(buf)), _p(out), C.c_size_t(cap))
+        if n == -3:
+            cap *= 4
+            continue
+        if n < 0:
+            raise ValueError(f"orc_jpeg_coefficients: {n}")
+        return out[:n].copy()
+
+
 def resize_area(src, dw, dh):
     src = np.ascontiguousarray(src, dtype=np.uint8)
     sh, sw = src.shape[:2]

@@ -112,6 +112,9 @@ void orc_epnp(const double* X, const double* x, int n, const double K[4], double
 /* ---- ingest: JPEG decode of from_ros_to_cv_image (math_utility.cpp:154-173: cv_bridge::toCvCopy -> cv::imdecode) ---- */
 /* baseline / extended-sequential Huffman, 8-bit, 1 or 3 components.  0 on success, -1 corrupt, -2 unsupported. */
 int orc_jpeg_info(const uint8_t* data, size_t len, int* w, int* h, int* channels);
+/* parity tap: quantised coefficients after entropy decoding (component-major, blocks padded to whole MCUs, natural
+ * order); returns their count, negative on error */
+long orc_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* out, size_t capacity);
 /* out: h x w (1 component) or h x w x 3 BGR, as cv::imdecode(IMREAD_UNCHANGED) lays it out */
 int orc_jpeg_decode(const uint8_t* data, size_t len, uint8_t* out);
 

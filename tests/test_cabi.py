@@ -109,16 +109,18 @@ def test_ctypes_mirrors_have_the_header_sizes(tmp_path):
     import ergo_uvo_b200 as U
     from ergo_uvo_b200 import _lib as L
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvo_c.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvo_c.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(uvo_params), sizeof(uvo_camera), sizeof(uvo_stereo_result), sizeof(uvo_mono_result),'
                    'sizeof(uvo_keypoint), sizeof(uvo_dmatch), offsetof(uvo_params, stereo_gate),'
-                   'offsetof(uvo_params, max_features));return 0;}\n')
+                   'offsetof(uvo_params, max_features), sizeof(uvo_jpeg_layout), offsetof(uvo_jpeg_layout, coeff_offset),'
+                   'offsetof(uvo_jpeg_layout, quant));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(L.Params), C.sizeof(L.Camera), C.sizeof(L.StereoResult), C.sizeof(L.MonoResult),
             U.KEYPOINT_DTYPE.itemsize, U.DMATCH_DTYPE.itemsize, L.Params.stereo_gate.offset,
-            L.Params.max_features.offset]
+            L.Params.max_features.offset, C.sizeof(L.JpegLayout), L.JpegLayout.coeff_offset.offset,
+            L.JpegLayout.quant.offset]
     assert got == want
 
 

@@ -1,0 +1,83 @@
+"""CPU: the host half of the JPEG decode in the product library (csrc/jpeg.cu: uvo_jpeg_info and
+uvo_jpeg_entropy_decode, host-only entry points like the camera set-up) against the oracle's coefficients -- exact.
+This is the decode inside from_ros_to_cv_image (math_utility.cpp:154-173).  The GPU half (IDCT, upsampling, colour)
+is compared with the oracle in tests/test_gpu_zz_jpeg.py."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import noise_image
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+try:
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+def _same(U, oracle, data):
+    lay, coef = U.jpeg_entropy_decode(data)
+    want = oracle.jpeg_coefficients(data)
+    assert lay.coeff_total == len(want) == len(coef)
+    assert np.array_equal(coef, want)
+    return lay
+
+
+def test_entropy_decode_golden_streams(oracle):
+    import ergo_uvo_b200 as U
+    z = np.load(os.path.join(GOLD, "jpeg_64x48.npz"))
+    for n in ("c420_rst2", "c422", "c440", "c444_opt", "gray"):
+        data = z[n + "_jpg"].tobytes()
+        lay = _same(U, oracle, data)
+        img = z[n + "_img"]
+        assert (lay.height, lay.width) == img.shape[:2] and lay.components == (1 if img.ndim == 2 else 3)
+    lay = U.jpeg_info(z["c420_rst2_jpg"].tobytes())
+    assert list(lay.h_samp) == [2, 1, 1] and list(lay.v_samp) == [2, 1, 1]
+    assert list(lay.blocks_x) == [8, 4, 4] and list(lay.blocks_y) == [6, 3, 3]          # 61 x 45: 4 x 3 MCUs of 16 x 16
+    assert list(lay.samples_x) == [61, 31, 31] and list(lay.samples_y) == [45, 23, 23]
+    assert list(lay.coeff_offset) == [0, 48 * 64, 60 * 64] and lay.coeff_total == 72 * 64
+    assert lay.quant[0][0] > 0 and lay.quant[1][63] > 0
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_entropy_decode_live_streams(oracle):
+    import ergo_uvo_b200 as U
+    from PIL import Image
+    rs = np.random.RandomState(3)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    n = 0
+    for h, w in [(1, 1), (3, 5), (17, 33), (31, 47), (100, 6), (243, 317)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8) if h < 40 else noise_image(h, w, seed=h, channels=3)
+        for sf in ("444", "422", "420", "440", "411"):
+            for q, rst in ((15, 0), (75, 3), (100, 1)):
+                ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, S,
+                                                     getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sf),
+                                                     cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                _same(U, oracle, enc.tobytes())
+                n += 1
+        ok, enc = cv2.imencode(".jpg", img[:, :, 0].copy(), [cv2.IMWRITE_JPEG_QUALITY, 60, cv2.IMWRITE_JPEG_OPTIMIZE, 1])
+        _same(U, oracle, enc.tobytes())
+    big = noise_image(1024, 1280, seed=9, channels=3)
+    ok, enc = cv2.imencode(".jpg", big, [cv2.IMWRITE_JPEG_QUALITY, 90])
+    lay = _same(U, oracle, enc.tobytes())
+    assert (lay.width, lay.height) == (1280, 1024)
+    b = io.BytesIO()
+    Image.fromarray(big[:200, :300, ::-1]).save(b, "JPEG", quality=85, subsampling=2, optimize=True)
+    _same(U, oracle, b.getvalue())
+    assert n == 90
+
+
+def test_entropy_decode_refusals():
+    import ergo_uvo_b200 as U
+    with pytest.raises(U.UvoError) as e:
+        U.jpeg_info(b"not a jpeg at all")
+    assert e.value.code == -3
+    z = np.load(os.path.join(GOLD, "jpeg_64x48.npz"))
+    data = z["c444_opt_jpg"].tobytes()
+    with pytest.raises(U.UvoError) as e:
+        U.jpeg_info(data.replace(b"\xff\xc0", b"\xff\xc2", 1))  # a progressive frame header
+    assert e.value.code == -5
+    with pytest.raises(U.UvoError):
+        U.jpeg_info(data[:100])  # cut inside the tables: no frame header
