@@ -34,6 +34,21 @@ struct HuffTab {
   int32_t maxcode[18];            // largest code of each length, -1 if none
   int32_t valoff[17];             // huffval index of the first code of a length minus that code
   uint8_t huffval[256];
+  // AC tables only: where code + magnitude bits fit in FAST_BITS, the whole coefficient in one look-up:
+  // (value << 16) | (zero run << 8) | bits consumed; 0 = take the two-step path
+  int32_t fast_ac[1 << FAST_BITS];
+  void build_fast_ac() {
+    for (int i = 0; i < (1 << FAST_BITS); i++) {
+      fast_ac[i] = 0;
+      const unsigned e = fast[i];
+      if (!e) continue;
+      const int len = e >> 8, run = (e & 255) >> 4, mag = e & 15;
+      if (mag == 0 || len + mag > FAST_BITS) continue;
+      int v = ((i << len) & ((1 << FAST_BITS) - 1)) >> (FAST_BITS - mag);
+      if (v < (1 << (mag - 1))) v += -(1 << mag) + 1;
+      fast_ac[i] = v * 65536 + (run << 8) + (len + mag);
+    }
+  }
   void build(const uint8_t counts[16], const uint8_t* vals, int nv) {
     memcpy(huffval, vals, nv);
     memset(fast, 0, sizeof(fast));
@@ -207,6 +222,7 @@ struct Parser {
       for (int j = 0; j < 16; j++) nv += s[k + 1 + j];
       if (th > 3 || tc > 1 || nv > 256 || k + 17 + nv > n) throw InvalidArg{"jpeg: bad DHT", UVO_ERR_INVALID};
       (tc ? ac : dc)[th].build(s + k + 1, s + k + 17, nv);
+      if (tc) ac[th].build_fast_ac();
       k += 17 + nv;
     }
   }
@@ -316,6 +332,15 @@ struct Parser {
     out[0] = (int16_t)c.pred;
     const HuffTab& t = ac[c.ta];
     for (int k = 1; k < 64;) {
+      if (b.cnt < 16) b.refill();
+      const int fa = t.fast_ac[b.peek(FAST_BITS)];
+      if (fa) {  // run, size and magnitude bits in one step
+        k += (fa >> 8) & 255;
+        if (k > 63) throw InvalidArg{"jpeg: corrupt AC run", UVO_ERR_INVALID};
+        b.skip(fa & 255);
+        out[kNatural[k++]] = (int16_t)(fa >> 16);
+        continue;
+      }
       const int rs = huff_decode(b, t);
       s = rs & 15;
       if (s == 0) {
