@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "capi_internal.cuh"
+#include "jpeg_kernels.cuh"
 
 using namespace uvo;
 
@@ -357,160 +358,19 @@ struct Parser {
 };
 
 // ------------------------------------------------------------------------------------------------ device
-struct IdctComp {
-  const int16_t* coef;  // blocks_y x blocks_x x 64, natural order
-  uint8_t* plane;       // (blocks_y * 8) rows, pitch = blocks_x * 8
-  int blocks_x, n_blocks, first;  // first: index of the component's first block in the launch
-  uint16_t quant[64];
-};
-struct IdctArgs {
-  IdctComp c[3];
-  int n_comp, total_blocks;
-};
+// The thread bodies live in jpeg_kernels.cuh (host/device functions of the block and thread index, so that the test
+// harness can run the same code on the CPU); the kernels bind them to the launch geometry.
+using namespace uvo::jpegk;
 
-__device__ __forceinline__ int jdescale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
-// libjpeg's post-IDCT range-limit table, indexed with the value masked to 10 bits
-__device__ __forceinline__ unsigned jrange(int v) {
-  const int i = v & 1023;
-  return (unsigned)(i < 128 ? i + 128 : i < 512 ? 255 : i < 896 ? 0 : i - 896);
-}
-
-// one 1-D pass of jpeg_idct_islow on eight inputs; results not yet descaled
-__device__ __forceinline__ void islow_1d(const int in[8], int out[8], const int even_shift) {
-  constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
-                F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
-  int z2 = in[2], z3 = in[6];
-  int z1 = (z2 + z3) * F_0_541;
-  int tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
-  int tmp0 = (in[0] + in[4]) << even_shift, tmp1 = (in[0] - in[4]) << even_shift;
-  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-  tmp0 = in[7];
-  tmp1 = in[5];
-  tmp2 = in[3];
-  tmp3 = in[1];
-  z1 = tmp0 + tmp3;
-  z2 = tmp1 + tmp2;
-  z3 = tmp0 + tmp2;
-  int z4 = tmp1 + tmp3;
-  const int z5 = (z3 + z4) * F_1_175;
-  tmp0 *= F_0_298;
-  tmp1 *= F_2_053;
-  tmp2 *= F_3_072;
-  tmp3 *= F_1_501;
-  z1 *= -F_0_899;
-  z2 *= -F_2_562;
-  z3 *= -F_1_961;
-  z4 *= -F_0_390;
-  z3 += z5;
-  z4 += z5;
-  tmp0 += z1 + z3;
-  tmp1 += z2 + z4;
-  tmp2 += z2 + z3;
-  tmp3 += z1 + z4;
-  out[0] = tmp10 + tmp3;
-  out[7] = tmp10 - tmp3;
-  out[1] = tmp11 + tmp2;
-  out[6] = tmp11 - tmp2;
-  out[2] = tmp12 + tmp1;
-  out[5] = tmp12 - tmp1;
-  out[3] = tmp13 + tmp0;
-  out[4] = tmp13 - tmp0;
-}
-
-constexpr int IDCT_THREADS = 256, IDCT_BLOCKS = IDCT_THREADS / 8;  // JPEG blocks per thread block
-
-// eight threads per 8x8 block: thread t transforms column t (dequantising on the way in), then row t.  The zero-AC
-// shortcut of the CPU code is not needed: the full column pass yields dc * 4 exactly in that case.
 __global__ void __launch_bounds__(IDCT_THREADS) k_jpeg_idct(const __grid_constant__ IdctArgs a) {
-  __shared__ int s_ws[IDCT_BLOCKS][64 + 8];  // +8: rows of a block land on different banks in pass 2
-  const int t = threadIdx.x & 7, g = threadIdx.x >> 3;
-  const int blk = blockIdx.x * IDCT_BLOCKS + g;
-  const bool live = blk < a.total_blocks;
-  int ci = 0;
-  if (live)
-    while (ci + 1 < a.n_comp && blk >= a.c[ci + 1].first) ci++;
-  const IdctComp& c = a.c[ci];
-  const int local = blk - c.first;
-  if (live) {
-    const int16_t* in = c.coef + (size_t)local * 64;
-    int v[8], o[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = (int)in[8 * r + t] * (int)c.quant[8 * r + t];
-    islow_1d(v, o, 13);
-#pragma unroll
-    for (int r = 0; r < 8; r++) s_ws[g][9 * r + t] = jdescale(o[r], 11);  // CONST_BITS - PASS1_BITS
-  }
-  __syncwarp();  // the eight threads of a block sit in one warp
-  if (live) {
-    int v[8], o[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = s_ws[g][9 * t + k];
-    islow_1d(v, o, 13);
-    unsigned lo = 0, hi = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      lo |= jrange(jdescale(o[k], 18)) << (8 * k);  // CONST_BITS + PASS1_BITS + 3
-      hi |= jrange(jdescale(o[4 + k], 18)) << (8 * k);
-    }
-    const int by = local / c.blocks_x, bx = local - by * c.blocks_x;
-    uint8_t* dst = c.plane + ((size_t)(by * 8 + t) * c.blocks_x + bx) * 8;
-    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
-  }
+  __shared__ int s_ws[IDCT_BLOCKS * WS_STRIDE];
+  idct_pass1(a, blockIdx.x, threadIdx.x, s_ws);
+  __syncwarp();  // the eight threads of a JPEG block sit in one warp
+  idct_pass2(a, blockIdx.x, threadIdx.x, s_ws);
 }
 
-struct ColorComp {
-  const uint8_t* plane;
-  int pitch, dw, dh;   // real sample counts of the component
-  int hexp, vexp;      // expansion to full resolution
-};
-struct ColorArgs {
-  ColorComp c[3];
-  int w, h;
-  uint8_t* out;
-  size_t out_pitch;
-};
-
-// the component's value at full-resolution pixel (x, y): jdsample.c's fancy filters, replication otherwise
-__device__ __forceinline__ int jsample(const ColorComp& c, int x, int y) {
-  if (c.hexp == 1 && c.vexp == 1) return c.plane[(size_t)y * c.pitch + x];
-  const bool fancy = c.dw > 2;
-  if (c.hexp == 2 && c.vexp == 1 && fancy) {  // h2v1_fancy_upsample
-    const uint8_t* p = c.plane + (size_t)y * c.pitch;
-    const int i = x >> 1;
-    if (x & 1) return i == c.dw - 1 ? p[i] : (p[i] * 3 + p[i + 1] + 2) >> 2;
-    return i == 0 ? p[0] : (p[i] * 3 + p[i - 1] + 1) >> 2;
-  }
-  if (c.hexp == 2 && c.vexp == 2 && fancy) {  // h2v2_fancy_upsample
-    const int r = y >> 1, r1 = (y & 1) ? min(r + 1, c.dh - 1) : max(r - 1, 0);
-    const uint8_t* p0 = c.plane + (size_t)r * c.pitch;
-    const uint8_t* p1 = c.plane + (size_t)r1 * c.pitch;
-    const int i = x >> 1;
-    const int cs = p0[i] * 3 + p1[i];
-    if (x & 1) return i == c.dw - 1 ? (cs * 4 + 7) >> 4 : (cs * 3 + p0[i + 1] * 3 + p1[i + 1] + 7) >> 4;
-    return i == 0 ? (cs * 4 + 8) >> 4 : (cs * 3 + p0[i - 1] * 3 + p1[i - 1] + 8) >> 4;
-  }
-  if (c.hexp == 1 && c.vexp == 2) {  // h1v2_fancy_upsample
-    const int r = y >> 1, r1 = (y & 1) ? min(r + 1, c.dh - 1) : max(r - 1, 0);
-    return (c.plane[(size_t)r * c.pitch + x] * 3 + c.plane[(size_t)r1 * c.pitch + x] + ((y & 1) ? 2 : 1)) >> 2;
-  }
-  return c.plane[(size_t)(y / c.vexp) * c.pitch + x / c.hexp];
-}
-
-__device__ __forceinline__ unsigned jclamp(int v) { return (unsigned)min(max(v, 0), 255); }
-
-// jdcolor.c ycc_rgb_convert (SCALEBITS 16), written B, G, R
-__global__ void __launch_bounds__(256) k_jpeg_color(const __grid_constant__ ColorArgs a) {
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (x >= a.w || y >= a.h) return;
-  const int Y = jsample(a.c[0], x, y), cb = jsample(a.c[1], x, y) - 128, cr = jsample(a.c[2], x, y) - 128;
-  constexpr int FIX_1_402 = 91881, FIX_1_772 = 116130, FIX_0_714 = 46802, FIX_0_344 = 22554;
-  const int r = Y + ((FIX_1_402 * cr + 32768) >> 16);
-  const int g = Y + ((-FIX_0_344 * cb + 32768 - FIX_0_714 * cr) >> 16);
-  const int b = Y + ((FIX_1_772 * cb + 32768) >> 16);
-  uint8_t* o = a.out + (size_t)y * a.out_pitch + 3 * (size_t)x;
-  o[0] = (uint8_t)jclamp(b);
-  o[1] = (uint8_t)jclamp(g);
-  o[2] = (uint8_t)jclamp(r);
+__global__ void __launch_bounds__(COLOR_TX* COLOR_TY) k_jpeg_color(const __grid_constant__ ColorArgs a) {
+  color_thread(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 }  // namespace
@@ -564,56 +424,23 @@ int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_
     // device: coefficients, component planes, output
     StageScratch& s = ctx->scratch;
     s.bytes_a.ensure(sizeof(int16_t) * total);
-    size_t plane_bytes = 0, plane_off[3];
-    for (int k = 0; k < nc; k++) {
-      plane_off[k] = plane_bytes;
-      plane_bytes += (size_t)L.blocks_x[k] * L.blocks_y[k] * 64;
-    }
-    s.bytes_b.ensure(plane_bytes);
+    s.bytes_b.ensure(jpegk::plane_bytes(L));
+    const size_t dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
+    if (nc == 3) s.bytes_c.ensure(dpitch * Hh);
     UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), ctx->jpeg_coef.p, sizeof(int16_t) * total, cudaMemcpyHostToDevice,
                              c.stream));
-    IdctArgs ia{};
-    ia.n_comp = nc;
-    int first = 0;
-    for (int k = 0; k < nc; k++) {
-      ia.c[k].coef = (const int16_t*)s.bytes_a.get() + L.coeff_offset[k];
-      ia.c[k].plane = s.bytes_b.get() + plane_off[k];
-      ia.c[k].blocks_x = L.blocks_x[k];
-      ia.c[k].n_blocks = L.blocks_x[k] * L.blocks_y[k];
-      ia.c[k].first = first;
-      memcpy(ia.c[k].quant, L.quant[k], sizeof(ia.c[k].quant));
-      first += ia.c[k].n_blocks;
-    }
-    ia.total_blocks = first;
+    IdctArgs ia;
+    ColorArgs ca;
+    fill_args(L, (const int16_t*)s.bytes_a.get(), s.bytes_b.get(), nc == 3 ? s.bytes_c.get() : nullptr, dpitch, ia, ca);
     UVO_KERNEL(c, "k_jpeg_idct");
-    k_jpeg_idct<<<div_up(first, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
+    k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
     UVO_LAUNCH_CHECK(c);
     if (nc == 1) {  // the luminance plane is the image
       UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh,
                                  cudaMemcpyDeviceToHost, c.stream));
     } else {
-      const size_t dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
-      s.bytes_c.ensure(dpitch * Hh);
-      ColorArgs ca{};
-      int hmax = 1, vmax = 1;
-      for (int k = 0; k < 3; k++) {
-        hmax = std::max(hmax, L.h_samp[k]);
-        vmax = std::max(vmax, L.v_samp[k]);
-      }
-      for (int k = 0; k < 3; k++) {
-        ca.c[k].plane = ia.c[k].plane;
-        ca.c[k].pitch = L.blocks_x[k] * 8;
-        ca.c[k].dw = L.samples_x[k];
-        ca.c[k].dh = L.samples_y[k];
-        ca.c[k].hexp = hmax / L.h_samp[k];
-        ca.c[k].vexp = vmax / L.v_samp[k];
-      }
-      ca.w = W;
-      ca.h = Hh;
-      ca.out = s.bytes_c.get();
-      ca.out_pitch = dpitch;
       UVO_KERNEL(c, "k_jpeg_color");
-      k_jpeg_color<<<dim3(div_up(W, 64), div_up(Hh, 4)), 256, 0, c.stream>>>(ca);
+      k_jpeg_color<<<dim3(div_up(W, COLOR_TX), div_up(Hh, COLOR_TY)), COLOR_TX * COLOR_TY, 0, c.stream>>>(ca);
       UVO_LAUNCH_CHECK(c);
       UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s.bytes_c.get(), dpitch, (size_t)3 * W, Hh,
                                  cudaMemcpyDeviceToHost, c.stream));

@@ -2,7 +2,8 @@
 cv::imdecode(IMREAD_UNCHANGED) inside from_ros_to_cv_image (math_utility.cpp:154-173).
 
 STATUS: the two kernels were written after round 1's GPU minutes were spent and have NOT run on a GPU yet (the host
-half is verified on the CPU: tests/test_jpeg_host.py).  Until their first run these tests are non-strict xfail, so an
+half is verified on the CPU: tests/test_jpeg_host.py; the kernels' thread bodies are executed on the CPU over the launch
+grid by tests/test_jpeg_emu.py).  Until their first run these tests are non-strict xfail, so an
 unverified kernel cannot turn the parity suite red; DESIGN.md says the same.  Remove the marker after the first pass."""
 import os
 
