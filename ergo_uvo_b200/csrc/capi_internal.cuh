@@ -22,6 +22,6 @@ struct uvo_ctx {
   uvo::FrontEnd fe;  // front end used by the stage-level uvo_detect_features
   uvo::PinnedBuf<int> pinned_counts;
   int last_match_fallbacks = 0;  // queries of the last matcher call that took the exact full-scan path
-  uvo::PinnedBuf<int16_t> jpeg_coef;  // uvo_jpeg_decode: quantised coefficients, host side of the H2D copy
+  uvo::PinnedBuf<uint32_t> jpeg_coef;  // uvo_jpeg_decode: sparse quantised coefficients, host side of the H2D copy
   int match_exact_only = 0;      // diagnostics (uvo_match_exact_only): stage-level matcher calls skip the tcgen05 pass
 };

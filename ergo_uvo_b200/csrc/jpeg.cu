@@ -132,6 +132,18 @@ inline int receive_extend(BitReader& b, int s) {
   return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
 }
 
+// Where the decoded coefficients go.  Dense: int16 planes (the parity tap uvo_jpeg_entropy_decode).  Sparse: what
+// uvo_jpeg_decode ships to the GPU -- one 32-bit entry per NON-ZERO coefficient, (natural index << 16) | value, in scan
+// order, plus per block (numbered component-major, row-major: the k_jpeg_idct launch order) the position of its first
+// entry and its entry count.  At q75-q90 11-16 % of the coefficients are non-zero: ~1 MB instead of 3.9 MB per 1280x1024.
+struct CoefSink {
+  int16_t* dense = nullptr;
+  uint32_t* entries = nullptr;
+  uint32_t* first = nullptr;
+  uint8_t* count = nullptr;
+  size_t n = 0, cap = 0;
+};
+
 struct CompInfo {
   int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
 };
@@ -151,7 +163,19 @@ struct Parser {
   }
 
   // walks the marker segments; with `coef` decodes every scan into it, without stops at the first SOS
+  CoefSink sink;
   void run(const uint8_t* d, size_t len, int16_t* coef) {
+    sink.dense = coef;
+    walk(d, len, coef != nullptr);
+  }
+  void run_sparse(const uint8_t* d, size_t len, uint32_t* entries, size_t cap, uint32_t* first, uint8_t* count) {
+    sink.entries = entries;
+    sink.cap = cap;
+    sink.first = first;
+    sink.count = count;
+    walk(d, len, true);
+  }
+  void walk(const uint8_t* d, size_t len, bool decode) {
     if (!d || len < 4 || d[0] != 0xFF || d[1] != 0xD8) throw InvalidArg{"jpeg: not a JPEG stream (no SOI)", UVO_ERR_INVALID};
     size_t i = 2;
     while (i + 4 <= len) {
@@ -181,12 +205,12 @@ struct Parser {
           break;
         case 0xDA: {
           if (!have_sof) throw InvalidArg{"jpeg: SOS before SOF", UVO_ERR_INVALID};
-          if (!coef) {  // header only: report the quantisation tables as defined so far
+          if (!decode) {  // header only: report the quantisation tables as defined so far
             for (int c = 0; c < L.components; c++)
               if (qt_present[comp[c].tq]) memcpy(L.quant[c], qt[comp[c].tq], sizeof(L.quant[0]));
             return;
           }
-          const uint8_t* e = scan(s, n, d + i + seg, d + len, coef);
+          const uint8_t* e = scan(s, n, d + i + seg, d + len);
           i = (size_t)(e - d);
           continue;
         }
@@ -270,7 +294,7 @@ struct Parser {
   }
 
   // one scan: header at s, entropy-coded data from p; returns the position of the marker that ends it
-  const uint8_t* scan(const uint8_t* s, size_t n, const uint8_t* p, const uint8_t* end, int16_t* coef) {
+  const uint8_t* scan(const uint8_t* s, size_t n, const uint8_t* p, const uint8_t* end) {
     const int ns = n ? s[0] : 0;
     if (ns < 1 || ns > L.components || n < (size_t)(1 + 2 * ns + 3)) throw InvalidArg{"jpeg: bad SOS", UVO_ERR_INVALID};
     int idx[3];
@@ -316,7 +340,11 @@ struct Parser {
           for (int by = 0; by < nby; by++)
             for (int bx = 0; bx < nbx; bx++) {
               const int X = mx * nbx + bx, Y = my * nby + by;
-              block(b, c, coef + L.coeff_offset[ci] + ((int64_t)Y * L.blocks_x[ci] + X) * 64);
+              const int64_t blk = L.coeff_offset[ci] / 64 + (int64_t)Y * L.blocks_x[ci] + X;
+              if (sink.dense)
+                block<false>(b, c, sink.dense + blk * 64, blk);
+              else
+                block<true>(b, c, nullptr, blk);
             }
         }
         if (restart) left--;
@@ -326,11 +354,23 @@ struct Parser {
     return q;
   }
 
-  void block(BitReader& b, CompInfo& c, int16_t* out) {
+  template <bool SPARSE>
+  void emit(int16_t* out, int pos, int value) {
+    if (SPARSE) {
+      if (sink.n >= sink.cap) throw InvalidArg{"jpeg: coefficient entry buffer too small", UVO_ERR_CAPACITY};
+      sink.entries[sink.n++] = ((uint32_t)pos << 16) | (uint16_t)(int16_t)value;
+    } else {
+      out[pos] = (int16_t)value;
+    }
+  }
+
+  template <bool SPARSE>
+  void block(BitReader& b, CompInfo& c, int16_t* out, int64_t blk) {
+    const size_t n0 = sink.n;
     int s = huff_decode(b, dc[c.td]);
     if (s > 15) throw InvalidArg{"jpeg: corrupt DC coefficient", UVO_ERR_INVALID};
     c.pred += s ? receive_extend(b, s) : 0;
-    out[0] = (int16_t)c.pred;
+    if (!SPARSE || (int16_t)c.pred != 0) emit<SPARSE>(out, 0, c.pred);
     const HuffTab& t = ac[c.ta];
     for (int k = 1; k < 64;) {
       if (b.cnt < 16) b.refill();
@@ -339,7 +379,7 @@ struct Parser {
         k += (fa >> 8) & 255;
         if (k > 63) throw InvalidArg{"jpeg: corrupt AC run", UVO_ERR_INVALID};
         b.skip(fa & 255);
-        out[kNatural[k++]] = (int16_t)(fa >> 16);
+        emit<SPARSE>(out, kNatural[k++], fa >> 16);
         continue;
       }
       const int rs = huff_decode(b, t);
@@ -351,8 +391,12 @@ struct Parser {
       }
       k += rs >> 4;
       if (k > 63) throw InvalidArg{"jpeg: corrupt AC run", UVO_ERR_INVALID};
-      out[kNatural[k]] = (int16_t)receive_extend(b, s);
+      emit<SPARSE>(out, kNatural[k], receive_extend(b, s));
       k++;
+    }
+    if (SPARSE) {
+      sink.first[blk] = (uint32_t)n0;
+      sink.count[blk] = (uint8_t)(sink.n - n0);  // <= 64
     }
   }
 };
@@ -364,8 +408,13 @@ using namespace uvo::jpegk;
 
 __global__ void __launch_bounds__(IDCT_THREADS) k_jpeg_idct(const __grid_constant__ IdctArgs a) {
   __shared__ int s_ws[IDCT_BLOCKS * WS_STRIDE];
-  idct_pass1(a, blockIdx.x, threadIdx.x, s_ws);
+  __shared__ int16_t s_tile[IDCT_BLOCKS * TILE_STRIDE];
+  idct_clear(a, blockIdx.x, threadIdx.x, s_tile);
   __syncwarp();  // the eight threads of a JPEG block sit in one warp
+  idct_scatter(a, blockIdx.x, threadIdx.x, s_tile);
+  __syncwarp();
+  idct_pass1(a, blockIdx.x, threadIdx.x, s_tile, s_ws);
+  __syncwarp();
   idct_pass2(a, blockIdx.x, threadIdx.x, s_ws);
 }
 
@@ -401,6 +450,23 @@ int uvo_jpeg_entropy_decode(const uint8_t* jpeg, size_t len, int16_t* coeffs_hos
   });
 }
 
+int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries_host, size_t capacity,
+                                   uint32_t* block_first_host, uint8_t* block_count_host, size_t* n_entries,
+                                   uvo_jpeg_layout* layout) {
+  if (!layout || !entries_host || !block_first_host || !block_count_host || !n_entries) return UVO_ERR_INVALID;
+  return guarded(nullptr, [&] {
+    Parser H;
+    H.run(jpeg, len, nullptr);
+    const size_t nb = (size_t)H.L.coeff_total / 64;
+    memset(block_first_host, 0, sizeof(uint32_t) * nb);  // blocks no scan visits stay empty
+    memset(block_count_host, 0, nb);
+    Parser P;
+    P.run_sparse(jpeg, len, entries_host, capacity, block_first_host, block_count_host);
+    *n_entries = P.sink.n;
+    *layout = P.L;
+  });
+}
+
 int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
                     size_t out_capacity, int* width, int* height, int* channels) {
   if (!ctx) return UVO_ERR_INVALID;
@@ -414,24 +480,34 @@ int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_
     const int W = H.L.width, Hh = H.L.height, nc = H.L.components;
     if (out_pitch < (size_t)W * nc || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * nc)
       throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
-    // host: entropy decoding into pinned memory
+    // host: entropy decoding into pinned memory, as the sparse form (one 32-bit entry per non-zero coefficient + a
+    // (first, count) pair per block); one pinned buffer: [first: nb x u32][entries: <= total x u32][count: nb x u8]
     UVO_CUDA(cudaStreamSynchronize(c.stream));  // the pinned buffer may still feed the previous call's copy
-    ctx->jpeg_coef.ensure(total);
-    memset(ctx->jpeg_coef.p, 0, sizeof(int16_t) * total);
+    const size_t nb = total / 64;
+    ctx->jpeg_coef.ensure(nb + total + (nb + 3) / 4);
+    uint32_t* h_first = ctx->jpeg_coef.p;
+    uint32_t* h_entries = h_first + nb;
+    uint8_t* h_count = (uint8_t*)(h_entries + total);
+    memset(h_first, 0, sizeof(uint32_t) * nb);  // blocks no scan visits (padding of a non-interleaved scan) stay empty
+    memset(h_count, 0, nb);
     Parser P;
-    P.run(jpeg, len, ctx->jpeg_coef.p);
+    P.run_sparse(jpeg, len, h_entries, total, h_first, h_count);
     const uvo_jpeg_layout& L = P.L;
-    // device: coefficients, component planes, output
+    const size_t ne = P.sink.n;
+    // device: the same three arrays (only the used entries travel), component planes, output
     StageScratch& s = ctx->scratch;
-    s.bytes_a.ensure(sizeof(int16_t) * total);
+    s.bytes_a.ensure(sizeof(uint32_t) * (nb + std::max<size_t>(ne, 1)) + nb);
+    uint32_t* d_first = (uint32_t*)s.bytes_a.get();
+    uint32_t* d_entries = d_first + nb;
+    uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(ne, 1));
     s.bytes_b.ensure(jpegk::plane_bytes(L));
     const size_t dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
     if (nc == 3) s.bytes_c.ensure(dpitch * Hh);
-    UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), ctx->jpeg_coef.p, sizeof(int16_t) * total, cudaMemcpyHostToDevice,
-                             c.stream));
+    UVO_CUDA(cudaMemcpyAsync(d_first, h_first, sizeof(uint32_t) * (nb + ne), cudaMemcpyHostToDevice, c.stream));
+    UVO_CUDA(cudaMemcpyAsync(d_count, h_count, nb, cudaMemcpyHostToDevice, c.stream));
     IdctArgs ia;
     ColorArgs ca;
-    fill_args(L, (const int16_t*)s.bytes_a.get(), s.bytes_b.get(), nc == 3 ? s.bytes_c.get() : nullptr, dpitch, ia, ca);
+    fill_args(L, d_entries, d_first, d_count, s.bytes_b.get(), nc == 3 ? s.bytes_c.get() : nullptr, dpitch, ia, ca);
     UVO_KERNEL(c, "k_jpeg_idct");
     k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
     UVO_LAUNCH_CHECK(c);

@@ -26,14 +26,18 @@ namespace uvo {
 namespace jpegk {
 
 struct IdctComp {
-  const int16_t* coef;  // blocks_y x blocks_x x 64, natural order
-  uint8_t* plane;       // (blocks_y * 8) rows, pitch = blocks_x * 8
+  uint8_t* plane;  // (blocks_y * 8) rows, pitch = blocks_x * 8
   int blocks_x, n_blocks, first;  // first: index of the component's first block in the launch
   uint16_t quant[64];
 };
 struct IdctArgs {
   IdctComp c[3];
   int n_comp, total_blocks;
+  // sparse coefficients: per block (launch order: component-major, row-major) its first entry and entry count; an
+  // entry is (natural index << 16) | (value & 0xffff), non-zero coefficients only
+  const uint32_t* entries;
+  const uint32_t* first;
+  const uint8_t* count;
 };
 struct ColorComp {
   const uint8_t* plane;
@@ -49,6 +53,7 @@ struct ColorArgs {
 
 constexpr int IDCT_THREADS = 256, IDCT_BLOCKS = IDCT_THREADS / 8;  // JPEG blocks per thread block
 constexpr int WS_STRIDE = 72;  // ints of workspace per JPEG block: 8 rows 9 apart (rows on different banks in pass 2)
+constexpr int TILE_STRIDE = 64;  // int16 coefficients per JPEG block in the dense tile rebuilt in shared memory
 constexpr int COLOR_TX = 64, COLOR_TY = 4;
 
 UVO_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -120,13 +125,36 @@ UVO_HD IdctWho idct_who(const IdctArgs& a, int block_idx, int thread_idx) {
   return w;
 }
 
+// stage 0: the eight threads of a block clear its dense 8x8 tile (thread t: row t)
+UVO_HD void idct_clear(const IdctArgs& a, int block_idx, int thread_idx, int16_t* tile /* IDCT_BLOCKS x TILE_STRIDE */) {
+  const IdctWho w = idct_who(a, block_idx, thread_idx);
+  if (!w.live) return;
+  UVO_UNROLL
+  for (int k = 0; k < 8; k++) tile[w.g * TILE_STRIDE + 8 * w.t + k] = 0;
+}
+
+// stage 1: scatter the block's non-zero coefficients into the tile (thread t: entries t, t + 8, ...); positions are
+// distinct within a block, so the writes do not collide
+UVO_HD void idct_scatter(const IdctArgs& a, int block_idx, int thread_idx, int16_t* tile) {
+  const IdctWho w = idct_who(a, block_idx, thread_idx);
+  if (!w.live) return;
+  const int blk = block_idx * IDCT_BLOCKS + w.g;
+  const uint32_t* e = a.entries + a.first[blk];
+  const int n = a.count[blk];
+  for (int i = w.t; i < n; i += 8) {
+    const uint32_t v = e[i];
+    tile[w.g * TILE_STRIDE + (int)((v >> 16) & 63)] = (int16_t)(v & 0xffffu);
+  }
+}
+
 // pass 1: thread t transforms column t of its block (dequantising on the way in) into the block's workspace.  The
 // zero-AC shortcut of the CPU code is not needed: the full column pass yields dc * 4 exactly in that case.
-UVO_HD void idct_pass1(const IdctArgs& a, int block_idx, int thread_idx, int* ws /* IDCT_BLOCKS x WS_STRIDE */) {
+UVO_HD void idct_pass1(const IdctArgs& a, int block_idx, int thread_idx, const int16_t* tile,
+                       int* ws /* IDCT_BLOCKS x WS_STRIDE */) {
   const IdctWho w = idct_who(a, block_idx, thread_idx);
   if (!w.live) return;
   const IdctComp& c = a.c[w.ci];
-  const int16_t* in = c.coef + (size_t)w.local * 64;
+  const int16_t* in = tile + w.g * TILE_STRIDE;
   int v[8], o[8];
 UVO_UNROLL
   for (int r = 0; r < 8; r++) v[r] = (int)in[8 * r + w.t] * (int)c.quant[8 * r + w.t];
@@ -204,33 +232,32 @@ UVO_HD void color_thread(const ColorArgs& a, int block_x, int block_y, int threa
   o[2] = (uint8_t)jclamp(r);
 }
 
-// argument set-up shared by uvo_jpeg_decode and the harness: coefficient planes at coef + coeff_offset[c], sample
-// planes packed one after the other from `planes`
+// argument set-up shared by uvo_jpeg_decode and the harness: the sparse coefficient arrays, sample planes packed one
+// after the other from `planes`
 inline size_t plane_bytes(const uvo_jpeg_layout& L) {
   size_t n = 0;
   for (int k = 0; k < L.components; k++) n += (size_t)L.blocks_x[k] * L.blocks_y[k] * 64;
   return n;
 }
-inline void fill_args(const uvo_jpeg_layout& L, const int16_t* coef, uint8_t* planes, uint8_t* out, size_t out_pitch,
-                      IdctArgs& ia, ColorArgs& ca) {
+inline void fill_args(const uvo_jpeg_layout& L, const uint32_t* entries, const uint32_t* first, const uint8_t* count,
+                      uint8_t* planes, uint8_t* out, size_t out_pitch, IdctArgs& ia, ColorArgs& ca) {
   memset(&ia, 0, sizeof(ia));
   memset(&ca, 0, sizeof(ca));
   const int nc = L.components;
   ia.n_comp = nc;
-  int first = 0, hmax = 1, vmax = 1;
+  int first_block = 0, hmax = 1, vmax = 1;
   size_t off = 0;
   for (int k = 0; k < nc; k++) {
     hmax = L.h_samp[k] > hmax ? L.h_samp[k] : hmax;
     vmax = L.v_samp[k] > vmax ? L.v_samp[k] : vmax;
   }
   for (int k = 0; k < nc; k++) {
-    ia.c[k].coef = coef + L.coeff_offset[k];
     ia.c[k].plane = planes + off;
     ia.c[k].blocks_x = L.blocks_x[k];
     ia.c[k].n_blocks = L.blocks_x[k] * L.blocks_y[k];
-    ia.c[k].first = first;
+    ia.c[k].first = first_block;
     memcpy(ia.c[k].quant, L.quant[k], sizeof(ia.c[k].quant));
-    first += ia.c[k].n_blocks;
+    first_block += ia.c[k].n_blocks;
     off += (size_t)ia.c[k].n_blocks * 64;
     if (k < 3) {
       ca.c[k].plane = ia.c[k].plane;
@@ -241,7 +268,10 @@ inline void fill_args(const uvo_jpeg_layout& L, const int16_t* coef, uint8_t* pl
       ca.c[k].vexp = vmax / L.v_samp[k];
     }
   }
-  ia.total_blocks = first;
+  ia.total_blocks = first_block;
+  ia.entries = entries;
+  ia.first = first;
+  ia.count = count;
   ca.w = L.width;
   ca.h = L.height;
   ca.out = out;

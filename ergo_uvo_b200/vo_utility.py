@@ -16,7 +16,7 @@ KEYPOINT_DTYPE = np.dtype(
      ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
-__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "jpeg_info", "jpeg_entropy_decode", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
+__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "jpeg_info", "jpeg_entropy_decode", "jpeg_entropy_decode_sparse", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
 
 
 def _p(a):
@@ -87,6 +87,23 @@ def jpeg_entropy_decode(data):
     if rc != L.UVO_OK:
         raise L.UvoError(rc, "uvo_jpeg_entropy_decode: corrupt or unsupported JPEG stream")
     return lay, coef
+
+
+def jpeg_entropy_decode_sparse(data):
+    """uvo_jpeg_entropy_decode_sparse: (layout, entries u32, block_first u32, block_count u8) -- the form that travels
+    to the GPU: one entry per non-zero coefficient"""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    lay = jpeg_info(data)
+    nb = int(lay.coeff_total) // 64
+    entries = np.empty(int(lay.coeff_total), np.uint32)
+    first = np.empty(nb, np.uint32)
+    count = np.empty(nb, np.uint8)
+    n = C.c_size_t(0)
+    rc = L.load().uvo_jpeg_entropy_decode_sparse(_p(buf), C.c_size_t(len(buf)), _p(entries), C.c_size_t(len(entries)),
+                                                 _p(first), _p(count), C.byref(n), C.byref(lay))
+    if rc != L.UVO_OK:
+        raise L.UvoError(rc, "uvo_jpeg_entropy_decode_sparse: corrupt or unsupported JPEG stream")
+    return lay, entries[:n.value].copy(), first, count
 
 
 class Context:

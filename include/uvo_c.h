@@ -178,6 +178,13 @@ UVO_API int uvo_jpeg_info(const uint8_t* jpeg, size_t len, uvo_jpeg_layout* layo
  * natural order at coeff_offset[c]; `capacity` in coefficients (>= coeff_total, else UVO_ERR_CAPACITY) */
 UVO_API int uvo_jpeg_entropy_decode(const uint8_t* jpeg, size_t len, int16_t* coeffs_host, size_t capacity,
                                     uvo_jpeg_layout* layout);
+/* the same, in the form uvo_jpeg_decode ships to the GPU: one 32-bit entry per NON-ZERO coefficient,
+ * (natural index << 16) | (value & 0xffff), in scan order (capacity in entries; coeff_total always suffices), and per
+ * block -- numbered component-major, row-major, coeff_offset[c] / 64 first -- the index of its first entry and its
+ * entry count (coeff_total / 64 elements each) */
+UVO_API int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries_host, size_t capacity,
+                                           uint32_t* block_first_host, uint8_t* block_count_host, size_t* n_entries,
+                                           uvo_jpeg_layout* layout);
 /* the whole decode: out_host is height x width (1 component) or height x width x 3 BGR, rows out_pitch bytes apart,
  * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes */
 UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,

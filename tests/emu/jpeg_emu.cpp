@@ -12,20 +12,25 @@
 
 using namespace uvo::jpegk;
 
-extern "C" int emu_jpeg_decode(const int16_t* coef, const uvo_jpeg_layout* L, uint8_t* out, size_t out_pitch) {
-  if (!coef || !L || !out) return -1;
+extern "C" int emu_jpeg_decode(const uint32_t* entries, const uint32_t* first, const uint8_t* count,
+                               const uvo_jpeg_layout* L, uint8_t* out, size_t out_pitch) {
+  if (!entries || !first || !count || !L || !out) return -1;
   std::vector<uint8_t> planes(plane_bytes(*L), 0xAB);
   IdctArgs ia;
   ColorArgs ca;
-  fill_args(*L, coef, planes.data(), L->components == 3 ? out : nullptr, out_pitch, ia, ca);
+  fill_args(*L, entries, first, count, planes.data(), L->components == 3 ? out : nullptr, out_pitch, ia, ca);
   // k_jpeg_idct<<<div_up(total_blocks, IDCT_BLOCKS), IDCT_THREADS>>>
   const int grid = (ia.total_blocks + IDCT_BLOCKS - 1) / IDCT_BLOCKS;
   std::vector<int> ws(IDCT_BLOCKS * WS_STRIDE);
+  std::vector<int16_t> tile(IDCT_BLOCKS * TILE_STRIDE);
   for (int b = 0; b < grid; b++) {
     for (auto& v : ws) v = 0x5A5A5A5A;  // shared memory is not initialised
-    for (int warp = 0; warp < IDCT_THREADS / 32; warp++) {
-      for (int lane = 0; lane < 32; lane++) idct_pass1(ia, b, warp * 32 + lane, ws.data());
-      for (int lane = 0; lane < 32; lane++) idct_pass2(ia, b, warp * 32 + lane, ws.data());
+    for (auto& v : tile) v = 0x5A5A;
+    for (int warp = 0; warp < IDCT_THREADS / 32; warp++) {  // the stages are what the kernel separates by __syncwarp()
+      for (int lane = 0; lane < 32; lane++) idct_clear(ia, b, warp * 32 + lane, tile.data());
+      for (int lane = 31; lane >= 0; lane--) idct_scatter(ia, b, warp * 32 + lane, tile.data());
+      for (int lane = 0; lane < 32; lane++) idct_pass1(ia, b, warp * 32 + lane, tile.data(), ws.data());
+      for (int lane = 31; lane >= 0; lane--) idct_pass2(ia, b, warp * 32 + lane, ws.data());
     }
   }
   if (L->components == 1) {  // cudaMemcpy2D of the luminance plane

@@ -32,10 +32,13 @@ def emu(tmp_path_factory):
 
 def _decode(emu, data):
     import ergo_uvo_b200 as U
-    lay, coef = U.jpeg_entropy_decode(data)
+    lay, entries, first, count = U.jpeg_entropy_decode_sparse(data)
     ch = 1 if lay.components == 1 else 3
     out = np.full((lay.height, lay.width) if ch == 1 else (lay.height, lay.width, 3), 0xCD, np.uint8)
-    rc = emu.emu_jpeg_decode(coef.ctypes.data_as(C.c_void_p), C.byref(lay), out.ctypes.data_as(C.c_void_p),
+    if len(entries) == 0:
+        entries = np.zeros(1, np.uint32)
+    rc = emu.emu_jpeg_decode(entries.ctypes.data_as(C.c_void_p), first.ctypes.data_as(C.c_void_p),
+                             count.ctypes.data_as(C.c_void_p), C.byref(lay), out.ctypes.data_as(C.c_void_p),
                              C.c_size_t(lay.width * ch))
     assert rc == 0
     return out

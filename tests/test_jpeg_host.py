@@ -22,6 +22,15 @@ def _same(U, oracle, data):
     want = oracle.jpeg_coefficients(data)
     assert lay.coeff_total == len(want) == len(coef)
     assert np.array_equal(coef, want)
+    # the sparse form (what travels to the GPU) expands to the same planes: non-zero coefficients only, per block
+    _, entries, first, count = U.jpeg_entropy_decode_sparse(data)
+    assert len(entries) == int(np.count_nonzero(want)) == int(count.sum())
+    dense = np.zeros(len(want), np.int16)
+    blk = np.repeat(np.arange(len(count)), count)                       # owning block of every entry, block by block
+    idx = np.concatenate([np.arange(f, f + c) for f, c in zip(first, count)]) if len(entries) else np.zeros(0, int)
+    e = entries[idx.astype(np.int64)]
+    dense[blk * 64 + (e >> 16).astype(np.int64)] = (e & 0xFFFF).astype(np.uint16).view(np.int16)
+    assert np.array_equal(dense, want)
     return lay
 
 
