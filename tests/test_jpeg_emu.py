@@ -1,7 +1,8 @@
 """CPU: the thread bodies of the two JPEG kernels (ergo_uvo_b200/csrc/jpeg_kernels.cuh), executed on the host over the
 kernels' launch grid by the harness tests/emu/jpeg_emu.cpp, fed with the coefficients of the product's host-side Huffman
 decoder, against the oracle -- bit-exact.  This covers the index arithmetic, the integer IDCT / upsampling / colour
-pipeline and the __syncwarp() granularity of k_jpeg_idct; it is not a GPU run (tests/test_gpu_zz_jpeg.py is).
+pipeline (clear / scatter of the sparse coefficients, IDCT, upsampling, colour) and the __syncwarp() granularity of
+k_jpeg_idct; it is not a GPU run (tests/test_gpu_zz_jpeg.py is).
 Reference path: the cv::imdecode inside from_ros_to_cv_image, math_utility.cpp:154-173."""
 import ctypes as C
 import io
