@@ -467,64 +467,84 @@ int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* en
   });
 }
 
+// shared body of uvo_jpeg_decode (out on the host) and uvo_jpeg_decode_device (out in device memory, no copy back)
+static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out, size_t out_pitch,
+                             size_t out_capacity, bool out_on_device, int* width, int* height, int* channels) {
+  UVO_REQUIRE(jpeg && out && width && height && channels, "uvo_jpeg_decode: bad argument");
+  Ctx& c = ctx->c;
+  UVO_CUDA(cudaSetDevice(c.device));
+  Parser H;
+  H.run(jpeg, len, nullptr);
+  const size_t total = (size_t)H.L.coeff_total;
+  const int W = H.L.width, Hh = H.L.height, nc = H.L.components;
+  if (out_pitch < (size_t)W * nc || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * nc)
+    throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
+  // host: entropy decoding into pinned memory, as the sparse form (one 32-bit entry per non-zero coefficient + a
+  // (first, count) pair per block); one pinned buffer: [first: nb x u32][entries: <= total x u32][count: nb x u8]
+  UVO_CUDA(cudaStreamSynchronize(c.stream));  // the pinned buffer may still feed the previous call's copy
+  const size_t nb = total / 64;
+  ctx->jpeg_coef.ensure(nb + total + (nb + 3) / 4);
+  uint32_t* h_first = ctx->jpeg_coef.p;
+  uint32_t* h_entries = h_first + nb;
+  uint8_t* h_count = (uint8_t*)(h_entries + total);
+  memset(h_first, 0, sizeof(uint32_t) * nb);  // blocks no scan visits (padding of a non-interleaved scan) stay empty
+  memset(h_count, 0, nb);
+  Parser P;
+  P.run_sparse(jpeg, len, h_entries, total, h_first, h_count);
+  const uvo_jpeg_layout& L = P.L;
+  const size_t ne = P.sink.n;
+  // device: the same three arrays (only the used entries travel), component planes, output
+  StageScratch& s = ctx->scratch;
+  s.bytes_a.ensure(sizeof(uint32_t) * (nb + std::max<size_t>(ne, 1)) + nb);
+  uint32_t* d_first = (uint32_t*)s.bytes_a.get();
+  uint32_t* d_entries = d_first + nb;
+  uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(ne, 1));
+  s.bytes_b.ensure(jpegk::plane_bytes(L));
+  // the colour kernel writes straight into the caller's device buffer, or into a staging image that is copied back
+  size_t dpitch = out_pitch;
+  uint8_t* d_out = out;
+  if (!out_on_device && nc == 3) {
+    dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
+    s.bytes_c.ensure(dpitch * Hh);
+    d_out = s.bytes_c.get();
+  }
+  UVO_CUDA(cudaMemcpyAsync(d_first, h_first, sizeof(uint32_t) * (nb + ne), cudaMemcpyHostToDevice, c.stream));
+  UVO_CUDA(cudaMemcpyAsync(d_count, h_count, nb, cudaMemcpyHostToDevice, c.stream));
+  IdctArgs ia;
+  ColorArgs ca;
+  fill_args(L, d_entries, d_first, d_count, s.bytes_b.get(), nc == 3 ? d_out : nullptr, dpitch, ia, ca);
+  UVO_KERNEL(c, "k_jpeg_idct");
+  k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
+  UVO_LAUNCH_CHECK(c);
+  if (nc == 1) {  // the luminance plane is the image
+    UVO_CUDA(cudaMemcpy2DAsync(out, out_pitch, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh,
+                               out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+  } else {
+    UVO_KERNEL(c, "k_jpeg_color");
+    k_jpeg_color<<<dim3(div_up(W, COLOR_TX), div_up(Hh, COLOR_TY)), COLOR_TX * COLOR_TY, 0, c.stream>>>(ca);
+    UVO_LAUNCH_CHECK(c);
+    if (!out_on_device)
+      UVO_CUDA(cudaMemcpy2DAsync(out, out_pitch, d_out, dpitch, (size_t)3 * W, Hh, cudaMemcpyDeviceToHost, c.stream));
+  }
+  if (!out_on_device) UVO_CUDA(cudaStreamSynchronize(c.stream));  // device output: ordered on the context stream
+  *width = W;
+  *height = Hh;
+  *channels = nc;
+}
+
 int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
                     size_t out_capacity, int* width, int* height, int* channels) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
-    UVO_REQUIRE(jpeg && out_host && width && height && channels, "uvo_jpeg_decode: bad argument");
-    Ctx& c = ctx->c;
-    UVO_CUDA(cudaSetDevice(c.device));
-    Parser H;
-    H.run(jpeg, len, nullptr);
-    const size_t total = (size_t)H.L.coeff_total;
-    const int W = H.L.width, Hh = H.L.height, nc = H.L.components;
-    if (out_pitch < (size_t)W * nc || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * nc)
-      throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
-    // host: entropy decoding into pinned memory, as the sparse form (one 32-bit entry per non-zero coefficient + a
-    // (first, count) pair per block); one pinned buffer: [first: nb x u32][entries: <= total x u32][count: nb x u8]
-    UVO_CUDA(cudaStreamSynchronize(c.stream));  // the pinned buffer may still feed the previous call's copy
-    const size_t nb = total / 64;
-    ctx->jpeg_coef.ensure(nb + total + (nb + 3) / 4);
-    uint32_t* h_first = ctx->jpeg_coef.p;
-    uint32_t* h_entries = h_first + nb;
-    uint8_t* h_count = (uint8_t*)(h_entries + total);
-    memset(h_first, 0, sizeof(uint32_t) * nb);  // blocks no scan visits (padding of a non-interleaved scan) stay empty
-    memset(h_count, 0, nb);
-    Parser P;
-    P.run_sparse(jpeg, len, h_entries, total, h_first, h_count);
-    const uvo_jpeg_layout& L = P.L;
-    const size_t ne = P.sink.n;
-    // device: the same three arrays (only the used entries travel), component planes, output
-    StageScratch& s = ctx->scratch;
-    s.bytes_a.ensure(sizeof(uint32_t) * (nb + std::max<size_t>(ne, 1)) + nb);
-    uint32_t* d_first = (uint32_t*)s.bytes_a.get();
-    uint32_t* d_entries = d_first + nb;
-    uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(ne, 1));
-    s.bytes_b.ensure(jpegk::plane_bytes(L));
-    const size_t dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
-    if (nc == 3) s.bytes_c.ensure(dpitch * Hh);
-    UVO_CUDA(cudaMemcpyAsync(d_first, h_first, sizeof(uint32_t) * (nb + ne), cudaMemcpyHostToDevice, c.stream));
-    UVO_CUDA(cudaMemcpyAsync(d_count, h_count, nb, cudaMemcpyHostToDevice, c.stream));
-    IdctArgs ia;
-    ColorArgs ca;
-    fill_args(L, d_entries, d_first, d_count, s.bytes_b.get(), nc == 3 ? s.bytes_c.get() : nullptr, dpitch, ia, ca);
-    UVO_KERNEL(c, "k_jpeg_idct");
-    k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
-    UVO_LAUNCH_CHECK(c);
-    if (nc == 1) {  // the luminance plane is the image
-      UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh,
-                                 cudaMemcpyDeviceToHost, c.stream));
-    } else {
-      UVO_KERNEL(c, "k_jpeg_color");
-      k_jpeg_color<<<dim3(div_up(W, COLOR_TX), div_up(Hh, COLOR_TY)), COLOR_TX * COLOR_TY, 0, c.stream>>>(ca);
-      UVO_LAUNCH_CHECK(c);
-      UVO_CUDA(cudaMemcpy2DAsync(out_host, out_pitch, s.bytes_c.get(), dpitch, (size_t)3 * W, Hh,
-                                 cudaMemcpyDeviceToHost, c.stream));
-    }
-    UVO_CUDA(cudaStreamSynchronize(c.stream));
-    *width = W;
-    *height = Hh;
-    *channels = nc;
+    jpeg_decode_impl(ctx, jpeg, len, out_host, out_pitch, out_capacity, false, width, height, channels);
+  });
+}
+
+int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_dev, size_t out_pitch,
+                           size_t out_capacity, int* width, int* height, int* channels) {
+  if (!ctx) return UVO_ERR_INVALID;
+  return guarded(&ctx->c, [&] {
+    jpeg_decode_impl(ctx, jpeg, len, out_dev, out_pitch, out_capacity, true, width, height, channels);
   });
 }
 

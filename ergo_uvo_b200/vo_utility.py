@@ -223,6 +223,16 @@ class Context:
                                           C.c_size_t(out.nbytes), C.byref(w), C.byref(h), C.byref(c)))
         return out
 
+    def jpeg_decode_device(self, data, out_ptr, out_pitch, out_capacity):
+        """as jpeg_decode with the image left in device memory at out_ptr (ordered on the context stream);
+        returns (width, height, channels)"""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_jpeg_decode_device(self.h, _p(buf), C.c_size_t(len(buf)), C.c_void_p(out_ptr),
+                                                 C.c_size_t(out_pitch), C.c_size_t(out_capacity), C.byref(w),
+                                                 C.byref(h), C.byref(c)))
+        return w.value, h.value, c.value
+
     # ------------------------------------------------------------------ VO_utility.h:100
     def detect_features(self, img, capacity=None):
         """void detect_features(Mat img, vector<KeyPoint>&, Mat&) -> (keypoints, descriptors)."""

@@ -189,6 +189,10 @@ UVO_API int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint
  * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes */
 UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
                             size_t out_capacity, int* width, int* height, int* channels);
+/* the same with the image left in DEVICE memory (no copy back; the work is ordered on the context stream), ready for
+ * uvo_stereo_enqueue_device / uvo_mono_frame_device on the same context */
+UVO_API int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_dev, size_t out_pitch,
+                                   size_t out_capacity, int* width, int* height, int* channels);
 
 /* ---------------------------------------------------------------------------------------------------- K4-K7 */
 /* void detect_features(Mat img, vector<KeyPoint>&, Mat& descriptors) -- VO_utility.h:100, VO_utility.cpp:114-119:

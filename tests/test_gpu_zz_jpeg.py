@@ -64,3 +64,30 @@ def test_jpeg_decode_refusals(ctx):
     with pytest.raises(U.UvoError) as e:
         ctx.jpeg_decode(data.replace(b"\xff\xc0", b"\xff\xc2", 1))
     assert e.value.code == -5
+
+
+def test_jpeg_decode_device_feeds_the_stereo_handle(ctx, oracle, small_stereo):
+    """JPEG streams -> uvo_jpeg_decode_device -> uvo_stereo_frame_device on the same context: the record equals the one
+    of the host-image call on the decoded (oracle) images"""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    import ergo_uvo_b200 as U
+    seq = small_stereo
+    p = U.default_params(True)
+    p.surf_min_hessian = 3000
+    p.max_features = 16384
+    cams = (U.make_camera(seq.KL, seq.DL, seq.newKL), U.make_camera(seq.KR, seq.DR, seq.newKR))
+    enc = [[cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 92])[1].tobytes() for im in pair] for pair in seq.frames]
+    vo = U.StereoVO(ctx, seq.w, seq.h, *cams, seq.R_right, seq.t_right, p)
+    want = [vo.frame(oracle.jpeg_decode(l), oracle.jpeg_decode(r), 0.1) for l, r in enc]
+    vo.close()
+    vo = U.StereoVO(ctx, seq.w, seq.h, *cams, seq.R_right, seq.t_right, p)
+    dL = torch.empty((seq.h, seq.w, 3), dtype=torch.uint8, device="cuda")
+    dR = torch.empty_like(dL)
+    for (l, r), w in zip(enc, want):
+        assert ctx.jpeg_decode_device(l, dL.data_ptr(), 3 * seq.w, dL.numel()) == (seq.w, seq.h, 3)
+        assert ctx.jpeg_decode_device(r, dR.data_ptr(), 3 * seq.w, dR.numel()) == (seq.w, seq.h, 3)
+        got = vo.frame_device(dL.data_ptr(), dR.data_ptr(), 3 * seq.w, 0.1)
+        assert bytes(got) == bytes(w)
+    assert got.valid == 1
+    vo.close()
