@@ -468,8 +468,9 @@ int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* en
 }
 
 // shared body of uvo_jpeg_decode (out on the host) and uvo_jpeg_decode_device (out in device memory, no copy back)
-static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out, size_t out_pitch,
-                             size_t out_capacity, bool out_on_device, int* width, int* height, int* channels) {
+static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out,
+                             size_t out_pitch, size_t out_capacity, bool out_on_device, int* width, int* height,
+                             int* channels) {
   UVO_REQUIRE(jpeg && out && width && height && channels, "uvo_jpeg_decode: bad argument");
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
@@ -477,7 +478,12 @@ static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint
   H.run(jpeg, len, nullptr);
   const size_t total = (size_t)H.L.coeff_total;
   const int W = H.L.width, Hh = H.L.height, nc = H.L.components;
-  if (out_pitch < (size_t)W * nc || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * nc)
+  // a bayer-format message is a 1-component stream holding the BGGR mosaic: from_ros_to_cv_image runs
+  // cvtColor(COLOR_BayerBGGR2BGR) on the decoded image (math_utility.cpp:161-164)
+  const bool demosaic = bayer_bggr != 0 && nc == 1;
+  if (demosaic && (W < 3 || Hh < 3)) throw InvalidArg{"uvo_jpeg_decode: a bayer image needs w, h >= 3", UVO_ERR_INVALID};
+  const int och = (nc == 3 || demosaic) ? 3 : 1;  // channels of the output image
+  if (out_pitch < (size_t)W * och || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * och)
     throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
   // host: entropy decoding into pinned memory, as the sparse form (one 32-bit entry per non-zero coefficient + a
   // (first, count) pair per block); one pinned buffer: [first: nb x u32][entries: <= total x u32][count: nb x u8]
@@ -503,7 +509,7 @@ static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint
   // the colour kernel writes straight into the caller's device buffer, or into a staging image that is copied back
   size_t dpitch = out_pitch;
   uint8_t* d_out = out;
-  if (!out_on_device && nc == 3) {
+  if (!out_on_device && och == 3) {
     dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
     s.bytes_c.ensure(dpitch * Hh);
     d_out = s.bytes_c.get();
@@ -516,7 +522,11 @@ static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint
   UVO_KERNEL(c, "k_jpeg_idct");
   k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
   UVO_LAUNCH_CHECK(c);
-  if (nc == 1) {  // the luminance plane is the image
+  if (demosaic) {  // the luminance plane is the mosaic
+    launch_demosaic_bggr(c, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh, d_out, dpitch);
+    if (!out_on_device)
+      UVO_CUDA(cudaMemcpy2DAsync(out, out_pitch, d_out, dpitch, (size_t)3 * W, Hh, cudaMemcpyDeviceToHost, c.stream));
+  } else if (nc == 1) {  // the luminance plane is the image
     UVO_CUDA(cudaMemcpy2DAsync(out, out_pitch, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, W, Hh,
                                out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
   } else {
@@ -529,22 +539,22 @@ static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint
   if (!out_on_device) UVO_CUDA(cudaStreamSynchronize(c.stream));  // device output: ordered on the context stream
   *width = W;
   *height = Hh;
-  *channels = nc;
+  *channels = och;
 }
 
-int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
-                    size_t out_capacity, int* width, int* height, int* channels) {
+int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_host,
+                    size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
-    jpeg_decode_impl(ctx, jpeg, len, out_host, out_pitch, out_capacity, false, width, height, channels);
+    jpeg_decode_impl(ctx, jpeg, len, bayer_bggr, out_host, out_pitch, out_capacity, false, width, height, channels);
   });
 }
 
-int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_dev, size_t out_pitch,
-                           size_t out_capacity, int* width, int* height, int* channels) {
+int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,
+                           size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
-    jpeg_decode_impl(ctx, jpeg, len, out_dev, out_pitch, out_capacity, true, width, height, channels);
+    jpeg_decode_impl(ctx, jpeg, len, bayer_bggr, out_dev, out_pitch, out_capacity, true, width, height, channels);
   });
 }
 

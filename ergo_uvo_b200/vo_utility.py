@@ -212,23 +212,26 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ math_utility.h:27
-    def jpeg_decode(self, data):
-        """the cv::imdecode(IMREAD_UNCHANGED) inside from_ros_to_cv_image: h x w (1 component) or h x w x 3 BGR"""
+    def jpeg_decode(self, data, bayer=False):
+        """the cv::imdecode(IMREAD_UNCHANGED) inside from_ros_to_cv_image: h x w (1 component) or h x w x 3 BGR;
+        bayer=True: a 1-component stream is the BGGR mosaic and comes back demosaiced (math_utility.cpp:161-164)"""
         buf = np.frombuffer(bytes(data), np.uint8)
         lay = jpeg_info(data)
-        ch = 1 if lay.components == 1 else 3
+        ch = 1 if (lay.components == 1 and not bayer) else 3
         out = np.empty((lay.height, lay.width) if ch == 1 else (lay.height, lay.width, 3), np.uint8)
         w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
-        self._ck(self.lib.uvo_jpeg_decode(self.h, _p(buf), C.c_size_t(len(buf)), _p(out), C.c_size_t(lay.width * ch),
+        self._ck(self.lib.uvo_jpeg_decode(self.h, _p(buf), C.c_size_t(len(buf)), int(bool(bayer)), _p(out),
+                                          C.c_size_t(lay.width * ch),
                                           C.c_size_t(out.nbytes), C.byref(w), C.byref(h), C.byref(c)))
         return out
 
-    def jpeg_decode_device(self, data, out_ptr, out_pitch, out_capacity):
+    def jpeg_decode_device(self, data, out_ptr, out_pitch, out_capacity, bayer=False):
         """as jpeg_decode with the image left in device memory at out_ptr (ordered on the context stream);
         returns (width, height, channels)"""
         buf = np.frombuffer(bytes(data), np.uint8)
         w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
-        self._ck(self.lib.uvo_jpeg_decode_device(self.h, _p(buf), C.c_size_t(len(buf)), C.c_void_p(out_ptr),
+        self._ck(self.lib.uvo_jpeg_decode_device(self.h, _p(buf), C.c_size_t(len(buf)), int(bool(bayer)),
+                                                 C.c_void_p(out_ptr),
                                                  C.c_size_t(out_pitch), C.c_size_t(out_capacity), C.byref(w),
                                                  C.byref(h), C.byref(c)))
         return w.value, h.value, c.value

@@ -186,13 +186,15 @@ UVO_API int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint
                                            uint32_t* block_first_host, uint8_t* block_count_host, size_t* n_entries,
                                            uvo_jpeg_layout* layout);
 /* the whole decode: out_host is height x width (1 component) or height x width x 3 BGR, rows out_pitch bytes apart,
- * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes */
-UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_host, size_t out_pitch,
-                            size_t out_capacity, int* width, int* height, int* channels);
+ * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes.  bayer_bggr != 0 mirrors
+ * `image->format.find("bayer") != npos` (math_utility.cpp:161-164): a 1-component stream is taken as the BGGR mosaic
+ * and cvtColor(COLOR_BayerBGGR2BGR) is applied on the GPU, the output is height x width x 3 (ignored for 3 components) */
+UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_host,
+                            size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels);
 /* the same with the image left in DEVICE memory (no copy back; the work is ordered on the context stream), ready for
  * uvo_stereo_enqueue_device / uvo_mono_frame_device on the same context */
-UVO_API int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, uint8_t* out_dev, size_t out_pitch,
-                                   size_t out_capacity, int* width, int* height, int* channels);
+UVO_API int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,
+                                   size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels);
 
 /* ---------------------------------------------------------------------------------------------------- K4-K7 */
 /* void detect_features(Mat img, vector<KeyPoint>&, Mat& descriptors) -- VO_utility.h:100, VO_utility.cpp:114-119:

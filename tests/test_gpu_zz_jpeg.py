@@ -91,3 +91,18 @@ def test_jpeg_decode_device_feeds_the_stereo_handle(ctx, oracle, small_stereo):
         assert bytes(got) == bytes(w)
     assert got.valid == 1
     vo.close()
+
+
+def test_jpeg_decode_bayer_message(ctx, oracle):
+    """a bayer-format compressed message: 1-component JPEG of the BGGR mosaic, decoded and demosaiced on the GPU --
+    from_ros_to_cv_image's imdecode + cvtColor(COLOR_BayerBGGR2BGR) (math_utility.cpp:158-164)"""
+    cv2 = pytest.importorskip("cv2")
+    for h, w in [(3, 3), (48, 64), (243, 317), (512, 640)]:
+        mosaic = noise_image(h, w, seed=h + w)
+        ok, enc = cv2.imencode(".jpg", mosaic, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        want = oracle.bayer_bggr2bgr(oracle.jpeg_decode(enc.tobytes()))
+        got = ctx.jpeg_decode(enc.tobytes(), bayer=True)
+        assert got.shape == (h, w, 3) and np.array_equal(got, want), (h, w)
+        assert np.array_equal(want, cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_UNCHANGED), cv2.COLOR_BayerBGGR2BGR))
+        # without the flag the mosaic comes back as it is
+        assert np.array_equal(ctx.jpeg_decode(enc.tobytes()), oracle.jpeg_decode(enc.tobytes()))
