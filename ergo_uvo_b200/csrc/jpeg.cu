@@ -51,6 +51,12 @@ struct HuffTab {
     }
   }
   void build(const uint8_t counts[16], const uint8_t* vals, int nv) {
+    // the counts must describe a prefix code: at most 2^l codes of length l once the shorter ones are taken out
+    for (int l = 1, code = 0; l <= 16; l++) {
+      code += counts[l - 1];
+      if (code > (1 << l)) throw InvalidArg{"jpeg: bad DHT (not a prefix code)", UVO_ERR_INVALID};
+      code <<= 1;
+    }
     memcpy(huffval, vals, nv);
     memset(fast, 0, sizeof(fast));
     int code = 0, k = 0;
@@ -253,6 +259,7 @@ struct Parser {
   }
 
   void sof(const uint8_t* s, size_t n) {
+    if (have_sof) throw InvalidArg{"jpeg: more than one frame header", UVO_ERR_INVALID};  // buffers follow the first
     if (n < 6) throw InvalidArg{"jpeg: bad SOF", UVO_ERR_INVALID};
     if (s[0] != 8) throw InvalidArg{"jpeg: only 8-bit samples are supported", UVO_ERR_UNSUPPORTED};
     L.height = (s[1] << 8) | s[2];

@@ -90,3 +90,17 @@ def test_entropy_decode_refusals():
     assert e.value.code == -5
     with pytest.raises(U.UvoError):
         U.jpeg_info(data[:100])  # cut inside the tables: no frame header
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_parser_survives_mutated_streams():
+    """the streams come off the network (ROS CompressedImage): byte edits, truncations and insertions must end in a
+    status code, never in a crash or an out-of-bounds table (tools/jpeg_fuzz.py runs the long version, also under
+    AddressSanitizer)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "jpeg_fuzz.py"), "7", "2500"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    assert "('sparse', 0)" in r.stdout and "('info', -3)" in r.stdout  # both outcomes occurred
