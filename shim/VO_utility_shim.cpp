@@ -248,6 +248,28 @@ bool solvePnPRansac(const Mat& X /* Nx3 CV_64F */, const vector<Point2f>& x, con
 }
 }  // namespace uvo_shim
 
+#ifdef UVO_SHIM_GPU_IMAGE_DECODE
+// math_utility.cpp:154-173 -- optional (take the definition out of math_utility.cpp when enabling this one): the
+// cv::imdecode that cv_bridge::toCvCopy performs on a compressed message, and the demosaic of bayer-format messages, on
+// the GPU.  Baseline JPEG only; for anything else (PNG, progressive JPEG) uvo_jpeg_info fails and the caller gets the
+// reference's own error behaviour: a ROS_ERROR line and an empty image.  toCvCopy's channel-order conversions for
+// encodings other than bgr8 / mono8 / bayer are not reproduced.
+Mat from_ros_to_cv_image(const sensor_msgs::CompressedImage::ConstPtr& image) {
+  const bool bayer = image->format.find("bayer") != std::string::npos;
+  uvo_jpeg_layout lay;
+  if (uvo_jpeg_info(image->data.data(), image->data.size(), &lay) != UVO_OK) {
+    ROS_ERROR("cv_bridge exception: %s", "uvo_b200: not a baseline JPEG stream");
+    return Mat();
+  }
+  const bool three = lay.components == 3 || bayer;
+  Mat out(lay.height, lay.width, three ? CV_8UC3 : CV_8UC1);
+  int w = 0, h = 0, c = 0;
+  check(uvo_jpeg_decode(ctx(), image->data.data(), image->data.size(), bayer ? 1 : 0, out.data, out.step,
+                        (size_t)out.step * out.rows, &w, &h, &c));
+  return out;
+}
+#endif
+
 // compute_projection_matrix, convert_from_homogeneous_coords, extract_inliers, reproject_errors,
 // select_desired_*, the parameter loaders and show_matches carry no hot arithmetic and are
 // compiled unchanged from the reference's VO_utility.cpp.

@@ -23,9 +23,10 @@ def _check(src, extra=()):
 
 
 @needs_ref
-@pytest.mark.parametrize("src", ["VO_utility_shim.cpp", "cv_interpose.cpp"])
-def test_shim_type_checks_against_reference_header(src):
-    r = _check(os.path.join(ROOT, "shim", src))
+@pytest.mark.parametrize("src,extra", [("VO_utility_shim.cpp", ()), ("VO_utility_shim.cpp", ("-DUVO_SHIM_GPU_IMAGE_DECODE",)),
+                                       ("cv_interpose.cpp", ())])
+def test_shim_type_checks_against_reference_header(src, extra):
+    r = _check(os.path.join(ROOT, "shim", src), extra=extra)
     assert r.returncode == 0, r.stderr[-4000:]
 
 
