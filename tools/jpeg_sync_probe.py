@@ -96,6 +96,57 @@ def run(bits, dc, ac, comps, start, true_states, max_symbols):
     return seen if true_states is None else None
 
 
+def advance(bits, dc, ac, comps, state, stop_at):
+    """decode from `state` = (bit position, block of the MCU, k) to the first symbol start at or after `stop_at`"""
+    blocks = [c for c in comps for _ in range(c[0] * c[1])]
+    pos, b, k = state
+    nbits = len(bits)
+    while pos < stop_at and pos < nbits:
+        table = (dc if k == 0 else ac)[blocks[b][2 if k == 0 else 3]]
+        code, ln, sym = 0, 0, None
+        while ln < 16 and pos < nbits:
+            code = (code << 1) | int(bits[pos])
+            pos += 1
+            ln += 1
+            sym = table.get((ln, code))
+            if sym is not None:
+                break
+        if sym is None:
+            sym = 0
+        if k == 0:
+            pos += sym & 15
+            k = 1
+        else:
+            r, s = sym >> 4, sym & 15
+            pos += s
+            k = 64 if (s == 0 and r != 15) else k + (16 if s == 0 else r + 1)
+        if k >= 64:
+            k = 0
+            b = (b + 1) % len(blocks)
+    return (pos, b, k)
+
+
+def parallel_rounds(bits, dc, ac, comps, S):
+    """the parallel scheme itself, run sequentially: sub-sequences of S bits, one decoder each.  Decoder i holds a
+    candidate state for boundary i (the true one for i = 0, a guess -- block 0, k = 0 at bit i * S -- otherwise) and
+    computes the state it implies at boundary i + 1; a round replaces every candidate by its left neighbour's
+    implication.  Returns (rounds until nothing changes, whether the fixed point is the sequential decode)."""
+    n = (len(bits) + S - 1) // S
+    cand = [(i * S, 0, 0) for i in range(n)]
+    truth = [(0, 0, 0)]
+    for i in range(1, n):
+        truth.append(advance(bits, dc, ac, comps, truth[-1], i * S))
+    rounds = 0
+    while True:
+        implied = [advance(bits, dc, ac, comps, cand[i], (i + 1) * S) for i in range(n - 1)]
+        new = [cand[0]] + implied
+        rounds += 1
+        if new == cand:
+            break
+        cand = new
+    return rounds, cand == truth, n
+
+
 def main():
     import cv2
     from tools import synth
@@ -103,6 +154,8 @@ def main():
     ap.add_argument("--quality", type=int, default=75)
     ap.add_argument("--starts", type=int, default=400)
     ap.add_argument("--size", type=int, nargs=2, default=(640, 512))
+    ap.add_argument("--subsequence", type=int, nargs="*", default=[1024, 4096],
+                    help="also run the parallel scheme with sub-sequences of this many bits")
     a = ap.parse_args()
     seq = synth.StereoSequence(a.size[0], a.size[1], n_frames=1, tex_size=1024)
     ok, enc = cv2.imencode(".jpg", seq.frames[0][0], [cv2.IMWRITE_JPEG_QUALITY, a.quality])
@@ -119,9 +172,14 @@ def main():
             syms.append(r[1])
     d, n = np.array(dist), np.array(syms)
     pct = lambda v, q: float(np.percentile(v, q)) if len(v) else None
+    par = {}
+    for S in a.subsequence:
+        rounds, ok, ndec = parallel_rounds(bits, dc, ac, comps, S)
+        par[str(S)] = {"decoders": ndec, "rounds_to_fixed_point": rounds, "equals_sequential_decode": ok}
     print(json.dumps({"image": f"{a.size[0]}x{a.size[1]} synthetic frame, q{a.quality}, 4:2:0 interleaved",
                       "scan_bits": int(len(bits)), "starts": a.starts, "not_locked_within_3000_symbols": lost,
                       "lock_in_bits": {"median": pct(d, 50), "p90": pct(d, 90), "p99": pct(d, 99), "max": pct(d, 100)},
+                      "parallel_scheme": par,
                       "lock_in_symbols": {"median": pct(n, 50), "p90": pct(n, 90), "p99": pct(n, 99), "max": pct(n, 100)}}))
 
 
