@@ -148,3 +148,21 @@ def test_integration_doc_names_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert len(syms) > 40
     assert [s for s in syms if s not in doc] == []
+
+
+def test_cpp_example_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/stereo_sequence.cpp: a C++ consumer of the C ABI (no ROS, no OpenCV) builds against include/uvo_c.h and
+    the in-tree library; without arguments it prints its usage, and on a machine without a GPU it stops at
+    uvo_ctx_create instead of computing anything on the CPU"""
+    import torch
+    exe = str(tmp_path / "stereo_sequence")
+    lib_dir = os.path.join(ROOT, "ergo_uvo_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "stereo_sequence.cpp"), "-L" + lib_dir, "-luvo_b200",
+                           "-Wl,-rpath," + lib_dir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage:" in r.stderr and "sm_100a" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "640", "512", "0.1", "/nonexistent/l%04d", "/nonexistent/r%04d", "0", "2"],
+                           capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
