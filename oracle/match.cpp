@@ -9,12 +9,32 @@
 #include "uvo_oracle.h"
 
 #include <cmath>
+#if defined(__SSE2__)
+#include <immintrin.h>
+#endif
 #include <limits>
 #include <thread>
 #include <vector>
 
 static inline float norm_l2_sqr(const float* a, const float* b, int n) {
   int j = 0;
+  float s[4];
+#if defined(__SSE2__)
+  // the same operations in the same order as the scalar branch below, four lanes at a time (this IS the baseline
+  // SSE build of normL2Sqr_; separate multiply and add, no FMA): bit-identical, about twice as fast
+  __m128 acc0 = _mm_setzero_ps(), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+  for (; j <= n - 16; j += 16) {
+    __m128 t0 = _mm_sub_ps(_mm_loadu_ps(a + j), _mm_loadu_ps(b + j));
+    __m128 t1 = _mm_sub_ps(_mm_loadu_ps(a + j + 4), _mm_loadu_ps(b + j + 4));
+    __m128 t2 = _mm_sub_ps(_mm_loadu_ps(a + j + 8), _mm_loadu_ps(b + j + 8));
+    __m128 t3 = _mm_sub_ps(_mm_loadu_ps(a + j + 12), _mm_loadu_ps(b + j + 12));
+    acc0 = _mm_add_ps(acc0, _mm_mul_ps(t0, t0));
+    acc1 = _mm_add_ps(acc1, _mm_mul_ps(t1, t1));
+    acc2 = _mm_add_ps(acc2, _mm_mul_ps(t2, t2));
+    acc3 = _mm_add_ps(acc3, _mm_mul_ps(t3, t3));
+  }
+  _mm_storeu_ps(s, _mm_add_ps(_mm_add_ps(_mm_add_ps(acc0, acc1), acc2), acc3));
+#else
   float acc[4][4] = {};
   for (; j <= n - 16; j += 16)
     for (int k = 0; k < 4; k++)
@@ -22,8 +42,8 @@ static inline float norm_l2_sqr(const float* a, const float* b, int n) {
         float t = a[j + 4 * k + l] - b[j + 4 * k + l];
         acc[k][l] = acc[k][l] + t * t;
       }
-  float s[4];
   for (int l = 0; l < 4; l++) s[l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l];
+#endif
   float d = (s[0] + s[2]) + (s[1] + s[3]);
   for (; j < n; j++) {
     float t = a[j] - b[j];
