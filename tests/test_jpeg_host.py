@@ -104,3 +104,21 @@ def test_parser_survives_mutated_streams():
                        text=True)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     assert "('sparse', 0)" in r.stdout and "('info', -3)" in r.stdout  # both outcomes occurred
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_parallel_subsequence_scheme_reaches_the_sequential_decode():
+    """design check for a GPU entropy stage: decoders started at arbitrary bit offsets lock onto the true
+    decode, and the round-based sub-sequence scheme has the sequential decode as its fixed point"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "jpeg_sync_probe.py"), "--size", "320", "256",
+                        "--starts", "40", "--subsequence", "1024", "4096"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["not_locked_within_3000_symbols"] == 0 and d["lock_in_bits"]["max"] < 20000
+    for S in ("1024", "4096"):
+        assert d["parallel_scheme"][S]["equals_sequential_decode"] is True
+        assert d["parallel_scheme"][S]["rounds_to_fixed_point"] <= 16
