@@ -358,13 +358,16 @@ struct HostGate {  // optional stereo gate of uvo_match_features_gated
 
 static void match_host(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n2, int dim, float ratio,
                        uvo_dmatch* matches, int* count, uvo_dmatch* knn_out, const HostGate* gate = nullptr) {
+  if (count) *count = 0;
+  UVO_REQUIRE(n1 >= 0 && n2 >= 0, "matcher: bad argument");
+  // an empty query set is routine (the frame after a failed gate; knnMatch returns no rows): no match, whatever the
+  // row length of the empty matrix says
+  if (n1 == 0) return;
   if (dim != 64 && dim != 128)
     throw InvalidArg{"matcher: descriptor rows must be 64 (SURF) or 128 (extended SURF) floats", UVO_ERR_UNSUPPORTED};
-  UVO_REQUIRE(n1 >= 0 && n2 >= 0 && (n1 == 0 || d1) && (n2 == 0 || d2), "matcher: bad argument");
+  UVO_REQUIRE(d1 && (n2 == 0 || d2), "matcher: bad argument");
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
-  if (count) *count = 0;
-  if (n1 == 0) return;
   StageScratch& s = ctx->scratch;
   s.bytes_a.ensure(sizeof(float) * dim * (size_t)n1);
   s.bytes_b.ensure(sizeof(float) * dim * (size_t)std::max(n2, 1));
@@ -426,7 +429,7 @@ int uvo_match_features(uvo_ctx* ctx, const float* d1, int n1, const float* d2, i
                        uvo_dmatch* matches, int* count) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
-    UVO_REQUIRE(matches && count, "uvo_match_features: null output");
+    UVO_REQUIRE(count && (n1 <= 0 || matches), "uvo_match_features: null output");
     match_host(ctx, d1, n1, d2, n2, dim, ratio, matches, count, nullptr);
   });
 }
@@ -436,7 +439,7 @@ int uvo_match_features_gated(uvo_ctx* ctx, const uvo_keypoint* k1, const float* 
                              float max_disp, uvo_dmatch* matches, int* count) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
-    UVO_REQUIRE(matches && count, "uvo_match_features_gated: null output");
+    UVO_REQUIRE(count && (n1 <= 0 || matches), "uvo_match_features_gated: null output");
     UVO_REQUIRE((n1 == 0 || k1) && (n2 == 0 || k2), "uvo_match_features_gated: null keypoints");
     const HostGate g{k1, k2, max_dy, min_disp, max_disp};
     match_host(ctx, d1, n1, d2, n2, dim, ratio, matches, count, nullptr, &g);
@@ -454,6 +457,14 @@ int uvo_knn_match2(uvo_ctx* ctx, const float* d1, int n1, const float* d2, int n
 int uvo_match_last_fallbacks(uvo_ctx* ctx, int* count) {
   if (!ctx || !count) return UVO_ERR_INVALID;
   *count = ctx->last_match_fallbacks;
+  return UVO_OK;
+}
+
+int uvo_pnp_profile(uvo_ctx* ctx, int enable, int64_t stamps[32]) {
+  if (!ctx) return UVO_ERR_INVALID;
+  ctx->pnp_profile = enable != 0;
+  if (stamps)
+    for (int i = 0; i < 32; i++) stamps[i] = (int64_t)ctx->pnp_stamps[i];
   return UVO_OK;
 }
 
@@ -821,7 +832,7 @@ int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X, const float* x, int n, c
     Ctx& c = ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
     const int iters = std::max(iterations, 1);
-    ctx->scratch.bytes_a.ensure((size_t)n * 64 + (size_t)iters * 160 + 8192);
+    ctx->scratch.bytes_a.ensure((size_t)n * 48 + pnp_scratch_bytes(n, iters) + 16384);
     Arena ar{ctx->scratch.bytes_a.get(), 0, ctx->scratch.bytes_a.n};
     PnpArgs a{};
     double* dX = ar.take<double>(3 * (size_t)n);
@@ -838,15 +849,16 @@ int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X, const float* x, int n, c
     a.inliers = ar.take<int32_t>(n);
     a.n_inliers = ar.take<int>(1);
     a.hyps = ar.take<int>(1);
-    a.subsets = ar.take<int32_t>((size_t)iters * 5);
-    a.hyp_model = ar.take<double>((size_t)iters * 15);
-    a.hyp_good = ar.take<int>(iters);
-    a.xs = ar.take<float>(2 * (size_t)n);
-    a.Xf = ar.take<float>(3 * (size_t)n);
-    a.best = ar.take<int>(2);
+    pnp_bind_scratch(a, ar.take<uint8_t>(pnp_scratch_bytes(n, iters)), n, iters);
     UVO_CUDA(cudaMemcpyAsync(dX, X, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c.stream));
     UVO_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c.stream));
+    if (ctx->pnp_profile) {
+      a.prof = ar.take<long long>(32);
+      UVO_CUDA(cudaMemsetAsync(a.prof, 0, sizeof(long long) * 32, c.stream));
+    }
     launch_pnp_ransac(c, a);
+    if (a.prof)
+      UVO_CUDA(cudaMemcpyAsync(ctx->pnp_stamps, a.prof, sizeof(long long) * 32, cudaMemcpyDeviceToHost, c.stream));
     double res[8];
     int cnt[2];
     UVO_CUDA(cudaMemcpyAsync(res, a.result, sizeof(double) * 7, cudaMemcpyDeviceToHost, c.stream));

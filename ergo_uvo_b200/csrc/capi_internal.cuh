@@ -24,4 +24,6 @@ struct uvo_ctx {
   int last_match_fallbacks = 0;  // queries of the last matcher call that took the exact full-scan path
   uvo::PinnedBuf<uint32_t> jpeg_coef;  // uvo_jpeg_decode: sparse quantised coefficients, host side of the H2D copy
   int match_exact_only = 0;      // diagnostics (uvo_match_exact_only): stage-level matcher calls skip the tcgen05 pass
+  int pnp_profile = 0;           // diagnostics (uvo_pnp_profile): uvo_solve_pnp_ransac records clock64 phase stamps
+  long long pnp_stamps[32] = {};
 };

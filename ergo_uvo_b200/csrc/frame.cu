@@ -477,21 +477,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   pa.inliers = L.inliers.get();
   pa.n_inliers = L.small.get();
   pa.hyps = L.small.get() + 1;
-  pa.best = L.small.get() + 2;
-  {
-    const int iters = std::max(p.iterations_count, 1);
-    uint8_t* b = L.pnp_scratch.get();
-    auto take = [&](size_t bytes) {
-      uint8_t* r = b;
-      b += (bytes + 255) & ~(size_t)255;
-      return r;
-    };
-    pa.subsets = (int32_t*)take(sizeof(int32_t) * 5 * iters);
-    pa.hyp_model = (double*)take(sizeof(double) * 15 * iters);
-    pa.hyp_good = (int*)take(sizeof(int) * iters);
-    pa.xs = (float*)take(sizeof(float) * 2 * cap);
-    pa.Xf = (float*)take(sizeof(float) * 3 * cap);
-  }
+  pnp_bind_scratch(pa, L.pnp_scratch.get(), cap, p.iterations_count);
   launch_pnp_ransac(c, pa);
   mark(7);
   // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host

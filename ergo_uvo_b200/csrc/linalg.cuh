@@ -140,79 +140,189 @@ __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, doubl
   }
 }
 
-// Eigen-decomposition of a symmetric N x N matrix by the cyclic two-sided Jacobi method: A = Vt^T diag(w) Vt, w
-// descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional null space (5-point
-// minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30 sweeps; with the
-// absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet another basis of
-// that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels and the CPU oracle
-// run this same sequence of IEEE operations (no FMA, sqrt and divide correctly rounded on both).
-// (the one-thread form of this routine is oracle/linalg.h: jacobi_eigh)
-
-// jacobi_eigh spread over a group of GL >= N lanes of one warp (`gl` = lane index inside the group, `gmask` = the
-// group's lane mask; every lane of the group calls with the same arguments).  S (N x N, holds A on entry, destroyed)
-// and Vr / Vt (N x N each) live in shared memory.  The two-sided rotation has no reductions: every element update is
-// an independent expression, so handing element k to lane k leaves each IEEE operation -- and therefore every output
-// bit -- exactly as in the one-thread version (and the CPU oracle), while a rotation costs ~40 instructions of latency
-// instead of ~300.
+// Eigen-decomposition of a symmetric N x N matrix (N even) by the two-sided Jacobi method in round-robin order:
+// A = Vt^T diag(w) Vt, w descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional
+// null space (5-point minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30
+// sweeps; with the absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet
+// another basis of that null space, so no choice is bit-comparable with OpenCV; this routine and the
+// CPU oracle (oracle/linalg.h: jacobi_eigh, which documents the order) run the same sequence of IEEE operations (no
+// FMA, sqrt and divide correctly rounded on both) and agree bit for bit.
+//
+// A sweep is N-1 rounds of N/2 index-disjoint rotations whose angles are all taken from the matrix at the start of the
+// round: lanes p < partner(p) compute the N/2 rotations side by side (the dependent chain of a round is ONE rotation's
+// two square roots and reciprocal, not N/2 of them -- the cyclic order this replaces paid 66 chains per sweep, this
+// pays 11), then every thread evaluates its share of the N(N+1)/2 upper-triangle elements of J^T S J and of the N^2
+// elements of J^T Vr.
 template <int N>
-__device__ void jacobi_eigh_group(double* S, double* Vr, double* w, double* Vt, int gl, unsigned gmask) {
-  if (gl < N)
-    for (int k = 0; k < N; k++) Vr[gl * N + k] = (k == gl) ? 1.0 : 0.0;
+__device__ __forceinline__ int rr_partner(int x, int r) {
+  if (x == N - 1) return r;
+  if (x == r) return N - 1;
+  int v = 2 * r - x;
+  v += (v < 0) ? (N - 1) : 0;
+  v -= (v >= N - 1) ? (N - 1) : 0;
+  return v;
+}
+
+// partners of index x over the N-1 rounds of a sweep, 4 bits per round (N <= 16)
+template <int N>
+__device__ __forceinline__ unsigned long long rr_partners_packed(int x) {
+  unsigned long long v = 0;
+  for (int r = 0; r < N - 1; r++) v |= (unsigned long long)rr_partner<N>(x, r) << (4 * r);
+  return v;
+}
+
+// NT = 32: one warp per matrix (tid = lane, __syncwarp); NT = a whole block of 64 / 128 / 256 threads per matrix
+// (tid = threadIdx.x, __syncthreads): the element updates of a round then spread over every warp of the block, which
+// matters because a single warp runs this code at one dependent instruction per ~8 cycles.  The result does not
+// depend on NT.  Shared memory: S and Vr hold TWO N x N buffers each (the round reads one and writes the other; A
+// arrives in the first buffer of S), rot 2 N doubles, rflag 2 words.
+template <int N, int NT>
+__device__ void jacobi_eigh_rr(double* S, double* Vr, double* w, double* Vt, double* rot, unsigned* rflag, int tid,
+                               long long* prof = nullptr) {
+  static_assert(N % 2 == 0 && N <= 16, "round-robin order: even dimension, partners packed 4 bits per round");
+  constexpr int NV = N * N;
+  constexpr int NE = N * (N + 1) / 2;          // upper triangle incl. diagonal
+  constexpr int EPT = (NE + NT - 1) / NT;      // elements of S per thread
+  constexpr int VPT = (NV + NT - 1) / NT;      // elements of Vr per thread
+  auto sync = [] {
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+  };
+  long long t_rot = 0, t_apply = 0, t0 = 0, n_rounds = 0;
+  double* cc = rot;
+  double* ss = rot + N;
+  double* Sc = S;
+  double* Sn = S + NV;
+  double* Vc = Vr;
+  double* Vn = Vr + NV;
+  int ei[EPT], ej[EPT];
+  unsigned long long pi[EPT], pj[EPT];
+#pragma unroll
+  for (int m = 0; m < EPT; m++) {
+    // elements 0 .. NE-N-1: the strict upper triangle, row-major; the last N: the diagonal (kept together so that the
+    // three formulas below diverge in one warp only)
+    int e = tid + NT * m, i = -1, j = -1;
+    if (e < NE - N) {
+      i = 0;
+      while (e >= N - 1 - i) {
+        e -= N - 1 - i;
+        i++;
+      }
+      j = i + 1 + e;
+    } else if (e < NE) {
+      i = j = e - (NE - N);
+    }
+    ei[m] = i;
+    ej[m] = j;
+    pi[m] = i < 0 ? 0ull : rr_partners_packed<N>(i);
+    pj[m] = i < 0 ? 0ull : rr_partners_packed<N>(j);
+  }
+  unsigned long long pv[VPT];
+#pragma unroll
+  for (int m = 0; m < VPT; m++) {
+    const int v = (NT - 1 - tid) + NT * m;
+    pv[m] = v < NV ? rr_partners_packed<N>(v / N) : 0ull;
+  }
+  const unsigned long long prot = tid < N ? rr_partners_packed<N>(tid) : 0ull;
+  for (int v = tid; v < NV; v += NT) Vc[v] = (v / N == v % N) ? 1.0 : 0.0;
   double tr = 0;
-  for (int i = 0; i < N; i++) tr += fabs(S[i * N + i]);
+  for (int i = 0; i < N; i++) tr += fabs(Sc[i * N + i]);
   const double thr = tr * DBL_EPSILON;
-  __syncwarp(gmask);
+  sync();
   for (int sweep = 0; sweep < 30; sweep++) {
     bool changed = false;
-    for (int p = 0; p < N - 1; p++)
-      for (int q = p + 1; q < N; q++) {
-        const double apq = S[p * N + q];
-        if (fabs(apq) <= thr) continue;  // group-uniform
-        const double app = S[p * N + p], aqq = S[q * N + q];
-        // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), c = 1 / sqrt(t^2 + 1), s = t c with theta = d / x, written
-        // so that only two square roots and one reciprocal are on the dependent chain
-        const double d = aqq - app, x = 2 * apq;
-        const double rr = sqrt(d * d + x * x);
-        const double u = fabs(d) + rr, xs = d >= 0 ? x : -x;
-        const double ih = 1 / sqrt(x * x + u * u);
-        const double t = xs / u, c = u * ih, s = xs * ih;
-        double skp = 0, skq = 0, vp = 0, vq = 0;
-        const int k = gl;
-        if (k < N) {
-          skp = S[k * N + p];
-          skq = S[k * N + q];
-          vp = Vr[p * N + k];
-          vq = Vr[q * N + k];
+    for (int r = 0; r < N - 1; r++) {
+      if (prof) t0 = clock64();
+      if (tid < 32) {
+        bool rt = false;
+        const int p = tid, q = (int)(prot >> (4 * r)) & 15;
+        if (tid < N && p < q) {
+          // c = u / h, s = sgn(d) x / h with d = aqq - app, x = 2 apq, u = |d| + sqrt(d^2 + x^2), h^2 = x^2 + u^2:
+          // two square roots and one reciprocal on the dependent chain.  Evaluated unconditionally (apq = 0 gives
+          // h = u = 2 |d| or, for d = 0 too, 0 / 0, which the select below discards) so that the code has no branch.
+          const double apq = Sc[p * N + q], app = Sc[p * N + p], aqq = Sc[q * N + q];
+          rt = fabs(apq) > thr;
+          const double d = aqq - app, x = 2 * apq;
+          const double rr = sqrt(d * d + x * x);
+          const double u = fabs(d) + rr, xs = d >= 0 ? x : -x;
+          const double ih = 1 / sqrt(x * x + u * u);
+          const double c = rt ? u * ih : 1.0, s = rt ? xs * ih : 0.0;
+          cc[p] = cc[q] = c;
+          ss[p] = ss[q] = s;
         }
-        __syncwarp(gmask);  // every lane has read this rotation's inputs
-        if (k < N) {
-          if (k != p && k != q) {
-            const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
-            S[k * N + p] = np_;
-            S[p * N + k] = np_;
-            S[k * N + q] = nq_;
-            S[q * N + k] = nq_;
-          }
-          Vr[p * N + k] = c * vp - s * vq;
-          Vr[q * N + k] = s * vp + c * vq;
-        }
-        if (gl == 0) {
-          S[p * N + p] = app - t * apq;
-          S[q * N + q] = aqq + t * apq;
-          S[p * N + q] = 0;
-          S[q * N + p] = 0;
-        }
-        __syncwarp(gmask);
-        changed = true;
+        const unsigned m = __ballot_sync(0xffffffffu, rt);  // bit p: the pair whose smaller index is p rotates
+        if (tid == 0) rflag[r & 1] = m;
       }
+      sync();
+      const unsigned rmask = rflag[r & 1];
+      if (!rmask) continue;  // uniform over the NT threads
+      changed = true;
+      if (prof) {
+        const long long t1 = clock64();
+        t_rot += t1 - t0;
+        t0 = t1;
+        n_rounds++;
+      }
+#pragma unroll
+      for (int m = 0; m < EPT; m++) {
+        const int i = ei[m], j = ej[m];
+        if (i < 0) continue;
+        const int i2 = (int)(pi[m] >> (4 * r)) & 15;
+        const bool lowi = i < i2, roti = (rmask >> (lowi ? i : i2)) & 1u;
+        const double ci = cc[i], si = ss[i];
+        double v;
+        if (i == j) {
+          const double aii = Sc[i * N + i], a22 = Sc[i2 * N + i2], a12 = Sc[i * N + i2];
+          v = !roti ? aii
+                    : (lowi ? (ci * ci) * aii - (2 * ci * si) * a12 + (si * si) * a22
+                            : (si * si) * a22 + (2 * ci * si) * a12 + (ci * ci) * aii);
+        } else if (i2 == j) {
+          v = roti ? 0.0 : Sc[i * N + j];
+        } else {
+          const int j2 = (int)(pj[m] >> (4 * r)) & 15;
+          const bool lowj = j < j2;
+          const double cj = cc[j], sj = ss[j];
+          const double a0 = Sc[i * N + j], a1 = Sc[i * N + j2], b0 = Sc[i2 * N + j], b1 = Sc[i2 * N + j2];
+          const double bi = lowj ? cj * a0 - sj * a1 : sj * a1 + cj * a0;
+          const double bi2 = lowj ? cj * b0 - sj * b1 : sj * b1 + cj * b0;
+          v = lowi ? ci * bi - si * bi2 : si * bi2 + ci * bi;
+        }
+        Sn[i * N + j] = v;
+        Sn[j * N + i] = v;
+      }
+#pragma unroll
+      for (int m = 0; m < VPT; m++) {
+        const int v = (NT - 1 - tid) + NT * m;  // the threads with the fewest S elements take the most Vr elements
+        if (v >= NV) continue;
+        const int x = v / N, k = v - N * x, x2 = (int)(pv[m] >> (4 * r)) & 15;
+        const double a = Vc[x * N + k], b = Vc[x2 * N + k];
+        Vn[v] = (x < x2) ? cc[x] * a - ss[x] * b : ss[x] * b + cc[x] * a;
+      }
+      sync();
+      {
+        double* t = Sc;
+        Sc = Sn;
+        Sn = t;
+        t = Vc;
+        Vc = Vn;
+        Vn = t;
+      }
+      if (prof) t_apply += clock64() - t0;
+    }
     if (!changed) break;
   }
+  if (prof && tid == 0) {
+    prof[0] = t_rot;
+    prof[1] = t_apply;
+    prof[2] = 0;
+    prof[3] = n_rounds;
+  }
   // selection sort (descending) of the eigenvalues; the row swaps are applied as one permutation
-  int perm[N];
-  {
+  if (tid < 32) {
+    int perm[N];
     double W[N];
     for (int i = 0; i < N; i++) {
-      W[i] = S[i * N + i];
+      W[i] = Sc[i * N + i];
       perm[i] = i;
     }
     for (int i = 0; i < N - 1; i++) {
@@ -228,12 +338,12 @@ __device__ void jacobi_eigh_group(double* S, double* Vr, double* w, double* Vt, 
         perm[j] = tp;
       }
     }
-    if (gl == 0)
+    if (tid == 0)
       for (int i = 0; i < N; i++) w[i] = W[i];
+    if (tid < N)
+      for (int i = 0; i < N; i++) Vt[i * N + tid] = Vc[perm[i] * N + tid];
   }
-  if (gl < N)
-    for (int i = 0; i < N; i++) Vt[i * N + gl] = Vr[perm[i] * N + gl];
-  __syncwarp(gmask);
+  sync();
 }
 
 // least-squares / pseudo-inverse solve via SVD (cvSolve CV_SVD); m <= 6, n <= 6

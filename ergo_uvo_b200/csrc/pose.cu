@@ -217,28 +217,14 @@ __device__ __forceinline__ int pnp_n(const PnpArgs& a) {
   return n;
 }
 
-__global__ void __launch_bounds__(256) k_pnp_prepare(const __grid_constant__ PnpArgs a) {
-  const int n = pnp_n(a);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    if (a.x_idx) {
-      const uvo_keypoint& k = a.kps[a.matches[a.x_idx[i]].trainIdx];
-      a.xs[2 * i] = k.x;
-      a.xs[2 * i + 1] = k.y;
-    } else {
-      a.xs[2 * i] = a.x[2 * i];
-      a.xs[2 * i + 1] = a.x[2 * i + 1];
-    }
-    for (int cc = 0; cc < 3; cc++) a.Xf[3 * i + cc] = (float)a.X[3 * i + cc];  // opoints0.convertTo(CV_32F)
-  }
+__device__ __forceinline__ void pnp_prof(const PnpArgs& a, int slot) {
+  if (a.prof) a.prof[slot] = clock64();
 }
 
 // getSubset stream for all iterations (one warp).  Lane l speculatively takes draws [p+5l, p+5l+5); a subset with a
 // repeated index is rebuilt sequentially by lane 0 with OpenCV's redraw rule and the stream position re-aligned.
-__global__ void __launch_bounds__(32) k_pnp_subsets(const __grid_constant__ PnpArgs a,
-                                                    const uint32_t* __restrict__ rng) {
-  const int n = pnp_n(a);
+__device__ void pnp_subsets_warp(const PnpArgs& a, const uint32_t* __restrict__ rng, int n, int lane) {
   const int iters = max(a.iterations, 1);
-  const int lane = threadIdx.x;
   if (n < 5) return;
   if (n == 5) {
     if (lane < 5) a.subsets[lane] = lane;
@@ -289,87 +275,37 @@ __global__ void __launch_bounds__(32) k_pnp_subsets(const __grid_constant__ PnpA
   }
 }
 
-// One EPnP hypothesis (PnPRansacCallback::runKernel) per group of HYP_GL lanes.  The 5 correspondences arrive as f32,
-// image points are normalised with undistortPoints (f32 round trip), the pose goes R -> rvec (Rodrigues) and is stored
-// together with the rotation matrix projectPoints rebuilds from rvec.  Inside a group: the small set-up algebra is
-// done redundantly by every lane, M^T M is accumulated 9 entries per lane, the 12 x 12 eigen-decomposition is
-// lane-parallel (jacobi_eigh_group), lanes 0..5 / 6..11 build L / rho, and lanes 0..2 each refine one of the three
-// beta candidates and its pose.  Every value is produced by the same IEEE operations in the same order as the
-// one-thread restatement in the oracle, so the split changes latency, not bits.
-constexpr int HYP_GL = 16;  // (one warp per hypothesis was measured slower: 305 vs 281 us, and it crowds the SMs)
-constexpr int HYP_PER_BLOCK = 8;
-
-__global__ void __launch_bounds__(HYP_GL* HYP_PER_BLOCK) k_pnp_hyp(const __grid_constant__ PnpArgs a) {
-  __shared__ double s_S[HYP_PER_BLOCK][144], s_Vr[HYP_PER_BLOCK][144], s_ut[HYP_PER_BLOCK][144];
-  __shared__ double s_w[HYP_PER_BLOCK][12], s_l[HYP_PER_BLOCK][60], s_rho[HYP_PER_BLOCK][6];
-  __shared__ double s_al[HYP_PER_BLOCK][5][4];
+// Gathers the correspondences (f32 copies, as solvePnPRansac makes them), rebuilds the subset stream (the last block's
+// first warp) and resets the RANSAC bookkeeping the chunk kernels carry.
+__global__ void __launch_bounds__(256) k_pnp_prepare(const __grid_constant__ PnpArgs a,
+                                                     const uint32_t* __restrict__ rng) {
   const int n = pnp_n(a);
-  if (n < 5) return;
-  const int iters = (n == 5) ? 1 : max(a.iterations, 1);
-  const int g = threadIdx.x / HYP_GL, gl = threadIdx.x % HYP_GL;
-  const int h = blockIdx.x * HYP_PER_BLOCK + g;
-  if (h >= iters) return;  // whole group
-  const int lane = threadIdx.x & 31;
-  const int gbase = lane & ~(HYP_GL - 1);
-  const unsigned gmask = (HYP_GL == 32 ? 0xffffffffu : ((1u << (HYP_GL & 31)) - 1u)) << gbase;
-  EpnpCam cam{a.K[0], a.K[1], a.K[2], a.K[3]};
-  const double ifx = 1. / a.K[0], ify = 1. / a.K[1];
-  double pws[15], us[10];
-  for (int k = 0; k < 5; k++) {
-    const int i = a.subsets[(size_t)h * 5 + k];
-    for (int cc = 0; cc < 3; cc++) pws[3 * k + cc] = (double)a.Xf[3 * i + cc];
-    const double xn = (double)(float)(((double)a.xs[2 * i] - a.K[2]) * ifx);
-    const double yn = (double)(float)(((double)a.xs[2 * i + 1] - a.K[3]) * ify);
-    us[2 * k] = xn * cam.fu + cam.uc;
-    us[2 * k + 1] = yn * cam.fv + cam.vc;
-  }
-  double cws[4][3], ci[9];
-  double(*alphas)[4] = s_al[g];
-  {
-    double al[5][4];
-    epnp_small_setup(pws, 5, cws, ci, al);  // every lane computes the same values
-    if (gl == 0)
-      for (int i = 0; i < 5; i++)
-        for (int k = 0; k < 4; k++) alphas[i][k] = al[i][k];
-  }
-  __syncwarp(gmask);
-  // M^T M, each entry summed over the points in index order
-  for (int e = gl; e < 144; e += HYP_GL) {
-    const int ra = e / 12, rb = e - 12 * ra;
-    double acc = 0;
-    for (int i = 0; i < 5; i++) {
-      double m1a, m2a, m1b, m2b;
-      epnp_m_elem(alphas[i], us[2 * i], us[2 * i + 1], cam, ra, m1a, m2a);
-      epnp_m_elem(alphas[i], us[2 * i], us[2 * i + 1], cam, rb, m1b, m2b);
-      acc += m1a * m1b + m2a * m2b;
+  if (blockIdx.x == gridDim.x - 1) {
+    if (threadIdx.x < 32) pnp_subsets_warp(a, rng, n, threadIdx.x);
+    if (threadIdx.x == 32) {
+      PnpState* st = a.state;
+      st->niters = (n == 5) ? 1 : max(a.iterations, 1);
+      st->best = 0;
+      st->best_h = -1;
+      st->iter = 0;
+      st->ticket = 0;
+      st->done = n < 5 ? 1 : 0;
+      a.best[0] = -1;
+      a.best[1] = 0;
+      *a.hyps = 0;
     }
-    s_S[g][e] = acc;
+    return;
   }
-  __syncwarp(gmask);
-  jacobi_eigh_group<12>(s_S[g], s_Vr[g], s_w[g], s_ut[g], gl, gmask);
-  if (gl < 6) epnp_L_row(s_ut[g], gl, s_l[g] + 10 * gl);
-  else if (gl < 12) s_rho[g][gl - 6] = epnp_rho_entry(cws, gl - 6);
-  __syncwarp(gmask);
-  double err = 0, Rw[9], tw[3];
-  if (gl < 3) {
-    double betas[4];
-    epnp_betas_which(s_l[g], s_rho[g], gl + 1, betas);
-    err = epnp_candidate(pws, us, 5, alphas, betas, s_ut[g], cam, Rw, tw);
-  }
-  // N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
-  const double e1 = __shfl_sync(gmask, err, gbase + 0), e2 = __shfl_sync(gmask, err, gbase + 1),
-               e3 = __shfl_sync(gmask, err, gbase + 2);
-  int N = 1;
-  if (e2 < e1) N = 2;
-  if (e3 < (N == 1 ? e1 : e2)) N = 3;
-  if (gl == N - 1) {
-    double rvec[3], R2[9];
-    rodrigues_mat2vec(Rw, rvec);
-    rodrigues_vec2mat(rvec, R2);
-    double* m = a.hyp_model + (size_t)h * 15;
-    for (int i = 0; i < 9; i++) m[i] = R2[i];
-    for (int i = 0; i < 3; i++) m[9 + i] = tw[i];
-    for (int i = 0; i < 3; i++) m[12 + i] = rvec[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (gridDim.x - 1) * blockDim.x) {
+    if (a.x_idx) {
+      const uvo_keypoint& k = a.kps[a.matches[a.x_idx[i]].trainIdx];
+      a.xs[2 * i] = k.x;
+      a.xs[2 * i + 1] = k.y;
+    } else {
+      a.xs[2 * i] = a.x[2 * i];
+      a.xs[2 * i + 1] = a.x[2 * i + 1];
+    }
+    for (int cc = 0; cc < 3; cc++) a.Xf[3 * i + cc] = (float)a.X[3 * i + cc];  // opoints0.convertTo(CV_32F)
   }
 }
 
@@ -382,28 +318,6 @@ __device__ __forceinline__ bool pnp_is_inlier(const double* m, const float* Xf, 
   const float dx = __fsub_rn(xs[2 * i], (float)pr[0]), dy = __fsub_rn(xs[2 * i + 1], (float)pr[1]);
   const float e = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
   return e <= thr;
-}
-
-__global__ void __launch_bounds__(256) k_pnp_score(const __grid_constant__ PnpArgs a) {
-  __shared__ int s_cnt[8];
-  const int n = pnp_n(a);
-  if (n < 5) return;
-  const int iters = (n == 5) ? 1 : max(a.iterations, 1);
-  const int h = blockIdx.x;
-  if (h >= iters) return;
-  const float thr = (float)((double)a.reproj_err * (double)a.reproj_err);
-  const double* m = a.hyp_model + (size_t)h * 15;
-  int cnt = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) cnt += pnp_is_inlier(m, a.Xf, a.xs, i, a.K, thr) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int w = 0; w < 8; w++) tot += s_cnt[w];
-    a.hyp_good[h] = tot;
-  }
 }
 
 __device__ inline int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
@@ -419,33 +333,169 @@ __device__ inline int ransac_update_num_iters(double p, double ep, int model_poi
   return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
 }
 
-// sequential RANSAC bookkeeping replayed by one warp over the per-hypothesis inlier counts
-__global__ void __launch_bounds__(32) k_pnp_scan(const __grid_constant__ PnpArgs a) {
+// One EPnP hypothesis (PnPRansacCallback::runKernel) on a group of NT = 32 NW threads (NW warps).  The 5
+// correspondences arrive as f32, image points are normalised with undistortPoints (f32 round trip), the pose goes
+// R -> rvec (Rodrigues) and is stored together with the rotation matrix projectPoints rebuilds from rvec.  Inside the
+// group: the small set-up algebra runs on the group's first warp (every lane computes the same values), M^T M and the
+// 12 x 12 eigen-decomposition (jacobi_eigh_rr) are spread over all NT threads, lanes 0..5 / 6..11 of the first warp
+// build L / rho, and lanes 0..2 each refine one of the three beta candidates and its pose.  Every value is produced
+// by the same IEEE operations in the same order as the one-thread restatement in the oracle, so the split changes
+// latency, not bits.
+struct HypSmem {
+  double S[2 * 144], Vr[2 * 144], ut[144], w[12], l[60], rho[6], al[5][4], us[10], rot[24], model[15];
+  unsigned rflag[2];
+  int cnt[4];
+};
+
+template <int NT>
+__device__ __forceinline__ void group_sync() {
+  if (NT == 32) __syncwarp();
+  else __syncthreads();
+}
+
+template <int NT>
+__device__ void pnp_hypothesis(const PnpArgs& a, int h, HypSmem& sm, int tid, bool prof) {
+  const EpnpCam cam{a.K[0], a.K[1], a.K[2], a.K[3]};
+  double pws[15], us[10], cws[4][3];
+  if (tid < 32) {
+    const double ifx = 1. / a.K[0], ify = 1. / a.K[1];
+    for (int k = 0; k < 5; k++) {
+      const int i = a.subsets[(size_t)h * 5 + k];
+      for (int cc = 0; cc < 3; cc++) pws[3 * k + cc] = (double)a.Xf[3 * i + cc];
+      const double xn = (double)(float)(((double)a.xs[2 * i] - a.K[2]) * ifx);
+      const double yn = (double)(float)(((double)a.xs[2 * i + 1] - a.K[3]) * ify);
+      us[2 * k] = xn * cam.fu + cam.uc;
+      us[2 * k + 1] = yn * cam.fv + cam.vc;
+    }
+    if (prof && tid == 0) pnp_prof(a, 1);
+    double ci[9], al[5][4];
+    epnp_small_setup(pws, 5, cws, ci, al);  // every lane computes the same values
+    if (tid == 0) {
+      for (int i = 0; i < 5; i++)
+        for (int k = 0; k < 4; k++) sm.al[i][k] = al[i][k];
+      for (int i = 0; i < 10; i++) sm.us[i] = us[i];
+    }
+    if (prof && tid == 0) pnp_prof(a, 2);
+  }
+  group_sync<NT>();
+  // M^T M, each entry summed over the points in index order
+  for (int e = tid; e < 144; e += NT) {
+    const int ra = e / 12, rb = e - 12 * ra;
+    double acc = 0;
+    for (int i = 0; i < 5; i++) {
+      double m1a, m2a, m1b, m2b;
+      epnp_m_elem(sm.al[i], sm.us[2 * i], sm.us[2 * i + 1], cam, ra, m1a, m2a);
+      epnp_m_elem(sm.al[i], sm.us[2 * i], sm.us[2 * i + 1], cam, rb, m1b, m2b);
+      acc += m1a * m1b + m2a * m2b;
+    }
+    sm.S[e] = acc;
+  }
+  group_sync<NT>();
+  if (prof && tid == 0) pnp_prof(a, 3);
+  jacobi_eigh_rr<12, NT>(sm.S, sm.Vr, sm.w, sm.ut, sm.rot, sm.rflag, tid, prof ? a.prof + 10 : nullptr);
+  if (prof && tid == 0) pnp_prof(a, 4);
+  if (tid < 32) {
+    const int lane = tid;
+    if (lane < 6) epnp_L_row(sm.ut, lane, sm.l + 10 * lane);
+    else if (lane < 12) sm.rho[lane - 6] = epnp_rho_entry(cws, lane - 6);
+    __syncwarp();
+    double err = 0, Rw[9], tw[3];
+    if (lane < 3) {
+      double betas[4];
+      epnp_betas_which(sm.l, sm.rho, lane + 1, betas);
+      if (prof && lane == 2) pnp_prof(a, 5);
+      err = epnp_candidate(pws, us, 5, sm.al, betas, sm.ut, cam, Rw, tw);
+      if (prof && lane == 2) pnp_prof(a, 6);
+    }
+    // N = 1; if (rep[2] < rep[1]) N = 2; if (rep[3] < rep[N]) N = 3;
+    const double e1 = __shfl_sync(0xffffffffu, err, 0), e2 = __shfl_sync(0xffffffffu, err, 1),
+                 e3 = __shfl_sync(0xffffffffu, err, 2);
+    int N = 1;
+    if (e2 < e1) N = 2;
+    if (e3 < (N == 1 ? e1 : e2)) N = 3;
+    if (lane == N - 1) {
+      double rvec[3], R2[9];
+      rodrigues_mat2vec(Rw, rvec);
+      rodrigues_vec2mat(rvec, R2);
+      double* m = a.hyp_model + (size_t)h * 15;
+      for (int i = 0; i < 9; i++) sm.model[i] = m[i] = R2[i];
+      for (int i = 0; i < 3; i++) sm.model[9 + i] = m[9 + i] = tw[i];
+      for (int i = 0; i < 3; i++) sm.model[12 + i] = m[12 + i] = rvec[i];
+    }
+    if (prof && lane == 0) pnp_prof(a, 7);
+  }
+  group_sync<NT>();
+}
+
+// One chunk [lo, hi) of the RANSAC iterations.  A group of NW warps solves one hypothesis (pnp_hypothesis) and counts
+// that model's inliers; a block of 4 warps holds 4 / NW groups.  The last block of the chunk to finish replays
+// OpenCV's sequential bookkeeping -- `if (good > max(best, 4)) { best = good; niters = RANSACUpdateNumIters(...) }` --
+// over the chunk's counts, carrying (niters, best, best_h, iter) in a.state from chunk to chunk.  Once the replay
+// reaches niters the state is marked done and every later chunk kernel returns at once: hypotheses the CPU loop would
+// never have drawn are not solved (the reference configuration stops after a handful -- 97 % inliers give niters = 2
+// -- so the first chunk of 32 is normally the only one that runs).  Exactness is untouched: the replay sees the same
+// counts in the same order.  NW = 4 (one hypothesis per block) for the small leading chunks, where the latency of ONE
+// hypothesis is the latency of the stage; NW = 1 (four per block) for the large ones, where throughput counts.
+constexpr int CHUNK_THREADS = 128;
+
+template <int NW>
+__global__ void __launch_bounds__(CHUNK_THREADS) k_pnp_chunk(const __grid_constant__ PnpArgs a, int lo, int hi) {
+  constexpr int NT = 32 * NW, HPB = 4 / NW;
+  __shared__ HypSmem s_hyp[HPB];
+  __shared__ int s_last;
+  PnpState* st = a.state;
+  if (st->done) return;  // written by an earlier kernel of the stream
   const int n = pnp_n(a);
-  const int lane = threadIdx.x;
-  if (n < 5) {
-    if (lane == 0) {
-      a.best[0] = -1;
-      a.best[1] = 0;
-      *a.hyps = 0;
+  const int iters = (n == 5) ? 1 : max(a.iterations, 1);
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT, lane = threadIdx.x & 31;
+  const int h = lo + blockIdx.x * HPB + grp;
+  HypSmem& sm = s_hyp[grp];
+  const bool prof = a.prof && h == 0;
+  if (h < min(hi, iters)) {  // uniform over the group
+    if (prof && tid == 0) pnp_prof(a, 0);
+    pnp_hypothesis<NT>(a, h, sm, tid, prof);
+    const float thr = (float)((double)a.reproj_err * (double)a.reproj_err);
+    int cnt = 0;
+    for (int i = tid; i < n; i += NT) cnt += pnp_is_inlier(sm.model, a.Xf, a.xs, i, a.K, thr) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (NW > 1) {
+      if (lane == 0) sm.cnt[tid >> 5] = cnt;
+      group_sync<NT>();
+      if (tid == 0) {
+        cnt = 0;
+        for (int w = 0; w < NW; w++) cnt += sm.cnt[w];
+      }
     }
-    return;
+    if (tid == 0) {
+      a.hyp_good[h] = cnt;
+      if (prof) pnp_prof(a, 8);
+    }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  __threadfence();
+  // the sequential RANSAC bookkeeping, continued over this chunk's counts by one warp
+  int niters = st->niters, best = st->best, best_h = st->best_h, iter = st->iter;
   if (n == 5) {  // count == modelPoints: a single kernel call, every point an inlier
-    if (lane == 0) {
-      a.best[0] = 0;
-      a.best[1] = 5;
-      *a.hyps = 1;
-    }
-    return;
+    best_h = 0;
+    best = 5;
+    iter = 1;
+    niters = 1;
   }
-  int niters = max(a.iterations, 1), best = 0, best_h = -1, iter = 0;
-  while (iter < niters) {
+  for (;;) {
+    const int limit = min(niters, hi);
+    if (iter >= limit) break;
     const int idx = iter + lane;
-    const int g = idx < niters ? a.hyp_good[idx] : -1;
+    const int g = idx < limit ? __ldcg(a.hyp_good + idx) : -1;
     const unsigned mask = __ballot_sync(0xffffffffu, g > max(best, 4));
     if (!mask) {
-      iter = min(iter + 32, niters);
+      iter = min(iter + 32, limit);
       continue;
     }
     const int f = __ffs(mask) - 1;
@@ -455,34 +505,43 @@ __global__ void __launch_bounds__(32) k_pnp_scan(const __grid_constant__ PnpArgs
     iter = best_h + 1;
   }
   if (lane == 0) {
-    a.best[0] = best_h;
-    a.best[1] = best;
-    *a.hyps = iter;
+    st->niters = niters;
+    st->best = best;
+    st->best_h = best_h;
+    st->iter = iter;
+    st->ticket = 0;
+    if (iter >= niters) {
+      st->done = 1;
+      a.best[0] = best_h;
+      a.best[1] = best;
+      *a.hyps = iter;
+    }
+    if (a.prof && lo == 0) pnp_prof(a, 9);
   }
 }
 
 // inlier mask of the winning hypothesis -> ascending inlier list, then the EPnP refit on all inliers
 // (solvePnPRansac's final solvePnP on f64 copies of the f32 data).  One block.
 constexpr int REFIT_THREADS = 256;
-constexpr int REFIT_TILE = 64;
+constexpr int REFIT_MAX_WORDS = 2048;  // inlier-mask words: up to 65 536 correspondences
 
 __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_constant__ PnpArgs a) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
-  __shared__ double s_red[32 * 27], s_out[27];
+  __shared__ double s_red[8 * 40], s_out[40];
   __shared__ double s_cws[4][3], s_ci[9], s_ut[144], s_betas[3][4], s_ccs3[3][4][3], s_R3[3][9], s_t3[3][3], s_sign3[3];
-  __shared__ double s_rows[REFIT_TILE][24];
-  __shared__ double s_mtm[144], s_Vr[144], s_w[12], s_l[60], s_rho[6];
-  const int tid = threadIdx.x;
+  __shared__ double s_mtm[2 * 144], s_Vr[2 * 144], s_w[12], s_l[60], s_rho[6], s_rot[24];
+  __shared__ unsigned s_rflag[2];
+  __shared__ unsigned s_mask[REFIT_MAX_WORDS];
+  __shared__ int s_off[REFIT_MAX_WORDS];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = pnp_n(a);
   const int best_h = a.best[0];
+  if (a.prof && tid == 0) pnp_prof(a, 16);
   if (n < 5 || best_h < 0) {
     if (tid == 0) {
       *a.n_inliers = 0;
       for (int i = 0; i < 6; i++) a.result[i] = 0.0;
       a.result[6] = 0.0;
-      if (n >= 5 && best_h < 0 && a.iterations > 0) {  // no model beat 4 inliers: cv2 returns the last rvec/tvec
-      }
     }
     return;
   }
@@ -498,17 +557,40 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     }
     return;
   }
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + tid;
-    const bool keep = i < n && pnp_is_inlier(m, a.Xf, a.xs, i, a.K, thr);
-    const int slot = ordered_slot(keep, s_warp, &s_base);
-    if (slot >= 0) a.inliers[slot] = i;
+  // ascending inlier list: one ballot per 32 consecutive points, an exclusive scan of the popcounts by warp 0, then
+  // every warp writes its words' inliers in place
+  const int words = (n + 31) >> 5;
+  for (int wd = wid; wd < words; wd += REFIT_THREADS / 32) {
+    const int i = 32 * wd + lane;
+    const unsigned b = __ballot_sync(0xffffffffu, i < n && pnp_is_inlier(m, a.Xf, a.xs, i, a.K, thr));
+    if (lane == 0) s_mask[wd] = b;
   }
   __syncthreads();
-  const int ni = s_base;
+  if (wid == 0) {
+    int run = 0;
+    for (int base = 0; base < words; base += 32) {
+      const int wd = base + lane;
+      const int c = wd < words ? __popc(s_mask[wd]) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (wd < words) s_off[wd] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_total = run;
+  }
+  __syncthreads();
+  for (int wd = wid; wd < words; wd += REFIT_THREADS / 32) {
+    const unsigned b = s_mask[wd];
+    if ((b >> lane) & 1u) a.inliers[s_off[wd] + __popc(b & ((1u << lane) - 1u))] = 32 * wd + lane;
+  }
+  const int ni = s_total;
   if (tid == 0) *a.n_inliers = ni;
+  __syncthreads();  // the list is read back below by other threads
+  if (a.prof && tid == 0) pnp_prof(a, 17);
   // ---------------- EPnP on the inliers ----------------
   const EpnpCam cam{a.K[0], a.K[1], a.K[2], a.K[3]};
   const double ifx = 1. / a.K[0], ify = 1. / a.K[1];
@@ -545,34 +627,62 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     epnp_control_points(c0, cov, ni, s_cws, s_ci);
   }
   __syncthreads();
-  // MtM, summed over points in index order (entry (p,q) owned by thread p*12+q)
-  double mt = 0;
-  for (int base = 0; base < ni; base += REFIT_TILE) {
-    const int cntp = min(REFIT_TILE, ni - base);
-    if (tid < cntp) {
+  if (a.prof && tid == 0) pnp_prof(a, 18);
+  // M^T M.  A point contributes rows M1 = [a_k fu, 0, a_k (uc - u)]_k, M2 = [0, a_k fv, a_k (vc - v)]_k, so the 12 x 12
+  // sum is (a a^T) (x) G(u, v): four weighted sums of the ten products a_k a_k' -- weights 1, uc - u, vc - v,
+  // (uc - u)^2 + (vc - v)^2 -- give every entry.  Each thread accumulates its points in 40 registers, one block
+  // reduction adds them (a fixed-shape tree; the refit is compared with the oracle to 1e-9, not bit for bit).
+  {
+    double acc[40];
+#pragma unroll
+    for (int i = 0; i < 40; i++) acc[i] = 0;
+    for (int k = tid; k < ni; k += blockDim.x) {
       double al[4];
-      point(base + tid, pw, u, v);
+      point(k, pw, u, v);
       epnp_alphas(pw, s_cws, s_ci, al);
-      epnp_m_rows(al, u, v, cam, &s_rows[tid][0], &s_rows[tid][12]);
+      const double du = cam.uc - u, dv = cam.vc - v, dd = du * du + dv * dv;
+      int e = 0;
+#pragma unroll
+      for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = p; q < 4; q++) {
+          const double aa = al[p] * al[q];
+          acc[e] += aa;
+          acc[10 + e] += aa * du;
+          acc[20 + e] += aa * dv;
+          acc[30 + e] += aa * dd;
+          e++;
+        }
     }
-    __syncthreads();
+    block_reduce_sum<40>(acc, s_red, s_out);
     if (tid < 144) {
-      const int p = tid / 12, q = tid % 12;
-      for (int k = 0; k < cntp; k++) mt += s_rows[k][p] * s_rows[k][q] + s_rows[k][12 + p] * s_rows[k][12 + q];
+      const int ra = tid / 12, rb = tid - 12 * ra;
+      const int ka = ra / 3, ta = ra - 3 * ka, kb = rb / 3, tb = rb - 3 * kb;
+      const int p = min(ka, kb), q = max(ka, kb);
+      const int e = p * 4 - (p * (p - 1)) / 2 + (q - p);  // index of (p, q), p <= q, in the row-major upper triangle
+      const double P = s_out[e], Q = s_out[10 + e], R = s_out[20 + e], T = s_out[30 + e];
+      double val = 0.0;
+      if (ta == 0 && tb == 0) val = (cam.fu * cam.fu) * P;
+      else if (ta == 1 && tb == 1) val = (cam.fv * cam.fv) * P;
+      else if (ta == 2 && tb == 2) val = T;
+      else if ((ta == 0 && tb == 2) || (ta == 2 && tb == 0)) val = cam.fu * Q;
+      else if ((ta == 1 && tb == 2) || (ta == 2 && tb == 1)) val = cam.fv * R;
+      s_mtm[tid] = val;
     }
     __syncthreads();
   }
-  if (tid < 144) s_mtm[tid] = mt;
-  __syncthreads();
-  // eigenvectors of M^T M lane-parallel on warp 0, L / rho on lanes 0..11, one beta candidate per lane 0..2
+  if (a.prof && tid == 0) pnp_prof(a, 19);
+  // eigenvectors of M^T M over the whole block, L / rho on lanes 0..11, one beta candidate per lane 0..2
+  jacobi_eigh_rr<12, REFIT_THREADS>(s_mtm, s_Vr, s_w, s_ut, s_rot, s_rflag, tid);
+  if (a.prof && tid == 0) pnp_prof(a, 20);
   if (tid < 32) {
-    jacobi_eigh_group<12>(s_mtm, s_Vr, s_w, s_ut, tid, 0xffffffffu);
     if (tid < 6) epnp_L_row(s_ut, tid, s_l + 10 * tid);
     else if (tid < 12) s_rho[tid - 6] = epnp_rho_entry(s_cws, tid - 6);
     __syncwarp();
     if (tid < 3) epnp_betas_which(s_l, s_rho, tid + 1, s_betas[tid]);
   }
   __syncthreads();
+  if (a.prof && tid == 0) pnp_prof(a, 21);
   // the three beta candidates go through compute_R_and_t together: one pass over the inliers accumulates all three
   // sums (the barycentric coordinates of a point are shared), the one-thread steps run on lanes 0..2 of warp 0.  Per
   // candidate the operations and their order are those of a loop over the candidates.
@@ -629,6 +739,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     epnp_rt_from_abt(abt, pc0[tid], c0, s_R3[tid], s_t3[tid]);
   }
   __syncthreads();
+  if (a.prof && tid == 0) pnp_prof(a, 22);
   {
     double acc[3] = {0, 0, 0};
     for (int k = tid; k < ni; k += blockDim.x) {
@@ -653,6 +764,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     for (int i = 0; i < 3; i++) a.result[i] = rvec[i];
     for (int i = 0; i < 3; i++) a.result[3 + i] = bestt[i];
     a.result[6] = 1.0;
+    if (a.prof) pnp_prof(a, 23);
   }
 }
 
@@ -747,37 +859,56 @@ void launch_front_z(Ctx& c, const double* pts, int n, const double R[9], const d
   UVO_LAUNCH_CHECK(c);
 }
 
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
 size_t pnp_scratch_bytes(int n, int iterations) {
   const size_t it = (size_t)std::max(iterations, 1);
-  return it * 5 * sizeof(int32_t) + it * 15 * sizeof(double) + it * sizeof(int) + (size_t)n * 2 * sizeof(float) +
-         (size_t)n * 3 * sizeof(float) + 64;
+  return al256(it * 5 * sizeof(int32_t)) + al256(it * 15 * sizeof(double)) + al256(it * sizeof(int)) +
+         al256((size_t)n * 2 * sizeof(float)) + al256((size_t)n * 3 * sizeof(float)) + al256(sizeof(PnpState)) +
+         al256(2 * sizeof(int)) + 256;
+}
+
+void pnp_bind_scratch(PnpArgs& a, uint8_t* base, int n, int iterations) {
+  const size_t it = (size_t)std::max(iterations, 1);
+  uint8_t* b = (uint8_t*)al256((size_t)base);
+  auto take = [&](size_t bytes) {
+    uint8_t* r = b;
+    b += al256(bytes);
+    return r;
+  };
+  a.subsets = (int32_t*)take(it * 5 * sizeof(int32_t));
+  a.hyp_model = (double*)take(it * 15 * sizeof(double));
+  a.hyp_good = (int*)take(it * sizeof(int));
+  a.xs = (float*)take((size_t)n * 2 * sizeof(float));
+  a.Xf = (float*)take((size_t)n * 3 * sizeof(float));
+  a.state = (PnpState*)take(sizeof(PnpState));
+  a.best = (int*)take(2 * sizeof(int));
 }
 
 void launch_pnp_prepare(Ctx& c, const PnpArgs& a) {
+  UVO_REQUIRE(a.n <= 32 * REFIT_MAX_WORDS, "solvePnPRansac: more than 65 536 correspondences");
   const uint32_t* rng = rng_table_device(c);
   const int iters = std::max(a.iterations, 1);
   UVO_REQUIRE((size_t)iters * 8 < (size_t)RNG_TABLE_SIZE, "solvePnPRansac: iterationsCount too large for the RNG table");
-  if (a.n > 0) {
-    UVO_KERNEL(c, "k_pnp_prepare");
-    k_pnp_prepare<<<std::min(div_up(a.n, 256), 4 * c.sm_count), 256, 0, c.stream>>>(a);
-    UVO_LAUNCH_CHECK(c);
-  }
-  UVO_KERNEL(c, "k_pnp_subsets");
-  k_pnp_subsets<<<1, 32, 0, c.stream>>>(a, rng);
+  UVO_KERNEL(c, "k_pnp_prepare");
+  k_pnp_prepare<<<std::min(div_up(std::max(a.n, 1), 256), 4 * c.sm_count) + 1, 256, 0, c.stream>>>(a, rng);
   UVO_LAUNCH_CHECK(c);
 }
 
 void launch_pnp_solve(Ctx& c, const PnpArgs& a) {
   const int iters = std::max(a.iterations, 1);
-  UVO_KERNEL(c, "k_pnp_hyp");
-  k_pnp_hyp<<<div_up(iters, HYP_PER_BLOCK), HYP_GL * HYP_PER_BLOCK, 0, c.stream>>>(a);
-  UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_pnp_score");
-  k_pnp_score<<<iters, 256, 0, c.stream>>>(a);
-  UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_pnp_scan");
-  k_pnp_scan<<<1, 32, 0, c.stream>>>(a);
-  UVO_LAUNCH_CHECK(c);
+  // chunks of the iteration range: small first (the reference configuration stops within it), then growing
+  const int bounds[4] = {32, 128, 512, iters};
+  int lo = 0;
+  for (int k = 0; k < 4 && lo < iters; k++) {
+    const int hi = std::min(bounds[k], iters);
+    if (hi <= lo) continue;
+    UVO_KERNEL(c, "k_pnp_chunk");
+    if (hi <= 128) k_pnp_chunk<4><<<hi - lo, CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
+    else k_pnp_chunk<1><<<div_up(hi - lo, 4), CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
+    UVO_LAUNCH_CHECK(c);
+    lo = hi;
+  }
   UVO_KERNEL(c, "k_pnp_finalize");
   k_pnp_finalize<<<1, REFIT_THREADS, 0, c.stream>>>(a);
   UVO_LAUNCH_CHECK(c);

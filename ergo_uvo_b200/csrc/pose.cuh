@@ -49,6 +49,16 @@ struct Extract3dArgs {
 };
 void launch_extract3d(Ctx& c, const Extract3dArgs& a);
 
+// RANSAC bookkeeping carried from one chunk of iterations to the next (device memory, reset by k_pnp_prepare)
+struct PnpState {
+  int niters;   // current RANSACUpdateNumIters bound
+  int best;     // best inlier count so far
+  int best_h;   // its hypothesis (-1: none yet)
+  int iter;     // iterations replayed so far
+  int ticket;   // blocks of the running chunk that have finished
+  int done;     // the sequential loop would have stopped: later chunks return at once
+};
+
 struct PnpArgs {
   const double* X;       // n x 3 f64 (down-cast to f32 inside, as solvePnPRansac does)
   const float* x;        // n x 2 f32 (used when x_idx == nullptr)
@@ -75,7 +85,11 @@ struct PnpArgs {
   float* xs;             // n x 2 gathered image points
   float* Xf;             // n x 3 f32 object points
   int* best;             // [0] best hypothesis, [1] best count
+  PnpState* state;       // chunk-to-chunk bookkeeping
+  long long* prof;       // optional (diagnostics): clock64 stamps of the phases of hypothesis 0 and of the refit
 };
+// carves subsets / hyp_model / hyp_good / xs / Xf / state / best out of one allocation of pnp_scratch_bytes(n, iterations)
+void pnp_bind_scratch(PnpArgs& a, uint8_t* base, int n, int iterations);
 void launch_pnp_ransac(Ctx& c, const PnpArgs& a);   // = prepare + solve
 // the two halves, for callers that split them over streams: prepare gathers the correspondences and rebuilds the
 // subset stream; solve runs hypotheses, scoring, the sequential bookkeeping replay and the refit

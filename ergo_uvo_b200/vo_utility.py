@@ -404,6 +404,12 @@ class Context:
             C.byref(ni), C.byref(hyp)))
         return ni.value > 0, rvec, tvec, inl[:ni.value].copy(), hyp.value
 
+    def pnp_profile(self, enable=True):
+        """diagnostics: SM clock stamps of the previous solvePnPRansac call (uvo_pnp_profile)"""
+        st = np.zeros(32, np.int64)
+        self._ck(self.lib.uvo_pnp_profile(self.h, int(bool(enable)), _p(st)))
+        return st
+
     # ------------------------------------------------------------------ VO_utility.h:102
     def extract_3Dpoints(self, keypoints1_conv, keypoints2_conv, R1, t1, R2, t2, cameraMatrix1, cameraMatrix2,
                          points4D):

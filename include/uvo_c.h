@@ -259,6 +259,11 @@ UVO_API int uvo_scale_factor(uvo_ctx* ctx, const double* points_nx3_host, int n,
 UVO_API int uvo_solve_pnp_ransac(uvo_ctx* ctx, const double* X_host, const float* x_host, int n, const double K[4],
                                  int iterations, float reprojection_error, double confidence, double rvec[3],
                                  double tvec[3], int32_t* inliers_host, int* n_inliers, int* hyps_evaluated);
+/* diagnostics: when enabled, uvo_solve_pnp_ransac records SM clock stamps (clock64) at the phase boundaries of
+ * hypothesis 0 (slots 0-9: start, correspondences read, control points, M^T M, eigenvectors, betas, pose, model
+ * stored, scored, bookkeeping) and of the refit (slots 16-23: start, inlier list, control points, M^T M, eigenvectors,
+ * betas, poses, done).  `stamps` (nullable) receives the stamps of the previous call. */
+UVO_API int uvo_pnp_profile(uvo_ctx* ctx, int enable, int64_t stamps[32]);
 
 /* ---------------------------------------------------------------------------------------------------- K10a / K10b */
 /* cv::findHomography(p1, p2, method, ransacReprojThreshold, mask, maxIters, confidence) -- VO_utility.cpp:152.

@@ -119,16 +119,36 @@ inline void jacobi_svd(const double* A, int m, int n, double* w, double* U, doub
   }
 }
 
-// Eigen-decomposition of a symmetric N x N matrix by the cyclic two-sided Jacobi method: A = Vt^T diag(w) Vt, w
-// descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional null space (5-point
-// minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30 sweeps; with the
-// absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet another basis of
-// that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels and the CPU oracle
-// run this same sequence of IEEE operations (no FMA, sqrt and divide correctly rounded on both).
+// Eigen-decomposition of a symmetric N x N matrix (N even) by the two-sided Jacobi method in ROUND-ROBIN order:
+// A = Vt^T diag(w) Vt, w descending, rows of Vt = eigenvectors.  Used for EPnP's 12 x 12 M^T M, whose 2-dimensional
+// null space (5-point minimal sets) keeps a Hestenes SVD with a relative stopping rule rotating noise for all 30
+// sweeps; with the absolute threshold eps * trace this converges in 6-8 sweeps.  The cv2 wheel's LAPACK produces yet
+// another basis of that null space, so no choice is bit-comparable with OpenCV; the CUDA kernels
+// (csrc/linalg.cuh: jacobi_eigh_rr_warp) and this routine run the same sequence of IEEE operations (no FMA, sqrt and
+// divide correctly rounded on both), so the two agree bit for bit.
+//
+// Order: a sweep is N-1 rounds of N/2 index-disjoint pairs (the circle method: index N-1 stays, the others rotate --
+// round r pairs N-1 with r and (r+k) mod (N-1) with (r-k) mod (N-1), k = 1..N/2-1).  Disjoint rotations commute, so
+// the N/2 rotation angles of a round are all taken from the matrix as it stands at the start of the round and the
+// round is applied as one congruence S' = J^T S J with J = the product of the round's rotations.  Element (i, j), i < j,
+// of S' is evaluated as: columns first (the rotation of j's pair applied to rows i and partner(i)), then rows (the
+// rotation of i's pair); the lower triangle mirrors the upper one.  The N/2 rotations of a round have no data
+// dependence on each other, which is what the GPU uses: one lane per rotation, one lane per element.
+template <int N>
+struct RoundRobin {
+  // partner of index x in round r
+  static int partner(int x, int r) {
+    if (x == N - 1) return r;
+    if (x == r) return N - 1;
+    return ((2 * r - x) % (N - 1) + (N - 1)) % (N - 1);
+  }
+};
+
 template <int N>
 inline void jacobi_eigh(const double* A, double* w, double* Vt) {
+  static_assert(N % 2 == 0, "round-robin order needs an even dimension");
   // S: full symmetric working copy, Vr: rows converge to the eigenvectors
-  double S[N * N], Vr[N * N], W[N];
+  double S[N * N], T[N * N], Vr[N * N], V2[N * N], W[N];
   for (int i = 0; i < N * N; i++) S[i] = A[i];
   for (int i = 0; i < N; i++)
     for (int k = 0; k < N; k++) Vr[i * N + k] = (k == i) ? 1.0 : 0.0;
@@ -137,38 +157,74 @@ inline void jacobi_eigh(const double* A, double* w, double* Vt) {
   const double thr = tr * DBL_EPSILON;  // absolute: an off-diagonal entry below eps * trace is left alone
   for (int sweep = 0; sweep < 30; sweep++) {
     bool changed = false;
-    for (int p = 0; p < N - 1; p++)
-      for (int q = p + 1; q < N; q++) {
-        const double apq = S[p * N + q];
-        if (std::fabs(apq) <= thr) continue;
-        const double app = S[p * N + p], aqq = S[q * N + q];
-        // t = sgn(theta) / (|theta| + std::sqrt(theta^2 + 1)), c = 1 / std::sqrt(t^2 + 1), s = t c with theta = d / x, written
-        // so that only two square roots and one reciprocal are on the dependent chain
-        const double d = aqq - app, x = 2 * apq;
-        const double rr = std::sqrt(d * d + x * x);
-        const double u = std::fabs(d) + rr, xs = d >= 0 ? x : -x;
-        const double ih = 1 / std::sqrt(x * x + u * u);
-        const double t = xs / u, c = u * ih, s = xs * ih;
-        S[p * N + p] = app - t * apq;
-        S[q * N + q] = aqq + t * apq;
-        S[p * N + q] = 0;
-        S[q * N + p] = 0;
-        for (int k = 0; k < N; k++) {
-          if (k == p || k == q) continue;
-          const double skp = S[k * N + p], skq = S[k * N + q];
-          const double np_ = c * skp - s * skq, nq_ = s * skp + c * skq;
-          S[k * N + p] = np_;
-          S[p * N + k] = np_;
-          S[k * N + q] = nq_;
-          S[q * N + k] = nq_;
-        }
-        for (int k = 0; k < N; k++) {
-          const double vp = Vr[p * N + k], vq = Vr[q * N + k];
-          Vr[p * N + k] = c * vp - s * vq;
-          Vr[q * N + k] = s * vp + c * vq;
-        }
-        changed = true;
+    for (int r = 0; r < N - 1; r++) {
+      int pt[N];
+      bool low[N], rot[N];   // low: the index is the smaller one (p) of its pair; rot: its pair is rotated this round
+      double cc[N], ss[N];
+      bool any = false;
+      for (int x = 0; x < N; x++) {
+        pt[x] = RoundRobin<N>::partner(x, r);
+        low[x] = x < pt[x];
       }
+      for (int p = 0; p < N; p++) {
+        if (!low[p]) continue;
+        const int q = pt[p];
+        const double apq = S[p * N + q];
+        double c = 1.0, s = 0.0;
+        const bool rt = std::fabs(apq) > thr;
+        if (rt) {
+          const double app = S[p * N + p], aqq = S[q * N + q];
+          // c = u / h, s = sgn(d) x / h with d = aqq - app, x = 2 apq, u = |d| + sqrt(d^2 + x^2), h^2 = x^2 + u^2
+          // (t = s / c = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = d / x): two square roots and one
+          // reciprocal on the dependent chain
+          const double d = aqq - app, x = 2 * apq;
+          const double rr = std::sqrt(d * d + x * x);
+          const double u = std::fabs(d) + rr, xs = d >= 0 ? x : -x;
+          const double ih = 1 / std::sqrt(x * x + u * u);
+          c = u * ih;
+          s = xs * ih;
+          changed = true;
+        }
+        cc[p] = cc[q] = c;
+        ss[p] = ss[q] = s;
+        rot[p] = rot[q] = rt;
+        any = any || rt;
+      }
+      if (!any) continue;  // a round without a rotation leaves S and Vr as they are
+      for (int i = 0; i < N; i++)
+        for (int j = i; j < N; j++) {
+          double v;
+          if (i == j) {
+            // the pair's own diagonal: a'pp = c^2 app - 2 c s apq + s^2 aqq, a'qq = s^2 app + 2 c s apq + c^2 aqq
+            const int i2 = pt[i];
+            const double aii = S[i * N + i], a22 = S[i2 * N + i2], a12 = S[i * N + i2], ci = cc[i], si = ss[i];
+            v = !rot[i] ? aii
+                        : (low[i] ? (ci * ci) * aii - (2 * ci * si) * a12 + (si * si) * a22
+                                  : (si * si) * a22 + (2 * ci * si) * a12 + (ci * ci) * aii);
+          } else if (pt[i] == j) {
+            v = rot[i] ? 0.0 : S[i * N + j];
+          } else {
+            const int i2 = pt[i], j2 = pt[j];
+            // columns j / j2 of rows i and i2, then rows i / i2
+            const double bi = low[j] ? cc[j] * S[i * N + j] - ss[j] * S[i * N + j2]
+                                     : ss[j] * S[i * N + j2] + cc[j] * S[i * N + j];
+            const double bi2 = low[j] ? cc[j] * S[i2 * N + j] - ss[j] * S[i2 * N + j2]
+                                      : ss[j] * S[i2 * N + j2] + cc[j] * S[i2 * N + j];
+            v = low[i] ? cc[i] * bi - ss[i] * bi2 : ss[i] * bi2 + cc[i] * bi;
+          }
+          T[i * N + j] = v;
+          T[j * N + i] = v;
+        }
+      for (int x = 0; x < N; x++)
+        for (int k = 0; k < N; k++) {
+          const double a = Vr[x * N + k], b = Vr[pt[x] * N + k];
+          V2[x * N + k] = low[x] ? cc[x] * a - ss[x] * b : ss[x] * b + cc[x] * a;
+        }
+      for (int i = 0; i < N * N; i++) {
+        S[i] = T[i];
+        Vr[i] = V2[i];
+      }
+    }
     if (!changed) break;
   }
   for (int i = 0; i < N; i++) W[i] = S[i * N + i];

@@ -120,6 +120,14 @@ void detect_features(Mat img, vector<KeyPoint>& keypoints, Mat& descriptors) {
 // VO_utility.cpp:515-543
 void match_features(vector<KeyPoint> keypoints1, vector<KeyPoint> keypoints2, Mat descriptors1, Mat descriptors2,
                     vector<DMatch>& matches) {
+  // knnMatch on an empty query set returns no rows and the node carries on into its "TOO LOW ... ASSUMING CONSTANT
+  // MOTION" branch (visual_odometry.h:567, :626); an empty cv::Mat has type() == 0, so this comes before the asserts.
+  // Fewer than two train descriptors: the reference reads knn[i][1] out of bounds (VO_utility.cpp:536) -- no match here.
+  if (descriptors1.rows == 0 || descriptors2.rows < 2) {
+    ROS_INFO("MATCHES BEFORE LOWE'S RATIO: %d", descriptors1.rows);
+    ROS_INFO("MATCHES AFTER LOWE'S RATIO: %lu", matches.size());
+    return;
+  }
   std::vector<uvo_dmatch> m(std::max(descriptors1.rows, 1));
   int n = 0;
   CV_Assert(descriptors1.type() == CV_32F && descriptors2.type() == CV_32F && descriptors1.isContinuous() &&

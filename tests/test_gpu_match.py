@@ -60,6 +60,13 @@ def test_match_edge_cases(ctx, oracle):
     assert len(ctx.match_features(None, None, q, q[:1])) == 0          # 1 train row: reference UB, defined as no match
     k = ctx.knn_match2(q, q[:1])
     assert np.all(k["trainIdx"][:, 0] == 0) and np.all(k["trainIdx"][:, 1] == -1)
+    # an empty cv::Mat as the query set (rows == 0 and cols == 0: the descriptors the node carries after a frame that
+    # failed a gate, visual_odometry.h:592) is "no match", not UVO_ERR_UNSUPPORTED for the row length
+    import ctypes as C
+    n = C.c_int(7)
+    rc = ctx.lib.uvo_match_features(ctx.h, None, 0, q.ctypes.data_as(C.c_void_p), 10, 0, C.c_float(0.8), None,
+                                    C.byref(n))
+    assert rc == 0 and n.value == 0
 
 
 def test_match_7arg_overload_points(ctx, oracle):
