@@ -128,14 +128,56 @@ __device__ inline void epnp_qr_solve(double* A, int nr, int nc, double* b, doubl
   }
 }
 
-// One of the three beta candidates (which = 1, 2, 3: the N = 1, 2, 3 approximations), refined by 5 Gauss-Newton steps
-__device__ inline void epnp_betas_which(const double* l, const double* rho, int which, double betas[4]) {
-  const int cols1[4] = {0, 1, 3, 6}, cols23[5] = {0, 1, 2, 3, 4};
+// The three beta candidates (which = 1, 2, 3: the N = 1, 2, 3 approximations) on one warp: candidate w is solved by
+// lane w, with lanes w + 3 and w + 6 helping in the sweeps of its 6 x {4, 3, 5} least-squares SVD
+// (jacobi_sweeps_rr); each is then refined by 5 Gauss-Newton steps on its own lane.  Every lane of the warp calls;
+// lanes 0..2 receive the betas of candidates 1..3.
+struct BetaSmem {
+  double At[3][30], V[3][25], W[3][5];
+};
+
+__device__ inline void epnp_betas_warp(const double* l, const double* rho, BetaSmem& bs, int lane, double betas[4],
+                                       long long* prof = nullptr) {
+  const int cand = lane % 3, which = cand + 1;
   const int nc = which == 1 ? 4 : which == 2 ? 3 : 5;
-  double A[30], x[5];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < nc; j++) A[i * nc + j] = l[10 * i + (which == 1 ? cols1[j] : cols23[j])];
-  svd_solve6(A, 6, nc, rho, x);
+  const int cols1[4] = {0, 1, 3, 6};
+  double* At = bs.At[cand];
+  double* V = bs.V[cand];
+  double* W = bs.W[cand];
+  if (lane < 3) {
+    for (int j = 0; j < nc; j++) {
+      double sd = 0;
+      for (int i = 0; i < 6; i++) {
+        const double v = l[10 * i + (which == 1 ? cols1[j] : j)];
+        At[j * 6 + i] = v;
+        sd += v * v;
+      }
+      W[j] = sd;
+      for (int k = 0; k < nc; k++) V[j * nc + k] = (k == j) ? 1.0 : 0.0;
+    }
+  }
+  __syncwarp();
+  if (prof && lane == 2) prof[0] = clock64();
+  jacobi_sweeps_rr(At, V, W, 6, nc, lane < 9 ? lane / 3 : -1);
+  if (prof && lane == 2) prof[1] = clock64();
+  if (lane >= 3) return;
+  double x[5];
+  {  // cvSolve(CV_SVD): x = V diag(1 / w) U^T rho over the singular values above the threshold
+    double w[6], U[36], Vt[36];
+    jacobi_svd_finish<6>(At, V, W, 6, nc, w, U, Vt);
+    double thr = 0;
+    for (int i = 0; i < nc; i++) thr += w[i];
+    thr *= DBL_EPSILON * 2;
+    for (int k = 0; k < nc; k++) x[k] = 0;
+    for (int i = 0; i < nc; i++) {
+      if (w[i] <= thr) continue;
+      double sacc = 0;
+      for (int k = 0; k < 6; k++) sacc += U[k * nc + i] * rho[k];
+      sacc /= w[i];
+      for (int k = 0; k < nc; k++) x[k] += sacc * Vt[i * nc + k];
+    }
+  }
+  if (prof && lane == 2) prof[2] = clock64();
   if (which == 1) {
     if (x[0] < 0) {
       betas[0] = sqrt(-x[0]);

@@ -7,6 +7,71 @@
 
 namespace uvo {
 
+// The part of jacobi_svd after the sweeps: singular values from the column norms, descending selection sort, U = A V
+// / w with the completion rule for (numerically) zero singular values.  At (n rows of length m), V (n x n), W (n) are
+// the sweep state and may live in registers, local or shared memory.
+template <int MAXD>
+__device__ __forceinline__ void jacobi_svd_finish(double* At, double* V, double* W, int m, int n, double* w, double* U, double* Vt) {
+  for (int i = 0; i < n; i++) {
+    double sd = 0;
+    for (int k = 0; k < m; k++) sd += At[i * m + k] * At[i * m + k];
+    W[i] = sqrt(sd);
+  }
+  for (int i = 0; i < n - 1; i++) {
+    int j = i;
+    for (int k = i + 1; k < n; k++)
+      if (W[j] < W[k]) j = k;
+    if (i != j) {
+      double t = W[i];
+      W[i] = W[j];
+      W[j] = t;
+      for (int k = 0; k < m; k++) {
+        t = At[i * m + k];
+        At[i * m + k] = At[j * m + k];
+        At[j * m + k] = t;
+      }
+      for (int k = 0; k < n; k++) {
+        t = V[i * n + k];
+        V[i * n + k] = V[j * n + k];
+        V[j * n + k] = t;
+      }
+    }
+  }
+  const double minval = W[0] * DBL_EPSILON * 4 + DBL_MIN * 100;
+  for (int i = 0; i < n; i++) {
+    w[i] = W[i];
+    if (Vt)
+      for (int k = 0; k < n; k++) Vt[i * n + k] = V[i * n + k];
+    if (!U) continue;
+    if (W[i] > minval) {
+      const double s = 1 / W[i];
+      for (int k = 0; k < m; k++) U[k * n + i] = At[i * m + k] * s;
+    } else {
+      // complete U with Gram-Schmidt on the coordinate axes (arbitrary by construction; same rule as the oracle)
+      bool done = false;
+      for (int ax = 0; ax < m && !done; ax++) {
+        double v[MAXD];
+        for (int k = 0; k < m; k++) v[k] = (k == ax) ? 1.0 : 0.0;
+        for (int rep = 0; rep < 2; rep++)
+          for (int j = 0; j < i; j++) {
+            double d = 0;
+            for (int k = 0; k < m; k++) d += v[k] * U[k * n + j];
+            for (int k = 0; k < m; k++) v[k] -= d * U[k * n + j];
+          }
+        double nn = 0;
+        for (int k = 0; k < m; k++) nn += v[k] * v[k];
+        if (nn > 1e-6) {
+          nn = 1 / sqrt(nn);
+          for (int k = 0; k < m; k++) U[k * n + i] = v[k] * nn;
+          done = true;
+        }
+      }
+      if (!done)
+        for (int k = 0; k < m; k++) U[k * n + i] = 0;
+    }
+  }
+}
+
 // A: m x n row-major, m,n <= MAXD.  A = U diag(w) Vt, w descending.  U: m x n (may be null), Vt: n x n.
 // CM / CN: compile-time copies of m / n (0 = run-time).  With both known the k-loops unroll, so the loads of a pair's two
 // rows are issued back to back instead of one per trip of a serial loop; the arithmetic and its order are unchanged.
@@ -80,63 +145,77 @@ __device__ void jacobi_svd(const double* A, int m_rt, int n_rt, double* w, doubl
       }
     if (!changed) break;
   }
-  for (int i = 0; i < n; i++) {
-    double sd = 0;
-    for (int k = 0; k < m; k++) sd += At[i * m + k] * At[i * m + k];
-    W[i] = sqrt(sd);
-  }
-  for (int i = 0; i < n - 1; i++) {
-    int j = i;
-    for (int k = i + 1; k < n; k++)
-      if (W[j] < W[k]) j = k;
-    if (i != j) {
-      double t = W[i];
-      W[i] = W[j];
-      W[j] = t;
-      for (int k = 0; k < m; k++) {
-        t = At[i * m + k];
-        At[i * m + k] = At[j * m + k];
-        At[j * m + k] = t;
-      }
-      for (int k = 0; k < n; k++) {
-        t = V[i * n + k];
-        V[i * n + k] = V[j * n + k];
-        V[j * n + k] = t;
-      }
-    }
-  }
-  const double minval = W[0] * DBL_EPSILON * 4 + DBL_MIN * 100;
-  for (int i = 0; i < n; i++) {
-    w[i] = W[i];
-    if (Vt)
-      for (int k = 0; k < n; k++) Vt[i * n + k] = V[i * n + k];
-    if (!U) continue;
-    if (W[i] > minval) {
-      const double s = 1 / W[i];
-      for (int k = 0; k < m; k++) U[k * n + i] = At[i * m + k] * s;
-    } else {
-      // complete U with Gram-Schmidt on the coordinate axes (arbitrary by construction; same rule as the oracle)
-      bool done = false;
-      for (int ax = 0; ax < m && !done; ax++) {
-        double v[MAXD];
-        for (int k = 0; k < m; k++) v[k] = (k == ax) ? 1.0 : 0.0;
-        for (int rep = 0; rep < 2; rep++)
-          for (int j = 0; j < i; j++) {
-            double d = 0;
-            for (int k = 0; k < m; k++) d += v[k] * U[k * n + j];
-            for (int k = 0; k < m; k++) v[k] -= d * U[k * n + j];
+  jacobi_svd_finish<MAXD>(At, V, W, m, n, w, U, Vt);
+}
+
+// The sweeps of jacobi_svd in ROUND-ROBIN pair order (oracle/linalg.h: jacobi_svd(..., round_robin = true)) for up to
+// three small systems at once on one warp.  A lane works on the system its At / V / W pointers name; `slot` (0..2, or
+// -1 for a lane that only keeps the warp's barriers company) is the pair of the round the lane rotates.  The pairs of a
+// round touch disjoint columns, so rotating them side by side gives the bits of rotating them one after the other; a
+// sweep costs NP - 1 rotation latencies instead of n (n - 1) / 2.  A system that has converged sees no rotation pass
+// its test in the extra sweeps the slowest system of the warp still needs, so its state does not change.
+__device__ inline void jacobi_sweeps_rr(double* At, double* V, double* W, int m, int n, int slot) {
+  const double eps = DBL_EPSILON * 10;
+  const int NP = (n + 1) & ~1;
+  const int max_iter = m > 30 ? m : 30;
+  for (int iter = 0; iter < max_iter; iter++) {
+    bool changed = false;
+    for (int r = 0; r < 5; r++) {  // NP <= 6
+      if (slot >= 0 && r < NP - 1 && slot < NP / 2) {
+        const int ia = slot == 0 ? NP - 1 : (r + slot) % (NP - 1), ib = slot == 0 ? r : (r - slot + NP - 1) % (NP - 1);
+        const int i = min(ia, ib), j = max(ia, ib);
+        if (j < n) {
+          // OpenCV's rotation with the two branches of its c / s formulas folded into one expression (the factors 0.5
+          // and 2 are exact, so (g - b) 0.5 / g for b < 0 and (g + b) / (2 g) for b >= 0 are both (g + |b|) / (2 g)),
+          // gamma = sqrt(p^2 + beta^2) written out, and the convergence test evaluated beside the rotation instead of
+          // in front of it: the dependent chain is dot product, sqrt, divide, sqrt, divide.  The pair's two columns
+          // stay in registers.  (m <= 6)
+          double* Ai = At + i * m;
+          double* Aj = At + j * m;
+          double ai[6], aj[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            ai[k] = k < m ? Ai[k] : 0.0;
+            aj[k] = k < m ? Aj[k] : 0.0;
           }
-        double nn = 0;
-        for (int k = 0; k < m; k++) nn += v[k] * v[k];
-        if (nn > 1e-6) {
-          nn = 1 / sqrt(nn);
-          for (int k = 0; k < m; k++) U[k * n + i] = v[k] * nn;
-          done = true;
+          double a = W[i], b = W[j], p = 0;
+#pragma unroll
+          for (int k = 0; k < 6; k++)
+            if (k < m) p += ai[k] * aj[k];
+          const bool rot = !(fabs(p) <= eps * sqrt(a * b));
+          p *= 2;
+          const double beta = a - b, gamma = sqrt(p * p + beta * beta);
+          const double r1 = sqrt((gamma + fabs(beta)) / (gamma * 2)), r2 = p / (gamma * r1 * 2);
+          const double c = beta < 0 ? r2 : r1, s = beta < 0 ? r1 : r2;
+          if (rot) {
+            a = b = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              if (k < m) {
+                const double t0 = c * ai[k] + s * aj[k];
+                const double t1 = -s * ai[k] + c * aj[k];
+                Ai[k] = t0;
+                Aj[k] = t1;
+                a += t0 * t0;
+                b += t1 * t1;
+              }
+            W[i] = a;
+            W[j] = b;
+            changed = true;
+            double* Vi = V + i * n;
+            double* Vj = V + j * n;
+            for (int k = 0; k < n; k++) {
+              const double t0 = c * Vi[k] + s * Vj[k];
+              const double t1 = -s * Vi[k] + c * Vj[k];
+              Vi[k] = t0;
+              Vj[k] = t1;
+            }
+          }
         }
       }
-      if (!done)
-        for (int k = 0; k < m; k++) U[k * n + i] = 0;
+      __syncwarp();
     }
+    if (!__any_sync(0xffffffffu, changed)) break;
   }
 }
 
@@ -346,7 +425,7 @@ __device__ void jacobi_eigh_rr(double* S, double* Vr, double* w, double* Vt, dou
   sync();
 }
 
-// least-squares / pseudo-inverse solve via SVD (cvSolve CV_SVD); m <= 6, n <= 6
+// least-squares / pseudo-inverse solve via SVD (cvSolve CV_SVD); m <= 6, n <= 6 (one thread, cyclic pair order)
 __device__ inline void svd_solve6(const double* A, int m, int n, const double* b, double* x) {
   double w[6], U[36], Vt[36];
   jacobi_svd<6>(A, m, n, w, U, Vt);

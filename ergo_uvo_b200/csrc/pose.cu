@@ -221,57 +221,85 @@ __device__ __forceinline__ void pnp_prof(const PnpArgs& a, int slot) {
   if (a.prof) a.prof[slot] = clock64();
 }
 
-// getSubset stream for all iterations (one warp).  Lane l speculatively takes draws [p+5l, p+5l+5); a subset with a
-// repeated index is rebuilt sequentially by lane 0 with OpenCV's redraw rule and the stream position re-aligned.
-__device__ void pnp_subsets_warp(const PnpArgs& a, const uint32_t* __restrict__ rng, int n, int lane) {
+// getSubset stream for all iterations (one block; the draws are made by its first warp).  The fixed RNG table is
+// staged through a shared-memory window by the whole block, so a draw costs a shared-memory read instead of an L2
+// round trip.  Lane l speculatively takes draws [p+5l, p+5l+5); a subset with a repeated index is rebuilt
+// sequentially by lane 0 with OpenCV's redraw rule and the stream position re-aligned.
+constexpr int RNG_WINDOW = 4096;  // words; one warp step consumes 160 + the redraws of one subset
+
+__device__ void pnp_subsets_block(const PnpArgs& a, const uint32_t* __restrict__ rng, int n) {
+  __shared__ uint32_t s_rng[RNG_WINDOW];
+  __shared__ int s_ps[2];
   const int iters = max(a.iterations, 1);
+  const int lane = threadIdx.x;
   if (n < 5) return;
   if (n == 5) {
     if (lane < 5) a.subsets[lane] = lane;
     return;
   }
-  int p = 0, s = 0;
-  while (s < iters) {
-    int idx[5];
-    bool dup = false;
-    const int q = p + 5 * lane;
-    const bool in_range = (s + lane < iters) && (q + 5 <= RNG_TABLE_SIZE);
-    if (in_range) {
+  int p = 0, s = 0;  // stream position, subsets done (block-uniform at the top of the loop)
+  while (s < iters && p + 5 <= RNG_TABLE_SIZE) {
+    const int w0 = p;
+    for (int i = threadIdx.x; i < RNG_WINDOW; i += blockDim.x) s_rng[i] = rng[min(w0 + i, RNG_TABLE_SIZE - 1)];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // one step needs at most 160 draws for the speculation and a handful for a sequential rebuild
+      while (s < iters && p + 256 <= w0 + RNG_WINDOW) {
+        int idx[5];
+        bool dup = false;
+        const int q = p + 5 * lane;
+        const bool in_range = (s + lane < iters) && (q + 5 <= RNG_TABLE_SIZE);
+        if (in_range) {
 #pragma unroll
-      for (int k = 0; k < 5; k++) idx[k] = (int)(rng[q + k] % (unsigned)n);
+          for (int k = 0; k < 5; k++) idx[k] = (int)(s_rng[q + k - w0] % (unsigned)n);
 #pragma unroll
-      for (int k = 1; k < 5; k++)
+          for (int k = 1; k < 5; k++)
 #pragma unroll
-        for (int j = 0; j < k; j++) dup |= (idx[k] == idx[j]);
-    }
-    const unsigned bad = __ballot_sync(0xffffffffu, in_range && dup);
-    const unsigned act = __ballot_sync(0xffffffffu, in_range);
-    const int n_act = __popc(act);
-    if (n_act == 0) break;  // RNG table exhausted (cannot happen for iterations*5*redraws < 2^18)
-    const int first_bad = bad ? (__ffs(bad) - 1) : n_act;
-    if (in_range && lane < first_bad)
-      for (int k = 0; k < 5; k++) a.subsets[(size_t)(s + lane) * 5 + k] = idx[k];
-    s += first_bad;
-    p += 5 * first_bad;
-    if (bad) {
-      if (lane == 0) {
-        int sub[5];
-        for (int i = 0; i < 5; i++) {
-          int v;
-          for (;;) {
-            v = (int)(rng[min(p, RNG_TABLE_SIZE - 1)] % (unsigned)n);
-            p++;
-            bool d2 = false;
-            for (int k = 0; k < i; k++) d2 |= (sub[k] == v);
-            if (!d2) break;
-          }
-          sub[i] = v;
+            for (int j = 0; j < k; j++) dup |= (idx[k] == idx[j]);
         }
-        for (int k = 0; k < 5; k++) a.subsets[(size_t)s * 5 + k] = sub[k];
+        const unsigned bad = __ballot_sync(0xffffffffu, in_range && dup);
+        const unsigned act = __ballot_sync(0xffffffffu, in_range);
+        const int n_act = __popc(act);
+        if (n_act == 0) {  // RNG table exhausted (cannot happen for iterations * 8 < 2^18)
+          s = iters;
+          break;
+        }
+        const int first_bad = bad ? (__ffs(bad) - 1) : n_act;
+        if (in_range && lane < first_bad)
+          for (int k = 0; k < 5; k++) a.subsets[(size_t)(s + lane) * 5 + k] = idx[k];
+        s += first_bad;
+        p += 5 * first_bad;
+        if (bad) {
+          if (lane == 0) {
+            int sub[5];
+            for (int i = 0; i < 5; i++) {
+              int v;
+              for (;;) {
+                const int pp = min(p, RNG_TABLE_SIZE - 1);
+                const uint32_t rv = (pp - w0 < RNG_WINDOW) ? s_rng[pp - w0] : rng[pp];
+                v = (int)(rv % (unsigned)n);
+                p++;
+                bool d2 = false;
+                for (int k = 0; k < i; k++) d2 |= (sub[k] == v);
+                if (!d2) break;
+              }
+              sub[i] = v;
+            }
+            for (int k = 0; k < 5; k++) a.subsets[(size_t)s * 5 + k] = sub[k];
+          }
+          p = __shfl_sync(0xffffffffu, p, 0);
+          s += 1;
+        }
       }
-      p = __shfl_sync(0xffffffffu, p, 0);
-      s += 1;
+      if (lane == 0) {
+        s_ps[0] = p;
+        s_ps[1] = s;
+      }
     }
+    __syncthreads();
+    p = s_ps[0];
+    s = s_ps[1];
+    __syncthreads();
   }
 }
 
@@ -281,7 +309,7 @@ __global__ void __launch_bounds__(256) k_pnp_prepare(const __grid_constant__ Pnp
                                                      const uint32_t* __restrict__ rng) {
   const int n = pnp_n(a);
   if (blockIdx.x == gridDim.x - 1) {
-    if (threadIdx.x < 32) pnp_subsets_warp(a, rng, n, threadIdx.x);
+    pnp_subsets_block(a, rng, n);
     if (threadIdx.x == 32) {
       PnpState* st = a.state;
       st->niters = (n == 5) ? 1 : max(a.iterations, 1);
@@ -343,6 +371,7 @@ __device__ inline int ransac_update_num_iters(double p, double ep, int model_poi
 // latency, not bits.
 struct HypSmem {
   double S[2 * 144], Vr[2 * 144], ut[144], w[12], l[60], rho[6], al[5][4], us[10], rot[24], model[15];
+  BetaSmem beta;
   unsigned rflag[2];
   int cnt[4];
 };
@@ -399,10 +428,9 @@ __device__ void pnp_hypothesis(const PnpArgs& a, int h, HypSmem& sm, int tid, bo
     if (lane < 6) epnp_L_row(sm.ut, lane, sm.l + 10 * lane);
     else if (lane < 12) sm.rho[lane - 6] = epnp_rho_entry(cws, lane - 6);
     __syncwarp();
-    double err = 0, Rw[9], tw[3];
+    double err = 0, Rw[9], tw[3], betas[4];
+    epnp_betas_warp(sm.l, sm.rho, sm.beta, lane, betas, prof ? a.prof + 24 : nullptr);
     if (lane < 3) {
-      double betas[4];
-      epnp_betas_which(sm.l, sm.rho, lane + 1, betas);
       if (prof && lane == 2) pnp_prof(a, 5);
       err = epnp_candidate(pws, us, 5, sm.al, betas, sm.ut, cam, Rw, tw);
       if (prof && lane == 2) pnp_prof(a, 6);
@@ -456,6 +484,7 @@ __global__ void __launch_bounds__(CHUNK_THREADS) k_pnp_chunk(const __grid_consta
     pnp_hypothesis<NT>(a, h, sm, tid, prof);
     const float thr = (float)((double)a.reproj_err * (double)a.reproj_err);
     int cnt = 0;
+#pragma unroll 4
     for (int i = tid; i < n; i += NT) cnt += pnp_is_inlier(sm.model, a.Xf, a.xs, i, a.K, thr) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
@@ -529,6 +558,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
   __shared__ double s_red[8 * 40], s_out[40];
   __shared__ double s_cws[4][3], s_ci[9], s_ut[144], s_betas[3][4], s_ccs3[3][4][3], s_R3[3][9], s_t3[3][3], s_sign3[3];
   __shared__ double s_mtm[2 * 144], s_Vr[2 * 144], s_w[12], s_l[60], s_rho[6], s_rot[24];
+  __shared__ BetaSmem s_beta;
   __shared__ unsigned s_rflag[2];
   __shared__ unsigned s_mask[REFIT_MAX_WORDS];
   __shared__ int s_off[REFIT_MAX_WORDS];
@@ -560,6 +590,7 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
   // ascending inlier list: one ballot per 32 consecutive points, an exclusive scan of the popcounts by warp 0, then
   // every warp writes its words' inliers in place
   const int words = (n + 31) >> 5;
+#pragma unroll 4
   for (int wd = wid; wd < words; wd += REFIT_THREADS / 32) {
     const int i = 32 * wd + lane;
     const unsigned b = __ballot_sync(0xffffffffu, i < n && pnp_is_inlier(m, a.Xf, a.xs, i, a.K, thr));
@@ -679,7 +710,10 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     if (tid < 6) epnp_L_row(s_ut, tid, s_l + 10 * tid);
     else if (tid < 12) s_rho[tid - 6] = epnp_rho_entry(s_cws, tid - 6);
     __syncwarp();
-    if (tid < 3) epnp_betas_which(s_l, s_rho, tid + 1, s_betas[tid]);
+    double betas[4];
+    epnp_betas_warp(s_l, s_rho, s_beta, tid, betas);
+    if (tid < 3)
+      for (int i = 0; i < 4; i++) s_betas[tid][i] = betas[i];
   }
   __syncthreads();
   if (a.prof && tid == 0) pnp_prof(a, 21);

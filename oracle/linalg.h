@@ -5,13 +5,18 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <utility>
 #include <vector>
 
 namespace orc {
 
 // A: m x n row-major (m >= n not required).  Computes A = U diag(w) Vt with w descending.
 // U: m x n (thin, columns = left singular vectors), Vt: n x n.  Works on the transpose like OpenCV.
-inline void jacobi_svd(const double* A, int m, int n, double* w, double* U, double* Vt) {
+// round_robin = false: OpenCV's cyclic pair order (i, j), i < j.  round_robin = true: the circle-method order of
+// jacobi_eigh below -- rounds of index-disjoint column pairs over NP = n rounded up to even (a pair with the padding
+// index is skipped); the pairs of a round touch disjoint columns, so the GPU rotates them side by side
+// (csrc/linalg.cuh: jacobi_sweeps_rr) and obtains the same bits.  Used for EPnP's 6 x {3, 4, 5} beta systems only.
+inline void jacobi_svd(const double* A, int m, int n, double* w, double* U, double* Vt, bool round_robin = false) {
   // At: n rows of length m (columns of A)
   std::vector<double> At((size_t)n * m), V((size_t)n * n, 0.0), W(n);
   for (int i = 0; i < n; i++)
@@ -24,24 +29,49 @@ inline void jacobi_svd(const double* A, int m, int n, double* w, double* U, doub
   }
   const double eps = DBL_EPSILON * 10;
   const int max_iter = std::max(m, 30);
+  // the pair list of one sweep
+  std::vector<std::pair<int, int>> order;
+  if (!round_robin) {
+    for (int i = 0; i < n - 1; i++)
+      for (int j = i + 1; j < n; j++) order.emplace_back(i, j);
+  } else {
+    const int NP = (n + 1) & ~1;
+    for (int r = 0; r < NP - 1; r++)
+      for (int k = 0; k < NP / 2; k++) {
+        const int a = k == 0 ? NP - 1 : (r + k) % (NP - 1), b = k == 0 ? r : (r - k + NP - 1) % (NP - 1);
+        const int i = std::min(a, b), j = std::max(a, b);
+        if (j < n) order.emplace_back(i, j);
+      }
+  }
   for (int iter = 0; iter < max_iter; iter++) {
     bool changed = false;
-    for (int i = 0; i < n - 1; i++)
-      for (int j = i + 1; j < n; j++) {
+    for (const auto& pr : order) {
+        const int i = pr.first, j = pr.second;
         double* Ai = &At[(size_t)i * m];
         double* Aj = &At[(size_t)j * m];
         double a = W[i], p = 0, b = W[j];
         for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
         if (std::abs(p) <= eps * std::sqrt(a * b)) continue;
         p *= 2;
-        double beta = a - b, gamma = std::hypot(p, beta), c, s;
-        if (beta < 0) {
-          double delta = (gamma - beta) * 0.5;
-          s = std::sqrt(delta / gamma);
-          c = p / (gamma * s * 2);
+        double beta = a - b, c, s;
+        if (round_robin) {
+          // the same rotation with gamma = sqrt(p^2 + beta^2) written out and the two branches folded into one
+          // expression (0.5 and 2 are exact factors: (g - b) 0.5 / g = (g + |b|) / (2 g) for b < 0) -- the form the
+          // GPU evaluates without a branch, kept identical here so that the two agree bit for bit
+          const double gamma = std::sqrt(p * p + beta * beta);
+          const double r1 = std::sqrt((gamma + std::fabs(beta)) / (gamma * 2)), r2 = p / (gamma * r1 * 2);
+          c = beta < 0 ? r2 : r1;
+          s = beta < 0 ? r1 : r2;
         } else {
-          c = std::sqrt((gamma + beta) / (gamma * 2));
-          s = p / (gamma * c * 2);
+          const double gamma = std::hypot(p, beta);
+          if (beta < 0) {
+            double delta = (gamma - beta) * 0.5;
+            s = std::sqrt(delta / gamma);
+            c = p / (gamma * s * 2);
+          } else {
+            c = std::sqrt((gamma + beta) / (gamma * 2));
+            s = p / (gamma * c * 2);
+          }
         }
         a = b = 0;
         for (int k = 0; k < m; k++) {
@@ -250,9 +280,9 @@ inline void jacobi_eigh(const double* A, double* w, double* Vt) {
 }
 
 // least-squares / pseudo-inverse solve of A x = b via SVD (cvSolve(..., CV_SVD)); A m x n, b m, x n
-inline void svd_solve(const double* A, int m, int n, const double* b, double* x) {
+inline void svd_solve(const double* A, int m, int n, const double* b, double* x, bool round_robin = false) {
   std::vector<double> w(n), U((size_t)m * n), Vt((size_t)n * n);
-  jacobi_svd(A, m, n, w.data(), U.data(), Vt.data());
+  jacobi_svd(A, m, n, w.data(), U.data(), Vt.data(), round_robin);
   double thr = 0;
   for (int i = 0; i < n; i++) thr += w[i];
   thr *= DBL_EPSILON * 2;

@@ -302,7 +302,7 @@ struct Epnp {
     double A[6 * 5], x[5];
     for (int i = 0; i < 6; i++)
       for (int j = 0; j < nc; j++) A[i * nc + j] = l[10 * i + cols[j]];
-    svd_solve(A, 6, nc, rho, x);
+    svd_solve(A, 6, nc, rho, x, /*round_robin=*/true);
     if (which == 1) {
       if (x[0] < 0) {
         betas[0] = std::sqrt(-x[0]);

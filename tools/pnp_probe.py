@@ -56,6 +56,10 @@ def main():
     if st[13]:
         out["eigh_breakdown_cycles_per_round"] = {"rotation": round(st[10] / st[13]), "apply": round(st[11] / st[13]),
                                                   "write": round(st[12] / st[13]), "rounds": int(st[13])}
+    if st[24]:
+        out["betas_breakdown_us"] = {"L_rho_init": round((st[24] - st[4]) / clk, 2), "sweeps": round((st[25] - st[24]) / clk, 2),
+                                     "finish+solve": round((st[26] - st[25]) / clk, 2),
+                                     "gauss_newton": round((st[5] - st[26]) / clk, 2)}
     out["stage_us_sum"] = round(sum(out["kernels_us"].values()), 2)
     print(json.dumps(out))
     ctx.close()
