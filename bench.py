@@ -4,13 +4,18 @@
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (the CPU path -- the oracle port -- on the host cores)
+  python bench.py --config E ...                           (BASELINE config[4]: 2448x2048, one sequence per GPU)
 
 A step = one stereo frame through the whole hot path (get_image x2 -> SURF x2 -> stereo match -> temporal match ->
 triangulate -> extract_3Dpoints -> solvePnPRansac -> velocity).
   value : frames/s with the input images already resident in HBM (device-resident ring larger than L2), frames
           enqueued asynchronously through the C ABI, timed with CUDA events on the library's stream.
-  e2e   : frames/s through the reference-facing call uvo_stereo_frame with HOST (pinned) images: H2D of both images
-          and D2H of the result record inside the timed region, one synchronous call per frame.
+  e2e   : frames/s through the reference-facing host-buffer call (uvo_stereo_enqueue_host + uvo_stereo_collect) with
+          HOST (pinned) images: H2D of both images and D2H of the result record inside the timed region.
+Both are the MEDIAN of --regions (9) consecutive timed regions of exactly K frames, each bracketed by barrier +
+synchronize, max over ranks per region; `timing` carries every region and one long steady-state region.
+  roofline : the top kernel by time per frame over ALL kernels (each timed alone with CUDA events); HBM, tensor or --
+          for the fp64 pose kernels -- the FP64-issue bound measured live by tools/probes/fp64_probe.
 Multi-GPU: VO is sequential within a stream, so ranks run independent sequences (seed 1300+rank) -- replicas,
 no collective on the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time.
 """
@@ -27,10 +32,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 1280, 1024
 TARGET_KP = 4096
-N_DISTINCT = 8       # rendered stereo pairs; the sequence ping-pongs through them (0..7,6..1,0..)
-RING = 28            # device-resident pairs (2 ping-pong cycles, 220 MB > 126 MB L2)
+# BASELINE.json configs: B = configs[1] (the configuration the metric is quoted on, the default and the headline),
+# E = configs[4] (2448x2048, one sequence per GPU; run it at N = 1, 2, 4, 8 with --config E).
+#   n_distinct: rendered stereo pairs, the sequence ping-pongs through them (0..n-1, n-2..1, 0..)
+#   ring: device-resident pairs (whole ping-pong cycles, larger than the 126 MB L2)
+CONFIGS = {
+    "B": dict(w=1280, h=1024, n_distinct=8, ring=28,
+              workload="stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML "
+                       "(BASELINE config[1]); one independent sequence per GPU"),
+    "E": dict(w=2448, h=2048, n_distinct=4, ring=12,
+              workload="stereo UVO 2448x2048, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML "
+                       "(BASELINE config[4]); one independent sequence per GPU"),
+}
+REGIONS = 9          # consecutive timed regions of `steps` frames each; the median region is the reported one
 
 
 def pingpong(i, n):
@@ -103,9 +118,26 @@ def load_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def make_sequence(seed, n_frames=N_DISTINCT):
+def make_sequence(seed, cfg, n_frames=None):
     from tools import synth
-    return synth.StereoSequence(W, H, n_frames=n_frames, seed=seed, tex_size=2048)
+    return synth.StereoSequence(cfg["w"], cfg["h"], n_frames=n_frames or cfg["n_distinct"], seed=seed, tex_size=2048)
+
+
+def fp64_peak():
+    """FP64-issue roofline of the pose kernels: sustained DFMA rate of this GPU, measured live by
+    tools/probes/fp64_probe (built by __graft_entry__.build()); the committed round-2 measurement otherwise."""
+    exe = os.path.join(ROOT, "tools", "probes", "fp64_probe")
+    try:
+        d = json.loads(subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout)
+        return float(d["dfma_tflops"]), "measured live (tools/probes/fp64_probe: dependent DFMA %.1f cycles)" % \
+            d["latency_cycles"]["dfma"]
+    except Exception:
+        pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "fp64_probe_r02.json")))
+        return float(d["dfma_tflops"]), "profiles/fp64_probe_r02.json"
+    except Exception:
+        return 37.0, "fallback (B200 FP64 nominal)"
 
 
 def pick_threshold(ctx, U, seq):
@@ -219,7 +251,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    seq = make_sequence(1300, n_frames=4)
+    cfg = CONFIGS[args.config]
+    seq = make_sequence(1300, cfg, n_frames=4)
     thr = args.threshold or pick_threshold_cpu(seq)
     cores = min(16, os.cpu_count() or 1)
     for _ in range(max(args.warmup, 0)):
@@ -231,8 +264,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spf * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
         "data": "synthetic",
-        "config": {"workload": "stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML",
-                   "surf_min_hessian": thr},
+        "config": {"workload": cfg["workload"], "width": cfg["w"], "height": cfg["h"], "surf_min_hessian": thr},
+        # one CPU process runs ONE sequence whatever --gpus says (the contract: rank 0 alone runs the reference arm);
+        # a ratio against an N-GPU line compares N sequences with this one
+        "n_sequences": 1,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} consecutive stereo frames of the same synthetic sequence through the "
                                    "oracle port of the OpenCV CPU path (SURF restated, not OpenCV)",
@@ -246,11 +281,37 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+def kernel_models(P, n_kp, n3d, iters):
+    """ALGORITHMIC bytes / flops per launch of each kernel: name -> (bound, amount).
+    hbm: bytes; tensor: flops of the TF32 contraction; fp64: double-precision flops (FP64-issue roofline)."""
+    # EPnP on a minimal set, counted from the code: 12x12 round-robin Jacobi ~60 rounds x (78 x 13 + 144 x 3 + 6 x 60)
+    # ~ 1.1e5, three beta systems + Gauss-Newton ~ 2.5e4, small SVDs / Rodrigues ~ 1e4
+    f_epnp = 1.45e5
+    f_score = 32.0  # SURVEY 8d: PnP reprojection, flops per (hypothesis, correspondence)
+    m = {
+        # one launch covers both images of the pair (blockIdx.z = image)
+        "k_gray_undistort": ("hbm", 2 * 4.0 * P), "k_clahe_hist": ("hbm", 2 * 1.0 * P),
+        "k_clahe_apply": ("hbm", 2 * 2.0 * P), "k_integral_rows": ("hbm", 2 * 5.0 * P),
+        "k_integral_cols": ("hbm", 2 * 8.0 * P),
+        "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_patch": ("hbm", 2 * n_kp * (40 * 40 + 256)),
+        "k_surf_vector": ("hbm", 2 * n_kp * (441 + 256)),
+        "k_knn_tc": ("tensor", 2.0 * n_kp * n_kp * 64),
+        "k_triangulate": ("fp64", n3d * 2000.0),                      # SURVEY 8d: 4x4 SVD ~ 2 kflop per point
+        "k_pnp_chunk[0:32]": ("fp64", 32 * (n3d * f_score + f_epnp)),
+        # refit: inlier test over all points + one EPnP on the inliers (40 sums + 3 x (9 + 27 + 3) sums per point)
+        "k_pnp_finalize": ("fp64", n3d * (f_score + 2 * 40 + 3 * 2 * 39 + 60) + f_epnp),
+    }
+    return m
+
+
 def run_gpu(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import ergo_uvo_b200 as U
 
+    cfg = CONFIGS[args.config]
+    W, H, N_DISTINCT, RING = cfg["w"], cfg["h"], cfg["n_distinct"], cfg["ring"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -269,7 +330,7 @@ def run_gpu(args):
     stream = torch.cuda.Stream(device=local)
     ctx = U.Context(local, stream=stream.cuda_stream)
 
-    seq = make_sequence(sequence_seed(rank))
+    seq = make_sequence(sequence_seed(rank), cfg)
     if args.threshold:
         thr, n0 = args.threshold, -1
     else:
@@ -280,6 +341,7 @@ def run_gpu(args):
     camL = U.make_camera(seq.KL, seq.DL, seq.newKL)
     camR = U.make_camera(seq.KR, seq.DR, seq.newKR)
     vo = U.StereoVO(ctx, W, H, camL, camR, seq.R_right, seq.t_right, p)
+    vo.set_graphs(args.graphs)
 
     # device ring (inputs resident in HBM, larger than L2) and pinned host ring
     pitch = 3 * W
@@ -296,10 +358,10 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_enqueue_s = [0.0, 0]  # host time inside the enqueue call (kernel launches, copies, event waits), calls
+    host_enqueue_s = [0.0, 0]  # host time inside the enqueue call (launches, copies, event waits), calls; timed regions
 
-    def run_device(n, start, inflight=inflight, ring=None, host=False):
-        ring = ring or dev_ring
+    def run_frames(n, start, inflight=inflight, host=False, count_host_time=False):
+        ring = host_ring if host else dev_ring
         enq = vo.enqueue_host if host else vo.enqueue_device
         valid = 0
         q = 0
@@ -307,8 +369,9 @@ def run_gpu(args):
             L, R = ring[(start + i) % RING]
             t_enq = time.perf_counter()
             enq(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
-            host_enqueue_s[0] += time.perf_counter() - t_enq
-            host_enqueue_s[1] += 1
+            if count_host_time:
+                host_enqueue_s[0] += time.perf_counter() - t_enq
+                host_enqueue_s[1] += 1
             q += 1
             if q >= inflight:
                 valid += vo.collect().valid
@@ -318,143 +381,149 @@ def run_gpu(args):
             q -= 1
         return valid
 
-    def run_host(n, start):
-        return run_device(n, start, ring=host_ring, host=True)
-
     def run_host_sync(n, start):
         valid = 0
         for i in range(n):
             L, R = host_ring[(start + i) % RING]
-            res = vo.lib  # noqa: F841
             r = U.StereoResult()
-            import ctypes as C
             rc = vo.lib.uvo_stereo_frame(vo.h, C.c_void_p(L.data_ptr()), C.c_void_p(R.data_ptr()), C.c_size_t(pitch),
                                          C.c_double(dt_frame), C.byref(r))
             ctx._ck(rc)
             valid += r.valid
         return valid
 
-    # ---- device-resident throughput (value)
-    pos = 0
-    run_device(max(args.warmup, 3), pos)
-    pos += max(args.warmup, 3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pos = [0]
+
+    def timed_region(n, host, count_host_time=False):
+        """EXACTLY n frames between barrier + synchronize on both sides; CUDA events on the library's stream (wall clock
+        as a floor for the host-buffer path, whose copies run on the library's own copy stream)"""
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            valid = run_frames(n, pos[0], host=host, count_host_time=count_host_time)
+            e1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        pos[0] += n
+        return (max(ms, wall) if host else ms), valid
+
+    # ---- device-resident throughput (value): REGIONS consecutive regions of `steps` frames, the median is reported
+    n_warm = max(args.warmup, 3)
+    run_frames(max(n_warm, 16), pos[0])  # >= 16: every lane has run a frame directly and captured its graphs
+    pos[0] += max(n_warm, 16)
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
     sampler.start()
-    barrier()
-    launches0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        valid_dev = run_device(args.steps, pos)
-        e1.record(stream)
-    barrier()
+    launches0, graphs0 = ctx.launches, vo.graph_launches
+    dev_regions, valid_dev = [], 0
+    for _ in range(args.regions):
+        ms, v_ = timed_region(args.steps, host=False, count_host_time=True)
+        dev_regions.append(ms)
+        valid_dev += v_
     launches = ctx.launches - launches0
-    ms_dev = e0.elapsed_time(e1)
-    pos += args.steps
+    graph_launches = vo.graph_launches - graphs0
 
     # ---- end-to-end through the host-buffer call (e2e)
     n_warm_host = max(args.warmup, 16)  # every staging slot of the library's ring is allocated and touched once
-    run_host(n_warm_host, pos)
-    pos += n_warm_host
-    barrier()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        valid_host = run_host(args.steps, pos)
-        e1.record(stream)
-    barrier()
-    ms_host = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    pos += args.steps
+    run_frames(n_warm_host, pos[0], host=True)
+    pos[0] += n_warm_host
+    host_regions, valid_host = [], 0
+    for _ in range(args.regions):
+        ms, v_ = timed_region(args.steps, host=True)
+        host_regions.append(ms)
+        valid_host += v_
+    # ---- steady state: one long region each (pipeline fill / drain amortised), reported beside the contract's numbers
+    n_long = max(10 * args.steps, 200)
+    ms_long_dev, _ = timed_region(n_long, host=False)
+    ms_long_host, _ = timed_region(n_long, host=True)
     # synchronous per-frame latency through uvo_stereo_frame (one frame in flight, H2D + D2H inside)
     n_sync = min(args.steps, 30)
-    run_host_sync(2, pos)
+    run_host_sync(2, pos[0])
     t0 = time.perf_counter()
-    run_host_sync(n_sync, pos + 2)
+    run_host_sync(n_sync, pos[0] + 2)
     sync_ms = (time.perf_counter() - t0) * 1e3 / n_sync
-    pos += n_sync + 2
+    pos[0] += n_sync + 2
     stop.set()
     sampler.join(timeout=3)
 
     # ---- per-kernel CUDA-event timing (roofline leg): same workload, events around every launch
     kern = {}
     stage = {}
+    n3d = 0
     if rank == 0:
         ctx.kernel_timing(True)
-        n_prof = min(args.steps, 50)
-        run_device(n_prof, pos, inflight=1)   # one frame at a time: every kernel is timed running alone
+        n_prof = min(max(args.steps, 20), 50)
+        run_frames(n_prof, pos[0], inflight=1)   # one frame at a time: every kernel is timed running alone
         rep = ctx.kernel_report()
         ctx.kernel_timing(False)
         kern = {k: {"launches_per_frame": c / n_prof, "ms_per_frame": ms / n_prof, "us_per_launch": 1e3 * ms / c}
                 for k, (c, ms) in rep.items()}
-        L, R = dev_ring[(pos + n_prof) % RING]
-        vo.frame_device(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
+        L, R = dev_ring[(pos[0] + n_prof) % RING]
+        r_last = vo.frame_device(L.data_ptr(), R.data_ptr(), pitch, dt_frame)
+        n3d = int(r_last.n_3d)
         stage = vo.stage_ms()
-    res_last = None
     kl, _ = vo.last_keypoints(False)
     kr, _ = vo.last_keypoints(True)
 
-    # ---- max over ranks
-    (ms_dev, ms_host), v = aggregate_over_ranks(dist if world > 1 else None, [ms_dev, ms_host],
-                                                [float(valid_dev), float(valid_host)], "cuda")
+    # ---- max over ranks (per region), then the median region
+    all_ms, v = aggregate_over_ranks(dist if world > 1 else None, dev_regions + host_regions + [ms_long_dev, ms_long_host],
+                                     [float(valid_dev), float(valid_host)], "cuda")
+    R_ = args.regions
+    dev_regions, host_regions = all_ms[:R_], all_ms[R_:2 * R_]
+    ms_long_dev, ms_long_host = all_ms[2 * R_], all_ms[2 * R_ + 1]
+    ms_dev, ms_host = float(np.median(dev_regions)), float(np.median(host_regions))
     total_frames = args.steps * world
     value = total_frames / (ms_dev * 1e-3)
     e2e = total_frames / (ms_host * 1e-3)
 
     if rank == 0:
         hbm, tf_burst, tf_sus, which = load_peaks()
+        f64_peak, f64_src = fp64_peak()
         n_kp = (len(kl) + len(kr)) / 2.0
         P = W * H
-        # algorithmic bytes / flops per launch of each kernel (DESIGN.md "Kernels")
-        algo = {
-            # one launch covers both images of the pair (blockIdx.z = image)
-            "k_gray_undistort": ("hbm", 2 * 4.0 * P), "k_clahe_hist": ("hbm", 2 * 1.0 * P),
-            "k_clahe_apply": ("hbm", 2 * 2.0 * P), "k_integral_rows": ("hbm", 2 * 5.0 * P),
-            "k_integral_cols": ("hbm", 2 * 8.0 * P),
-            "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_patch": ("hbm", 2 * n_kp * (40 * 40 + 256)),
-            "k_knn_tc": ("tensor", 2.0 * n_kp * n_kp * 64),
-        }
+        algo = kernel_models(P, n_kp, n3d, p.iterations_count)
         # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this same command
         # (profiles/ncu_traffic.json, written by tools/ncu_summary.py); null when the kernel was not captured
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
-        roof = None
-        top_overall = max(kern.items(), key=lambda kv: kv[1]["ms_per_frame"])[0] if kern else None
-        cands = {k: v for k, v in kern.items() if k in algo}
-        if cands:
-            # dominant kernel among those SURVEY 8d gives an algorithmic bytes/flops figure for (front end + matcher);
-            # the pose kernels are small fp64 algebra with no HBM or tensor roofline
-            top = max(cands.items(), key=lambda kv: kv[1]["ms_per_frame"])
-            name, kt = top
-            bound, per_launch = algo.get(name, ("hbm", None))
-            if per_launch is not None:
-                sec = kt["us_per_launch"] * 1e-6
-                if bound == "hbm":
-                    ach = per_launch / sec / 1e9
-                    roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                            "frac": ach / hbm, "traffic": traffic.get(name), "peak_source": which,
-                            "algorithmic_bytes_per_launch": per_launch, "us_per_launch": kt["us_per_launch"]}
-                else:
-                    ach = per_launch / sec / 1e12
-                    roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
-                            "frac": ach / tf_sus, "traffic": traffic.get(name), "peak_source": which + " (sustained bf16)",
-                            "algorithmic_flops_per_launch": per_launch, "us_per_launch": kt["us_per_launch"],
-                            "note": "tcgen05 kind::tf32 (nominal dense peak is half of bf16's); peak quoted is the "
-                                    "measured bf16 figure as the profiling recipe prescribes"}
-        rooflines = {}
-        for name, kt in kern.items():
+
+        def roof_of(name, kt):
             if name not in algo:
-                continue
+                return None
             bound, per_launch = algo[name]
             sec = kt["us_per_launch"] * 1e-6
             if bound == "hbm":
-                rooflines[name] = {"bound": "hbm", "achieved_GBps": per_launch / sec / 1e9,
-                                   "frac": per_launch / sec / 1e9 / hbm}
+                ach, peak, unit, src = per_launch / sec / 1e9, hbm, "GB/s", which
+            elif bound == "tensor":
+                ach, peak, unit, src = per_launch / sec / 1e12, tf_sus, "TFLOP/s", which + " (sustained bf16)"
             else:
-                rooflines[name] = {"bound": "tensor", "achieved_TFLOPps": per_launch / sec / 1e12,
-                                   "frac": per_launch / sec / 1e12 / tf_sus}
+                ach, peak, unit, src = per_launch / sec / 1e12, f64_peak, "TFLOP/s", f64_src
+            r = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                 "traffic": traffic.get(name.split("[")[0]), "peak_source": src, "us_per_launch": kt["us_per_launch"],
+                 ("algorithmic_bytes_per_launch" if bound == "hbm" else "algorithmic_flops_per_launch"): per_launch}
+            if bound == "tensor":
+                r["note"] = ("tcgen05 kind::tf32 (nominal dense peak is half of bf16's); peak quoted is the measured "
+                             "bf16 figure as the profiling recipe prescribes")
+            if bound == "fp64":
+                r["note"] = ("FP64-issue roofline: sustained DFMA rate of the chip; the kernel is one dependent chain "
+                             "per hypothesis (Jacobi rotations: sqrt, sqrt, reciprocal), so it is bound by the 8-cycle "
+                             "DFMA latency, not by the issue rate")
+            return r
+
+        # the dominant kernel: top by time per frame over ALL kernels (each timed running alone)
+        top_overall = max(kern.items(), key=lambda kv: kv[1]["ms_per_frame"])[0] if kern else None
+        roof = roof_of(top_overall, kern[top_overall]) if top_overall else None
+        rooflines = {}
+        for name, kt in kern.items():
+            r = roof_of(name, kt)
+            if r:
+                rooflines[name] = {"bound": r["bound"], "achieved": r["achieved"], "unit": r["unit"], "frac": r["frac"],
+                                   "us_per_launch": kt["us_per_launch"]}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
         cpu = None
         if not args.no_cpu and world == 1:  # the CPU baseline is reported by the single-GPU run only
@@ -466,29 +535,42 @@ def run_gpu(args):
                    "host_cpus": os.cpu_count(),
                    "stage_ms": getattr(cpu_frames, "last_stage_ms", None),
                    "stage_ms_cv2": getattr(cpu_frames, "last_stage_ms_cv2", None)}
+        frames_timed = args.steps * args.regions
         line = {
             "metric": "stereo_uvo_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
             "data": "synthetic",
-            "config": {"workload": "stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo "
-                                   "YAML (BASELINE config[1]); one independent sequence per GPU",
+            "config": {"workload": cfg["workload"], "name": args.config,
                        "width": W, "height": H, "surf_min_hessian": thr, "keypoints_per_image": n_kp,
-                       "sequences_per_gpu": 1, "frames_in_flight": inflight,
+                       "sequences_per_gpu": 1, "frames_in_flight": inflight, "cuda_graphs": bool(args.graphs),
                        "l2": f"inputs larger than L2: ring of {RING} device-resident stereo pairs "
                              f"({RING * 2 * 3 * P / 1e6:.0f} MB), each read once per {RING} frames"},
+            "n_sequences": world,
+            # every number above is the MEDIAN of `regions` consecutive timed regions of exactly `steps` frames, each
+            # bracketed by barrier + synchronize (max over ranks per region); a 20-frame region is 7 ms long against a
+            # 1 ms pipeline fill, so single regions scatter by several percent
+            "timing": {"regions": args.regions, "region_ms": dev_regions, "spread": (max(dev_regions) - min(dev_regions)) /
+                       ms_dev, "e2e_region_ms": host_regions,
+                       "e2e_spread": (max(host_regions) - min(host_regions)) / ms_host,
+                       "steady_state": {"frames": n_long, "value": n_long * world / (ms_long_dev * 1e-3),
+                                        "e2e": n_long * world / (ms_long_host * 1e-3)}},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * 3 * P,
-                    "d2h_bytes_per_step": int(__import__('ctypes').sizeof(U.StereoResult)),
+                    "d2h_bytes_per_step": int(C.sizeof(U.StereoResult)),
                     "ms_per_step": ms_host / args.steps,
                     "api": f"uvo_stereo_enqueue_host + uvo_stereo_collect (pinned host images, {inflight} frames in "
                            "flight; H2D of both images and D2H of the result record inside the timed region)",
                     "sync_frame_latency_ms": sync_ms},
             "host_enqueue_us_per_frame": 1e6 * host_enqueue_s[0] / max(host_enqueue_s[1], 1),
-            "gpu_launches": int(launches),
-            "launches_per_frame": launches / float(args.steps),
-            "valid_frames": {"device": int(v[0]), "host": int(v[1]), "of": total_frames},
+            # kernels the library launched inside the timed regions of `value` (graph-replayed kernels counted one by
+            # one), per region of `steps` frames; host-side launch calls are graph launches + direct launches
+            "gpu_launches": int(round(launches / float(args.regions))),
+            "launches_per_frame": launches / float(frames_timed),
+            "graph_launches_per_frame": graph_launches / float(frames_timed),
+            "valid_frames": {"device": int(v[0]), "host": int(v[1]), "of": frames_timed * world},
             "clocks": summarise_clocks(samples),
             "roofline": roof, "rooflines_all": rooflines, "top_kernel_by_time": top_overall, "cpu_baseline": cpu,
+            "fp64_peak_tflops": f64_peak,
             "stage_ms": stage, "kernels": kern,
         }
         print(json.dumps(line))
@@ -505,10 +587,15 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS), help="BASELINE.json config: B = configs[1] "
+                    "(1280x1024, the headline), E = configs[4] (2448x2048, one sequence per GPU)")
+    ap.add_argument("--regions", type=int, default=REGIONS, help="consecutive timed regions of --steps frames (median)")
     ap.add_argument("--threshold", type=int, default=0, help="SURF min_hessian (0: bisect for ~4096 keypoints)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=8, help="frames kept in flight per sequence (<= the library's lanes)")
+    ap.add_argument("--graphs", type=int, default=1, help="0: launch every kernel directly instead of replaying graphs")
     args = ap.parse_args()
+    args.regions = max(args.regions, 1)
     if args.impl == "reference":
         if args.steps > 20:
             args.steps = 20  # bounded sample: ~2 s of CPU work per frame

@@ -153,8 +153,22 @@ static const char* kStageNames[UVO_N_STAGES] = {"h2d",        "get_image",    "s
 //   gather(t)        after triangulate(t-N_LANES+1)   (lane t's after-stereo sets are still being read by the frame after
 //                                                      the one that last used this lane)
 //   result(t)        after result(t-1)        (t_prevCam_currCam carried across gate failures)
+// A fixed run of kernels of one lane, captured once into a CUDA graph and replayed: every argument in it is a
+// lane-owned buffer or a device-resident count, so nothing changes from frame to frame.  The cross-lane event waits
+// and records stay ordinary stream operations BETWEEN segments (an event node inside a graph takes effect when the
+// node executes, not when the graph is launched, which is not the order the lanes need).
+struct Segment {
+  cudaGraphExec_t exec = nullptr;
+  int kernels = 0;  // kernel launches the segment stands for (keeps uvo_ctx_launch_count meaningful)
+  ~Segment() {
+    if (exec) cudaGraphExecDestroy(exec);
+  }
+};
+
 struct Lane {
   cudaStream_t stream = nullptr;
+  Segment seg[3];
+  int frames = 0;  // frames this lane has run (the first one runs eagerly: lazy one-time set-up must not be captured)
   FrontEnd fe;
   DevBuf<uvo_keypoint> kL_as, kR_as;
   DevBuf<float> dL_as;
@@ -201,8 +215,11 @@ struct uvo_stereo {
   size_t bayer_pitch = 0;
   cudaEvent_t ev_copied[RING] = {};
   long frame_no = 0;
-  std::deque<std::pair<int, cudaEvent_t>> pending;  // (slot, done event)
+  std::deque<int> pending;  // result slots in flight, oldest first
   cudaEvent_t ev[UVO_N_STAGES + 1] = {};
+  cudaEvent_t ev_done[RING] = {};  // one per result slot, re-recorded
+  bool use_graphs = true;          // uvo_stereo_set_graphs
+  long graph_launches = 0;
   bool timing = false;
   float stage_ms[UVO_N_STAGES] = {};
   bool has_timing = false;
@@ -210,7 +227,8 @@ struct uvo_stereo {
   Lane& last_lane() { return lane[(int)((frame_no + N_LANES - 1) % N_LANES)]; }
 
   ~uvo_stereo() {
-    for (auto& p : pending) cudaEventDestroy(p.second);
+    for (auto& e : ev_done)
+      if (e) cudaEventDestroy(e);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (ev_in) cudaEventDestroy(ev_in);
@@ -290,6 +308,7 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
   s->h_result.ensure(uvo_stereo::RING);
   UVO_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
   for (auto& e : s->ev) UVO_CUDA(cudaEventCreate(&e));
+  for (auto& e : s->ev_done) UVO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   rng_table_device(c);
   UVO_CUDA(cudaStreamSynchronize(c.stream));
 }
@@ -312,6 +331,8 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   FrameCtrl* ctrl = L.ctrl.get();
   FrameCtrl* pctrl = PL.ctrl.get();
   const GateParams g{p.min_num_features, p.min_num_3dpoints, p.min_num_inliers, cap};
+  const double KL[4] = {s->cam[0].nfx, s->cam[0].nfy, s->cam[0].ncx, s->cam[0].ncy};
+  const double KR[4] = {s->cam[1].nfx, s->cam[1].nfy, s->cam[1].ncx, s->cam[1].ncy};
   cudaStream_t caller_stream = c.stream;
   // whatever the caller enqueued on the context stream (e.g. the production of the device images) comes first
   UVO_CUDA(cudaEventRecord(s->ev_in, caller_stream));
@@ -361,21 +382,47 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     pitch = s->src_pitch;
   }
   mark(1);
+  // Graph replay: off while per-stage or per-kernel timing is on (the marks and the kernel timer are stream
+  // operations between kernels) and for a lane's first frame (one-time set-up inside the launchers -- function
+  // attributes, constant tables -- must run for real, not be captured).
+  const bool graphs = s->use_graphs && !s->timing && !c.kt.enabled && L.frames > 0;
+  auto segment = [&](int k, auto&& body) {
+    Segment& sg = L.seg[k];
+    if (!graphs) {
+      body();
+      return;
+    }
+    if (!sg.exec) {
+      const int64_t before = c.launches;
+      cudaGraph_t graph = nullptr;
+      UVO_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        body();
+      } catch (...) {
+        cudaStreamEndCapture(c.stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      UVO_CUDA(cudaStreamEndCapture(c.stream, &graph));
+      sg.kernels = (int)(c.launches - before);
+      c.launches = before;
+      const cudaError_t e = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      UVO_CUDA(e);
+    }
+    UVO_CUDA(cudaGraphLaunch(sg.exec, c.stream));
+    c.launches += sg.kernels;
+    s->graph_launches++;
+  };
   // 1. get_image x2 (visual_odometry.h:542-543)
   // both images through each preparation kernel at once (blockIdx.z = image).  (Running the right image on a second
   // stream instead was measured: -48 us of frame latency but -9 % end-to-end throughput with 8 frames in flight.)
-  L.fe.prep_pair(c, dL, dR, pitch, s->cam[0], s->cam[1], p.clahe, p.clip_limit);
-  mark(2);
-  // 2. detect_features x2 (:548-549), both images batched through each kernel
-  L.fe.surf(c, 0, 2, p, /*with_integral=*/false);
+  // The kernel that reads the source images takes this frame's pointers and is launched directly.
+  L.fe.prep_pair(c, dL, dR, pitch, s->cam[0], s->cam[1], p.clahe, p.clip_limit, PREP_PART_SOURCE);
   const int* cL = L.fe.counters.get();
   const int* cR = L.fe.counters.get() + 4;
-  UVO_KERNEL(c, "k_gate_features");
-  k_gate_features<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, g);
-  UVO_LAUNCH_CHECK(c);
-  mark(3);
-  // 3. match_features(curr_left, curr_right) (:558)
   MatchArgs ms{};
+  // arguments of the stereo match (:558); the temporal match below copies and edits them
   ms.q = L.fe.desc[0].get();
   ms.t = L.fe.desc[1].get();
   ms.nq_dev = &ctrl->nq_stereo;
@@ -394,7 +441,18 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   match_bind_scratch(ms, L.knn_scratch.get(), cap, cap);
   ms.matches = L.m_stereo.get();
   ms.n_matches = &ctrl->n_stereo;
+  segment(0, [&] {
+  L.fe.prep_pair(c, dL, dR, pitch, s->cam[0], s->cam[1], p.clahe, p.clip_limit, PREP_PART_REST);
+  mark(2);
+  // 2. detect_features x2 (:548-549), both images batched through each kernel
+  L.fe.surf(c, 0, 2, p, /*with_integral=*/false);
+  UVO_KERNEL(c, "k_gate_features");
+  k_gate_features<<<1, 1, 0, c.stream>>>(cL, cR, ctrl, g);
+  UVO_LAUNCH_CHECK(c);
+  mark(3);
+  // 3. match_features(curr_left, curr_right) (:558)
   launch_match(c, ms);
+  });
   // 4. gathers (:569-579).  From here on the frame depends on its predecessor.
   if (PL.used) UVO_CUDA(cudaStreamWaitEvent(c.stream, PL.ev_gather, 0));
   if (NX.used && &NX != &PL) UVO_CUDA(cudaStreamWaitEvent(c.stream, NX.ev_consumed, 0));
@@ -406,6 +464,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   UVO_LAUNCH_CHECK(c);
   UVO_CUDA(cudaEventRecord(L.ev_gather, c.stream));
   mark(4);
+  segment(1, [&] {
   // 5. triangular match: prev-left-after-stereo (query) vs all current left features (train) (:592)
   MatchArgs mt = ms;
   mt.gate_kq = mt.gate_kt = nullptr;  // the gate is a stereo (rectified pair) constraint only
@@ -434,7 +493,9 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ta.pts2_out = L.pts2.get();
   ta.n_out = &ctrl->n_tri;
   launch_triangulate(c, ta);
+  });
   UVO_CUDA(cudaEventRecord(L.ev_consumed, c.stream));  // the previous frame's after-stereo sets are no longer needed
+  segment(2, [&] {
   Extract3dArgs ea{};
   ea.kp1 = L.pts1.get();
   ea.kp2 = L.pts2.get();
@@ -447,8 +508,6 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   memcpy(ea.t1, z3, sizeof(z3));
   memcpy(ea.R2, s->R_right, sizeof(I));
   memcpy(ea.t2, s->t_right, sizeof(z3));
-  const double KL[4] = {s->cam[0].nfx, s->cam[0].nfy, s->cam[0].ncx, s->cam[0].ncy};
-  const double KR[4] = {s->cam[1].nfx, s->cam[1].nfy, s->cam[1].ncx, s->cam[1].ncy};
   memcpy(ea.K1, KL, sizeof(KL));
   memcpy(ea.K2, KR, sizeof(KR));
   ea.tol = p.reprojection_tolerance;
@@ -479,6 +538,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   pa.hyps = L.small.get() + 1;
   pnp_bind_scratch(pa, L.pnp_scratch.get(), cap, p.iterations_count);
   launch_pnp_ransac(c, pa);
+  });
   mark(7);
   // 11-13. Rodrigues, t_prevCam_currCam, velocity; one record back to the host
   if (PL.used) UVO_CUDA(cudaStreamWaitEvent(c.stream, PL.ev_result, 0));
@@ -491,11 +551,10 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
                            cudaMemcpyDeviceToHost, c.stream));
   mark(8);
-  cudaEvent_t done;
-  UVO_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-  UVO_CUDA(cudaEventRecord(done, c.stream));
-  s->pending.emplace_back(slot, done);
+  UVO_CUDA(cudaEventRecord(s->ev_done[slot], c.stream));
+  s->pending.push_back(slot);
   L.used = true;
+  L.frames++;
   // 14. carry curr -> prev (:723-733): the next frame reads this lane's after-stereo sets
   s->frame_no++;
 }
@@ -572,11 +631,10 @@ int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out) {
   if (!s || !out) return UVO_ERR_INVALID;
   return guarded(&s->ctx->c, [&] {
     UVO_REQUIRE(!s->pending.empty(), "uvo_stereo_collect: no frame in flight");
-    auto pr = s->pending.front();
+    const int slot = s->pending.front();
     s->pending.pop_front();
-    UVO_CUDA(cudaEventSynchronize(pr.second));
-    cudaEventDestroy(pr.second);
-    *out = s->h_result.p[pr.first];
+    UVO_CUDA(cudaEventSynchronize(s->ev_done[slot]));
+    *out = s->h_result.p[slot];
     if (out->gate == -1)
       throw InvalidArg{"more SURF keypoints than max_features: raise uvo_params.max_features", UVO_ERR_CAPACITY};
   });
@@ -612,6 +670,14 @@ int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3, const uint8_t* right3,
 }
 
 int uvo_stereo_max_in_flight(void) { return uvo_stereo::RING; }
+
+int uvo_stereo_set_graphs(uvo_stereo* s, int enable) {
+  if (!s) return UVO_ERR_INVALID;
+  s->use_graphs = enable != 0;
+  return UVO_OK;
+}
+
+int64_t uvo_stereo_graph_launches(const uvo_stereo* s) { return s ? (int64_t)s->graph_launches : 0; }
 
 // the debug taps read the buffers of the most recent frame; they wait for every lane first
 static void stereo_quiesce(uvo_stereo* s) {

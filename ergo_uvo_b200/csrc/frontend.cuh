@@ -82,13 +82,13 @@ struct FrontEnd {
 
   // get_image + integral for slots 0 and 1 together (stereo pair), one launch per kernel
   void prep_pair(Ctx& c, const uint8_t* srcL, const uint8_t* srcR, size_t spitch, const uvo_camera& camL,
-                 const uvo_camera& camR, int clahe, int clip_limit) {
+                 const uvo_camera& camR, int clahe, int clip_limit, int part = PREP_PART_SOURCE | PREP_PART_REST) {
     const uint8_t* src[2] = {srcL, srcR};
     const UndistortParams P[2] = {make_undistort_params(camL), make_undistort_params(camR)};
     uint8_t* g2[2] = {gray[0].get(), gray[1].get()};
     int32_t* s2[2] = {sum[0].get(), sum[1].get()};
     launch_prep_pair(c, src, spitch, w, h, P, clahe, make_clahe_geom(w, h, (double)clip_limit, 8, 8), hist.get(),
-                     lut.get(), g2, gpitch, s2);
+                     lut.get(), g2, gpitch, s2, part);
   }
 
   // integral image of slot `idx` (the first step of SURF::detectAndCompute)

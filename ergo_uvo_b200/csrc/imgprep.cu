@@ -402,14 +402,15 @@ void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, i
 // narrow kernels (histograms, LUTs, the two scan passes) get twice the blocks.  d_hist / d_lut: 2 * tiles * 256.
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
                       const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
-                      int32_t* d_sum[2]) {
-  {
+                      int32_t* d_sum[2], int part) {
+  if (part & PREP_PART_SOURCE) {
     dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
     UVO_KERNEL(c, "k_gray_undistort");
     k_gray_undistort<<<grid, block, 0, c.stream>>>(d_src3[0], d_src3[1], spitch, w, h, P[0], P[1], d_gray[0], d_gray[1],
                                                    gpitch);
     UVO_LAUNCH_CHECK(c);
   }
+  if (!(part & PREP_PART_REST)) return;
   if (clahe) {
     const int tiles = g.tiles_x * g.tiles_y;
     UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles * 2, c.stream));

@@ -37,9 +37,12 @@ struct AreaCell {  // one destination index of computeResizeAreaTab: optional le
 void launch_resize_area(Ctx& c, const uint8_t* d_src, size_t spitch, int sw, int sh, int cn, uint8_t* d_dst,
                         size_t dpitch, int dw, int dh, AreaCell* d_tab);
 // get_image (gray + undistort + optional CLAHE) and the integral image for both images of a stereo pair, batched
+// part: the kernel that reads the source images (the only one whose arguments change from frame to frame) and the
+// rest can be launched separately, so that the rest can live in a CUDA graph
+enum { PREP_PART_SOURCE = 1, PREP_PART_REST = 2 };
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
                       const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
-                      int32_t* d_sum[2]);
+                      int32_t* d_sum[2], int part = PREP_PART_SOURCE | PREP_PART_REST);
 // d_sum: (h+1) x (w+1) int32, dense
 void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum);
 

@@ -937,7 +937,10 @@ void launch_pnp_solve(Ctx& c, const PnpArgs& a) {
   for (int k = 0; k < 4 && lo < iters; k++) {
     const int hi = std::min(bounds[k], iters);
     if (hi <= lo) continue;
-    UVO_KERNEL(c, "k_pnp_chunk");
+    // timed under one name per chunk: the first runs hypotheses, the later ones normally return at once
+    static const char* const kChunkNames[4] = {"k_pnp_chunk[0:32]", "k_pnp_chunk[32:128]", "k_pnp_chunk[128:512]",
+                                               "k_pnp_chunk[512:]"};
+    UVO_KERNEL(c, kChunkNames[k]);
     if (hi <= 128) k_pnp_chunk<4><<<hi - lo, CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
     else k_pnp_chunk<1><<<div_up(hi - lo, 4), CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
     UVO_LAUNCH_CHECK(c);

@@ -494,6 +494,16 @@ class StereoVO:
     def max_in_flight(self):
         return int(self.lib.uvo_stereo_max_in_flight())
 
+    def set_graphs(self, enable):
+        """replay each lane's fixed kernel runs as CUDA graphs (default) or launch every kernel directly"""
+        self.ctx._ck(self.lib.uvo_stereo_set_graphs(self.h, int(bool(enable))))
+
+    @property
+    def graph_launches(self):
+        self.lib.uvo_stereo_graph_launches.restype = C.c_int64
+        self.lib.uvo_stereo_graph_launches.argtypes = [C.c_void_p]
+        return int(self.lib.uvo_stereo_graph_launches(self.h))
+
     def collect(self):
         res = L.StereoResult()
         self.ctx._ck(self.lib.uvo_stereo_collect(self.h, C.byref(res)))

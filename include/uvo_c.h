@@ -343,6 +343,11 @@ UVO_API int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3_host, co
 UVO_API int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1_host, const uint8_t* right1_host,
                                           size_t pitch, double dt);
 UVO_API int uvo_stereo_max_in_flight(void);
+/* The asynchronous entry points replay each lane's fixed runs of kernels as CUDA graphs (three graph launches + a few
+ * direct launches per frame instead of ~30 kernel launches; results are identical).  `enable` = 0 goes back to direct
+ * launches (diagnostics / A-B measurements); uvo_stereo_graph_launches counts the graph launches made so far. */
+UVO_API int uvo_stereo_set_graphs(uvo_stereo* s, int enable);
+UVO_API int64_t uvo_stereo_graph_launches(const uvo_stereo* s);
 UVO_API int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out);
 /* Debug/parity taps of the last frame (device -> host copies of intermediate products).  Descriptor rows are 64
  * floats, 128 when the handle was created with surf_extended. */

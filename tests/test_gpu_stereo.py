@@ -214,3 +214,54 @@ def test_bayer_input_equals_demosaiced_input(ctx, oracle, small_stereo):
         assert ka.tobytes() == kb.tobytes() and len(ka) > 100
     vo_a.close()
     vo_b.close()
+
+
+def test_stereo_graph_replay_matches_direct_launches(ctx, small_stereo):
+    """the asynchronous path replays each lane's kernel runs as CUDA graphs from the lane's second frame on: 40 frames
+    (five per lane: direct, capture + launch, three replays) give byte-identical result records and identical
+    intermediate products to the synchronous one-frame-at-a-time path, which launches every kernel directly"""
+    import torch
+    seq = small_stereo
+    order = [k % len(seq.frames) for k in range(40)]
+    vo, p = _make(ctx, seq, 3000)
+    sync = [vo.frame(*seq.frames[k], 0.1) for k in order]
+    taps = (vo.last_keypoints(False), vo.last_keypoints(True), vo.last_matches(False), vo.last_matches(True),
+            vo.last_inliers())
+    assert vo.graph_launches == 0          # the synchronous call times its stages: no graphs
+    vo.close()
+    pinned = [(torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory()) for (L, R) in seq.frames]
+
+    def run(graphs):
+        vo, _ = _make(ctx, seq, 3000)
+        vo.set_graphs(graphs)
+        got, q = [], 0
+        for k in order:
+            L, R = pinned[k]
+            vo.enqueue_host(L.data_ptr(), R.data_ptr(), 3 * seq.w, 0.1)
+            q += 1
+            if q >= 8:
+                got.append(vo.collect())
+                q -= 1
+        while q:
+            got.append(vo.collect())
+            q -= 1
+        t = (vo.last_keypoints(False), vo.last_keypoints(True), vo.last_matches(False), vo.last_matches(True),
+             vo.last_inliers())
+        n = vo.graph_launches
+        vo.close()
+        return got, t, n
+
+    got, t, n = run(True)
+    assert n == 3 * (len(order) - 8)       # three graph launches per frame after each of the 8 lanes' first frame
+    assert any(r.valid for r in got)
+    for a, b in zip(got, sync):
+        assert bytes(a) == bytes(b)
+    for a, b in zip(t, taps):
+        if isinstance(a, tuple):
+            assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+        else:
+            assert a.tobytes() == b.tobytes()
+    got2, _, n2 = run(False)
+    assert n2 == 0
+    for a, b in zip(got2, sync):
+        assert bytes(a) == bytes(b)
