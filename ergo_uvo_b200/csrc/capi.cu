@@ -289,7 +289,7 @@ int uvo_integral(uvo_ctx* ctx, const uint8_t* gray, int w, int h, size_t pitch, 
     s.gray.ensure(gp * h);
     s.integral.ensure((size_t)(w + 1) * (h + 1));
     UVO_CUDA(cudaMemcpy2DAsync(s.gray.get(), gp, gray, pitch, w, h, cudaMemcpyHostToDevice, c.stream));
-    launch_integral(c, s.gray.get(), gp, w, h, s.integral.get());
+    launch_integral(c, s.gray.get(), gp, w, h, s.integral.get());  // dense: pitch w + 1
     UVO_CUDA(cudaMemcpyAsync(sum, s.integral.get(), sizeof(int32_t) * (size_t)(w + 1) * (h + 1),
                              cudaMemcpyDeviceToHost, c.stream));
     UVO_CUDA(cudaStreamSynchronize(c.stream));

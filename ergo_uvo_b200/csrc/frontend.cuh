@@ -10,6 +10,10 @@ namespace uvo {
 struct FrontEnd {
   int w = 0, h = 0, n_img = 0, capacity = 0;
   size_t gpitch = 0;
+  int sum_pitch = 0;  // integral row pitch (elements)
+  SurfMaps maps{};
+  const int32_t* maps_for[2] = {nullptr, nullptr};
+  int maps_w = 0, maps_h = 0;
   SurfGeom geom{};
   bool geom_valid = false;
   double geom_thr = -1;
@@ -34,9 +38,10 @@ struct FrontEnd {
     n_img = std::max(n_img, n_img_);
     capacity = std::max(capacity, capacity_);
     gpitch = ((size_t)w + 15) & ~(size_t)15;
+    sum_pitch = surf_sum_pitch(w);
     for (int i = 0; i < n_img; i++) {
       gray[i].ensure(gpitch * h);
-      sum[i].ensure((size_t)(w + 1) * (h + 1));
+      sum[i].ensure((size_t)sum_pitch * (h + 1));
       raw[i].ensure(capacity);
       kps[i].ensure(capacity);
       // sized for extended (128-d) rows; the row stride in use is 64 unless surf() is asked for extended descriptors
@@ -50,6 +55,13 @@ struct FrontEnd {
     counters.ensure(8);
     hist.ensure(2 * 64 * 256);
     lut.ensure(2 * 64 * 256);
+    if (maps_for[0] != sum[0].get() || maps_for[1] != sum[n_img > 1 ? 1 : 0].get() || maps_w != w || maps_h != h) {
+      maps_w = w;
+      maps_h = h;
+      maps_for[0] = sum[0].get();
+      maps_for[1] = sum[n_img > 1 ? 1 : 0].get();
+      maps = make_surf_maps(maps_for[0], maps_for[1], w, h);
+    }
   }
 
   SurfBatch batch(int first, int count) const {
@@ -88,11 +100,11 @@ struct FrontEnd {
     uint8_t* g2[2] = {gray[0].get(), gray[1].get()};
     int32_t* s2[2] = {sum[0].get(), sum[1].get()};
     launch_prep_pair(c, src, spitch, w, h, P, clahe, make_clahe_geom(w, h, (double)clip_limit, 8, 8), hist.get(),
-                     lut.get(), g2, gpitch, s2, part);
+                     lut.get(), g2, gpitch, s2, part, sum_pitch);
   }
 
   // integral image of slot `idx` (the first step of SURF::detectAndCompute)
-  void integral(Ctx& c, int idx) { launch_integral(c, gray[idx].get(), gpitch, w, h, sum[idx].get()); }
+  void integral(Ctx& c, int idx) { launch_integral(c, gray[idx].get(), gpitch, w, h, sum[idx].get(), sum_pitch); }
 
   // SURF::detectAndCompute on images [first, first+count); `with_integral` = false when the caller already ran
   // integral() for those slots (the stereo pipeline does, per image, on two streams)
@@ -109,7 +121,9 @@ struct FrontEnd {
     if (with_integral)
       for (int i = 0; i < count; i++) integral(c, first + i);
     SurfBatch b = batch(first, count);
-    launch_surf_detect(c, geom, b, capacity);
+    SurfMaps m = maps;
+    if (first == 1) m.sum[0] = maps.sum[1];
+    launch_surf_detect(c, geom, b, m, capacity);
     launch_surf_sort(c, b, capacity);
     launch_surf_describe(c, geom, b, capacity, p.surf_upright, p.surf_extended);
     // describe can delete keypoints only in oriented mode or when the image is smaller than the largest

@@ -323,13 +323,13 @@ void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, con
 // and (warp 0) row 0.  Pass 2: column prefix in place, each block owns 32 columns x 32 row segments.
 __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* img0, const uint8_t* img1,
                                                        size_t pitch, int w, int h, int32_t* sum0,
-                                                       int32_t* sum1) {
+                                                       int32_t* sum1, int sw) {
   const uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
   int32_t* __restrict__ sum = blockIdx.z ? sum1 : sum0;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int sw = w + 1;
+  // sw: row pitch of the integral in elements (>= w + 1; the SURF front end pads it to 16 bytes for TMA)
   if (warp == 0)
-    for (int j = lane; j < sw; j += 32) sum[j] = 0;
+    for (int j = lane; j < w + 1; j += 32) sum[j] = 0;
   if (warp >= h) return;
   const uint8_t* row = img + (size_t)warp * pitch;
   int32_t* out = sum + (size_t)(warp + 1) * sw;
@@ -365,36 +365,36 @@ __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* img0, cons
 
 // block = 32 (columns) x 32 (row segments).  Segment totals -> exclusive scan in smem -> second sweep adds.
 __global__ void __launch_bounds__(1024) k_integral_cols(int32_t* sum0, int32_t* sum1, int w,
-                                                        int h) {
+                                                        int h, int sw) {
   __shared__ int32_t tot[32][33];
   int32_t* __restrict__ sum = blockIdx.z ? sum1 : sum0;
-  const int sw = w + 1;
   const int col = 1 + blockIdx.x * 32 + threadIdx.x;
   const int seg = threadIdx.y;
   const int rows_per = (h + 31) / 32;
   const int r0 = 1 + seg * rows_per, r1 = min(r0 + rows_per, h + 1);
   int32_t acc = 0;
-  if (col < sw)
+  if (col < w + 1)
     for (int r = r0; r < r1; r++) acc += sum[(size_t)r * sw + col];
   tot[seg][threadIdx.x] = acc;
   __syncthreads();
   int32_t run = 0;
   for (int k = 0; k < seg; k++) run += tot[k][threadIdx.x];
-  if (col < sw)
+  if (col < w + 1)
     for (int r = r0; r < r1; r++) {
       run += sum[(size_t)r * sw + col];
       sum[(size_t)r * sw + col] = run;
     }
 }
 
-void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum) {
+void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum, int sum_pitch) {
   const int warps_per_block = 8;
+  const int sw = sum_pitch > 0 ? sum_pitch : w + 1;
   UVO_KERNEL(c, "k_integral_rows");
   k_integral_rows<<<div_up(h, warps_per_block), 32 * warps_per_block, 0, c.stream>>>(d_img, d_img, pitch, w, h, d_sum,
-                                                                                      d_sum);
+                                                                                      d_sum, sw);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
-  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, d_sum, w, h);
+  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, d_sum, w, h, sw);
   UVO_LAUNCH_CHECK(c);
 }
 
@@ -402,7 +402,7 @@ void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, i
 // narrow kernels (histograms, LUTs, the two scan passes) get twice the blocks.  d_hist / d_lut: 2 * tiles * 256.
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
                       const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
-                      int32_t* d_sum[2], int part) {
+                      int32_t* d_sum[2], int part, int sum_pitch) {
   if (part & PREP_PART_SOURCE) {
     dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
     UVO_KERNEL(c, "k_gray_undistort");
@@ -428,12 +428,13 @@ void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, in
     UVO_LAUNCH_CHECK(c);
   }
   const int warps_per_block = 8;
+  const int sw = sum_pitch > 0 ? sum_pitch : w + 1;
   UVO_KERNEL(c, "k_integral_rows");
   k_integral_rows<<<dim3(div_up(h, warps_per_block), 1, 2), 32 * warps_per_block, 0, c.stream>>>(
-      d_gray[0], d_gray[1], gpitch, w, h, d_sum[0], d_sum[1]);
+      d_gray[0], d_gray[1], gpitch, w, h, d_sum[0], d_sum[1], sw);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
-  k_integral_cols<<<dim3(div_up(w, 32), 1, 2), dim3(32, 32), 0, c.stream>>>(d_sum[0], d_sum[1], w, h);
+  k_integral_cols<<<dim3(div_up(w, 32), 1, 2), dim3(32, 32), 0, c.stream>>>(d_sum[0], d_sum[1], w, h, sw);
   UVO_LAUNCH_CHECK(c);
 }
 

@@ -42,8 +42,8 @@ void launch_resize_area(Ctx& c, const uint8_t* d_src, size_t spitch, int sw, int
 enum { PREP_PART_SOURCE = 1, PREP_PART_REST = 2 };
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
                       const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
-                      int32_t* d_sum[2], int part = PREP_PART_SOURCE | PREP_PART_REST);
-// d_sum: (h+1) x (w+1) int32, dense
-void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum);
+                      int32_t* d_sum[2], int part = PREP_PART_SOURCE | PREP_PART_REST, int sum_pitch = 0);
+// d_sum: (h+1) rows of sum_pitch int32 (w+1 used; sum_pitch = 0: dense, pitch w+1)
+void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum, int sum_pitch = 0);
 
 }  // namespace uvo

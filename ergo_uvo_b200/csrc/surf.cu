@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "surf.cuh"
+#include "tma.cuh"
 
 namespace uvo {
 
@@ -80,6 +81,8 @@ SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, i
   g.n_octaves = n_octaves;
   g.n_layers = n_layers;
   g.thr = (float)hessian_threshold;
+  g.spitch = surf_sum_pitch(w);
+  const int ws_pitch = g.spitch;
   int tile_begin = 0;
   for (int o = 0; o < n_octaves; o++) {
     SurfOctave& O = g.oct[o];
@@ -100,12 +103,12 @@ SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, i
         L.samples_i = 1 + (h - L.size) / O.step;
         L.samples_j = 1 + (w - L.size) / O.step;
       }
-      resize_haar_h(dx_s, L.box + 0, 3, 9, L.size, w + 1);
-      resize_haar_h(dy_s, L.box + 3, 3, 9, L.size, w + 1);
-      resize_haar_h(dxy_s, L.box + 6, 4, 9, L.size, w + 1);
+      resize_haar_h(dx_s, L.box + 0, 3, 9, L.size, ws_pitch);
+      resize_haar_h(dy_s, L.box + 3, 3, 9, L.size, ws_pitch);
+      resize_haar_h(dxy_s, L.box + 6, 4, 9, L.size, ws_pitch);
       {
         const float ratio = (float)L.size / 9;
-        const int ws = w + 1;
+        const int ws = ws_pitch;
         L.xx_row[0] = cv_roundf_h(ratio * 2) * ws;
         L.xx_row[1] = cv_roundf_h(ratio * 7) * ws;
         L.yy_col[0] = cv_roundf_h(ratio * 2);
@@ -198,7 +201,13 @@ __host__ __device__ constexpr int haar_off(int k) {  // resizeHaarPattern: cvRou
   return cround_c((float)SIZE / 9 * (float)k);
 }
 constexpr int T0_MAXM = 13;                                 // margin of the largest middle layer (size 27) at step 1
-constexpr int T0_ROWS = SURF_TILE_H + 2 + 27, T0_COLS = SURF_TILE_W + 2 + 27;  // 45 x 61 integral samples
+// 45 x 61 integral samples inside one TMA box of 45 x 64: the copy engine wants the inner extent AND the inner start
+// coordinate to be multiples of 16 bytes (measured: tools/probes/tma_tile_probe.cu -- a start column that is not a
+// multiple of 4 ints faults), so the box starts T0_XOFF = 2 columns left of the first sample the tile needs
+// (tile column 0 = image column tj0 - 16, tj0 a multiple of 32)
+constexpr int T0_ROWS = SURF_TILE_H + 2 + 27, T0_COLS = 64, T0_XOFF = 2;
+static_assert(SURF_TILE_W + 2 + 27 + T0_XOFF <= T0_COLS, "octave-0 tile does not fit its TMA box");
+static_assert((SURF_TILE_W % 4) == 0 && ((1 + T0_MAXM + T0_XOFF) % 4) == 0, "TMA start column must be 16-byte aligned");
 
 template <int SIZE, bool LAZY = false>
 __device__ __forceinline__ float det_tile0(const int* __restrict__ T, const SurfLayer& L, int i, int j, int y, int x,
@@ -206,7 +215,7 @@ __device__ __forceinline__ float det_tile0(const int* __restrict__ T, const Surf
   constexpr int M = SIZE / 2;
   const int si = i - M, sj = j - M;
   if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return 0.f;  // never-written map border
-  const int* o = T + (y + T0_MAXM - M) * T0_COLS + (x + T0_MAXM - M);
+  const int* o = T + (y + T0_MAXM - M) * T0_COLS + (x + T0_MAXM - M + T0_XOFF);
   constexpr int c0 = haar_off<SIZE>(0), c1 = haar_off<SIZE>(1), c2 = haar_off<SIZE>(2), c3 = haar_off<SIZE>(3),
                 c4 = haar_off<SIZE>(4), c5 = haar_off<SIZE>(5), c6 = haar_off<SIZE>(6), c7 = haar_off<SIZE>(7),
                 c8 = haar_off<SIZE>(8), c9 = haar_off<SIZE>(9);
@@ -310,8 +319,8 @@ __device__ __noinline__ void emit_keypoint(const SurfOctave& O, const SurfImage&
 #ifndef UVO_DET_MINB
 #define UVO_DET_MINB 6
 #endif
-__global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_constant__ SurfGeom g, const __grid_constant__ SurfBatch b,
-                                                     int capacity) {
+__global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_constant__ SurfMaps maps, const __grid_constant__ SurfGeom g,
+                                                     const __grid_constant__ SurfBatch b, int capacity) {
   // sdet[l] holds pyramid layer l + 1 (the middle layers)
   __shared__ float sdet[SURF_MAX_LAYERS - 2][TH + 2][TW + 2];
   __shared__ DetCand s_cand[DET_LIST];
@@ -324,10 +333,11 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   t -= O.tile_begin;
   const int ti0 = (t / O.tiles_x) * TH, tj0 = (t % O.tiles_x) * TW;
   const int nmid = g.n_layers;
-  const int scols = g.w + 1;
+  const int scols = g.spitch;
   const int step = O.step;
   constexpr int PLANE = (TH + 2) * (TW + 2);
-  __shared__ int s_tile[T0_ROWS * T0_COLS];
+  __shared__ __align__(128) int s_tile[T0_ROWS * T0_COLS];
+  __shared__ __align__(8) unsigned long long s_bar;
   // exact value of middle layer lm (0-based) at tile position (y, x): the full evaluation of a skipped sample
   auto mid_exact = [&](int lm, int y, int x) -> float {
     const int i = ti0 + y - 1, j = tj0 + x - 1;
@@ -340,15 +350,20 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   };
   if (threadIdx.x == 0) s_ncand = 0;
   if (o == 0) {
-    // octave 0 (three quarters of all samples): stage the integral tile once, then evaluate from shared memory
-    const int R0 = ti0 - 1 - T0_MAXM, C0 = tj0 - 1 - T0_MAXM;
-    for (int idx = threadIdx.x; idx < T0_ROWS * T0_COLS; idx += blockDim.x) {
-      const int ry = idx / T0_COLS, rx = idx - ry * T0_COLS;
-      const int gy = R0 + ry, gx = C0 + rx;
-      s_tile[idx] = ((unsigned)gy <= (unsigned)g.h && (unsigned)gx <= (unsigned)g.w)
-                        ? __ldg(im.sum + (size_t)gy * scols + gx) : 0;
+    // octave 0 (three quarters of all samples): the integral tile arrives as ONE TMA box (cp.async.bulk.tensor.2d,
+    // completion on an mbarrier) -- coordinates left of / above the image and past its last row / column are filled
+    // with zeros by the copy engine, which is the border rule of the evaluation -- then every sample is evaluated
+    // from shared memory
+    const int R0 = ti0 - 1 - T0_MAXM, C0 = tj0 - 1 - T0_MAXM - T0_XOFF;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, T0_ROWS * T0_COLS * (int)sizeof(int));
+      tma_load_2d(smem_u32(s_tile), blockIdx.y ? &maps.sum[1] : &maps.sum[0], C0, R0, bar);
     }
-    __syncthreads();
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    mbar_wait(bar, 0);
     for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
       const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
       const int i = ti0 + y - 1, j = tj0 + x - 1;
@@ -471,11 +486,28 @@ static bool tile0_offsets_match(const SurfLayer& L, int ws) {
          L.xx_col[3] == haar_off<SIZE>(9) && L.yy_row[1] == haar_off<SIZE>(3) * ws;
 }
 
-void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity) {
+SurfMaps make_surf_maps(const int32_t* sum0, const int32_t* sum1, int w, int h) {
+  SurfMaps m;
+  const int32_t* base[2] = {sum0, sum1};
+  for (int i = 0; i < 2; i++) {
+    const cuuint64_t dims[2] = {(cuuint64_t)(w + 1), (cuuint64_t)(h + 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)surf_sum_pitch(w) * sizeof(int32_t)};
+    const cuuint32_t box[2] = {(cuuint32_t)T0_COLS, (cuuint32_t)T0_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled_fn()(&m.sum[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void*)base[i], dims, strides, box,
+                                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      throw InvalidArg{"cuTensorMapEncodeTiled (integral image) failed (" + std::to_string((int)r) + ")", UVO_ERR_CUDA};
+  }
+  return m;
+}
+
+void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, const SurfMaps& maps, int capacity) {
   upload_tables(c);
   {
     const SurfOctave& O = g.oct[0];
-    const int ws = g.w + 1;
+    const int ws = g.spitch;
     bool ok = O.step == 1 && tile0_offsets_match<15>(O.layer[1], ws);
     if (g.n_layers >= 2) ok = ok && tile0_offsets_match<21>(O.layer[2], ws);
     if (g.n_layers >= 3) ok = ok && tile0_offsets_match<27>(O.layer[3], ws);
@@ -485,7 +517,9 @@ void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capac
     UVO_CUDA(cudaMemsetAsync(b.im[i].counters, 0, 4 * sizeof(int), c.stream));
   }
   UVO_KERNEL(c, "k_surf_detect");
-  k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(g, b, capacity);
+  // the tensor maps come first: the copy engine reads them from the parameter space, and the geometry (> 4 KB of box
+  // tables) would push them past the first 4 KB of it
+  k_surf_detect<<<dim3(g.total_tiles, b.n_img), 256, 0, c.stream>>>(maps, g, b, capacity);
   UVO_LAUNCH_CHECK(c);
 }
 
@@ -806,7 +840,8 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
   __shared__ int s_iscale, s_area_fast;
   const SurfImage& im = b.im[blockIdx.y];
   const int n = im.counters[1];
-  const int w = g.w, h = g.h, srows = h + 1, scols = w + 1;
+  const int w = g.w, h = g.h, srows = h + 1, scols = w + 1;  // sum.rows / sum.cols of the CPU code
+  const int spitch = g.spitch;                                // row pitch of the integral in memory
   const int tid = threadIdx.x;
   // dynamic queue (counters[2], zeroed by the sort kernel): window areas span 21^2 .. 576^2 pixels, so a static
   // assignment leaves most blocks waiting for the one that drew the largest windows
@@ -847,10 +882,10 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
         const int y = __float2int_rn(__fsub_rn(__fadd_rn(cy, __fmul_rn((float)c_apt[tid][1], s)), (float)(gws - 1) / 2));
         if (!(y < 0 || y >= srows - gws || x < 0 || x >= scols - gws)) {
           valid = true;
-          const int* o = im.sum + (size_t)y * scols + x;
+          const int* o = im.sum + (size_t)y * spitch + x;
           auto box = [&](int x1, int y1, int x2, int y2) -> int {
-            return (int)((unsigned)__ldg(o + y1 * scols + x1) + (unsigned)__ldg(o + y2 * scols + x2) -
-                         (unsigned)__ldg(o + y2 * scols + x1) - (unsigned)__ldg(o + y1 * scols + x2));
+            return (int)((unsigned)__ldg(o + y1 * spitch + x1) + (unsigned)__ldg(o + y2 * spitch + x2) -
+                         (unsigned)__ldg(o + y2 * spitch + x1) - (unsigned)__ldg(o + y1 * spitch + x2));
           };
           double dxv = 0, dyv = 0;
           dxv = __dadd_rn(dxv, (double)__fmul_rn((float)box(0, 0, c2, c4), -wx));

@@ -2,6 +2,7 @@
 // 3x3x3 non-max suppression + interpolation, total-order sort, (orientation) and 64-d descriptors.
 // Replaces SURF::create(...)->detectAndCompute (reference VO_utility.cpp:117-118).
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace uvo {
@@ -30,8 +31,13 @@ struct SurfOctave {
   SurfLayer layer[SURF_MAX_LAYERS];
 };
 
+// row pitch of the integral image in elements: (w + 1) padded to 16 bytes, which is what a TMA tensor map needs of a
+// global row stride (the octave-0 tiles of k_surf_detect arrive by cp.async.bulk.tensor)
+static inline int surf_sum_pitch(int w) { return (w + 1 + 3) & ~3; }
+
 struct SurfGeom {
   int w, h, n_octaves, n_layers, total_tiles;
+  int spitch;  // surf_sum_pitch(w)
   float thr;
   SurfOctave oct[SURF_MAX_OCTAVES];
 };
@@ -42,7 +48,7 @@ SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, i
 struct SurfImage {
   const uint8_t* img = nullptr;   // gray image (device)
   size_t pitch = 0;
-  const int32_t* sum = nullptr;   // integral (h+1)x(w+1)
+  const int32_t* sum = nullptr;   // integral, (h+1) rows of surf_sum_pitch(w) ints (w+1 used)
   uvo_keypoint* raw = nullptr;    // unordered detections
   uvo_keypoint* kps = nullptr;    // sorted (OpenCV order), compacted
   float* desc = nullptr;          // capacity x 64 (capacity x 128 when extended)
@@ -56,8 +62,15 @@ struct SurfBatch {
   int n_img;
 };
 
+// TMA descriptors of the two integral images (2-D int32, (w+1) x (h+1), boxes of 64 x 45: one octave-0 tile); built
+// once per front end, passed to k_surf_detect as a __grid_constant__ parameter
+struct alignas(64) SurfMaps {
+  CUtensorMap sum[2];
+};
+SurfMaps make_surf_maps(const int32_t* sum0, const int32_t* sum1, int w, int h);
+
 // detection (pyramid + NMS + interpolation) for n_img images of identical geometry, appends to raw[]/counters[0]
-void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, int capacity);
+void launch_surf_detect(Ctx& c, const SurfGeom& g, const SurfBatch& b, const SurfMaps& maps, int capacity);
 // rank sort raw -> kps in KeypointGreater order, sets counters[1] = min(counters[0], capacity)
 void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity);
 // upright/oriented descriptors (64-d, or 128-d rows when `extended`) for kps[0..counters[1]); sets angle; marks
