@@ -89,4 +89,23 @@ int uvo_resize_camera_matrix(int original_width, int original_height, int desire
   return uvo_optimal_new_camera_matrix(K_inout, D, desired_width, desired_height, newK);
 }
 
+// cv::Rodrigues(rvec, R) as the node calls it on solvePnPRansac's output (visual_odometry.h:673): rotation vector ->
+// 3 x 3 matrix, fp64, the arithmetic of OpenCV's cvRodrigues2 (theta = |r|; R = cos I + (1 - cos) r r^T + sin [r]x).
+// Host-only (a 3-vector), here so that the cv:: interposer needs no OpenCV for it; pinned against cv2 in
+// tests/test_cabi.py.
+int uvo_rodrigues(const double rvec[3], double R[9]) {
+  if (!rvec || !R) return UVO_ERR_INVALID;
+  const double theta = std::sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2]);
+  if (theta < DBL_EPSILON) {
+    for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return UVO_OK;
+  }
+  const double c = std::cos(theta), s = std::sin(theta), c1 = 1. - c, it = 1. / theta;
+  const double x = rvec[0] * it, y = rvec[1] * it, z = rvec[2] * it;
+  const double rrt[9] = {x * x, x * y, x * z, x * y, y * y, y * z, x * z, y * z, z * z};
+  const double rx[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  for (int i = 0; i < 9; i++) R[i] = c * (i % 4 == 0 ? 1. : 0.) + c1 * rrt[i] + s * rx[i];
+  return UVO_OK;
+}
+
 }  // extern "C"

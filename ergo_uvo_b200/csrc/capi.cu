@@ -52,7 +52,10 @@ int uvo_ctx_create(int device, void* cuda_stream, uvo_ctx** out) {
     cudaDeviceProp prop;
     UVO_CUDA(cudaGetDeviceProperties(&prop, device));
     c->c.sm_count = prop.multiProcessorCount;
-    UVO_REQUIRE(prop.major >= 10, "libuvo_b200 is built for sm_100a only; this device is older");
+    // the library carries sm_100a machine code only (no PTX): any other part -- older, or sm_103 / sm_12x -- would
+    // create a context and then fail every launch with "no kernel image"
+    UVO_REQUIRE(prop.major == 10 && prop.minor == 0,
+                "libuvo_b200 is built for sm_100a (B200) only; this device has another compute capability");
   });
   if (rc != UVO_OK) {
     fprintf(stderr, "uvo_ctx_create: %s\n", c->c.err.c_str());
@@ -792,10 +795,16 @@ int uvo_select_estimation_method(uvo_ctx* ctx, const float* p1, const float* p2,
 
 int uvo_scale_factor(uvo_ctx* ctx, const double* pts, int n, const double R[9], const double t[3], float range,
                      double* scale_factor) {
+  return uvo_scale_factor_front(ctx, pts, n, R, t, range, scale_factor, nullptr);
+}
+
+int uvo_scale_factor_front(uvo_ctx* ctx, const double* pts, int n, const double R[9], const double t[3], float range,
+                           double* scale_factor, int* n_front) {
   if (!ctx) return UVO_ERR_INVALID;
   return guarded(&ctx->c, [&] {
     UVO_REQUIRE(scale_factor && R && t && n >= 0 && (n == 0 || pts), "uvo_scale_factor: bad argument");
     *scale_factor = 0.0;
+    if (n_front) *n_front = 0;
     if (n == 0) return;
     Ctx& c = ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
@@ -815,6 +824,7 @@ int uvo_scale_factor(uvo_ctx* ctx, const double* pts, int n, const double R[9], 
     UVO_CUDA(cudaStreamSynchronize(c.stream));
     // compute_scale_factor(float distance, ...): distance / Zmedian, 0.0 when no point is in front of the camera
     *scale_factor = m > 0 ? (double)range / med : 0.0;
+    if (n_front) *n_front = m;
   });
 }
 

@@ -21,6 +21,7 @@
 using namespace uvo;
 
 namespace {
+constexpr int64_t JPEG_MAX_PIXELS = (int64_t)1 << 28;  // 16384 x 16384; the cameras of the reference are 5 MP
 
 // ------------------------------------------------------------------------------------------------ host: parsing
 const uint8_t kNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -57,6 +58,7 @@ struct HuffTab {
       if (code > (1 << l)) throw InvalidArg{"jpeg: bad DHT (not a prefix code)", UVO_ERR_INVALID};
       code <<= 1;
     }
+    memset(huffval, 0, sizeof(huffval));  // entries past nv stay defined: a corrupt code can index them
     memcpy(huffval, vals, nv);
     memset(fast, 0, sizeof(fast));
     int code = 0, k = 0;
@@ -266,6 +268,10 @@ struct Parser {
     L.width = (s[3] << 8) | s[4];
     L.components = s[5];
     if (L.width <= 0 || L.height <= 0) throw InvalidArg{"jpeg: empty frame", UVO_ERR_INVALID};
+    // the bytes come off the network (a ROS CompressedImage): a 65535 x 65535 frame header in a tiny stream must not
+    // size tens of GB of buffers (cv::imdecode has CV_IO_MAX_IMAGE_PIXELS = 2^30 for the same reason)
+    if ((int64_t)L.width * L.height > JPEG_MAX_PIXELS)
+      throw InvalidArg{"jpeg: frame larger than the supported 2^28 pixels", UVO_ERR_UNSUPPORTED};
     if (L.components != 1 && L.components != 3)
       throw InvalidArg{"jpeg: only 1- and 3-component streams are supported", UVO_ERR_UNSUPPORTED};
     if (n < (size_t)(6 + 3 * L.components)) throw InvalidArg{"jpeg: bad SOF", UVO_ERR_INVALID};
@@ -376,7 +382,8 @@ struct Parser {
     const size_t n0 = sink.n;
     int s = huff_decode(b, dc[c.td]);
     if (s > 15) throw InvalidArg{"jpeg: corrupt DC coefficient", UVO_ERR_INVALID};
-    c.pred += s ? receive_extend(b, s) : 0;
+    // valid streams keep the DC predictor within 16 bits; a corrupt one must not run it into signed overflow
+    c.pred = (int)(int16_t)(c.pred + (s ? receive_extend(b, s) : 0));
     if (!SPARSE || (int16_t)c.pred != 0) emit<SPARSE>(out, 0, c.pred);
     const HuffTab& t = ac[c.ta];
     for (int k = 1; k < 64;) {

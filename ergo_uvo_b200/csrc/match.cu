@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include <cfloat>
+#include <mutex>
 
 #include "match.cuh"
 #include "tma.cuh"
@@ -645,10 +646,16 @@ void match_bind_scratch(MatchArgs& a, void* scratch, int cap_q, int cap_t) {
 
 template <int D>
 static void launch_match_dim(Ctx& c, const MatchArgs& a) {
-  static bool attr_set[64] = {};  // function attributes are per device: one process may hold contexts on several GPUs
-  if (c.device >= 64 || !attr_set[c.device]) {
-    UVO_CUDA(cudaFuncSetAttribute(k_knn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeom<D>::SMEM_ALLOC));
-    if (c.device < 64) attr_set[c.device] = true;
+  {
+    // function attributes are per device (one process may hold contexts on several GPUs) and contexts may be driven
+    // from several host threads
+    static std::mutex attr_mutex;
+    static bool attr_set[64] = {};
+    std::lock_guard<std::mutex> lock(attr_mutex);
+    if (c.device >= 64 || !attr_set[c.device]) {
+      UVO_CUDA(cudaFuncSetAttribute(k_knn_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeom<D>::SMEM_ALLOC));
+      if (c.device < 64) attr_set[c.device] = true;
+    }
   }
   if (a.exact_only) {
     UVO_KERNEL(c, "k_knn_flag_all");

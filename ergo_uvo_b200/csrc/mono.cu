@@ -197,10 +197,11 @@ static void mono_frame(uvo_mono* m, const uint8_t* img, size_t pitch, bool from_
       valid = 0;  // "NOT ENOUGH TRIANGULATED POINTS - ASSUMING CONSTANT MOTION"
     } else {
       double sf = 0;
-      ck(uvo_scale_factor(ctx, good.data(), n3d, m->R, m->t, (float)range, &sf));
-      // compute_scale_factor returns 0.0 for an empty set; the node only assigns SF when the converted set is
-      // non-empty (visual_odometry.h:365-374)
-      if (sf != 0.0)
+      int n_front = 0;
+      ck(uvo_scale_factor_front(ctx, good.data(), n3d, m->R, m->t, (float)range, &sf, &n_front));
+      // the node assigns SF whenever good_currCam_points is non-empty (visual_odometry.h:365-374) -- also when
+      // range == 0 (no altimeter message yet) makes it 0 -- and keeps successful_estimate = 1 then
+      if (n_front > 0)
         m->SF = sf;
       else
         valid = 0;

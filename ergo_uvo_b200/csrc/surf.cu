@@ -11,6 +11,7 @@
 //   * descriptors: one block per keypoint does window extraction + INTER_AREA 21x21 resize + Haar + 4x4x4 sums.
 // Every floating-point step keeps the CPU operation order (compiled with -fmad=false).
 #include <cfloat>
+#include <mutex>
 #include <cmath>
 
 #include "surf.cuh"
@@ -660,11 +661,15 @@ void launch_surf_sort(Ctx& c, const SurfBatch& b, int capacity) {
     int P = 2;
     while (P < capacity) P <<= 1;
     const size_t smem = (size_t)P * sizeof(unsigned long long);
-    static bool attr_set[64] = {};
-    if (c.device >= 64 || !attr_set[c.device]) {
-      UVO_CUDA(cudaFuncSetAttribute(k_surf_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    SORT_BLOCK_MAX * (int)sizeof(unsigned long long)));
-      if (c.device < 64) attr_set[c.device] = true;
+    {
+      static std::mutex attr_mutex;
+      static bool attr_set[64] = {};
+      std::lock_guard<std::mutex> lock(attr_mutex);
+      if (c.device >= 64 || !attr_set[c.device]) {
+        UVO_CUDA(cudaFuncSetAttribute(k_surf_sort_block, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SORT_BLOCK_MAX * (int)sizeof(unsigned long long)));
+        if (c.device < 64) attr_set[c.device] = true;
+      }
     }
     UVO_KERNEL(c, "k_surf_sort_block");
     k_surf_sort_block<<<b.n_img, 1024, smem, c.stream>>>(b, capacity);

@@ -428,13 +428,15 @@ class Context:
         return pts[:m.value].copy(), idx[:m.value].copy()
 
     # ------------------------------------------------------------------ VO_utility.h:97-98
-    def compute_scale_factor(self, distance, good_prevCam_points, R, t):
-        """convert_3Dpoints_camera + compute_scale_factor (visual_odometry.h:365-368)."""
+    def compute_scale_factor(self, distance, good_prevCam_points, R, t, with_count=False):
+        """convert_3Dpoints_camera + compute_scale_factor (visual_odometry.h:365-368); with_count also returns the
+        number of points convert_3Dpoints_camera kept (uvo_scale_factor_front)."""
         pts = np.ascontiguousarray(good_prevCam_points, np.float64).reshape(-1, 3)
         sf = C.c_double(0)
-        self._ck(self.lib.uvo_scale_factor(self.h, _p(pts), pts.shape[0], _p(_f64(R, 9)), _p(_f64(t, 3)),
-                                           C.c_float(distance), C.byref(sf)))
-        return sf.value
+        m = C.c_int(0)
+        self._ck(self.lib.uvo_scale_factor_front(self.h, _p(pts), pts.shape[0], _p(_f64(R, 9)), _p(_f64(t, 3)),
+                                                 C.c_float(distance), C.byref(sf), C.byref(m)))
+        return (sf.value, m.value) if with_count else sf.value
 
 
 class StereoVO:

@@ -132,6 +132,10 @@ UVO_API int uvo_optimal_new_camera_matrix(const double K[9], const double D[4], 
 UVO_API int uvo_resize_camera_matrix(int original_width, int original_height, int desired_width, double K_inout[9],
                                      const double D[4], double newK[9], int* out_width, int* out_height);
 
+/* cv::Rodrigues(rvec, R), rotation vector -> 3x3 row-major matrix, as the node calls it on solvePnPRansac's output
+ * (visual_odometry.h:673).  Host-only, no GPU. */
+UVO_API int uvo_rodrigues(const double rvec[3], double R[9]);
+
 /* ---------------------------------------------------------------------------------------------------- ingest */
 /* cvtColor(image, image, COLOR_BayerBGGR2BGR) -- the demosaic from_ros_to_cv_image applies to bayer-format camera
  * messages (math_utility.h:27, math_utility.cpp:161-164), bit-exact with OpenCV's bilinear demosaic.  bayer: 1-channel
@@ -252,6 +256,11 @@ UVO_API int uvo_extract_3dpoints(uvo_ctx* ctx, const float* kp1_host, const floa
 /* convert_3Dpoints_camera + compute_scale_factor -- VO_utility.cpp:23-63 (visual_odometry.h:365-368) */
 UVO_API int uvo_scale_factor(uvo_ctx* ctx, const double* points_nx3_host, int n, const double R[9],
                              const double t[3], float range, double* scale_factor);
+/* the same, also returning how many points convert_3Dpoints_camera kept (the columns of good_currCam_points): the
+ * node assigns SF whenever that set is non-empty -- visual_odometry.h:365-374 -- which is not the same as SF != 0
+ * (range == 0 before the first altimeter message gives SF = 0 with a non-empty set) */
+UVO_API int uvo_scale_factor_front(uvo_ctx* ctx, const double* points_nx3_host, int n, const double R[9],
+                                   const double t[3], float range, double* scale_factor, int* n_front);
 
 /* ---------------------------------------------------------------------------------------------------- K10 */
 /* cv::solvePnPRansac(X, x, K, 0-dist, rvec, tvec, false, iters, err, conf, inliers, SOLVEPNP_EPNP)

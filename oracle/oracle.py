@@ -275,9 +275,12 @@ def compute_median(v):
     return float(lib().orc_compute_median(_p(v), v.shape[0]))
 
 
-def scale_factor(pts, R, t, rng):
+def scale_factor(pts, R, t, rng, with_count=False):
     pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
-    return float(lib().orc_scale_factor(_p(pts), pts.shape[0], _p(_d4(R)), _p(_d4(t)), C.c_float(rng)))
+    m = C.c_int(0)
+    lib().orc_scale_factor_front.restype = C.c_double
+    sf = float(lib().orc_scale_factor_front(_p(pts), pts.shape[0], _p(_d4(R)), _p(_d4(t)), C.c_float(rng), C.byref(m)))
+    return (sf, m.value) if with_count else sf
 
 
 def select_estimation_method(p1, p2, distance):

@@ -670,13 +670,20 @@ extern "C" int orc_extract_3dpoints(const float* kp1, const float* kp2, int n, c
 }
 
 // convert_3Dpoints_camera (keeps the UN-transformed row when the transformed z > 0, App. D-3) + compute_scale_factor
-extern "C" double orc_scale_factor(const double* pts, int n, const double R[9], const double t[3], float range) {
+// convert_3Dpoints_camera + compute_scale_factor; *n_front (nullable) = columns of good_currCam_points, the set whose
+// emptiness -- not the value of SF -- decides whether the node assigns SF (visual_odometry.h:365-374)
+extern "C" double orc_scale_factor_front(const double* pts, int n, const double R[9], const double t[3], float range,
+                                         int* n_front) {
   std::vector<double> z;
   for (int i = 0; i < n; i++) {
     const double* p = pts + 3 * i;
     double zc = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + t[2];
     if (zc > 0) z.push_back(p[2]);
   }
+  if (n_front) *n_front = (int)z.size();
   if (z.empty()) return 0.0;  // caller keeps the previous SF (visual_odometry.h:366-374)
   return (double)range / orc_compute_median(z.data(), (int)z.size());
+}
+extern "C" double orc_scale_factor(const double* pts, int n, const double R[9], const double t[3], float range) {
+  return orc_scale_factor_front(pts, n, R, t, range, nullptr);
 }

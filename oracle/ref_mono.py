@@ -88,8 +88,8 @@ class RefMonoVO:
             if len(good) < p.min_num_3dpoints:
                 valid = False
             else:
-                sf = O.scale_factor(good, self.R, self.t, np.float32(rng))
-                if sf != 0.0:
+                sf, n_front = O.scale_factor(good, self.R, self.t, np.float32(rng), with_count=True)
+                if n_front > 0:  # `if(!good_currCam_points.empty())`, visual_odometry.h:366 -- also when range == 0
                     self.SF = sf
                 else:
                     valid = False

@@ -1,6 +1,6 @@
 // shim/VO_utility_shim.cpp -- reference-side binding (NOT compiled in this repository: it needs the OpenCV C++ and
 // ROS headers the reference builds against; see INTEGRATION.md.  tests/test_shim_compiles.py type-checks it against
-// the reference's own VO_utility.h with the declaration-only stand-ins of shim/stubs).
+// the reference's own VO_utility.h with the declaration-only stand-ins of tests/stubs).
 //
 // Drop-in replacement translation unit for uvo_libraries/src/VO_utility.cpp: it defines the same C++ free functions
 // with the same signatures (uvo_libraries/include/uvo_libraries/VO_utility.h:96-117), reads the same header-defined

@@ -1,15 +1,19 @@
 // shim/cv_interpose.cpp -- optional interposer for the cv:: calls the UVO node makes DIRECTLY, i.e. not through
-// uvo_libraries: cv::triangulatePoints (visual_odometry.h:355, :631) and cv::solvePnPRansac
-// (visual_odometry.h:647-648).  NOT compiled in this repository (needs the OpenCV C++ headers; type-checked against
-// shim/stubs by tests/test_shim_compiles.py).  See INTEGRATION.md, "Unchanged node".
+// uvo_libraries: cv::triangulatePoints (visual_odometry.h:355, :631), cv::solvePnPRansac
+// (visual_odometry.h:647-648) and cv::Rodrigues (visual_odometry.h:673).  The real build needs the OpenCV C++ headers;
+// here it is type-checked against tests/stubs (tests/test_shim_compiles.py) and -- linked against a toy OpenCV in the
+// node's link order -- RUN by tests/test_interpose.py, which checks with LD_DEBUG=bindings that the node's calls bind
+// to these definitions and that unsupported argument shapes fall through to the next definition.  See
+// INTEGRATION.md, "Unchanged node".
 //
 // How it works: this object defines the two functions with OpenCV's own signatures, so an executable that resolves
 // them against this object first (link order: -luvo_libraries before ${OpenCV_LIBS}, or LD_PRELOAD of the shim
 // library) reaches the GPU without a source change in the node.  Each definition takes the GPU route only for the
 // argument shapes the node uses -- 3x4 CV_64F projection matrices with N x 1 CV_32FC2 points; N x 3 CV_64F object
 // points, zero distortion, no extrinsic guess, SOLVEPNP_EPNP -- and hands every other call to the next definition
-// of the same symbol (OpenCV's), found with dlsym(RTLD_NEXT, <own mangled name>).  cv::Rodrigues (:673) is a 3-vector
-// operation and stays on OpenCV.
+// of the same symbol (OpenCV's), found with dlsym(RTLD_NEXT, <own mangled name>).  cv::Rodrigues (:673) takes the
+// library's host-only uvo_rodrigues for the node's shape (a 3-vector in, the matrix out, no Jacobian).
+// cv::KeyPoint::convert (:616-617, :640) is left alone: it copies points the node already holds in host vectors.
 #include <dlfcn.h>
 
 #include <opencv2/opencv.hpp>
@@ -48,6 +52,24 @@ bool all_zero_or_empty(const cv::Mat& m) {
 }  // namespace
 
 namespace cv {
+
+void Rodrigues(InputArray src, OutputArray dst, OutputArray jacobian) {
+  typedef void (*Fn)(InputArray, OutputArray, OutputArray);
+  const Mat r = src.getMat();
+  if (!jacobian.needed() && r.type() == CV_64F && r.rows * r.cols == 3 && r.isContinuous()) {
+    double R[9];
+    if (uvo_rodrigues(r.ptr<double>(), R) == UVO_OK) {
+      dst.create(3, 3, CV_64F);
+      Mat out = dst.getMat();
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) out.at<double>(i, j) = R[3 * i + j];
+      return;
+    }
+  }
+  Fn next = next_definition<Fn>(&cv::Rodrigues);
+  if (!next) throw Exception(Error::StsError, "uvo_b200: no OpenCV Rodrigues to fall through to", __func__, __FILE__, __LINE__);
+  next(src, dst, jacobian);
+}
 
 void triangulatePoints(InputArray projMatr1, InputArray projMatr2, InputArray projPoints1, InputArray projPoints2,
                        OutputArray points4D) {

@@ -1,8 +1,11 @@
-// Declaration-only stand-in for <opencv2/opencv.hpp> (see shim/stubs/README.md).  Only what VO_utility.h,
-// math_utility.h and shim/VO_utility_shim.cpp name; PODs that cross the C ABI have OpenCV's layout.
+// Stand-in for <opencv2/opencv.hpp> (see tests/stubs/README.md): declarations only, of what VO_utility.h,
+// math_utility.h and the two shim sources name; PODs that cross the C ABI have OpenCV's layout.  The classes carry
+// just enough state for tests/interpose/fake_cv_core.cpp to implement them (a toy cv::Mat), which is what lets
+// tests/test_interpose.py link and RUN the cv:: interposer without OpenCV.
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -42,6 +45,8 @@ enum Code { StsError = -2, GpuNotSupported = -216 };
 class Exception : public std::exception {
  public:
   Exception(int code, const String& err, const String& func, const String& file, int line);
+  const char* what() const noexcept override;
+  String msg;
 };
 void error(int code, const String& err, const char* func, const char* file, int line);
 #define CV_Assert(expr) \
@@ -55,6 +60,7 @@ class Mat {
   int rows, cols;
   uchar* data;
   struct MStep {
+    size_t bytes = 0;
     operator size_t() const;
   } step;
   Mat();
@@ -78,6 +84,10 @@ class Mat {
   void push_back(const Mat& m);
   static MatExpr eye(int rows, int cols, int type);
   static MatExpr zeros(int rows, int cols, int type);
+
+ private:
+  int type_ = 0;
+  std::shared_ptr<uchar> owner_;  // toy implementation: tests/interpose/fake_cv_core.cpp
 };
 class MatExpr {
  public:
@@ -92,6 +102,11 @@ class _InputArray {
   template <class T> _InputArray(const std::vector<T>& v);
   Mat getMat(int idx = -1) const;
   bool empty() const;
+
+ protected:
+  enum Kind { NONE, MAT, VEC_POINT2F, VEC_INT, VEC_DOUBLE };
+  int kind_ = NONE;
+  void* obj_ = nullptr;
 };
 class _OutputArray : public _InputArray {
  public:
@@ -106,6 +121,7 @@ typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 const _OutputArray& noArray();
 enum SolvePnPMethod { SOLVEPNP_ITERATIVE = 0, SOLVEPNP_EPNP = 1, SOLVEPNP_P3P = 2 };
+void Rodrigues(InputArray src, OutputArray dst, OutputArray jacobian = noArray());
 void triangulatePoints(InputArray projMatr1, InputArray projMatr2, InputArray projPoints1, InputArray projPoints2,
                        OutputArray points4D);
 bool solvePnPRansac(InputArray objectPoints, InputArray imagePoints, InputArray cameraMatrix, InputArray distCoeffs,

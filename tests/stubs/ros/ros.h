@@ -1,4 +1,4 @@
-// Declaration-only stand-in for ros/ros.h (see shim/stubs/README.md): the logging macros keep printf format checking.
+// Declaration-only stand-in for ros/ros.h (see tests/stubs/README.md): the logging macros keep printf format checking.
 #pragma once
 #include <string>
 namespace ros {

@@ -1,4 +1,4 @@
-// Declaration-only stand-in (see shim/stubs/README.md)
+// Declaration-only stand-in (see tests/stubs/README.md)
 #pragma once
 namespace sensor_msgs {
 struct Range {};

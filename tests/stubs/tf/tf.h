@@ -1,4 +1,4 @@
-// Declaration-only stand-in (see shim/stubs/README.md): math_utility.h names geometry_msgs::Vector3
+// Declaration-only stand-in (see tests/stubs/README.md): math_utility.h names geometry_msgs::Vector3
 #pragma once
 namespace geometry_msgs {
 struct Vector3 {

@@ -50,3 +50,24 @@ def test_mono_gates(ctx):
     r = vo.frame(seq.frames[0], 0.1, 3.0)
     assert r.initialised == 0 and r.n_keypoints == 0 and r.published == 0
     vo.close()
+
+
+def test_mono_zero_range_assigns_zero_scale_and_stays_valid(ctx, oracle):
+    """before the first altimeter message `range` is 0: compute_scale_factor returns 0 with a NON-empty converted set,
+    the node assigns SF = 0, keeps successful_estimate = 1 and publishes zero velocity (visual_odometry.h:365-374,
+    :382) -- the gate is the emptiness of the set, not the value of SF"""
+    import ergo_uvo_b200 as U
+    from oracle.ref_mono import RefMonoVO
+    from tools import synth
+    seq = synth.MonoSequence(640, 480, n_frames=3, tex_size=1024, velocity=(0.02, 0.004, 0.0))
+    p = U.default_params(False)
+    vo = U.MonoVO(ctx, 640, 480, U.make_camera(seq.K, seq.D, seq.newK), p)
+    ref = RefMonoVO(oracle, seq, p)
+    ranges = [seq.ranges[0], seq.ranges[1], 0.0]
+    for k in range(3):
+        r = vo.frame(seq.frames[k], 0.1, ranges[k])
+        o = ref.frame(seq.frames[k], 0.1, ranges[k])
+        assert (r.valid, r.published, r.n_3d) == (o["valid"], o["published"], o["n_3d"])
+    assert o["valid"] == 1 and o["scale_factor"] == 0.0
+    assert r.valid == 1 and r.scale_factor == 0.0 and np.all(np.array(r.velocity) == 0.0)
+    vo.close()

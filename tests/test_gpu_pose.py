@@ -111,3 +111,54 @@ def test_pnp_ransac_degenerate_inputs(ctx):
     x = rs.uniform(0, 1000, (40, 2)).astype(np.float32)
     ok, rv, tv, inl, hyps = ctx.solvePnPRansac(X, x, K, 50, 0.01, 0.99)
     assert not ok and len(inl) == 0 and hyps == 50
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 64, 255, 256, 257, 1000, 4001])
+def test_select_estimation_method_stage(ctx, oracle, n):
+    """K9 (VO_utility.cpp:725-748 + compute_median, math_utility.cpp:65-86) on its own: odd and even counts, medians
+    far from, just below, exactly at and just above DISTANCE -- `median < DISTANCE` means homography"""
+    rs = np.random.RandomState(n)
+    p1 = rs.uniform(0, 1000, (n, 2)).astype(np.float32)
+    ang = rs.uniform(0, 2 * np.pi, n)
+    for scale in (2.0, 9.99, 10.0, 10.01, 40.0):
+        disp = rs.uniform(0.5, 1.5, n) * scale
+        p2 = (p1 + np.stack([np.cos(ang), np.sin(ang)], -1) * disp[:, None]).astype(np.float32)
+        ctx.params.distance = 10
+        assert ctx.select_estimation_method(p1, p2) == oracle.select_estimation_method(p1, p2, 10), (n, scale)
+    # every displacement exactly DISTANCE (3-4-5 triangles, exact in f32): the median equals DISTANCE -> essential
+    p1 = np.round(p1)
+    p2 = p1 + np.array([6.0, 8.0], np.float32)
+    assert ctx.select_estimation_method(p1, p2) is True and oracle.select_estimation_method(p1, p2, 10) is True
+    # the median of an even count is the mean of the middle two: {8, 12} -> 10 -> essential, {8, 11.99} -> homography
+    if n % 2 == 0:
+        d = np.where(np.arange(n) < n // 2, 8.0, 12.0).astype(np.float32)
+        p2 = p1 + np.stack([d, np.zeros(n, np.float32)], -1)
+        assert ctx.select_estimation_method(p1, p2) is True and oracle.select_estimation_method(p1, p2, 10) is True
+        d[n // 2:] = 11.75
+        p2 = p1 + np.stack([d, np.zeros(n, np.float32)], -1)
+        assert ctx.select_estimation_method(p1, p2) is False and oracle.select_estimation_method(p1, p2, 10) is False
+
+
+def test_scale_factor_stage(ctx, oracle):
+    """uvo_scale_factor (convert_3Dpoints_camera + compute_scale_factor, VO_utility.cpp:23-63) on its own: empty set,
+    every point behind the camera, odd / even medians, f32 narrowing of the range (App. D-4), range == 0"""
+    rs = np.random.RandomState(5)
+    R = oracle.rodrigues_vec2mat(np.array([0.02, -0.01, 0.03]))
+    t = np.array([0.05, -0.02, 0.1])
+    assert ctx.compute_scale_factor(3.0, np.zeros((0, 3)), R, t, with_count=True) == (0.0, 0)
+    for n in (1, 2, 5, 6, 255, 256, 257, 3000):
+        pts = np.stack([rs.uniform(-2, 2, n), rs.uniform(-2, 2, n), rs.uniform(0.5, 9, n)], -1)
+        pts[::3, 2] *= -1                      # a third of the points end up behind the current camera
+        for rng in (2.9371, 0.0):
+            sf, m = ctx.compute_scale_factor(rng, pts, R, t, with_count=True)
+            sfo, mo = oracle.scale_factor(pts, R, t, np.float32(rng), with_count=True)
+            assert m == mo and sf == sfo, (n, rng)       # the median is an order statistic: bit-exact
+            if m > 0 and rng > 0:
+                z = np.sort(pts[(pts @ R[2] + t[2]) > 0][:, 2])
+                med = z[len(z) // 2] if len(z) % 2 else (z[len(z) // 2 - 1] + z[len(z) // 2]) / 2.0
+                assert sf == float(np.float32(rng)) / med
+    behind = np.stack([rs.uniform(-1, 1, 50), rs.uniform(-1, 1, 50), -rs.uniform(1, 5, 50)], -1)
+    assert ctx.compute_scale_factor(3.0, behind, np.eye(3), np.zeros(3), with_count=True) == (0.0, 0)
+    # range == 0 with points in front: SF = 0 but the set is non-empty (the node assigns SF = 0 and stays valid)
+    front = np.abs(behind)
+    assert ctx.compute_scale_factor(0.0, front, np.eye(3), np.zeros(3), with_count=True) == (0.0, 50)

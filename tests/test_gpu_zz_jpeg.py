@@ -1,10 +1,9 @@
 """Ingest: uvo_jpeg_decode (host Huffman decoding + k_jpeg_idct + k_jpeg_color) against the oracle, bit-exact -- the
 cv::imdecode(IMREAD_UNCHANGED) inside from_ros_to_cv_image (math_utility.cpp:154-173).
 
-STATUS: the two kernels were written after round 1's GPU minutes were spent and have NOT run on a GPU yet (the host
-half is verified on the CPU: tests/test_jpeg_host.py; the kernels' thread bodies are executed on the CPU over the launch
-grid by tests/test_jpeg_emu.py).  Until their first run these tests are non-strict xfail, so an
-unverified kernel cannot turn the parity suite red; DESIGN.md says the same.  Remove the marker after the first pass."""
+Verified on a B200 (6 / 6 passed as XPASS on the round-1 driver run; the non-strict xfail marker they carried until then
+is gone, so a regression in k_jpeg_idct / k_jpeg_color now turns the suite red).  The host half is also checked on the
+CPU (tests/test_jpeg_host.py) and the kernels' thread bodies by tests/test_jpeg_emu.py."""
 import os
 
 import numpy as np
@@ -12,8 +11,7 @@ import pytest
 
 from conftest import noise_image
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="k_jpeg_idct / k_jpeg_color not yet run on a GPU (see module docstring)")]
+pytestmark = [pytest.mark.gpu]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 

@@ -1,6 +1,6 @@
 """CPU: the reference-side binding (shim/VO_utility_shim.cpp, shim/cv_interpose.cpp) type-checks against the
 reference's OWN header uvo_libraries/VO_utility.h (VO_utility.h:96-117 function declarations, :25-89 globals), with the
-declaration-only ROS / OpenCV stand-ins of shim/stubs.  This is a compile check, not a link or a run: the real build
+declaration-only ROS / OpenCV stand-ins of tests/stubs.  This is a compile check, not a link or a run: the real build
 needs ROS + OpenCV.  /root/reference is read where it lies and only in this container."""
 import os
 import shutil
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_INC = "/root/reference/uvo_libraries/include"
 CXX = shutil.which("g++")
 FLAGS = ["-std=c++14", "-fsyntax-only", "-Wall", "-Wextra", "-Wformat=2", "-Werror", "-Wno-unused-parameter",
-         "-I" + os.path.join(ROOT, "shim", "stubs"), "-I" + REF_INC, "-I" + os.path.join(ROOT, "include")]
+         "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + REF_INC, "-I" + os.path.join(ROOT, "include")]
 
 needs_ref = pytest.mark.skipif(CXX is None or not os.path.exists(os.path.join(REF_INC, "uvo_libraries", "VO_utility.h")),
                                reason="needs g++ and the reference headers (this container only)")
@@ -74,6 +74,6 @@ static_assert(sizeof(cv::DMatch) == 16 && sizeof(uvo_dmatch) == 16, "DMatch");
 static_assert(sizeof(cv::Point2f) == 8, "Point2f");
 int main() { return 0; }
 ''')
-    r = subprocess.run([CXX, "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "shim", "stubs"),
+    r = subprocess.run([CXX, "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "stubs"),
                         "-I" + os.path.join(ROOT, "include"), str(probe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
