@@ -166,3 +166,19 @@ def test_cpp_example_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
         r = subprocess.run([exe, "640", "512", "0.1", "/nonexistent/l%04d", "/nonexistent/r%04d", "0", "2"],
                            capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_rodrigues_host_matches_cv2():
+    """uvo_rodrigues (host-only; cv::Rodrigues(rvec, R) of visual_odometry.h:673) against cv2, no GPU needed"""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    import ergo_uvo_b200 as U
+    lib = U.load()
+    rs = np.random.RandomState(3)
+    vecs = [np.zeros(3), np.array([1e-20, 0, 0]), np.array([np.pi, 0, 0]), np.array([0.01, -0.02, 0.015])]
+    vecs += [rs.uniform(-3, 3, 3) for _ in range(50)]
+    for r in vecs:
+        R = np.zeros(9)
+        assert lib.uvo_rodrigues(r.ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p)) == 0
+        assert np.abs(R.reshape(3, 3) - cv2.Rodrigues(r)[0]).max() <= 4e-16, r
+    assert lib.uvo_rodrigues(None, None) != 0
