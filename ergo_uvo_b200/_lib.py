@@ -73,6 +73,12 @@ class JpegLayout(C.Structure):
     ]
 
 
+class JpegSparse(C.Structure):
+    """uvo_jpeg_sparse: one compressed image as entropy-decoded sparse coefficients"""
+    _fields_ = [("entries", C.c_void_p), ("n_entries", C.c_size_t), ("block_first", C.c_void_p),
+                ("block_count", C.c_void_p), ("layout", JpegLayout)]
+
+
 _lib = None
 
 

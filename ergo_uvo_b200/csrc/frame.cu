@@ -8,8 +8,10 @@
 // count the next stage reads, and one 160-byte result record comes back per frame.
 #include <cstring>
 #include <deque>
+#include <thread>
 
 #include "capi_internal.cuh"
+#include "jpeg.cuh"
 #include "linalg.cuh"
 #include "match.cuh"
 #include "pose.cuh"
@@ -213,6 +215,10 @@ struct uvo_stereo {
   DevBuf<uint8_t> stage[RING][2];
   DevBuf<uint8_t> stage_bayer[RING][2];  // 1-channel staging of uvo_stereo_enqueue_host_bayer (allocated on first use)
   size_t bayer_pitch = 0;
+  // compressed input (uvo_stereo_enqueue_host_sparse / _jpeg): per result slot and eye, the device copy of the sparse
+  // coefficients and the component planes the IDCT writes; for _jpeg also the pinned host side of the entropy decode
+  DevBuf<uint8_t> jpeg_sparse[RING][2], jpeg_planes[RING][2];
+  PinnedBuf<uint32_t> jpeg_host[RING][2];
   cudaEvent_t ev_copied[RING] = {};
   long frame_no = 0;
   std::deque<int> pending;  // result slots in flight, oldest first
@@ -315,10 +321,10 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
 
 // enqueue every kernel of one frame on its lane's stream.  Images: device pointers (host == nullptr) or pinned/pageable
 // host pointers that are first copied into the lane's staging buffers on the same stream.
-enum { SRC_DEVICE = 0, SRC_HOST_BGR = 1, SRC_HOST_BAYER = 2 };
+enum { SRC_DEVICE = 0, SRC_HOST_BGR = 1, SRC_HOST_BAYER = 2, SRC_HOST_SPARSE = 3 };
 
 static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt, int slot,
-                           int src_mode) {
+                           int src_mode, const uvo_jpeg_sparse* const* sparse = nullptr, int bayer_bggr = 0) {
   const bool from_host = src_mode != SRC_DEVICE;
   Ctx& c = s->ctx->c;
   const uvo_params& p = s->prm;
@@ -347,7 +353,23 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     if (s->timing) UVO_CUDA(cudaEventRecord(s->ev[i], c.stream));
   };
   mark(0);
-  if (src_mode == SRC_HOST_BAYER) {
+  if (src_mode == SRC_HOST_SPARSE) {
+    // compressed frames: the sparse coefficients go up on the copy stream, the transform runs on the lane
+    UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
+    for (int i = 0; i < 2; i++) {
+      s->jpeg_sparse[slot][i].ensure(jpeg_sparse_device_bytes(sparse[i]->layout, sparse[i]->n_entries) + 256);
+      s->jpeg_planes[slot][i].ensure(jpeg_plane_bytes(sparse[i]->layout));
+      jpeg_upload_sparse(s->copy_stream, *sparse[i], s->jpeg_sparse[slot][i].get());
+    }
+    UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
+    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_copied[slot], 0));
+    for (int i = 0; i < 2; i++)
+      jpeg_launch_transform(c, sparse[i]->layout, sparse[i]->n_entries, s->jpeg_sparse[slot][i].get(),
+                            s->jpeg_planes[slot][i].get(), bayer_bggr, s->stage[slot][i].get(), s->src_pitch);
+    dL = s->stage[slot][0].get();
+    dR = s->stage[slot][1].get();
+    pitch = s->src_pitch;
+  } else if (src_mode == SRC_HOST_BAYER) {
     // 1-channel bayer images: a third of the bytes over PCIe, demosaiced on the lane's stream into the slot's staging pair
     UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
     for (int i = 0; i < 2; i++)
@@ -584,6 +606,17 @@ void uvo_stereo_destroy(uvo_stereo* s) {
   delete s;
 }
 
+static void stereo_prepare_host_ring(uvo_stereo* s) {
+  if (s->copy_stream) return;
+  // first host frame: the copy stream and the whole staging ring at once (one allocation hiccup, not RING of
+  // them).  Slot k's previous user (frame_no - RING) has always been collected before it is reused.
+  UVO_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < uvo_stereo::RING; k++) {
+    for (int i = 0; i < 2; i++) s->stage[k][i].ensure(s->src_pitch * s->h);
+    UVO_CUDA(cudaEventCreateWithFlags(&s->ev_copied[k], cudaEventDisableTiming));
+  }
+}
+
 static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t* R, size_t pitch, double dt,
                                   int src_mode) {
   if (!s) return UVO_ERR_INVALID;
@@ -597,15 +630,7 @@ static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t
     Ctx& c = s->ctx->c;
     UVO_CUDA(cudaSetDevice(c.device));
     const int slot = (int)(s->frame_no % uvo_stereo::RING);
-    if (from_host && !s->copy_stream) {
-      // first host frame: the copy stream and the whole staging ring at once (one allocation hiccup, not RING of
-      // them).  Slot k's previous user (frame_no - RING) has always been collected before it is reused.
-      UVO_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-      for (int k = 0; k < uvo_stereo::RING; k++) {
-        for (int i = 0; i < 2; i++) s->stage[k][i].ensure(s->src_pitch * s->h);
-        UVO_CUDA(cudaEventCreateWithFlags(&s->ev_copied[k], cudaEventDisableTiming));
-      }
-    }
+    if (from_host) stereo_prepare_host_ring(s);
     if (src_mode == SRC_HOST_BAYER && !s->bayer_pitch) {
       s->bayer_pitch = ((size_t)s->w + 15) & ~(size_t)15;
       for (int k = 0; k < uvo_stereo::RING; k++)
@@ -613,6 +638,93 @@ static int stereo_enqueue_checked(uvo_stereo* s, const uint8_t* L, const uint8_t
     }
     stereo_enqueue(s, L, R, pitch, dt, slot, src_mode);
   });
+}
+
+static void check_sparse(const uvo_stereo* s, const uvo_jpeg_sparse* sp, int bayer_bggr) {
+  UVO_REQUIRE(sp && sp->block_first && sp->block_count && (sp->n_entries == 0 || sp->entries),
+              "uvo_stereo_enqueue_host_sparse: null buffer");
+  UVO_REQUIRE(sp->layout.width == s->w && sp->layout.height == s->h,
+              "compressed image size differs from the handle's (the reference would resize: use uvo_get_image_resized)");
+  const int nc = sp->layout.components;
+  if (!(nc == 3 || (nc == 1 && bayer_bggr)))
+    throw InvalidArg{"compressed input: a 3-component stream, or a 1-component stream with bayer_bggr, is required",
+                     UVO_ERR_UNSUPPORTED};
+  UVO_REQUIRE(sp->layout.coeff_total > 0 && sp->n_entries <= (size_t)sp->layout.coeff_total, "bad sparse image");
+}
+
+int uvo_stereo_enqueue_host_sparse(uvo_stereo* s, const uvo_jpeg_sparse* left, const uvo_jpeg_sparse* right,
+                                   int bayer_bggr, double dt) {
+  if (!s) return UVO_ERR_INVALID;
+  return guarded(&s->ctx->c, [&] {
+    UVO_REQUIRE(dt != 0.0, "uvo_stereo_enqueue: bad argument");
+    check_sparse(s, left, bayer_bggr);
+    check_sparse(s, right, bayer_bggr);
+    UVO_REQUIRE(!bayer_bggr || (s->w >= 3 && s->h >= 3), "bayer input needs w, h >= 3");
+    UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING,
+                "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
+    Ctx& c = s->ctx->c;
+    UVO_CUDA(cudaSetDevice(c.device));
+    stereo_prepare_host_ring(s);
+    const int slot = (int)(s->frame_no % uvo_stereo::RING);
+    const uvo_jpeg_sparse* both[2] = {left, right};
+    stereo_enqueue(s, nullptr, nullptr, 0, dt, slot, SRC_HOST_SPARSE, both, bayer_bggr);
+  });
+}
+
+int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t left_len, const uint8_t* right_jpeg,
+                                 size_t right_len, int bayer_bggr, double dt) {
+  if (!s) return UVO_ERR_INVALID;
+  uvo_jpeg_sparse sp[2];
+  int rc = guarded(&s->ctx->c, [&] {
+    UVO_REQUIRE(left_jpeg && right_jpeg && left_len && right_len, "uvo_stereo_enqueue_host_jpeg: bad argument");
+    UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING,
+                "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
+    UVO_CUDA(cudaSetDevice(s->ctx->c.device));
+    const int slot = (int)(s->frame_no % uvo_stereo::RING);
+    const uint8_t* src[2] = {left_jpeg, right_jpeg};
+    const size_t len[2] = {left_len, right_len};
+    // pinned host side of the slot, sized from the headers: [first: nb][entries: <= total][count: nb bytes]
+    for (int i = 0; i < 2; i++) {
+      uvo_jpeg_layout L;
+      const int e = uvo_jpeg_info(src[i], len[i], &L);
+      if (e != UVO_OK) throw InvalidArg{"uvo_stereo_enqueue_host_jpeg: not a decodable baseline JPEG stream", e};
+      const size_t nb = (size_t)L.coeff_total / 64;
+      s->jpeg_host[slot][i].ensure(nb + (size_t)L.coeff_total + (nb + 3) / 4);
+    }
+    // Huffman decoding, the two images of the pair on two host threads (the slot's previous user was collected, so
+    // its upload is long finished)
+    std::string err[2];
+    int code[2] = {UVO_OK, UVO_OK};
+    auto job = [&](int i) {
+      try {
+        uvo_jpeg_layout L;
+        if (uvo_jpeg_info(src[i], len[i], &L) != UVO_OK) throw InvalidArg{"bad stream", UVO_ERR_INVALID};
+        const size_t nb = (size_t)L.coeff_total / 64, total = (size_t)L.coeff_total;
+        uint32_t* first = s->jpeg_host[slot][i].p;
+        uint32_t* entries = first + nb;
+        uint8_t* count = (uint8_t*)(entries + total);
+        size_t ne = 0;
+        jpeg_host_decode_sparse(src[i], len[i], entries, total, first, count, &ne, &sp[i].layout);
+        sp[i].entries = entries;
+        sp[i].n_entries = ne;
+        sp[i].block_first = first;
+        sp[i].block_count = count;
+      } catch (const InvalidArg& e) {
+        err[i] = e.msg;
+        code[i] = e.code;
+      } catch (const std::exception& e) {
+        err[i] = e.what();
+        code[i] = UVO_ERR_INVALID;
+      }
+    };
+    std::thread right_thread(job, 1);
+    job(0);
+    right_thread.join();
+    for (int i = 0; i < 2; i++)
+      if (code[i] != UVO_OK) throw InvalidArg{(i ? "right image: " : "left image: ") + err[i], code[i]};
+  });
+  if (rc != UVO_OK) return rc;
+  return uvo_stereo_enqueue_host_sparse(s, &sp[0], &sp[1], bayer_bggr, dt);
 }
 
 int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt) {

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "capi_internal.cuh"
+#include "jpeg.cuh"
 #include "jpeg_kernels.cuh"
 
 using namespace uvo;
@@ -437,6 +438,65 @@ __global__ void __launch_bounds__(COLOR_TX* COLOR_TY) k_jpeg_color(const __grid_
 }
 
 }  // namespace
+
+namespace uvo {
+
+size_t jpeg_sparse_device_bytes(const uvo_jpeg_layout& L, size_t n_entries) {
+  const size_t nb = (size_t)L.coeff_total / 64;
+  return sizeof(uint32_t) * (nb + std::max<size_t>(n_entries, 1)) + nb;
+}
+
+size_t jpeg_plane_bytes(const uvo_jpeg_layout& L) { return jpegk::plane_bytes(L); }
+
+void jpeg_upload_sparse(cudaStream_t copy_stream, const uvo_jpeg_sparse& sp, uint8_t* d_sparse) {
+  const size_t nb = (size_t)sp.layout.coeff_total / 64, ne = sp.n_entries;
+  uint32_t* d_first = (uint32_t*)d_sparse;
+  uint32_t* d_entries = d_first + nb;
+  uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(ne, 1));
+  UVO_CUDA(cudaMemcpyAsync(d_first, sp.block_first, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, copy_stream));
+  if (ne) UVO_CUDA(cudaMemcpyAsync(d_entries, sp.entries, sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, copy_stream));
+  UVO_CUDA(cudaMemcpyAsync(d_count, sp.block_count, nb, cudaMemcpyHostToDevice, copy_stream));
+}
+
+void jpeg_launch_transform(Ctx& c, const uvo_jpeg_layout& L, size_t n_entries, uint8_t* d_sparse, uint8_t* d_planes,
+                           int bayer_bggr, uint8_t* d_bgr, size_t bgr_pitch) {
+  const size_t nb = (size_t)L.coeff_total / 64;
+  const int nc = L.components;
+  const bool demosaic = bayer_bggr != 0 && nc == 1;
+  if (!(nc == 3 || demosaic))
+    throw InvalidArg{"jpeg input: a 3-component stream, or a 1-component bayer stream, is required", UVO_ERR_UNSUPPORTED};
+  uint32_t* d_first = (uint32_t*)d_sparse;
+  uint32_t* d_entries = d_first + nb;
+  uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(n_entries, 1));
+  IdctArgs ia;
+  ColorArgs ca;
+  fill_args(L, d_entries, d_first, d_count, d_planes, nc == 3 ? d_bgr : nullptr, bgr_pitch, ia, ca);
+  UVO_KERNEL(c, "k_jpeg_idct");
+  k_jpeg_idct<<<div_up(ia.total_blocks, IDCT_BLOCKS), IDCT_THREADS, 0, c.stream>>>(ia);
+  UVO_LAUNCH_CHECK(c);
+  if (demosaic) {
+    launch_demosaic_bggr(c, ia.c[0].plane, (size_t)L.blocks_x[0] * 8, L.width, L.height, d_bgr, bgr_pitch);
+  } else {
+    UVO_KERNEL(c, "k_jpeg_color");
+    k_jpeg_color<<<dim3(div_up(L.width, COLOR_TX), div_up(L.height, COLOR_TY)), COLOR_TX * COLOR_TY, 0, c.stream>>>(ca);
+    UVO_LAUNCH_CHECK(c);
+  }
+}
+
+void jpeg_host_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries, size_t capacity, uint32_t* first,
+                             uint8_t* count, size_t* n_entries, uvo_jpeg_layout* layout) {
+  Parser H;
+  H.run(jpeg, len, nullptr);
+  const size_t nb = (size_t)H.L.coeff_total / 64;
+  memset(first, 0, sizeof(uint32_t) * nb);  // blocks no scan visits stay empty
+  memset(count, 0, nb);
+  Parser P;
+  P.run_sparse(jpeg, len, entries, capacity, first, count);
+  *n_entries = P.sink.n;
+  *layout = P.L;
+}
+
+}  // namespace uvo
 
 extern "C" {
 

@@ -1,0 +1,24 @@
+// jpeg.cuh -- internal interface of the JPEG ingest (csrc/jpeg.cu) for the whole-frame handles: the device half of
+// the decode (sparse coefficients -> IDCT -> upsampling + colour conversion, or bayer demosaic) launched on a caller's
+// stream into a caller's device image, and the host half (Huffman decoding) callable from any thread.
+// Reference: the cv::imdecode inside from_ros_to_cv_image, math_utility.cpp:154-173.
+#pragma once
+#include "common.cuh"
+
+namespace uvo {
+
+// bytes of the device copy of one image's sparse form: block_first (nb x u32), entries (ne x u32), block_count (nb x u8)
+size_t jpeg_sparse_device_bytes(const uvo_jpeg_layout& L, size_t n_entries);
+// bytes of the component planes the IDCT writes
+size_t jpeg_plane_bytes(const uvo_jpeg_layout& L);
+// H2D of the three arrays on `copy_stream` into d_sparse (laid out as above)
+void jpeg_upload_sparse(cudaStream_t copy_stream, const uvo_jpeg_sparse& sp, uint8_t* d_sparse);
+// k_jpeg_idct + (k_jpeg_color | k_demosaic_bggr) on c.stream: d_sparse -> d_planes -> d_bgr (3-channel interleaved).
+// 3-component streams, or 1-component streams with bayer_bggr set (the compressed-bayer message of the reference)
+void jpeg_launch_transform(Ctx& c, const uvo_jpeg_layout& L, size_t n_entries, uint8_t* d_sparse, uint8_t* d_planes,
+                           int bayer_bggr, uint8_t* d_bgr, size_t bgr_pitch);
+// host half: throws InvalidArg on malformed / unsupported streams.  `first` (nb) and `count` (nb) are zeroed here.
+void jpeg_host_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries, size_t capacity, uint32_t* first,
+                             uint8_t* count, size_t* n_entries, uvo_jpeg_layout* layout);
+
+}  // namespace uvo

@@ -16,7 +16,7 @@ KEYPOINT_DTYPE = np.dtype(
      ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
-__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "jpeg_info", "jpeg_entropy_decode", "jpeg_entropy_decode_sparse", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
+__all__ = ["Context", "default_params", "make_camera", "resize_camera_matrix", "jpeg_info", "jpeg_entropy_decode", "jpeg_entropy_decode_sparse", "SparseImage", "KEYPOINT_DTYPE", "DMATCH_DTYPE", "StereoVO", "MonoVO"]
 
 
 def _p(a):
@@ -104,6 +104,53 @@ def jpeg_entropy_decode_sparse(data):
     if rc != L.UVO_OK:
         raise L.UvoError(rc, "uvo_jpeg_entropy_decode_sparse: corrupt or unsupported JPEG stream")
     return lay, entries[:n.value].copy(), first, count
+
+
+class SparseImage:
+    """A compressed image after the host half of the decode (uvo_jpeg_entropy_decode_sparse), in buffers that stay
+    alive with the object -- pinned host memory when `pinned` (uvo_host_alloc), so that the upload inside
+    uvo_stereo_enqueue_host_sparse is asynchronous.  Building one touches no GPU state and releases the GIL for the
+    duration of the Huffman decode: several can be built in parallel from Python threads."""
+
+    def __init__(self, data, pinned=True):
+        lib = L.load()
+        buf = np.frombuffer(bytes(data), np.uint8)
+        lay = jpeg_info(data)
+        nb, total = int(lay.coeff_total) // 64, int(lay.coeff_total)
+        self._pinned = None
+        words = nb + total + (nb + 3) // 4
+        if pinned:
+            ptr = lib.uvo_host_alloc(C.c_size_t(4 * words))
+            if not ptr:
+                raise MemoryError("uvo_host_alloc failed")
+            self._pinned = ptr
+            self._lib = lib
+            base = np.ctypeslib.as_array((C.c_uint32 * words).from_address(ptr))
+        else:
+            base = np.empty(words, np.uint32)
+        self._base = base
+        first, entries = base[:nb], base[nb:nb + total]
+        count = base[nb + total:].view(np.uint8)[:nb]
+        n = C.c_size_t(0)
+        rc = lib.uvo_jpeg_entropy_decode_sparse(_p(buf), C.c_size_t(len(buf)), _p(entries), C.c_size_t(total),
+                                                _p(first), _p(count), C.byref(n), C.byref(lay))
+        if rc != L.UVO_OK:
+            self.close()
+            raise L.UvoError(rc, "uvo_jpeg_entropy_decode_sparse: corrupt or unsupported JPEG stream")
+        self.layout, self.n_entries = lay, int(n.value)
+        self.c = L.JpegSparse(entries.ctypes.data, n.value, first.ctypes.data, count.ctypes.data, lay)
+        self.nbytes = 4 * nb + 4 * self.n_entries + nb  # what travels to the GPU
+
+    def close(self):
+        if self._pinned:
+            self._lib.uvo_host_free(C.c_void_p(self._pinned))
+            self._pinned = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Context:
@@ -492,6 +539,19 @@ class StereoVO:
         """host pointers to 1-channel BGGR bayer images (demosaiced on the device, uvo_stereo_enqueue_host_bayer)"""
         self.ctx._ck(self.lib.uvo_stereo_enqueue_host_bayer(self.h, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
                                                             C.c_size_t(pitch), C.c_double(dt)))
+
+    def enqueue_host_jpeg(self, left_jpeg, right_jpeg, dt, bayer=False):
+        """both images as JPEG byte strings (uvo_stereo_enqueue_host_jpeg: Huffman decoding inside, on two threads)"""
+        l = np.frombuffer(bytes(left_jpeg), np.uint8)
+        r = np.frombuffer(bytes(right_jpeg), np.uint8)
+        self.ctx._ck(self.lib.uvo_stereo_enqueue_host_jpeg(self.h, _p(l), C.c_size_t(len(l)), _p(r), C.c_size_t(len(r)),
+                                                           int(bool(bayer)), C.c_double(dt)))
+
+    def enqueue_host_sparse(self, left, right, dt, bayer=False):
+        """both images as SparseImage objects (uvo_stereo_enqueue_host_sparse); they must stay alive until the frame
+        has been collected"""
+        self.ctx._ck(self.lib.uvo_stereo_enqueue_host_sparse(self.h, C.byref(left.c), C.byref(right.c),
+                                                             int(bool(bayer)), C.c_double(dt)))
 
     def max_in_flight(self):
         return int(self.lib.uvo_stereo_max_in_flight())

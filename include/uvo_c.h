@@ -189,6 +189,16 @@ UVO_API int uvo_jpeg_entropy_decode(const uint8_t* jpeg, size_t len, int16_t* co
 UVO_API int uvo_jpeg_entropy_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries_host, size_t capacity,
                                            uint32_t* block_first_host, uint8_t* block_count_host, size_t* n_entries,
                                            uvo_jpeg_layout* layout);
+/* one compressed camera image in that form: what the GPU half of the decode takes.  Produced by
+ * uvo_jpeg_entropy_decode_sparse on any host thread (it touches no GPU state), consumed by
+ * uvo_stereo_enqueue_host_sparse; buffers from uvo_host_alloc (pinned) make the upload asynchronous. */
+typedef struct {
+  const uint32_t* entries;       /* n_entries words */
+  size_t n_entries;
+  const uint32_t* block_first;   /* layout.coeff_total / 64 words */
+  const uint8_t* block_count;    /* layout.coeff_total / 64 bytes */
+  uvo_jpeg_layout layout;
+} uvo_jpeg_sparse;
 /* the whole decode: out_host is height x width (1 component) or height x width x 3 BGR, rows out_pitch bytes apart,
  * exactly what cv::imdecode(IMREAD_UNCHANGED) returns; out_capacity in bytes.  bayer_bggr != 0 mirrors
  * `image->format.find("bayer") != npos` (math_utility.cpp:161-164): a 1-component stream is taken as the BGGR mosaic
@@ -352,6 +362,18 @@ UVO_API int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3_host, co
 UVO_API int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1_host, const uint8_t* right1_host,
                                           size_t pitch, double dt);
 UVO_API int uvo_stereo_max_in_flight(void);
+/* COMPRESSED input (the step before the path: the node receives sensor_msgs::CompressedImage and from_ros_to_cv_image
+ * decodes it, math_utility.cpp:154-173).  The frame travels to the GPU as entropy-decoded sparse coefficients (about
+ * a quarter of the raw image's bytes); IDCT, chroma upsampling and colour conversion (or, with bayer_bggr, the demosaic
+ * of a 1-component mosaic) run on the frame's lane ahead of get_image.  Results are identical to enqueueing the image
+ * cv::imdecode would have produced.  The image size must be the handle's.
+ *   _sparse: the caller has run uvo_jpeg_entropy_decode_sparse (typically on several host threads -- the Huffman
+ *            decode is the serial part, ~2 ms per 1280x1024 image and core);
+ *   _jpeg:   the library does it, the two images of the pair on two host threads, inside the call. */
+UVO_API int uvo_stereo_enqueue_host_sparse(uvo_stereo* s, const uvo_jpeg_sparse* left, const uvo_jpeg_sparse* right,
+                                           int bayer_bggr, double dt);
+UVO_API int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t left_len,
+                                         const uint8_t* right_jpeg, size_t right_len, int bayer_bggr, double dt);
 /* The asynchronous entry points replay each lane's fixed runs of kernels as CUDA graphs (three graph launches + a few
  * direct launches per frame instead of ~30 kernel launches; results are identical).  `enable` = 0 goes back to direct
  * launches (diagnostics / A-B measurements); uvo_stereo_graph_launches counts the graph launches made so far. */

@@ -104,3 +104,86 @@ def test_jpeg_decode_bayer_message(ctx, oracle):
         assert np.array_equal(want, cv2.cvtColor(cv2.imdecode(enc, cv2.IMREAD_UNCHANGED), cv2.COLOR_BayerBGGR2BGR))
         # without the flag the mosaic comes back as it is
         assert np.array_equal(ctx.jpeg_decode(enc.tobytes()), oracle.jpeg_decode(enc.tobytes()))
+
+
+def _jpeg_pair_sequence(seq, quality=90, sampling="420"):
+    cv2 = pytest.importorskip("cv2")
+    out = []
+    for (L, R) in seq.frames:
+        enc = []
+        for img in (L, R):
+            ok, e = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                               getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)])
+            assert ok
+            enc.append(e.tobytes())
+        out.append(tuple(enc))
+    return out
+
+
+@pytest.mark.parametrize("mode", ["jpeg", "sparse"])
+def test_stereo_compressed_input_equals_decoded_input(ctx, oracle, small_stereo, mode):
+    """uvo_stereo_enqueue_host_jpeg / _sparse (compressed pair in, Huffman decode on the host, IDCT + colour on the
+    frame's lane) give byte-identical result records and identical intermediate products to uvo_stereo_frame on the
+    images the CPU decode (oracle = cv2 / libjpeg-turbo, pinned) produces: the step before the path,
+    from_ros_to_cv_image (math_utility.cpp:154-173), moved behind the boundary.  20 frames: direct launches, graph
+    capture and graph replay on every lane."""
+    import ergo_uvo_b200 as U
+    from test_gpu_stereo import _make
+    seq = small_stereo
+    jp = _jpeg_pair_sequence(seq)
+    dec = [(oracle.jpeg_decode(l), oracle.jpeg_decode(r)) for (l, r) in jp]
+    assert dec[0][0].shape == (seq.h, seq.w, 3)
+    order = [k % len(jp) for k in range(20)]
+    vo, p = _make(ctx, seq, 3000)
+    want = [vo.frame(np.ascontiguousarray(dec[k][0]), np.ascontiguousarray(dec[k][1]), 0.1) for k in order]
+    taps = (vo.last_keypoints(False), vo.last_matches(True), vo.last_inliers())
+    vo.close()
+    assert any(r.valid for r in want)
+    vo, p = _make(ctx, seq, 3000)
+    got, q, keep = [], 0, []
+    for k in order:
+        if mode == "jpeg":
+            vo.enqueue_host_jpeg(jp[k][0], jp[k][1], 0.1)
+        else:
+            sl, sr = U.SparseImage(jp[k][0]), U.SparseImage(jp[k][1])
+            keep.append((sl, sr))
+            assert sl.nbytes < 0.5 * 3 * seq.w * seq.h       # what crosses PCIe: well under the raw image
+            vo.enqueue_host_sparse(sl, sr, 0.1)
+        q += 1
+        if q >= 6:
+            got.append(vo.collect())
+            q -= 1
+    while q:
+        got.append(vo.collect())
+        q -= 1
+    for a, b in zip(got, want):
+        assert bytes(a) == bytes(b)
+    t = (vo.last_keypoints(False), vo.last_matches(True), vo.last_inliers())
+    assert t[0][0].tobytes() == taps[0][0].tobytes() and t[0][1].tobytes() == taps[0][1].tobytes()
+    assert t[1].tobytes() == taps[1].tobytes() and t[2].tobytes() == taps[2].tobytes()
+    assert vo.graph_launches > 0
+    vo.close()
+
+
+def test_stereo_compressed_input_errors(ctx, small_stereo):
+    import ergo_uvo_b200 as U
+    from test_gpu_stereo import _make
+    cv2 = pytest.importorskip("cv2")
+    seq = small_stereo
+    vo, p = _make(ctx, seq, 3000)
+    good = _jpeg_pair_sequence(seq)[0]
+    with pytest.raises(U.UvoError):                       # truncated stream
+        vo.enqueue_host_jpeg(good[0][:200], good[1], 0.1)
+    ok, small = cv2.imencode(".jpg", noise_image(64, 80, seed=1, channels=3))
+    with pytest.raises(U.UvoError):                       # wrong size
+        vo.enqueue_host_jpeg(small.tobytes(), small.tobytes(), 0.1)
+    ok, gray = cv2.imencode(".jpg", noise_image(seq.h, seq.w, seed=1))
+    with pytest.raises(U.UvoError) as e:                  # 1-component stream without the bayer flag
+        vo.enqueue_host_jpeg(gray.tobytes(), gray.tobytes(), 0.1)
+    assert e.value.code == -5
+    vo.enqueue_host_jpeg(good[0], good[1], 0.1)           # the handle is still usable
+    assert vo.collect().n_left > 0
+    # compressed bayer: a 1-component stream with the flag goes through the demosaic
+    vo.enqueue_host_jpeg(gray.tobytes(), gray.tobytes(), 0.1, bayer=True)
+    assert vo.collect().n_left > 0
+    vo.close()
