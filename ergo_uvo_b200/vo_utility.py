@@ -70,7 +70,7 @@ def resize_camera_matrix(original_width, original_height, desired_width, cameraM
 def jpeg_info(data):
     """header of a JPEG stream (uvo_jpeg_info, host-only): the uvo_jpeg_layout of the decode inside
     from_ros_to_cv_image (math_utility.cpp:154-173)"""
-    buf = np.frombuffer(bytes(data), np.uint8)
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), np.uint8)
     lay = L.JpegLayout()
     rc = L.load().uvo_jpeg_info(_p(buf), C.c_size_t(len(buf)), C.byref(lay))
     if rc != L.UVO_OK:
@@ -112,23 +112,33 @@ class SparseImage:
     uvo_stereo_enqueue_host_sparse is asynchronous.  Building one touches no GPU state and releases the GIL for the
     duration of the Huffman decode: several can be built in parallel from Python threads."""
 
-    def __init__(self, data, pinned=True):
-        lib = L.load()
-        buf = np.frombuffer(bytes(data), np.uint8)
-        lay = jpeg_info(data)
-        nb, total = int(lay.coeff_total) // 64, int(lay.coeff_total)
+    def __init__(self, data=None, pinned=True):
         self._pinned = None
+        self._base = None
+        self._use_pinned = pinned
+        self._lib = L.load()
+        if data is not None:
+            self.decode(data)
+
+    def decode(self, data):
+        """(re)fill this object from a JPEG stream; the buffers are reused when they are large enough, so a ring of
+        SparseImage objects decodes frame after frame without allocating"""
+        lib = self._lib
+        buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), np.uint8)
+        lay = jpeg_info(buf)
+        nb, total = int(lay.coeff_total) // 64, int(lay.coeff_total)
         words = nb + total + (nb + 3) // 4
-        if pinned:
-            ptr = lib.uvo_host_alloc(C.c_size_t(4 * words))
-            if not ptr:
-                raise MemoryError("uvo_host_alloc failed")
-            self._pinned = ptr
-            self._lib = lib
-            base = np.ctypeslib.as_array((C.c_uint32 * words).from_address(ptr))
-        else:
-            base = np.empty(words, np.uint32)
-        self._base = base
+        if self._base is None or len(self._base) < words:
+            self.close()
+            if self._use_pinned:
+                ptr = lib.uvo_host_alloc(C.c_size_t(4 * words))
+                if not ptr:
+                    raise MemoryError("uvo_host_alloc failed")
+                self._pinned = ptr
+                self._base = np.ctypeslib.as_array((C.c_uint32 * words).from_address(ptr))
+            else:
+                self._base = np.empty(words, np.uint32)
+        base = self._base
         first, entries = base[:nb], base[nb:nb + total]
         count = base[nb + total:].view(np.uint8)[:nb]
         n = C.c_size_t(0)
@@ -140,8 +150,10 @@ class SparseImage:
         self.layout, self.n_entries = lay, int(n.value)
         self.c = L.JpegSparse(entries.ctypes.data, n.value, first.ctypes.data, count.ctypes.data, lay)
         self.nbytes = 4 * nb + 4 * self.n_entries + nb  # what travels to the GPU
+        return self
 
     def close(self):
+        self._base = None
         if self._pinned:
             self._lib.uvo_host_free(C.c_void_p(self._pinned))
             self._pinned = None
