@@ -523,7 +523,9 @@ void robust_host(uvo_ctx* ctx, const float* p1, const float* p2, int n, int kind
                  double threshold, int max_iters, double confidence, double model[9], uint8_t* mask, int* n_inliers,
                  int* hyps, int* ok) {
   UVO_REQUIRE(n >= 0 && (n == 0 || (p1 && p2)) && model, "two-view estimation: bad argument");
-  UVO_REQUIRE(method == TV_RANSAC || method == TV_LMEDS, "two-view estimation: method must be 8 (RANSAC) or 4 (LMEDS)");
+  if (!(method == TV_RANSAC || method == TV_LMEDS || (method == TV_LSQ && kind == TV_HOMOGRAPHY)))
+    throw InvalidArg{"two-view estimation: method must be 8 (RANSAC), 4 (LMEDS) or, for findHomography, 0 (all points); "
+                     "RHO (16) and the USAC family (32-38) are not implemented", UVO_ERR_UNSUPPORTED};
   UVO_REQUIRE(confidence > 0 && confidence < 1, "two-view estimation: confidence must be in (0, 1)");
   const int mp = kind == TV_ESSENTIAL ? 5 : 4;
   for (int k = 0; k < 9; k++) model[k] = 0;

@@ -308,9 +308,12 @@ __device__ void jacobi_eigh_rr(double* S, double* Vr, double* w, double* Vt, dou
   for (int i = 0; i < N; i++) tr += fabs(Sc[i * N + i]);
   const double thr = tr * DBL_EPSILON;
   sync();
+  int slot = 0;  // rflag is double-buffered over ALL rounds (a sweep has an odd number of them: r & 1 would reuse a
+                 // slot across the sweep boundary while a slow thread still reads it)
   for (int sweep = 0; sweep < 30; sweep++) {
     bool changed = false;
     for (int r = 0; r < N - 1; r++) {
+      slot ^= 1;
       if (prof) t0 = clock64();
       if (tid < 32) {
         bool rt = false;
@@ -330,10 +333,10 @@ __device__ void jacobi_eigh_rr(double* S, double* Vr, double* w, double* Vt, dou
           ss[p] = ss[q] = s;
         }
         const unsigned m = __ballot_sync(0xffffffffu, rt);  // bit p: the pair whose smaller index is p rotates
-        if (tid == 0) rflag[r & 1] = m;
+        if (tid == 0) rflag[slot] = m;
       }
       sync();
-      const unsigned rmask = rflag[r & 1];
+      const unsigned rmask = rflag[slot];
       if (!rmask) continue;  // uniform over the NT threads
       changed = true;
       if (prof) {

@@ -327,6 +327,8 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   __shared__ DetCand s_cand[DET_LIST];
   __shared__ float s_outer[DET_LIST][9];
   __shared__ int s_ncand;
+  __shared__ int s_dead[DET_LIST];  // candidate beaten by an outer-layer neighbour
+  __shared__ unsigned s_claim[((SURF_MAX_LAYERS - 2) * (TH + 2) * (TW + 2) + 31) / 32];
   const SurfImage& im = b.im[blockIdx.y];
   int t = blockIdx.x, o = 0;
   while (o + 1 < g.n_octaves && t >= g.oct[o + 1].tile_begin) o++;
@@ -350,6 +352,8 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
     return det_at(im.sum, scols, O.layer[lm + 1], step, i, j);
   };
   if (threadIdx.x == 0) s_ncand = 0;
+  if (threadIdx.x < (int)(sizeof(s_claim) / sizeof(unsigned))) s_claim[threadIdx.x] = 0;
+  if (threadIdx.x < DET_LIST) s_dead[threadIdx.x] = 0;
   if (o == 0) {
     // octave 0 (three quarters of all samples): the integral tile arrives as ONE TMA box (cp.async.bulk.tensor.2d,
     // completion on an mbarrier) -- coordinates left of / above the image and past its last row / column are filled
@@ -428,15 +432,30 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   __syncthreads();
   const int ncand = min(s_ncand, DET_LIST);
   // exact values of the skipped middle-layer neighbours of the listed maxima (27 slots per maximum)
-  for (int idx = threadIdx.x; idx < ncand * 27; idx += blockDim.x) {
-    const int c = idx / 27, r = idx - c * 27, a = r / 9, q = r - a * 9;
-    const DetCand cd = s_cand[c];
-    const int l = cd.m - 1 + a;
-    if (l < 1 || l > nmid) continue;
-    const int y = cd.y + q / 3, x = cd.x + q % 3;
-    if (sdet[l - 1][y][x] == DET_SKIPPED) sdet[l - 1][y][x] = mid_exact(l - 1, y, x);  // same bits from any writer
+  // Neighbourhoods of nearby maxima overlap, so a cell can be wanted by several threads: each cell is claimed in a
+  // bitmap (atomicOr) and filled by the one thread that wins the claim -- no thread reads a cell another may write
+  // (compute-sanitizer racecheck clean).  The claim is taken only for cells that were skipped, which every thread
+  // establishes before the first write of the phase.
+  for (int base = 0; base < ncand * 27; base += blockDim.x) {
+    const int idx = base + threadIdx.x;
+    int l = 0, y = 0, x = 0;
+    bool need = false;
+    if (idx < ncand * 27) {
+      const int c = idx / 27, r = idx - c * 27, a = r / 9, q = r - a * 9;
+      const DetCand cd = s_cand[c];
+      l = cd.m - 1 + a;
+      y = cd.y + q / 3;
+      x = cd.x + q % 3;
+      need = l >= 1 && l <= nmid && sdet[l - 1][y][x] == DET_SKIPPED;
+    }
+    __syncthreads();  // every read of this round precedes its writes
+    if (need) {
+      const int cell = ((l - 1) * (TH + 2) + y) * (TW + 2) + x;
+      const unsigned bit = 1u << (cell & 31);
+      if (!(atomicOr(&s_claim[cell >> 5], bit) & bit)) sdet[l - 1][y][x] = mid_exact(l - 1, y, x);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // outer-layer samples of the listed candidates: 9 per (candidate, outer plane); with a single middle layer a
   // candidate needs both outer planes, handled as two passes
   for (int pass = 0; pass < 2; pass++) {
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
       if (l < 0) continue;
       const float v = det_at(im.sum, scols, O.layer[l], step, ti0 + cd.y - 1 + q / 3, tj0 + cd.x - 1 + q % 3);
       s_outer[c][q] = v;
-      if (!(sdet[cd.m - 1][cd.y + 1][cd.x + 1] > v)) s_cand[c].alive = 0;  // benign race: all writers store 0
+      if (!(sdet[cd.m - 1][cd.y + 1][cd.x + 1] > v)) atomicExch(&s_dead[c], 1);  // up to nine writers per candidate
     }
     __syncthreads();
     // finish candidates whose last missing plane was this pass's (pass 0 also finishes those that need none)
@@ -455,7 +474,7 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
       const DetCand cd = s_cand[c];
       const bool needs1 = cd.m == nmid;
       const bool last = pass == 1 ? needs1 : !needs1;
-      if (!last || !cd.alive) continue;
+      if (!last || s_dead[c]) continue;
       float N[3][9];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
@@ -788,7 +807,6 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 constexpr int DESC_THREADS = UVO_DESC_THREADS;
 constexpr int DESC_BUF_ROWS = 168;  // window rows buffered at once (14 KB); taller windows are streamed in chunks
 constexpr int PATCH_STRIDE = 448;   // bytes per keypoint in SurfImage::patch (441 used)
-
 // INTER_AREA tables by window size.  The 21 AreaSpan entries, iscale and is_area_fast are functions of win_size alone
 // (fp64 divisions, ceil / floor); they are tabulated once per device by the same device code the kernel would run, so
 // a keypoint's prologue is a 600-byte load instead of a chain of fp64 divisions on 21 of the block's 256 threads.
@@ -1029,21 +1047,23 @@ __global__ void __launch_bounds__(DESC_THREADS, UVO_DESC_MINB) k_surf_patch(cons
         // t / ncg by a float reciprocal: (t + 0.5) / ncg is at least 0.5 / ncg (>= 0.01) away from any integer and
         // t < 2^12, so the f32 rounding (relative 2^-23) cannot move the floor
         const float inv_ncg = 1.0f / (float)ncg;
+        // pixels of window column j for the four window rows of column group m (image columns xw .. xw + 3), as one
+        // little-endian word; columns / rows outside the image replicate the border
+        auto load4g = [&](int j, int xw) -> unsigned {
+          int y = sy0 - j;
+          if (!interior_y) y = min(max(y, 0), h - 1);
+          const uint8_t* row = img + (size_t)y * pitch;
+          if (xw >= 0 && xw + 3 <= w - 1) return __ldg((const unsigned*)(row + xw));
+          unsigned v = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) v |= (unsigned)__ldg(row + min(max(xw + q, 0), w - 1)) << (8 * q);
+          return v;
+        };
         for (int t = tid; t < ncg * 21; t += DESC_THREADS) {
           const int d = (int)(((float)t + 0.5f) * inv_ncg), m = t - d * ncg;
           const int xw = xa + 4 * m, il0 = xw - x_first;
           const bool x_in = xw >= 0 && xw + 3 <= w - 1;
-          // pixels of window column j for this item's four window rows, as one little-endian word
-          auto load4 = [&](int j) -> unsigned {
-            int y = sy0 - j;
-            if (!interior_y) y = min(max(y, 0), h - 1);
-            const uint8_t* row = img + (size_t)y * pitch;
-            if (x_in) return __ldg((const unsigned*)(row + xw));
-            unsigned v = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) v |= (unsigned)__ldg(row + min(max(xw + q, 0), w - 1)) << (8 * q);
-            return v;
-          };
+          auto load4 = [&](int j) -> unsigned { return load4g(j, xw); };
           float r0, r1, r2, r3;
           if (area_fast) {
             const int j0 = d * iscale;

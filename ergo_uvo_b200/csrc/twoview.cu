@@ -426,17 +426,23 @@ __global__ void __launch_bounds__(FIN_THREADS) k_tv_finalize(const __grid_consta
       a.ctl[5] = 0;
     }
   };
-  if (best_h < 0) {
+  // findHomography(method = 0) (and, in OpenCV, npoints == 4): no sampling -- every point is in the set the kernel
+  // and the refinement run on (fundam.cpp: `tempMask = Mat::ones(...)`, `result = cb->runKernel(src, dst, H) > 0`)
+  const bool lsq = a.method == TV_LSQ;
+  if (best_h < 0 && !lsq) {
     fail();
     return;
   }
   TvModel md;
-  tv_load_model(a, a.best, md);
-  const float thr = (float)a.best[9];
+  float thr = 0.f;
+  if (!lsq) {
+    tv_load_model(a, a.best, md);
+    thr = (float)a.best[9];
+  }
   // mask of the winning hypothesis
   int cnt = 0;
   for (int i = tid; i < n; i += blockDim.x) {
-    const bool in = (n == mp) || tv_error(a, md, i) <= thr;
+    const bool in = lsq || (n == mp) || tv_error(a, md, i) <= thr;
     a.mask[i] = in ? 1 : 0;
     cnt += in ? 1 : 0;
   }
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_tv_finalize(const __grid_consta
     fail();
     return;
   }
-  if (a.kind == TV_ESSENTIAL || n <= 4 || total == 0) {
+  if (!lsq && (a.kind == TV_ESSENTIAL || n <= 4 || total == 0)) {
     if (tid == 0) {
       for (int k = 0; k < 9; k++) a.model_out[k] = a.best[k];
       *a.n_inliers = total;
@@ -496,10 +502,22 @@ __global__ void __launch_bounds__(FIN_THREADS) k_tv_finalize(const __grid_consta
       if (a.mask[i]) dlt_accumulate(nm, a.p1[2 * i], a.p1[2 * i + 1], a.p2[2 * i], a.p2[2 * i + 1], ltl);
     block_sum<45>(ltl, s_red, s_out);
     if (tid == 0) dlt_solve(nm, s_out, s_h);
+  } else if (lsq) {  // runKernel returned 0 and there is no hypothesis to keep: findHomography returns an empty H
+    fail();
+    return;
   } else if (tid == 0) {
     for (int k = 0; k < 9; k++) s_h[k] = a.best[k];  // runKernel returned 0: H keeps the hypothesis value
   }
   __syncthreads();
+  if (lsq && n <= 4) {  // exactly determined: no refinement (`npoints > 4` guards it), every point an inlier
+    if (tid == 0) {
+      for (int k = 0; k < 9; k++) a.model_out[k] = s_h[k];
+      *a.n_inliers = n;
+      a.ctl[4] = 1;
+      a.ctl[5] = 1;
+    }
+    return;
+  }
   // Levenberg-Marquardt exactly as cv::LMSolverImpl::run drives it (levmarq.cpp); small algebra on thread 0
   __shared__ double s_A[64], s_v[8], s_D[8], s_d[8], s_S, s_lambda, s_lc, s_rcur, s_dmax;
   h_refine_eval<true>(a, s_h, s_red, s_out, &s_rmax);
@@ -601,6 +619,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_tv_finalize(const __grid_consta
     for (int w = 0; w < FIN_THREADS / 32; w++) tot += s_cnt[w];
     for (int k = 0; k < 9; k++) a.model_out[k] = s_h[k];
     *a.n_inliers = tot;
+    if (lsq) a.ctl[4] = 1;  // one kernel call
     a.ctl[5] = 1;
   }
 }
@@ -744,6 +763,7 @@ static int update_num_iters_host(double p, double ep, int model_points, int max_
 }
 
 int robust_iterations(int method, int model_points, double confidence, int max_iters) {
+  if (method == TV_LSQ) return 1;
   max_iters = std::max(max_iters, 1);
   if (method == TV_LMEDS) return std::max(update_num_iters_host(confidence, 0.45, model_points, max_iters), 3);
   return max_iters;
@@ -777,6 +797,13 @@ void robust_bind_scratch(RobustArgs& a, void* scratch) {
 }
 
 void launch_robust(Ctx& c, const RobustArgs& a) {
+  if (a.method == TV_LSQ) {  // no hypotheses: the kernel on all points + the refinement, both inside k_tv_finalize
+    UVO_REQUIRE(a.kind == TV_HOMOGRAPHY, "method 0 exists for findHomography only");
+    UVO_KERNEL(c, "k_tv_finalize");
+    k_tv_finalize<<<1, FIN_THREADS, 0, c.stream>>>(a);
+    UVO_LAUNCH_CHECK(c);
+    return;
+  }
   const uint32_t* rng = rng_table_device(c);
   const int mph = a.kind == TV_ESSENTIAL ? TV_MAX_MODELS : 1;
   if (a.kind == TV_ESSENTIAL && a.n > 0) {

@@ -8,6 +8,7 @@ namespace uvo {
 
 constexpr int TV_HOMOGRAPHY = 0, TV_ESSENTIAL = 1;
 constexpr int TV_RANSAC = 8, TV_LMEDS = 4;
+constexpr int TV_LSQ = 0;  // findHomography(method = 0): "a regular method using all the points" (no sampling)
 constexpr int TV_MAX_MODELS = 10;  // essential matrices per 5-point hypothesis
 
 struct RobustArgs {
@@ -15,7 +16,7 @@ struct RobustArgs {
   const float* p2;
   int n;
   int kind;    // TV_HOMOGRAPHY / TV_ESSENTIAL
-  int method;  // TV_RANSAC / TV_LMEDS
+  int method;  // TV_RANSAC / TV_LMEDS / TV_LSQ (homography only)
   double threshold, confidence;
   int iters;   // hypotheses generated: maxIters (RANSAC) or the fixed LMedS count
   double K[4]; // essential: fx, fy, cx, cy

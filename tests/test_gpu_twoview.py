@@ -134,3 +134,38 @@ def test_batched_ransac_sweep_config_d(ctx):
     E2, m2, _ = ctx.findEssentialMat(p1, p2, K4, 8, 1 - 2.0 ** -53, 1.0, 4096)
     assert hyp == 4096 and np.array_equal(m, m2)
     assert m.sum() > 2000  # the true model (2500 inliers) is found
+
+
+@pytest.mark.parametrize("n,noise", [(4, 0.0), (5, 0.3), (60, 0.5), (2000, 0.3)])
+def test_find_homography_method_0_all_points(ctx, n, noise):
+    """cv::findHomography(p1, p2, 0): "a regular method using all the points" (mono_VO_parameters.yaml:23 lists it) --
+    the DLT kernel on every point, the 10 Levenberg-Marquardt iterations for n > 4, and the mask cv2 4.13 returns (the
+    refined model's at the threshold).  Against the numpy oracle and cv2 itself."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import twoview as T
+    rs = np.random.RandomState(n)
+    p1 = rs.uniform(0, 1000, (n, 2)).astype(np.float32)
+    Ht = np.array([[1.01, 0.02, 5], [-0.01, 0.99, -3], [1e-5, 2e-5, 1]])
+    q = np.c_[p1, np.ones(n)] @ Ht.T
+    p2 = (q[:, :2] / q[:, 2:] + rs.randn(n, 2) * noise).astype(np.float32)
+    H, mask, hyps = ctx.findHomography(p1, p2, 0, 3.0, 2000, 0.995)
+    Ho, mo, _ = T.find_homography(p1, p2, 0, 3.0)
+    Hc, mc = cv2.findHomography(p1, p2, 0, 3.0)
+    assert H is not None and hyps == 1
+    assert np.array_equal(mask, mo) and np.array_equal(mask, mc.ravel())
+    assert np.abs(H - Ho).max() <= 1e-6 * max(1.0, np.abs(Ho).max()) and np.abs(H - Hc).max() <= 1e-5 * np.abs(Hc).max()
+
+
+def test_find_homography_method_0_degenerate_and_unsupported(ctx):
+    import ergo_uvo_b200 as U
+    p = np.zeros((10, 2), np.float32)                       # all points identical: runKernel fails -> no model
+    H, mask, hyps = ctx.findHomography(p, p, 0, 3.0, 2000, 0.995)
+    assert H is None and not mask.any()
+    rs = np.random.RandomState(0)
+    a, b = rs.rand(20, 2).astype(np.float32) * 100, rs.rand(20, 2).astype(np.float32) * 100
+    for method in (16, 32, 38):                             # RHO, USAC_DEFAULT, USAC_MAGSAC: not implemented
+        with pytest.raises(U.UvoError) as e:
+            ctx.findHomography(a, b, method, 3.0, 2000, 0.995)
+        assert e.value.code == -5
+    with pytest.raises(U.UvoError):                         # findEssentialMat has no method 0
+        ctx.findEssentialMat(a, b, np.array([[1300.0, 0, 640], [0, 1300.0, 512], [0, 0, 1]]), 0, 0.99, 1.0, 1000)
