@@ -494,7 +494,31 @@ def run_gpu(args):
                 comp_valid += v_
                 comp_bytes += b_
             pool.shutdown()
-            comp = {"region_ms": comp_regions, "frames_per_region": n_comp, "valid": comp_valid,
+            # the same with Huffman decoding ON THE GPU: one host thread hands the JPEG bytes to
+            # uvo_stereo_enqueue_host_jpeg (marker walk + unstuffed copy of the scan on the host, nothing else)
+            def run_compressed_gpu(n, start):
+                valid, q = 0, 0
+                for i in range(n):
+                    k = pingpong(start + i, N_DISTINCT)
+                    vo.enqueue_host_jpeg(enc[k][0], enc[k][1], dt_frame)
+                    q += 1
+                    if q >= inflight:
+                        valid += vo.collect().valid
+                        q -= 1
+                while q:
+                    valid += vo.collect().valid
+                    q -= 1
+                return valid
+            run_compressed_gpu(48, 0)
+            gpu_regions = []
+            for r_ in range(min(args.regions, 5)):
+                barrier()
+                t0 = time.perf_counter()
+                run_compressed_gpu(n_comp, 48 + r_ * n_comp)
+                barrier()
+                gpu_regions.append((time.perf_counter() - t0) * 1e3)
+            comp = {"gpu_region_ms": gpu_regions, "gpu_entropy_frames": vo.gpu_entropy_frames,
+                    "gpu_h2d_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])) + 2 * 9500.0,"region_ms": comp_regions, "frames_per_region": n_comp, "valid": comp_valid,
                     "h2d_bytes_per_step": comp_bytes / float(n_comp * len(comp_regions)),
                     "jpeg_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])),
                     "host_threads": args.jpeg_threads}
@@ -535,10 +559,11 @@ def run_gpu(args):
 
     # ---- max over ranks (per region), then the median region
     comp_ms = float(np.median(comp["region_ms"])) if comp else 0.0
+    comp_gpu_ms = float(np.median(comp["gpu_region_ms"])) if comp else 0.0
     all_ms, v = aggregate_over_ranks(dist if world > 1 else None,
-                                     dev_regions + host_regions + [ms_long_dev, ms_long_host, comp_ms],
+                                     dev_regions + host_regions + [ms_long_dev, ms_long_host, comp_ms, comp_gpu_ms],
                                      [float(valid_dev), float(valid_host)], "cuda")
-    comp_ms = all_ms[-1]
+    comp_ms, comp_gpu_ms = all_ms[-2], all_ms[-1]
     R_ = args.regions
     dev_regions, host_regions = all_ms[:R_], all_ms[R_:2 * R_]
     ms_long_dev, ms_long_host = all_ms[2 * R_], all_ms[2 * R_ + 1]
@@ -637,7 +662,12 @@ def run_gpu(args):
                 "jpeg_bytes_per_step": comp["jpeg_bytes_per_step"], "host_threads_per_gpu": comp["host_threads"],
                 "region_ms": comp["region_ms"],
                 "api": "uvo_jpeg_entropy_decode_sparse on host threads + uvo_stereo_enqueue_host_sparse + "
-                       "uvo_stereo_collect; wall clock, barrier + synchronize on both sides"},
+                       "uvo_stereo_collect; wall clock, barrier + synchronize on both sides",
+                # Huffman decoding on the GPU (k_jpeg_huff): one host thread, JPEG bytes in, scan bytes over PCIe
+                "gpu_entropy": {"value": comp["frames_per_region"] * world / (comp_gpu_ms * 1e-3), "unit": "frames/s",
+                                "h2d_bytes_per_step": comp["gpu_h2d_bytes_per_step"], "host_threads_per_gpu": 1,
+                                "region_ms": comp["gpu_region_ms"], "frames_on_gpu_decoder": comp["gpu_entropy_frames"],
+                                "api": "uvo_stereo_enqueue_host_jpeg + uvo_stereo_collect"}},
             "host_enqueue_us_per_frame": 1e6 * host_enqueue_s[0] / max(host_enqueue_s[1], 1),
             # kernels the library launched inside the timed regions of `value` (graph-replayed kernels counted one by
             # one), per region of `steps` frames; host-side launch calls are graph launches + direct launches

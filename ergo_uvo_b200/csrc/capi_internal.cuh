@@ -24,6 +24,10 @@ struct uvo_ctx {
   int last_match_fallbacks = 0;  // queries of the last matcher call that took the exact full-scan path
   uvo::PinnedBuf<uint32_t> jpeg_coef;  // uvo_jpeg_decode: sparse quantised coefficients, host side of the H2D copy
   int match_exact_only = 0;      // diagnostics (uvo_match_exact_only): stage-level matcher calls skip the tcgen05 pass
+  int jpeg_gpu_entropy = 1;      // uvo_jpeg_gpu_entropy: Huffman decoding on the GPU for streams that qualify
+  int jpeg_last_route = 0;       // 1: the last uvo_jpeg_decode ran the GPU entropy decoder, 0: the host decoder
+  int jpeg_last_rounds = 0;      // synchronisation rounds of that decode
+  int jpeg_stamps[64] = {};      // diagnostics: [0] count, then 64-bit globaltimer stamps of the decode's phases
   int pnp_profile = 0;           // diagnostics (uvo_pnp_profile): uvo_solve_pnp_ransac records clock64 phase stamps
   long long pnp_stamps[32] = {};
 };

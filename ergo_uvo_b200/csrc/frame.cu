@@ -94,7 +94,7 @@ struct ResultParams {
 
 // gates 3-5 (visual_odometry.h:626, :634, :665), Rodrigues + t_prevCam_currCam = -R^T t (:673-675), velocity (:148-159)
 __global__ void k_frame_result(FrameCtrl* ctrl, FrameState* st, const double* pnp_result, const int* n_inl_dev,
-                               const int* hyps_dev, uvo_stereo_result* out, ResultParams p) {
+                               const int* hyps_dev, uvo_stereo_result* out, ResultParams p, const int* jpeg_status) {
   const GateParams& g = p.g;
   uvo_stereo_result r;
   memset(&r, 0, sizeof(r));
@@ -121,6 +121,9 @@ __global__ void k_frame_result(FrameCtrl* ctrl, FrameState* st, const double* pn
       r.tvec[i] = pnp_result[3 + i];
     }
   }
+  // a compressed image whose entropy-coded data was corrupt decodes to an empty image: reported, not published
+  const bool bad_input = jpeg_status && (jpeg_status[0] | jpeg_status[2]);
+  if (bad_input) gate = -2;
   if (was_init) {
     r.gate = gate;
     r.valid = gate == 0 ? 1 : 0;
@@ -130,7 +133,7 @@ __global__ void k_frame_result(FrameCtrl* ctrl, FrameState* st, const double* pn
       for (int i = 0; i < 3; i++) st->t_prev_curr[i] = -(R[i] * r.tvec[0] + R[3 + i] * r.tvec[1] + R[6 + i] * r.tvec[2]);
     }
   } else {
-    r.gate = gate == -1 ? -1 : 0;
+    r.gate = gate < 0 ? gate : 0;
     r.valid = 0;
   }
   r.initialised = (was_init || ctrl->n_as > 0) ? 1 : 0;
@@ -183,6 +186,7 @@ struct Lane {
   DevBuf<double> pnp_result;
   DevBuf<int32_t> inliers;
   DevBuf<int> small;  // [0] n_inliers [1] hyps [2..3] best
+  DevBuf<int> jpeg_status;  // GPU entropy decode of the lane's frame: [0] / [2] error of the left / right image
   DevBuf<uint8_t> pnp_scratch;
   cudaEvent_t ev_gather = nullptr, ev_consumed = nullptr, ev_result = nullptr;
   bool used = false;
@@ -225,6 +229,8 @@ struct uvo_stereo {
   cudaEvent_t ev[UVO_N_STAGES + 1] = {};
   cudaEvent_t ev_done[RING] = {};  // one per result slot, re-recorded
   bool use_graphs = true;          // uvo_stereo_set_graphs
+  bool gpu_entropy = true;         // uvo_stereo_set_gpu_entropy: Huffman decoding of compressed input on the GPU
+  long gpu_entropy_frames = 0;
   long graph_launches = 0;
   bool timing = false;
   float stage_ms[UVO_N_STAGES] = {};
@@ -302,6 +308,8 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
     l.pnp_result.ensure(8);
     l.small.ensure(8);
     UVO_CUDA(cudaMemsetAsync(l.small.get(), 0, 8 * sizeof(int), c.stream));
+    l.jpeg_status.ensure(80);
+    UVO_CUDA(cudaMemsetAsync(l.jpeg_status.get(), 0, 80 * sizeof(int), c.stream));
     UVO_CUDA(cudaMemsetAsync(l.pnp_result.get(), 0, 8 * sizeof(double), c.stream));
     l.pnp_scratch.ensure(pnp_scratch_bytes(cap, prm->iterations_count) + 4096);
     UVO_CUDA(cudaEventCreateWithFlags(&l.ev_gather, cudaEventDisableTiming));
@@ -321,10 +329,11 @@ static void stereo_init(uvo_stereo* s, uvo_ctx* ctx, int w, int h, const uvo_cam
 
 // enqueue every kernel of one frame on its lane's stream.  Images: device pointers (host == nullptr) or pinned/pageable
 // host pointers that are first copied into the lane's staging buffers on the same stream.
-enum { SRC_DEVICE = 0, SRC_HOST_BGR = 1, SRC_HOST_BAYER = 2, SRC_HOST_SPARSE = 3 };
+enum { SRC_DEVICE = 0, SRC_HOST_BGR = 1, SRC_HOST_BAYER = 2, SRC_HOST_SPARSE = 3, SRC_HOST_JPEG_GPU = 4 };
 
 static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt, int slot,
-                           int src_mode, const uvo_jpeg_sparse* const* sparse = nullptr, int bayer_bggr = 0) {
+                           int src_mode, const uvo_jpeg_sparse* const* sparse = nullptr, int bayer_bggr = 0,
+                           const JpegGpuJob* gpu_jobs = nullptr) {
   const bool from_host = src_mode != SRC_DEVICE;
   Ctx& c = s->ctx->c;
   const uvo_params& p = s->prm;
@@ -353,7 +362,33 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
     if (s->timing) UVO_CUDA(cudaEventRecord(s->ev[i], c.stream));
   };
   mark(0);
-  if (src_mode == SRC_HOST_SPARSE) {
+  bool jpeg_on_gpu = false;
+  if (src_mode == SRC_HOST_JPEG_GPU) {
+    // compressed frames, Huffman decoding on the GPU: the scan bytes and the table plan go up on the copy stream
+    // (one copy per image), then k_jpeg_huff (both images in one cooperative launch) + IDCT + colour on the lane
+    UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
+    uint8_t* d_buf[2];
+    uint8_t* d_planes[2];
+    uint8_t* d_bgr[2];
+    for (int i = 0; i < 2; i++) {
+      const size_t need = jpeg_gpu_device_bytes(gpu_jobs[i].L, gpu_jobs[i].upload_bytes);
+      if (s->jpeg_sparse[slot][i].n < need) s->jpeg_sparse[slot][i].ensure(need + need / 4);  // head-room: scans vary
+      s->jpeg_planes[slot][i].ensure(jpeg_plane_bytes(gpu_jobs[i].L));
+      d_buf[i] = s->jpeg_sparse[slot][i].get();
+      d_planes[i] = s->jpeg_planes[slot][i].get();
+      d_bgr[i] = s->stage[slot][i].get();
+      UVO_CUDA(cudaMemcpyAsync(d_buf[i], s->jpeg_host[slot][i].p, gpu_jobs[i].upload_bytes, cudaMemcpyHostToDevice,
+                               s->copy_stream));
+    }
+    UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
+    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_copied[slot], 0));
+    jpeg_gpu_launch(c, 2, gpu_jobs, d_buf, d_planes, bayer_bggr, d_bgr, s->src_pitch, L.jpeg_status.get());
+    jpeg_on_gpu = true;
+    s->gpu_entropy_frames++;
+    dL = d_bgr[0];
+    dR = d_bgr[1];
+    pitch = s->src_pitch;
+  } else if (src_mode == SRC_HOST_SPARSE) {
     // compressed frames: the sparse coefficients go up on the copy stream, the transform runs on the lane
     UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
     for (int i = 0; i < 2; i++) {
@@ -567,7 +602,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   ResultParams rp{g, dt};
   UVO_KERNEL(c, "k_frame_result");
   k_frame_result<<<1, 1, 0, c.stream>>>(ctrl, s->state.get(), L.pnp_result.get(), L.small.get(), L.small.get() + 1,
-                                        s->d_result.get() + slot, rp);
+                                        s->d_result.get() + slot, rp, jpeg_on_gpu ? L.jpeg_status.get() : nullptr);
   UVO_LAUNCH_CHECK(c);
   UVO_CUDA(cudaEventRecord(L.ev_result, c.stream));
   UVO_CUDA(cudaMemcpyAsync(s->h_result.p + slot, s->d_result.get() + slot, sizeof(uvo_stereo_result),
@@ -675,14 +710,38 @@ int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t
                                  size_t right_len, int bayer_bggr, double dt) {
   if (!s) return UVO_ERR_INVALID;
   uvo_jpeg_sparse sp[2];
+  JpegGpuJob gpu_jobs[2];
+  bool use_gpu = false;
   int rc = guarded(&s->ctx->c, [&] {
-    UVO_REQUIRE(left_jpeg && right_jpeg && left_len && right_len, "uvo_stereo_enqueue_host_jpeg: bad argument");
+    UVO_REQUIRE(left_jpeg && right_jpeg && left_len && right_len && dt != 0.0, "uvo_stereo_enqueue_host_jpeg: bad argument");
     UVO_REQUIRE((int)s->pending.size() < uvo_stereo::RING,
                 "too many frames in flight (uvo_stereo_max_in_flight): call uvo_stereo_collect");
     UVO_CUDA(cudaSetDevice(s->ctx->c.device));
     const int slot = (int)(s->frame_no % uvo_stereo::RING);
     const uint8_t* src[2] = {left_jpeg, right_jpeg};
     const size_t len[2] = {left_len, right_len};
+    if (s->gpu_entropy) {
+      // Huffman decoding on the GPU: the host only walks the markers and copies the scan with its stuffed zeros
+      // removed into the slot's pinned staging.  Streams the GPU decoder does not take fall through to the host one.
+      bool ok = true;
+      for (int i = 0; i < 2 && ok; i++) {
+        const size_t hb = jpeg_gpu_host_bytes(len[i]);
+        s->jpeg_host[slot][i].ensure((hb + 3) / 4 + 1024);
+        ok = jpeg_gpu_prepare(src[i], len[i], (uint8_t*)s->jpeg_host[slot][i].p, s->jpeg_host[slot][i].n * 4, &gpu_jobs[i]);
+        if (ok) {
+          const uvo_jpeg_layout& L = gpu_jobs[i].L;
+          UVO_REQUIRE(L.width == s->w && L.height == s->h,
+                      "compressed image size differs from the handle's (the reference would resize: use uvo_get_image_resized)");
+          if (!(L.components == 3 || (L.components == 1 && bayer_bggr)))
+            throw InvalidArg{"compressed input: a 3-component stream, or a 1-component stream with bayer_bggr, is required",
+                             UVO_ERR_UNSUPPORTED};
+        }
+      }
+      if (ok) {
+        use_gpu = true;
+        return;
+      }
+    }
     // pinned host side of the slot, sized from the headers: [first: nb][entries: <= total][count: nb bytes]
     for (int i = 0; i < 2; i++) {
       uvo_jpeg_layout L;
@@ -724,8 +783,23 @@ int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t
       if (code[i] != UVO_OK) throw InvalidArg{(i ? "right image: " : "left image: ") + err[i], code[i]};
   });
   if (rc != UVO_OK) return rc;
+  if (use_gpu)
+    return guarded(&s->ctx->c, [&] {
+      UVO_REQUIRE(!bayer_bggr || (s->w >= 3 && s->h >= 3), "bayer input needs w, h >= 3");
+      stereo_prepare_host_ring(s);
+      const int slot = (int)(s->frame_no % uvo_stereo::RING);
+      stereo_enqueue(s, nullptr, nullptr, 0, dt, slot, SRC_HOST_JPEG_GPU, nullptr, bayer_bggr, gpu_jobs);
+    });
   return uvo_stereo_enqueue_host_sparse(s, &sp[0], &sp[1], bayer_bggr, dt);
 }
+
+int uvo_stereo_set_gpu_entropy(uvo_stereo* s, int enable) {
+  if (!s) return UVO_ERR_INVALID;
+  s->gpu_entropy = enable != 0;
+  return UVO_OK;
+}
+
+int64_t uvo_stereo_gpu_entropy_frames(const uvo_stereo* s) { return s ? (int64_t)s->gpu_entropy_frames : 0; }
 
 int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, size_t pitch, double dt) {
   return stereo_enqueue_checked(s, dL, dR, pitch, dt, SRC_DEVICE);
@@ -749,6 +823,8 @@ int uvo_stereo_collect(uvo_stereo* s, uvo_stereo_result* out) {
     *out = s->h_result.p[slot];
     if (out->gate == -1)
       throw InvalidArg{"more SURF keypoints than max_features: raise uvo_params.max_features", UVO_ERR_CAPACITY};
+    if (out->gate == -2)
+      throw InvalidArg{"corrupt or truncated entropy-coded data in a compressed input image", UVO_ERR_INVALID};
   });
 }
 

@@ -12,11 +12,14 @@
 //                 16-bit fixed-point YCbCr -> BGR conversion; interleaved u8 output
 // Integer arithmetic throughout, the same operations in the same order as libjpeg-turbo: results are bit-identical.
 // Not handled: progressive / arithmetic / lossless / 12-bit streams, CMYK, Adobe RGB -> UVO_ERR_UNSUPPORTED.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
 
 #include "capi_internal.cuh"
 #include "jpeg.cuh"
+#include "jpeg_huff.cuh"
 #include "jpeg_kernels.cuh"
 
 using namespace uvo;
@@ -437,6 +440,515 @@ __global__ void __launch_bounds__(COLOR_TX* COLOR_TY) k_jpeg_color(const __grid_
   color_thread(a, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
+
+// ------------------------------------------------------------------------------------------------ Huffman decode on the GPU
+// see jpeg_huff.cuh.  Host side: walk the markers, build the table plan, copy the scan with the stuffed zeros removed.
+// Returns false for streams this path does not take (several scans, restart intervals, table ids above 1): the caller
+// uses the host decoder for those.  Throws on malformed streams like the host decoder.
+struct GpuPlanOut {
+  uvo_jpeg_layout L;
+  size_t scan_bytes;
+};
+
+bool build_gpu_plan(const uint8_t* d, size_t len, JhPlan* plan, uint8_t* scan_out, size_t scan_cap, GpuPlanOut* out) {
+  struct Walker : Parser {
+    const uint8_t* sos = nullptr;
+    size_t sos_n = 0;
+    const uint8_t* data = nullptr;
+    const uint8_t* end = nullptr;
+    int scans = 0;
+  } P;
+  // the marker walk of Parser::walk, stopping at the first SOS with the position of its data
+  if (!d || len < 4 || d[0] != 0xFF || d[1] != 0xD8) throw InvalidArg{"jpeg: not a JPEG stream (no SOI)", UVO_ERR_INVALID};
+  size_t i = 2;
+  while (i + 4 <= len) {
+    if (d[i] != 0xFF || d[i + 1] == 0xFF) {
+      i++;
+      continue;
+    }
+    const int m = d[i + 1];
+    i += 2;
+    if (m == 0xD9) break;
+    if (m == 0x01 || m == 0x00 || (m >= 0xD0 && m <= 0xD7)) continue;
+    const size_t seg = ((size_t)d[i] << 8) | d[i + 1];
+    if (seg < 2 || i + seg > len) throw InvalidArg{"jpeg: truncated marker segment", UVO_ERR_INVALID};
+    const uint8_t* s = d + i + 2;
+    const size_t n = seg - 2;
+    if (m == 0xDB) P.dqt(s, n);
+    else if (m == 0xC4) P.dht(s, n);
+    else if (m == 0xC0 || m == 0xC1) P.sof(s, n);
+    else if (m == 0xDD) {
+      if (n < 2) throw InvalidArg{"jpeg: bad DRI", UVO_ERR_INVALID};
+      P.restart = (s[0] << 8) | s[1];
+    } else if (m == 0xEE) {
+      if (n >= 12 && memcmp(s, "Adobe", 5) == 0) P.adobe_transform = s[11];
+    } else if (m == 0xDA) {
+      if (!P.have_sof) throw InvalidArg{"jpeg: SOS before SOF", UVO_ERR_INVALID};
+      P.sos = s;
+      P.sos_n = n;
+      P.data = d + i + seg;
+      P.end = d + len;
+      break;
+    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC8) {
+      throw InvalidArg{"jpeg: only baseline / extended-sequential Huffman streams are supported", UVO_ERR_UNSUPPORTED};
+    }
+    i += seg;
+  }
+  if (!P.have_sof || !P.sos) throw InvalidArg{"jpeg: no frame header / no scan", UVO_ERR_INVALID};
+  if (P.L.components == 3 && P.adobe_transform == 0)
+    throw InvalidArg{"jpeg: Adobe RGB streams are not supported", UVO_ERR_UNSUPPORTED};
+  const uvo_jpeg_layout& L = P.L;
+  const int ns = P.sos_n ? P.sos[0] : 0;
+  if (ns < 1 || ns > L.components || P.sos_n < (size_t)(1 + 2 * ns + 3)) throw InvalidArg{"jpeg: bad SOS", UVO_ERR_INVALID};
+  if (ns != L.components || P.restart != 0) return false;  // several scans / restart intervals: host decoder
+  memset(plan, 0, sizeof(*plan));
+  int order[3];
+  for (int j = 0; j < ns; j++) {
+    int c = -1;
+    for (int q = 0; q < L.components; q++)
+      if (P.comp[q].id == P.sos[1 + 2 * j]) c = q;
+    if (c < 0) throw InvalidArg{"jpeg: SOS names an unknown component", UVO_ERR_INVALID};
+    const int td = P.sos[2 + 2 * j] >> 4, ta = P.sos[2 + 2 * j] & 15;
+    if (td > 3 || ta > 3 || !P.dc[td].present || !P.ac[ta].present || !P.qt_present[P.comp[c].tq])
+      throw InvalidArg{"jpeg: scan refers to a table that was not defined", UVO_ERR_INVALID};
+    if (td > 1 || ta > 1) return false;  // baseline allows table ids 0 and 1
+    plan->dc_tab[c] = (uint8_t)td;
+    plan->ac_tab[c] = (uint8_t)(2 + ta);
+    order[j] = c;
+  }
+  for (int t = 0; t < 4; t++) {
+    const HuffTab& h = t < 2 ? P.dc[t] : P.ac[t - 2];
+    if (!h.present) continue;
+    for (int k = 0; k < (1 << JH_FAST_BITS); k++) {
+      const unsigned e = h.fast[k << (FAST_BITS - JH_FAST_BITS)];
+      plan->fast[t][k] = (e && (int)(e >> 8) <= JH_FAST_BITS) ? (uint16_t)e : 0;
+    }
+    memcpy(plan->maxcode[t], h.maxcode, sizeof(h.maxcode));
+    memcpy(plan->valoff[t], h.valoff, sizeof(h.valoff));
+    memcpy(plan->huffval[t], h.huffval, sizeof(h.huffval));
+  }
+  int bpm = 0;
+  for (int j = 0; j < ns; j++) {
+    const int c = order[j];
+    const int nbx = ns == 1 ? 1 : P.comp[c].h, nby = ns == 1 ? 1 : P.comp[c].v;
+    for (int by = 0; by < nby; by++)
+      for (int bx = 0; bx < nbx; bx++) {
+        if (bpm >= JH_MAX_BPM) return false;
+        plan->blk_comp[bpm] = (uint8_t)c;
+        plan->blk_v[bpm] = (uint8_t)by;
+        plan->blk_h[bpm] = (uint8_t)bx;
+        bpm++;
+      }
+  }
+  plan->bpm = bpm;
+  plan->components = L.components;
+  if (ns == 1) {
+    // a single-component frame: one block per MCU, row-major over the blocks that hold real samples -- which are all
+    // of its blocks only when the padded block grid equals the sample grid
+    plan->mcus_x = div_up(L.samples_x[order[0]], 8);
+    plan->mcus_y = div_up(L.samples_y[order[0]], 8);
+    if (plan->mcus_x != L.blocks_x[order[0]] || plan->mcus_y != L.blocks_y[order[0]]) return false;
+  } else {
+    plan->mcus_x = L.blocks_x[order[0]] / P.comp[order[0]].h;
+    plan->mcus_y = L.blocks_y[order[0]] / P.comp[order[0]].v;
+  }
+  plan->total_blocks = plan->mcus_x * plan->mcus_y * bpm;
+  if ((int64_t)plan->total_blocks != L.coeff_total / 64) return false;
+  for (int c = 0; c < L.components; c++) {
+    plan->H[c] = ns == 1 ? 1 : P.comp[c].h;
+    plan->V[c] = ns == 1 ? 1 : P.comp[c].v;
+    plan->blocks_x[c] = L.blocks_x[c];
+    plan->block_off[c] = (int32_t)(L.coeff_offset[c] / 64);
+  }
+  for (int j = 0; j < ns; j++) memcpy(P.L.quant[order[j]], P.qt[P.comp[order[j]].tq], sizeof(P.L.quant[0]));
+  // the scan data: up to the next marker that is neither a stuffed zero nor (there are none) a restart; stuffed
+  // zeros removed on the way into the (pinned) output
+  const uint8_t* q = P.data;
+  size_t o = 0;
+  while (q < P.end) {
+    const uint8_t* f = (const uint8_t*)memchr(q, 0xFF, (size_t)(P.end - q));
+    const size_t run = (size_t)((f ? f : P.end) - q);
+    if (o + run + 1 > scan_cap) throw InvalidArg{"jpeg: scan larger than its staging buffer", UVO_ERR_CAPACITY};
+    memcpy(scan_out + o, q, run);
+    o += run;
+    if (!f) {
+      q = P.end;
+      break;
+    }
+    if (f + 1 < P.end && f[1] == 0x00) {  // stuffed zero: keep the 0xFF, drop the zero
+      scan_out[o++] = 0xFF;
+      q = f + 2;
+      continue;
+    }
+    if (f + 1 < P.end && f[1] == 0xFF) {  // fill byte before a marker
+      q = f + 1;
+      continue;
+    }
+    q = f;  // a marker: the scan ends here
+    break;
+  }
+  // a second scan (the stream would be multi-scan after all) is not handled here
+  if (q + 1 < P.end && q[0] == 0xFF && q[1] != 0xD9) return false;
+  if (o + 16 > scan_cap) throw InvalidArg{"jpeg: scan larger than its staging buffer", UVO_ERR_CAPACITY};
+  memset(scan_out + o, 0, 16);
+  if (o * 8 >= (size_t)1 << 31) return false;
+  plan->total_bits = (uint32_t)(o * 8);
+  plan->entries_cap = (uint32_t)L.coeff_total;
+  out->L = P.L;
+  out->scan_bytes = o;
+  return true;
+}
+
+struct JhShared {
+  uint16_t fast[4][1 << JH_FAST_BITS];
+  int32_t maxcode[4][18];
+  int32_t valoff[4][17];
+  uint8_t huffval[4][256];
+  uint8_t blk_comp[JH_MAX_BPM + 2], blk_v[JH_MAX_BPM + 2], blk_h[JH_MAX_BPM + 2], dc_tab[4], ac_tab[4];
+};
+
+__device__ const uint8_t d_kNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                           12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                           58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// decoder state: position, block of the MCU, next coefficient index (0 = the DC symbol comes next)
+struct JhState {
+  unsigned pos;
+  int p, z;
+};
+
+// the big-endian bit stream from bit `pos` on, through a 64-bit register window refilled one aligned word at a time:
+// a symbol (<= 27 bits) costs shifts, not loads
+struct JhBits {
+  const uint32_t* __restrict__ w;
+  unsigned long long buf;  // the next `avail` bits of the stream, left-aligned
+  int avail;
+  unsigned next;           // index of the next word to load
+  __device__ __forceinline__ void open(const uint32_t* __restrict__ words, unsigned pos) {
+    w = words;
+    const unsigned k = pos >> 5, sh = pos & 31;
+    const unsigned long long a = __byte_perm(__ldg(w + k), 0, 0x0123), b = __byte_perm(__ldg(w + k + 1), 0, 0x0123);
+    buf = ((a << 32) | b) << sh;
+    avail = 64 - (int)sh;
+    next = k + 2;
+  }
+  __device__ __forceinline__ uint32_t peek32() {
+    if (avail <= 32) {
+      buf |= (unsigned long long)__byte_perm(__ldg(w + next), 0, 0x0123) << (32 - avail);
+      avail += 32;
+      next++;
+    }
+    return (uint32_t)(buf >> 32);
+  }
+  __device__ __forceinline__ void skip(int n) {
+    buf <<= n;
+    avail -= n;
+  }
+};
+
+// One symbol (Huffman code + magnitude bits).  kind: 0 = DC difference (a block starts), 1 = AC coefficient at zig-zag
+// index zz, 2 = nothing to store (end of block / zero run of 16).  Returns false when the symbol would run past the
+// end of the data (the decode stops there: what is left are the padding bits).  Same rules as the host decoder for
+// codes that are not in the table (16 bits skipped, symbol 0).
+__device__ __forceinline__ bool jh_symbol(const JhShared& T, JhBits& in, unsigned total_bits, int bpm, JhState& s,
+                                          int& kind, int& zz, int& val) {
+  const uint32_t x = in.peek32();
+  const int comp = T.blk_comp[s.p];
+  const int t = s.z == 0 ? T.dc_tab[comp] : T.ac_tab[comp];
+  int len, sym;
+  const unsigned e = T.fast[t][x >> (32 - JH_FAST_BITS)];
+  if (e) {
+    len = e >> 8;
+    sym = e & 255;
+  } else {
+    len = 16;
+    sym = 0;
+    for (int l = JH_FAST_BITS + 1; l <= 16; l++) {
+      const int code = (int)(x >> (32 - l));
+      if (code <= T.maxcode[t][l]) {
+        len = l;
+        sym = T.huffval[t][(code + T.valoff[t][l]) & 255];
+        break;
+      }
+    }
+  }
+  const bool dc = s.z == 0;
+  const int mag = dc ? min(sym, 15) : (sym & 15);  // the host decoder rejects DC categories above 15
+  const int used = len + mag;
+  if (s.pos + used > total_bits) return false;
+  int v = 0;
+  if (mag) {
+    v = (int)((x << len) >> (32 - mag));
+    if (v < (1 << (mag - 1))) v += -(1 << mag) + 1;
+  }
+  val = v;
+  if (dc) {
+    kind = 0;
+    zz = 0;
+    s.z = 1;
+  } else {
+    const int run = sym >> 4;
+    if (mag == 0) {
+      kind = 2;
+      s.z = (run == 15) ? s.z + 16 : 64;  // ZRL / EOB
+    } else {
+      const int k = s.z + run;
+      kind = k <= 63 ? 1 : 2;  // a run past the block is corrupt data: the block ends
+      zz = k & 63;
+      s.z = k + 1;
+    }
+  }
+  s.pos += used;
+  in.skip(used);
+  if (s.z >= 64) {
+    s.z = 0;
+    s.p = s.p + 1 == bpm ? 0 : s.p + 1;
+  }
+  return true;
+}
+
+// exclusive prefix sums of up to three ints per thread over one block; totals returned to everyone
+template <int K>
+__device__ __forceinline__ void jh_block_scan(int (&v)[K], int (*s_w)[K], int (&tot)[K]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    inc[k] = v[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc[k], o);
+      if (lane >= o) inc[k] += t;
+    }
+    if (lane == 31) s_w[wid][k] = inc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < K; k++) {
+      int run = 0;
+      for (int w = 0; w < nw; w++) {
+        const int t = s_w[w][k];
+        s_w[w][k] = run;
+        run += t;
+      }
+      s_w[nw][k] = run;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    tot[k] = s_w[nw][k];
+    v[k] = s_w[wid][k] + inc[k] - v[k];
+  }
+  __syncthreads();
+}
+
+// Cooperative kernel (grid-wide barriers): grid = (blocks per image, images), JH_BLOCK threads each, one thread per
+// sub-sequence of JH_SUB_BITS bits.  Phases: synchronisation rounds; count; per-image scan of the counts; write;
+// DC partial sums; per-image scan of those; DC prediction + block table in plane order.
+__device__ __forceinline__ unsigned long long jh_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ JhArgs args) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ JhShared T;
+  __shared__ int s_w[JH_BLOCK / 32 + 1][3];
+  const JhImage& im = args.im[blockIdx.y];
+  const JhPlan* __restrict__ P = im.plan;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (int)(sizeof(T.fast) / 2); i += JH_BLOCK) (&T.fast[0][0])[i] = (&P->fast[0][0])[i];
+  for (int i = tid; i < 4 * 18; i += JH_BLOCK) (&T.maxcode[0][0])[i] = (&P->maxcode[0][0])[i];
+  for (int i = tid; i < 4 * 17; i += JH_BLOCK) (&T.valoff[0][0])[i] = (&P->valoff[0][0])[i];
+  for (int i = tid; i < 4 * 256; i += JH_BLOCK) (&T.huffval[0][0])[i] = (&P->huffval[0][0])[i];
+  if (tid < JH_MAX_BPM + 2) {
+    T.blk_comp[tid] = P->blk_comp[tid];
+    T.blk_v[tid] = P->blk_v[tid];
+    T.blk_h[tid] = P->blk_h[tid];
+  }
+  if (tid < 4) {
+    T.dc_tab[tid] = P->dc_tab[tid];
+    T.ac_tab[tid] = P->ac_tab[tid];
+  }
+  const unsigned total_bits = P->total_bits;
+  const int bpm = P->bpm, total_blocks = P->total_blocks;
+  const unsigned cap = P->entries_cap;
+  const uint32_t* __restrict__ w = im.scan;
+  const int n_sub = (int)((total_bits + JH_SUB_BITS - 1) / JH_SUB_BITS);  // sub-sequences of this image
+  const int g = blockIdx.x * JH_BLOCK + tid;                             // this thread's sub-sequence
+  const bool live = g < n_sub;
+  int* flag = args.flag;
+  __syncthreads();
+  // diagnostics: phase time stamps (ns) of block (0, 0) in info[16 .. 63] (tools/jh_time.py)
+  unsigned long long* stamps = (unsigned long long*)(args.im[0].info + 16);
+  int n_stamp = 0;
+  auto stamp = [&]() {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && n_stamp < 24) stamps[n_stamp++] = jh_now();
+  };
+  stamp();
+  // ---- phase 1: self-synchronisation.  Round r reads the exit states of round r - 1 and writes those of round r
+  // (two buffers); a thread whose start state did not change keeps its exit state.  The loop runs until a round
+  // changes nothing in ANY image of the launch (every block must take part in every grid barrier).
+  const unsigned begin = (unsigned)g * JH_SUB_BITS, end = min(begin + JH_SUB_BITS, total_bits);
+  JhState start{begin, 0, 0}, prev{0xffffffffu, -1, -1}, ex{begin, 0, 0};
+  int kind, zz, val;
+  int rounds = 0;
+  for (;; rounds++) {
+    uint2* ex_cur = im.exits + (size_t)(rounds & 1) * n_sub;
+    const uint2* ex_prev = im.exits + (size_t)((rounds & 1) ^ 1) * n_sub;
+    // three flag slots: the one cleared here was last read in round - 2, and every thread has since passed the barrier
+    // of round - 1
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) flag[(rounds + 1) % 3] = 0;
+    if (live) {
+      if (g > 0 && rounds > 0) {
+        const uint2 e = ex_prev[g - 1];
+        start.pos = e.x;
+        start.p = (int)(e.y >> 8);
+        start.z = (int)(e.y & 255);
+      }
+      if (start.pos != prev.pos || start.p != prev.p || start.z != prev.z) {
+        prev = start;
+        JhState s = start;
+        JhBits in;
+        in.open(w, s.pos);
+        while (s.pos < end && jh_symbol(T, in, total_bits, bpm, s, kind, zz, val)) {
+        }
+        if (s.pos < end) s.pos = total_bits;  // stopped by the end of the data
+        if (rounds == 0 || s.pos != ex.pos || s.p != ex.p || s.z != ex.z) flag[rounds % 3] = 1;
+        ex = s;
+      }
+      ex_cur[g] = make_uint2(ex.pos, (unsigned)((ex.p << 8) | ex.z));
+    }
+    grid.sync();
+    if (rounds < 2) stamp();
+    if (!flag[rounds % 3] || rounds >= JH_MAX_ROUNDS) break;
+  }
+  stamp();
+  // (the start state of the last round is the true one: nothing changed in it)
+  // ---- phase 2: count what each thread owns (the symbols that start in [its true start, its exit))
+  int cnt[2] = {0, 0};  // blocks started, entries
+  if (live) {
+    JhState s = start;
+    JhBits in;
+    in.open(w, s.pos);
+    while (s.pos < end && jh_symbol(T, in, total_bits, bpm, s, kind, zz, val)) {
+      cnt[0] += kind == 0;
+      cnt[1] += kind != 2;
+    }
+    im.counts[g] = make_int2(cnt[0], cnt[1]);
+  }
+  grid.sync();
+  stamp();
+  // ---- per-image exclusive scan of the counts by the image's first block
+  if (blockIdx.x == 0) {
+    const int per = (n_sub + JH_BLOCK - 1) / JH_BLOCK;
+    const int a0 = min(tid * per, n_sub), a1 = min(a0 + per, n_sub);
+    int v[2] = {0, 0}, tot[2];
+    for (int i = a0; i < a1; i++) {
+      const int2 c = im.counts[i];
+      v[0] += c.x;
+      v[1] += c.y;
+    }
+    jh_block_scan<2>(v, (int(*)[2])s_w, tot);
+    for (int i = a0; i < a1; i++) {
+      const int2 c = im.counts[i];
+      im.counts[i] = make_int2(v[0], v[1]);
+      v[0] += c.x;
+      v[1] += c.y;
+    }
+    if (tid == 0) {
+      const int err = (tot[0] != total_blocks || (unsigned)tot[1] > cap || rounds >= JH_MAX_ROUNDS) ? 1 : 0;
+      im.first_scan[total_blocks] = (uint32_t)min((unsigned)tot[1], cap);
+      im.info[0] = (int)min((unsigned)tot[1], cap);
+      im.info[1] = err;
+      im.info[2] = rounds + 1;
+    }
+  }
+  grid.sync();
+  stamp();
+  // ---- phase 3: write the entries (DC entries carry the DIFFERENCE for now) and the scan-order block table
+  if (live) {
+    const int2 base = im.counts[g];
+    JhState s = start;
+    JhBits in;
+    in.open(w, s.pos);
+    int sb = base.x, e = base.y;
+    while (s.pos < end && jh_symbol(T, in, total_bits, bpm, s, kind, zz, val)) {
+      if (kind == 0) {
+        if (sb < total_blocks) im.first_scan[sb] = (uint32_t)e;
+        sb++;
+      }
+      if (kind != 2) {
+        if ((unsigned)e < cap) im.entries[e] = ((uint32_t)(kind == 0 ? 0 : d_kNatural[zz]) << 16) | (uint16_t)(int16_t)val;
+        e++;
+      }
+    }
+  }
+  grid.sync();
+  stamp();
+  const bool err = im.info[1] != 0;
+  // ---- phase 4: DC prediction = running sum of the differences per component, in scan order: per-thread partial sums
+  // over a contiguous range of scan-order blocks, scanned by the image's first block
+  const int n_thr = gridDim.x * JH_BLOCK;
+  const int bper = (total_blocks + n_thr - 1) / n_thr;
+  const int gi = blockIdx.x * JH_BLOCK + tid;
+  const int b0 = min(gi * bper, total_blocks), b1 = min(b0 + bper, total_blocks);
+  if (!err) {
+    int acc[3] = {0, 0, 0};
+    for (int sb = b0; sb < b1; sb++) acc[T.blk_comp[sb % bpm]] += (int)(int16_t)(im.entries[im.first_scan[sb]] & 0xffffu);
+    im.dc_part[gi] = make_int4(acc[0], acc[1], acc[2], 0);
+  }
+  grid.sync();
+  if (blockIdx.x == 0 && !err) {
+    const int per = (n_thr + JH_BLOCK - 1) / JH_BLOCK;
+    const int a0 = min(tid * per, n_thr), a1 = min(a0 + per, n_thr);
+    int v[3] = {0, 0, 0}, tot[3];
+    for (int i = a0; i < a1; i++) {
+      const int4 c = im.dc_part[i];
+      v[0] += c.x;
+      v[1] += c.y;
+      v[2] += c.z;
+    }
+    jh_block_scan<3>(v, s_w, tot);
+    for (int i = a0; i < a1; i++) {
+      const int4 c = im.dc_part[i];
+      im.dc_part[i] = make_int4(v[0], v[1], v[2], 0);
+      v[0] += c.x;
+      v[1] += c.y;
+      v[2] += c.z;
+    }
+  }
+  grid.sync();
+  // ---- phase 5: absolute DC values, and the block table in plane order (component-major, row-major), which is how
+  // k_jpeg_idct numbers its blocks.  A corrupt stream leaves a decodable (empty) image behind.
+  if (err) {
+    for (int b = b0; b < b1; b++) {
+      im.first[b] = 0;
+      im.count[b] = 0;
+    }
+    return;
+  }
+  const int4 pb = im.dc_part[gi];
+  int pred[3] = {pb.x, pb.y, pb.z};
+  const int mcus_x = P->mcus_x;
+  for (int sb = b0; sb < b1; sb++) {
+    const int k = sb % bpm, m = sb / bpm, c = T.blk_comp[k];
+    const uint32_t f = im.first_scan[sb], f1 = im.first_scan[sb + 1];
+    pred[c] += (int)(int16_t)(im.entries[f] & 0xffffu);
+    im.entries[f] = (uint32_t)(uint16_t)(int16_t)pred[c];  // natural index 0
+    const int mx = m % mcus_x, my = m / mcus_x;
+    const int X = mx * P->H[c] + T.blk_h[k], Y = my * P->V[c] + T.blk_v[k];
+    const int blk = P->block_off[c] + Y * P->blocks_x[c] + X;
+    im.first[blk] = f;
+    im.count[blk] = (uint8_t)(f1 - f);
+  }
+  stamp();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) args.im[0].info[15] = n_stamp;
+}
 }  // namespace
 
 namespace uvo {
@@ -458,16 +970,24 @@ void jpeg_upload_sparse(cudaStream_t copy_stream, const uvo_jpeg_sparse& sp, uin
   UVO_CUDA(cudaMemcpyAsync(d_count, sp.block_count, nb, cudaMemcpyHostToDevice, copy_stream));
 }
 
+static void transform_ptrs(Ctx& c, const uvo_jpeg_layout& L, const uint32_t* d_first, const uint32_t* d_entries,
+                           const uint8_t* d_count, uint8_t* d_planes, int bayer_bggr, uint8_t* d_bgr, size_t bgr_pitch);
+
 void jpeg_launch_transform(Ctx& c, const uvo_jpeg_layout& L, size_t n_entries, uint8_t* d_sparse, uint8_t* d_planes,
                            int bayer_bggr, uint8_t* d_bgr, size_t bgr_pitch) {
   const size_t nb = (size_t)L.coeff_total / 64;
+  uint32_t* d_first = (uint32_t*)d_sparse;
+  uint32_t* d_entries = d_first + nb;
+  uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(n_entries, 1));
+  transform_ptrs(c, L, d_first, d_entries, d_count, d_planes, bayer_bggr, d_bgr, bgr_pitch);
+}
+
+static void transform_ptrs(Ctx& c, const uvo_jpeg_layout& L, const uint32_t* d_first, const uint32_t* d_entries,
+                           const uint8_t* d_count, uint8_t* d_planes, int bayer_bggr, uint8_t* d_bgr, size_t bgr_pitch) {
   const int nc = L.components;
   const bool demosaic = bayer_bggr != 0 && nc == 1;
   if (!(nc == 3 || demosaic))
     throw InvalidArg{"jpeg input: a 3-component stream, or a 1-component bayer stream, is required", UVO_ERR_UNSUPPORTED};
-  uint32_t* d_first = (uint32_t*)d_sparse;
-  uint32_t* d_entries = d_first + nb;
-  uint8_t* d_count = (uint8_t*)(d_entries + std::max<size_t>(n_entries, 1));
   IdctArgs ia;
   ColorArgs ca;
   fill_args(L, d_entries, d_first, d_count, d_planes, nc == 3 ? d_bgr : nullptr, bgr_pitch, ia, ca);
@@ -494,6 +1014,105 @@ void jpeg_host_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries,
   P.run_sparse(jpeg, len, entries, capacity, first, count);
   *n_entries = P.sink.n;
   *layout = P.L;
+}
+
+static inline size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+size_t jpeg_gpu_host_bytes(size_t jpeg_len) { return up256(sizeof(JhPlan)) + up256(jpeg_len + 64); }
+
+bool jpeg_gpu_prepare(const uint8_t* jpeg, size_t len, uint8_t* pinned, size_t pinned_cap, JpegGpuJob* job) {
+  if (pinned_cap < jpeg_gpu_host_bytes(len)) throw InvalidArg{"jpeg: staging buffer too small", UVO_ERR_CAPACITY};
+  JhPlan* plan = (JhPlan*)pinned;
+  uint8_t* scan = pinned + up256(sizeof(JhPlan));
+  GpuPlanOut o;
+  if (!build_gpu_plan(jpeg, len, plan, scan, pinned_cap - up256(sizeof(JhPlan)), &o)) return false;
+  job->L = o.L;
+  job->upload_bytes = up256(sizeof(JhPlan)) + ((o.scan_bytes + 16 + 3) & ~(size_t)3);
+  return true;
+}
+
+struct GpuLayout {  // offsets inside the device buffer of one image
+  size_t first, entries, count, first_scan, info, exits, counts, dc_part, total;
+};
+static int jh_blocks(size_t scan_bytes) {  // blocks of the cooperative launch an image of this scan length needs
+  const size_t n_sub = (scan_bytes * 8 + JH_SUB_BITS - 1) / JH_SUB_BITS;
+  return (int)std::max<size_t>((n_sub + JH_BLOCK - 1) / JH_BLOCK, 1);
+}
+static GpuLayout gpu_layout(const uvo_jpeg_layout& L, size_t upload_bytes) {
+  const size_t nb = (size_t)L.coeff_total / 64;
+  GpuLayout g;
+  size_t o = up256(upload_bytes);
+  g.first = o;
+  o += up256(nb * 4);
+  g.entries = o;
+  o += up256((size_t)L.coeff_total * 4);
+  g.count = o;
+  o += up256(nb);
+  g.first_scan = o;
+  o += up256((nb + 1) * 4);
+  g.info = o;
+  o += 512;
+  // scratch of the parallel decode, sized from the (upper bound of the) scan length
+  const size_t n_thr = (size_t)jh_blocks(upload_bytes) * JH_BLOCK + JH_BLOCK;
+  g.exits = o;
+  o += up256(2 * n_thr * sizeof(uint2));
+  g.counts = o;
+  o += up256(n_thr * sizeof(int2));
+  g.dc_part = o;
+  o += up256(4 * n_thr * sizeof(int4));  // the DC pass runs on the threads of the widest image of the launch
+  g.total = o;
+  return g;
+}
+
+size_t jpeg_gpu_device_bytes(const uvo_jpeg_layout& L, size_t upload_bytes) { return gpu_layout(L, upload_bytes).total; }
+
+__global__ void k_jpeg_huff_status(const int* info0, const int* info1, int* status) {
+  status[0] = info0[1];
+  status[1] = info0[2];
+  if (info1) {
+    status[2] = info1[1];
+    status[3] = info1[2];
+  }
+  for (int i = 0; i < 64; i++) status[8 + i] = info0[15 + i];  // phase stamps (diagnostics)
+}
+
+void jpeg_gpu_launch(Ctx& c, int n, const JpegGpuJob* jobs, uint8_t* const* d_buf, uint8_t* const* d_planes,
+                     int bayer_bggr, uint8_t* const* d_bgr, size_t bgr_pitch, int* d_status) {
+  UVO_REQUIRE(n == 1 || n == 2, "jpeg_gpu_launch: one or two images");
+  JhArgs a{};
+  GpuLayout g[2];
+  for (int i = 0; i < n; i++) {
+    g[i] = gpu_layout(jobs[i].L, jobs[i].upload_bytes);
+    JhImage& im = a.im[i];
+    im.plan = (const JhPlan*)d_buf[i];
+    im.scan = (const uint32_t*)(d_buf[i] + up256(sizeof(JhPlan)));
+    im.first = (uint32_t*)(d_buf[i] + g[i].first);
+    im.entries = (uint32_t*)(d_buf[i] + g[i].entries);
+    im.count = d_buf[i] + g[i].count;
+    im.first_scan = (uint32_t*)(d_buf[i] + g[i].first_scan);
+    im.info = (int*)(d_buf[i] + g[i].info);
+    im.exits = (uint2*)(d_buf[i] + g[i].exits);
+    im.counts = (int2*)(d_buf[i] + g[i].counts);
+    im.dc_part = (int4*)(d_buf[i] + g[i].dc_part);
+  }
+  // the launch is as wide as its longest scan needs; the DC scratch above allows a factor 4 between the two images
+  int blocks = 1;
+  for (int i = 0; i < n; i++) blocks = std::max(blocks, jh_blocks(jobs[i].upload_bytes));
+  for (int i = 0; i < n; i++)
+    UVO_REQUIRE(blocks <= 4 * jh_blocks(jobs[i].upload_bytes) + 4, "jpeg pair: the two scans differ too much in length");
+  a.flag = (int*)(d_buf[0] + g[0].info) + 8;
+  UVO_CUDA(cudaMemsetAsync(a.flag, 0, 3 * sizeof(int), c.stream));
+  void* kargs[1] = {(void*)&a};
+  UVO_KERNEL(c, "k_jpeg_huff");
+  UVO_CUDA(cudaLaunchCooperativeKernel((const void*)k_jpeg_huff, dim3(blocks, n), dim3(JH_BLOCK), kargs, 0, c.stream));
+  UVO_LAUNCH_CHECK(c);
+  if (d_status) {
+    k_jpeg_huff_status<<<1, 1, 0, c.stream>>>(a.im[0].info, n > 1 ? a.im[1].info : nullptr, d_status);
+    UVO_CUDA(cudaGetLastError());
+  }
+  for (int i = 0; i < n; i++)
+    transform_ptrs(c, jobs[i].L, a.im[i].first, a.im[i].entries, a.im[i].count, d_planes[i], bayer_bggr, d_bgr[i],
+                   bgr_pitch);
 }
 
 }  // namespace uvo
@@ -548,6 +1167,54 @@ static void jpeg_decode_impl(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int 
   UVO_REQUIRE(jpeg && out && width && height && channels, "uvo_jpeg_decode: bad argument");
   Ctx& c = ctx->c;
   UVO_CUDA(cudaSetDevice(c.device));
+  ctx->jpeg_last_route = 0;
+  ctx->jpeg_last_rounds = 0;
+  if (ctx->jpeg_gpu_entropy) {
+    // Huffman decoding on the GPU: only the (unstuffed) scan bytes and the table plan cross PCIe
+    UVO_CUDA(cudaStreamSynchronize(c.stream));  // the pinned buffer may still feed the previous call's copy
+    const size_t hb = jpeg_gpu_host_bytes(len);
+    ctx->jpeg_coef.ensure((hb + 3) / 4);
+    JpegGpuJob job;
+    if (jpeg_gpu_prepare(jpeg, len, (uint8_t*)ctx->jpeg_coef.p, hb, &job)) {
+      const uvo_jpeg_layout& L = job.L;
+      const int W = L.width, Hh = L.height, nc = L.components;
+      const bool demosaic = bayer_bggr != 0 && nc == 1;
+      if (nc == 3 || demosaic) {
+        if (demosaic && (W < 3 || Hh < 3))
+          throw InvalidArg{"uvo_jpeg_decode: a bayer image needs w, h >= 3", UVO_ERR_INVALID};
+        if (out_pitch < (size_t)W * 3 || out_capacity < out_pitch * (size_t)(Hh - 1) + (size_t)W * 3)
+          throw InvalidArg{"uvo_jpeg_decode: output buffer too small (see uvo_jpeg_info)", UVO_ERR_CAPACITY};
+        StageScratch& s = ctx->scratch;
+        s.bytes_a.ensure(jpeg_gpu_device_bytes(L, job.upload_bytes));
+        s.bytes_b.ensure(jpegk::plane_bytes(L));
+        s.bytes_d.ensure(512);
+        size_t dpitch = out_pitch;
+        uint8_t* d_out = out;
+        if (!out_on_device) {
+          dpitch = ((size_t)3 * W + 15) & ~(size_t)15;
+          s.bytes_c.ensure(dpitch * Hh);
+          d_out = s.bytes_c.get();
+        }
+        UVO_CUDA(cudaMemcpyAsync(s.bytes_a.get(), ctx->jpeg_coef.p, job.upload_bytes, cudaMemcpyHostToDevice, c.stream));
+        uint8_t* d_buf = s.bytes_a.get();
+        uint8_t* d_planes = s.bytes_b.get();
+        jpeg_gpu_launch(c, 1, &job, &d_buf, &d_planes, bayer_bggr, &d_out, dpitch, (int*)s.bytes_d.get());
+        if (!out_on_device)
+          UVO_CUDA(cudaMemcpy2DAsync(out, out_pitch, d_out, dpitch, (size_t)3 * W, Hh, cudaMemcpyDeviceToHost, c.stream));
+        int status[72] = {0};
+        UVO_CUDA(cudaMemcpyAsync(status, s.bytes_d.get(), sizeof(status), cudaMemcpyDeviceToHost, c.stream));
+        UVO_CUDA(cudaStreamSynchronize(c.stream));
+        ctx->jpeg_last_route = 1;
+        ctx->jpeg_last_rounds = status[1];
+        memcpy(ctx->jpeg_stamps, status + 8, sizeof(ctx->jpeg_stamps));
+        if (status[0]) throw InvalidArg{"jpeg: corrupt or truncated entropy-coded data", UVO_ERR_INVALID};
+        *width = W;
+        *height = Hh;
+        *channels = 3;
+        return;
+      }
+    }
+  }
   Parser H;
   H.run(jpeg, len, nullptr);
   const size_t total = (size_t)H.L.coeff_total;
@@ -622,6 +1289,21 @@ int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bgg
   return guarded(&ctx->c, [&] {
     jpeg_decode_impl(ctx, jpeg, len, bayer_bggr, out_host, out_pitch, out_capacity, false, width, height, channels);
   });
+}
+
+int uvo_jpeg_gpu_entropy(uvo_ctx* ctx, int enable, int* last_route, int* last_rounds) {
+  if (!ctx) return UVO_ERR_INVALID;
+  if (enable >= 0) ctx->jpeg_gpu_entropy = enable != 0;
+  if (last_route) *last_route = ctx->jpeg_last_route;
+  if (last_rounds) *last_rounds = ctx->jpeg_last_rounds;
+  return UVO_OK;
+}
+
+int uvo_jpeg_gpu_entropy_stamps(uvo_ctx* ctx, int64_t stamps[24], int* count) {
+  if (!ctx || !stamps || !count) return UVO_ERR_INVALID;
+  *count = std::min(ctx->jpeg_stamps[0], 24);
+  memcpy(stamps, ctx->jpeg_stamps + 1, sizeof(int64_t) * 24);
+  return UVO_OK;
 }
 
 int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,

@@ -21,4 +21,22 @@ void jpeg_launch_transform(Ctx& c, const uvo_jpeg_layout& L, size_t n_entries, u
 void jpeg_host_decode_sparse(const uint8_t* jpeg, size_t len, uint32_t* entries, size_t capacity, uint32_t* first,
                              uint8_t* count, size_t* n_entries, uvo_jpeg_layout* layout);
 
+
+// ---- Huffman decoding on the GPU (jpeg_huff.cuh): qualifying streams never touch the host decoder
+struct JpegGpuJob {
+  uvo_jpeg_layout L;
+  size_t upload_bytes;  // front of the pinned staging to copy to the front of the device buffer: [JhPlan][scan bytes + pad]
+};
+// pinned staging needed for a stream of `jpeg_len` bytes
+size_t jpeg_gpu_host_bytes(size_t jpeg_len);
+// host part: marker walk, table plan, unstuffed copy of the scan into `pinned`.  false: the stream is one this path
+// does not take (several scans, restart intervals): use the host decoder.  Throws on malformed streams.
+bool jpeg_gpu_prepare(const uint8_t* jpeg, size_t len, uint8_t* pinned, size_t pinned_cap, JpegGpuJob* job);
+// device buffer for one image: upload region + sparse arrays + scratch
+size_t jpeg_gpu_device_bytes(const uvo_jpeg_layout& L, size_t upload_bytes);
+// k_jpeg_huff for n (1 or 2) uploaded images in ONE launch, then IDCT + colour / demosaic per image, all on c.stream.
+// d_status (nullable): two ints per image on the device, [error, synchronisation rounds]
+void jpeg_gpu_launch(Ctx& c, int n, const JpegGpuJob* jobs, uint8_t* const* d_buf, uint8_t* const* d_planes,
+                     int bayer_bggr, uint8_t* const* d_bgr, size_t bgr_pitch, int* d_status);
+
 }  // namespace uvo

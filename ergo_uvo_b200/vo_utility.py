@@ -284,6 +284,14 @@ class Context:
                                           C.c_size_t(out.nbytes), C.byref(w), C.byref(h), C.byref(c)))
         return out
 
+    def jpeg_gpu_entropy(self, enable=None):
+        """switch the GPU Huffman decoder on / off (None: leave); returns (route of the last jpeg_decode: 1 = GPU
+        entropy decoder, synchronisation rounds it took)"""
+        route, rounds = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.uvo_jpeg_gpu_entropy(self.h, -1 if enable is None else int(bool(enable)), C.byref(route),
+                                               C.byref(rounds)))
+        return route.value, rounds.value
+
     def jpeg_decode_device(self, data, out_ptr, out_pitch, out_capacity, bayer=False):
         """as jpeg_decode with the image left in device memory at out_ptr (ordered on the context stream);
         returns (width, height, channels)"""
@@ -554,10 +562,20 @@ class StereoVO:
 
     def enqueue_host_jpeg(self, left_jpeg, right_jpeg, dt, bayer=False):
         """both images as JPEG byte strings (uvo_stereo_enqueue_host_jpeg: Huffman decoding inside, on two threads)"""
-        l = np.frombuffer(bytes(left_jpeg), np.uint8)
-        r = np.frombuffer(bytes(right_jpeg), np.uint8)
+        l = left_jpeg if isinstance(left_jpeg, np.ndarray) else np.frombuffer(bytes(left_jpeg), np.uint8)
+        r = right_jpeg if isinstance(right_jpeg, np.ndarray) else np.frombuffer(bytes(right_jpeg), np.uint8)
         self.ctx._ck(self.lib.uvo_stereo_enqueue_host_jpeg(self.h, _p(l), C.c_size_t(len(l)), _p(r), C.c_size_t(len(r)),
                                                            int(bool(bayer)), C.c_double(dt)))
+
+    def set_gpu_entropy(self, enable):
+        """Huffman decoding of enqueue_host_jpeg's input on the GPU (default) or on the host"""
+        self.ctx._ck(self.lib.uvo_stereo_set_gpu_entropy(self.h, int(bool(enable))))
+
+    @property
+    def gpu_entropy_frames(self):
+        self.lib.uvo_stereo_gpu_entropy_frames.restype = C.c_int64
+        self.lib.uvo_stereo_gpu_entropy_frames.argtypes = [C.c_void_p]
+        return int(self.lib.uvo_stereo_gpu_entropy_frames(self.h))
 
     def enqueue_host_sparse(self, left, right, dt, bayer=False):
         """both images as SparseImage objects (uvo_stereo_enqueue_host_sparse); they must stay alive until the frame

@@ -205,6 +205,15 @@ typedef struct {
  * and cvtColor(COLOR_BayerBGGR2BGR) is applied on the GPU, the output is height x width x 3 (ignored for 3 components) */
 UVO_API int uvo_jpeg_decode(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_host,
                             size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels);
+/* Huffman decoding ON THE GPU (default on): streams made of one interleaved scan without restart intervals -- what
+ * cv::imencode and camera encoders write -- are entropy-decoded by a self-synchronising parallel decoder
+ * (csrc/jpeg_huff.cuh), so only the scan bytes cross PCIe and the host does no per-coefficient work; other streams take
+ * the host decoder.  Results are identical.  enable: 1 / 0, or -1 to leave the setting alone; last_route (nullable):
+ * 1 when the previous uvo_jpeg_decode on this context took the GPU decoder; last_rounds: its synchronisation rounds. */
+UVO_API int uvo_jpeg_gpu_entropy(uvo_ctx* ctx, int enable, int* last_route, int* last_rounds);
+/* diagnostics: nanosecond time stamps (%globaltimer) of the phases of the previous GPU entropy decode -- start, after
+ * rounds 1 and 2, after the last round, count, scan, write, DC partial sums ..., end (tools/jh_time.py) */
+UVO_API int uvo_jpeg_gpu_entropy_stamps(uvo_ctx* ctx, int64_t stamps[24], int* count);
 /* the same with the image left in DEVICE memory (no copy back; the work is ordered on the context stream), ready for
  * uvo_stereo_enqueue_device / uvo_mono_frame_device on the same context */
 UVO_API int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,
@@ -374,6 +383,12 @@ UVO_API int uvo_stereo_enqueue_host_sparse(uvo_stereo* s, const uvo_jpeg_sparse*
                                            int bayer_bggr, double dt);
 UVO_API int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t left_len,
                                          const uint8_t* right_jpeg, size_t right_len, int bayer_bggr, double dt);
+/* _jpeg decodes the Huffman data ON THE GPU when both streams qualify (uvo_jpeg_gpu_entropy: one interleaved scan,
+ * no restart interval): the host then only walks the markers and copies the scan bytes (~0.5 MB per pair) -- no
+ * per-coefficient host work.  enable = 0 forces the host decoder; _frames counts the frames that took the GPU decoder.
+ * A frame whose entropy-coded data is corrupt is reported by uvo_stereo_collect (UVO_ERR_INVALID). */
+UVO_API int uvo_stereo_set_gpu_entropy(uvo_stereo* s, int enable);
+UVO_API int64_t uvo_stereo_gpu_entropy_frames(const uvo_stereo* s);
 /* The asynchronous entry points replay each lane's fixed runs of kernels as CUDA graphs (three graph launches + a few
  * direct launches per frame instead of ~30 kernel launches; results are identical).  `enable` = 0 goes back to direct
  * launches (diagnostics / A-B measurements); uvo_stereo_graph_launches counts the graph launches made so far. */

@@ -120,7 +120,7 @@ def _jpeg_pair_sequence(seq, quality=90, sampling="420"):
     return out
 
 
-@pytest.mark.parametrize("mode", ["jpeg", "sparse"])
+@pytest.mark.parametrize("mode", ["jpeg", "jpeg_host", "sparse"])
 def test_stereo_compressed_input_equals_decoded_input(ctx, oracle, small_stereo, mode):
     """uvo_stereo_enqueue_host_jpeg / _sparse (compressed pair in, Huffman decode on the host, IDCT + colour on the
     frame's lane) give byte-identical result records and identical intermediate products to uvo_stereo_frame on the
@@ -140,9 +140,10 @@ def test_stereo_compressed_input_equals_decoded_input(ctx, oracle, small_stereo,
     vo.close()
     assert any(r.valid for r in want)
     vo, p = _make(ctx, seq, 3000)
+    vo.set_gpu_entropy(mode != "jpeg_host")   # "jpeg": Huffman decoding on the GPU (k_jpeg_huff); "jpeg_host": on the host
     got, q, keep = [], 0, []
     for k in order:
-        if mode == "jpeg":
+        if mode in ("jpeg", "jpeg_host"):
             vo.enqueue_host_jpeg(jp[k][0], jp[k][1], 0.1)
         else:
             sl, sr = U.SparseImage(jp[k][0]), U.SparseImage(jp[k][1])
@@ -162,6 +163,7 @@ def test_stereo_compressed_input_equals_decoded_input(ctx, oracle, small_stereo,
     assert t[0][0].tobytes() == taps[0][0].tobytes() and t[0][1].tobytes() == taps[0][1].tobytes()
     assert t[1].tobytes() == taps[1].tobytes() and t[2].tobytes() == taps[2].tobytes()
     assert vo.graph_launches > 0
+    assert vo.gpu_entropy_frames == (len(order) if mode == "jpeg" else 0)
     vo.close()
 
 
@@ -183,7 +185,72 @@ def test_stereo_compressed_input_errors(ctx, small_stereo):
     assert e.value.code == -5
     vo.enqueue_host_jpeg(good[0], good[1], 0.1)           # the handle is still usable
     assert vo.collect().n_left > 0
+    # entropy-coded data cut short (headers intact): the GPU decoder reports it when the frame is collected
+    cut = good[0][:len(good[0]) // 2] + b"\xff\xd9"
+    vo.enqueue_host_jpeg(cut, good[1], 0.1)
+    with pytest.raises(U.UvoError) as e:
+        vo.collect()
+    assert e.value.code == -3
+    vo.enqueue_host_jpeg(good[0], good[1], 0.1)
+    assert vo.collect().n_left > 0
     # compressed bayer: a 1-component stream with the flag goes through the demosaic
     vo.enqueue_host_jpeg(gray.tobytes(), gray.tobytes(), 0.1, bayer=True)
     assert vo.collect().n_left > 0
     vo.close()
+
+
+def test_jpeg_gpu_entropy_decoder_equals_host_decoder(ctx, oracle):
+    """Huffman decoding on the GPU (k_jpeg_huff: self-synchronising parallel decode, csrc/jpeg_huff.cuh) against the
+    host decoder and the oracle, bit-exact, over sizes from one MCU to a 1280x1024 frame, every sub-sampling, qualities
+    from 15 to 100 and optimised tables; streams with restart intervals must take the host route."""
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(11)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    cases = []
+    for h, w in [(8, 8), (16, 16), (17, 33), (100, 6), (243, 317), (480, 640), (1024, 1280)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8) if h * w < 2000 else noise_image(h, w, seed=h, channels=3)
+        for sf in ("444", "422", "420", "440", "411"):
+            for q in (15, 75, 90, 100):
+                if h * w > 100000 and (sf not in ("420", "444") or q in (15, 100)):
+                    continue
+                cases.append((img, sf, q, 0, 0))
+    cases.append((noise_image(480, 640, seed=3, channels=3), "420", 90, 0, 1))      # optimised Huffman tables
+    cases.append((noise_image(480, 640, seed=4, channels=3), "420", 90, 7, 0))      # restart interval -> host route
+    max_rounds = 0
+    for img, sf, q, rst, opt in cases:
+        ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, S, getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sf),
+                                             cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_OPTIMIZE, opt])
+        data = enc.tobytes()
+        ctx.jpeg_gpu_entropy(True)
+        got = ctx.jpeg_decode(data)
+        route, rounds = ctx.jpeg_gpu_entropy()
+        assert route == (0 if rst else 1), (img.shape, sf, q, rst)
+        max_rounds = max(max_rounds, rounds)
+        ctx.jpeg_gpu_entropy(False)
+        host = ctx.jpeg_decode(data)
+        assert ctx.jpeg_gpu_entropy()[0] == 0
+        ctx.jpeg_gpu_entropy(True)
+        assert np.array_equal(got, host), (img.shape, sf, q, rst, opt)
+        if img.shape[0] * img.shape[1] <= 320000:
+            assert np.array_equal(got, oracle.jpeg_decode(data)), (img.shape, sf, q)
+    assert 1 <= max_rounds <= 24, max_rounds   # a handful of rounds, not one per sub-sequence
+    # compressed bayer (1-component stream + demosaic) through the GPU decoder
+    ok, enc = cv2.imencode(".jpg", noise_image(240, 320, seed=5), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    a = ctx.jpeg_decode(enc.tobytes(), bayer=True)
+    assert ctx.jpeg_gpu_entropy()[0] == 1
+    ctx.jpeg_gpu_entropy(False)
+    b = ctx.jpeg_decode(enc.tobytes(), bayer=True)
+    ctx.jpeg_gpu_entropy(True)
+    assert np.array_equal(a, b)
+
+
+def test_jpeg_gpu_entropy_decoder_rejects_truncated_data(ctx):
+    import ergo_uvo_b200 as U
+    cv2 = pytest.importorskip("cv2")
+    ok, enc = cv2.imencode(".jpg", noise_image(240, 320, seed=6, channels=3), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    data = enc.tobytes()
+    cut = data[:len(data) // 2] + b"\xff\xd9"      # half of the scan is missing
+    ctx.jpeg_gpu_entropy(True)
+    with pytest.raises(U.UvoError):
+        ctx.jpeg_decode(cut)
+    assert np.array_equal(ctx.jpeg_decode(data), cv2.imdecode(enc, cv2.IMREAD_UNCHANGED))   # the context still works
