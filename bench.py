@@ -496,13 +496,21 @@ def run_gpu(args):
             pool.shutdown()
             # the same with Huffman decoding ON THE GPU: one host thread hands the JPEG bytes to
             # uvo_stereo_enqueue_host_jpeg (marker walk + unstuffed copy of the scan on the host, nothing else)
+            gpu_host_s = [0.0, 0]
+            # more frames enqueued than lanes: the decode of a frame runs on its slot's own stream and overlaps the
+            # lane work of the frames ahead of it
+            comp_inflight = max(inflight, vo.max_in_flight() - 2)
+
             def run_compressed_gpu(n, start):
                 valid, q = 0, 0
                 for i in range(n):
                     k = pingpong(start + i, N_DISTINCT)
+                    t_e = time.perf_counter()
                     vo.enqueue_host_jpeg(enc[k][0], enc[k][1], dt_frame)
+                    gpu_host_s[0] += time.perf_counter() - t_e
+                    gpu_host_s[1] += 1
                     q += 1
-                    if q >= inflight:
+                    if q >= comp_inflight:
                         valid += vo.collect().valid
                         q -= 1
                 while q:
@@ -510,6 +518,7 @@ def run_gpu(args):
                     q -= 1
                 return valid
             run_compressed_gpu(48, 0)
+            gpu_host_s[0], gpu_host_s[1] = 0.0, 0
             gpu_regions = []
             for r_ in range(min(args.regions, 5)):
                 barrier()
@@ -518,6 +527,7 @@ def run_gpu(args):
                 barrier()
                 gpu_regions.append((time.perf_counter() - t0) * 1e3)
             comp = {"gpu_region_ms": gpu_regions, "gpu_entropy_frames": vo.gpu_entropy_frames,
+                    "gpu_host_enqueue_us": 1e6 * gpu_host_s[0] / max(gpu_host_s[1], 1),
                     "gpu_h2d_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])) + 2 * 9500.0,"region_ms": comp_regions, "frames_per_region": n_comp, "valid": comp_valid,
                     "h2d_bytes_per_step": comp_bytes / float(n_comp * len(comp_regions)),
                     "jpeg_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])),
@@ -666,7 +676,9 @@ def run_gpu(args):
                 # Huffman decoding on the GPU (k_jpeg_huff): one host thread, JPEG bytes in, scan bytes over PCIe
                 "gpu_entropy": {"value": comp["frames_per_region"] * world / (comp_gpu_ms * 1e-3), "unit": "frames/s",
                                 "h2d_bytes_per_step": comp["gpu_h2d_bytes_per_step"], "host_threads_per_gpu": 1,
+                                "frames_in_flight": max(inflight, 14),
                                 "region_ms": comp["gpu_region_ms"], "frames_on_gpu_decoder": comp["gpu_entropy_frames"],
+                                "host_enqueue_us_per_frame": comp["gpu_host_enqueue_us"],
                                 "api": "uvo_stereo_enqueue_host_jpeg + uvo_stereo_collect"}},
             "host_enqueue_us_per_frame": 1e6 * host_enqueue_s[0] / max(host_enqueue_s[1], 1),
             # kernels the library launched inside the timed regions of `value` (graph-replayed kernels counted one by

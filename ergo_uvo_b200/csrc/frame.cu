@@ -223,6 +223,10 @@ struct uvo_stereo {
   // coefficients and the component planes the IDCT writes; for _jpeg also the pinned host side of the entropy decode
   DevBuf<uint8_t> jpeg_sparse[RING][2], jpeg_planes[RING][2];
   PinnedBuf<uint32_t> jpeg_host[RING][2];
+  // the decode of a compressed frame runs on its result slot's own stream, not on the lane: with up to RING frames
+  // enqueued, the (long, narrow) Huffman decode of frame t + N_LANES overlaps the lane work of frame t
+  cudaStream_t ingest_stream[RING] = {};
+  cudaEvent_t ev_ingest[RING] = {};
   cudaEvent_t ev_copied[RING] = {};
   long frame_no = 0;
   std::deque<int> pending;  // result slots in flight, oldest first
@@ -247,6 +251,10 @@ struct uvo_stereo {
     for (auto& e : ev_copied)
       if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (auto& e : ev_ingest)
+      if (e) cudaEventDestroy(e);
+    for (auto& st : ingest_stream)
+      if (st) cudaStreamDestroy(st);
   }
 };
 
@@ -381,8 +389,22 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
                                s->copy_stream));
     }
     UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
-    UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_copied[slot], 0));
-    jpeg_gpu_launch(c, 2, gpu_jobs, d_buf, d_planes, bayer_bggr, d_bgr, s->src_pitch, L.jpeg_status.get());
+    if (!s->ingest_stream[slot]) {
+      UVO_CUDA(cudaStreamCreateWithFlags(&s->ingest_stream[slot], cudaStreamNonBlocking));
+      UVO_CUDA(cudaEventCreateWithFlags(&s->ev_ingest[slot], cudaEventDisableTiming));
+    }
+    {
+      // decode on the slot's ingest stream; it may not overwrite the lane's status words or the slot's staging pair
+      // before the lane's previous frame (which read them) is done: the lane's result event covers both
+      cudaStream_t ing = s->ingest_stream[slot];
+      UVO_CUDA(cudaStreamWaitEvent(ing, s->ev_copied[slot], 0));
+      if (L.used) UVO_CUDA(cudaStreamWaitEvent(ing, L.ev_result, 0));
+      c.stream = ing;
+      jpeg_gpu_launch(c, 2, gpu_jobs, d_buf, d_planes, bayer_bggr, d_bgr, s->src_pitch, L.jpeg_status.get());
+      c.stream = L.stream;
+      UVO_CUDA(cudaEventRecord(s->ev_ingest[slot], ing));
+      UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_ingest[slot], 0));
+    }
     jpeg_on_gpu = true;
     s->gpu_entropy_frames++;
     dL = d_bgr[0];

@@ -526,6 +526,29 @@ bool build_gpu_plan(const uint8_t* d, size_t len, JhPlan* plan, uint8_t* scan_ou
     memcpy(plan->maxcode[t], h.maxcode, sizeof(h.maxcode));
     memcpy(plan->valoff[t], h.valoff, sizeof(h.valoff));
     memcpy(plan->huffval[t], h.huffval, sizeof(h.huffval));
+    // second level: every 16-bit pattern whose 10-bit prefix starts a longer code, resolved with the host decoder's rule
+    int n_sub = 0;
+    for (int pre = 0; pre < (1 << JH_FAST_BITS); pre++) {
+      if (plan->fast[t][pre]) continue;
+      bool any = false;
+      uint16_t tab[64];
+      for (int low = 0; low < 64; low++) {
+        const int x16 = (pre << 6) | low;
+        tab[low] = 0;
+        for (int l = JH_FAST_BITS + 1; l <= 16; l++) {
+          const int code = x16 >> (16 - l);
+          if (code <= h.maxcode[l]) {
+            tab[low] = (uint16_t)((l << 8) | h.huffval[(code + h.valoff[l]) & 255]);
+            any = true;
+            break;
+          }
+        }
+      }
+      if (!any || n_sub >= JH_SUB_TABLES) continue;  // no code there, or out of sub-tables: the slow walk handles it
+      memcpy(plan->sub[t] + 64 * n_sub, tab, sizeof(tab));
+      plan->fast[t][pre] = (uint16_t)(0x8000 | n_sub);
+      n_sub++;
+    }
   }
   int bpm = 0;
   for (int j = 0; j < ns; j++) {
@@ -601,6 +624,7 @@ bool build_gpu_plan(const uint8_t* d, size_t len, JhPlan* plan, uint8_t* scan_ou
 
 struct JhShared {
   uint16_t fast[4][1 << JH_FAST_BITS];
+  uint16_t sub[4][JH_SUB_TABLES * 64];
   int32_t maxcode[4][18];
   int32_t valoff[4][17];
   uint8_t huffval[4][256];
@@ -624,19 +648,22 @@ struct JhBits {
   const uint32_t* __restrict__ w;
   unsigned long long buf;  // the next `avail` bits of the stream, left-aligned
   int avail;
-  unsigned next;           // index of the next word to load
+  unsigned next;           // index of the word after `ahead`
+  uint32_t ahead;          // the next word, loaded one refill early so that its latency hides behind the symbols between
   __device__ __forceinline__ void open(const uint32_t* __restrict__ words, unsigned pos) {
     w = words;
     const unsigned k = pos >> 5, sh = pos & 31;
     const unsigned long long a = __byte_perm(__ldg(w + k), 0, 0x0123), b = __byte_perm(__ldg(w + k + 1), 0, 0x0123);
     buf = ((a << 32) | b) << sh;
     avail = 64 - (int)sh;
-    next = k + 2;
+    ahead = __ldg(w + k + 2);
+    next = k + 3;
   }
   __device__ __forceinline__ uint32_t peek32() {
     if (avail <= 32) {
-      buf |= (unsigned long long)__byte_perm(__ldg(w + next), 0, 0x0123) << (32 - avail);
+      buf |= (unsigned long long)__byte_perm(ahead, 0, 0x0123) << (32 - avail);
       avail += 32;
+      ahead = __ldg(w + next);
       next++;
     }
     return (uint32_t)(buf >> 32);
@@ -657,7 +684,8 @@ __device__ __forceinline__ bool jh_symbol(const JhShared& T, JhBits& in, unsigne
   const int comp = T.blk_comp[s.p];
   const int t = s.z == 0 ? T.dc_tab[comp] : T.ac_tab[comp];
   int len, sym;
-  const unsigned e = T.fast[t][x >> (32 - JH_FAST_BITS)];
+  unsigned e = T.fast[t][x >> (32 - JH_FAST_BITS)];
+  if (e & 0x8000u) e = T.sub[t][((e & 0x7fffu) << 6) | ((x >> (32 - JH_FAST_BITS - 6)) & 63u)];
   if (e) {
     len = e >> 8;
     sym = e & 255;
@@ -762,6 +790,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
   const JhPlan* __restrict__ P = im.plan;
   const int tid = threadIdx.x;
   for (int i = tid; i < (int)(sizeof(T.fast) / 2); i += JH_BLOCK) (&T.fast[0][0])[i] = (&P->fast[0][0])[i];
+  for (int i = tid; i < (int)(sizeof(T.sub) / 2); i += JH_BLOCK) (&T.sub[0][0])[i] = (&P->sub[0][0])[i];
   for (int i = tid; i < 4 * 18; i += JH_BLOCK) (&T.maxcode[0][0])[i] = (&P->maxcode[0][0])[i];
   for (int i = tid; i < 4 * 17; i += JH_BLOCK) (&T.valoff[0][0])[i] = (&P->valoff[0][0])[i];
   for (int i = tid; i < 4 * 256; i += JH_BLOCK) (&T.huffval[0][0])[i] = (&P->huffval[0][0])[i];
@@ -795,6 +824,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
   // changes nothing in ANY image of the launch (every block must take part in every grid barrier).
   const unsigned begin = (unsigned)g * JH_SUB_BITS, end = min(begin + JH_SUB_BITS, total_bits);
   JhState start{begin, 0, 0}, prev{0xffffffffu, -1, -1}, ex{begin, 0, 0};
+  unsigned cp_pos0 = 0xffffffffu, cp_pos1 = 0xffffffffu, cp_pos2 = 0xffffffffu, cp_pz0 = 0, cp_pz1 = 0, cp_pz2 = 0;
   int kind, zz, val;
   int rounds = 0;
   for (;; rounds++) {
@@ -815,11 +845,31 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
         JhState s = start;
         JhBits in;
         in.open(w, s.pos);
-        while (s.pos < end && jh_symbol(T, in, total_bits, bpm, s, kind, zz, val)) {
+        // check-points: the decoder's state at the first symbol boundary at or after each quarter of the sub-sequence.
+        // A re-decode that reaches a check-point in the state the previous decode had there is in step with it for
+        // good: it stops, and the exit state stands.
+        int ck = 0;
+        bool in_step = false;
+        while (s.pos < end) {
+          if (ck < 3 && s.pos >= begin + (unsigned)(JH_SUB_BITS / 4) * (ck + 1)) {
+            const unsigned key = (unsigned)((s.p << 8) | s.z);
+            unsigned& cpos = ck == 0 ? cp_pos0 : (ck == 1 ? cp_pos1 : cp_pos2);
+            unsigned& cpz = ck == 0 ? cp_pz0 : (ck == 1 ? cp_pz1 : cp_pz2);
+            if (rounds > 0 && cpos == s.pos && cpz == key) {
+              in_step = true;
+              break;
+            }
+            cpos = s.pos;
+            cpz = key;
+            ck++;
+          }
+          if (!jh_symbol(T, in, total_bits, bpm, s, kind, zz, val)) break;
         }
-        if (s.pos < end) s.pos = total_bits;  // stopped by the end of the data
-        if (rounds == 0 || s.pos != ex.pos || s.p != ex.p || s.z != ex.z) flag[rounds % 3] = 1;
-        ex = s;
+        if (!in_step) {
+          if (s.pos < end) s.pos = total_bits;  // stopped by the end of the data
+          if (rounds == 0 || s.pos != ex.pos || s.p != ex.p || s.z != ex.z) flag[rounds % 3] = 1;
+          ex = s;
+        }
       }
       ex_cur[g] = make_uint2(ex.pos, (unsigned)((ex.p << 8) | ex.z));
     }

@@ -26,8 +26,13 @@ constexpr int JH_SUB_BITS = 1024;    // bits per sub-sequence (= per thread): a 
 constexpr int JH_MAX_ROUNDS = 64;    // more rounds than that without a fixed point: reported as a corrupt stream
 constexpr int JH_MAX_BPM = 10;  // blocks per MCU (T.81: at most 10 in an interleaved scan)
 
+constexpr int JH_SUB_TABLES = 16;  // second-level tables (64 entries: the 6 bits after the first 10) per Huffman table
+
 struct JhPlan {  // host-built, read by the kernel (POD; lives in pinned memory next to the scan bytes)
-  uint16_t fast[4][1 << JH_FAST_BITS];  // tables 0, 1: DC; 2, 3: AC.  (code length << 8) | symbol, 0 = longer code
+  // tables 0, 1: DC; 2, 3: AC.  (code length << 8) | symbol; 0x8000 | k: a longer code, continue in sub-table k with
+  // the next 6 bits; 0: a longer code whose prefix got no sub-table (walk maxcode / valoff, as the host decoder does)
+  uint16_t fast[4][1 << JH_FAST_BITS];
+  uint16_t sub[4][JH_SUB_TABLES * 64];  // (code length << 8) | symbol, 0 = not a code
   int32_t maxcode[4][18];
   int32_t valoff[4][17];
   uint8_t huffval[4][256];
