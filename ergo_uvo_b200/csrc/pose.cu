@@ -373,7 +373,7 @@ struct HypSmem {
   double S[2 * 144], Vr[2 * 144], ut[144], w[12], l[60], rho[6], al[5][4], us[10], rot[24], model[15];
   BetaSmem beta;
   unsigned rflag[2];
-  int cnt[4];
+  int cnt[8];
 };
 
 template <int NT>
@@ -462,13 +462,16 @@ __device__ void pnp_hypothesis(const PnpArgs& a, int h, HypSmem& sm, int tid, bo
 // reaches niters the state is marked done and every later chunk kernel returns at once: hypotheses the CPU loop would
 // never have drawn are not solved (the reference configuration stops after a handful -- 97 % inliers give niters = 2
 // -- so the first chunk of 32 is normally the only one that runs).  Exactness is untouched: the replay sees the same
-// counts in the same order.  NW = 4 (one hypothesis per block) for the small leading chunks, where the latency of ONE
-// hypothesis is the latency of the stage; NW = 1 (four per block) for the large ones, where throughput counts.
-constexpr int CHUNK_THREADS = 128;
+// counts in the same order.  NW = 8 (one hypothesis per block of 8 warps: one S / Vr element per thread in a Jacobi
+// round, 256 threads on the scoring pass) for the small leading chunks, where the latency of ONE hypothesis is the
+// latency of the stage; NW = 1 (four one-warp hypotheses per block) for the large ones, where throughput counts.
+template <int NW>
+struct ChunkThreads { static constexpr int value = NW == 1 ? 128 : 32 * NW; };
+constexpr int CHUNK_NW = 8;
 
 template <int NW>
-__global__ void __launch_bounds__(CHUNK_THREADS) k_pnp_chunk(const __grid_constant__ PnpArgs a, int lo, int hi) {
-  constexpr int NT = 32 * NW, HPB = 4 / NW;
+__global__ void __launch_bounds__(ChunkThreads<NW>::value) k_pnp_chunk(const __grid_constant__ PnpArgs a, int lo, int hi) {
+  constexpr int NT = 32 * NW, HPB = ChunkThreads<NW>::value / NT;
   __shared__ HypSmem s_hyp[HPB];
   __shared__ int s_last;
   PnpState* st = a.state;
@@ -642,6 +645,8 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
   }
   const double c0[3] = {s_out[0] / ni, s_out[1] / ni, s_out[2] / ni};
   __syncthreads();
+  // (the covariance is summed from centred points: it must stay positive semi-definite to rounding -- a planar scene
+  // has a zero eigenvalue there, and a one-pass S2 - n c0 c0^T would replace it by cancellation noise)
   {
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = tid; k < ni; k += blockDim.x) {
@@ -730,27 +735,12 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
     s_sign3[w] = pc[2] < 0.0 ? -1.0 : 1.0;  // solve_for_sign
   }
   __syncthreads();
+  // centroids of the camera-frame points and ABt = sum (pc - pc0)(pw - pw0)^T = sum pc pw^T - n pc0 pw0^T for the three
+  // candidates from one pass over the inliers (36 sums)
   double pc0[3][3];
   {
-    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = tid; k < ni; k += blockDim.x) {
-      double al[4], pc[3];
-      point(k, pw, u, v);
-      epnp_alphas(pw, s_cws, s_ci, al);
-#pragma unroll
-      for (int w = 0; w < 3; w++) {
-        epnp_pc(al, s_ccs3[w], s_sign3[w], pc);
-        for (int cc = 0; cc < 3; cc++) acc[3 * w + cc] += pc[cc];
-      }
-    }
-    block_reduce_sum<9>(acc, s_red, s_out);
-    for (int w = 0; w < 3; w++)
-      for (int cc = 0; cc < 3; cc++) pc0[w][cc] = s_out[3 * w + cc] / ni;
-  }
-  __syncthreads();
-  {
-    double acc[27];
-    for (int i = 0; i < 27; i++) acc[i] = 0;
+    double acc[36];
+    for (int i = 0; i < 36; i++) acc[i] = 0;
     for (int k = tid; k < ni; k += blockDim.x) {
       double al[4], pc[3];
       point(k, pw, u, v);
@@ -759,17 +749,21 @@ __global__ void __launch_bounds__(REFIT_THREADS) k_pnp_finalize(const __grid_con
       for (int w = 0; w < 3; w++) {
         epnp_pc(al, s_ccs3[w], s_sign3[w], pc);
         for (int j = 0; j < 3; j++) {
-          acc[9 * w + 3 * j] += (pc[j] - pc0[w][j]) * (pw[0] - c0[0]);
-          acc[9 * w + 3 * j + 1] += (pc[j] - pc0[w][j]) * (pw[1] - c0[1]);
-          acc[9 * w + 3 * j + 2] += (pc[j] - pc0[w][j]) * (pw[2] - c0[2]);
+          acc[3 * w + j] += pc[j];
+          acc[9 + 9 * w + 3 * j] += pc[j] * pw[0];
+          acc[9 + 9 * w + 3 * j + 1] += pc[j] * pw[1];
+          acc[9 + 9 * w + 3 * j + 2] += pc[j] * pw[2];
         }
       }
     }
-    block_reduce_sum<27>(acc, s_red, s_out);
+    block_reduce_sum<36>(acc, s_red, s_out);
+    for (int w = 0; w < 3; w++)
+      for (int cc = 0; cc < 3; cc++) pc0[w][cc] = s_out[3 * w + cc] / ni;
   }
   if (tid < 3) {
     double abt[9];
-    for (int i = 0; i < 9; i++) abt[i] = s_out[9 * tid + i];
+    for (int j = 0; j < 3; j++)
+      for (int q = 0; q < 3; q++) abt[3 * j + q] = s_out[9 + 9 * tid + 3 * j + q] - ni * pc0[tid][j] * c0[q];
     epnp_rt_from_abt(abt, pc0[tid], c0, s_R3[tid], s_t3[tid]);
   }
   __syncthreads();
@@ -941,8 +935,8 @@ void launch_pnp_solve(Ctx& c, const PnpArgs& a) {
     static const char* const kChunkNames[4] = {"k_pnp_chunk[0:32]", "k_pnp_chunk[32:128]", "k_pnp_chunk[128:512]",
                                                "k_pnp_chunk[512:]"};
     UVO_KERNEL(c, kChunkNames[k]);
-    if (hi <= 128) k_pnp_chunk<4><<<hi - lo, CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
-    else k_pnp_chunk<1><<<div_up(hi - lo, 4), CHUNK_THREADS, 0, c.stream>>>(a, lo, hi);
+    if (hi <= 128) k_pnp_chunk<CHUNK_NW><<<hi - lo, ChunkThreads<CHUNK_NW>::value, 0, c.stream>>>(a, lo, hi);
+    else k_pnp_chunk<1><<<div_up(hi - lo, 4), ChunkThreads<1>::value, 0, c.stream>>>(a, lo, hi);
     UVO_LAUNCH_CHECK(c);
     lo = hi;
   }
