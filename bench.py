@@ -526,7 +526,15 @@ def run_gpu(args):
                 run_compressed_gpu(n_comp, 48 + r_ * n_comp)
                 barrier()
                 gpu_regions.append((time.perf_counter() - t0) * 1e3)
-            comp = {"gpu_region_ms": gpu_regions, "gpu_entropy_frames": vo.gpu_entropy_frames,
+            # one long region of the same leg: the fill of a 14-deep pipeline (upload + 0.8 ms decode + the frame
+            # itself) is a fifth of a 20-frame region
+            n_long_c = max(10 * args.steps, 200)
+            barrier()
+            t0 = time.perf_counter()
+            run_compressed_gpu(n_long_c, 48 + 5 * n_comp)
+            barrier()
+            gpu_long_ms = (time.perf_counter() - t0) * 1e3
+            comp = {"gpu_region_ms": gpu_regions, "gpu_long": (n_long_c, gpu_long_ms), "gpu_entropy_frames": vo.gpu_entropy_frames,
                     "gpu_host_enqueue_us": 1e6 * gpu_host_s[0] / max(gpu_host_s[1], 1),
                     "gpu_h2d_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])) + 2 * 9500.0,"region_ms": comp_regions, "frames_per_region": n_comp, "valid": comp_valid,
                     "h2d_bytes_per_step": comp_bytes / float(n_comp * len(comp_regions)),
@@ -570,10 +578,12 @@ def run_gpu(args):
     # ---- max over ranks (per region), then the median region
     comp_ms = float(np.median(comp["region_ms"])) if comp else 0.0
     comp_gpu_ms = float(np.median(comp["gpu_region_ms"])) if comp else 0.0
+    comp_gpu_long_ms = comp["gpu_long"][1] if comp else 0.0
     all_ms, v = aggregate_over_ranks(dist if world > 1 else None,
-                                     dev_regions + host_regions + [ms_long_dev, ms_long_host, comp_ms, comp_gpu_ms],
+                                     dev_regions + host_regions + [ms_long_dev, ms_long_host, comp_gpu_long_ms, comp_ms,
+                                                                   comp_gpu_ms],
                                      [float(valid_dev), float(valid_host)], "cuda")
-    comp_ms, comp_gpu_ms = all_ms[-2], all_ms[-1]
+    comp_gpu_long_ms, comp_ms, comp_gpu_ms = all_ms[-3], all_ms[-2], all_ms[-1]
     R_ = args.regions
     dev_regions, host_regions = all_ms[:R_], all_ms[R_:2 * R_]
     ms_long_dev, ms_long_host = all_ms[2 * R_], all_ms[2 * R_ + 1]
@@ -677,6 +687,8 @@ def run_gpu(args):
                 "gpu_entropy": {"value": comp["frames_per_region"] * world / (comp_gpu_ms * 1e-3), "unit": "frames/s",
                                 "h2d_bytes_per_step": comp["gpu_h2d_bytes_per_step"], "host_threads_per_gpu": 1,
                                 "frames_in_flight": max(inflight, 14),
+                                "steady_state": {"frames": comp["gpu_long"][0],
+                                                 "value": comp["gpu_long"][0] * world / (comp_gpu_long_ms * 1e-3)},
                                 "region_ms": comp["gpu_region_ms"], "frames_on_gpu_decoder": comp["gpu_entropy_frames"],
                                 "host_enqueue_us_per_frame": comp["gpu_host_enqueue_us"],
                                 "api": "uvo_stereo_enqueue_host_jpeg + uvo_stereo_collect"}},

@@ -225,6 +225,7 @@ struct uvo_stereo {
   PinnedBuf<uint32_t> jpeg_host[RING][2];
   // the decode of a compressed frame runs on its result slot's own stream, not on the lane: with up to RING frames
   // enqueued, the (long, narrow) Huffman decode of frame t + N_LANES overlaps the lane work of frame t
+  DevBuf<int> jpeg_slot_status[RING];
   cudaStream_t ingest_stream[RING] = {};
   cudaEvent_t ev_ingest[RING] = {};
   cudaEvent_t ev_copied[RING] = {};
@@ -389,21 +390,25 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
                                s->copy_stream));
     }
     UVO_CUDA(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
-    if (!s->ingest_stream[slot]) {
-      UVO_CUDA(cudaStreamCreateWithFlags(&s->ingest_stream[slot], cudaStreamNonBlocking));
-      UVO_CUDA(cudaEventCreateWithFlags(&s->ev_ingest[slot], cudaEventDisableTiming));
-    }
+    // the decode runs on an ingest stream, not on the lane, and depends on nothing but its own upload: every buffer
+    // it writes belongs to the result slot (whose previous user, frame_no - RING, has been collected), including
+    // the status words -- the lane gets a copy.  Frame t + k therefore decodes while the lanes work on frames t ...
+    // The number of ingest streams in use bounds how many decoder launches are in flight (jpeg_gpu_max_concurrent).
+    const int n_ing = std::min(uvo_stereo::RING, jpeg_gpu_max_concurrent(c, 2, gpu_jobs));
+    const int is = slot % n_ing;
+    if (!s->ingest_stream[is]) UVO_CUDA(cudaStreamCreateWithFlags(&s->ingest_stream[is], cudaStreamNonBlocking));
+    if (!s->ev_ingest[slot]) UVO_CUDA(cudaEventCreateWithFlags(&s->ev_ingest[slot], cudaEventDisableTiming));
+    s->jpeg_slot_status[slot].ensure(80);
     {
-      // decode on the slot's ingest stream; it may not overwrite the lane's status words or the slot's staging pair
-      // before the lane's previous frame (which read them) is done: the lane's result event covers both
-      cudaStream_t ing = s->ingest_stream[slot];
+      cudaStream_t ing = s->ingest_stream[is];
       UVO_CUDA(cudaStreamWaitEvent(ing, s->ev_copied[slot], 0));
-      if (L.used) UVO_CUDA(cudaStreamWaitEvent(ing, L.ev_result, 0));
       c.stream = ing;
-      jpeg_gpu_launch(c, 2, gpu_jobs, d_buf, d_planes, bayer_bggr, d_bgr, s->src_pitch, L.jpeg_status.get());
+      jpeg_gpu_launch(c, 2, gpu_jobs, d_buf, d_planes, bayer_bggr, d_bgr, s->src_pitch, s->jpeg_slot_status[slot].get());
       c.stream = L.stream;
       UVO_CUDA(cudaEventRecord(s->ev_ingest[slot], ing));
       UVO_CUDA(cudaStreamWaitEvent(c.stream, s->ev_ingest[slot], 0));
+      UVO_CUDA(cudaMemcpyAsync(L.jpeg_status.get(), s->jpeg_slot_status[slot].get(), 80 * sizeof(int),
+                               cudaMemcpyDeviceToDevice, c.stream));
     }
     jpeg_on_gpu = true;
     s->gpu_entropy_frames++;

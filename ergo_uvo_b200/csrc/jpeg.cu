@@ -15,7 +15,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "capi_internal.cuh"
 #include "jpeg.cuh"
@@ -781,9 +783,53 @@ __device__ __forceinline__ unsigned long long jh_now() {
   return t;
 }
 
+// Grid-wide barrier of a launch whose blocks are all resident (the host bounds how many of these launches are in
+// flight, see jpeg_gpu_max_concurrent): a monotonic arrival counter, one poller per block.  A block that waits longer
+// than JH_BARRIER_TIMEOUT_NS raises the launch's abort word and every block leaves -- the image is reported corrupt
+// instead of the GPU hanging if the residency assumption were ever violated.
+constexpr unsigned long long JH_BARRIER_TIMEOUT_NS = 500ull * 1000 * 1000;
+__device__ __forceinline__ bool jh_soft_sync(unsigned* bar, unsigned& target, unsigned nblk) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblk;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v, ab = 0, polls = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if ((++polls & 1023u) == 0) {
+        asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(ab) : "l"(bar + 1) : "memory");
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (!t0) t0 = t;
+        if (t - t0 > JH_BARRIER_TIMEOUT_NS) {
+          atomicExch(bar + 1, 1u);
+          ab = 1;
+        }
+        if (ab) break;
+      }
+    }
+    __threadfence();
+    s_ok = !ab;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
 __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ JhArgs args) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  unsigned bar_target = 0;
+  const unsigned n_blk = gridDim.x * gridDim.y;
+  bool aborted = false;
+  auto grid_sync = [&]() {
+    if (args.bar) {
+      if (!aborted && !jh_soft_sync(args.bar, bar_target, n_blk)) aborted = true;
+    } else {
+      cooperative_groups::this_grid().sync();
+    }
+  };
   __shared__ JhShared T;
   __shared__ int s_w[JH_BLOCK / 32 + 1][3];
   const JhImage& im = args.im[blockIdx.y];
@@ -811,6 +857,30 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
   const int g = blockIdx.x * JH_BLOCK + tid;                             // this thread's sub-sequence
   const bool live = g < n_sub;
   int* flag = args.flag;
+  // this thread's share of the scan-order blocks in the DC passes (and of the block table it must leave decodable)
+  const int n_thr = gridDim.x * JH_BLOCK;
+  const int bper = (total_blocks + n_thr - 1) / n_thr;
+  const int gi = blockIdx.x * JH_BLOCK + tid;
+  const int b0 = min(gi * bper, total_blocks), b1 = min(b0 + bper, total_blocks);
+  auto leave_empty = [&]() {  // a corrupt stream (or an aborted launch) leaves a decodable, empty image behind
+    for (int b = b0; b < b1; b++) {
+      im.first[b] = 0;
+      im.count[b] = 0;
+    }
+    if (aborted && gi == 0) {
+      im.info[0] = 0;
+      im.info[1] = 1;
+      im.info[2] = JH_MAX_ROUNDS + 1;
+    }
+  };
+#define JH_GRID_SYNC()  \
+  do {                  \
+    grid_sync();        \
+    if (aborted) {      \
+      leave_empty();    \
+      return;           \
+    }                   \
+  } while (0)
   __syncthreads();
   // diagnostics: phase time stamps (ns) of block (0, 0) in info[16 .. 63] (tools/jh_time.py)
   unsigned long long* stamps = (unsigned long long*)(args.im[0].info + 16);
@@ -873,7 +943,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
       }
       ex_cur[g] = make_uint2(ex.pos, (unsigned)((ex.p << 8) | ex.z));
     }
-    grid.sync();
+    JH_GRID_SYNC();
     if (rounds < 2) stamp();
     if (!flag[rounds % 3] || rounds >= JH_MAX_ROUNDS) break;
   }
@@ -891,7 +961,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
     }
     im.counts[g] = make_int2(cnt[0], cnt[1]);
   }
-  grid.sync();
+  JH_GRID_SYNC();
   stamp();
   // ---- per-image exclusive scan of the counts by the image's first block
   if (blockIdx.x == 0) {
@@ -918,7 +988,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
       im.info[2] = rounds + 1;
     }
   }
-  grid.sync();
+  JH_GRID_SYNC();
   stamp();
   // ---- phase 3: write the entries (DC entries carry the DIFFERENCE for now) and the scan-order block table
   if (live) {
@@ -938,21 +1008,17 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
       }
     }
   }
-  grid.sync();
+  JH_GRID_SYNC();
   stamp();
   const bool err = im.info[1] != 0;
   // ---- phase 4: DC prediction = running sum of the differences per component, in scan order: per-thread partial sums
   // over a contiguous range of scan-order blocks, scanned by the image's first block
-  const int n_thr = gridDim.x * JH_BLOCK;
-  const int bper = (total_blocks + n_thr - 1) / n_thr;
-  const int gi = blockIdx.x * JH_BLOCK + tid;
-  const int b0 = min(gi * bper, total_blocks), b1 = min(b0 + bper, total_blocks);
   if (!err) {
     int acc[3] = {0, 0, 0};
     for (int sb = b0; sb < b1; sb++) acc[T.blk_comp[sb % bpm]] += (int)(int16_t)(im.entries[im.first_scan[sb]] & 0xffffu);
     im.dc_part[gi] = make_int4(acc[0], acc[1], acc[2], 0);
   }
-  grid.sync();
+  JH_GRID_SYNC();
   if (blockIdx.x == 0 && !err) {
     const int per = (n_thr + JH_BLOCK - 1) / JH_BLOCK;
     const int a0 = min(tid * per, n_thr), a1 = min(a0 + per, n_thr);
@@ -972,14 +1038,11 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
       v[2] += c.z;
     }
   }
-  grid.sync();
+  JH_GRID_SYNC();
   // ---- phase 5: absolute DC values, and the block table in plane order (component-major, row-major), which is how
   // k_jpeg_idct numbers its blocks.  A corrupt stream leaves a decodable (empty) image behind.
   if (err) {
-    for (int b = b0; b < b1; b++) {
-      im.first[b] = 0;
-      im.count[b] = 0;
-    }
+    leave_empty();
     return;
   }
   const int4 pb = im.dc_part[gi];
@@ -999,6 +1062,7 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
   stamp();
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) args.im[0].info[15] = n_stamp;
 }
+#undef JH_GRID_SYNC
 }  // namespace
 
 namespace uvo {
@@ -1116,6 +1180,39 @@ static GpuLayout gpu_layout(const uvo_jpeg_layout& L, size_t upload_bytes) {
 
 size_t jpeg_gpu_device_bytes(const uvo_jpeg_layout& L, size_t upload_bytes) { return gpu_layout(L, upload_bytes).total; }
 
+// The decoder's grid barrier.  Default: the kernel's own arrival counter on an ordinary launch -- cooperative launches
+// do not overlap one another, which would cap compressed input at 1 / (decode time of one pair) however many frames
+// are enqueued.  UVO_JPEG_COOPERATIVE=1 selects cudaLaunchCooperativeKernel + cooperative_groups' grid sync instead.
+static bool jh_use_cooperative() {
+  static const bool v = [] {
+    const char* e = getenv("UVO_JPEG_COOPERATIVE");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+// blocks of k_jpeg_huff the device holds at once (every block of a launch spins at the barriers, so all must be resident)
+static int jh_resident_blocks(Ctx& c) {
+  static std::mutex mu;
+  static int cached[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  int& v = cached[c.device & 63];
+  if (!v) {
+    int per_sm = 0, sms = 0;
+    UVO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jpeg_huff, JH_BLOCK, 0));
+    UVO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    v = std::max(per_sm * sms, 1);
+  }
+  return v;
+}
+// how many decoder launches of this width may be in flight at once: together they stay inside half of the device, so
+// whatever order the hardware dispatches their blocks in, every launch becomes fully resident
+int jpeg_gpu_max_concurrent(Ctx& c, int n, const JpegGpuJob* jobs) {
+  if (jh_use_cooperative()) return 1 << 20;
+  int blocks = 1;
+  for (int i = 0; i < n; i++) blocks = std::max(blocks, jh_blocks(jobs[i].upload_bytes));
+  return std::max(jh_resident_blocks(c) / 2 / (blocks * n), 1);
+}
+
 __global__ void k_jpeg_huff_status(const int* info0, const int* info1, int* status) {
   status[0] = info0[1];
   status[1] = info0[2];
@@ -1151,10 +1248,17 @@ void jpeg_gpu_launch(Ctx& c, int n, const JpegGpuJob* jobs, uint8_t* const* d_bu
   for (int i = 0; i < n; i++)
     UVO_REQUIRE(blocks <= 4 * jh_blocks(jobs[i].upload_bytes) + 4, "jpeg pair: the two scans differ too much in length");
   a.flag = (int*)(d_buf[0] + g[0].info) + 8;
-  UVO_CUDA(cudaMemsetAsync(a.flag, 0, 3 * sizeof(int), c.stream));
-  void* kargs[1] = {(void*)&a};
+  const bool cooperative = jh_use_cooperative();
+  a.bar = cooperative ? nullptr : (unsigned*)(a.flag + 4);
+  UVO_CUDA(cudaMemsetAsync(a.flag, 0, 6 * sizeof(int), c.stream));
   UVO_KERNEL(c, "k_jpeg_huff");
-  UVO_CUDA(cudaLaunchCooperativeKernel((const void*)k_jpeg_huff, dim3(blocks, n), dim3(JH_BLOCK), kargs, 0, c.stream));
+  if (cooperative) {
+    void* kargs[1] = {(void*)&a};
+    UVO_CUDA(cudaLaunchCooperativeKernel((const void*)k_jpeg_huff, dim3(blocks, n), dim3(JH_BLOCK), kargs, 0, c.stream));
+  } else {
+    UVO_REQUIRE(blocks * n <= jh_resident_blocks(c), "jpeg: the scan needs more decoder blocks than the device holds");
+    k_jpeg_huff<<<dim3(blocks, n), JH_BLOCK, 0, c.stream>>>(a);
+  }
   UVO_LAUNCH_CHECK(c);
   if (d_status) {
     k_jpeg_huff_status<<<1, 1, 0, c.stream>>>(a.im[0].info, n > 1 ? a.im[1].info : nullptr, d_status);

@@ -36,6 +36,8 @@ bool jpeg_gpu_prepare(const uint8_t* jpeg, size_t len, uint8_t* pinned, size_t p
 size_t jpeg_gpu_device_bytes(const uvo_jpeg_layout& L, size_t upload_bytes);
 // k_jpeg_huff for n (1 or 2) uploaded images in ONE launch, then IDCT + colour / demosaic per image, all on c.stream.
 // d_status (nullable): two ints per image on the device, [error, synchronisation rounds]
+// how many jpeg_gpu_launch calls of this size may be in flight at once (on different streams); see jpeg.cu
+int jpeg_gpu_max_concurrent(Ctx& c, int n, const JpegGpuJob* jobs);
 void jpeg_gpu_launch(Ctx& c, int n, const JpegGpuJob* jobs, uint8_t* const* d_buf, uint8_t* const* d_planes,
                      int bayer_bggr, uint8_t* const* d_bgr, size_t bgr_pitch, int* d_status);
 

@@ -61,6 +61,7 @@ struct JhImage {
 struct JhArgs {
   JhImage im[2];
   int* flag;              // three ints: "some exit state changed in this round", by round number mod 3
+  unsigned* bar;          // software grid barrier: [0] arrivals (monotonic), [1] abort; nullptr: cooperative launch
 };
 
 }  // namespace uvo

@@ -123,6 +123,19 @@ SurfGeom make_surf_geom(int w, int h, double hessian_threshold, int n_octaves, i
     for (int l = 1; l <= n_layers; l++) O.nms_margin[l] = (O.layer[l + 1].size / 2) / O.step + 1;
   }
   g.total_tiles = tile_begin;
+  // the screen of k_surf_detect (see screen_tile0): valid when the Dxx / Dyy weights of every middle layer are
+  // (w, -2w, w) in f32 and the integer combination stays below 2^24; otherwise nothing is screened out
+  bool screen_ok = true;
+  for (int o = 0; o < n_octaves; o++)
+    for (int l = 1; l <= n_layers; l++) {
+      const SurfLayer& L = g.oct[o].layer[l];
+      for (int a = 0; a < 6; a += 3) {
+        const float wgt = L.box[a].w;
+        screen_ok = screen_ok && wgt > 0.f && L.box[a + 2].w == wgt && L.box[a + 1].w == -2.f * wgt &&
+                    4.0 * 255.0 / (double)wgt < 16777216.0;
+      }
+    }
+  g.thr_skip = screen_ok ? std::nextafterf(g.thr - 1.0f - fabsf(g.thr) * 1e-6f, -INFINITY) : -INFINITY;
   return g;
 }
 
@@ -252,6 +265,65 @@ __device__ __forceinline__ float det_tile0(const int* __restrict__ T, const Surf
   return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
 
+// ---- screening ---------------------------------------------------------------------------------------------------
+// Most samples fail the lazy test fl(dx dy) > thr, but a warp pays for the exact evaluation (f64 sums, and the Dxy
+// half) as soon as ONE of its lanes passes.  So the tile is evaluated in two passes: a cheap screen of every sample,
+// then the exact evaluation of the survivors only, packed densely over the block.
+// The screen: the three Dxx boxes have equal areas (3 * size / 9 is an integer), so their weights are w, -2w, w with
+// the SAME f32 w (the host checks it, screen_weights_ok) and
+//     ax = fl((v0 - 2 v1 + v2) w)      (the integer is exact; |v0 - 2 v1 + v2| < 2^24 up to layer size 195)
+// differs from the exact dx = fl(fl(v0 w) - fl(2 v1 w) + fl(v2 w)) by at most 2^-24 (v0 + 2 v1 + v2) w + 2 * 2^-24 * 510
+// <= 1.3e-4 for 8-bit images (v w <= 255, |dx| <= 510); likewise ay.  Hence |dx dy - ax ay| <= 2 * 510 * 1.3e-4 = 0.13,
+// and with the f32 roundings of the two products (<= 0.016 each) a sample with ax ay <= thr - 1 can never have
+// fl(dx dy) > thr: it is DET_SKIPPED exactly as the lazy rule would have made it.  Everything else is evaluated
+// exactly.  The stored values are bit for bit those of the one-pass evaluation.
+__device__ __forceinline__ int screen_combine(unsigned A0, unsigned A1, unsigned A2, unsigned A3, unsigned B0,
+                                              unsigned B1, unsigned B2, unsigned B3) {
+  // v0 - 2 v1 + v2 with v_k = A_k + B_{k+1} - B_k - A_{k+1}
+  return (int)((A0 - A3 - B0 + B3) + 3u * (A2 - A1 + B1 - B2));
+}
+enum { SCREEN_OUTSIDE = 0, SCREEN_SKIP = 1, SCREEN_KEEP = 2 };
+
+template <int SIZE>
+__device__ __forceinline__ int screen_tile0(const int* __restrict__ T, const SurfLayer& L, int i, int j, int y, int x,
+                                            float thr_skip) {
+  constexpr int M = SIZE / 2;
+  const int si = i - M, sj = j - M;
+  if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return SCREEN_OUTSIDE;
+  const int* o = T + (y + T0_MAXM - M) * T0_COLS + (x + T0_MAXM - M + T0_XOFF);
+  constexpr int c0 = haar_off<SIZE>(0), c2 = haar_off<SIZE>(2), c3 = haar_off<SIZE>(3), c6 = haar_off<SIZE>(6),
+                c7 = haar_off<SIZE>(7), c9 = haar_off<SIZE>(9);
+  auto at = [&](int r, int c) -> unsigned { return (unsigned)o[r * T0_COLS + c]; };
+  const int sx = screen_combine(at(c2, c0), at(c2, c3), at(c2, c6), at(c2, c9), at(c7, c0), at(c7, c3), at(c7, c6),
+                                at(c7, c9));
+  const int sy = screen_combine(at(c0, c2), at(c3, c2), at(c6, c2), at(c9, c2), at(c0, c7), at(c3, c7), at(c6, c7),
+                                at(c9, c7));
+  const float ax = __fmul_rn((float)sx, L.box[0].w), ay = __fmul_rn((float)sy, L.box[3].w);
+  return __fmul_rn(ax, ay) > thr_skip ? SCREEN_KEEP : SCREEN_SKIP;
+}
+
+__device__ __forceinline__ int screen_at(const int* __restrict__ sum, int scols, const SurfLayer& L, int step, int i,
+                                         int j, float thr_skip) {
+  const int si = i - L.margin, sj = j - L.margin;
+  if (si < 0 || sj < 0 || si >= L.samples_i || sj >= L.samples_j) return SCREEN_OUTSIDE;
+  const int* o = sum + (size_t)(si * step) * scols + sj * step;
+  unsigned A[4], B[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    A[k] = (unsigned)__ldg(o + L.xx_row[0] + L.xx_col[k]);
+    B[k] = (unsigned)__ldg(o + L.xx_row[1] + L.xx_col[k]);
+  }
+  const int sx = screen_combine(A[0], A[1], A[2], A[3], B[0], B[1], B[2], B[3]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    A[k] = (unsigned)__ldg(o + L.yy_row[k] + L.yy_col[0]);
+    B[k] = (unsigned)__ldg(o + L.yy_row[k] + L.yy_col[1]);
+  }
+  const int sy = screen_combine(A[0], A[1], A[2], A[3], B[0], B[1], B[2], B[3]);
+  const float ax = __fmul_rn((float)sx, L.box[0].w), ay = __fmul_rn((float)sy, L.box[3].w);
+  return __fmul_rn(ax, ay) > thr_skip ? SCREEN_KEEP : SCREEN_SKIP;
+}
+
 // interpolateKeypoint: 3x3 Cramer solve in f32 (Matx33f::solve(DECOMP_LU))
 __device__ __forceinline__ bool interpolate_keypoint(const float N[3][9], int step, int ds, float& px, float& py,
                                                      float& psize) {
@@ -329,6 +401,8 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   __shared__ int s_ncand;
   __shared__ int s_dead[DET_LIST];  // candidate beaten by an outer-layer neighbour
   __shared__ unsigned s_claim[((SURF_MAX_LAYERS - 2) * (TH + 2) * (TW + 2) + 31) / 32];
+  __shared__ unsigned short s_surv[(SURF_MAX_LAYERS - 2) * (TH + 2) * (TW + 2)];  // samples that pass the screen
+  __shared__ int s_nsurv;
   const SurfImage& im = b.im[blockIdx.y];
   int t = blockIdx.x, o = 0;
   while (o + 1 < g.n_octaves && t >= g.oct[o + 1].tile_begin) o++;
@@ -351,7 +425,10 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
     }
     return det_at(im.sum, scols, O.layer[lm + 1], step, i, j);
   };
-  if (threadIdx.x == 0) s_ncand = 0;
+  if (threadIdx.x == 0) {
+    s_ncand = 0;
+    s_nsurv = 0;
+  }
   if (threadIdx.x < (int)(sizeof(s_claim) / sizeof(unsigned))) s_claim[threadIdx.x] = 0;
   if (threadIdx.x < DET_LIST) s_dead[threadIdx.x] = 0;
   if (o == 0) {
@@ -369,20 +446,53 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
     }
     __syncthreads();  // the barrier is initialised before anyone polls it
     mbar_wait(bar, 0);
-    for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
-      const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+  } else {
+    __syncthreads();
+  }
+  // pass 1: screen every sample of the middle layers; survivors go to a list (warp-aggregated append)
+  const int total = nmid * PLANE;
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int idx = base + threadIdx.x;
+    int verdict = SCREEN_SKIP, l = 0, y = 0, x = 0;
+    if (idx < total) {
+      l = idx / PLANE;
+      const int r = idx - l * PLANE;
+      y = r / (TW + 2);
+      x = r - y * (TW + 2);
       const int i = ti0 + y - 1, j = tj0 + x - 1;
-      float v;
+      if (o == 0) {
+        if (l == 0) verdict = screen_tile0<15>(s_tile, O.layer[1], i, j, y, x, g.thr_skip);
+        else if (l == 1) verdict = screen_tile0<21>(s_tile, O.layer[2], i, j, y, x, g.thr_skip);
+        else verdict = screen_tile0<27>(s_tile, O.layer[3], i, j, y, x, g.thr_skip);
+      } else {
+        verdict = screen_at(im.sum, scols, O.layer[l + 1], step, i, j, g.thr_skip);
+      }
+      if (verdict != SCREEN_KEEP) sdet[l][y][x] = verdict == SCREEN_OUTSIDE ? 0.f : DET_SKIPPED;
+    }
+    const unsigned keep = __ballot_sync(0xffffffffu, verdict == SCREEN_KEEP);
+    if (keep) {
+      const int lane = threadIdx.x & 31;
+      int at0 = 0;
+      if (lane == 0) at0 = atomicAdd(&s_nsurv, __popc(keep));
+      at0 = __shfl_sync(0xffffffffu, at0, 0);
+      if (verdict == SCREEN_KEEP) s_surv[at0 + __popc(keep & ((1u << lane) - 1))] = (unsigned short)idx;
+    }
+  }
+  __syncthreads();
+  // pass 2: the survivors, evaluated exactly (the lazy rule still skips the Dxy half of those with fl(dx dy) <= thr)
+  for (int k = threadIdx.x; k < s_nsurv; k += blockDim.x) {
+    const int idx = s_surv[k];
+    const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+    const int i = ti0 + y - 1, j = tj0 + x - 1;
+    float v;
+    if (o == 0) {
       if (l == 0) v = det_tile0<15, true>(s_tile, O.layer[1], i, j, y, x, g.thr);
       else if (l == 1) v = det_tile0<21, true>(s_tile, O.layer[2], i, j, y, x, g.thr);
       else v = det_tile0<27, true>(s_tile, O.layer[3], i, j, y, x, g.thr);
-      sdet[l][y][x] = v;
+    } else {
+      v = det_at<true>(im.sum, scols, O.layer[l + 1], step, i, j, g.thr);
     }
-  } else {
-    for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
-      const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
-      sdet[l][y][x] = det_at<true>(im.sum, scols, O.layer[l + 1], step, ti0 + y - 1, tj0 + x - 1, g.thr);
-    }
+    sdet[l][y][x] = v;
   }
   __syncthreads();
   // local maxima among the middle layers.  A skipped neighbour is <= thr < val0, and DET_SKIPPED = -inf compares

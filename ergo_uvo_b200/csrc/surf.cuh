@@ -39,6 +39,7 @@ struct SurfGeom {
   int w, h, n_octaves, n_layers, total_tiles;
   int spitch;  // surf_sum_pitch(w)
   float thr;
+  float thr_skip;  // samples whose screened fl(ax ay) is <= this cannot pass `det > thr` (-inf: screen disabled)
   SurfOctave oct[SURF_MAX_OCTAVES];
 };
 
