@@ -22,6 +22,10 @@ no collective on the data path; torch.distributed is used only for the barrier a
 import argparse
 import json
 import os
+
+# more hardware work queues than the default 8: the stereo handle uses 8 lane streams + a copy stream + the ingest
+# streams of compressed input; set before CUDA initialises (torch does that first in this process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading

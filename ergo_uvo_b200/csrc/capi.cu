@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points of libuvo_b200.so (include/uvo_c.h): context management and the
 // stage-level calls that take HOST buffers (the drop-in layer under the reference's VO_utility functions).
 // Device-resident whole-frame pipelines live in frame.cu.
+#include <cstdlib>
 #include <cstring>
 
 #include "capi_internal.cuh"
@@ -32,6 +33,11 @@ const char* uvo_version(void) { return "uvo-b200 0.1 (sm_100a)"; }
 int uvo_ctx_create(int device, void* cuda_stream, uvo_ctx** out) {
   if (!out) return UVO_ERR_INVALID;
   *out = nullptr;
+  // A stereo handle runs 8 lane streams, a copy stream and up to 14 ingest streams; with the default of 8 hardware
+  // work queues they alias and a long narrow kernel (the Huffman decode) holds up the lane that shares its queue
+  // (measured: 2 116 -> 2 410 frames/s from JPEG bytes).  Only effective when this is the process' first CUDA call;
+  // a host that initialises CUDA earlier sets the variable itself.  Never overrides the user's value.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {

@@ -198,9 +198,12 @@ struct Lane {
   }
 };
 
+#ifndef UVO_STEREO_RING
+#define UVO_STEREO_RING 16  // result slots = frames that may be enqueued and not yet collected
+#endif
 struct uvo_stereo {
   static constexpr int N_LANES = 8;
-  static constexpr int RING = 16;
+  static constexpr int RING = UVO_STEREO_RING;
   uvo_ctx* ctx = nullptr;
   int w = 0, h = 0, cap = 0;
   uvo_camera cam[2];

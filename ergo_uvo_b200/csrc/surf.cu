@@ -392,6 +392,9 @@ __device__ __noinline__ void emit_keypoint(const SurfOctave& O, const SurfImage&
 #ifndef UVO_DET_MINB
 #define UVO_DET_MINB 6
 #endif
+#ifndef UVO_DET_SCREEN
+#define UVO_DET_SCREEN 0  // two-pass evaluation (screen, then packed survivors): exact, but measured slower -- see DESIGN 4
+#endif
 __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_constant__ SurfMaps maps, const __grid_constant__ SurfGeom g,
                                                      const __grid_constant__ SurfBatch b, int capacity) {
   // sdet[l] holds pyramid layer l + 1 (the middle layers)
@@ -401,8 +404,10 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   __shared__ int s_ncand;
   __shared__ int s_dead[DET_LIST];  // candidate beaten by an outer-layer neighbour
   __shared__ unsigned s_claim[((SURF_MAX_LAYERS - 2) * (TH + 2) * (TW + 2) + 31) / 32];
+#if UVO_DET_SCREEN
   __shared__ unsigned short s_surv[(SURF_MAX_LAYERS - 2) * (TH + 2) * (TW + 2)];  // samples that pass the screen
   __shared__ int s_nsurv;
+#endif
   const SurfImage& im = b.im[blockIdx.y];
   int t = blockIdx.x, o = 0;
   while (o + 1 < g.n_octaves && t >= g.oct[o + 1].tile_begin) o++;
@@ -427,7 +432,9 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   };
   if (threadIdx.x == 0) {
     s_ncand = 0;
+#if UVO_DET_SCREEN
     s_nsurv = 0;
+#endif
   }
   if (threadIdx.x < (int)(sizeof(s_claim) / sizeof(unsigned))) s_claim[threadIdx.x] = 0;
   if (threadIdx.x < DET_LIST) s_dead[threadIdx.x] = 0;
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
   } else {
     __syncthreads();
   }
+#if UVO_DET_SCREEN
   // pass 1: screen every sample of the middle layers; survivors go to a list (warp-aggregated append)
   const int total = nmid * PLANE;
   for (int base = 0; base < total; base += blockDim.x) {
@@ -494,6 +502,21 @@ __global__ void __launch_bounds__(256, UVO_DET_MINB) k_surf_detect(const __grid_
     }
     sdet[l][y][x] = v;
   }
+#else
+  for (int idx = threadIdx.x; idx < nmid * PLANE; idx += blockDim.x) {
+    const int l = idx / PLANE, r = idx - l * PLANE, y = r / (TW + 2), x = r - y * (TW + 2);
+    const int i = ti0 + y - 1, j = tj0 + x - 1;
+    float v;
+    if (o == 0) {
+      if (l == 0) v = det_tile0<15, true>(s_tile, O.layer[1], i, j, y, x, g.thr);
+      else if (l == 1) v = det_tile0<21, true>(s_tile, O.layer[2], i, j, y, x, g.thr);
+      else v = det_tile0<27, true>(s_tile, O.layer[3], i, j, y, x, g.thr);
+    } else {
+      v = det_at<true>(im.sum, scols, O.layer[l + 1], step, i, j, g.thr);
+    }
+    sdet[l][y][x] = v;
+  }
+#endif
   __syncthreads();
   // local maxima among the middle layers.  A skipped neighbour is <= thr < val0, and DET_SKIPPED = -inf compares
   // exactly like that.  Every maximum goes to the list; what it still misses (exact values of skipped neighbours,
