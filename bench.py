@@ -45,7 +45,7 @@ CONFIGS = {
     "B": dict(w=1280, h=1024, n_distinct=8, ring=28,
               workload="stereo UVO 1280x1024, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML "
                        "(BASELINE config[1]); one independent sequence per GPU"),
-    "E": dict(w=2448, h=2048, n_distinct=4, ring=12,
+    "E": dict(w=2448, h=2048, n_distinct=4, ring=16,
               workload="stereo UVO 2448x2048, ~4k SURF features/image, solvePnPRansac(EPNP), shipped stereo YAML "
                        "(BASELINE config[4]); one independent sequence per GPU"),
 }
@@ -107,6 +107,29 @@ def aggregate_over_ranks(dist, ms_list, count_list, device):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
     return t.tolist(), v.tolist()
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """multi-GPU runs: keep this rank's threads -- and through first touch its pinned image ring -- on the NUMA node its
+    GPU hangs off (sysfs), so that N ranks do not pull their H2D traffic across the socket link.  Best effort: returns
+    a description, or None when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
 
 
 def sequence_seed(rank):
@@ -294,7 +317,7 @@ def kernel_models(P, n_kp, n3d, iters):
     f_score = 32.0  # PnP reprojection, flops per (hypothesis, correspondence)
     m = {
         # one launch covers both images of the pair (blockIdx.z = image)
-        "k_gray_undistort": ("hbm", 2 * 4.0 * P), "k_clahe_hist": ("hbm", 2 * 1.0 * P),
+        "k_gray_undistort": ("hbm", 2 * 4.0 * P), "k_clahe_tile_lut": ("hbm", 2 * 1.0 * P),
         "k_clahe_apply": ("hbm", 2 * 2.0 * P), "k_integral_rows": ("hbm", 2 * 5.0 * P),
         "k_integral_cols": ("hbm", 2 * 8.0 * P),
         "k_surf_detect": ("hbm", 2 * 16.0 * P), "k_surf_patch": ("hbm", 2 * n_kp * (40 * 40 + 256)),
@@ -322,6 +345,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         # NCCL is used for the barrier / MAX-over-ranks only; its debug output (the "NCCL version ..." banner at
         # NCCL_DEBUG=VERSION and above) goes to stdout by default: send it to stderr so that stdout carries the one
@@ -355,7 +379,7 @@ def run_gpu(args):
                   torch.from_numpy(seq.frames[pingpong(i, N_DISTINCT)][1]).pin_memory()) for i in range(RING)]
     torch.cuda.synchronize()
     dt_frame = 0.1
-    inflight = args.inflight
+    inflight = args.inflight if args.inflight > 0 else vo.lanes()
 
     def barrier():
         if world > 1:
@@ -416,8 +440,9 @@ def run_gpu(args):
 
     # ---- device-resident throughput (value): REGIONS consecutive regions of `steps` frames, the median is reported
     n_warm = max(args.warmup, 3)
-    run_frames(max(n_warm, 16), pos[0])  # >= 16: every lane has run a frame directly and captured its graphs
-    pos[0] += max(n_warm, 16)
+    n_roll = max(n_warm, 2 * vo.lanes() + 4)  # every lane has run a frame directly and captured its graphs
+    run_frames(n_roll, pos[0])
+    pos[0] += n_roll
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=clocks_sampler, args=(stop, samples, local), daemon=True)
     sampler.start()
@@ -431,7 +456,7 @@ def run_gpu(args):
     graph_launches = vo.graph_launches - graphs0
 
     # ---- end-to-end through the host-buffer call (e2e)
-    n_warm_host = max(args.warmup, 16)  # every staging slot of the library's ring is allocated and touched once
+    n_warm_host = max(args.warmup, vo.max_in_flight())  # every staging slot of the library's ring allocated and touched
     run_frames(n_warm_host, pos[0], host=True)
     pos[0] += n_warm_host
     host_regions, valid_host = [], 0
@@ -538,7 +563,7 @@ def run_gpu(args):
             run_compressed_gpu(n_long_c, 48 + 5 * n_comp)
             barrier()
             gpu_long_ms = (time.perf_counter() - t0) * 1e3
-            comp = {"gpu_region_ms": gpu_regions, "gpu_long": (n_long_c, gpu_long_ms), "gpu_entropy_frames": vo.gpu_entropy_frames,
+            comp = {"gpu_inflight": comp_inflight, "gpu_region_ms": gpu_regions, "gpu_long": (n_long_c, gpu_long_ms), "gpu_entropy_frames": vo.gpu_entropy_frames,
                     "gpu_host_enqueue_us": 1e6 * gpu_host_s[0] / max(gpu_host_s[1], 1),
                     "gpu_h2d_bytes_per_step": float(np.mean([len(a) + len(b) for a, b in enc])) + 2 * 9500.0,"region_ms": comp_regions, "frames_per_region": n_comp, "valid": comp_valid,
                     "h2d_bytes_per_step": comp_bytes / float(n_comp * len(comp_regions)),
@@ -690,13 +715,14 @@ def run_gpu(args):
                 # Huffman decoding on the GPU (k_jpeg_huff): one host thread, JPEG bytes in, scan bytes over PCIe
                 "gpu_entropy": {"value": comp["frames_per_region"] * world / (comp_gpu_ms * 1e-3), "unit": "frames/s",
                                 "h2d_bytes_per_step": comp["gpu_h2d_bytes_per_step"], "host_threads_per_gpu": 1,
-                                "frames_in_flight": max(inflight, 14),
+                                "frames_in_flight": comp["gpu_inflight"],
                                 "steady_state": {"frames": comp["gpu_long"][0],
                                                  "value": comp["gpu_long"][0] * world / (comp_gpu_long_ms * 1e-3)},
                                 "region_ms": comp["gpu_region_ms"], "frames_on_gpu_decoder": comp["gpu_entropy_frames"],
                                 "host_enqueue_us_per_frame": comp["gpu_host_enqueue_us"],
                                 "api": "uvo_stereo_enqueue_host_jpeg + uvo_stereo_collect"}},
             "host_enqueue_us_per_frame": 1e6 * host_enqueue_s[0] / max(host_enqueue_s[1], 1),
+            "host_affinity": affinity,
             # kernels the library launched inside the timed regions of `value` (graph-replayed kernels counted one by
             # one), per region of `steps` frames; host-side launch calls are graph launches + direct launches
             "gpu_launches": int(round(launches / float(args.regions))),
@@ -727,7 +753,7 @@ def main():
     ap.add_argument("--regions", type=int, default=REGIONS, help="consecutive timed regions of --steps frames (median)")
     ap.add_argument("--threshold", type=int, default=0, help="SURF min_hessian (0: bisect for ~4096 keypoints)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=8, help="frames kept in flight per sequence (<= the library's lanes)")
+    ap.add_argument("--inflight", type=int, default=0, help="frames kept in flight per sequence (0: the library's lanes)")
     ap.add_argument("--graphs", type=int, default=1, help="0: launch every kernel directly instead of replaying graphs")
     ap.add_argument("--jpeg-threads", type=int, default=8, help="host threads of the compressed-input leg (0: skip it)")
     args = ap.parse_args()

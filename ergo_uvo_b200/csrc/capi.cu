@@ -200,13 +200,12 @@ int uvo_get_image(uvo_ctx* ctx, const uint8_t* src3, int w, int h, size_t spitch
     const size_t gp = ((size_t)w + 3) & ~(size_t)3;
     s.src3.ensure(spitch * h);
     s.gray.ensure(gp * h);
-    s.hist.ensure(64 * 256);
     s.lut.ensure(64 * 256);
     UVO_CUDA(cudaMemcpyAsync(s.src3.get(), src3, spitch * h, cudaMemcpyHostToDevice, c.stream));
     launch_gray_undistort(c, s.src3.get(), spitch, w, h, make_undistort_params(*cam), s.gray.get(), gp);
     if (clahe) {
       ClaheGeom g = make_clahe_geom(w, h, (double)clip_limit, 8, 8);
-      launch_clahe(c, s.gray.get(), gp, w, h, g, s.hist.get(), s.lut.get(), s.gray.get(), gp);
+      launch_clahe(c, s.gray.get(), gp, w, h, g, s.lut.get(), s.gray.get(), gp);
     }
     UVO_CUDA(cudaMemcpy2DAsync(dst, dpitch, s.gray.get(), gp, w, h, cudaMemcpyDeviceToHost, c.stream));
     UVO_CUDA(cudaStreamSynchronize(c.stream));
@@ -273,14 +272,13 @@ int uvo_get_image_resized(uvo_ctx* ctx, const uint8_t* src3, int w, int h, size_
     s.bytes_b.ensure(rp * dh);
     s.bytes_d.ensure(sizeof(AreaCell) * (size_t)(dw + dh));
     s.gray.ensure(gp * dh);
-    s.hist.ensure(64 * 256);
     s.lut.ensure(64 * 256);
     UVO_CUDA(cudaMemcpyAsync(s.src3.get(), src3, spitch * h, cudaMemcpyHostToDevice, c.stream));
     launch_resize_area(c, s.src3.get(), spitch, w, h, 3, s.bytes_b.get(), rp, dw, dh, (AreaCell*)s.bytes_d.get());
     launch_gray_undistort(c, s.bytes_b.get(), rp, dw, dh, make_undistort_params(*cam), s.gray.get(), gp);
     if (clahe) {
       ClaheGeom g = make_clahe_geom(dw, dh, (double)clip_limit, 8, 8);
-      launch_clahe(c, s.gray.get(), gp, dw, dh, g, s.hist.get(), s.lut.get(), s.gray.get(), gp);
+      launch_clahe(c, s.gray.get(), gp, dw, dh, g, s.lut.get(), s.gray.get(), gp);
     }
     UVO_CUDA(cudaMemcpy2DAsync(dst, dpitch, s.gray.get(), gp, dw, dh, cudaMemcpyDeviceToHost, c.stream));
     UVO_CUDA(cudaStreamSynchronize(c.stream));

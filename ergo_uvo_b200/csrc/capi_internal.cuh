@@ -9,7 +9,6 @@ namespace uvo {
 
 struct StageScratch {
   DevBuf<uint8_t> src3, gray, lut;
-  DevBuf<unsigned int> hist;
   DevBuf<int32_t> integral;
   DevBuf<uint8_t> bytes_a, bytes_b, bytes_c, bytes_d, bytes_e;  // generic staging for the other stage calls
 };

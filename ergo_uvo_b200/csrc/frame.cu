@@ -198,11 +198,14 @@ struct Lane {
   }
 };
 
+#ifndef UVO_STEREO_LANES
+#define UVO_STEREO_LANES 12  // frames whose kernels may be on the GPU at once (one stream + one set of buffers each)
+#endif
 #ifndef UVO_STEREO_RING
-#define UVO_STEREO_RING 16  // result slots = frames that may be enqueued and not yet collected
+#define UVO_STEREO_RING (2 * UVO_STEREO_LANES)  // result slots = frames that may be enqueued and not yet collected
 #endif
 struct uvo_stereo {
-  static constexpr int N_LANES = 8;
+  static constexpr int N_LANES = UVO_STEREO_LANES;
   static constexpr int RING = UVO_STEREO_RING;
   uvo_ctx* ctx = nullptr;
   int w = 0, h = 0, cap = 0;
@@ -888,6 +891,7 @@ int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3, const uint8_t* right3,
 }
 
 int uvo_stereo_max_in_flight(void) { return uvo_stereo::RING; }
+int uvo_stereo_lanes(void) { return uvo_stereo::N_LANES; }
 
 int uvo_stereo_set_graphs(uvo_stereo* s, int enable) {
   if (!s) return UVO_ERR_INVALID;

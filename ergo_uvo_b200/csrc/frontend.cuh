@@ -25,7 +25,6 @@ struct FrontEnd {
   DevBuf<uint8_t> patch[2];
   DevBuf<int> counters;  // 4 ints per image
   DevBuf<int> rank[2];
-  DevBuf<unsigned int> hist;
   DevBuf<uint8_t> lut;
   DevBuf<uvo_keypoint> tmp_kps;
   DevBuf<float> tmp_desc;
@@ -53,7 +52,6 @@ struct FrontEnd {
       patch[i].ensure((size_t)capacity * 448);
     }
     counters.ensure(8);
-    hist.ensure(2 * 64 * 256);
     lut.ensure(2 * 64 * 256);
     if (maps_for[0] != sum[0].get() || maps_for[1] != sum[n_img > 1 ? 1 : 0].get() || maps_w != w || maps_h != h) {
       maps_w = w;
@@ -87,7 +85,7 @@ struct FrontEnd {
     launch_gray_undistort(c, d_src3, spitch, w, h, make_undistort_params(cam), gray[idx].get(), gpitch);
     if (clahe) {
       ClaheGeom g = make_clahe_geom(w, h, (double)clip_limit, 8, 8);
-      launch_clahe(c, gray[idx].get(), gpitch, w, h, g, hist.get() + idx * 64 * 256, lut.get() + idx * 64 * 256,
+      launch_clahe(c, gray[idx].get(), gpitch, w, h, g, lut.get() + idx * 64 * 256,
                    gray[idx].get(), gpitch);
     }
   }
@@ -99,8 +97,8 @@ struct FrontEnd {
     const UndistortParams P[2] = {make_undistort_params(camL), make_undistort_params(camR)};
     uint8_t* g2[2] = {gray[0].get(), gray[1].get()};
     int32_t* s2[2] = {sum[0].get(), sum[1].get()};
-    launch_prep_pair(c, src, spitch, w, h, P, clahe, make_clahe_geom(w, h, (double)clip_limit, 8, 8), hist.get(),
-                     lut.get(), g2, gpitch, s2, part, sum_pitch);
+    launch_prep_pair(c, src, spitch, w, h, P, clahe, make_clahe_geom(w, h, (double)clip_limit, 8, 8), lut.get(),
+                     g2, gpitch, s2, part, sum_pitch);
   }
 
   // integral image of slot `idx` (the first step of SURF::detectAndCompute)

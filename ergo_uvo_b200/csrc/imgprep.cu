@@ -153,39 +153,63 @@ __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
-// grid: (tiles_x*tiles_y, slices).  Each block histograms a horizontal slice of one tile in shared memory and
-// merges it into the tile's global histogram with 256 atomics.
-__global__ void __launch_bounds__(256) k_clahe_hist(const uint8_t* img0, const uint8_t* img1,
-                                                    size_t pitch, int w, int h, ClaheGeom g,
-                                                    unsigned int* __restrict__ hist) {
-  __shared__ unsigned int sh[256];
-  const uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
-  hist += (size_t)blockIdx.z * g.tiles_x * g.tiles_y * 256;  // the pair's histograms (and LUTs) are contiguous
-  sh[threadIdx.x] = 0;
-  __syncthreads();
-  const int tile = blockIdx.x, txi = tile % g.tiles_x, tyi = tile / g.tiles_x;
-  const int rows_per = div_up_dev(g.th, gridDim.y);
-  const int y0 = tyi * g.th + blockIdx.y * rows_per, y1 = min(y0 + rows_per, (tyi + 1) * g.th);
-  const int x0 = txi * g.tw;
-  const int npx = (y1 - y0) * g.tw;
-  for (int t = threadIdx.x; t < npx; t += blockDim.x) {
-    int y = y0 + t / g.tw, x = x0 + t % g.tw;
-    if (y >= h) y = reflect101(y, h);
-    if (x >= w) x = reflect101(x, w);
-    atomicAdd(&sh[img[(size_t)y * pitch + x]], 1u);
-  }
-  __syncthreads();
-  unsigned int v = sh[threadIdx.x];
-  if (v) atomicAdd(&hist[tile * 256 + threadIdx.x], v);
-}
-
-// one block (256 threads) per tile: clip, redistribute, cumulative sum, LUT (OpenCV clahe.cpp CLAHE_CalcLut_Body)
-__global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restrict__ hist, ClaheGeom g,
-                                                   uint8_t* __restrict__ lut) {
+// One block per (tile, image): histogram of the tile in shared memory (four sub-histograms, one aligned 32-bit load
+// per four pixels), then clip, redistribute, cumulative sum and the LUT (OpenCV clahe.cpp CLAHE_CalcLut_Body) in the
+// same block -- no global histogram, no atomics to global memory, no separate LUT launch.  Pixels right of / below the
+// image (tile sizes that do not divide it) are BORDER_REFLECT_101 copies, as copyMakeBorder provides them.
+constexpr int CLAHE_HIST_THREADS = 1024, CLAHE_HIST_UN = 5;
+__global__ void __launch_bounds__(CLAHE_HIST_THREADS) k_clahe_tile_lut(const uint8_t* img0, const uint8_t* img1,
+                                                                       size_t pitch, int w, int h, ClaheGeom g,
+                                                                       uint8_t* __restrict__ lut) {
+  __shared__ unsigned int sh[4][256];
   __shared__ int warp_sums[8];
   __shared__ int s_total;
-  const int tile = blockIdx.x, b = threadIdx.x, lane = b & 31, wid = b >> 5;
-  int v = (int)hist[tile * 256 + b];
+  const uint8_t* __restrict__ img = blockIdx.z ? img1 : img0;
+  lut += (size_t)blockIdx.z * g.tiles_x * g.tiles_y * 256;  // the pair's LUTs are contiguous
+  const int b = threadIdx.x, lane = b & 31, wid = b >> 5;
+  sh[b >> 8][b & 255] = 0;
+  __syncthreads();
+  const int tile = blockIdx.x, txi = tile % g.tiles_x, tyi = tile / g.tiles_x;
+  const int x0 = txi * g.tw, y0 = tyi * g.th;
+  unsigned int* mine = sh[wid & 3];
+  const bool words = x0 + g.tw <= w && y0 + g.th <= h && ((g.tw | x0) & 3) == 0 && (pitch & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+  if (words) {
+    // batches of CLAHE_HIST_UN words per thread, all loads of a batch in flight before the first atomic
+    const int wpr = g.tw >> 2, nw = wpr * g.th;
+    for (int t0 = 0; t0 < nw; t0 += CLAHE_HIST_THREADS * CLAHE_HIST_UN) {
+      unsigned v[CLAHE_HIST_UN];
+      bool in[CLAHE_HIST_UN];
+#pragma unroll
+      for (int u = 0; u < CLAHE_HIST_UN; u++) {
+        const int t = t0 + u * CLAHE_HIST_THREADS + b;
+        in[u] = t < nw;
+        const int y = t / wpr, xw = t - y * wpr;
+        v[u] = in[u] ? __ldg(reinterpret_cast<const unsigned*>(img + (size_t)(y0 + y) * pitch + x0) + xw) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < CLAHE_HIST_UN; u++) {
+        if (!in[u]) continue;
+        atomicAdd(&mine[v[u] & 255u], 1u);
+        atomicAdd(&mine[(v[u] >> 8) & 255u], 1u);
+        atomicAdd(&mine[(v[u] >> 16) & 255u], 1u);
+        atomicAdd(&mine[v[u] >> 24], 1u);
+      }
+    }
+  } else {
+    const int npx = g.tw * g.th;
+    for (int t = b; t < npx; t += blockDim.x) {
+      int y = y0 + t / g.tw, x = x0 + t % g.tw;
+      if (y >= h) y = reflect101(y, h);
+      if (x >= w) x = reflect101(x, w);
+      atomicAdd(&mine[img[(size_t)y * pitch + x]], 1u);
+    }
+  }
+  __syncthreads();
+  if (b >= 256) return;
+  // the LUT on the first 256 threads (8 warps); their barriers are named and counted, the other warps are gone
+  auto sync256 = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  int v = (int)(sh[0][b] + sh[1][b] + sh[2][b] + sh[3][b]);
   if (g.clip > 0) {
     int excess = v > g.clip ? v - g.clip : 0;
     if (v > g.clip) v = g.clip;
@@ -193,13 +217,13 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restric
 #pragma unroll
     for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if (lane == 0) warp_sums[wid] = e;
-    __syncthreads();
+    sync256();
     if (b == 0) {
       int t = 0;
       for (int k = 0; k < 8; k++) t += warp_sums[k];
       s_total = t;
     }
-    __syncthreads();
+    sync256();
     const int clipped = s_total;
     const int batch = clipped / 256, residual = clipped - batch * 256;
     v += batch;
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restric
       const int step = max(256 / residual, 1);
       if (b % step == 0 && b / step < residual) v += 1;
     }
-    __syncthreads();
+    sync256();
   }
   // inclusive scan over the 256 bins
   int s = v;
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const unsigned int* __restric
     if (lane >= o) s += t;
   }
   if (lane == 31) warp_sums[wid] = s;
-  __syncthreads();
+  sync256();
   int base = 0;
   for (int k = 0; k < wid; k++) base += warp_sums[k];
   s += base;
@@ -301,16 +325,11 @@ ClaheGeom make_clahe_geom(int w, int h, double clip_limit, int tiles_x, int tile
   return g;
 }
 
-void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g,
-                  unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_dst, size_t dpitch) {
+void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, uint8_t* d_lut,
+                  uint8_t* d_dst, size_t dpitch) {
   const int tiles = g.tiles_x * g.tiles_y;
-  UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles, c.stream));
-  int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
-  UVO_KERNEL(c, "k_clahe_hist");
-  k_clahe_hist<<<dim3(tiles, slices), 256, 0, c.stream>>>(d_src, d_src, spitch, w, h, g, d_hist);
-  UVO_LAUNCH_CHECK(c);
-  UVO_KERNEL(c, "k_clahe_lut");
-  k_clahe_lut<<<tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);
+  UVO_KERNEL(c, "k_clahe_tile_lut");
+  k_clahe_tile_lut<<<tiles, CLAHE_HIST_THREADS, 0, c.stream>>>(d_src, d_src, spitch, w, h, g, d_lut);
   UVO_LAUNCH_CHECK(c);
   dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8));
   UVO_KERNEL(c, "k_clahe_apply");
@@ -320,7 +339,10 @@ void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, con
 
 // ------------------------------------------------------------------------------------------------ K3 integral
 // Pass 1: one warp per image row; inclusive prefix along the row, written to sum[(i+1)][1..w]; also zeroes column 0
-// and (warp 0) row 0.  Pass 2: column prefix in place, each block owns 32 columns x 32 row segments.
+// and (warp 0) row 0.  The row is taken in batches of INT_UN x 128 pixels whose loads are all issued before the first
+// scan (a warp is alone with its row: what it waits for is the load latency, once per batch instead of once per 128 px).
+// Pass 2: column prefix in place, each block owns INT_CW columns x (1024 / INT_CW) row segments.
+constexpr int INT_UN = 5;
 __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* img0, const uint8_t* img1,
                                                        size_t pitch, int w, int h, int32_t* sum0,
                                                        int32_t* sum1, int sw) {
@@ -334,51 +356,98 @@ __global__ void __launch_bounds__(256) k_integral_rows(const uint8_t* img0, cons
   const uint8_t* row = img + (size_t)warp * pitch;
   int32_t* out = sum + (size_t)(warp + 1) * sw;
   if (lane == 0) out[0] = 0;
+  const bool aligned = (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
   int carry = 0;
-  for (int base = 0; base < w; base += 128) {
-    const int j = base + lane * 4;
-    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    if (j + 3 < w && (pitch & 3) == 0) {
-      uchar4 q = *reinterpret_cast<const uchar4*>(row + j);
-      v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
-    } else {
-      if (j < w) v0 = row[j];
-      if (j + 1 < w) v1 = row[j + 1];
-      if (j + 2 < w) v2 = row[j + 2];
-      if (j + 3 < w) v3 = row[j + 3];
-    }
-    v1 += v0; v2 += v1; v3 += v2;
-    int s = v3;
+  for (int base0 = 0; base0 < w; base0 += 128 * INT_UN) {
+    unsigned q[INT_UN];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
+    for (int u = 0; u < INT_UN; u++) {
+      const int j = base0 + 128 * u + lane * 4;
+      unsigned v = 0;
+      if (j + 3 < w && aligned) {
+        v = __ldg(reinterpret_cast<const unsigned*>(row + j));
+      } else {
+        if (j < w) v |= row[j];
+        if (j + 1 < w) v |= (unsigned)row[j + 1] << 8;
+        if (j + 2 < w) v |= (unsigned)row[j + 2] << 16;
+        if (j + 3 < w) v |= (unsigned)row[j + 3] << 24;
+      }
+      q[u] = v;
     }
-    const int excl = s - v3 + carry;
-    if (j < w) out[j + 1] = v0 + excl;
-    if (j + 1 < w) out[j + 2] = v1 + excl;
-    if (j + 2 < w) out[j + 3] = v2 + excl;
-    if (j + 3 < w) out[j + 4] = v3 + excl;
-    carry += __shfl_sync(0xffffffffu, s, 31);
+#pragma unroll
+    for (int u = 0; u < INT_UN; u++) {
+      const int j = base0 + 128 * u + lane * 4;
+      if (base0 + 128 * u >= w) break;  // warp-uniform
+      int v0 = q[u] & 255u, v1 = (q[u] >> 8) & 255u, v2 = (q[u] >> 16) & 255u, v3 = q[u] >> 24;
+      v1 += v0; v2 += v1; v3 += v2;
+      int s = v3;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+      }
+      const int excl = s - v3 + carry;
+      if (j < w) out[j + 1] = v0 + excl;
+      if (j + 1 < w) out[j + 2] = v1 + excl;
+      if (j + 2 < w) out[j + 3] = v2 + excl;
+      if (j + 3 < w) out[j + 4] = v3 + excl;
+      carry += __shfl_sync(0xffffffffu, s, 31);
+    }
   }
 }
 
-// block = 32 (columns) x 32 (row segments).  Segment totals -> exclusive scan in smem -> second sweep adds.
-__global__ void __launch_bounds__(1024) k_integral_cols(int32_t* sum0, int32_t* sum1, int w,
+// block = INT_CW (columns) x INT_SEG (row segments).  Segment totals -> exclusive scan over the segments of each
+// column (one warp per column) -> second sweep adds.  Block shape measured on the stereo pair (tools/pair_probe.py):
+// 16 x 64 is the fastest kernel run alone (17 us against 22 for 32 x 32) but 32 x 32 -- 80 blocks, half the SMs left
+// to the kernels of the other frames in flight -- gives the highest frame rate, which is what counts.
+#ifndef UVO_INT_CW
+#define UVO_INT_CW 32
+#endif
+#ifndef UVO_INT_SEG
+#define UVO_INT_SEG 32
+#endif
+constexpr int INT_CW = UVO_INT_CW, INT_SEG = UVO_INT_SEG;
+static_assert(INT_CW * INT_SEG <= 1024 && INT_CW * 32 <= INT_CW * INT_SEG && INT_SEG % 32 == 0,
+              "column scan: one warp per column, whole words of segments per lane");
+__global__ void __launch_bounds__(INT_CW* INT_SEG) k_integral_cols(int32_t* sum0, int32_t* sum1, int w,
                                                         int h, int sw) {
-  __shared__ int32_t tot[32][33];
+  __shared__ int32_t tot[INT_SEG][INT_CW + 1];
   int32_t* __restrict__ sum = blockIdx.z ? sum1 : sum0;
-  const int col = 1 + blockIdx.x * 32 + threadIdx.x;
+  const int col = 1 + blockIdx.x * INT_CW + threadIdx.x;
   const int seg = threadIdx.y;
-  const int rows_per = (h + 31) / 32;
-  const int r0 = 1 + seg * rows_per, r1 = min(r0 + rows_per, h + 1);
+  const int rows_per = (h + INT_SEG - 1) / INT_SEG;
+  const int r0 = min(1 + seg * rows_per, h + 1), r1 = min(r0 + rows_per, h + 1);
   int32_t acc = 0;
   if (col < w + 1)
     for (int r = r0; r < r1; r++) acc += sum[(size_t)r * sw + col];
   tot[seg][threadIdx.x] = acc;
   __syncthreads();
-  int32_t run = 0;
-  for (int k = 0; k < seg; k++) run += tot[k][threadIdx.x];
+  {  // exclusive scan of tot[.][c] over the segments: warp c takes column c, INT_SEG / 32 consecutive segments per lane
+    const int t = threadIdx.y * INT_CW + threadIdx.x, c = t >> 5, lane = t & 31;
+    if (c < INT_CW) {
+      constexpr int PER = INT_SEG / 32;
+      int32_t loc[PER], run = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        loc[k] = tot[lane * PER + k][c];
+        run += loc[k];
+      }
+      int32_t s = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t x = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += x;
+      }
+      int32_t e = s - run;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        tot[lane * PER + k][c] = e;
+        e += loc[k];
+      }
+    }
+  }
+  __syncthreads();
+  int32_t run = tot[seg][threadIdx.x];
   if (col < w + 1)
     for (int r = r0; r < r1; r++) {
       run += sum[(size_t)r * sw + col];
@@ -394,14 +463,14 @@ void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, i
                                                                                       d_sum, sw);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
-  k_integral_cols<<<div_up(w, 32), dim3(32, 32), 0, c.stream>>>(d_sum, d_sum, w, h, sw);
+  k_integral_cols<<<div_up(w, INT_CW), dim3(INT_CW, INT_SEG), 0, c.stream>>>(d_sum, d_sum, w, h, sw);
   UVO_LAUNCH_CHECK(c);
 }
 
 // K1-K3 for both images of a stereo pair in one launch per kernel (blockIdx.z = image): half the launches, and the
-// narrow kernels (histograms, LUTs, the two scan passes) get twice the blocks.  d_hist / d_lut: 2 * tiles * 256.
+// narrow kernels (tile histograms + LUTs, the two scan passes) get twice the blocks.  d_lut: 2 * tiles * 256.
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
-                      const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
+                      const ClaheGeom& g, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
                       int32_t* d_sum[2], int part, int sum_pitch) {
   if (part & PREP_PART_SOURCE) {
     dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
@@ -413,13 +482,8 @@ void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, in
   if (!(part & PREP_PART_REST)) return;
   if (clahe) {
     const int tiles = g.tiles_x * g.tiles_y;
-    UVO_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 256 * tiles * 2, c.stream));
-    int slices = max(1, min(g.th, (4 * c.sm_count) / tiles));
-    UVO_KERNEL(c, "k_clahe_hist");
-    k_clahe_hist<<<dim3(tiles, slices, 2), 256, 0, c.stream>>>(d_gray[0], d_gray[1], gpitch, w, h, g, d_hist);
-    UVO_LAUNCH_CHECK(c);
-    UVO_KERNEL(c, "k_clahe_lut");
-    k_clahe_lut<<<2 * tiles, 256, 0, c.stream>>>(d_hist, g, d_lut);  // tile index runs over both images
+    UVO_KERNEL(c, "k_clahe_tile_lut");
+    k_clahe_tile_lut<<<dim3(tiles, 1, 2), CLAHE_HIST_THREADS, 0, c.stream>>>(d_gray[0], d_gray[1], gpitch, w, h, g, d_lut);
     UVO_LAUNCH_CHECK(c);
     dim3 block(32, 8), grid(div_up(div_up(w, 4), 32), div_up(h, 8), 2);
     UVO_KERNEL(c, "k_clahe_apply");
@@ -434,7 +498,7 @@ void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, in
       d_gray[0], d_gray[1], gpitch, w, h, d_sum[0], d_sum[1], sw);
   UVO_LAUNCH_CHECK(c);
   UVO_KERNEL(c, "k_integral_cols");
-  k_integral_cols<<<dim3(div_up(w, 32), 1, 2), dim3(32, 32), 0, c.stream>>>(d_sum[0], d_sum[1], w, h, sw);
+  k_integral_cols<<<dim3(div_up(w, INT_CW), 1, 2), dim3(INT_CW, INT_SEG), 0, c.stream>>>(d_sum[0], d_sum[1], w, h, sw);
   UVO_LAUNCH_CHECK(c);
 }
 

@@ -24,9 +24,9 @@ void launch_gray_undistort(Ctx& c, const uint8_t* d_src3, size_t spitch, int w, 
                            uint8_t* d_dst, size_t dpitch);
 // cvtColor(COLOR_BayerBGGR2BGR): 1-channel bayer (w, h >= 3) -> 3-channel interleaved BGR
 void launch_demosaic_bggr(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, uint8_t* d_dst3, size_t dpitch);
-// d_hist: tiles*256 u32 scratch, d_lut: tiles*256 u8 scratch; src and dst may alias
-void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, unsigned int* d_hist,
-                  uint8_t* d_lut, uint8_t* d_dst, size_t dpitch);
+// d_lut: tiles*256 u8 scratch; src and dst may alias
+void launch_clahe(Ctx& c, const uint8_t* d_src, size_t spitch, int w, int h, const ClaheGeom& g, uint8_t* d_lut,
+                  uint8_t* d_dst, size_t dpitch);
 // K0: cv::resize(src, dst, Size(dw, dh), 0, 0, INTER_AREA) for interleaved u8 images with `cn` channels (the
 // pre-scaling branch of get_image, reference VO_utility.cpp:362-363).  d_tab: (dw + dh) AreaCell scratch.
 struct AreaCell {  // one destination index of computeResizeAreaTab: optional left partial cell, full cells
@@ -41,7 +41,7 @@ void launch_resize_area(Ctx& c, const uint8_t* d_src, size_t spitch, int sw, int
 // rest can be launched separately, so that the rest can live in a CUDA graph
 enum { PREP_PART_SOURCE = 1, PREP_PART_REST = 2 };
 void launch_prep_pair(Ctx& c, const uint8_t* d_src3[2], size_t spitch, int w, int h, const UndistortParams P[2], int clahe,
-                      const ClaheGeom& g, unsigned int* d_hist, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
+                      const ClaheGeom& g, uint8_t* d_lut, uint8_t* d_gray[2], size_t gpitch,
                       int32_t* d_sum[2], int part = PREP_PART_SOURCE | PREP_PART_REST, int sum_pitch = 0);
 // d_sum: (h+1) rows of sum_pitch int32 (w+1 used; sum_pitch = 0: dense, pitch w+1)
 void launch_integral(Ctx& c, const uint8_t* d_img, size_t pitch, int w, int h, int32_t* d_sum, int sum_pitch = 0);

@@ -586,6 +586,9 @@ class StereoVO:
     def max_in_flight(self):
         return int(self.lib.uvo_stereo_max_in_flight())
 
+    def lanes(self):
+        return int(self.lib.uvo_stereo_lanes())
+
     def set_graphs(self, enable):
         """replay each lane's fixed kernel runs as CUDA graphs (default) or launch every kernel directly"""
         self.ctx._ck(self.lib.uvo_stereo_set_graphs(self.h, int(bool(enable))))

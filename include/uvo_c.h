@@ -358,8 +358,8 @@ UVO_API int uvo_stereo_frame(uvo_stereo* s, const uint8_t* left3_host, const uin
 UVO_API int uvo_stereo_frame_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
                                     size_t pitch, double dt, uvo_stereo_result* out);
 /* Asynchronous calls: enqueue a frame without waiting; results are collected in order.  Consecutive frames run on
- * separate CUDA streams inside the library (the front end of frame t+1 does not depend on frame t), so keeping 2-4
- * frames in flight is what fills the GPU; at most uvo_stereo_max_in_flight() frames may be pending.
+ * separate CUDA streams inside the library (the front end of frame t+1 does not depend on frame t), so keeping
+ * uvo_stereo_lanes() frames in flight is what fills the GPU; at most uvo_stereo_max_in_flight() frames may be pending.
  * _host: images in host memory (pinned for a truly asynchronous copy); the H2D copies are part of the enqueued work and
  * the buffers may be reused once the frame has been collected. */
 UVO_API int uvo_stereo_enqueue_device(uvo_stereo* s, const uint8_t* left3_dev, const uint8_t* right3_dev,
@@ -371,6 +371,9 @@ UVO_API int uvo_stereo_enqueue_host(uvo_stereo* s, const uint8_t* left3_host, co
 UVO_API int uvo_stereo_enqueue_host_bayer(uvo_stereo* s, const uint8_t* left1_host, const uint8_t* right1_host,
                                           size_t pitch, double dt);
 UVO_API int uvo_stereo_max_in_flight(void);
+/* number of lanes: frames whose kernels can be on the GPU at the same time (frames enqueued beyond that wait for a lane;
+ * keeping this many in flight gives the highest frame rate) */
+UVO_API int uvo_stereo_lanes(void);
 /* COMPRESSED input (the step before the path: the node receives sensor_msgs::CompressedImage and from_ros_to_cv_image
  * decodes it, math_utility.cpp:154-173).  The frame travels to the GPU as entropy-decoded sparse coefficients (about
  * a quarter of the raw image's bytes); IDCT, chroma upsampling and colour conversion (or, with bayer_bggr, the demosaic

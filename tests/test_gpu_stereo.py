@@ -165,8 +165,8 @@ def test_stereo_host_async_pipeline_matches_sync(ctx, small_stereo):
     library) returns exactly the records of the one-frame-at-a-time synchronous call, over more frames than lanes"""
     import torch
     seq = small_stereo
-    order = [k % len(seq.frames) for k in range(11)]
     vo, p = _make(ctx, seq, 3000)
+    order = [k % len(seq.frames) for k in range(vo.lanes() + 3)]
     sync = [vo.frame(*seq.frames[k], 0.1) for k in order]
     vo.close()
     vo, p = _make(ctx, seq, 3000)
@@ -217,13 +217,14 @@ def test_bayer_input_equals_demosaiced_input(ctx, oracle, small_stereo):
 
 
 def test_stereo_graph_replay_matches_direct_launches(ctx, small_stereo):
-    """the asynchronous path replays each lane's kernel runs as CUDA graphs from the lane's second frame on: 40 frames
-    (five per lane: direct, capture + launch, three replays) give byte-identical result records and identical
+    """the asynchronous path replays each lane's kernel runs as CUDA graphs from the lane's second frame on: five
+    frames per lane (direct, capture + launch, three replays) give byte-identical result records and identical
     intermediate products to the synchronous one-frame-at-a-time path, which launches every kernel directly"""
     import torch
     seq = small_stereo
-    order = [k % len(seq.frames) for k in range(40)]
     vo, p = _make(ctx, seq, 3000)
+    lanes = vo.lanes()
+    order = [k % len(seq.frames) for k in range(5 * lanes)]
     sync = [vo.frame(*seq.frames[k], 0.1) for k in order]
     taps = (vo.last_keypoints(False), vo.last_keypoints(True), vo.last_matches(False), vo.last_matches(True),
             vo.last_inliers())
@@ -239,7 +240,7 @@ def test_stereo_graph_replay_matches_direct_launches(ctx, small_stereo):
             L, R = pinned[k]
             vo.enqueue_host(L.data_ptr(), R.data_ptr(), 3 * seq.w, 0.1)
             q += 1
-            if q >= 8:
+            if q >= lanes:
                 got.append(vo.collect())
                 q -= 1
         while q:
@@ -252,7 +253,7 @@ def test_stereo_graph_replay_matches_direct_launches(ctx, small_stereo):
         return got, t, n
 
     got, t, n = run(True)
-    assert n == 3 * (len(order) - 8)       # three graph launches per frame after each of the 8 lanes' first frame
+    assert n == 3 * (len(order) - lanes)   # three graph launches per frame after each lane's first frame
     assert any(r.valid for r in got)
     for a, b in zip(got, sync):
         assert bytes(a) == bytes(b)

@@ -1,4 +1,4 @@
-"""Event-timed SURF kernels of one 1280x1024 stereo pair's left image at the bench threshold (A/B of kernel variants:
+"""Event-timed image-preparation and SURF kernels of one 1280x1024 stereo pair's left image at the bench threshold (A/B of kernel variants:
 rebuild with `make -C ergo_uvo_b200/csrc EXTRA=-D...`, run this).  Prints one JSON line."""
 import json
 import os
@@ -20,6 +20,7 @@ def main():
         ctx.detect_features(g)
     ctx.kernel_timing(True)
     for _ in range(20):
+        ctx.get_image(seq.frames[0][0], seq.KL, seq.DL, seq.newKL)
         ctx.detect_features(g)
     rep = ctx.kernel_report()
     print(json.dumps({"keypoints": len(k), "us_per_launch": {n: round(1e3 * ms / c, 2) for n, (c, ms) in sorted(rep.items())}}))
