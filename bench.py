@@ -274,6 +274,16 @@ def default_params_cpu(thr):
     return p
 
 
+def config_dict(cfg, name, thr):
+    """the `config` object of both arms (identical for the same --config and threshold, so that the driver can tell the
+    two lines describe the same workload); what is specific to a run is in `run`"""
+    P = cfg["w"] * cfg["h"]
+    return {"workload": cfg["workload"], "name": name, "width": cfg["w"], "height": cfg["h"], "surf_min_hessian": thr,
+            "l2": f"GPU arm: inputs larger than L2 -- a ring of {cfg['ring']} device-resident stereo pairs "
+                  f"({cfg['ring'] * 2 * 3 * P / 1e6:.0f} MB), each read once per {cfg['ring']} frames; "
+                  "CPU arm: consecutive frames of the same sequence from host memory"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -291,7 +301,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spf * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
         "data": "synthetic",
-        "config": {"workload": cfg["workload"], "width": cfg["w"], "height": cfg["h"], "surf_min_hessian": thr},
+        "config": config_dict(cfg, args.config, thr),
         # one CPU process runs ONE sequence whatever --gpus says (the contract: rank 0 alone runs the reference arm);
         # a ratio against an N-GPU line compares N sequences with this one
         "n_sequences": 1,
@@ -683,11 +693,9 @@ def run_gpu(args):
             "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32/f64",
             "data": "synthetic",
-            "config": {"workload": cfg["workload"], "name": args.config,
-                       "width": W, "height": H, "surf_min_hessian": thr, "keypoints_per_image": n_kp,
-                       "sequences_per_gpu": 1, "frames_in_flight": inflight, "cuda_graphs": bool(args.graphs),
-                       "l2": f"inputs larger than L2: ring of {RING} device-resident stereo pairs "
-                             f"({RING * 2 * 3 * P / 1e6:.0f} MB), each read once per {RING} frames"},
+            "config": config_dict(cfg, args.config, thr),
+            "run": {"keypoints_per_image": n_kp, "sequences_per_gpu": 1, "frames_in_flight": inflight,
+                    "cuda_graphs": bool(args.graphs)},
             "n_sequences": world,
             # every number above is the MEDIAN of `regions` consecutive timed regions of exactly `steps` frames, each
             # bracketed by barrier + synchronize (max over ranks per region); a 20-frame region is 7 ms long against a
@@ -761,7 +769,7 @@ def main():
     if args.impl == "reference":
         if args.steps > 20:
             args.steps = 20  # bounded sample: ~2 s of CPU work per frame
-        args.warmup = min(args.warmup, 1)
+        args.warmup = min(args.warmup, 5)
         return run_reference(args)
     return run_gpu(args)
 
