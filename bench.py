@@ -670,6 +670,11 @@ def run_gpu(args):
         # the dominant kernel: top by time per frame over ALL kernels (each timed running alone)
         top_overall = max(kern.items(), key=lambda kv: kv[1]["ms_per_frame"])[0] if kern else None
         roof = roof_of(top_overall, kern[top_overall]) if top_overall else None
+        # beside it, the top WIDE kernel: the pose kernels that lead by duration run on 1-32 blocks and overlap the other
+        # frames in flight; the kernel that leads among those whose grid fills the chip is what bounds the frame rate
+        wide = {n: kt for n, kt in kern.items() if n in algo and algo[n][0] != "fp64"}
+        top_wide = max(wide.items(), key=lambda kv: kv[1]["ms_per_frame"])[0] if wide else None
+        roof_wide = roof_of(top_wide, kern[top_wide]) if top_wide else None
         rooflines = {}
         for name, kt in kern.items():
             r = roof_of(name, kt)
@@ -738,7 +743,8 @@ def run_gpu(args):
             "graph_launches_per_frame": graph_launches / float(frames_timed),
             "valid_frames": {"device": int(v[0]), "host": int(v[1]), "of": frames_timed * world},
             "clocks": summarise_clocks(samples),
-            "roofline": roof, "rooflines_all": rooflines, "top_kernel_by_time": top_overall, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_top_wide_kernel": roof_wide, "rooflines_all": rooflines,
+            "top_kernel_by_time": top_overall, "cpu_baseline": cpu,
             "fp64_peak_tflops": f64_peak,
             "stage_ms": stage, "kernels": kern,
         }
