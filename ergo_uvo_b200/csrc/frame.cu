@@ -380,7 +380,7 @@ static void stereo_enqueue(uvo_stereo* s, const uint8_t* dL, const uint8_t* dR, 
   bool jpeg_on_gpu = false;
   if (src_mode == SRC_HOST_JPEG_GPU) {
     // compressed frames, Huffman decoding on the GPU: the scan bytes and the table plan go up on the copy stream
-    // (one copy per image), then k_jpeg_huff (both images in one cooperative launch) + IDCT + colour on the lane
+    // (one copy per image), then k_jpeg_huff (both images in one launch) + IDCT + colour on an ingest stream
     UVO_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_in, 0));
     uint8_t* d_buf[2];
     uint8_t* d_planes[2];

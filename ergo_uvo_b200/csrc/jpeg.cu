@@ -774,7 +774,8 @@ __device__ __forceinline__ void jh_block_scan(int (&v)[K], int (*s_w)[K], int (&
   __syncthreads();
 }
 
-// Cooperative kernel (grid-wide barriers): grid = (blocks per image, images), JH_BLOCK threads each, one thread per
+// Kernel with grid-wide barriers (jh_soft_sync, or cooperative_groups under UVO_JPEG_COOPERATIVE=1): grid = (blocks
+// per image, images), JH_BLOCK threads each, one thread per
 // sub-sequence of JH_SUB_BITS bits.  Phases: synchronisation rounds; count; per-image scan of the counts; write;
 // DC partial sums; per-image scan of those; DC prediction + block table in plane order.
 __device__ __forceinline__ unsigned long long jh_now() {
@@ -1148,7 +1149,7 @@ bool jpeg_gpu_prepare(const uint8_t* jpeg, size_t len, uint8_t* pinned, size_t p
 struct GpuLayout {  // offsets inside the device buffer of one image
   size_t first, entries, count, first_scan, info, exits, counts, dc_part, total;
 };
-static int jh_blocks(size_t scan_bytes) {  // blocks of the cooperative launch an image of this scan length needs
+static int jh_blocks(size_t scan_bytes) {  // blocks of the decoder launch an image of this scan length needs
   const size_t n_sub = (scan_bytes * 8 + JH_SUB_BITS - 1) / JH_SUB_BITS;
   return (int)std::max<size_t>((n_sub + JH_BLOCK - 1) / JH_BLOCK, 1);
 }

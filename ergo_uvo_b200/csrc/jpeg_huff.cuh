@@ -8,7 +8,7 @@
 // rounds reach the fixed point, which is the sequential decode.  Two more passes count and then write the
 // coefficients in the sparse form k_jpeg_idct takes; the DC predictions are prefix sums per component.
 //
-// One cooperative launch per image pair: one thread per sub-sequence of 1024 bits, blocks of 64 threads spread over
+// One launch per image pair (grid-wide barriers between the phases): one thread per sub-sequence of 1024 bits, blocks of 64 threads spread over
 // the SMs, grid-wide barriers between the rounds and the passes (a first version ran one 1024-thread block per image:
 // correct, but 1.5 ms per 1280x1024 frame -- 32 warps of divergent table walks issue-bound on one SM).
 // Supported here: one interleaved scan (every component in it), no restart interval -- what cv::imencode and the
@@ -20,7 +20,7 @@ namespace uvo {
 
 constexpr int JH_FAST_BITS = 10;  // look-up bits (the host tables are built for 10)
 #include <cuda_runtime.h>
-constexpr int JH_BLOCK = 64;         // threads per block of the cooperative launch
+constexpr int JH_BLOCK = 64;         // threads per block of the decoder launch
 constexpr int JH_SUB_BITS = 1024;    // bits per sub-sequence (= per thread): a decoder started in a wrong state needs a
                                      // few hundred bits to fall into step (median 450 at q75, never more than 6.4 kbit)
 constexpr int JH_MAX_ROUNDS = 64;    // more rounds than that without a fixed point: reported as a corrupt stream
