@@ -59,3 +59,33 @@ def test_reference_arm_runs_only_on_rank0():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_workload():
+    """the `config` object is built by one function for the GPU arm and the reference arm (the driver compares them),
+    names the workload of BASELINE.json's configs and says how L2 is taken out of the measurement"""
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, cfg in bench.CONFIGS.items():
+        a = bench.config_dict(cfg, name, 11032)
+        b = bench.config_dict(dict(cfg), name, 11032)
+        assert a == b and a["name"] == name and a["width"] == cfg["w"] and a["height"] == cfg["h"]
+        assert "larger than L2" in a["l2"] and str(cfg["ring"]) in a["l2"]
+        assert 2 * 3 * cfg["w"] * cfg["h"] * cfg["ring"] > 126e6  # the ring of inputs does exceed the 126 MB L2
+    assert "1280x1024" in bench.CONFIGS["B"]["workload"] and "2448x2048" in bench.CONFIGS["E"]["workload"]
+
+
+def test_numa_binding_is_best_effort():
+    """multi-GPU runs bind a rank to its GPU's NUMA node when sysfs shows one; anything unreadable means 'leave the
+    affinity alone', never an error"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class NoTopology:
+        class cuda:
+            @staticmethod
+            def get_device_properties(i):
+                raise RuntimeError("no device")
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_numa_node(NoTopology, 0) is None
+    assert os.sched_getaffinity(0) == before
