@@ -322,6 +322,8 @@ struct Parser {
       for (int q = 0; q < L.components; q++)
         if (comp[q].id == s[1 + 2 * j]) c = q;
       if (c < 0) throw InvalidArg{"jpeg: SOS names an unknown component", UVO_ERR_INVALID};
+      for (int k = 0; k < j; k++)  // libjpeg-turbo: JERR_BAD_COMPONENT_ID
+        if (idx[k] == c) throw InvalidArg{"jpeg: SOS names a component twice", UVO_ERR_INVALID};
       comp[c].td = s[2 + 2 * j] >> 4;
       comp[c].ta = s[2 + 2 * j] & 15;
       if (comp[c].td > 3 || comp[c].ta > 3 || !dc[comp[c].td].present || !ac[comp[c].ta].present ||
@@ -510,6 +512,9 @@ bool build_gpu_plan(const uint8_t* d, size_t len, JhPlan* plan, uint8_t* scan_ou
     for (int q = 0; q < L.components; q++)
       if (P.comp[q].id == P.sos[1 + 2 * j]) c = q;
     if (c < 0) throw InvalidArg{"jpeg: SOS names an unknown component", UVO_ERR_INVALID};
+    // every component exactly once: a component named twice would leave another one's block table unwritten
+    for (int k = 0; k < j; k++)
+      if (order[k] == c) throw InvalidArg{"jpeg: SOS names a component twice", UVO_ERR_INVALID};
     const int td = P.sos[2 + 2 * j] >> 4, ta = P.sos[2 + 2 * j] & 15;
     if (td > 3 || ta > 3 || !P.dc[td].present || !P.ac[ta].present || !P.qt_present[P.comp[c].tq])
       throw InvalidArg{"jpeg: scan refers to a table that was not defined", UVO_ERR_INVALID};

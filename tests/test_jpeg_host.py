@@ -92,6 +92,24 @@ def test_entropy_decode_refusals():
         U.jpeg_info(data[:100])  # cut inside the tables: no frame header
 
 
+def test_scan_header_naming_a_component_twice_is_refused():
+    """libjpeg-turbo rejects a scan whose header names a component twice (JERR_BAD_COMPONENT_ID; cv::imdecode returns
+    an empty Mat); here the GPU route would leave the other component's block table unwritten, so both routes refuse"""
+    import ergo_uvo_b200 as U
+    z = np.load(os.path.join(GOLD, "jpeg_64x48.npz"))
+    data = bytearray(z["c444_opt_jpg"].tobytes())
+    p = data.index(b"\xff\xda")
+    assert data[p + 4] == 3                      # Ns: three components in the scan
+    ids = [data[p + 5 + 2 * j] for j in range(3)]
+    assert len(set(ids)) == 3
+    data[p + 5 + 2] = ids[0]                     # the second entry now repeats the first component
+    with pytest.raises(U.UvoError) as e:
+        U.jpeg_entropy_decode(bytes(data))
+    assert e.value.code == -3
+    if cv2 is not None:
+        assert cv2.imdecode(np.frombuffer(bytes(data), np.uint8), cv2.IMREAD_UNCHANGED) is None
+
+
 @pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
 def test_parser_survives_mutated_streams():
     """the streams come off the network (ROS CompressedImage): byte edits, truncations and insertions must end in a
