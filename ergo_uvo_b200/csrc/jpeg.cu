@@ -873,10 +873,12 @@ __global__ void __launch_bounds__(JH_BLOCK) k_jpeg_huff(const __grid_constant__ 
       im.first[b] = 0;
       im.count[b] = 0;
     }
-    if (aborted && gi == 0) {
-      im.info[0] = 0;
+    if (aborted && tid == 0) {  // every block that gives up says so: the launch is reported as a corrupt image
       im.info[1] = 1;
-      im.info[2] = JH_MAX_ROUNDS + 1;
+      if (gi == 0) {
+        im.info[0] = 0;
+        im.info[2] = JH_MAX_ROUNDS + 1;
+      }
     }
   };
 #define JH_GRID_SYNC()  \
