@@ -1468,6 +1468,22 @@ int uvo_jpeg_gpu_entropy_stamps(uvo_ctx* ctx, int64_t stamps[24], int* count) {
   return UVO_OK;
 }
 
+size_t uvo_jpeg_gpu_staging_bytes(size_t len) { return jpeg_gpu_host_bytes(len); }
+
+int uvo_jpeg_gpu_plan(const uint8_t* jpeg, size_t len, uint8_t* staging, size_t staging_bytes, int* qualifies,
+                      size_t* upload_bytes, uint32_t* scan_bits, uvo_jpeg_layout* layout) {
+  if (!staging || !qualifies) return UVO_ERR_INVALID;
+  *qualifies = 0;
+  return guarded(nullptr, [&] {
+    JpegGpuJob job{};
+    if (!jpeg_gpu_prepare(jpeg, len, staging, staging_bytes, &job)) return;
+    *qualifies = 1;
+    if (upload_bytes) *upload_bytes = job.upload_bytes;
+    if (scan_bits) *scan_bits = ((const JhPlan*)staging)->total_bits;
+    if (layout) *layout = job.L;
+  });
+}
+
 int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,
                            size_t out_pitch, size_t out_capacity, int* width, int* height, int* channels) {
   if (!ctx) return UVO_ERR_INVALID;

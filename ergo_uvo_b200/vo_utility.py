@@ -106,6 +106,23 @@ def jpeg_entropy_decode_sparse(data):
     return lay, entries[:n.value].copy(), first, count
 
 
+def jpeg_gpu_plan(data):
+    """uvo_jpeg_gpu_plan (host-only): the host half of the GPU Huffman route.  Returns None when the stream takes the
+    host decoder, else (layout, scan bits, upload bytes, staging bytes as a numpy array: [table plan][unstuffed scan])."""
+    lib = L.load()
+    lib.uvo_jpeg_gpu_staging_bytes.restype = C.c_size_t
+    buf = np.frombuffer(bytes(data), np.uint8)
+    staging = np.zeros(int(lib.uvo_jpeg_gpu_staging_bytes(C.c_size_t(len(buf)))), np.uint8)
+    ok, up, bits, lay = C.c_int(0), C.c_size_t(0), C.c_uint32(0), L.JpegLayout()
+    rc = lib.uvo_jpeg_gpu_plan(_p(buf), C.c_size_t(len(buf)), _p(staging), C.c_size_t(len(staging)), C.byref(ok),
+                               C.byref(up), C.byref(bits), C.byref(lay))
+    if rc != L.UVO_OK:
+        raise L.UvoError(rc, "uvo_jpeg_gpu_plan: corrupt or unsupported JPEG stream")
+    if not ok.value:
+        return None
+    return lay, int(bits.value), int(up.value), staging
+
+
 class SparseImage:
     """A compressed image after the host half of the decode (uvo_jpeg_entropy_decode_sparse), in buffers that stay
     alive with the object -- pinned host memory when `pinned` (uvo_host_alloc), so that the upload inside

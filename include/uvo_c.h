@@ -214,6 +214,13 @@ UVO_API int uvo_jpeg_gpu_entropy(uvo_ctx* ctx, int enable, int* last_route, int*
 /* diagnostics: nanosecond time stamps (%globaltimer) of the phases of the previous GPU entropy decode -- start, after
  * rounds 1 and 2, after the last round, count, scan, write, DC partial sums ..., end (tools/jh_time.py) */
 UVO_API int uvo_jpeg_gpu_entropy_stamps(uvo_ctx* ctx, int64_t stamps[24], int* count);
+/* host-only (no GPU needed; tests and the fuzzer): the HOST half of that route -- marker walk, table plan, copy of the
+ * scan with the stuffed zeros removed -- run into caller memory.  staging holds uvo_jpeg_gpu_staging_bytes(len) bytes.
+ * *qualifies = 1: the stream takes the GPU decoder, *upload_bytes of staging would go to the device and the scan is
+ * *scan_bits long; 0: it takes the host decoder.  Malformed streams return an error like uvo_jpeg_info. */
+UVO_API size_t uvo_jpeg_gpu_staging_bytes(size_t len);
+UVO_API int uvo_jpeg_gpu_plan(const uint8_t* jpeg, size_t len, uint8_t* staging, size_t staging_bytes, int* qualifies,
+                              size_t* upload_bytes, uint32_t* scan_bits, uvo_jpeg_layout* layout);
 /* the same with the image left in DEVICE memory (no copy back; the work is ordered on the context stream), ready for
  * uvo_stereo_enqueue_device / uvo_mono_frame_device on the same context */
 UVO_API int uvo_jpeg_decode_device(uvo_ctx* ctx, const uint8_t* jpeg, size_t len, int bayer_bggr, uint8_t* out_dev,

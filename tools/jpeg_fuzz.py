@@ -1,5 +1,5 @@
 """Mutation fuzzer for the host half of the JPEG decode (uvo_jpeg_info, uvo_jpeg_entropy_decode,
-uvo_jpeg_entropy_decode_sparse): valid streams (all sub-samplings, with and without restart intervals, grayscale) with
+uvo_jpeg_entropy_decode_sparse, and uvo_jpeg_gpu_plan -- the host half of the GPU Huffman route): valid streams (all sub-samplings, with and without restart intervals, grayscale) with
 random byte edits, truncations, header edits and insertions; every call must return a status code, and the sparse
 tables must stay inside their bounds.  The streams arrive from the network (ROS CompressedImage messages), so the parser
 must not trust them.
@@ -15,6 +15,7 @@ import ergo_uvo_b200 as U
 from ergo_uvo_b200 import _lib as L
 from conftest import noise_image
 lib=L.load()
+lib.uvo_jpeg_gpu_staging_bytes.restype=C.c_size_t
 rs=np.random.RandomState(int(sys.argv[1]) if len(sys.argv)>1 else 0)
 img=noise_image(67,93,seed=1,channels=3)
 seeds=[]
@@ -39,6 +40,15 @@ for it in range(N):
     lay=L.JpegLayout()
     rc=lib.uvo_jpeg_info(buf.ctypes.data_as(C.c_void_p),C.c_size_t(len(buf)),C.byref(lay))
     codes[("info",rc)]=codes.get(("info",rc),0)+1
+    # the host half of the GPU Huffman route (marker walk, table plan, unstuffed scan copy) on the same bytes: the
+    # staging buffer is allocated at exactly the size the library asks for, so an overrun is the sanitizer's to find
+    stg=np.empty(int(lib.uvo_jpeg_gpu_staging_bytes(C.c_size_t(len(buf)))),np.uint8)
+    q=C.c_int(0); up=C.c_size_t(0); bits=C.c_uint32(0); lay2=L.JpegLayout()
+    rc2=lib.uvo_jpeg_gpu_plan(buf.ctypes.data_as(C.c_void_p),C.c_size_t(len(buf)),stg.ctypes.data_as(C.c_void_p),C.c_size_t(len(stg)),C.byref(q),C.byref(up),C.byref(bits),C.byref(lay2))
+    codes[("plan",rc2,q.value)]=codes.get(("plan",rc2,q.value),0)+1
+    if rc2==0 and q.value:
+        assert up.value<=len(stg) and (bits.value+7)//8+16<=up.value and rc==0 and lay2.coeff_total==lay.coeff_total
+    if rc2==0: assert rc==0   # what the GPU route accepts, the host parser accepts
     if rc==0:
         tot=int(lay.coeff_total)
         if tot<=0 or tot>64*1000000: 
