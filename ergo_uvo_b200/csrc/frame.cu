@@ -780,6 +780,9 @@ int uvo_stereo_enqueue_host_jpeg(uvo_stereo* s, const uint8_t* left_jpeg, size_t
       uvo_jpeg_layout L;
       const int e = uvo_jpeg_info(src[i], len[i], &L);
       if (e != UVO_OK) throw InvalidArg{"uvo_stereo_enqueue_host_jpeg: not a decodable baseline JPEG stream", e};
+      // before anything is sized from the header: a stream of another size is refused, it does not get a buffer
+      UVO_REQUIRE(L.width == s->w && L.height == s->h,
+                  "compressed image size differs from the handle's (the reference would resize: use uvo_get_image_resized)");
       const size_t nb = (size_t)L.coeff_total / 64;
       s->jpeg_host[slot][i].ensure(nb + (size_t)L.coeff_total + (nb + 3) / 4);
     }
